@@ -1,0 +1,147 @@
+/*
+ * b200_turbomind.h -- C ABI of the B200-native TurboMind decode hot path (libb200tm.so).
+ *
+ * Every entry point below replaces one reference interface on the decode path of
+ * InternLM/lmdeploy 0.16.0 (paths relative to the reference root).  The reference has no extern "C"
+ * surface (its FFI is the pybind11 module `_turbomind`, src/turbomind/python/bind.cpp:423-1004);
+ * these are the plain-pointer equivalents of the *inner* operator boundary its own layers call
+ * (SURVEY.md section 8b), plus an engine-level handle API that stands where
+ * LanguageModel::Run / ModelRequest::Forward sit.  INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions: all pointers are DEVICE pointers unless a name ends in `_host`; `stream` is a
+ * cudaStream_t passed as void*; calls are asynchronous on that stream; every function returns 0 on
+ * success or a negative b200_status / positive cudaError_t on failure (b200_last_error() gives text).
+ * No torch types, no C++ types.  dtype: 0 = fp16, 1 = bf16.
+ */
+#ifndef B200_TURBOMIND_H
+#define B200_TURBOMIND_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define B200_API __attribute__((visibility("default")))
+#else
+#define B200_API
+#endif
+
+#define B200_DTYPE_F16 0
+#define B200_DTYPE_BF16 1
+
+typedef enum {
+    B200_OK              = 0,
+    B200_ERR_INVALID_ARG = -1,
+    B200_ERR_UNSUPPORTED = -2, /* shape / feature outside the hot-path scope (head_dim != 128, ...) */
+    B200_ERR_WORKSPACE   = -3,
+    B200_ERR_STATE       = -4
+} b200_status;
+
+/* Text of the last error raised on the calling thread ("" if none). */
+B200_API const char* b200_last_error(void);
+/* "b200tm <version> sm_100a" */
+B200_API const char* b200_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * RoPE parameters.  Replaces core::RopeConfig -> RopeKernelParam
+ * (src/turbomind/models/attention_weight.h:15-35, attention_weight.cc:37-93,
+ *  src/turbomind/models/llama/llama_rope.h:9-62).  type: 0 null, 1 default, 2 linear, 3 dynamic(unsupported),
+ *  4 yarn, 5 llama3.  Derived kernel constants are computed inside the library exactly as
+ *  init_rope_kernel_param does.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int   type;
+    int   dim;
+    float base;
+    float factor;
+    int   max_position_embeddings;
+    float llama3_low_freq_factor;
+    float llama3_high_freq_factor;
+    int   llama3_original_max_position_embeddings;
+    float yarn_attention_factor;
+    float yarn_beta_fast;
+    float yarn_beta_slow;
+} b200_rope_config;
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode attention.  Replaces
+ *   template<class T> void dispatchDecoding(const AttentionParams<T>&)
+ *     (src/turbomind/kernels/attention/decoding.h:9-10, decoding.cu:13-39)
+ * with the argument block AttentionParams<T> (attention_params.h:31-103) and BlockIteratorParams
+ * (attention_params.h:20-25) flattened to C.  Field meaning is the reference's:
+ *   q/k/v: the new token's fused QKV row per sequence, token-major, row stride `stride` elements;
+ *   cu_q_len / cu_k_len: [batch+1] prefix sums (decode: q_len == 1, k_len includes the new token);
+ *   block_ptrs[cu_block_nums[b] + i]: base pointer of the i-th KV block of sequence b (all layers in
+ *   one block, KV page format of kernels/attention/block.h:124-219); layer_offset: byte offset of this
+ *   layer inside a block (unified_attention_layer.cc:163-171); quant_policy 0 / 4 / 8.
+ * The call (1) adds bias, applies RoPE to q and k, quantises k/v and stores them into the page at
+ * position history_len (unless inside the read-only prefix), (2) runs split-KV flash decoding over the
+ * paged cache, (3) merges split partials.  Unsupported reference features return B200_ERR_UNSUPPORTED:
+ * window_size, attention sinks, log-n scaling, context parallel, head_dim != 128, q_len > 1.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    void*       out;
+    const void* q;
+    const void* k;
+    const void* v;
+    int64_t     stride;
+    const void* q_bias;
+    const void* k_bias;
+    const void* v_bias;
+
+    const int*     cu_q_len;
+    const int*     cu_k_len;
+    const int*     readonly_block_num; /* may be NULL */
+    const uint8_t* finished;           /* may be NULL; bool per sequence */
+
+    void**     block_ptrs;
+    const int* cu_block_nums;
+    int        layer_offset;
+    int        block_len;
+
+    int token_num;
+    int batch_size;
+    int max_k_len;
+
+    int   num_heads;
+    int   num_kv_heads;
+    int   size_per_head;
+    float inv_sqrt_dh; /* log2(e) * softmax_scale, as unified_attention_layer.cc:541-548 */
+    int   window_size; /* must be 0 */
+
+    b200_rope_config rope;
+    int              quant_policy;
+    int              dtype;
+
+    /* workspace: b200_decode_attention_workspace_bytes() bytes, 256-byte aligned.  Stands where
+     * split_cnt / partial_O / partial_ML (unified_attention_layer.cc:220-224) stand in the reference. */
+    void*  workspace;
+    size_t workspace_bytes;
+
+    /* optional: a plan computed once per step by b200_decode_attention_plan (valid for every layer of
+     * the step); if NULL the call plans internally. */
+    const int* plan;
+
+    void* stream;
+} b200_attention_params;
+
+B200_API size_t b200_decode_attention_workspace_bytes(int batch_size, int num_heads, int num_kv_heads);
+/* plan buffer: (batch_size + 1) ints, device memory */
+B200_API int b200_decode_attention_plan(int* plan, const int* cu_k_len, const uint8_t* finished, int batch_size, void* stream);
+B200_API int b200_decode_attention(const b200_attention_params* params);
+
+/* Prefill-side KV writer.  Replaces invokeProcessKV_v2 (kernels/attention/kv_cache_utils_v2.cu:18-210):
+ * bias + RoPE on K, quantise K/V, store token positions [history_len, history_len + q_len) of every
+ * sequence into the paged cache.  Same argument block; `q`, `out` are ignored. */
+B200_API int b200_process_kv(const b200_attention_params* params);
+
+/* Number of CTAs the attention kernel launches on the current device (for tests / profiling). */
+B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_TURBOMIND_H */

@@ -1,0 +1,72 @@
+"""ctypes binding of libb200tm.so.  The product path has NO fallback: if the CUDA library is missing
+or cannot be loaded this raises immediately."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200tm.so")
+
+
+class B200LibraryError(RuntimeError):
+    pass
+
+
+class RopeConfig(C.Structure):
+    _fields_ = [
+        ("type", C.c_int), ("dim", C.c_int), ("base", C.c_float), ("factor", C.c_float),
+        ("max_position_embeddings", C.c_int),
+        ("llama3_low_freq_factor", C.c_float), ("llama3_high_freq_factor", C.c_float),
+        ("llama3_original_max_position_embeddings", C.c_int),
+        ("yarn_attention_factor", C.c_float), ("yarn_beta_fast", C.c_float), ("yarn_beta_slow", C.c_float),
+    ]
+
+
+class AttentionParams(C.Structure):
+    _fields_ = [
+        ("out", C.c_void_p), ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("stride", C.c_int64),
+        ("q_bias", C.c_void_p), ("k_bias", C.c_void_p), ("v_bias", C.c_void_p),
+        ("cu_q_len", C.c_void_p), ("cu_k_len", C.c_void_p), ("readonly_block_num", C.c_void_p),
+        ("finished", C.c_void_p),
+        ("block_ptrs", C.c_void_p), ("cu_block_nums", C.c_void_p), ("layer_offset", C.c_int),
+        ("block_len", C.c_int),
+        ("token_num", C.c_int), ("batch_size", C.c_int), ("max_k_len", C.c_int),
+        ("num_heads", C.c_int), ("num_kv_heads", C.c_int), ("size_per_head", C.c_int),
+        ("inv_sqrt_dh", C.c_float), ("window_size", C.c_int),
+        ("rope", RopeConfig), ("quant_policy", C.c_int), ("dtype", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("plan", C.c_void_p),
+        ("stream", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200LibraryError(
+            f"{LIB_PATH} not found: build it with `python -m lmdeploy_b200.build` "
+            "(lmdeploy_b200 has no CPU or PyTorch fallback)")
+    try:
+        lib = C.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise B200LibraryError(f"cannot load {LIB_PATH}: {e}") from e
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_version.restype = C.c_char_p
+    lib.b200_decode_attention_workspace_bytes.restype = C.c_size_t
+    lib.b200_decode_attention_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.b200_decode_attention_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200_decode_attention.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_process_kv.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_decode_attention_grid.argtypes = [C.c_int, C.c_int]
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().b200_last_error().decode()
+        raise B200LibraryError(f"{what} failed (code {rc}): {msg}")
