@@ -141,6 +141,45 @@ B200_API int b200_process_kv(const b200_attention_params* params);
 /* Number of CTAs the attention kernel launches on the current device (for tests / profiling). */
 B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
 
+/* ------------------------------------------------------------------------------------------------
+ * Weight-only-quant linear layer.  Replaces
+ *   LinearWeight (models/linear_weight.h:42-112) + LinearWeight::prepare (models/linear_weight.cc:101-324)
+ *   LlamaLinear::Forward (models/llama/LlamaLinear.cu:226-273) -> gemm::Gemm::Run (kernels/gemm/gemm.h:23-41)
+ * weight_format: 0 dense T [K,N]; 1 u4 AWQ (TurboMind pre-prepare layout: qweight int32 [K, N/8] with nibble i of
+ *   word w = column 8w+i -- what lmdeploy/turbomind/weight_format.py:63-74 pack_u4_row produces -- plus
+ *   scales T [K/g, N] and integer-valued zeros T [K/g, N], g = 128).
+ * D[m, N] = x[m, K] . dequant(W) (+ bias); dequant is w = fma_T(q, s, -(z*s)_T) exactly as
+ * kernels/gemm/transform.h:48-74 / cast.cu:155; accumulation fp32 on tcgen05 tensor cores.
+ * epilogue: 0 none; 1 gated SiLU over element-interleaved (gate, up) columns -> [m, N/2]
+ *   (kernels/gemm/epilogue.h:158-177).
+ * `prepared` is library-owned layout (b200_linear_prepared_bytes bytes); `bias` may be NULL.
+ * Workspace must be zero-filled ONCE before its first use (split-K arrival counters live in it; the
+ * kernels leave them zero).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int         input_dim;     /* K */
+    int         output_dim;    /* N */
+    int         weight_format; /* 0 dense, 1 u4 */
+    int         dtype;         /* activation / scale type T */
+    int         group_size;    /* 128 for u4 */
+    const void* prepared;      /* output of b200_linear_prepare */
+    const void* bias;          /* [N] T or NULL */
+} b200_linear_desc;
+
+B200_API size_t b200_linear_prepared_bytes(const b200_linear_desc* desc);
+B200_API int b200_linear_prepare(const b200_linear_desc* desc, const void* weight, const void* scales, const void* zeros,
+                        int weight_is_transposed, void* prepared, void* stream);
+B200_API size_t b200_linear_workspace_bytes(const b200_linear_desc* desc, int max_tokens);
+/* x: [m, K] row-major (row stride ldx elements), y: [m, N or N/2] row-major (row stride ldy), 1 <= m <= 128 */
+B200_API int b200_linear_forward(const b200_linear_desc* desc, const void* x, int64_t ldx, int m, void* y, int64_t ldy,
+                        int epilogue, void* workspace, size_t workspace_bytes, void* stream);
+/* Activations already in the UMMA K-major tile layout [K/8][mt][8] (mt = padded tokens, multiple of 16);
+ * out_packed_mt > 0 writes the output in the same packed layout (feeds the next GEMM without a repack). */
+B200_API int b200_linear_forward_packed(const b200_linear_desc* desc, const void* xp, int mt, int m, void* y, int64_t ldy,
+                               int epilogue, int out_packed_mt, void* workspace, size_t workspace_bytes,
+                               void* stream);
+B200_API int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,13 @@ class AttentionParams(C.Structure):
     ]
 
 
+class LinearDesc(C.Structure):
+    _fields_ = [
+        ("input_dim", C.c_int), ("output_dim", C.c_int), ("weight_format", C.c_int), ("dtype", C.c_int),
+        ("group_size", C.c_int), ("prepared", C.c_void_p), ("bias", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -62,6 +69,18 @@ def load():
     lib.b200_decode_attention.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_process_kv.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_decode_attention_grid.argtypes = [C.c_int, C.c_int]
+    lib.b200_linear_prepared_bytes.restype = C.c_size_t
+    lib.b200_linear_prepared_bytes.argtypes = [C.POINTER(LinearDesc)]
+    lib.b200_linear_prepare.argtypes = [C.POINTER(LinearDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_void_p]
+    lib.b200_linear_workspace_bytes.restype = C.c_size_t
+    lib.b200_linear_workspace_bytes.argtypes = [C.POINTER(LinearDesc), C.c_int]
+    lib.b200_linear_forward.argtypes = [C.POINTER(LinearDesc), C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+                                        C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200_linear_forward_packed.argtypes = [C.POINTER(LinearDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                               C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200_pack_activations.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]
     _lib = lib
     return lib
 

@@ -1,0 +1,326 @@
+// Host side of the weight-only-quant linear layer: weight re-pack ("prepare"), activation packing and the
+// launchers behind b200_linear_*.  See gemm.cuh for the kernel design.
+#include "../../include/b200_turbomind.h"
+#include "gemm.cuh"
+#include "host_utils.h"
+
+#include <algorithm>
+
+namespace b200 {
+namespace gemm {
+
+// ------------------------------------------------------------------------------------------------
+// prepare: loader-visible tensors -> tile stream consumed by gemm_kernel
+//   u4 input (pre-prepare format, SURVEY 8a11 / lmdeploy/turbomind/weight_format.py:63-74):
+//     qweight int32 [K, N/8], nibble i of word w = column 8w+i;  scales, zeros T [K/128, N]
+//   output per (n-tile nt, k-group kg):  data [c:2][hh:2][n:128][16 B] then params [n:128]{s, t=-z*s}
+//   the 32 nibbles of a 16-byte unit are k = kg*128 + c*64 + hh*32 + (0..31); inside each u32 the nibble
+//   at position j holds k-offset [0,2,4,6,1,3,5,7][j] so that lop3 unpacking yields (k, k+1) pairs.
+// ------------------------------------------------------------------------------------------------
+template<class T>
+__global__ void prepare_u4_kernel(uint8_t* dst, const uint32_t* qweight, const T* scales, const T* zeros, int K, int N)
+{
+    using Ops       = TypeOps<T>;
+    const int kgs   = K / kKG;
+    const int nts   = N / kBN;
+    const size_t nw = (size_t)nts * kgs * (kU4BlockBytes / 4);  // u32 words incl. params
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nw; idx += (size_t)gridDim.x * blockDim.x) {
+        const int    within = (int)(idx % (kU4BlockBytes / 4));
+        const size_t blk    = idx / (kU4BlockBytes / 4);
+        const int    kg     = (int)(blk % kgs);
+        const int    nt     = (int)(blk / kgs);
+        uint32_t     out;
+        if (within < 2048) {
+            const int u  = within & 3;
+            const int n  = (within >> 2) & 127;
+            const int hh = (within >> 9) & 1;
+            const int c  = within >> 10;
+            const int k0 = kg * kKG + c * 64 + hh * 32 + u * 8;
+            const int ng = nt * kBN + n;
+            out          = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int      ko = (j < 4) ? 2 * j : 2 * (j - 4) + 1;  // [0,2,4,6,1,3,5,7]
+                const uint32_t w  = qweight[(size_t)(k0 + ko) * (N / 8) + (ng >> 3)];
+                out |= ((w >> (4 * (ng & 7))) & 0xF) << (4 * j);
+            }
+        }
+        else {
+            const int n  = within - 2048;
+            const int ng = nt * kBN + n;
+            const T   s  = scales[(size_t)kg * N + ng];
+            const T   z  = zeros ? zeros[(size_t)kg * N + ng] : Ops::from_f32(0.f);
+            // fuse_scales_and_zeros (cast.cu:134-165): t = -z * s evaluated in T
+            const T t = Ops::mul(Ops::from_f32(-Ops::to_f32(z)), s);
+            T       pr[2] = {s, t};
+            out           = *reinterpret_cast<uint32_t*>(&pr[0]);
+        }
+        reinterpret_cast<uint32_t*>(dst)[idx] = out;
+    }
+}
+
+// dense: W [K, N] row-major (trans == 0) or [N, K] row-major (trans == 1) -> per (nt, kg): [k8:16][n:128][8] T
+template<class T>
+__global__ void prepare_dense_kernel(T* dst, const T* w, int K, int N, int trans)
+{
+    const int    kgs = K / kKG;
+    const size_t ne  = (size_t)K * N;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < ne; idx += (size_t)gridDim.x * blockDim.x) {
+        const int    e   = (int)(idx & 7);
+        const int    n   = (int)((idx >> 3) & 127);
+        const int    k8  = (int)((idx >> 10) & 15);
+        const size_t blk = idx >> 14;
+        const int    kg  = (int)(blk % kgs);
+        const int    nt  = (int)(blk / kgs);
+        const int    k   = kg * kKG + k8 * 8 + e;
+        const int    ng  = nt * kBN + n;
+        dst[idx]         = trans ? w[(size_t)ng * K + k] : w[(size_t)k * N + ng];
+    }
+}
+
+// activations: X [M][ldx] row-major -> XP [K/8][MT][8]; rows >= M are zero
+template<class T>
+__global__ void pack_x_kernel(T* xp, const T* x, int M, int MT, int K, int64_t ldx)
+{
+    const size_t n16 = (size_t)(K / 8) * MT;  // 16-byte units
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < n16; idx += (size_t)gridDim.x * blockDim.x) {
+        const int tok = (int)(idx % MT);
+        const int k8  = (int)(idx / MT);
+        uint4     v   = make_uint4(0, 0, 0, 0);
+        if (tok < M) {
+            v = *reinterpret_cast<const uint4*>(x + (size_t)tok * ldx + (size_t)k8 * 8);
+        }
+        reinterpret_cast<uint4*>(xp)[idx] = v;
+    }
+}
+
+static int pick_splits(int N, int K)
+{
+    const int nts = N / kBN, kgs = K / kKG;
+    int       s   = (148 + nts / 2) / nts;
+    s             = std::max(1, std::min(s, std::min(kgs, 8)));
+    return s;
+}
+
+static int pick_stages(int fmt, int MT)
+{
+    const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    const int WB_pad = (WB + 1023) & ~1023;
+    const int stage  = WB_pad + MT * 256;
+    int       st     = std::min(kMaxStages, (220 * 1024) / stage);
+    return std::max(2, st);
+}
+
+struct LinearWs {
+    void*  xp;
+    float* partials;
+    int*   counters;
+    size_t total;
+};
+
+static size_t align_up(size_t x, size_t a)
+{
+    return (x + a - 1) / a * a;
+}
+
+static LinearWs carve_ws(void* base, int K, int N, int MT)
+{
+    LinearWs w{};
+    size_t   off  = 0;
+    auto     take = [&](size_t bytes) {
+        void* p = base ? (char*)base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    w.counters = (int*)take((size_t)(N / kBN) * 4 + 256);
+    w.xp       = take((size_t)K * MT * 2);
+    w.partials = (float*)take((size_t)(N / kBN) * 8 * MT * kBN * 4);
+    w.total    = off;
+    return w;
+}
+
+template<class T, int FMT>
+static int launch(const Params& p, cudaStream_t st)
+{
+    const int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    const int WB_pad = (WB + 1023) & ~1023;
+    const int smem   = p.stages * (WB_pad + p.MT * 256);
+    auto      kern   = gemm_kernel<T, FMT>;
+    static int configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+        if (e != cudaSuccess) {
+            return fail_cuda(e, "cudaFuncSetAttribute(gemm_kernel)");
+        }
+        configured = 227 * 1024;
+    }
+    dim3 grid(p.N / kBN, p.splits);
+    kern<<<grid, kThreads, smem, st>>>(p);
+    return check_launch("gemm_kernel");
+}
+
+}  // namespace gemm
+}  // namespace b200
+
+using namespace b200;
+using namespace b200::gemm;
+
+static int validate_desc(const b200_linear_desc* d)
+{
+    if (!d) {
+        return fail(B200_ERR_INVALID_ARG, "linear desc is NULL");
+    }
+    if (d->input_dim <= 0 || d->input_dim % kKG) {
+        return fail(B200_ERR_UNSUPPORTED, "input_dim must be a multiple of 128");
+    }
+    if (d->output_dim <= 0 || d->output_dim % kBN) {
+        return fail(B200_ERR_UNSUPPORTED, "output_dim must be a multiple of 128");
+    }
+    if (d->weight_format == kU4 && d->group_size != 128) {
+        return fail(B200_ERR_UNSUPPORTED, "u4 weights require group_size 128");
+    }
+    if (d->weight_format != kU4 && d->weight_format != kDense) {
+        return fail(B200_ERR_UNSUPPORTED, "weight_format must be 0 (dense) or 1 (u4 awq)");
+    }
+    if (d->dtype != B200_DTYPE_F16 && d->dtype != B200_DTYPE_BF16) {
+        return fail(B200_ERR_INVALID_ARG, "dtype must be 0 or 1");
+    }
+    return 0;
+}
+
+extern "C" size_t b200_linear_prepared_bytes(const b200_linear_desc* d)
+{
+    if (validate_desc(d)) {
+        return 0;
+    }
+    const size_t blocks = (size_t)(d->output_dim / kBN) * (d->input_dim / kKG);
+    return blocks * (d->weight_format == kU4 ? kU4BlockBytes : kDenseBlockBytes);
+}
+
+extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight, const void* scales, const void* zeros,
+                                   int weight_is_transposed, void* prepared, void* stream)
+{
+    if (int e = validate_desc(d)) {
+        return e;
+    }
+    if (!weight || !prepared) {
+        return fail(B200_ERR_INVALID_ARG, "weight / prepared is NULL");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int    K = d->input_dim, N = d->output_dim;
+    if (d->weight_format == kU4) {
+        if (!scales) {
+            return fail(B200_ERR_INVALID_ARG, "u4 weights need scales");
+        }
+        if (d->dtype == B200_DTYPE_F16) {
+            prepare_u4_kernel<half><<<1024, 256, 0, st>>>((uint8_t*)prepared, (const uint32_t*)weight,
+                                                          (const half*)scales, (const half*)zeros, K, N);
+        }
+        else {
+            prepare_u4_kernel<nv_bfloat16><<<1024, 256, 0, st>>>((uint8_t*)prepared, (const uint32_t*)weight,
+                                                                 (const nv_bfloat16*)scales,
+                                                                 (const nv_bfloat16*)zeros, K, N);
+        }
+    }
+    else {
+        prepare_dense_kernel<uint16_t><<<2048, 256, 0, st>>>((uint16_t*)prepared, (const uint16_t*)weight, K, N,
+                                                             weight_is_transposed);
+    }
+    return check_launch("prepare kernel");
+}
+
+extern "C" size_t b200_linear_workspace_bytes(const b200_linear_desc* d, int max_tokens)
+{
+    if (validate_desc(d)) {
+        return 0;
+    }
+    const int MT = std::max(16, (max_tokens + 15) / 16 * 16);
+    return carve_ws(nullptr, d->input_dim, d->output_dim, MT).total;
+}
+
+extern "C" int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream)
+{
+    (void)dtype;
+    if (!x || !xp || m < 0 || mt < m || mt % 16 || k % 8) {
+        return fail(B200_ERR_INVALID_ARG, "bad pack arguments");
+    }
+    const size_t n16 = (size_t)(k / 8) * mt;
+    const int    blocks = (int)std::min<size_t>((n16 + 255) / 256, 4096);
+    pack_x_kernel<uint16_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((uint16_t*)xp, (const uint16_t*)x, m, mt, k, ldx);
+    return check_launch("pack_x_kernel");
+}
+
+static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y, int64_t ldy, int epilogue,
+                          int out_mode, int out_mt, float* partials, int* counters, cudaStream_t st)
+{
+    if (mt < 16 || mt > 128 || mt % 16) {
+        return fail(B200_ERR_UNSUPPORTED, "padded token count must be a multiple of 16 in [16, 128]");
+    }
+    if (epilogue != 0 && epilogue != 1) {
+        return fail(B200_ERR_INVALID_ARG, "epilogue must be 0 (none) or 1 (gated SiLU)");
+    }
+    Params p{};
+    p.w        = (const uint8_t*)d->prepared;
+    p.xp       = xp;
+    p.y        = y;
+    p.partials = partials;
+    p.counters = counters;
+    p.bias     = d->bias;
+    p.N        = d->output_dim;
+    p.K        = d->input_dim;
+    p.MT       = mt;
+    p.M        = m;
+    p.splits   = pick_splits(p.N, p.K);
+    p.stages   = pick_stages(d->weight_format, mt);
+    p.epilogue = epilogue;
+    p.out_mode = out_mode;
+    p.ldy      = (int)ldy;
+    p.out_mt   = out_mt;
+    const bool bf = d->dtype == B200_DTYPE_BF16;
+    if (d->weight_format == kU4) {
+        return bf ? launch<nv_bfloat16, kU4>(p, st) : launch<half, kU4>(p, st);
+    }
+    return bf ? launch<nv_bfloat16, kDense>(p, st) : launch<half, kDense>(p, st);
+}
+
+extern "C" int b200_linear_forward(const b200_linear_desc* d, const void* x, int64_t ldx, int m, void* y, int64_t ldy,
+                                   int epilogue, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (int e = validate_desc(d)) {
+        return e;
+    }
+    if (!d->prepared || !x || !y) {
+        return fail(B200_ERR_INVALID_ARG, "prepared / x / y is NULL");
+    }
+    if (m <= 0 || m > 128) {
+        return fail(B200_ERR_UNSUPPORTED, "m must be in [1, 128] (decode batch)");
+    }
+    const int mt = std::max(16, (m + 15) / 16 * 16);
+    LinearWs  w  = carve_ws(workspace, d->input_dim, d->output_dim, mt);
+    if (!workspace || workspace_bytes < w.total) {
+        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_linear_workspace_bytes)");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int e = b200_pack_activations(x, ldx, m, d->input_dim, mt, d->dtype, w.xp, stream)) {
+        return e;
+    }
+    return forward_packed(d, w.xp, mt, m, y, ldy, epilogue, 0, 0, w.partials, w.counters, st);
+}
+
+extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y,
+                                          int64_t ldy, int epilogue, int out_packed_mt, void* workspace,
+                                          size_t workspace_bytes, void* stream)
+{
+    if (int e = validate_desc(d)) {
+        return e;
+    }
+    if (!d->prepared || !xp || !y) {
+        return fail(B200_ERR_INVALID_ARG, "prepared / xp / y is NULL");
+    }
+    LinearWs w = carve_ws(workspace, d->input_dim, d->output_dim, mt);
+    if (!workspace || workspace_bytes < w.total) {
+        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_linear_workspace_bytes)");
+    }
+    return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
+                          w.counters, (cudaStream_t)stream);
+}

@@ -1,0 +1,276 @@
+// Weight-only-quant GEMM for decode (M = tokens <= 128) on tcgen05 tensor cores, sm_100a.
+//
+// Replaces, behind the C ABI, LlamaLinear::Forward -> gemm::Gemm::Run
+//   (src/turbomind/models/llama/LlamaLinear.cu:140-216, kernels/gemm/gemm.cu:257-344) together with the
+//   paired weight re-packer LinearWeight::prepare (models/linear_weight.cc:101-324).
+// It is NOT a port of the sm80 mma.sync kernels: the problem is computed transposed,
+//     Y^T[N_out, tokens] = W^T[N_out, K] . X^T[K, tokens]
+// so the streamed operand (weights) sits on the UMMA M side (128 output features per CTA) and the tiny
+// activation tile is UMMA N (16..128 tokens).  Per 128-wide K group (= one AWQ quant group):
+//   * a producer thread issues two 1-D TMA bulk copies: one contiguous 8.5 KB block of packed u4 weights +
+//     their fused (scale, -zero*scale) pairs, and the contiguous activation tile (already in UMMA
+//     K-major "interleaved" layout in global memory);
+//   * 8 dequant warps unpack u4 -> f16 with lop3 and apply w = fma(q, s, t) in f16 (bit-identical to the
+//     reference's transform, transform.h:48-74 / cast.cu:155) and write the A operand straight into
+//     TENSOR MEMORY with tcgen05.st (no shared-memory round trip for the dequantised weights);
+//   * one thread issues tcgen05.mma (A from TMEM, B from smem), fp32 accumulators in TMEM;
+//   * the epilogue reads accumulators with tcgen05.ld, does the deterministic split-K fix-up through an
+//     fp32 workspace (last-arriving CTA reduces in split order), bias / gated-SiLU, and writes fp16/bf16.
+// The kernel is HBM-bound at decode batch sizes: algorithmic bytes = packed weight stream, read once.
+#pragma once
+
+#include "umma.cuh"
+
+namespace b200 {
+namespace gemm {
+
+constexpr int kBN        = 128;  // output features per CTA (UMMA M)
+constexpr int kKG        = 128;  // K per pipeline stage (= quant group size)
+constexpr int kMaxStages = 4;
+constexpr int kThreads   = 320;  // warp0 TMA, warp1 MMA/TMEM, warps2-5 dequant A + epilogue, warps6-9 dequant B
+constexpr int kTmemCols  = 512;
+constexpr int kTmemACol  = 128;  // A operand columns start (64 per stage)
+
+enum WeightFormat : int
+{
+    kDense = 0,  // T weights, [k/8][128][8] tiles
+    kU4    = 1,  // AWQ-style u4 + (scale, zero) per 128-group
+    kFp8   = 2,  // e4m3 + per-128x128-block scale
+};
+
+constexpr int kU4BlockBytes    = 8192 + 512;           // one (n-tile, k-group): data + fused params
+constexpr int kDenseBlockBytes = kBN * kKG * 2;        // 32 KB
+constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // data + block scale (T, padded to 16 B)
+
+struct Params {
+    const uint8_t* w;   // prepared weight stream
+    const void*    xp;  // packed activations [K/8][MT][8] T
+    void*          y;
+    float*         partials;  // [n_tile][split][MT][128] fp32
+    int*           counters;  // [n_tile], zero before first use; reset by the kernel
+    const void*    bias;      // [N] T or null
+    int            N, K;
+    int            MT;  // padded token count (multiple of 16, <= 128)
+    int            M;   // real tokens
+    int            splits;
+    int            stages;
+    int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
+    int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
+    int            ldy;
+    int            out_mt;
+};
+
+B200_DEVICE int w_block_bytes(int fmt)
+{
+    return fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+}
+
+template<class T>
+B200_DEVICE void store_out(const Params& p, int tok, int col, float v)
+{
+    using Ops = TypeOps<T>;
+    T* y      = reinterpret_cast<T*>(p.y);
+    if (p.out_mode == 0) {
+        y[(size_t)tok * p.ldy + col] = Ops::from_f32(v);
+    }
+    else {
+        y[((size_t)(col >> 3) * p.out_mt + tok) * 8 + (col & 7)] = Ops::from_f32(v);
+    }
+}
+
+// one accumulator value of row n_g (all 32 lanes of the warp call this with the same tok)
+template<class T>
+B200_DEVICE void finalize(const Params& p, int tok, int n_g, float acc)
+{
+    using Ops = TypeOps<T>;
+    if (p.bias) {
+        acc += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g]);
+    }
+    if (p.epilogue == 1) {
+        const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
+        if ((n_g & 1) == 0 && tok < p.M) {
+            const float silu = acc / (1.f + expf(-acc));
+            store_out<T>(p, tok, n_g >> 1, silu * other);
+        }
+    }
+    else if (tok < p.M) {
+        store_out<T>(p, tok, n_g, acc);
+    }
+}
+
+template<class T, int FMT>
+__global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
+{
+    using Ops = TypeOps<T>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t                       bar_full[kMaxStages], bar_empty[kMaxStages], bar_aready[kMaxStages];
+    __shared__ uint64_t                       bar_dready;
+    __shared__ uint32_t                       s_tmem;
+    __shared__ int                            s_last;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x, sp = blockIdx.y;
+    const int kgs = p.K / kKG;
+    const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
+    const int nk = kg1 - kg0;
+
+    constexpr int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    const int     XB     = p.MT * 256;  // 16 k8-chunks x MT x 16 B
+    const int     WB_pad = (WB + 1023) & ~1023;
+    const int     stage_bytes = WB_pad + XB;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxStages; ++s) {
+            mbar_init(smem_u32(&bar_full[s]), 1);
+            mbar_init(smem_u32(&bar_empty[s]), 1);
+            mbar_init(smem_u32(&bar_aready[s]), 128);
+        }
+        mbar_init(smem_u32(&bar_dready), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        umma::tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            const uint64_t pol_w = make_evict_first_policy();
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (i / p.stages) & 1;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                const uint32_t bar = smem_u32(&bar_full[s]);
+                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
+                mbar_expect_tx(bar, WB + XB);
+                bulk_g2s_hint(dst, p.w + ((size_t)nt * kgs + kg0 + i) * WB, WB, bar, pol_w);
+                bulk_g2s(dst + WB_pad, reinterpret_cast<const uint8_t*>(p.xp) + (size_t)(kg0 + i) * XB, XB, bar);
+            }
+        }
+    }
+    else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            const uint32_t idesc = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
+            for (int i = 0; i < nk; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (i / p.stages) & 1;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                if (FMT != kDense) {
+                    mbar_wait(smem_u32(&bar_aready[s]), ph);
+                }
+                umma::fence_after_sync();
+                const uint32_t sbase = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t xbase = sbase + WB_pad;
+#pragma unroll
+                for (int ks = 0; ks < kKG / 16; ++ks) {
+                    const uint64_t bd = umma::make_smem_desc(xbase + ks * 2 * (p.MT * 16), p.MT * 16, 128);
+                    const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                    if (FMT == kDense) {
+                        const uint64_t ad = umma::make_smem_desc(sbase + ks * 2 * (kBN * 16), kBN * 16, 128);
+                        umma::mma_f16_ss(tmem, ad, bd, idesc, acc);
+                    }
+                    else {
+                        umma::mma_f16_ts(tmem, tmem + kTmemACol + s * 64 + ks * 8, bd, idesc, acc);
+                    }
+                }
+                umma::commit(smem_u32(&bar_empty[s]));
+            }
+            umma::commit(smem_u32(&bar_dready));
+        }
+    }
+    else {
+        // ================================ dequant warps ================================
+        const int      grp       = (warp - 2) >> 2;              // 0: warps 2-5, 1: warps 6-9
+        const int      lane_base = 32 * (warp & 3);              // TMEM lanes this warp may touch
+        const int      n_local   = lane_base + lane;
+        const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
+        if constexpr (FMT == kU4) {
+            for (int i = grp; i < nk; i += 2) {
+                const int s = i % p.stages;
+                const uint32_t ph = (i / p.stages) & 1;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                const uint32_t wsm = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
+                const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const uint4 v = lds128(wsm + ((c * 2 + hh) * 128 + n_local) * 16);
+                        uint32_t    r[16];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint32_t h[4];
+                            Ops::cvt_u4x8((&v.x)[u], h);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                        }
+                        umma::st_32x32b_x16(trow + kTmemACol + s * 64 + c * 32 + hh * 16, r);
+                    }
+                }
+                umma::wait_st();
+                umma::fence_before_sync();
+                mbar_arrive(smem_u32(&bar_aready[s]));
+            }
+        }
+        // ================================ epilogue (group 0) ================================
+        if (grp == 0) {
+            mbar_wait(smem_u32(&bar_dready), 0);
+            umma::fence_after_sync();
+            const int n_g = nt * kBN + n_local;
+            if (p.splits == 1) {
+                for (int t0 = 0; t0 < p.MT; t0 += 16) {
+                    uint32_t v[16];
+                    umma::ld_32x32b_x16(trow + t0, v);
+                    umma::wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
+                }
+            }
+            else {
+                float* ws = p.partials + ((size_t)nt * p.splits + sp) * p.MT * kBN;
+                for (int t0 = 0; t0 < p.MT; t0 += 16) {
+                    uint32_t v[16];
+                    umma::ld_32x32b_x16(trow + t0, v);
+                    umma::wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ws[(size_t)(t0 + i) * kBN + n_local] = __uint_as_float(v[i]);
+                }
+                __threadfence();
+                named_bar_sync(1, 128);
+                if (threadIdx.x == 64) {
+                    const int old = atomicAdd(&p.counters[nt], 1);
+                    s_last        = (old == p.splits - 1);
+                }
+                named_bar_sync(1, 128);
+                if (s_last) {
+                    __threadfence();
+                    const float* base = p.partials + (size_t)nt * p.splits * p.MT * kBN;
+                    for (int tok = 0; tok < p.MT; ++tok) {
+                        float acc = 0.f;
+                        for (int k = 0; k < p.splits; ++k) {
+                            acc += __ldcg(base + ((size_t)k * p.MT + tok) * kBN + n_local);
+                        }
+                        finalize<T>(p, tok, n_g, acc);
+                    }
+                    if (threadIdx.x == 64) {
+                        p.counters[nt] = 0;
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        umma::tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+}  // namespace gemm
+}  // namespace b200

@@ -1,0 +1,153 @@
+"""GPU parity: b200_linear_* (tcgen05 W4A16 / dense GEMM) vs the CPU oracle.
+
+Bars: the dequantised weight is bit-identical by construction (f16 fma); the product is accumulated in fp32
+on the tensor core in an unspecified order, so outputs are compared at 1 fp16 ulp of the output scale:
+|diff| <= 2e-4 + 2e-3*|ref|  (reference gate for the same quantity: max_abs <= 0.25,
+tests/turbomind/linear/fixture.py:34-42; we are ~1000x tighter)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import linear as OL
+from oracle.numerics import F16, BF16, rn
+
+from harness import to_dev_T, from_dev_T
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk_u4(rng, K, N):
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    q, s, z = OL.quantize_groupwise_u4(w, 128)
+    return q, s, z
+
+
+class DevLinear:
+    def __init__(self, lib, K, N, fmt, dtype, weight, scales=None, zeros=None, bias=None, transposed=0):
+        import torch
+        from lmdeploy_b200 import _lib as L
+        self.lib, self.L, self.torch = lib, L, torch
+        self.d = L.LinearDesc(K, N, fmt, 0 if dtype == F16 else 1, 128, None, None)
+        nbytes = lib.b200_linear_prepared_bytes(C.byref(self.d))
+        assert nbytes > 0, lib.b200_last_error()
+        self.prepared = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        self.d.prepared = self.prepared.data_ptr()
+        if bias is not None:
+            self.bias = to_dev_T(bias, dtype)
+            self.d.bias = self.bias.data_ptr()
+        st = torch.cuda.current_stream().cuda_stream
+        if fmt == 1:
+            qw = torch.from_numpy(OL.pack_u4_row(weight)).cuda()
+            ds, dz = to_dev_T(scales, dtype), to_dev_T(zeros, dtype)
+            L.check(lib.b200_linear_prepare(C.byref(self.d), qw.data_ptr(), ds.data_ptr(), dz.data_ptr(), 0,
+                                            self.prepared.data_ptr(), st), "prepare")
+        else:
+            dw = to_dev_T(weight, dtype)
+            L.check(lib.b200_linear_prepare(C.byref(self.d), dw.data_ptr(), None, None, transposed,
+                                            self.prepared.data_ptr(), st), "prepare")
+        torch.cuda.synchronize()
+        self.dtype = dtype
+        self.K, self.N = K, N
+        self.ws = torch.zeros(lib.b200_linear_workspace_bytes(C.byref(self.d), 128), dtype=torch.uint8, device="cuda")
+
+    def forward(self, x, epilogue=0):
+        torch, L, lib = self.torch, self.L, self.lib
+        m = x.shape[0]
+        dx = to_dev_T(x, self.dtype)
+        nout = self.N // 2 if epilogue == 1 else self.N
+        y = torch.zeros(m, nout, dtype=dx.dtype, device="cuda")
+        L.check(lib.b200_linear_forward(C.byref(self.d), dx.data_ptr(), self.K, m, y.data_ptr(), nout, epilogue,
+                                        self.ws.data_ptr(), self.ws.numel(), torch.cuda.current_stream().cuda_stream),
+                "b200_linear_forward")
+        torch.cuda.synchronize()
+        return from_dev_T(y, self.dtype)
+
+
+def _assert_close(got, ref, atol=2e-4, rtol=2e-3):
+    err = np.abs(got - ref)
+    lim = atol + rtol * np.abs(ref)
+    assert np.isfinite(got).all()
+    bad = err > lim
+    assert not bad.any(), f"{bad.sum()} / {bad.size} out of tolerance; max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} ref {ref.flat[err.argmax()]} got {got.flat[err.argmax()]}"
+
+
+@pytest.mark.parametrize("shape", [(256, 128), (1024, 256), (4096, 6144), (4096, 4096), (14336, 4096)])
+@pytest.mark.parametrize("m", [1, 16, 64])
+def test_w4a16_f16(lib, shape, m):
+    K, N = shape
+    rng = np.random.default_rng(K + N + m)
+    q, s, z = _mk_u4(rng, K, N)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), F16)
+    got = lin.forward(x)
+    ref = OL.linear(x, OL.dequant_u4(q, s, z, F16), F16)
+    _assert_close(got, ref)
+
+
+@pytest.mark.parametrize("m", [3, 33, 128])
+def test_w4a16_ragged_m_and_bias(lib, m):
+    K, N = 512, 384
+    rng = np.random.default_rng(m)
+    q, s, z = _mk_u4(rng, K, N)
+    bias = rn((rng.standard_normal(N) * 0.05).astype(np.float32), F16)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z, bias=bias)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), F16)
+    got = lin.forward(x)
+    ref = OL.linear(x, OL.dequant_u4(q, s, z, F16), F16, bias=bias)
+    _assert_close(got, ref)
+
+
+def test_w4a16_gated_silu(lib):
+    K, N = 4096, 2048     # N interleaved (gate, up) -> 1024 outputs
+    rng = np.random.default_rng(9)
+    q, s, z = _mk_u4(rng, K, N)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z)
+    x = rn(rng.standard_normal((64, K)).astype(np.float32), F16)
+    got = lin.forward(x, epilogue=1)
+    ref = OL.linear_gated_silu(x, OL.dequant_u4(q, s, z, F16), F16)
+    _assert_close(got, ref, atol=3e-4)
+
+
+@pytest.mark.parametrize("dtype", [F16, BF16])
+@pytest.mark.parametrize("transposed", [0, 1])
+def test_dense(lib, dtype, transposed):
+    K, N, m = 1024, 512, 40
+    rng = np.random.default_rng(3)
+    w = rn((rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32), dtype)
+    lin = DevLinear(lib, K, N, 0, dtype, w.T.copy() if transposed else w, transposed=transposed)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), dtype)
+    got = lin.forward(x)
+    ref = OL.linear(x, w, dtype)
+    _assert_close(got, ref, atol=2e-4 if dtype == F16 else 2e-3, rtol=2e-3 if dtype == F16 else 1.6e-2)
+
+
+def test_w4a16_bf16(lib):
+    K, N, m = 1024, 256, 16
+    rng = np.random.default_rng(4)
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    q, s, z = OL.quantize_groupwise_u4(w, 128)
+    s = rn(s, BF16)
+    lin = DevLinear(lib, K, N, 1, BF16, q, s, z)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), BF16)
+    got = lin.forward(x)
+    ref = OL.linear(x, OL.dequant_u4(q, s, z, BF16), BF16)
+    _assert_close(got, ref, atol=2e-3, rtol=1.6e-2)
+
+
+def test_linearity_property_full_size(lib):
+    """Size-independent property at the 7B w1w3 shape: f(a*x) == a*f(x) for a power of two (exact in fp
+    arithmetic), and f(0) == 0."""
+    K, N = 4096, 28672
+    rng = np.random.default_rng(5)
+    q, s, z = _mk_u4(rng, K, N)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z)
+    x = rn(rng.standard_normal((64, K)).astype(np.float32), F16)
+    y1 = lin.forward(x)
+    y2 = lin.forward(rn(x * 0.5, F16))
+    assert (y2 == rn(y1 * 0.5, F16)).mean() > 0.999   # halving is exact except f16 subnormal outputs
+    assert (lin.forward(np.zeros_like(x)) == 0).all()
+    # spot-check 64 random columns against the oracle
+    cols = rng.choice(N, 64, replace=False)
+    wd = OL.dequant_u4(q[:, cols], s[:, cols], z[:, cols], F16)
+    _assert_close(y1[:, cols], OL.linear(x, wd, F16))
