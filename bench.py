@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of the B200-native TurboMind decode path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c1-tiny]
+
+Workload (BASELINE.json configs[1], "C2"): InternLM2-7B geometry, W4A16 AWQ (u4 g128) weights + KV int8, bs = 64,
+2K context, greedy decode; synthetic random weights / KV (no checkpoints exist in the image).  A "step" is one
+decode forward for the whole batch (64 new tokens).  N > 1 = tensor parallel over N GPUs of one box (heads / FFN /
+vocab sharded, fused NVLink all-reduce), launched by torchrun, one rank per GPU: total work is fixed => "strong".
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; `roofline` is for the dominant kernel
+(decode_attention_kernel), `cpu_baseline` is the oracle port timed on the host cores, `e2e` goes through the
+public engine API with host token buffers (H2D / D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (spec, batch, ctx, kv quant policy)
+    "c2": ("internlm2-7b", 64, 2048, 8),
+    "c3": ("llama3-8b", 128, 4096, 4),
+    "c4": ("internlm2-20b", 64, 2048, 0),
+    "c1-tiny": ("internlm2-1.8b", 1, 128, 0),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(CONFIGS))
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--attn-iters", type=int, default=20)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples SM clock + throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm: the CPU port of the path, all host threads (the reference has no CPU engine; see oracle/)
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from lmdeploy_b200.turbomind.specs import SPECS
+    from oracle import cpu_baseline
+    name, batch, ctx, qp = CONFIGS[args.config]
+    spec = SPECS[name]
+    cores = os.cpu_count()
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=1, threads=cores)
+    reps = max(1, min(args.steps, 3))
+    r = cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=reps, threads=cores)
+    line = {
+        "impl": "reference", "metric": "decode tokens/sec", "value": r["tokens_per_s"], "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name} W4A16+KV-int{qp} decode bs={batch} ctx={ctx} (CPU port of the path)"},
+        "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": cores, "kind": "port",
+                         "sample": r["sample"]},
+        "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lmdeploy_b200 import _lib as L
+    from lmdeploy_b200.turbomind import SPECS, DecodeModel, KvCachePool
+    from lmdeploy_b200.turbomind.tp import TpGroup
+    from lmdeploy_b200.engine import StaticBatchRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    name, batch, ctx, qp = CONFIGS[args.config]
+    spec = SPECS[name]
+    total_steps = args.warmup + args.steps
+    # two phases run back to back on the same cache: device-resident (value) and host-fed (e2e)
+    max_len = ctx + 2 * total_steps + 8
+
+    model = DecodeModel(spec, quant_policy=qp, max_batch=batch, tp_size=world, tp_rank=rank)
+    model.load_synthetic(seed=0)
+    tp = None
+    if world > 1:
+        tp = TpGroup(model, rank, world)
+    runner = StaticBatchRunner(model, batch=batch, max_len=max_len, seed=0)
+    runner.prefill_random(ctx)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- phase A: device-resident steps (value) ----------------
+    use_graph = not args.no_graph and world == 1
+    runner.reset_lengths(ctx)
+    step_fn = runner.make_device_step(graph=use_graph)
+    for _ in range(args.warmup):
+        step_fn()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for _ in range(args.steps):
+            step_fn()
+        ev1.record()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+    ms_per_step = ms / args.steps
+    value = batch * args.steps / (ms * 1e-3)
+
+    # ---------------- phase B: end to end through the engine API with host buffers ----------------
+    import numpy as np
+    host_tokens = np.random.default_rng(0).integers(0, spec.vocab, batch).astype(np.int32)
+    for _ in range(min(args.warmup, 3)):
+        host_tokens = runner.step_host(host_tokens)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        host_tokens = runner.step_host(host_tokens)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = batch * args.steps / e2e_s
+
+    # ---------------- roofline of the dominant kernel (decode attention), timed alone ----------------
+    peak, peak_src = measured_peaks()
+    attn = runner.time_attention_kernel(ctx + args.warmup + args.steps, iters=args.attn_iters)
+    sb = model.step_bytes(batch, ctx + args.warmup + args.steps // 2)
+    step_gbs = sb["total"] / (ms_per_step * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "decode_attention_kernel", "achieved": attn["gbs"], "peak": peak, "unit": "GB/s",
+        "frac": attn["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "bytes_per_launch": attn["bytes"], "us_per_launch": attn["us"],
+        "step": {"algorithmic_bytes": sb["total"], "achieved_gbs_per_gpu": step_gbs, "frac": step_gbs / peak},
+    }
+
+    line = {
+        "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"{name} W4A16(AWQ u4 g128)+KV-int{qp} greedy decode, bs={batch}, ctx={ctx}"
+                   if spec.weight_format == "awq" else f"{name} fp16 + KV quant {qp} decode bs={batch} ctx={ctx}",
+                   "parallelism": f"tp{world}", "cuda_graph": use_graph,
+                   "l2": "inputs larger than L2 (>= 6 GB of KV + weights streamed per step per GPU)"},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": batch * 4, "d2h_bytes_per_step": batch * 4,
+                "ms_per_step": e2e_s / args.steps * 1e3},
+        "gpu_launches": runner.launches_per_step * args.steps,
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline
+        r = cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=1, threads=os.cpu_count())
+        line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "port",
+                                "sample": r["sample"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        if tp is not None:
+            tp.close()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,14 @@ typedef struct {
      * the step); if NULL the call plans internally. */
     const int* plan;
 
+    /* > 0: write `out` in the UMMA K-major tile layout [num_heads*128/8][out_packed_mt][8] consumed by
+     * b200_linear_forward_packed (fuses the repack in front of the `wo` GEMM); 0: token-major rows. */
+    int out_packed_mt;
+
+    /* profiling aid: bit 0 = skip the prologue (q/k/v of this step already processed by a previous identical
+     * call), bit 1 = skip the fix-up kernel.  0 in production. */
+    int debug_flags;
+
     void* stream;
 } b200_attention_params;
 
@@ -179,6 +187,118 @@ B200_API int b200_linear_forward_packed(const b200_linear_desc* desc, const void
                                int epilogue, int out_packed_mt, void* workspace, size_t workspace_bytes,
                                void* stream);
 B200_API int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Step glue.  Replace invokeRMSNorm / invokeBiasResidualRMSNorm (kernels/norm/rms_norm.cu:21-86, 287-363),
+ * invokeEmbeddingLookup (kernels/gpt_kernels.cu:43) and the greedy (top_k = 1) path of Generation::Forward
+ * (generation/generation.cc:247-293).  `out_packed_mt` > 0 writes the normalised activations directly in
+ * the packed tile layout of b200_linear_forward_packed.
+ *   rmsnorm:           out = T(float(x) * rsqrt(mean(x^2) + eps)) * w
+ *   residual_rmsnorm:  residual += hidden (+ bias) in T (stored); out = rmsnorm(residual)
+ *   argmax:            index of the largest fp32-cast logit per row; exact ties -> smallest index
+ * ---------------------------------------------------------------------------------------------- */
+B200_API int b200_rmsnorm(void* out, int out_packed_mt, const void* x, const void* weight, int tokens, int dim, float eps,
+                 int dtype, void* stream);
+B200_API int b200_residual_rmsnorm(void* out, int out_packed_mt, void* residual, const void* hidden, const void* weight,
+                          const void* bias, int tokens, int dim, float eps, int dtype, void* stream);
+B200_API int b200_embedding_lookup(void* out, const void* table, const int* token_ids, int tokens, int dim, int vocab,
+                          int dtype, void* stream);
+B200_API int b200_argmax(int* out, const void* logits, int rows, int vocab, int64_t ld, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-parallel device communicator over NVLink peer memory (one process per GPU; peers' buffers are
+ * mapped with CUDA IPC by the host side and handed over as raw pointers).  Replaces
+ *   DeviceCommImpl::AllreduceResidualBiasRMSnorm / AllReduceSum / AllGather
+ *     (src/turbomind/comm/device_comm.h:21-143; native impl comm/cuda_ipc/fused_allreduce.cu:25-553)
+ * with ONE kernel per call that reads every peer's partial GEMM output straight over NVLink (one-shot
+ * "pull"), sums the ranks in rank order in T (as the reference's push/pull kernels do), adds the residual,
+ * RMS-normalises and writes the next GEMM's input tile -- no separate collective, no NCCL on the path.
+ *   peer_data[r]  : rank r's exchange buffer (b200_comm_buffer_bytes() bytes), peer-mapped
+ *   peer_flags[r] : rank r's flag array     (b200_comm_flags_bytes() bytes, zero-initialised), peer-mapped
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_comm b200_comm;
+B200_API size_t b200_comm_buffer_bytes(int max_tokens, int hidden, int vocab_per_rank);
+B200_API size_t b200_comm_flags_bytes(void);
+B200_API int b200_comm_create(b200_comm** comm, int rank, int world_size, void* const* peer_data, void* const* peer_flags);
+B200_API void b200_comm_destroy(b200_comm* comm);
+/* this rank's exchange buffer: the GEMM that feeds a fused all-reduce must write its output here */
+B200_API void* b200_comm_local_buffer(b200_comm* comm);
+/* hidden_partial: this rank's [tokens, dim] partial sums (T).  On return (stream order):
+ *   residual += sum_ranks(hidden_partial) (+ bias);  out = RMSNorm(residual) * weight  (packed if out_packed_mt > 0) */
+B200_API int b200_comm_allreduce_residual_rmsnorm(b200_comm* comm, void* out, int out_packed_mt, void* residual,
+                                         const void* hidden_partial, const void* weight, const void* bias, int tokens,
+                                         int dim, float eps, int dtype, void* stream);
+/* Vocab-sharded greedy sampling: local argmax per rank, (value, index) pairs exchanged over peer memory,
+ * every rank returns the global token id (replaces the logits all-gather of language_model.cc:306-334). */
+B200_API int b200_comm_argmax_allgather(b200_comm* comm, int* out_tokens, const void* local_logits, int rows,
+                               int vocab_per_rank, int dtype, void* stream);
+/* plain all-reduce(sum) of a [count] T buffer, in place (AllReduceSum). */
+B200_API int b200_comm_allreduce_sum(b200_comm* comm, void* data, size_t count, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode-step driver.  Stands where LanguageModel::Run(kForward) (models/language_model.cc:493-542) +
+ * UnifiedDecoder::Forward (models/llama/unified_decoder.cc:163-380) + Generation::Forward (greedy) stand:
+ * one call enqueues embedding -> L x [qkv GEMM, decode attention, wo GEMM, (all-reduce+)residual RMSNorm,
+ * w1w3 GEMM + gated SiLU, w2 GEMM, (all-reduce+)residual RMSNorm] -> lm_head GEMM -> argmax on `stream`
+ * with no host synchronisation (CUDA-graph capturable).  Weights are caller-owned device memory in the
+ * `prepared` layout; per-rank shapes when tp_size > 1 (heads, inter_size and vocab already divided).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct b200_model b200_model;
+
+typedef struct {
+    int   num_layers;
+    int   hidden;
+    int   num_heads;    /* local q heads */
+    int   num_kv_heads; /* local kv heads */
+    int   head_dim;
+    int   inter_size;   /* local */
+    int   vocab;        /* local lm_head rows (multiple of 128) */
+    int   embedding_rows; /* rows of the (replicated) embedding table */
+    float norm_eps;
+    float inv_sqrt_dh;
+    b200_rope_config rope;
+    int   dtype;
+    int   quant_policy; /* KV cache: 0 / 4 / 8 */
+    int   block_len;
+    int   max_batch;
+    int   tp_size;
+    int   tp_rank;
+} b200_model_config;
+
+enum { B200_W_QKV = 0, B200_W_O = 1, B200_W_GATE_UP = 2, B200_W_DOWN = 3, B200_W_LM_HEAD = 4 };
+enum { B200_T_EMBEDDING = 0, B200_T_FINAL_NORM = 1, B200_T_ATTN_NORM = 2, B200_T_FFN_NORM = 3 };
+
+typedef struct {
+    int            batch_size;
+    const int*     token_ids;     /* [batch] input token of every sequence */
+    const int*     cu_q_len;      /* [batch+1] = 0..batch */
+    const int*     cu_k_len;      /* [batch+1] context lengths INCLUDING the new token */
+    const uint8_t* finished;      /* [batch] or NULL */
+    void**         block_ptrs;
+    const int*     cu_block_nums; /* [batch+1] */
+    int            layer_stride_bytes; /* bytes of one layer inside a KV block */
+    int            max_k_len;
+    int*           out_tokens;    /* [batch] greedy token ids (may be NULL: logits only) */
+    int            advance;       /* != 0: after sampling, token_ids <- out_tokens and k_len += 1 on device
+                                     (writes through token_ids / cu_k_len; lets a captured graph self-iterate) */
+} b200_step_inputs;
+
+B200_API int b200_model_create(b200_model** model, const b200_model_config* config);
+B200_API void b200_model_destroy(b200_model* model);
+B200_API int b200_model_set_linear(b200_model* model, int layer, int which, const b200_linear_desc* desc);
+B200_API int b200_model_set_tensor(b200_model* model, int layer, int which, const void* ptr);
+B200_API int b200_model_set_comm(b200_model* model, b200_comm* comm);
+/* internal activations for tests: 0 logits [max_batch, vocab], 1 residual, 2 last GEMM output, 3 qkv */
+B200_API void* b200_model_buffer(b200_model* model, int which);
+B200_API int b200_model_decode_step(b200_model* model, const b200_step_inputs* inputs, void* stream);
+B200_API int b200_step_advance(const int* token_ids, const int* out_tokens, int* cu_k_len, const uint8_t* finished,
+                      int batch, void* stream);
+
+/* CUDA-IPC helpers for the one-process-per-GPU communicator (host side exchanges the 64-byte handles). */
+B200_API int b200_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+B200_API int b200_ipc_open(const unsigned char handle[64], void** ptr);
+B200_API int b200_ipc_close(void* ptr);
+B200_API int b200_ipc_free(void* ptr);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,8 @@ class AttentionParams(C.Structure):
         ("rope", RopeConfig), ("quant_policy", C.c_int), ("dtype", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("plan", C.c_void_p),
+        ("out_packed_mt", C.c_int),
+        ("debug_flags", C.c_int),
         ("stream", C.c_void_p),
     ]
 
@@ -45,6 +47,27 @@ class LinearDesc(C.Structure):
         ("group_size", C.c_int), ("prepared", C.c_void_p), ("bias", C.c_void_p),
     ]
 
+
+class ModelConfig(C.Structure):
+    _fields_ = [
+        ("num_layers", C.c_int), ("hidden", C.c_int), ("num_heads", C.c_int), ("num_kv_heads", C.c_int),
+        ("head_dim", C.c_int), ("inter_size", C.c_int), ("vocab", C.c_int), ("embedding_rows", C.c_int),
+        ("norm_eps", C.c_float), ("inv_sqrt_dh", C.c_float), ("rope", RopeConfig), ("dtype", C.c_int),
+        ("quant_policy", C.c_int), ("block_len", C.c_int), ("max_batch", C.c_int), ("tp_size", C.c_int),
+        ("tp_rank", C.c_int),
+    ]
+
+
+class StepInputs(C.Structure):
+    _fields_ = [
+        ("batch_size", C.c_int), ("token_ids", C.c_void_p), ("cu_q_len", C.c_void_p), ("cu_k_len", C.c_void_p),
+        ("finished", C.c_void_p), ("block_ptrs", C.c_void_p), ("cu_block_nums", C.c_void_p),
+        ("layer_stride_bytes", C.c_int), ("max_k_len", C.c_int), ("out_tokens", C.c_void_p), ("advance", C.c_int),
+    ]
+
+
+W_QKV, W_O, W_GATE_UP, W_DOWN, W_LM_HEAD = range(5)
+T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM = range(4)
 
 _lib = None
 
@@ -81,6 +104,40 @@ def load():
                                                C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200_pack_activations.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
+    lib.b200_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,
+                                 C.c_void_p]
+    lib.b200_residual_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    lib.b200_embedding_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_void_p]
+    lib.b200_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    lib.b200_comm_buffer_bytes.restype = C.c_size_t
+    lib.b200_comm_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.b200_comm_flags_bytes.restype = C.c_size_t
+    lib.b200_comm_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_void_p)]
+    lib.b200_comm_destroy.argtypes = [C.c_void_p]
+    lib.b200_comm_local_buffer.restype = C.c_void_p
+    lib.b200_comm_local_buffer.argtypes = [C.c_void_p]
+    lib.b200_comm_allreduce_residual_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                         C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                                         C.c_int, C.c_void_p]
+    lib.b200_comm_argmax_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                               C.c_void_p]
+    lib.b200_comm_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
+    lib.b200_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(ModelConfig)]
+    lib.b200_model_destroy.argtypes = [C.c_void_p]
+    lib.b200_model_set_linear.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(LinearDesc)]
+    lib.b200_model_set_tensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_model_set_comm.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200_model_buffer.restype = C.c_void_p
+    lib.b200_model_buffer.argtypes = [C.c_void_p, C.c_int]
+    lib.b200_model_decode_step.argtypes = [C.c_void_p, C.POINTER(StepInputs), C.c_void_p]
+    lib.b200_step_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.b200_ipc_close.argtypes = [C.c_void_p]
+    lib.b200_ipc_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 

@@ -452,8 +452,10 @@ static int launch_decode(const b200_attention_params* a)
         }
         plan = w.plan;
     }
-    if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st)) {
-        return e;
+    if (!(a->debug_flags & 1)) {
+        if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st)) {
+            return e;
+        }
     }
     constexpr int STAGES = stages_for<KVBITS>();
     using SS             = SharedStorage<T, KVBITS, STAGES>;
@@ -477,9 +479,13 @@ static int launch_decode(const b200_attention_params* a)
     p.num_heads     = a->num_heads;
     p.num_kv_heads  = a->num_kv_heads;
     p.qk_scale      = a->inv_sqrt_dh;
+    p.out_mt        = a->out_packed_mt;
     decode_attention_kernel<T, KVBITS, STAGES><<<grid, kThreads, sizeof(SS), st>>>(p);
     if (int e = check_launch("decode_attention_kernel")) {
         return e;
+    }
+    if (a->debug_flags & 2) {
+        return 0;
     }
     dim3 rgrid(a->num_kv_heads, a->batch_size);
     decode_reduce_kernel<T><<<rgrid, 128, 0, st>>>(p, grid);

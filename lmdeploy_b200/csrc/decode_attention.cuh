@@ -65,6 +65,7 @@ struct KernelParams {
     int         num_heads;
     int         num_kv_heads;
     float       qk_scale;  // log2(e)/sqrt(D)  (AttentionParams::inv_sqrt_dh)
+    int         out_mt;    // > 0: write `out` in the UMMA K-major tile layout [Hq*D/8][out_mt][8]
 };
 
 // slot (0..15 inside a warp's 16-key MMA) -> token index inside the 64-token tile
@@ -585,14 +586,17 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
             const bool complete = (first_tile == 0) && last_tile;
             const int  ctid     = threadIdx.x;  // 0..127
             if (complete) {
-                T* ob = reinterpret_cast<T*>(p.out) + (size_t)it.b * p.out_stride + (size_t)it.h * G * kHeadDim;
                 for (int i = ctid; i < G * kHeadDim / 2; i += kConsumerWarps * 32) {
                     const int   hd  = (2 * i) / kHeadDim;
                     const int   d   = (2 * i) % kHeadDim;
                     const float inv = 1.f / ss.final_L[hd];
                     const float x0  = (ss.merge_O[0][hd][d] + ss.merge_O[1][hd][d]) * inv;
                     const float x1  = (ss.merge_O[0][hd][d + 1] + ss.merge_O[1][hd][d + 1]) * inv;
-                    reinterpret_cast<uint32_t*>(ob)[i] = Ops::pack2(x0, x1);
+                    const int   col = it.h * G * kHeadDim + 2 * i;
+                    T*          dst = reinterpret_cast<T*>(p.out)
+                             + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + it.b) * 8 + (col & 7) :
+                                               (size_t)it.b * p.out_stride + col);
+                    *reinterpret_cast<uint32_t*>(dst) = Ops::pack2(x0, x1);
                 }
             }
             else {
@@ -639,7 +643,6 @@ __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
     }
     const long long lo_cf = total * cf / grid_main;
     const float     c     = p.qk_scale;
-    T* ob = reinterpret_cast<T*>(p.out) + (size_t)b * p.out_stride + (size_t)h * G * kHeadDim;
     for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x) {
         const int hd = i / kHeadDim;
         float     m  = -INFINITY;
@@ -656,7 +659,10 @@ __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
             l += w * lk;
             acc += w * p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i];
         }
-        ob[i] = Ops::from_f32(acc / l);
+        const int col = h * G * kHeadDim + i;
+        T*        dst = reinterpret_cast<T*>(p.out)
+                 + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + b) * 8 + (col & 7) : (size_t)b * p.out_stride + col);
+        *dst = Ops::from_f32(acc / l);
     }
 }
 

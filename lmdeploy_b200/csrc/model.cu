@@ -1,0 +1,304 @@
+// Decode-step driver: the layer loop of one decode forward, natively in C++ (the reference's is C++ too:
+//   LanguageModel::Impl::Forward      src/turbomind/models/language_model.cc:493-542
+//   UnifiedDecoder::Forward           src/turbomind/models/llama/unified_decoder.cc:163-380
+//   UnifiedAttentionLayer::Forward    src/turbomind/models/llama/unified_attention_layer.cc:365-441
+//   LlamaFfnLayer::forward            src/turbomind/models/llama/LlamaFfnLayer.cc:28-91
+//   Generation::Forward (greedy)      src/turbomind/generation/generation.cc:247-293 )
+// One call enqueues the whole step on a stream with no host synchronisation, so the caller can capture it in a
+// CUDA graph.  Activations between kernels live in the UMMA K-major tile layout so that every GEMM's B operand
+// is one contiguous TMA bulk copy.
+#include "../../include/b200_turbomind.h"
+#include "host_utils.h"
+
+#include <cstring>
+#include <vector>
+
+namespace b200 {
+
+struct LayerW {
+    b200_linear_desc qkv{}, wo{}, w13{}, w2{};
+    const void*      attn_norm{};
+    const void*      ffn_norm{};
+};
+
+}  // namespace b200
+
+struct b200_model {
+    b200_model_config       cfg{};
+    std::vector<b200::LayerW> layers;
+    b200_linear_desc        lm_head{};
+    const void*             embedding{};
+    const void*             final_norm{};
+    b200_comm*              comm{};
+    // device buffers
+    int   mt_cap{};
+    void* residual{};
+    void* xp{};
+    void* qkv{};
+    void* attn_xp{};
+    void* o{};
+    void* o_x{};  // GEMM output inside the comm exchange buffer (TP) -- overrides `o`
+    void* act_xp{};
+    void* logits{};
+    void* attn_ws{};
+    size_t attn_ws_bytes{};
+    void* lin_ws{};
+    size_t lin_ws_bytes{};
+    int*  plan{};
+};
+
+using namespace b200;
+
+static int round16(int x)
+{
+    return std::max(16, (x + 15) / 16 * 16);
+}
+
+extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
+{
+    if (!out || !c) {
+        return fail(B200_ERR_INVALID_ARG, "model_create: NULL argument");
+    }
+    if (c->head_dim != 128) {
+        return fail(B200_ERR_UNSUPPORTED, "head_dim must be 128");
+    }
+    if (c->max_batch <= 0 || c->max_batch > 128) {
+        return fail(B200_ERR_UNSUPPORTED, "max_batch must be in [1, 128]");
+    }
+    if (c->num_heads % c->num_kv_heads || c->hidden % 128 || c->inter_size % 128 || c->vocab % 128) {
+        return fail(B200_ERR_UNSUPPORTED, "hidden / inter_size / vocab (per rank) must be multiples of 128");
+    }
+    auto* m   = new b200_model();
+    m->cfg    = *c;
+    m->layers.resize(c->num_layers);
+    m->mt_cap = round16(c->max_batch);
+    const size_t es = 2;
+    const int    MT = m->mt_cap, MB = c->max_batch;
+    const int    qkv_dim = (c->num_heads + 2 * c->num_kv_heads) * c->head_dim;
+    auto alloc = [&](void** p, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(p, bytes);
+        if (e != cudaSuccess) {
+            return fail_cuda(e, "cudaMalloc(model buffers)");
+        }
+        e = cudaMemset(*p, 0, bytes);
+        return e == cudaSuccess ? 0 : fail_cuda(e, "cudaMemset");
+    };
+    int rc = 0;
+    rc = rc ? rc : alloc(&m->residual, (size_t)MB * c->hidden * es);
+    rc = rc ? rc : alloc(&m->xp, (size_t)MT * c->hidden * es);
+    rc = rc ? rc : alloc(&m->qkv, (size_t)MB * qkv_dim * es);
+    rc = rc ? rc : alloc(&m->attn_xp, (size_t)MT * c->num_heads * c->head_dim * es);
+    rc = rc ? rc : alloc(&m->o, (size_t)MB * c->hidden * es);
+    rc = rc ? rc : alloc(&m->act_xp, (size_t)MT * c->inter_size * es);
+    rc = rc ? rc : alloc(&m->logits, (size_t)MB * c->vocab * es);
+    m->attn_ws_bytes = b200_decode_attention_workspace_bytes(MB, c->num_heads, c->num_kv_heads);
+    rc = rc ? rc : alloc(&m->attn_ws, m->attn_ws_bytes);
+    // linear workspace: sized for the largest (K, N) on the path
+    size_t lin = 0;
+    {
+        const int shapes[5][2] = {{c->hidden, qkv_dim},
+                                  {c->num_heads * c->head_dim, c->hidden},
+                                  {c->hidden, 2 * c->inter_size},
+                                  {c->inter_size, c->hidden},
+                                  {c->hidden, c->vocab}};
+        for (auto& s : shapes) {
+            b200_linear_desc d{};
+            d.input_dim = s[0], d.output_dim = (s[1] + 127) / 128 * 128, d.weight_format = 0, d.dtype = c->dtype,
+            d.group_size = 128;
+            lin          = std::max(lin, b200_linear_workspace_bytes(&d, MB));
+        }
+    }
+    m->lin_ws_bytes = lin;
+    rc = rc ? rc : alloc(&m->lin_ws, lin);
+    rc = rc ? rc : alloc((void**)&m->plan, (size_t)(MB + 1) * 4);
+    if (rc) {
+        b200_model_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return 0;
+}
+
+extern "C" void b200_model_destroy(b200_model* m)
+{
+    if (!m) {
+        return;
+    }
+    void* bufs[] = {m->residual, m->xp, m->qkv, m->attn_xp, m->o, m->act_xp, m->logits, m->attn_ws, m->lin_ws, m->plan};
+    for (void* p : bufs) {
+        if (p) {
+            cudaFree(p);
+        }
+    }
+    delete m;
+}
+
+extern "C" int b200_model_set_linear(b200_model* m, int layer, int which, const b200_linear_desc* d)
+{
+    if (!m || !d) {
+        return fail(B200_ERR_INVALID_ARG, "set_linear: NULL argument");
+    }
+    if (which == B200_W_LM_HEAD) {
+        m->lm_head = *d;
+        return 0;
+    }
+    if (layer < 0 || layer >= (int)m->layers.size()) {
+        return fail(B200_ERR_INVALID_ARG, "set_linear: layer out of range");
+    }
+    LayerW& L = m->layers[layer];
+    switch (which) {
+        case B200_W_QKV: L.qkv = *d; break;
+        case B200_W_O: L.wo = *d; break;
+        case B200_W_GATE_UP: L.w13 = *d; break;
+        case B200_W_DOWN: L.w2 = *d; break;
+        default: return fail(B200_ERR_INVALID_ARG, "set_linear: bad weight id");
+    }
+    return 0;
+}
+
+extern "C" int b200_model_set_tensor(b200_model* m, int layer, int which, const void* ptr)
+{
+    if (!m || !ptr) {
+        return fail(B200_ERR_INVALID_ARG, "set_tensor: NULL argument");
+    }
+    if (which == B200_T_EMBEDDING) {
+        m->embedding = ptr;
+        return 0;
+    }
+    if (which == B200_T_FINAL_NORM) {
+        m->final_norm = ptr;
+        return 0;
+    }
+    if (layer < 0 || layer >= (int)m->layers.size()) {
+        return fail(B200_ERR_INVALID_ARG, "set_tensor: layer out of range");
+    }
+    if (which == B200_T_ATTN_NORM) {
+        m->layers[layer].attn_norm = ptr;
+    }
+    else if (which == B200_T_FFN_NORM) {
+        m->layers[layer].ffn_norm = ptr;
+    }
+    else {
+        return fail(B200_ERR_INVALID_ARG, "set_tensor: bad tensor id");
+    }
+    return 0;
+}
+
+extern "C" int b200_model_set_comm(b200_model* m, b200_comm* comm)
+{
+    if (!m) {
+        return fail(B200_ERR_INVALID_ARG, "set_comm: NULL model");
+    }
+    m->comm = comm;
+    m->o_x  = comm ? b200_comm_local_buffer(comm) : nullptr;
+    return 0;
+}
+
+extern "C" void* b200_model_buffer(b200_model* m, int which)
+{
+    if (!m) {
+        return nullptr;
+    }
+    switch (which) {
+        case 0: return m->logits;
+        case 1: return m->residual;
+        case 2: return m->o;
+        case 3: return m->qkv;
+        default: return nullptr;
+    }
+}
+
+#define TRY(x)                                                                                                         \
+    do {                                                                                                               \
+        int _rc = (x);                                                                                                 \
+        if (_rc) {                                                                                                     \
+            return _rc;                                                                                                \
+        }                                                                                                              \
+    } while (0)
+
+extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in, void* stream)
+{
+    if (!m || !in) {
+        return fail(B200_ERR_INVALID_ARG, "decode_step: NULL argument");
+    }
+    const b200_model_config& c = m->cfg;
+    const int                B = in->batch_size;
+    if (B <= 0 || B > c.max_batch) {
+        return fail(B200_ERR_INVALID_ARG, "decode_step: batch_size out of range");
+    }
+    if (!m->embedding || !m->final_norm || !m->lm_head.prepared) {
+        return fail(B200_ERR_STATE, "decode_step: model weights not set");
+    }
+    const int MT      = round16(B);
+    const int qkv_dim = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
+    const int es      = 2;
+    const int L       = c.num_layers;
+    void*     o_buf   = m->o_x ? m->o_x : m->o;
+
+    TRY(b200_embedding_lookup(m->residual, m->embedding, in->token_ids, B, c.hidden, c.embedding_rows, c.dtype, stream));
+    TRY(b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, B, c.hidden, c.norm_eps, c.dtype, stream));
+    TRY(b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
+
+    for (int l = 0; l < L; ++l) {
+        const LayerW& W = m->layers[l];
+        if (!W.qkv.prepared || !W.wo.prepared || !W.w13.prepared || !W.w2.prepared || !W.attn_norm || !W.ffn_norm) {
+            return fail(B200_ERR_STATE, "decode_step: layer weights not set");
+        }
+        // ---- attention block ----
+        TRY(b200_linear_forward_packed(&W.qkv, m->xp, MT, B, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        b200_attention_params a{};
+        a.out    = m->attn_xp;
+        a.q      = m->qkv;
+        a.k      = (char*)m->qkv + (size_t)c.num_heads * c.head_dim * es;
+        a.v      = (char*)m->qkv + (size_t)(c.num_heads + c.num_kv_heads) * c.head_dim * es;
+        a.stride = qkv_dim;
+        a.cu_q_len = in->cu_q_len, a.cu_k_len = in->cu_k_len, a.finished = in->finished;
+        a.block_ptrs = in->block_ptrs, a.cu_block_nums = in->cu_block_nums;
+        a.layer_offset = l * in->layer_stride_bytes, a.block_len = c.block_len;
+        a.token_num = B, a.batch_size = B, a.max_k_len = in->max_k_len;
+        a.num_heads = c.num_heads, a.num_kv_heads = c.num_kv_heads, a.size_per_head = c.head_dim;
+        a.inv_sqrt_dh = c.inv_sqrt_dh, a.window_size = 0;
+        a.rope = c.rope, a.quant_policy = c.quant_policy, a.dtype = c.dtype;
+        a.workspace = m->attn_ws, a.workspace_bytes = m->attn_ws_bytes;
+        a.plan = m->plan, a.out_packed_mt = MT, a.stream = stream;
+        TRY(b200_decode_attention(&a));
+        TRY(b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        // AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287)
+        if (m->comm) {
+            TRY(b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
+                                                     c.hidden, c.norm_eps, c.dtype, stream));
+        }
+        else {
+            TRY(b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
+                                      c.dtype, stream));
+        }
+        // ---- FFN block ----
+        TRY(b200_linear_forward_packed(&W.w13, m->xp, MT, B, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
+                                       stream));
+        TRY(b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        const void* next_norm = (l + 1 < L) ? m->layers[l + 1].attn_norm : m->final_norm;
+        if (m->comm) {
+            TRY(b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, next_norm, nullptr, B,
+                                                     c.hidden, c.norm_eps, c.dtype, stream));
+        }
+        else {
+            TRY(b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
+                                      stream));
+        }
+    }
+    // PostEmbedding (language_model.cc:285-335) + greedy sampling
+    TRY(b200_linear_forward_packed(&m->lm_head, m->xp, MT, B, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
+                                   stream));
+    if (in->out_tokens) {
+        if (m->comm && c.tp_size > 1) {
+            TRY(b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, B, c.vocab, c.dtype, stream));
+        }
+        else {
+            TRY(b200_argmax(in->out_tokens, m->logits, B, c.vocab, c.vocab, c.dtype, stream));
+        }
+    }
+    if (in->advance) {
+        TRY(b200_step_advance(in->token_ids, in->out_tokens, (int*)in->cu_k_len, in->finished, B, stream));
+    }
+    return 0;
+}

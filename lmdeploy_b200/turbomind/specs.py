@@ -1,0 +1,35 @@
+"""Model geometries on the hot path (public HF configs of these models --
+lmdeploy/turbomind/models/internlm2.py:70-84, models/llama.py:44-99 read the same fields)."""
+from dataclasses import dataclass, replace
+
+
+@dataclass(frozen=True)
+class ModelSpec:
+    name: str
+    arch: str                 # 'internlm2' | 'llama'
+    hidden: int
+    layers: int
+    heads: int
+    kv_heads: int
+    inter: int
+    vocab: int
+    rope_theta: float
+    head_dim: int = 128
+    norm_eps: float = 1e-5
+    rope_type: str = "default"      # 'default' | 'llama3'
+    rope_factor: float = 0.0
+    weight_format: str = "awq"      # 'awq' (u4 g128) | 'fp16' | 'fp8'
+    dtype: str = "f16"
+
+    def tiny(self, layers=2):
+        return replace(self, layers=layers)
+
+
+SPECS = {
+    "internlm2-1.8b": ModelSpec("internlm2-1.8b", "internlm2", 2048, 24, 16, 8, 8192, 92544, 1e6, weight_format="fp16"),
+    "internlm2-7b": ModelSpec("internlm2-7b", "internlm2", 4096, 32, 32, 8, 14336, 92544, 1e6),
+    "internlm2-20b": ModelSpec("internlm2-20b", "internlm2", 6144, 48, 48, 8, 16384, 92544, 1e6),
+    "llama3-8b": ModelSpec("llama3-8b", "llama", 4096, 32, 32, 8, 14336, 128256, 5e5, weight_format="fp16"),
+    "llama3-70b": ModelSpec("llama3-70b", "llama", 8192, 80, 64, 8, 28672, 128256, 5e5, weight_format="fp8",
+                            dtype="bf16"),
+}

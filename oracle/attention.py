@@ -162,13 +162,13 @@ def apply_rope(x, pos, rope: RopeParam, dtype):
     c = f32(c * kp["attention_scaling"])
     cT, sT = rn(c, dtype), rn(s, dtype)
     x = f32(x)
-    x0, x1 = x[..., 0::2], x[..., 1::2]
+    nd = rope.dim
+    x0, x1 = x[..., 0:nd:2], x[..., 1:nd:2]
     y0 = t_sub(t_mul(cT, x0, dtype), t_mul(sT, x1, dtype), dtype)
     y1 = t_add(t_mul(cT, x1, dtype), t_mul(sT, x0, dtype), dtype)
     out = x.copy()
-    nd = rope.dim
-    out[..., 0:nd:2] = y0[..., : nd // 2]
-    out[..., 1:nd:2] = y1[..., : nd // 2]
+    out[..., 0:nd:2] = y0
+    out[..., 1:nd:2] = y1
     return out
 
 

@@ -1,0 +1,111 @@
+"""CPU oracle: one full decode step of a TurboMind llama-family model (test infrastructure only).
+
+Layer order follows UnifiedDecoder::Forward (src/turbomind/models/llama/unified_decoder.cc:226-346):
+  x = RMSNorm(residual; attention_norm[0])
+  per layer:  qkv = x.Wqkv ; attn = decode_attention(qkv) ; o = attn.Wo
+              residual += o ; x = RMSNorm(residual; ffn_norm)            (AllreduceResidualRMSnorm #1)
+              a = gated_silu(x.W13) ; f = a.W2
+              residual += f ; x = RMSNorm(residual; next attention_norm | final norm)   (#2)
+  logits = x.Wout ; token = argmax(float(logits))   (language_model.cc:285-335, generation.cc:270-276)
+TP (tensor parallel) variant: heads / inter / vocab sharded, partial o / f summed over ranks in rank order in T
+(comm/cuda_ipc/fused_allreduce.cu:25-167 pull variant), logits concatenated.
+"""
+import numpy as np
+
+from . import attention as OA
+from . import linear as OL
+from .numerics import F16, rn, f32
+
+
+class TinyWeights:
+    """Random weights of a small llama-family model in TurboMind's loader-visible layout."""
+
+    def __init__(self, *, hidden, layers, heads, kv_heads, inter, vocab, fmt="awq", dtype=F16, seed=0, head_dim=128):
+        rng = np.random.default_rng(seed)
+        self.hidden, self.layers, self.heads, self.kv_heads = hidden, layers, heads, kv_heads
+        self.inter, self.vocab, self.fmt, self.dtype, self.D = inter, vocab, fmt, dtype, head_dim
+        D = head_dim
+
+        def lin(K, N):
+            w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+            if fmt == "awq":
+                q, s, z = OL.quantize_groupwise_u4(w, 128)
+                return dict(q=q, scales=s, zeros=z, deq=OL.dequant_u4(q, s, z, dtype))
+            w = rn(w, dtype)
+            return dict(w=w, deq=w)
+
+        self.embed = rn((rng.standard_normal((vocab, hidden)) * 0.5).astype(np.float32), dtype)
+        self.final_norm = rn((1 + 0.02 * rng.standard_normal(hidden)).astype(np.float32), dtype)
+        self.L = []
+        for _ in range(layers):
+            self.L.append(dict(
+                attn_norm=rn((1 + 0.02 * rng.standard_normal(hidden)).astype(np.float32), dtype),
+                ffn_norm=rn((1 + 0.02 * rng.standard_normal(hidden)).astype(np.float32), dtype),
+                w_qkv=lin(hidden, (heads + 2 * kv_heads) * D), wo=lin(heads * D, hidden),
+                w1w3=lin(hidden, 2 * inter), w2=lin(inter, hidden)))
+        out = rn((rng.standard_normal((hidden, vocab)) * 0.1 / np.sqrt(hidden)).astype(np.float32), dtype)
+        self.output = dict(w=out, deq=out)
+
+    # ---- TP shard of the loader-visible tensors (builders/_base.py:102-113, attention.py:65-76, ffn.py:238-243)
+    def shard(self, rank, tp):
+        D, Hq, Hkv = self.D, self.heads // tp, self.kv_heads // tp
+        I = self.inter // tp
+
+        def cols(x, idx):
+            return {k: (v[:, idx] if k in ("q", "deq", "w") else v[:, idx] if v.ndim == 2 else v) for k, v in x.items()}
+
+        def rows(x, sl):
+            out = {}
+            for k, v in x.items():
+                if k in ("q", "deq", "w"):
+                    out[k] = v[sl]
+                else:   # scales / zeros [K/128, N]
+                    out[k] = v[sl.start // 128: sl.stop // 128]
+            return out
+
+        sh = TinyWeights.__new__(TinyWeights)
+        sh.__dict__.update({k: v for k, v in self.__dict__.items() if k != "L"})
+        sh.heads, sh.kv_heads, sh.inter = Hq, Hkv, I
+        sh.vocab_local = self.vocab // tp
+        sh.L = []
+        for lw in self.L:
+            qi = np.arange(rank * Hq * D, (rank + 1) * Hq * D)
+            ki = self.heads * D + np.arange(rank * Hkv * D, (rank + 1) * Hkv * D)
+            vi = (self.heads + self.kv_heads) * D + np.arange(rank * Hkv * D, (rank + 1) * Hkv * D)
+            gu = np.arange(rank * 2 * I, (rank + 1) * 2 * I)      # interleaved (gate, up) pairs stay together
+            sh.L.append(dict(attn_norm=lw["attn_norm"], ffn_norm=lw["ffn_norm"],
+                             w_qkv=cols(lw["w_qkv"], np.concatenate([qi, ki, vi])),
+                             wo=rows(lw["wo"], slice(rank * Hq * D, (rank + 1) * Hq * D)),
+                             w1w3=cols(lw["w1w3"], gu),
+                             w2=rows(lw["w2"], slice(rank * I, (rank + 1) * I))))
+        vs = slice(rank * sh.vocab_local, (rank + 1) * sh.vocab_local)
+        sh.output = {k: v[:, vs] for k, v in self.output.items()}
+        return sh
+
+
+def decode_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables, hist, rope, eps=1e-5, tp_shards=None,
+                caches=None):
+    """Returns (logits [B, vocab] float32 exact in T, tokens [B]).  Mutates cache(s).
+    tp_shards: list of sharded TinyWeights (one per rank) with per-rank `caches` -> TP semantics."""
+    dtype = w.dtype
+    residual = w.embed[np.asarray(token_ids)]
+    shards = tp_shards if tp_shards else [w]
+    kvc = caches if caches else [cache]
+    x = OL.rmsnorm(residual, w.L[0]["attn_norm"], eps, dtype)
+    for l in range(w.layers):
+        parts = []
+        for r, sw in enumerate(shards):
+            lw = sw.L[l]
+            qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+            attn = OA.decode_attention(qkv, kvc[r], block_tables, hist, l, sw.heads, sw.kv_heads, rope)
+            parts.append(OL.linear(attn, lw["wo"]["deq"], dtype))
+        x, residual = OL.allreduce_residual_rmsnorm(parts, residual, w.L[l]["ffn_norm"], eps, dtype)
+        parts = []
+        for r, sw in enumerate(shards):
+            lw = sw.L[l]
+            a = OL.linear_gated_silu(x, lw["w1w3"]["deq"], dtype)
+            parts.append(OL.linear(a, lw["w2"]["deq"], dtype))
+        nxt = w.L[l + 1]["attn_norm"] if l + 1 < w.layers else w.final_norm
+        x, residual = OL.allreduce_residual_rmsnorm(parts, residual, nxt, eps, dtype)
+    logits = np.concatenate([OL.linear(x, sw.output["deq"], dtype) for sw in shards], axis=1)
+    return logits, logits.argmax(-1)
