@@ -1,0 +1,45 @@
+"""pipeline(): the user entry point, same shape as lmdeploy.pipeline (lmdeploy/api.py:15-82, pipeline.py:33-95)."""
+from typing import List, Optional, Union
+
+from .messages import GenerationConfig, Response, TurbomindEngineConfig
+from .turbomind.engine import TurboMind, batched_generate
+
+
+class Pipeline:
+    def __init__(self, model_path: str, backend_config: Optional[TurbomindEngineConfig] = None, tokenizer=None, **kw):
+        self.backend_config = backend_config or TurbomindEngineConfig()
+        self.engine = TurboMind.from_pretrained(model_path, self.backend_config, **kw)
+        self.tokenizer = tokenizer
+        if tokenizer is None:
+            import os
+            if os.path.isdir(model_path) and os.path.exists(os.path.join(model_path, "tokenizer.json")):
+                from transformers import AutoTokenizer
+                self.tokenizer = AutoTokenizer.from_pretrained(model_path)
+
+    def _encode(self, prompt):
+        if isinstance(prompt, (list, tuple)):
+            return list(prompt)
+        if self.tokenizer is None:
+            raise ValueError("no tokenizer: pass prompts as lists of token ids")
+        return self.tokenizer.encode(prompt)
+
+    def __call__(self, prompts: Union[str, List[int], List[str], List[List[int]]],
+                 gen_config: Optional[GenerationConfig] = None, **kw):
+        single = isinstance(prompts, str) or (isinstance(prompts, (list, tuple)) and prompts
+                                              and isinstance(prompts[0], int))
+        plist = [prompts] if single else list(prompts)
+        ids = [self._encode(p) for p in plist]
+        seqs = batched_generate(self.engine, ids, gen_config)
+        out = []
+        for i, s in enumerate(seqs):
+            text = self.tokenizer.decode(s.generated) if self.tokenizer is not None else ""
+            out.append(Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
+                                finish_reason=s.finish_reason, token_ids=list(s.generated), index=i))
+        return out[0] if single else out
+
+    def close(self):
+        self.engine = None
+
+
+def pipeline(model_path: str, backend_config: Optional[TurbomindEngineConfig] = None, **kw) -> Pipeline:
+    return Pipeline(model_path, backend_config, **kw)

@@ -162,6 +162,250 @@ struct SharedStorage {
     uint64_t empty[STAGES];
 };
 
+// swizzled index into the [head][128] fp32 merge rows: keeps (d, d+1) pairs adjacent and spreads the 16 lanes of
+// a half-warp over 16 distinct 8-byte slots (bank-conflict-free 64-bit accesses in the segment merge)
+B200_DEVICE int merge_idx(int hd, int d)
+{
+    return hd * kHeadDim + (d ^ ((((d >> 5) & 3) << 1) | ((hd >> 1) << 3)));
+}
+
+template<class T, int KVBITS>
+struct ConsumerCtx {
+    int      warp, g, t;
+    int      tokA, tokB, tokV0, tokV1, tokV2, tokV3;
+    uint32_t offA, offB, offV0, offV1, offV2, offV3;
+};
+
+// one 64-token tile: this warp's 16 keys.  `st` = shared address of the stage.
+template<class T, int KVBITS>
+B200_DEVICE void process_tile(const ConsumerCtx<T, KVBITS>& cx, uint32_t st, bool residue, int k_len, int t0, float c,
+                              const uint32_t (&qf)[8][2], float (&O)[8][4], float (&M)[2], float (&L)[2])
+{
+    using Ops = TypeOps<T>;
+    using Cfg = TileCfg<KVBITS>;
+    const int g = cx.g, t = cx.t;
+    const int tokA = cx.tokA, tokB = cx.tokB, tokV0 = cx.tokV0, tokV1 = cx.tokV1, tokV2 = cx.tokV2, tokV3 = cx.tokV3;
+    const uint32_t offA = cx.offA, offB = cx.offB, offV0 = cx.offV0, offV1 = cx.offV1, offV2 = cx.offV2, offV3 = cx.offV3;
+    // ------------------------------ S = K . Q^T ------------------------------
+    float S[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (KVBITS == 8) {
+        const uint32_t pA  = lds32(st + Cfg::kOffKP + tokA * 4);
+        const uint32_t pB  = lds32(st + Cfg::kOffKP + tokB * 4);
+        const uint32_t sA2 = __byte_perm(pA, pA, 0x1010), zA2 = __byte_perm(pA, pA, 0x3232);
+        const uint32_t sB2 = __byte_perm(pB, pB, 0x1010), zB2 = __byte_perm(pB, pB, 0x3232);
+        uint4          ka[2], kb[2];
+        ka[0] = lds128(st + Cfg::kOffK + offA + 16 * t);
+        ka[1] = lds128(st + Cfg::kOffK + offA + 16 * (t + 4));
+        kb[0] = lds128(st + Cfg::kOffK + offB + 16 * t);
+        kb[1] = lds128(st + Cfg::kOffK + offB + 16 * (t + 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t ua = (&ka[j >> 2].x)[j & 3];
+            const uint32_t ub = (&kb[j >> 2].x)[j & 3];
+            uint32_t       a[4];
+            Ops::cvt_u8x4(ua, a[0], a[2]);
+            Ops::cvt_u8x4(ub, a[1], a[3]);
+            a[0] = Ops::fma2(a[0], sA2, zA2);
+            a[2] = Ops::fma2(a[2], sA2, zA2);
+            a[1] = Ops::fma2(a[1], sB2, zB2);
+            a[3] = Ops::fma2(a[3], sB2, zB2);
+            Ops::mma16816(S, a, qf[j]);
+        }
+    }
+    else if constexpr (KVBITS == 4) {
+        const uint32_t pA  = lds32(st + Cfg::kOffKP + tokA * 4);
+        const uint32_t pB  = lds32(st + Cfg::kOffKP + tokB * 4);
+        const uint32_t sA2 = __byte_perm(pA, pA, 0x1010), zA2 = __byte_perm(pA, pA, 0x3232);
+        const uint32_t sB2 = __byte_perm(pB, pB, 0x1010), zB2 = __byte_perm(pB, pB, 0x3232);
+        const uint4    ka  = lds128(st + Cfg::kOffK + offA + 16 * t);
+        const uint4    kb  = lds128(st + Cfg::kOffK + offB + 16 * t);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t ha[4], hb[4];
+            Ops::cvt_u4x8((&ka.x)[i], ha);
+            Ops::cvt_u4x8((&kb.x)[i], hb);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                ha[x] = Ops::fma2(ha[x], sA2, zA2);
+                hb[x] = Ops::fma2(hb[x], sB2, zB2);
+            }
+            // u32 i covers dims 8i..8i+7 of this lane's chunk: k-steps 2i (dims 0-3) and 2i+1 (dims 4-7)
+            uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]};
+            uint32_t a1[4] = {ha[2], hb[2], ha[3], hb[3]};
+            Ops::mma16816(S, a0, qf[2 * i]);
+            Ops::mma16816(S, a1, qf[2 * i + 1]);
+        }
+    }
+    else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint4 ka = lds128(st + Cfg::kOffK + offA + 16 * (t + 4 * i));
+            const uint4 kb = lds128(st + Cfg::kOffK + offB + 16 * (t + 4 * i));
+            uint32_t    a0[4] = {ka.x, kb.x, ka.y, kb.y};
+            uint32_t    a1[4] = {ka.z, kb.z, ka.w, kb.w};
+            Ops::mma16816(S, a0, qf[2 * i]);
+            Ops::mma16816(S, a1, qf[2 * i + 1]);
+        }
+    }
+
+    // ------------------------------ online softmax ------------------------------
+    // S[0],S[1]: row g (tokA) heads 2t,2t+1;  S[2],S[3]: row g+8 (tokB)
+    const bool maskA = residue && (t0 + tokA >= k_len);
+    const bool maskB = residue && (t0 + tokB >= k_len);
+    if (maskA) {
+        S[0] = S[1] = -INFINITY;
+    }
+    if (maskB) {
+        S[2] = S[3] = -INFINITY;
+    }
+    float mx[2] = {fmaxf(S[0], S[2]), fmaxf(S[1], S[3])};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 4));
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 8));
+        mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 16));
+    }
+    float newM[2] = {fmaxf(M[0], mx[0]), fmaxf(M[1], mx[1])};
+    // a whole 16-key slice can only be fully masked in a residue tile
+    const bool dead0 = newM[0] == -INFINITY, dead1 = newM[1] == -INFINITY;
+    if (newM[0] != M[0] || newM[1] != M[1]) {
+        const float r0 = dead0 ? 1.f : exp2_approx((M[0] - newM[0]) * c);
+        const float r1 = dead1 ? 1.f : exp2_approx((M[1] - newM[1]) * c);
+        L[0] *= r0;
+        L[1] *= r1;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            O[j][0] *= r0;
+            O[j][1] *= r1;
+            O[j][2] *= r0;
+            O[j][3] *= r1;
+        }
+        M[0] = newM[0];
+        M[1] = newM[1];
+    }
+    const float mc0 = dead0 ? 0.f : M[0] * c, mc1 = dead1 ? 0.f : M[1] * c;
+    float       P[4];
+    P[0] = exp2_approx(fmaf(S[0], c, -mc0));
+    P[1] = exp2_approx(fmaf(S[1], c, -mc1));
+    P[2] = exp2_approx(fmaf(S[2], c, -mc0));
+    P[3] = exp2_approx(fmaf(S[3], c, -mc1));
+    L[0] += P[0] + P[2];  // per-lane partial row sums; reduced across g at segment end
+    L[1] += P[1] + P[3];
+
+    uint32_t pf[2];
+    pf[0] = transpose_8x8_b16(Ops::pack2(P[0], P[1]));  // k-slots 2t,2t+1 ; head g
+    pf[1] = transpose_8x8_b16(Ops::pack2(P[2], P[3]));  // k-slots 2t+8,2t+9 ; head g
+
+    // ------------------------------ O^T += V^T . P ------------------------------
+    if constexpr (KVBITS == 8) {
+        uint32_t p0 = lds32(st + Cfg::kOffVP + tokV0 * 4), p1 = lds32(st + Cfg::kOffVP + tokV1 * 4);
+        uint32_t p2 = lds32(st + Cfg::kOffVP + tokV2 * 4), p3 = lds32(st + Cfg::kOffVP + tokV3 * 4);
+        if (residue) {
+            if (t0 + tokV0 >= k_len) p0 = 0;
+            if (t0 + tokV1 >= k_len) p1 = 0;
+            if (t0 + tokV2 >= k_len) p2 = 0;
+            if (t0 + tokV3 >= k_len) p3 = 0;
+        }
+        const uint32_t s01 = __byte_perm(p0, p1, 0x5410), z01 = __byte_perm(p0, p1, 0x7632);
+        const uint32_t s23 = __byte_perm(p2, p3, 0x5410), z23 = __byte_perm(p2, p3, 0x7632);
+        const uint4    v0 = lds128(st + Cfg::kOffV + offV0 + 16 * g), v1 = lds128(st + Cfg::kOffV + offV1 + 16 * g);
+        const uint4    v2 = lds128(st + Cfg::kOffV + offV2 + 16 * g), v3 = lds128(st + Cfg::kOffV + offV3 + 16 * g);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const uint32_t A = (&v0.x)[jj], Bq = (&v1.x)[jj], C = (&v2.x)[jj], Dq = (&v3.x)[jj];
+            const uint32_t X = __byte_perm(A, Bq, 0x5140), Y = __byte_perm(A, Bq, 0x7362);
+            const uint32_t X2 = __byte_perm(C, Dq, 0x5140), Y2 = __byte_perm(C, Dq, 0x7362);
+            uint32_t       a[4];
+            Ops::cvt_u8x4(X, a[0], a[1]);
+            Ops::cvt_u8x4(X2, a[2], a[3]);
+            a[0] = Ops::fma2(a[0], s01, z01);
+            a[1] = Ops::fma2(a[1], s01, z01);
+            a[2] = Ops::fma2(a[2], s23, z23);
+            a[3] = Ops::fma2(a[3], s23, z23);
+            Ops::mma16816(O[2 * jj], a, pf);
+            Ops::cvt_u8x4(Y, a[0], a[1]);
+            Ops::cvt_u8x4(Y2, a[2], a[3]);
+            a[0] = Ops::fma2(a[0], s01, z01);
+            a[1] = Ops::fma2(a[1], s01, z01);
+            a[2] = Ops::fma2(a[2], s23, z23);
+            a[3] = Ops::fma2(a[3], s23, z23);
+            Ops::mma16816(O[2 * jj + 1], a, pf);
+        }
+    }
+    else if constexpr (KVBITS == 4) {
+        uint32_t p0 = lds32(st + Cfg::kOffVP + tokV0 * 4), p1 = lds32(st + Cfg::kOffVP + tokV1 * 4);
+        uint32_t p2 = lds32(st + Cfg::kOffVP + tokV2 * 4), p3 = lds32(st + Cfg::kOffVP + tokV3 * 4);
+        if (residue) {
+            if (t0 + tokV0 >= k_len) p0 = 0;
+            if (t0 + tokV1 >= k_len) p1 = 0;
+            if (t0 + tokV2 >= k_len) p2 = 0;
+            if (t0 + tokV3 >= k_len) p3 = 0;
+        }
+        const uint32_t s01 = __byte_perm(p0, p1, 0x5410), z01 = __byte_perm(p0, p1, 0x7632);
+        const uint32_t s23 = __byte_perm(p2, p3, 0x5410), z23 = __byte_perm(p2, p3, 0x7632);
+        const uint2    v0 = lds64(st + Cfg::kOffV + offV0 + 8 * g), v1 = lds64(st + Cfg::kOffV + offV1 + 8 * g);
+        const uint2    v2 = lds64(st + Cfg::kOffV + offV2 + 8 * g), v3 = lds64(st + Cfg::kOffV + offV3 + 8 * g);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const uint32_t A = (&v0.x)[m], Bq = (&v1.x)[m], C = (&v2.x)[m], Dq = (&v3.x)[m];
+            // lo16 of a word: elements e0,e2,e4,e6 (nibbles 0-3); hi16: e1,e3,e5,e7
+            const uint32_t Ye = __byte_perm(A, Bq, 0x5410), Yo = __byte_perm(A, Bq, 0x7632);
+            const uint32_t Ze = __byte_perm(C, Dq, 0x5410), Zo = __byte_perm(C, Dq, 0x7632);
+            uint32_t       he[4], ho[4], ge[4], go[4];
+            Ops::cvt_u4x8(Ye, he);  // he[x] = (A.e(2x), B.e(2x))   [(n0,n4),(n1,n5),..] of Ye
+            Ops::cvt_u4x8(Yo, ho);  // ho[x] = (A.e(2x+1), B.e(2x+1))
+            Ops::cvt_u4x8(Ze, ge);
+            Ops::cvt_u4x8(Zo, go);
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                // element index inside the word: even -> 2x (m-slot g), odd -> 2x+1 (m-slot g+8)
+                uint32_t a[4];
+                a[0] = Ops::fma2(he[x], s01, z01);
+                a[1] = Ops::fma2(ho[x], s01, z01);
+                a[2] = Ops::fma2(ge[x], s23, z23);
+                a[3] = Ops::fma2(go[x], s23, z23);
+                Ops::mma16816(O[4 * m + x], a, pf);
+            }
+        }
+    }
+    else {
+        uint4 va[2], vb[2], vc[2], vd[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            va[i] = lds128(st + Cfg::kOffV + offV0 + 16 * (g + 8 * i));
+            vb[i] = lds128(st + Cfg::kOffV + offV1 + 16 * (g + 8 * i));
+            vc[i] = lds128(st + Cfg::kOffV + offV2 + 16 * (g + 8 * i));
+            vd[i] = lds128(st + Cfg::kOffV + offV3 + 16 * (g + 8 * i));
+        }
+        if (residue) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            if (t0 + tokV0 >= k_len) va[0] = va[1] = z;
+            if (t0 + tokV1 >= k_len) vb[0] = vb[1] = z;
+            if (t0 + tokV2 >= k_len) vc[0] = vc[1] = z;
+            if (t0 + tokV3 >= k_len) vd[0] = vd[1] = z;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t A = (&va[j >> 2].x)[j & 3], Bq = (&vb[j >> 2].x)[j & 3];
+            const uint32_t C = (&vc[j >> 2].x)[j & 3], Dq = (&vd[j >> 2].x)[j & 3];
+            uint32_t       a[4];
+            a[0] = __byte_perm(A, Bq, 0x5410);  // (dim 2j, keys 2t,2t+1)
+            a[1] = __byte_perm(A, Bq, 0x7632);  // (dim 2j+1, ...)
+            a[2] = __byte_perm(C, Dq, 0x5410);
+            a[3] = __byte_perm(C, Dq, 0x7632);
+            Ops::mma16816(O[j], a, pf);
+        }
+    }
+
+}
+
+struct TileDesc {
+    const char* blk;  // block base + layer offset
+    int         h;
+    int         bt;    // token offset of the tile inside the block
+    int         rows;  // valid tokens in the tile
+};
+
 template<class T, int KVBITS, int STAGES>
 __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const KernelParams p)
 {
@@ -193,68 +437,90 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
         return;
     }
 
-    WorkIter it{p.batch, Hkv, p.tile_prefix};
-    it.seek(lo);
+    const uint32_t full0  = smem_u32(&ss.full[0]);
+    const uint32_t empty0 = smem_u32(&ss.empty[0]);
+    const uint32_t stage0 = smem_u32(&ss.stage[0][0]);
 
     if (warp == kConsumerWarps) {
-        // ================================ producer ================================
-        if (lane == 0) {
-            const uint64_t policy         = make_evict_first_policy();
-            const int      head_data_size = p.block_len * Cfg::kRowBytes;
-            const int      head_param_sz  = p.block_len * 4;
-            int            n              = 0;
-            for (long long idx = lo; idx < hi; ++idx, ++n, it.next()) {
-                const int      s     = n % STAGES;
-                const uint32_t phase = (n / STAGES) & 1;
-                mbar_wait(smem_u32(&ss.empty[s]), phase ^ 1);
-
+        // ================================ producer warp ================================
+        // Tile descriptors (block pointer through the block table, valid rows) are fetched 32 at a time, one per
+        // lane, one batch AHEAD of the copies being issued, so the dependent global loads
+        // (cu_k_len -> cu_block_nums -> block_ptrs) never sit on the critical path of the TMA issue loop.
+        const uint64_t policy         = make_evict_first_policy();
+        const int      head_data_size = p.block_len * Cfg::kRowBytes;
+        const int      head_param_sz  = p.block_len * 4;
+        auto           fetch          = [&](long long base) {
+            TileDesc        d{nullptr, 0, 0, 0};
+            const long long idx = base + lane;
+            if (idx < hi) {
+                WorkIter it{p.batch, Hkv, p.tile_prefix};
+                it.seek(idx);
                 const int k_len = p.cu_k_len[it.b + 1] - p.cu_k_len[it.b];
                 const int t0    = it.tile * kTile;
-                const int rows  = min(kTile, k_len - t0);
-                const int bi    = t0 / p.block_len;
-                const int bt    = t0 % p.block_len;
-                const char* blk = p.block_ptrs[p.cu_block_nums[it.b] + bi] + p.layer_offset;
-                const char* kd  = blk + (size_t)(it.h * 2) * head_data_size + (size_t)bt * Cfg::kRowBytes;
-                const char* vd  = kd + head_data_size;
-
-                const int      prow  = (rows + 3) & ~3;
-                const uint32_t bytes = 2 * rows * Cfg::kRowBytes + (Cfg::kQuant ? 2 * prow * 4 : 0);
-                const uint32_t bar   = smem_u32(&ss.full[s]);
-                mbar_expect_tx(bar, bytes);
-                const uint32_t st = smem_u32(&ss.stage[s][0]);
+                d.rows          = min(kTile, k_len - t0);
+                d.h             = it.h;
+                d.bt            = t0 % p.block_len;
+                d.blk           = p.block_ptrs[p.cu_block_nums[it.b] + t0 / p.block_len] + p.layer_offset;
+            }
+            return d;
+        };
+        int      s  = 0;
+        uint32_t ph = 0;
+        TileDesc cur = fetch(lo);
+        for (long long base = lo; base < hi; base += 32) {
+            const TileDesc nxt = fetch(base + 32);
+            const int      cnt = (int)min((long long)32, hi - base);
+            for (int l = 0; l < cnt; ++l) {
+                if (lane == l) {
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const int   rows = cur.rows;
+                    const char* kd   = cur.blk + (size_t)(cur.h * 2) * head_data_size + (size_t)cur.bt * Cfg::kRowBytes;
+                    const char* vd   = kd + head_data_size;
+                    const int   prow = (rows + 3) & ~3;
+                    const uint32_t bytes = 2 * rows * Cfg::kRowBytes + (Cfg::kQuant ? 2 * prow * 4 : 0);
+                    const uint32_t bar   = full0 + 8 * s;
+                    mbar_expect_tx(bar, bytes);
+                    const uint32_t st = stage0 + s * (uint32_t)Cfg::kStageBytes;
 #pragma unroll
-                for (int gq = 0; gq < kTile / kGroupRows; ++gq) {
-                    const int r = min(kGroupRows, rows - gq * kGroupRows);
-                    if (r > 0) {
-                        const uint32_t nb = r * Cfg::kRowBytes;
-                        bulk_g2s_hint(st + Cfg::kOffK + gq * Cfg::kGroupSize,
-                                      kd + gq * kGroupRows * Cfg::kRowBytes, nb, bar, policy);
-                        bulk_g2s_hint(st + Cfg::kOffV + gq * Cfg::kGroupSize,
-                                      vd + gq * kGroupRows * Cfg::kRowBytes, nb, bar, policy);
+                    for (int gq = 0; gq < kTile / kGroupRows; ++gq) {
+                        const int r = min(kGroupRows, rows - gq * kGroupRows);
+                        if (r > 0) {
+                            const uint32_t nb = r * Cfg::kRowBytes;
+                            bulk_g2s_hint(st + Cfg::kOffK + gq * Cfg::kGroupSize, kd + gq * kGroupRows * Cfg::kRowBytes,
+                                          nb, bar, policy);
+                            bulk_g2s_hint(st + Cfg::kOffV + gq * Cfg::kGroupSize, vd + gq * kGroupRows * Cfg::kRowBytes,
+                                          nb, bar, policy);
+                        }
+                    }
+                    if constexpr (Cfg::kQuant) {
+                        const char* kp = cur.blk + (size_t)Hkv * 2 * head_data_size
+                                         + (size_t)(cur.h * 2) * head_param_sz + (size_t)cur.bt * 4;
+                        bulk_g2s_hint(st + Cfg::kOffKP, kp, prow * 4, bar, policy);
+                        bulk_g2s_hint(st + Cfg::kOffVP, kp + head_param_sz, prow * 4, bar, policy);
                     }
                 }
-                if constexpr (Cfg::kQuant) {
-                    const char* kp = blk + (size_t)Hkv * 2 * head_data_size + (size_t)(it.h * 2) * head_param_sz
-                                     + (size_t)bt * 4;
-                    bulk_g2s_hint(st + Cfg::kOffKP, kp, prow * 4, bar, policy);
-                    bulk_g2s_hint(st + Cfg::kOffVP, kp + head_param_sz, prow * 4, bar, policy);
+                if (++s == STAGES) {
+                    s = 0;
+                    ph ^= 1;
                 }
             }
+            cur = nxt;
         }
         return;
     }
 
     // ================================== consumers ==================================
-    const int g = lane >> 2;  // mma "group id"
-    const int t = lane & 3;   // thread-in-group
-
-    // tokens (inside a tile) of the S rows this lane owns, and of the P/V k-slots it owns
-    const int tokA = slot_token(g, warp), tokB = slot_token(g + 8, warp);
-    const int tokV0 = slot_token(2 * t, warp), tokV1 = slot_token(2 * t + 1, warp);
-    const int tokV2 = slot_token(2 * t + 8, warp), tokV3 = slot_token(2 * t + 9, warp);
-    const uint32_t offA = token_smem_offset<KVBITS>(tokA), offB = token_smem_offset<KVBITS>(tokB);
-    const uint32_t offV0 = token_smem_offset<KVBITS>(tokV0), offV1 = token_smem_offset<KVBITS>(tokV1);
-    const uint32_t offV2 = token_smem_offset<KVBITS>(tokV2), offV3 = token_smem_offset<KVBITS>(tokV3);
+    ConsumerCtx<T, KVBITS> cx;
+    cx.warp = warp;
+    cx.g    = lane >> 2;
+    cx.t    = lane & 3;
+    const int g = cx.g, t = cx.t;
+    cx.tokA = slot_token(g, warp), cx.tokB = slot_token(g + 8, warp);
+    cx.tokV0 = slot_token(2 * t, warp), cx.tokV1 = slot_token(2 * t + 1, warp);
+    cx.tokV2 = slot_token(2 * t + 8, warp), cx.tokV3 = slot_token(2 * t + 9, warp);
+    cx.offA = token_smem_offset<KVBITS>(cx.tokA), cx.offB = token_smem_offset<KVBITS>(cx.tokB);
+    cx.offV0 = token_smem_offset<KVBITS>(cx.tokV0), cx.offV1 = token_smem_offset<KVBITS>(cx.tokV1);
+    cx.offV2 = token_smem_offset<KVBITS>(cx.tokV2), cx.offV3 = token_smem_offset<KVBITS>(cx.tokV3);
 
     uint32_t qf[8][2];  // Q as B-operand fragments, one per k-step
     float    O[8][4];   // O^T accumulators: m-tile j -> {(slot g,head 2t),(g,2t+1),(g+8,2t),(g+8,2t+1)}
@@ -262,17 +528,18 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
 
     const float c = p.qk_scale;
 
-    int       n           = 0;
-    bool      seg_start   = true;
-    long long seg_lo_idx  = lo;
-    int       first_tile  = 0;
+    WorkIter it{p.batch, Hkv, p.tile_prefix};
+    it.seek(lo);
+    int       s   = 0;
+    uint32_t  ph  = 0;
+    long long idx = lo;
 
-    for (long long idx = lo; idx < hi; ++idx, ++n) {
-        if (seg_start) {
-            seg_start  = false;
-            seg_lo_idx = idx;
-            first_tile = it.tile;
-            // ---- load Q fragments for (b, kv-head) ----
+    while (idx < hi) {
+        // ---------------- one segment: tiles [first_tile, first_tile + ntile) of (it.b, it.h) ----------------
+        const int first_tile = it.tile;
+        const int ntile      = (int)min((long long)(it.tiles - it.tile), hi - idx);
+        const int k_len      = p.cu_k_len[it.b + 1] - p.cu_k_len[it.b];
+        {
             const T* qb = reinterpret_cast<const T*>(p.q_rot) + ((size_t)it.b * p.num_heads + (size_t)it.h * G) * kHeadDim;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -290,330 +557,114 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
             M[0] = M[1] = -INFINITY;
             L[0] = L[1] = 0.f;
         }
-
-        const int      s     = n % STAGES;
-        const uint32_t phase = (n / STAGES) & 1;
-        mbar_wait(smem_u32(&ss.full[s]), phase);
-
-        const uint32_t st    = smem_u32(&ss.stage[s][0]);
-        const int      k_len = p.cu_k_len[it.b + 1] - p.cu_k_len[it.b];
-        const int      t0    = it.tile * kTile;
-        const bool     residue = t0 + kTile > k_len;
-
-        // ------------------------------ S = K . Q^T ------------------------------
-        float S[4] = {0.f, 0.f, 0.f, 0.f};
-        if constexpr (KVBITS == 8) {
-            const uint32_t pA  = lds32(st + Cfg::kOffKP + tokA * 4);
-            const uint32_t pB  = lds32(st + Cfg::kOffKP + tokB * 4);
-            const uint32_t sA2 = __byte_perm(pA, pA, 0x1010), zA2 = __byte_perm(pA, pA, 0x3232);
-            const uint32_t sB2 = __byte_perm(pB, pB, 0x1010), zB2 = __byte_perm(pB, pB, 0x3232);
-            uint4          ka[2], kb[2];
-            ka[0] = lds128(st + Cfg::kOffK + offA + 16 * t);
-            ka[1] = lds128(st + Cfg::kOffK + offA + 16 * (t + 4));
-            kb[0] = lds128(st + Cfg::kOffK + offB + 16 * t);
-            kb[1] = lds128(st + Cfg::kOffK + offB + 16 * (t + 4));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t ua = (&ka[j >> 2].x)[j & 3];
-                const uint32_t ub = (&kb[j >> 2].x)[j & 3];
-                uint32_t       a[4];
-                Ops::cvt_u8x4(ua, a[0], a[2]);
-                Ops::cvt_u8x4(ub, a[1], a[3]);
-                a[0] = Ops::fma2(a[0], sA2, zA2);
-                a[2] = Ops::fma2(a[2], sA2, zA2);
-                a[1] = Ops::fma2(a[1], sB2, zB2);
-                a[3] = Ops::fma2(a[3], sB2, zB2);
-                Ops::mma16816(S, a, qf[j]);
+        for (int tt = 0; tt < ntile; ++tt) {
+            const int  t0      = (first_tile + tt) * kTile;
+            const bool residue = t0 + kTile > k_len;
+            mbar_wait(full0 + 8 * s, ph);
+            process_tile<T, KVBITS>(cx, stage0 + s * (uint32_t)Cfg::kStageBytes, residue, k_len, t0, c, qf, O, M, L);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(empty0 + 8 * s);
+            }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
             }
         }
-        else if constexpr (KVBITS == 4) {
-            const uint32_t pA  = lds32(st + Cfg::kOffKP + tokA * 4);
-            const uint32_t pB  = lds32(st + Cfg::kOffKP + tokB * 4);
-            const uint32_t sA2 = __byte_perm(pA, pA, 0x1010), zA2 = __byte_perm(pA, pA, 0x3232);
-            const uint32_t sB2 = __byte_perm(pB, pB, 0x1010), zB2 = __byte_perm(pB, pB, 0x3232);
-            const uint4    ka  = lds128(st + Cfg::kOffK + offA + 16 * t);
-            const uint4    kb  = lds128(st + Cfg::kOffK + offB + 16 * t);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t ha[4], hb[4];
-                Ops::cvt_u4x8((&ka.x)[i], ha);
-                Ops::cvt_u4x8((&kb.x)[i], hb);
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    ha[x] = Ops::fma2(ha[x], sA2, zA2);
-                    hb[x] = Ops::fma2(hb[x], sB2, zB2);
-                }
-                // u32 i covers dims 8i..8i+7 of this lane's chunk: k-steps 2i (dims 0-3) and 2i+1 (dims 4-7)
-                uint32_t a0[4] = {ha[0], hb[0], ha[1], hb[1]};
-                uint32_t a1[4] = {ha[2], hb[2], ha[3], hb[3]};
-                Ops::mma16816(S, a0, qf[2 * i]);
-                Ops::mma16816(S, a1, qf[2 * i + 1]);
-            }
-        }
-        else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint4 ka = lds128(st + Cfg::kOffK + offA + 16 * (t + 4 * i));
-                const uint4 kb = lds128(st + Cfg::kOffK + offB + 16 * (t + 4 * i));
-                uint32_t    a0[4] = {ka.x, kb.x, ka.y, kb.y};
-                uint32_t    a1[4] = {ka.z, kb.z, ka.w, kb.w};
-                Ops::mma16816(S, a0, qf[2 * i]);
-                Ops::mma16816(S, a1, qf[2 * i + 1]);
-            }
-        }
+        const bool last_tile = first_tile + ntile == it.tiles;
 
-        // ------------------------------ online softmax ------------------------------
-        // S[0],S[1]: row g (tokA) heads 2t,2t+1;  S[2],S[3]: row g+8 (tokB)
-        const bool maskA = residue && (t0 + tokA >= k_len);
-        const bool maskB = residue && (t0 + tokB >= k_len);
-        if (maskA) {
-            S[0] = S[1] = -INFINITY;
-        }
-        if (maskB) {
-            S[2] = S[3] = -INFINITY;
-        }
-        float mx[2] = {fmaxf(S[0], S[2]), fmaxf(S[1], S[3])};
+        // ---------------- segment end: merge the 4 consumer warps, write final or partial ----------------
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 4));
-            mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 8));
-            mx[q] = fmaxf(mx[q], __shfl_xor_sync(0xffffffffu, mx[q], 16));
+            L[q] += __shfl_xor_sync(0xffffffffu, L[q], 4);
+            L[q] += __shfl_xor_sync(0xffffffffu, L[q], 8);
+            L[q] += __shfl_xor_sync(0xffffffffu, L[q], 16);
         }
-        float newM[2] = {fmaxf(M[0], mx[0]), fmaxf(M[1], mx[1])};
-        // a whole 16-key slice can only be fully masked in a residue tile
-        const bool dead0 = newM[0] == -INFINITY, dead1 = newM[1] == -INFINITY;
-        if (newM[0] != M[0] || newM[1] != M[1]) {
-            const float r0 = dead0 ? 1.f : exp2_approx((M[0] - newM[0]) * c);
-            const float r1 = dead1 ? 1.f : exp2_approx((M[1] - newM[1]) * c);
-            L[0] *= r0;
-            L[1] *= r1;
+        if (g == 0) {
+            ss.merge_M[warp][2 * t]     = M[0];
+            ss.merge_M[warp][2 * t + 1] = M[1];
+            ss.merge_L[warp][2 * t]     = L[0];
+            ss.merge_L[warp][2 * t + 1] = L[1];
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+        float sc[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int hd = 2 * t + q;
+            float     m  = ss.merge_M[0][hd];
+            for (int w = 1; w < kConsumerWarps; ++w) m = fmaxf(m, ss.merge_M[w][hd]);
+            float l = 0.f;
+            for (int w = 0; w < kConsumerWarps; ++w) {
+                const float mw = ss.merge_M[w][hd];
+                l += (mw == -INFINITY) ? 0.f : exp2_approx((mw - m) * c) * ss.merge_L[w][hd];
+            }
+            sc[q] = (M[q] == -INFINITY) ? 0.f : exp2_approx((M[q] - m) * c);
+            if (warp == 0 && g == 0) {
+                ss.final_M[hd] = m;
+                ss.final_L[hd] = l;
+            }
+        }
+        // fixed order (w0 + w2) + (w1 + w3)
+        float* mo = &ss.merge_O[warp & 1][0][0];
+        if (warp < 2) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                O[j][0] *= r0;
-                O[j][1] *= r1;
-                O[j][2] *= r0;
-                O[j][3] *= r1;
-            }
-            M[0] = newM[0];
-            M[1] = newM[1];
-        }
-        const float mc0 = dead0 ? 0.f : M[0] * c, mc1 = dead1 ? 0.f : M[1] * c;
-        float       P[4];
-        P[0] = exp2_approx(fmaf(S[0], c, -mc0));
-        P[1] = exp2_approx(fmaf(S[1], c, -mc1));
-        P[2] = exp2_approx(fmaf(S[2], c, -mc0));
-        P[3] = exp2_approx(fmaf(S[3], c, -mc1));
-        L[0] += P[0] + P[2];  // per-lane partial row sums; reduced across g at segment end
-        L[1] += P[1] + P[3];
-
-        uint32_t pf[2];
-        pf[0] = transpose_8x8_b16(Ops::pack2(P[0], P[1]));  // k-slots 2t,2t+1 ; head g
-        pf[1] = transpose_8x8_b16(Ops::pack2(P[2], P[3]));  // k-slots 2t+8,2t+9 ; head g
-
-        // ------------------------------ O^T += V^T . P ------------------------------
-        if constexpr (KVBITS == 8) {
-            uint32_t p0 = lds32(st + Cfg::kOffVP + tokV0 * 4), p1 = lds32(st + Cfg::kOffVP + tokV1 * 4);
-            uint32_t p2 = lds32(st + Cfg::kOffVP + tokV2 * 4), p3 = lds32(st + Cfg::kOffVP + tokV3 * 4);
-            if (residue) {
-                if (t0 + tokV0 >= k_len) p0 = 0;
-                if (t0 + tokV1 >= k_len) p1 = 0;
-                if (t0 + tokV2 >= k_len) p2 = 0;
-                if (t0 + tokV3 >= k_len) p3 = 0;
-            }
-            const uint32_t s01 = __byte_perm(p0, p1, 0x5410), z01 = __byte_perm(p0, p1, 0x7632);
-            const uint32_t s23 = __byte_perm(p2, p3, 0x5410), z23 = __byte_perm(p2, p3, 0x7632);
-            const uint4    v0 = lds128(st + Cfg::kOffV + offV0 + 16 * g), v1 = lds128(st + Cfg::kOffV + offV1 + 16 * g);
-            const uint4    v2 = lds128(st + Cfg::kOffV + offV2 + 16 * g), v3 = lds128(st + Cfg::kOffV + offV3 + 16 * g);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t A = (&v0.x)[jj], Bq = (&v1.x)[jj], C = (&v2.x)[jj], Dq = (&v3.x)[jj];
-                const uint32_t X = __byte_perm(A, Bq, 0x5140), Y = __byte_perm(A, Bq, 0x7362);
-                const uint32_t X2 = __byte_perm(C, Dq, 0x5140), Y2 = __byte_perm(C, Dq, 0x7362);
-                uint32_t       a[4];
-                Ops::cvt_u8x4(X, a[0], a[1]);
-                Ops::cvt_u8x4(X2, a[2], a[3]);
-                a[0] = Ops::fma2(a[0], s01, z01);
-                a[1] = Ops::fma2(a[1], s01, z01);
-                a[2] = Ops::fma2(a[2], s23, z23);
-                a[3] = Ops::fma2(a[3], s23, z23);
-                Ops::mma16816(O[2 * jj], a, pf);
-                Ops::cvt_u8x4(Y, a[0], a[1]);
-                Ops::cvt_u8x4(Y2, a[2], a[3]);
-                a[0] = Ops::fma2(a[0], s01, z01);
-                a[1] = Ops::fma2(a[1], s01, z01);
-                a[2] = Ops::fma2(a[2], s23, z23);
-                a[3] = Ops::fma2(a[3], s23, z23);
-                Ops::mma16816(O[2 * jj + 1], a, pf);
+                const int d = pv_dim<KVBITS>(g, j, 0);
+                *reinterpret_cast<float2*>(mo + merge_idx(2 * t, d))     = make_float2(O[j][0] * sc[0], O[j][2] * sc[0]);
+                *reinterpret_cast<float2*>(mo + merge_idx(2 * t + 1, d)) = make_float2(O[j][1] * sc[1], O[j][3] * sc[1]);
             }
         }
-        else if constexpr (KVBITS == 4) {
-            uint32_t p0 = lds32(st + Cfg::kOffVP + tokV0 * 4), p1 = lds32(st + Cfg::kOffVP + tokV1 * 4);
-            uint32_t p2 = lds32(st + Cfg::kOffVP + tokV2 * 4), p3 = lds32(st + Cfg::kOffVP + tokV3 * 4);
-            if (residue) {
-                if (t0 + tokV0 >= k_len) p0 = 0;
-                if (t0 + tokV1 >= k_len) p1 = 0;
-                if (t0 + tokV2 >= k_len) p2 = 0;
-                if (t0 + tokV3 >= k_len) p3 = 0;
+        named_bar_sync(1, kConsumerWarps * 32);
+        if (warp >= 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int d  = pv_dim<KVBITS>(g, j, 0);
+                float2*   a0 = reinterpret_cast<float2*>(mo + merge_idx(2 * t, d));
+                float2*   a1 = reinterpret_cast<float2*>(mo + merge_idx(2 * t + 1, d));
+                float2    x0 = *a0, x1 = *a1;
+                x0.x += O[j][0] * sc[0], x0.y += O[j][2] * sc[0];
+                x1.x += O[j][1] * sc[1], x1.y += O[j][3] * sc[1];
+                *a0 = x0, *a1 = x1;
             }
-            const uint32_t s01 = __byte_perm(p0, p1, 0x5410), z01 = __byte_perm(p0, p1, 0x7632);
-            const uint32_t s23 = __byte_perm(p2, p3, 0x5410), z23 = __byte_perm(p2, p3, 0x7632);
-            const uint2    v0 = lds64(st + Cfg::kOffV + offV0 + 8 * g), v1 = lds64(st + Cfg::kOffV + offV1 + 8 * g);
-            const uint2    v2 = lds64(st + Cfg::kOffV + offV2 + 8 * g), v3 = lds64(st + Cfg::kOffV + offV3 + 8 * g);
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const uint32_t A = (&v0.x)[m], Bq = (&v1.x)[m], C = (&v2.x)[m], Dq = (&v3.x)[m];
-                // lo16 of a word: elements e0,e2,e4,e6 (nibbles 0-3); hi16: e1,e3,e5,e7
-                const uint32_t Ye = __byte_perm(A, Bq, 0x5410), Yo = __byte_perm(A, Bq, 0x7632);
-                const uint32_t Ze = __byte_perm(C, Dq, 0x5410), Zo = __byte_perm(C, Dq, 0x7632);
-                uint32_t       he[4], ho[4], ge[4], go[4];
-                Ops::cvt_u4x8(Ye, he);  // he[x] = (A.e(2x), B.e(2x))   [(n0,n4),(n1,n5),..] of Ye
-                Ops::cvt_u4x8(Yo, ho);  // ho[x] = (A.e(2x+1), B.e(2x+1))
-                Ops::cvt_u4x8(Ze, ge);
-                Ops::cvt_u4x8(Zo, go);
-#pragma unroll
-                for (int x = 0; x < 4; ++x) {
-                    // element index inside the word: even -> 2x (m-slot g), odd -> 2x+1 (m-slot g+8)
-                    uint32_t a[4];
-                    a[0] = Ops::fma2(he[x], s01, z01);
-                    a[1] = Ops::fma2(ho[x], s01, z01);
-                    a[2] = Ops::fma2(ge[x], s23, z23);
-                    a[3] = Ops::fma2(go[x], s23, z23);
-                    Ops::mma16816(O[4 * m + x], a, pf);
-                }
+        }
+        named_bar_sync(1, kConsumerWarps * 32);
+        const bool complete = (first_tile == 0) && last_tile;
+        const int  ctid     = threadIdx.x;  // 0..127
+        const float* m0     = &ss.merge_O[0][0][0];
+        const float* m1     = &ss.merge_O[1][0][0];
+        if (complete) {
+            for (int i = ctid; i < G * kHeadDim / 2; i += kConsumerWarps * 32) {
+                const int    hd  = (2 * i) / kHeadDim;
+                const int    d   = (2 * i) % kHeadDim;
+                const float  inv = 1.f / ss.final_L[hd];
+                const int    mi  = merge_idx(hd, d);
+                const float2 a = *reinterpret_cast<const float2*>(m0 + mi), b2 = *reinterpret_cast<const float2*>(m1 + mi);
+                const int    col = it.h * G * kHeadDim + 2 * i;
+                T*           dst = reinterpret_cast<T*>(p.out)
+                         + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + it.b) * 8 + (col & 7) :
+                                           (size_t)it.b * p.out_stride + col);
+                *reinterpret_cast<uint32_t*>(dst) = Ops::pack2((a.x + b2.x) * inv, (a.y + b2.y) * inv);
             }
         }
         else {
-            uint4 va[2], vb[2], vc[2], vd[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                va[i] = lds128(st + Cfg::kOffV + offV0 + 16 * (g + 8 * i));
-                vb[i] = lds128(st + Cfg::kOffV + offV1 + 16 * (g + 8 * i));
-                vc[i] = lds128(st + Cfg::kOffV + offV2 + 16 * (g + 8 * i));
-                vd[i] = lds128(st + Cfg::kOffV + offV3 + 16 * (g + 8 * i));
+            const int slot = 2 * blockIdx.x + (idx == lo ? 0 : 1);
+            float*    po   = p.partial_O + (size_t)slot * kMaxGroup * kHeadDim;
+            for (int i = ctid; i < G * kHeadDim / 2; i += kConsumerWarps * 32) {
+                const int    hd = (2 * i) / kHeadDim, d = (2 * i) % kHeadDim;
+                const int    mi = merge_idx(hd, d);
+                const float2 a = *reinterpret_cast<const float2*>(m0 + mi), b2 = *reinterpret_cast<const float2*>(m1 + mi);
+                *reinterpret_cast<float2*>(po + 2 * i) = make_float2(a.x + b2.x, a.y + b2.y);
             }
-            if (residue) {
-                const uint4 z = make_uint4(0, 0, 0, 0);
-                if (t0 + tokV0 >= k_len) va[0] = va[1] = z;
-                if (t0 + tokV1 >= k_len) vb[0] = vb[1] = z;
-                if (t0 + tokV2 >= k_len) vc[0] = vc[1] = z;
-                if (t0 + tokV3 >= k_len) vd[0] = vd[1] = z;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t A = (&va[j >> 2].x)[j & 3], Bq = (&vb[j >> 2].x)[j & 3];
-                const uint32_t C = (&vc[j >> 2].x)[j & 3], Dq = (&vd[j >> 2].x)[j & 3];
-                uint32_t       a[4];
-                a[0] = __byte_perm(A, Bq, 0x5410);  // (dim 2j, keys 2t,2t+1)
-                a[1] = __byte_perm(A, Bq, 0x7632);  // (dim 2j+1, ...)
-                a[2] = __byte_perm(C, Dq, 0x5410);
-                a[3] = __byte_perm(C, Dq, 0x7632);
-                Ops::mma16816(O[j], a, pf);
+            if (ctid < G) {
+                p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2]     = ss.final_M[ctid];
+                p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2 + 1] = ss.final_L[ctid];
             }
         }
+        named_bar_sync(1, kConsumerWarps * 32);
 
-        // release the stage
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(smem_u32(&ss.empty[s]));
-        }
-
-        // ------------------------------ segment end? ------------------------------
-        const bool last_tile = it.tile == it.tiles - 1;
-        const bool seg_end   = last_tile || idx == hi - 1;
-        if (seg_end) {
-            // row sums across the 8 row-groups
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                L[q] += __shfl_xor_sync(0xffffffffu, L[q], 4);
-                L[q] += __shfl_xor_sync(0xffffffffu, L[q], 8);
-                L[q] += __shfl_xor_sync(0xffffffffu, L[q], 16);
-            }
-            // ---- merge the 4 consumer warps (fixed order: (w0+w2)+(w1+w3)) ----
-            if (g == 0) {
-                ss.merge_M[warp][2 * t]     = M[0];
-                ss.merge_M[warp][2 * t + 1] = M[1];
-                ss.merge_L[warp][2 * t]     = L[0];
-                ss.merge_L[warp][2 * t + 1] = L[1];
-            }
-            named_bar_sync(1, kConsumerWarps * 32);
-            float gm[2], gl[2], sc[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int hd = 2 * t + q;
-                float     m  = ss.merge_M[0][hd];
-                for (int w = 1; w < kConsumerWarps; ++w) m = fmaxf(m, ss.merge_M[w][hd]);
-                float l = 0.f;
-                for (int w = 0; w < kConsumerWarps; ++w) {
-                    const float mw = ss.merge_M[w][hd];
-                    l += (mw == -INFINITY) ? 0.f : exp2_approx((mw - m) * c) * ss.merge_L[w][hd];
-                }
-                gm[q] = m;
-                gl[q] = l;
-                sc[q] = (M[q] == -INFINITY) ? 0.f : exp2_approx((M[q] - m) * c);
-            }
-            if (warp == 0 && g == 0) {
-                ss.final_M[2 * t]     = gm[0];
-                ss.final_M[2 * t + 1] = gm[1];
-                ss.final_L[2 * t]     = gl[0];
-                ss.final_L[2 * t + 1] = gl[1];
-            }
-            float* mo = &ss.merge_O[warp & 1][0][0];
-            if (warp < 2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int d                    = pv_dim<KVBITS>(g, j, e);
-                        mo[(2 * t) * kHeadDim + d]     = O[j][2 * e] * sc[0];
-                        mo[(2 * t + 1) * kHeadDim + d] = O[j][2 * e + 1] * sc[1];
-                    }
-                }
-            }
-            named_bar_sync(1, kConsumerWarps * 32);
-            if (warp >= 2) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int d = pv_dim<KVBITS>(g, j, e);
-                        mo[(2 * t) * kHeadDim + d] += O[j][2 * e] * sc[0];
-                        mo[(2 * t + 1) * kHeadDim + d] += O[j][2 * e + 1] * sc[1];
-                    }
-                }
-            }
-            named_bar_sync(1, kConsumerWarps * 32);
-            // ---- write: final (segment complete inside this CTA) or partial ----
-            const bool complete = (first_tile == 0) && last_tile;
-            const int  ctid     = threadIdx.x;  // 0..127
-            if (complete) {
-                for (int i = ctid; i < G * kHeadDim / 2; i += kConsumerWarps * 32) {
-                    const int   hd  = (2 * i) / kHeadDim;
-                    const int   d   = (2 * i) % kHeadDim;
-                    const float inv = 1.f / ss.final_L[hd];
-                    const float x0  = (ss.merge_O[0][hd][d] + ss.merge_O[1][hd][d]) * inv;
-                    const float x1  = (ss.merge_O[0][hd][d + 1] + ss.merge_O[1][hd][d + 1]) * inv;
-                    const int   col = it.h * G * kHeadDim + 2 * i;
-                    T*          dst = reinterpret_cast<T*>(p.out)
-                             + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + it.b) * 8 + (col & 7) :
-                                               (size_t)it.b * p.out_stride + col);
-                    *reinterpret_cast<uint32_t*>(dst) = Ops::pack2(x0, x1);
-                }
-            }
-            else {
-                const int slot = 2 * blockIdx.x + (seg_lo_idx == lo ? 0 : 1);
-                float*    po   = p.partial_O + (size_t)slot * kMaxGroup * kHeadDim;
-                for (int i = ctid; i < G * kHeadDim; i += kConsumerWarps * 32) {
-                    const int hd = i / kHeadDim, d = i % kHeadDim;
-                    po[i] = ss.merge_O[0][hd][d] + ss.merge_O[1][hd][d];
-                }
-                if (ctid < G) {
-                    p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2]     = ss.final_M[ctid];
-                    p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2 + 1] = ss.final_L[ctid];
-                }
-            }
-            named_bar_sync(1, kConsumerWarps * 32);
-            seg_start = true;
-        }
+        // advance to the next segment
+        idx += ntile;
+        it.tile += ntile - 1;
         it.next();
     }
 }

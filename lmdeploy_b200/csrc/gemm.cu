@@ -94,12 +94,14 @@ __global__ void pack_x_kernel(T* xp, const T* x, int M, int MT, int K, int64_t l
     }
 }
 
-static int pick_splits(int N, int K)
+static int pick_splits(int N, int K, int MT)
 {
-    const int nts = N / kBN, kgs = K / kKG;
-    int       s   = (148 + nts / 2) / nts;
-    s             = std::max(1, std::min(s, std::min(kgs, 8)));
-    return s;
+    // aim at one wave of (148 SMs x CTAs per SM) CTAs, at least 4 K-groups per CTA; a pure function of the shape
+    const int nts    = N / kBN, kgs = K / kKG;
+    const int target = 148 * (MT <= 64 ? 2 : 1);
+    int       s      = target / nts;
+    s                = std::max(1, std::min(s, std::min(kgs / 4, 16)));
+    return std::max(1, s);
 }
 
 static int pick_stages(int fmt, int MT)
@@ -108,6 +110,9 @@ static int pick_stages(int fmt, int MT)
     const int WB_pad = (WB + 1023) & ~1023;
     const int stage  = WB_pad + MT * 256;
     int       st     = std::min(kMaxStages, (220 * 1024) / stage);
+    if (fmt != kDense && MT <= 64) {
+        st = std::min(st, 3);  // 3 x 64 A columns + 64 D columns = 256 TMEM columns -> 2 CTAs / SM
+    }
     return std::max(2, st);
 }
 
@@ -134,7 +139,7 @@ static LinearWs carve_ws(void* base, int K, int N, int MT)
     };
     w.counters = (int*)take((size_t)(N / kBN) * 4 + 256);
     w.xp       = take((size_t)K * MT * 2);
-    w.partials = (float*)take((size_t)(N / kBN) * 8 * MT * kBN * 4);
+    w.partials = (float*)take((size_t)(N / kBN) * 16 * MT * kBN * 4);
     w.total    = off;
     return w;
 }
@@ -270,8 +275,17 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.K        = d->input_dim;
     p.MT       = mt;
     p.M        = m;
-    p.splits   = pick_splits(p.N, p.K);
+    p.splits   = pick_splits(p.N, p.K, mt);
     p.stages   = pick_stages(d->weight_format, mt);
+    if (d->weight_format == kDense) {
+        p.tmem_cols = mt <= 32 ? 32 : (mt <= 64 ? 64 : 128);
+        p.a_col     = 0;
+    }
+    else {
+        const int need = mt <= 64 ? 64 + p.stages * 64 : 128 + p.stages * 64;
+        p.tmem_cols    = need <= 256 ? 256 : 512;
+        p.a_col        = mt <= 64 ? 64 : 128;
+    }
     p.epilogue = epilogue;
     p.out_mode = out_mode;
     p.ldy      = (int)ldy;

@@ -28,8 +28,8 @@ constexpr int kBN        = 128;  // output features per CTA (UMMA M)
 constexpr int kKG        = 128;  // K per pipeline stage (= quant group size)
 constexpr int kMaxStages = 4;
 constexpr int kThreads   = 320;  // warp0 TMA, warp1 MMA/TMEM, warps2-5 dequant A + epilogue, warps6-9 dequant B
-constexpr int kTmemCols  = 512;
-constexpr int kTmemACol  = 128;  // A operand columns start (64 per stage)
+// TMEM budget: D accumulators occupy columns [0, MT); the dequantised A operand uses 64 columns per stage starting
+// at column a_col.  MT <= 64 with 3 stages fits 256 columns, so two CTAs can be resident per SM.
 
 enum WeightFormat : int
 {
@@ -58,6 +58,8 @@ struct Params {
     int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
     int            ldy;
     int            out_mt;
+    int            tmem_cols;  // 256 or 512 (power of two)
+    int            a_col;      // first TMEM column of the A-operand ring
 };
 
 B200_DEVICE int w_block_bytes(int fmt)
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         fence_mbar_init();
     }
     if (warp == 1) {
-        umma::tmem_alloc(smem_u32(&s_tmem), kTmemCols);
+        umma::tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -140,15 +142,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         // ================================ TMA producer ================================
         if (lane == 0) {
             const uint64_t pol_w = make_evict_first_policy();
+            int      s  = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nk; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
                 const uint32_t bar = smem_u32(&bar_full[s]);
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
                 mbar_expect_tx(bar, WB + XB);
                 bulk_g2s_hint(dst, p.w + ((size_t)nt * kgs + kg0 + i) * WB, WB, bar, pol_w);
                 bulk_g2s(dst + WB_pad, reinterpret_cast<const uint8_t*>(p.xp) + (size_t)(kg0 + i) * XB, XB, bar);
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
         }
     }
@@ -156,9 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         // ================================ MMA issuer ================================
         if (lane == 0) {
             const uint32_t idesc = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
+            int      s  = 0;
+            uint32_t ph = 0;
             for (int i = 0; i < nk; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1;
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 if (FMT != kDense) {
                     mbar_wait(smem_u32(&bar_aready[s]), ph);
@@ -175,10 +181,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                         umma::mma_f16_ss(tmem, ad, bd, idesc, acc);
                     }
                     else {
-                        umma::mma_f16_ts(tmem, tmem + kTmemACol + s * 64 + ks * 8, bd, idesc, acc);
+                        umma::mma_f16_ts(tmem, tmem + p.a_col + s * 64 + ks * 8, bd, idesc, acc);
                     }
                 }
                 umma::commit(smem_u32(&bar_empty[s]));
+                if (++s == p.stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
             }
             umma::commit(smem_u32(&bar_dready));
         }
@@ -190,9 +200,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         const int      n_local   = lane_base + lane;
         const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
         if constexpr (FMT == kU4) {
+            int      s  = grp % p.stages;
+            uint32_t ph = (grp / p.stages) & 1;
             for (int i = grp; i < nk; i += 2) {
-                const int s = i % p.stages;
-                const uint32_t ph = (i / p.stages) & 1;
                 mbar_wait(smem_u32(&bar_full[s]), ph);
                 const uint32_t wsm = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
@@ -210,12 +220,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 #pragma unroll
                             for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
                         }
-                        umma::st_32x32b_x16(trow + kTmemACol + s * 64 + c * 32 + hh * 16, r);
+                        umma::st_32x32b_x16(trow + p.a_col + s * 64 + c * 32 + hh * 16, r);
                     }
                 }
                 umma::wait_st();
                 umma::fence_before_sync();
                 mbar_arrive(smem_u32(&bar_aready[s]));
+                s += 2;
+                while (s >= p.stages) {
+                    s -= p.stages;
+                    ph ^= 1;
+                }
             }
         }
         // ================================ epilogue (group 0) ================================
@@ -250,13 +265,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 named_bar_sync(1, 128);
                 if (s_last) {
                     __threadfence();
-                    const float* base = p.partials + (size_t)nt * p.splits * p.MT * kBN;
-                    for (int tok = 0; tok < p.MT; ++tok) {
-                        float acc = 0.f;
+                    const float* base = p.partials + (size_t)nt * p.splits * p.MT * kBN + n_local;
+                    // 8 tokens x all splits of independent loads in flight per thread (one L2 round trip per batch)
+                    for (int t0 = 0; t0 < p.MT; t0 += 8) {
+                        float acc[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
                         for (int k = 0; k < p.splits; ++k) {
-                            acc += __ldcg(base + ((size_t)k * p.MT + tok) * kBN + n_local);
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = __ldcg(base + ((size_t)k * p.MT + t0 + j) * kBN);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) acc[j] += v[j];
                         }
-                        finalize<T>(p, tok, n_g, acc);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) finalize<T>(p, t0 + j, n_g, acc[j]);
                     }
                     if (threadIdx.x == 64) {
                         p.counters[nt] = 0;
@@ -268,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) {
-        umma::tmem_dealloc(tmem, kTmemCols);
+        umma::tmem_dealloc(tmem, p.tmem_cols);
     }
 }
 

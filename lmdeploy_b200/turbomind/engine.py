@@ -1,0 +1,161 @@
+"""TurboMind / TurboMindInstance: the host-side engine the Python API drives.
+
+Mirrors lmdeploy/turbomind/turbomind.py (TurboMind :108-566, TurboMindInstance :568-813): an engine object owning
+weights + KV pool, instances that stream tokens for a session.  The model forward is the native decode step
+(libb200tm.so); scheduling is lmdeploy_b200.turbomind.scheduler."""
+import asyncio
+import threading
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from ..messages import EngineOutput, GenerationConfig, ResponseType, TurbomindEngineConfig
+from .runtime import DecodeModel, KvCachePool
+from .scheduler import Scheduler, Sequence
+from .specs import SPECS, ModelSpec
+
+
+class TurboMind:
+    def __init__(self, spec: ModelSpec, engine_config: Optional[TurbomindEngineConfig] = None, *, model: DecodeModel = None,
+                 eos_id: Optional[int] = None, num_blocks: Optional[int] = None, seed=0):
+        cfg = engine_config or TurbomindEngineConfig()
+        if cfg.tp != 1 and model is None:
+            raise NotImplementedError("tp > 1: launch one process per GPU (torchrun) and pass a TP-sharded DecodeModel "
+                                      "(see bench.py / lmdeploy_b200.turbomind.tp.TpGroup)")
+        self.config = cfg
+        self.spec = spec
+        self.eos_id = eos_id
+        self.max_batch = cfg.max_batch_size or 64
+        self.session_len = cfg.session_len or 4096
+        self.block_len = cfg.cache_block_seq_len
+        self.model = model or DecodeModel(spec, quant_policy=cfg.quant_policy, block_len=self.block_len,
+                                          max_batch=self.max_batch)
+        if model is None:
+            self.model.load_synthetic(seed)
+        dev = self.model.device
+        if num_blocks is None:
+            if cfg.cache_max_entry_count >= 1:
+                num_blocks = int(cfg.cache_max_entry_count)
+            else:   # ratio of free memory, as CreateEngine does (turbomind.cc:293-311)
+                free, _ = torch.cuda.mem_get_info(dev)
+                num_blocks = int(free * cfg.cache_max_entry_count) // (self.model.layer_bytes * spec.layers)
+        self.pool = KvCachePool(num_blocks, spec.layers, self.model.kv_heads, spec.head_dim, self.block_len,
+                                cfg.quant_policy, device=dev)
+        self.scheduler = Scheduler(max_batch=self.max_batch, block_len=self.block_len, num_blocks=num_blocks,
+                                   session_len=self.session_len)
+        B = self.max_batch
+        self._max_blocks = (self.session_len + self.block_len - 1) // self.block_len
+        self.d_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.d_out = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.d_cu_q = torch.arange(B + 1, dtype=torch.int32, device=dev)
+        self.d_cu_k = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.d_cu_blocks = torch.zeros(B + 1, dtype=torch.int32, device=dev)
+        self.d_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64, device=dev)
+        self.h_tokens = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_out = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.h_cu_k = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.h_cu_blocks = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.h_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64).pin_memory()
+        self._lock = threading.Lock()
+        self._next_session = 0
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, engine_config=None, **kw):
+        """`pretrained_model_name_or_path`: a key of SPECS (synthetic random weights of that geometry; no real
+        checkpoints exist in this image) or a directory holding an HF-format checkpoint (config.json +
+        *.safetensors, InternLM2 / Llama, fp16 or AWQ) read by lmdeploy_b200.turbomind.loader."""
+        import os
+        if pretrained_model_name_or_path in SPECS:
+            return cls(SPECS[pretrained_model_name_or_path], engine_config, **kw)
+        if os.path.isdir(pretrained_model_name_or_path):
+            from .loader import load_hf_checkpoint
+            cfg = engine_config or TurbomindEngineConfig()
+            spec, model, eos = load_hf_checkpoint(pretrained_model_name_or_path, quant_policy=cfg.quant_policy,
+                                                  block_len=cfg.cache_block_seq_len,
+                                                  max_batch=cfg.max_batch_size or 64)
+            return cls(spec, cfg, model=model, eos_id=eos, **kw)
+        raise FileNotFoundError(pretrained_model_name_or_path)
+
+    def create_instance(self):
+        return TurboMindInstance(self)
+
+    # ------------------------------------------------------------------ one engine step
+    def step(self):
+        """Schedule + run one decode step for the active batch; returns [(sequence, token|None)] events."""
+        sched = self.scheduler
+        batch = sched.schedule()
+        if not batch:
+            return []
+        B = len(batch)
+        ptrs, nblk = [], [0]
+        for i, s in enumerate(batch):
+            self.h_tokens[i] = s.next_input()
+            self.h_cu_k[i + 1] = self.h_cu_k[i] + (s.cached + 1) if i else (s.cached + 1)
+            ptrs += [self.pool.ptr(b) for b in s.blocks]
+            nblk.append(len(ptrs))
+        self.h_cu_k[0] = 0
+        acc = 0
+        for i, s in enumerate(batch):
+            acc += s.cached + 1
+            self.h_cu_k[i + 1] = acc
+        self.h_cu_blocks[:B + 1] = torch.tensor(nblk, dtype=torch.int32)
+        self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
+        self.d_tokens[:B].copy_(self.h_tokens[:B], non_blocking=True)
+        self.d_cu_k[:B + 1].copy_(self.h_cu_k[:B + 1], non_blocking=True)
+        self.d_cu_blocks[:B + 1].copy_(self.h_cu_blocks[:B + 1], non_blocking=True)
+        self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
+        self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
+                               block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
+                               max_k_len=max(s.cached for s in batch) + 1)
+        self.h_out[:B].copy_(self.d_out[:B], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return sched.update(batch, self.h_out[:B].tolist())
+
+    def new_session_id(self):
+        with self._lock:
+            self._next_session += 1
+            return self._next_session
+
+
+class TurboMindInstance:
+    """Stream tokens for one session.  Same call shape as the reference's
+    TurboMindInstance.async_stream_infer(session_id, input_ids, gen_config=...) (turbomind.py:687-813)."""
+
+    def __init__(self, engine: TurboMind):
+        self.engine = engine
+
+    def _submit(self, session_id, input_ids, gen_config):
+        g = gen_config or GenerationConfig()
+        seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=g.max_new_tokens,
+                       stop_token_ids=list(g.stop_token_ids or []), ignore_eos=g.ignore_eos, eos_id=self.engine.eos_id)
+        self.engine.scheduler.add(seq)
+        return seq
+
+    def stream_infer(self, session_id, input_ids, gen_config: GenerationConfig = None, **kw):
+        seq = self._submit(session_id, input_ids, gen_config)
+        sent = 0
+        while not seq.finished:
+            self.engine.step()
+            if len(seq.generated) > sent:
+                sent = len(seq.generated)
+                yield EngineOutput(ResponseType.SUCCESS, list(seq.generated), sent)
+        yield EngineOutput(ResponseType.FINISH if seq.finish_reason != "cancel" else ResponseType.CANCEL,
+                           list(seq.generated), len(seq.generated))
+
+    async def async_stream_infer(self, session_id, input_ids, gen_config: GenerationConfig = None, **kw):
+        for out in self.stream_infer(session_id, input_ids, gen_config):
+            yield out
+            await asyncio.sleep(0)
+
+    def cancel(self, session_id):
+        self.engine.scheduler.cancel(session_id)
+
+
+def batched_generate(engine: TurboMind, prompts: List[List[int]], gen_config: GenerationConfig = None):
+    """Run a list of token-id prompts to completion with continuous batching; returns per-prompt generated ids."""
+    inst = engine.create_instance()
+    seqs = [inst._submit(engine.new_session_id(), p, gen_config) for p in prompts]
+    while engine.scheduler.has_work:
+        engine.step()
+    return seqs

@@ -1,0 +1,204 @@
+"""HF checkpoint -> TurboMind pre-prepare tensors of one TP rank (then b200_linear_prepare on the GPU).
+
+Restates the loader transforms of the reference for the two architectures on the hot path
+(lmdeploy/turbomind/models/internlm2.py:32-135, models/llama.py:44-99):
+  * AWQ 'gemm' tensors are unpacked with the AWQ nibble order [0,4,1,5,2,6,3,7] and re-packed row-plain
+    (weight_format.py:47-74, 219-247); fp16 HF linears [N,K] are transposed to [K,N];
+  * InternLM2 `wqkv` is de-interleaved from the per-kv-group layout [q0..q(g-1) k v] (internlm2.py:32-49);
+  * q / k output channels are permuted from HF half-split RoPE to TurboMind's adjacent-pair RoPE
+    (models/utils.py:306-324) -- for quantised weights the same column permutation is applied to qweight,
+    scales and zeros (utils.py:355-371);
+  * gate/up are element-interleaved for the fused SiLU epilogue (builders/ffn.py:31-34);
+  * TP: q/k/v heads, gate/up columns, wo/w2 rows and lm_head vocab are sliced per rank
+    (builders/_base.py:102-113, attention.py:65-76, ffn.py:238-243).
+All functions are pure tensor code (CPU-testable); only `load_hf_checkpoint` touches the GPU."""
+import json
+import os
+
+import torch
+
+from .specs import ModelSpec
+
+AWQ_ORDER = [0, 4, 1, 5, 2, 6, 3, 7]
+
+
+def awq_unpack(x):
+    """int32 [R, C/8] -> uint8 [R, C]   (_unpack_awq_gemm, weight_format.py:56-60)."""
+    shifts = torch.tensor([4 * n for n in AWQ_ORDER], dtype=torch.int32)
+    return ((x.unsqueeze(-1) >> shifts) & 0xF).reshape(x.shape[0], -1).to(torch.uint8)
+
+
+def pack_u4_row(q):
+    """uint8 [K, N] -> int32 [K, N/8], nibble i = column 8w+i   (weight_format.py:63-74)."""
+    g = q.reshape(q.shape[0], -1, 8).to(torch.int64)
+    w = torch.zeros(g.shape[:2], dtype=torch.int64)
+    for i in range(8):
+        w |= g[:, :, i] << (4 * i)
+    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
+    return w.to(torch.int32)
+
+
+def rope_perm(num_heads, head_dim, rope_dim=None):
+    """Column permutation of _reorder_rotary_emb: new[h, 2i+j] = old[h, j*D/2 + i]."""
+    rope_dim = rope_dim or head_dim
+    idx = torch.arange(num_heads * head_dim).view(num_heads, head_dim)
+    rot = idx[:, :rope_dim].reshape(num_heads, 2, rope_dim // 2).transpose(1, 2).reshape(num_heads, rope_dim)
+    return torch.cat([rot, idx[:, rope_dim:]], dim=1).reshape(-1)
+
+
+class _Lin:
+    """A linear in TM orientation: q uint8 [K,N] + scales/zeros [K/g,N]  or  w [K,N]."""
+
+    def __init__(self, q=None, scales=None, zeros=None, w=None):
+        self.q, self.scales, self.zeros, self.w = q, scales, zeros, w
+
+    @property
+    def quant(self):
+        return self.q is not None
+
+    def cols(self, idx):
+        if self.quant:
+            return _Lin(self.q[:, idx], self.scales[:, idx], self.zeros[:, idx])
+        return _Lin(w=self.w[:, idx])
+
+    def rows(self, lo, hi, group=128):
+        if self.quant:
+            return _Lin(self.q[lo:hi], self.scales[lo // group:hi // group], self.zeros[lo // group:hi // group])
+        return _Lin(w=self.w[lo:hi])
+
+    @staticmethod
+    def cat(parts):
+        if parts[0].quant:
+            return _Lin(torch.cat([p.q for p in parts], 1), torch.cat([p.scales for p in parts], 1),
+                        torch.cat([p.zeros for p in parts], 1))
+        return _Lin(w=torch.cat([p.w for p in parts], 1))
+
+    def to_tm(self, device, dtype):
+        if self.quant:
+            return dict(weight=pack_u4_row(self.q.contiguous()).to(device), scales=self.scales.to(device, dtype).contiguous(),
+                        zeros=self.zeros.to(device, dtype).contiguous())
+        return dict(weight=self.w.to(device, dtype).contiguous())
+
+
+def _get_linear(tensors, prefix, awq):
+    if awq:
+        return _Lin(awq_unpack(tensors[prefix + ".qweight"]), tensors[prefix + ".scales"].to(torch.float32),
+                    awq_unpack(tensors[prefix + ".qzeros"]).to(torch.float32))
+    return _Lin(w=tensors[prefix + ".weight"].to(torch.float32).t().contiguous())
+
+
+def spec_from_config(cfg):
+    arch = cfg["architectures"][0]
+    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama"}.get(arch)
+    if name is None:
+        raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama)")
+    q = cfg.get("quantization_config") or {}
+    fmt = "fp16"
+    if q:
+        if q.get("quant_method") != "awq" or q.get("bits") != 4 or q.get("group_size") != 128:
+            raise NotImplementedError("only AWQ 4-bit group-128 checkpoints are supported")
+        fmt = "awq"
+    rs = cfg.get("rope_scaling") or {}
+    rope_type = "llama3" if rs.get("rope_type", rs.get("type")) == "llama3" else "default"
+    head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+    return ModelSpec(name=os.path.basename(cfg.get("_name_or_path", name)) or name, arch=name,
+                     hidden=cfg["hidden_size"], layers=cfg["num_hidden_layers"], heads=cfg["num_attention_heads"],
+                     kv_heads=cfg.get("num_key_value_heads", cfg["num_attention_heads"]),
+                     inter=cfg["intermediate_size"], vocab=cfg["vocab_size"],
+                     rope_theta=float(cfg.get("rope_theta", 10000.0)), head_dim=head_dim,
+                     norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope_type,
+                     rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt)
+
+
+def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
+    """-> dict(w_qkv, wo, w1w3, w2 : _Lin ; attention_norm, ffn_norm : tensor) for TP rank `rank`."""
+    D, Hq, Hkv = spec.head_dim, spec.heads, spec.kv_heads
+    awq = spec.weight_format == "awq"
+    if spec.arch == "internlm2":
+        p = f"model.layers.{i}."
+        wqkv = _get_linear(tensors, p + "attention.wqkv", awq)
+        g = Hq // Hkv
+        idx = torch.arange(Hkv * (g + 2) * D).view(Hkv, g + 2, D)
+        q = wqkv.cols(idx[:, :g].reshape(-1))
+        k = wqkv.cols(idx[:, g].reshape(-1))
+        v = wqkv.cols(idx[:, g + 1].reshape(-1))
+        wo = _get_linear(tensors, p + "attention.wo", awq)
+        w1 = _get_linear(tensors, p + "feed_forward.w1", awq)
+        w3 = _get_linear(tensors, p + "feed_forward.w3", awq)
+        w2 = _get_linear(tensors, p + "feed_forward.w2", awq)
+        an, fn = tensors[p + "attention_norm.weight"], tensors[p + "ffn_norm.weight"]
+    else:
+        p = f"model.layers.{i}."
+        q = _get_linear(tensors, p + "self_attn.q_proj", awq)
+        k = _get_linear(tensors, p + "self_attn.k_proj", awq)
+        v = _get_linear(tensors, p + "self_attn.v_proj", awq)
+        wo = _get_linear(tensors, p + "self_attn.o_proj", awq)
+        w1 = _get_linear(tensors, p + "mlp.gate_proj", awq)
+        w3 = _get_linear(tensors, p + "mlp.up_proj", awq)
+        w2 = _get_linear(tensors, p + "mlp.down_proj", awq)
+        an, fn = tensors[p + "input_layernorm.weight"], tensors[p + "post_attention_layernorm.weight"]
+    q = q.cols(rope_perm(Hq, D))
+    k = k.cols(rope_perm(Hkv, D))
+    hq, hkv, it = Hq // tp, Hkv // tp, spec.inter // tp
+    qs = q.cols(torch.arange(rank * hq * D, (rank + 1) * hq * D))
+    ks = k.cols(torch.arange(rank * hkv * D, (rank + 1) * hkv * D))
+    vs = v.cols(torch.arange(rank * hkv * D, (rank + 1) * hkv * D))
+    cols = torch.arange(rank * it, (rank + 1) * it)
+    gate, up = w1.cols(cols), w3.cols(cols)
+    inter_idx = torch.stack([torch.arange(it), it + torch.arange(it)], 1).reshape(-1)
+    return dict(w_qkv=_Lin.cat([qs, ks, vs]), wo=wo.rows(rank * hq * D, (rank + 1) * hq * D),
+                w1w3=_Lin.cat([gate, up]).cols(inter_idx), w2=w2.rows(rank * it, (rank + 1) * it),
+                attention_norm=an, ffn_norm=fn)
+
+
+def convert_globals(spec: ModelSpec, tensors, tp=1, rank=0):
+    if spec.arch == "internlm2":
+        emb, norm, out = tensors["model.tok_embeddings.weight"], tensors["model.norm.weight"], tensors["output.weight"]
+    else:
+        emb, norm = tensors["model.embed_tokens.weight"], tensors["model.norm.weight"]
+        out = tensors.get("lm_head.weight", emb)
+    vpad = (spec.vocab + 128 * tp - 1) // (128 * tp) * (128 * tp)
+    vl = vpad // tp
+    o = torch.zeros(vpad, spec.hidden, dtype=torch.float32)
+    o[:spec.vocab] = out.to(torch.float32)
+    return dict(tok_embeddings=emb, norm=norm, output=o[rank * vl:(rank + 1) * vl].t().contiguous())
+
+
+def read_checkpoint(path):
+    from safetensors.torch import load_file
+    cfg = json.load(open(os.path.join(path, "config.json")))
+    tensors = {}
+    for f in sorted(os.listdir(path)):
+        if f.endswith(".safetensors"):
+            tensors.update(load_file(os.path.join(path, f)))
+    return cfg, tensors
+
+
+def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0):
+    from .runtime import DecodeModel, _TORCH_T
+    cfg, tensors = read_checkpoint(path)
+    spec = spec_from_config(cfg)
+    model = DecodeModel(spec, quant_policy=quant_policy, block_len=block_len, max_batch=max_batch, tp_size=tp,
+                        tp_rank=rank)
+    dev, T = model.device, _TORCH_T[spec.dtype]
+    glob = convert_globals(spec, tensors, tp, rank)
+    cache = {}
+
+    def provider(name):
+        if name in ("tok_embeddings", "norm"):
+            return glob[name]
+        if name == "output":
+            return dict(weight=glob["output"].to(dev, T).contiguous())
+        parts = name.split(".")
+        i, kind = int(parts[1]), parts[2]
+        if i not in cache:
+            cache.clear()
+            cache[i] = convert_layer(spec, tensors, i, tp, rank)
+        x = cache[i][kind]
+        return x.to_tm(dev, T) if isinstance(x, _Lin) else x
+
+    model.load_tm_weights(provider)
+    eos = cfg.get("eos_token_id")
+    if isinstance(eos, list):
+        eos = eos[0]
+    return spec, model, eos

@@ -1,0 +1,178 @@
+"""Loader transforms (HF checkpoint -> TurboMind pre-prepare layout) checked end to end on CPU:
+an HF-semantics reference forward (separate q/k/v, half-split RoPE, gate/up, plain attention) on the ORIGINAL
+checkpoint tensors must agree with the oracle's TurboMind-semantics decode step on the CONVERTED tensors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import attention as OA
+from oracle import linear as OL
+from oracle.decode_step import TinyWeights, decode_step
+from oracle.numerics import F16, rn
+
+from lmdeploy_b200.turbomind import loader as LD
+
+H, L, HQ, HKV, I, V, D = 512, 2, 4, 2, 512, 256, 128
+
+
+def make_checkpoint(arch, awq, seed=0):
+    rng = np.random.default_rng(seed)
+    t, deq = {}, {}
+
+    def add(name, K, N):
+        w = (rng.standard_normal((K, N)) * 0.3 / np.sqrt(K)).astype(np.float32)
+        if awq:
+            q, s, z = OL.quantize_groupwise_u4(w, 128)
+            t[name + ".qweight"] = torch.from_numpy(OL.awq_pack(q))
+            t[name + ".qzeros"] = torch.from_numpy(OL.awq_pack(z.astype(np.uint8)))
+            t[name + ".scales"] = torch.from_numpy(s.astype(np.float16))
+            deq[name] = OL.dequant_u4(q, s, z, F16)
+        else:
+            w = rn(w, F16)
+            t[name + ".weight"] = torch.from_numpy(w.T.astype(np.float16).copy())      # HF: [out, in]
+            deq[name] = w
+
+    for i in range(L):
+        if arch == "internlm2":
+            p = f"model.layers.{i}."
+            add(p + "attention.wqkv", H, (HQ + 2 * HKV) * D)
+            add(p + "attention.wo", HQ * D, H)
+            add(p + "feed_forward.w1", H, I), add(p + "feed_forward.w3", H, I), add(p + "feed_forward.w2", I, H)
+            norms = (p + "attention_norm.weight", p + "ffn_norm.weight")
+        else:
+            p = f"model.layers.{i}."
+            add(p + "self_attn.q_proj", H, HQ * D), add(p + "self_attn.k_proj", H, HKV * D)
+            add(p + "self_attn.v_proj", H, HKV * D), add(p + "self_attn.o_proj", HQ * D, H)
+            add(p + "mlp.gate_proj", H, I), add(p + "mlp.up_proj", H, I), add(p + "mlp.down_proj", I, H)
+            norms = (p + "input_layernorm.weight", p + "post_attention_layernorm.weight")
+        for n in norms:
+            t[n] = torch.from_numpy((1 + 0.05 * rng.standard_normal(H)).astype(np.float16))
+    emb = "model.tok_embeddings.weight" if arch == "internlm2" else "model.embed_tokens.weight"
+    head = "output.weight" if arch == "internlm2" else "lm_head.weight"
+    t[emb] = torch.from_numpy((rng.standard_normal((V, H)) * 0.5).astype(np.float16))
+    t["model.norm.weight"] = torch.from_numpy((1 + 0.05 * rng.standard_normal(H)).astype(np.float16))
+    t[head] = torch.from_numpy((rng.standard_normal((V, H)) * 0.3 / np.sqrt(H)).astype(np.float16))
+    cfg = {"architectures": ["InternLM2ForCausalLM" if arch == "internlm2" else "LlamaForCausalLM"],
+           "hidden_size": H, "num_hidden_layers": L, "num_attention_heads": HQ, "num_key_value_heads": HKV,
+           "intermediate_size": I, "vocab_size": V, "rms_norm_eps": 1e-5, "rope_theta": 10000.0}
+    if awq:
+        cfg["quantization_config"] = {"quant_method": "awq", "bits": 4, "group_size": 128, "zero_point": True,
+                                      "version": "gemm"}
+    return cfg, t, deq
+
+
+def hf_forward(arch, t, deq, tokens):
+    """float64 HF-semantics forward over the whole token list; returns logits of every position."""
+    f = lambda n: t[n].to(torch.float64).numpy()
+    emb = f("model.tok_embeddings.weight" if arch == "internlm2" else "model.embed_tokens.weight")
+    x = emb[np.asarray(tokens)]
+    S = len(tokens)
+
+    def norm(x, w):
+        return x / np.sqrt((x ** 2).mean(-1, keepdims=True) + 1e-5) * w
+
+    inv = 1.0 / (10000.0 ** (np.arange(0, D, 2) / D))
+    ang = np.arange(S)[:, None] * inv[None]
+    cos, sin = np.cos(ang), np.sin(ang)
+
+    def rope(v):           # v [S, heads, D], HF half-split rotation
+        a, b = v[..., : D // 2], v[..., D // 2:]
+        return np.concatenate([a * cos[:, None] - b * sin[:, None], b * cos[:, None] + a * sin[:, None]], -1)
+
+    for i in range(L):
+        p = f"model.layers.{i}."
+        if arch == "internlm2":
+            h = norm(x, f(p + "attention_norm.weight"))
+            qkv = (h @ deq[p + "attention.wqkv"]).reshape(S, HKV, HQ // HKV + 2, D)
+            q = qkv[:, :, : HQ // HKV].reshape(S, HQ, D)
+            k, v = qkv[:, :, HQ // HKV], qkv[:, :, HQ // HKV + 1]
+            wo, w1, w3, w2 = (deq[p + "attention.wo"], deq[p + "feed_forward.w1"], deq[p + "feed_forward.w3"],
+                              deq[p + "feed_forward.w2"])
+            n2 = f(p + "ffn_norm.weight")
+        else:
+            h = norm(x, f(p + "input_layernorm.weight"))
+            q = (h @ deq[p + "self_attn.q_proj"]).reshape(S, HQ, D)
+            k = (h @ deq[p + "self_attn.k_proj"]).reshape(S, HKV, D)
+            v = (h @ deq[p + "self_attn.v_proj"]).reshape(S, HKV, D)
+            wo, w1, w3, w2 = (deq[p + "self_attn.o_proj"], deq[p + "mlp.gate_proj"], deq[p + "mlp.up_proj"],
+                              deq[p + "mlp.down_proj"])
+            n2 = f(p + "post_attention_layernorm.weight")
+        q, k = rope(q), rope(k)
+        g = HQ // HKV
+        out = np.zeros((S, HQ, D))
+        for hq in range(HQ):
+            s = q[:, hq] @ k[:, hq // g].T / np.sqrt(D)
+            s = np.where(np.tril(np.ones((S, S))) > 0, s, -np.inf)
+            pr = np.exp(s - s.max(-1, keepdims=True))
+            pr /= pr.sum(-1, keepdims=True)
+            out[:, hq] = pr @ v[:, hq // g]
+        x = x + out.reshape(S, HQ * D) @ wo
+        h = norm(x, n2)
+        gate, up = h @ w1, h @ w3
+        x = x + (gate / (1 + np.exp(-gate)) * up) @ w2
+    x = norm(x, f("model.norm.weight"))
+    head = f("output.weight" if arch == "internlm2" else "lm_head.weight")
+    return x @ head.T
+
+
+def to_tiny(spec, cfg_tensors, tp=1, rank=0):
+    """loader output -> oracle TinyWeights (TurboMind layout)."""
+    t = cfg_tensors
+    w = TinyWeights.__new__(TinyWeights)
+    w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab = H, L, HQ // tp, HKV // tp, I // tp, V
+    w.fmt, w.dtype, w.D = spec.weight_format, F16, D
+    glob = LD.convert_globals(spec, t, tp, rank)
+    w.embed = glob["tok_embeddings"].to(torch.float32).numpy()
+    w.final_norm = glob["norm"].to(torch.float32).numpy()
+    out = glob["output"].numpy()
+    w.output = dict(w=out, deq=rn(out, F16))
+    w.L = []
+
+    def lin(x):
+        if x.quant:
+            q, s, z = x.q.numpy(), x.scales.numpy(), x.zeros.numpy()
+            # the TM pre-prepare packing must round-trip
+            assert (LD.pack_u4_row(x.q).numpy().view(np.uint32) == OL.pack_u4_row(q).view(np.uint32)).all()
+            return dict(q=q, scales=s, zeros=z, deq=OL.dequant_u4(q, s, z, F16))
+        return dict(w=x.w.numpy(), deq=rn(x.w.numpy(), F16))
+
+    for i in range(L):
+        c = LD.convert_layer(spec, t, i, tp, rank)
+        w.L.append(dict(attn_norm=c["attention_norm"].to(torch.float32).numpy(),
+                        ffn_norm=c["ffn_norm"].to(torch.float32).numpy(),
+                        w_qkv=lin(c["w_qkv"]), wo=lin(c["wo"]), w1w3=lin(c["w1w3"]), w2=lin(c["w2"])))
+    return w
+
+
+@pytest.mark.parametrize("arch", ["internlm2", "llama"])
+@pytest.mark.parametrize("awq", [True, False])
+@pytest.mark.parametrize("tp", [1, 2])
+def test_loader_transforms_preserve_model_semantics(arch, awq, tp):
+    cfg, t, deq = make_checkpoint(arch, awq, seed=1)
+    spec = LD.spec_from_config(cfg)
+    assert spec.weight_format == ("awq" if awq else "fp16") and spec.arch == arch
+    tokens = [5, 17, 200, 3, 99]
+    ref = hf_forward(arch, t, deq, tokens)
+    shards = [to_tiny(spec, t, tp, r) for r in range(tp)]
+    full = shards[0] if tp == 1 else to_tiny(spec, t, 1, 0)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=D, base=10000.0)
+    caches = [OA.PagedKvCache(2, L, OA.KvLayout(HKV // tp, 64, D, 16), F16) for _ in range(tp)]
+    for pos, tok in enumerate(tokens):
+        logits, _ = decode_step(full, np.array([tok]), caches[0], [[0]], np.array([pos], np.int32), rope,
+                                tp_shards=shards if tp > 1 else None, caches=caches if tp > 1 else None)
+        err = np.abs(logits[0, :V] - ref[pos]).max()
+        assert err < 2e-2, (pos, err)
+        assert logits[0, :V].argmax() == ref[pos].argmax() or np.sort(ref[pos])[-1] - np.sort(ref[pos])[-2] < 4e-2
+
+
+def test_rope_perm_matches_reference_definition():
+    # _reorder_rotary_emb (models/utils.py:306-324): new[h, 2i+j] = old[h, j*D/2 + i]
+    p = LD.rope_perm(2, 8)
+    assert p.tolist() == [0, 4, 1, 5, 2, 6, 3, 7, 8, 12, 9, 13, 10, 14, 11, 15]
+
+
+def test_awq_unpack_matches_oracle():
+    rng = np.random.default_rng(0)
+    q = rng.integers(0, 16, (8, 32)).astype(np.uint8)
+    w = OL.awq_pack(q)
+    assert (LD.awq_unpack(torch.from_numpy(w)).numpy() == q).all()
