@@ -124,6 +124,9 @@ typedef struct {
     /* optional: a plan computed once per step by b200_decode_attention_plan (valid for every layer of
      * the step); if NULL the call plans internally. */
     const int* plan;
+    /* optional: per-token (cos, sin) table from b200_rope_table (token_num x 64 float pairs), shared by all
+     * layers of a step; NULL = computed inside the call. */
+    const float* rope_table;
 
     /* > 0: write `out` in the UMMA K-major tile layout [num_heads*128/8][out_packed_mt][8] consumed by
      * b200_linear_forward_packed (fuses the repack in front of the `wo` GEMM); 0: token-major rows. */
@@ -139,6 +142,8 @@ typedef struct {
 B200_API size_t b200_decode_attention_workspace_bytes(int batch_size, int num_heads, int num_kv_heads);
 /* plan buffer: (batch_size + 1) ints, device memory */
 B200_API int b200_decode_attention_plan(int* plan, const int* cu_k_len, const uint8_t* finished, int batch_size, void* stream);
+B200_API int b200_rope_table(float* table, const b200_rope_config* rope, const int* cu_q_len, const int* cu_k_len,
+                    int batch_size, int token_num, void* stream);
 B200_API int b200_decode_attention(const b200_attention_params* params);
 
 /* Prefill-side KV writer.  Replaces invokeProcessKV_v2 (kernels/attention/kv_cache_utils_v2.cu:18-210):

@@ -35,6 +35,7 @@ class AttentionParams(C.Structure):
         ("rope", RopeConfig), ("quant_policy", C.c_int), ("dtype", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("plan", C.c_void_p),
+        ("rope_table", C.c_void_p),
         ("out_packed_mt", C.c_int),
         ("debug_flags", C.c_int),
         ("stream", C.c_void_p),

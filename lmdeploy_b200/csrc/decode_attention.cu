@@ -121,6 +121,27 @@ __global__ void plan_kernel(int* plan, const int* cu_k_len, const uint8_t* finis
     }
 }
 
+// cos/sin of every new token's position, computed once per step and shared by all layers
+__global__ void rope_table_kernel(float2* table, RopeConst rope, const int* cu_q_len, const int* cu_k_len, int batch)
+{
+    const int tok = blockIdx.x;
+    int       lo = 0, hi = batch;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (cu_q_len[mid] <= tok) {
+            lo = mid;
+        }
+        else {
+            hi = mid;
+        }
+    }
+    const int b  = lo;
+    const int ti = (cu_k_len[b + 1] - cu_k_len[b]) - (cu_q_len[b + 1] - cu_q_len[b]) + (tok - cu_q_len[b]);
+    const int i  = threadIdx.x;  // pair index
+    table[(size_t)tok * (kHeadDim / 2) + i] =
+        (rope.type != 0 && 2 * i < rope.dim) ? rope_cos_sin(rope, 2 * i, ti) : make_float2(1.f, 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------
 // prologue: bias + RoPE (+ quantise + page store) for every new token
 //   (attention_universal.h:168-348 for decode, kv_cache_utils_v2.cu:18-210 for prefill)
@@ -147,6 +168,7 @@ struct PrologueParams {
     int         num_heads;
     int         num_kv_heads;
     RopeConst   rope;
+    const float2* rope_table;  // [token][kHeadDim/2] (cos, sin) or null
 };
 
 template<class T>
@@ -191,10 +213,17 @@ __global__ void __launch_bounds__(128) kv_prologue_kernel(const PrologueParams p
     const int di      = lane * 4;
 
     float2 cs[2];
+    if (p.rope_table) {
+        const float4 v = *reinterpret_cast<const float4*>(p.rope_table + (size_t)tok * (kHeadDim / 2) + (di >> 1));
+        cs[0]          = make_float2(v.x, v.y);
+        cs[1]          = make_float2(v.z, v.w);
+    }
+    else {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        cs[i] = (p.rope.type != 0 && di + 2 * i < p.rope.dim) ? rope_cos_sin(p.rope, di + 2 * i, ti) :
-                                                                 make_float2(1.f, 0.f);
+        for (int i = 0; i < 2; ++i) {
+            cs[i] = (p.rope.type != 0 && di + 2 * i < p.rope.dim) ? rope_cos_sin(p.rope, di + 2 * i, ti) :
+                                                                     make_float2(1.f, 0.f);
+        }
     }
     auto rotate = [&](T(&x)[4]) {
         if (p.rope.type == 0) {
@@ -430,6 +459,7 @@ static int launch_prologue(const b200_attention_params* a, void* q_rot, cudaStre
     p.num_heads          = a->num_heads;
     p.num_kv_heads       = a->num_kv_heads;
     p.rope               = make_rope_const(a->rope);
+    p.rope_table         = reinterpret_cast<const float2*>(a->rope_table);
     const int items      = (q_rot ? a->num_heads : 0) + a->num_kv_heads;
     dim3      grid(a->token_num, (items + 3) / 4);
     kv_prologue_kernel<T, KVBITS><<<grid, 128, 0, st>>>(p);
@@ -526,6 +556,17 @@ extern "C" int b200_decode_attention_plan(int* plan, const int* cu_k_len, const 
     }
     plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(plan, cu_k_len, finished, batch_size);
     return check_launch("plan_kernel");
+}
+
+extern "C" int b200_rope_table(float* table, const b200_rope_config* rope, const int* cu_q_len, const int* cu_k_len,
+                               int batch_size, int token_num, void* stream)
+{
+    if (!table || !rope || !cu_q_len || !cu_k_len || batch_size <= 0 || token_num <= 0) {
+        return fail(B200_ERR_INVALID_ARG, "bad rope_table arguments");
+    }
+    rope_table_kernel<<<token_num, kHeadDim / 2, 0, (cudaStream_t)stream>>>((float2*)table, make_rope_const(*rope),
+                                                                            cu_q_len, cu_k_len, batch_size);
+    return check_launch("rope_table_kernel");
 }
 
 extern "C" int b200_decode_attention(const b200_attention_params* a)

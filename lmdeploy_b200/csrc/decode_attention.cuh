@@ -467,37 +467,43 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
         int      s  = 0;
         uint32_t ph = 0;
         TileDesc cur = fetch(lo);
+        // Copy roles: lanes 0-7 move the four 16-row groups of K (even) and V (odd), lanes 8/9 the K/V quant params.
+        // The ten copies of one tile are issued by ten lanes in ONE pass (a single lane issuing them serially costs
+        // ~280 issue slots per tile on the scheduler this warp shares with a consumer warp).
+        const int  my_gq    = (lane >> 1) & 3;
+        const bool my_v     = lane & 1;
+        const bool my_data  = lane < 8;
+        const bool my_param = Cfg::kQuant && (lane == 8 || lane == 9);
         for (long long base = lo; base < hi; base += 32) {
             const TileDesc nxt = fetch(base + 32);
             const int      cnt = (int)min((long long)32, hi - base);
             for (int l = 0; l < cnt; ++l) {
-                if (lane == l) {
+                const unsigned long long blk = __shfl_sync(0xffffffffu, (unsigned long long)cur.blk, l);
+                const int packed = __shfl_sync(0xffffffffu, cur.h | (cur.bt << 8) | (cur.rows << 24), l);
+                const int h = packed & 0xff, bt = (packed >> 8) & 0xffff, rows = packed >> 24;
+                const uint32_t bar = full0 + 8 * s;
+                if (lane == 0) {
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
-                    const int   rows = cur.rows;
-                    const char* kd   = cur.blk + (size_t)(cur.h * 2) * head_data_size + (size_t)cur.bt * Cfg::kRowBytes;
-                    const char* vd   = kd + head_data_size;
+                    const int prow = (rows + 3) & ~3;
+                    mbar_expect_tx(bar, 2 * rows * Cfg::kRowBytes + (Cfg::kQuant ? 2 * prow * 4 : 0));
+                }
+                __syncwarp();
+                const uint32_t st = stage0 + s * (uint32_t)Cfg::kStageBytes;
+                const char*    hb = reinterpret_cast<const char*>(blk);
+                if (my_data) {
+                    const int r = min(kGroupRows, rows - my_gq * kGroupRows);
+                    if (r > 0) {
+                        const char* src = hb + (size_t)(h * 2 + (my_v ? 1 : 0)) * head_data_size
+                                          + (size_t)(bt + my_gq * kGroupRows) * Cfg::kRowBytes;
+                        bulk_g2s_hint(st + (my_v ? Cfg::kOffV : Cfg::kOffK) + my_gq * Cfg::kGroupSize, src,
+                                      r * Cfg::kRowBytes, bar, policy);
+                    }
+                }
+                else if (my_param) {
                     const int   prow = (rows + 3) & ~3;
-                    const uint32_t bytes = 2 * rows * Cfg::kRowBytes + (Cfg::kQuant ? 2 * prow * 4 : 0);
-                    const uint32_t bar   = full0 + 8 * s;
-                    mbar_expect_tx(bar, bytes);
-                    const uint32_t st = stage0 + s * (uint32_t)Cfg::kStageBytes;
-#pragma unroll
-                    for (int gq = 0; gq < kTile / kGroupRows; ++gq) {
-                        const int r = min(kGroupRows, rows - gq * kGroupRows);
-                        if (r > 0) {
-                            const uint32_t nb = r * Cfg::kRowBytes;
-                            bulk_g2s_hint(st + Cfg::kOffK + gq * Cfg::kGroupSize, kd + gq * kGroupRows * Cfg::kRowBytes,
-                                          nb, bar, policy);
-                            bulk_g2s_hint(st + Cfg::kOffV + gq * Cfg::kGroupSize, vd + gq * kGroupRows * Cfg::kRowBytes,
-                                          nb, bar, policy);
-                        }
-                    }
-                    if constexpr (Cfg::kQuant) {
-                        const char* kp = cur.blk + (size_t)Hkv * 2 * head_data_size
-                                         + (size_t)(cur.h * 2) * head_param_sz + (size_t)cur.bt * 4;
-                        bulk_g2s_hint(st + Cfg::kOffKP, kp, prow * 4, bar, policy);
-                        bulk_g2s_hint(st + Cfg::kOffVP, kp + head_param_sz, prow * 4, bar, policy);
-                    }
+                    const char* src  = hb + (size_t)Hkv * 2 * head_data_size
+                                      + (size_t)(h * 2 + (my_v ? 1 : 0)) * head_param_sz + (size_t)bt * 4;
+                    bulk_g2s_hint(st + (my_v ? Cfg::kOffVP : Cfg::kOffKP), src, prow * 4, bar, policy);
                 }
                 if (++s == STAGES) {
                     s = 0;

@@ -42,6 +42,22 @@ constexpr int kU4BlockBytes    = 8192 + 512;           // one (n-tile, k-group):
 constexpr int kDenseBlockBytes = kBN * kKG * 2;        // 32 KB
 constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // data + block scale (T, padded to 16 B)
 
+// Development aid (tools/gemm_trace.cu compiles this TU with -DB200_GEMM_TRACE): per-role clock64 stamps of the
+// first kTraceCtas CTAs.  Absent from the product build.
+#ifdef B200_GEMM_TRACE
+constexpr int kTraceCtas = 8, kTraceRoles = 6, kTraceSlots = 128;
+__device__ long long g_trace[kTraceCtas][kTraceRoles][kTraceSlots];
+#define GEMM_TRACE(role, slot)                                                                                         \
+    do {                                                                                                               \
+        const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                                            \
+        if (_c < kTraceCtas && (slot) < kTraceSlots) g_trace[_c][role][slot] = clock64();                              \
+    } while (0)
+#else
+#define GEMM_TRACE(role, slot)                                                                                         \
+    do {                                                                                                               \
+    } while (0)
+#endif
+
 struct Params {
     const uint8_t* w;   // prepared weight stream
     const void*    xp;  // packed activations [K/8][MT][8] T
@@ -115,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     const int kgs = p.K / kKG;
     const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
     const int nk = kg1 - kg0;
+    if (threadIdx.x == 64) GEMM_TRACE(4, 0);
 
     constexpr int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
     const int     XB     = p.MT * 256;  // 16 k8-chunks x MT x 16 B
@@ -137,6 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
+    if (threadIdx.x == 64) GEMM_TRACE(4, 1);
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -146,6 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             uint32_t ph = 0;
             for (int i = 0; i < nk; ++i) {
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                GEMM_TRACE(0, i);
                 const uint32_t bar = smem_u32(&bar_full[s]);
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
                 mbar_expect_tx(bar, WB + XB);
@@ -170,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     mbar_wait(smem_u32(&bar_aready[s]), ph);
                 }
                 umma::fence_after_sync();
+                GEMM_TRACE(3, i);
                 const uint32_t sbase = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t xbase = sbase + WB_pad;
 #pragma unroll
@@ -185,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     }
                 }
                 umma::commit(smem_u32(&bar_empty[s]));
+                GEMM_TRACE(5, i);
                 if (++s == p.stages) {
                     s = 0;
                     ph ^= 1;
@@ -204,6 +225,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             uint32_t ph = (grp / p.stages) & 1;
             for (int i = grp; i < nk; i += 2) {
                 mbar_wait(smem_u32(&bar_full[s]), ph);
+                if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(1, i);
                 const uint32_t wsm = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
                 const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
@@ -226,6 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 umma::wait_st();
                 umma::fence_before_sync();
                 mbar_arrive(smem_u32(&bar_aready[s]));
+                if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(2, i);
                 s += 2;
                 while (s >= p.stages) {
                     s -= p.stages;
@@ -237,6 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         if (grp == 0) {
             mbar_wait(smem_u32(&bar_dready), 0);
             umma::fence_after_sync();
+            if (threadIdx.x == 64) GEMM_TRACE(4, 2);
             const int n_g = nt * kBN + n_local;
             if (p.splits == 1) {
                 for (int t0 = 0; t0 < p.MT; t0 += 16) {
@@ -288,6 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             }
         }
     }
+    if (threadIdx.x == 64) GEMM_TRACE(4, 3);
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) {

@@ -45,6 +45,7 @@ struct b200_model {
     void* lin_ws{};
     size_t lin_ws_bytes{};
     int*  plan{};
+    float* rope_table{};
 };
 
 using namespace b200;
@@ -111,6 +112,7 @@ extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
     m->lin_ws_bytes = lin;
     rc = rc ? rc : alloc(&m->lin_ws, lin);
     rc = rc ? rc : alloc((void**)&m->plan, (size_t)(MB + 1) * 4);
+    rc = rc ? rc : alloc((void**)&m->rope_table, (size_t)MB * 64 * 8);
     if (rc) {
         b200_model_destroy(m);
         return rc;
@@ -124,7 +126,7 @@ extern "C" void b200_model_destroy(b200_model* m)
     if (!m) {
         return;
     }
-    void* bufs[] = {m->residual, m->xp, m->qkv, m->attn_xp, m->o, m->act_xp, m->logits, m->attn_ws, m->lin_ws, m->plan};
+    void* bufs[] = {m->residual, m->xp, m->qkv, m->attn_xp, m->o, m->act_xp, m->logits, m->attn_ws, m->lin_ws, m->plan, m->rope_table};
     for (void* p : bufs) {
         if (p) {
             cudaFree(p);
@@ -238,6 +240,7 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
     TRY(b200_embedding_lookup(m->residual, m->embedding, in->token_ids, B, c.hidden, c.embedding_rows, c.dtype, stream));
     TRY(b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, B, c.hidden, c.norm_eps, c.dtype, stream));
     TRY(b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
+    TRY(b200_rope_table(m->rope_table, &c.rope, in->cu_q_len, in->cu_k_len, B, B, stream));
 
     for (int l = 0; l < L; ++l) {
         const LayerW& W = m->layers[l];
@@ -260,7 +263,7 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
         a.inv_sqrt_dh = c.inv_sqrt_dh, a.window_size = 0;
         a.rope = c.rope, a.quant_policy = c.quant_policy, a.dtype = c.dtype;
         a.workspace = m->attn_ws, a.workspace_bytes = m->attn_ws_bytes;
-        a.plan = m->plan, a.out_packed_mt = MT, a.stream = stream;
+        a.plan = m->plan, a.rope_table = m->rope_table, a.out_packed_mt = MT, a.stream = stream;
         TRY(b200_decode_attention(&a));
         TRY(b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         // AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287)

@@ -1,0 +1,81 @@
+"""GPU parity of the glue kernels (RMSNorm family, embedding, argmax) against the oracle.
+RMSNorm bar: |diff| <= 2 fp16 ulp of the output (the fp32 sum-of-squares order and rsqrt are unspecified in the
+reference too: cub::BlockReduce + rsqrtf, rms_norm.cu:53-62); residual stream: BIT-EXACT (single fp16 add)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import linear as OL
+from oracle.numerics import F16, BF16, rn
+
+from harness import to_dev_T, from_dev_T
+
+pytestmark = pytest.mark.gpu
+
+
+def unpack_xp(xp, mt, dim, m):
+    """[dim/8][mt][8] -> [m, dim]"""
+    return xp.reshape(dim // 8, mt, 8).transpose(1, 0, 2).reshape(mt, dim)[:m]
+
+
+@pytest.mark.parametrize("dim", [512, 4096, 6144, 8192])
+@pytest.mark.parametrize("dtype", [F16, BF16])
+@pytest.mark.parametrize("packed", [0, 16])
+def test_residual_rmsnorm(lib, dim, dtype, packed):
+    import torch
+    from lmdeploy_b200 import _lib as L
+    rng = np.random.default_rng(dim)
+    m = 13
+    res = rn(rng.standard_normal((m, dim)).astype(np.float32), dtype)
+    hid = rn(rng.standard_normal((m, dim)).astype(np.float32) * 0.3, dtype)
+    w = rn((1 + 0.05 * rng.standard_normal(dim)).astype(np.float32), dtype)
+    bias = rn((0.1 * rng.standard_normal(dim)).astype(np.float32), dtype)
+    d_res, d_hid, d_w, d_b = (to_dev_T(x, dtype) for x in (res, hid, w, bias))
+    mt = packed if packed else m
+    d_out = torch.zeros(mt * dim, dtype=d_res.dtype, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b200_residual_rmsnorm(d_out.data_ptr(), packed, d_res.data_ptr(), d_hid.data_ptr(), d_w.data_ptr(),
+                                      d_b.data_ptr(), m, dim, 1e-5, 0 if dtype == F16 else 1, st), "residual_rmsnorm")
+    torch.cuda.synchronize()
+    ref_out, ref_res = OL.residual_rmsnorm(hid, res, w, 1e-5, dtype, bias=bias)
+    assert (from_dev_T(d_res, dtype) == ref_res).all()
+    got = from_dev_T(d_out, dtype)
+    got = unpack_xp(got, mt, dim, m) if packed else got.reshape(m, dim)
+    ulp = 2.0 ** (-10 if dtype == F16 else -7)
+    assert np.abs(got - ref_out).max() <= 2 * ulp * max(1.0, np.abs(ref_out).max())
+    # plain rmsnorm
+    d_x = to_dev_T(res, dtype)
+    L.check(lib.b200_rmsnorm(d_out.data_ptr(), packed, d_x.data_ptr(), d_w.data_ptr(), m, dim, 1e-5,
+                             0 if dtype == F16 else 1, st), "rmsnorm")
+    torch.cuda.synchronize()
+    got = from_dev_T(d_out, dtype)
+    got = unpack_xp(got, mt, dim, m) if packed else got.reshape(m, dim)
+    ref = OL.rmsnorm(res, w, 1e-5, dtype)
+    assert np.abs(got - ref).max() <= 2 * ulp * max(1.0, np.abs(ref).max())
+
+
+def test_embedding_and_argmax(lib):
+    import torch
+    from lmdeploy_b200 import _lib as L
+    rng = np.random.default_rng(0)
+    V, H, B = 92544, 512, 64
+    table = torch.randn(V, H, device="cuda", dtype=torch.float16)
+    ids = torch.from_numpy(rng.integers(0, V, B).astype(np.int32)).cuda()
+    out = torch.zeros(B, H, device="cuda", dtype=torch.float16)
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b200_embedding_lookup(out.data_ptr(), table.data_ptr(), ids.data_ptr(), B, H, V, 0, st), "embedding")
+    assert torch.equal(out, table[ids.long()])
+    logits = torch.randn(B, V, device="cuda", dtype=torch.float16)
+    # plant exact ties: the smallest index must win (documented tie rule)
+    logits[3, 100] = 9.0
+    logits[3, 50000] = 9.0
+    logits[7, V - 1] = 11.0
+    tok = torch.zeros(B, dtype=torch.int32, device="cuda")
+    L.check(lib.b200_argmax(tok.data_ptr(), logits.data_ptr(), B, V, V, 0, st), "argmax")
+    torch.cuda.synchronize()
+    ref = logits.float().argmax(-1)
+    got = tok.long()
+    assert got[3] == 100 and got[7] == V - 1
+    # torch.argmax tie-breaking is unspecified; compare values
+    assert torch.equal(logits.float().gather(1, got[:, None]), logits.float().gather(1, ref[:, None]))

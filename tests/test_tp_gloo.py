@@ -1,0 +1,91 @@
+"""Tensor-parallel host logic on CPU with a real 2-process world (gloo): every rank computes ITS shard of the oracle
+decode step from loader-sharded weights, the two per-layer exchanges are real all-reduces, vocab-sharded logits are
+all-gathered.  The result must equal the single-process oracle with TP semantics (rank-ordered sum)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import attention as OA
+from oracle import linear as OL
+from oracle.decode_step import TinyWeights, decode_step
+from oracle.numerics import F16, rn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=512, vocab=256, seed=5)
+    sw = w.shard(rank, world)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
+    cache = OA.PagedKvCache(2, w.layers, OA.KvLayout(sw.kv_heads, 64, 128, 8), F16)
+    tokens, hist = np.array([3, 9]), np.array([0, 0], np.int32)
+    dtype = F16
+
+    def allreduce_T(x):
+        """rank-ordered sum in T (what the fused NVLink kernel does): gather all partials, add in rank order"""
+        parts = [torch.zeros_like(torch.from_numpy(x)) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(x)))
+        acc = parts[0].numpy()
+        for p in parts[1:]:
+            acc = rn(acc + p.numpy(), dtype)
+        return acc
+
+    residual = w.embed[tokens]
+    x = OL.rmsnorm(residual, w.L[0]["attn_norm"], 1e-5, dtype)
+    for l in range(w.layers):
+        lw = sw.L[l]
+        qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+        attn = OA.decode_attention(qkv, cache, [[0], [1]], hist, l, sw.heads, sw.kv_heads, rope)
+        o = allreduce_T(OL.linear(attn, lw["wo"]["deq"], dtype))
+        x, residual = OL.residual_rmsnorm(o, residual, w.L[l]["ffn_norm"], 1e-5, dtype)
+        a = OL.linear_gated_silu(x, lw["w1w3"]["deq"], dtype)
+        f = allreduce_T(OL.linear(a, lw["w2"]["deq"], dtype))
+        nxt = w.L[l + 1]["attn_norm"] if l + 1 < w.layers else w.final_norm
+        x, residual = OL.residual_rmsnorm(f, residual, nxt, 1e-5, dtype)
+    local = torch.from_numpy(OL.linear(x, sw.output["deq"], dtype))
+    parts = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(parts, local)
+    logits = torch.cat(parts, 1).numpy()
+    if rank == 0:
+        q.put(logits)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_tp2_gloo_matches_single_process_oracle():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    logits = q.get(timeout=150)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=512, vocab=256, seed=5)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
+    caches = [OA.PagedKvCache(2, w.layers, OA.KvLayout(1, 64, 128, 8), F16) for _ in range(world)]
+    ref, _ = decode_step(w, np.array([3, 9]), None, [[0], [1]], np.array([0, 0], np.int32), rope,
+                         tp_shards=[w.shard(r, world) for r in range(world)], caches=caches)
+    assert (logits == ref).all()          # identical arithmetic, identical order -> bit-identical
+    # and TP changes the single-GPU result only by fp16 summation order
+    c1 = OA.PagedKvCache(2, w.layers, OA.KvLayout(2, 64, 128, 8), F16)
+    ref1, _ = decode_step(w, np.array([3, 9]), c1, [[0], [1]], np.array([0, 0], np.int32), rope)
+    assert np.abs(ref1 - ref).max() < 2e-3
