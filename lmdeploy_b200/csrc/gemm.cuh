@@ -52,10 +52,37 @@ __device__ long long g_trace[kTraceCtas][kTraceRoles][kTraceSlots];
         const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                                            \
         if (_c < kTraceCtas && (slot) < kTraceSlots) g_trace[_c][role][slot] = clock64();                              \
     } while (0)
+// watchdog wait: records (tag, cta, iteration) of the first wait that does not complete and traps
+__device__ int           g_hang[8];
+__device__ volatile int* g_hang_host;  // mapped pinned host memory: survives a dead context
+B200_DEVICE void mbar_wait_dbg(uint32_t bar, uint32_t parity, int tag, int it)
+{
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (*(volatile int*)&g_hang[0] != 0) {
+            return;  // somebody already timed out: drain the kernel
+        }
+        if (clock64() - t0 > 200000000ll) {
+            if (atomicCAS(&g_hang[0], 0, 1) == 0) {
+                g_hang[1] = tag, g_hang[2] = blockIdx.x, g_hang[3] = blockIdx.y, g_hang[4] = it, g_hang[5] = threadIdx.x;
+                g_hang[6] = (int)parity;
+                if (g_hang_host) {
+                    for (int q = 1; q < 7; ++q) g_hang_host[q] = g_hang[q];
+                    g_hang_host[0] = 1;
+                    __threadfence_system();
+                }
+                __threadfence();
+            }
+            return;
+        }
+    }
+}
+#define GEMM_WAIT(bar, parity, tag, it) mbar_wait_dbg(bar, parity, tag, it)
 #else
 #define GEMM_TRACE(role, slot)                                                                                         \
     do {                                                                                                               \
     } while (0)
+#define GEMM_WAIT(bar, parity, tag, it) mbar_wait(bar, parity)
 #endif
 
 struct Params {
@@ -142,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         for (int s = 0; s < kMaxStages; ++s) {
             mbar_init(smem_u32(&bar_full[s]), 1);
             mbar_init(smem_u32(&bar_empty[s]), 1);
-            mbar_init(smem_u32(&bar_aready[s]), 128);
+            mbar_init(smem_u32(&bar_aready[s]), 256);
         }
         mbar_init(smem_u32(&bar_dready), 1);
         fence_mbar_init();
@@ -163,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             int      s  = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nk; ++i) {
-                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                GEMM_WAIT(smem_u32(&bar_empty[s]), ph ^ 1, 1, i);
                 GEMM_TRACE(0, i);
                 const uint32_t bar = smem_u32(&bar_full[s]);
                 const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
@@ -184,9 +211,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             int      s  = 0;
             uint32_t ph = 0;
             for (int i = 0; i < nk; ++i) {
-                mbar_wait(smem_u32(&bar_full[s]), ph);
+                GEMM_WAIT(smem_u32(&bar_full[s]), ph, 2, i);
                 if (FMT != kDense) {
-                    mbar_wait(smem_u32(&bar_aready[s]), ph);
+                    GEMM_WAIT(smem_u32(&bar_aready[s]), ph, 3, i);
                 }
                 umma::fence_after_sync();
                 GEMM_TRACE(3, i);
@@ -221,44 +248,44 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         const int      n_local   = lane_base + lane;
         const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
         if constexpr (FMT == kU4) {
-            int      s  = grp % p.stages;
-            uint32_t ph = (grp / p.stages) & 1;
-            for (int i = grp; i < nk; i += 2) {
-                mbar_wait(smem_u32(&bar_full[s]), ph);
+            // Every dequant warp takes part in EVERY stage (warps 2-5: k-chunk 0, warps 6-9: k-chunk 1 of the
+            // 128-wide group), so each thread observes every phase of bar_full[s] (a parity wait is ambiguous for
+            // a waiter that skips phases) and the per-stage dequant latency is halved.
+            const int c  = grp;
+            int       s  = 0;
+            uint32_t  ph = 0;
+            for (int i = 0; i < nk; ++i) {
+                GEMM_WAIT(smem_u32(&bar_full[s]), ph, 4, i);
                 if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(1, i);
                 const uint32_t wsm = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
                 const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int hh = 0; hh < 2; ++hh) {
+                    const uint4 v = lds128(wsm + ((c * 2 + hh) * 128 + n_local) * 16);
+                    uint32_t    r[16];
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const uint4 v = lds128(wsm + ((c * 2 + hh) * 128 + n_local) * 16);
-                        uint32_t    r[16];
+                    for (int u = 0; u < 4; ++u) {
+                        uint32_t h[4];
+                        Ops::cvt_u4x8((&v.x)[u], h);
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            uint32_t h[4];
-                            Ops::cvt_u4x8((&v.x)[u], h);
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
-                        }
-                        umma::st_32x32b_x16(trow + p.a_col + s * 64 + c * 32 + hh * 16, r);
+                        for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
                     }
+                    umma::st_32x32b_x16(trow + p.a_col + s * 64 + c * 32 + hh * 16, r);
                 }
                 umma::wait_st();
                 umma::fence_before_sync();
                 mbar_arrive(smem_u32(&bar_aready[s]));
                 if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(2, i);
-                s += 2;
-                while (s >= p.stages) {
-                    s -= p.stages;
+                if (++s == p.stages) {
+                    s = 0;
                     ph ^= 1;
                 }
             }
         }
         // ================================ epilogue (group 0) ================================
         if (grp == 0) {
-            mbar_wait(smem_u32(&bar_dready), 0);
+            GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
             umma::fence_after_sync();
             if (threadIdx.x == 64) GEMM_TRACE(4, 2);
             const int n_g = nt * kBN + n_local;

@@ -40,10 +40,33 @@ int main(int argc, char** argv)
     const int iters  = argc > 2 ? atoi(argv[2]) : 20;
     const int dump   = argc > 3 ? atoi(argv[3]) : 1;
     const int mt     = (m + 15) / 16 * 16;
-    Shape     shapes[] = {{"qkv", 4096, 6144, 0, 1}, {"wo", 4096, 4096, 0, 1}, {"w1w3", 4096, 28672, 1, 1},
-                          {"w2", 14336, 4096, 0, 1}, {"lm_head", 4096, 92544, 0, 0}};
+    Shape     shapes[] = {{"w2", 14336, 4096, 0, 1}, {"qkv", 4096, 6144, 0, 1}, {"wo", 4096, 4096, 0, 1},
+                          {"w1w3", 4096, 28672, 1, 1}, {"lm_head", 4096, 92544, 0, 0}};
+    setvbuf(stdout, nullptr, _IONBF, 0);
     cudaStream_t st;
     CK(cudaStreamCreate(&st));
+#ifdef B200_GEMM_TRACE
+    int* hang_host = nullptr;
+    CK(cudaHostAlloc((void**)&hang_host, 64, cudaHostAllocMapped));
+    memset(hang_host, 0, 64);
+    {
+        int* dptr = nullptr;
+        CK(cudaHostGetDevicePointer((void**)&dptr, hang_host, 0));
+        CK(cudaMemcpyToSymbol(b200::gemm::g_hang_host, &dptr, sizeof(dptr)));
+    }
+#define CKH(x)                                                                                                         \
+    do {                                                                                                               \
+        cudaError_t e_ = (x);                                                                                          \
+        if (e_ != cudaSuccess) {                                                                                       \
+            printf("CUDA error %s at line %d; hang record: set=%d tag=%d cta=(%d,%d) iter=%d thread=%d parity=%d\n",   \
+                   cudaGetErrorString(e_), __LINE__, hang_host[0], hang_host[1], hang_host[2], hang_host[3],           \
+                   hang_host[4], hang_host[5], hang_host[6]);                                                          \
+            exit(1);                                                                                                   \
+        }                                                                                                              \
+    } while (0)
+#else
+#define CKH(x) CK(x)
+#endif
     for (const Shape& s : shapes) {
         b200_linear_desc d{};
         d.input_dim = s.K, d.output_dim = s.N, d.weight_format = s.fmt, d.dtype = B200_DTYPE_F16, d.group_size = 128;
@@ -74,8 +97,24 @@ int main(int argc, char** argv)
                 exit(1);
             }
         };
-        for (int i = 0; i < 3; ++i) run(i);
-        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 3; ++i) {
+            run(i);
+            CKH(cudaStreamSynchronize(st));
+        }
+#ifdef B200_GEMM_TRACE
+        {
+            int hang[8];
+            CK(cudaMemcpyFromSymbol(hang, b200::gemm::g_hang, sizeof(hang)));
+            if (hang[0]) {
+                printf("%-8s m=%d HANG: wait tag %d (1 empty/producer, 2 full/mma, 3 aready/mma, 4 full/dequant, 5 dready) "
+                       "cta (%d,%d) iter %d thread %d parity %d\n",
+                       s.name, m, hang[1], hang[2], hang[3], hang[4], hang[5], hang[6]);
+                memset(hang, 0, sizeof(hang));
+                CK(cudaMemcpyToSymbol(b200::gemm::g_hang, hang, sizeof(hang)));
+                continue;
+            }
+        }
+#endif
         CK(cudaEventRecord(e0, st));
         for (int i = 0; i < iters; ++i) run(i + 3);
         CK(cudaEventRecord(e1, st));
