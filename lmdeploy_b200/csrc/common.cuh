@@ -96,6 +96,20 @@ B200_DEVICE uint64_t make_evict_first_policy()
     return p;
 }
 
+// true in exactly one (converged) lane of the warp; keeps the surrounding code warp-uniform for ptxas
+B200_DEVICE bool elect_one()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 B200_DEVICE void named_bar_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

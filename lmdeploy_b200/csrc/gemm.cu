@@ -96,20 +96,25 @@ __global__ void pack_x_kernel(T* xp, const T* x, int M, int MT, int K, int64_t l
 
 static int pick_splits(int N, int K, int MT)
 {
-    // aim at one wave of (148 SMs x CTAs per SM) CTAs, at least 4 K-groups per CTA; a pure function of the shape
-    const int nts    = N / kBN, kgs = K / kKG;
-    const int target = 148 * (MT <= 64 ? 2 : 1);
-    int       s      = target / nts;
-    s                = std::max(1, std::min(s, std::min(kgs / 4, 16)));
-    return std::max(1, s);
+    // K is split over a thread-block cluster (1, 2, 4 or 8 CTAs along grid.y) whose partial sums meet in shared
+    // memory (gemm.cuh epilogue).  Largest cluster that still fits one wave of (148 SMs x resident CTAs) and
+    // leaves every CTA at least 4 K-groups (2 for the largest K); a pure function of the shape => deterministic.
+    const int nts = N / kBN, kgs = K / kKG;
+    const int slots = 148 * (MT <= 64 ? 2 : 1);
+    int       s   = 1;
+    while (s < 8 && nts * (s * 2) <= slots && kgs / (s * 2) >= 4 && MT % (s * 2) == 0) {
+        s *= 2;
+    }
+    return s;
 }
 
-static int pick_stages(int fmt, int MT)
+static int pick_stages(int fmt, int MT, int splits)
 {
     const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
     const int WB_pad = (WB + 1023) & ~1023;
     const int stage  = WB_pad + MT * 256;
-    int       st     = std::min(kMaxStages, (220 * 1024) / stage);
+    const int budget = 220 * 1024 - (splits > 1 ? MT * kBN * 4 : 0);
+    int       st     = std::min(kMaxStages, budget / stage);
     if (fmt != kDense && MT <= 64) {
         st = std::min(st, 3);  // 3 x 64 A columns + 64 D columns = 256 TMEM columns -> 2 CTAs / SM
     }
@@ -118,8 +123,6 @@ static int pick_stages(int fmt, int MT)
 
 struct LinearWs {
     void*  xp;
-    float* partials;
-    int*   counters;
     size_t total;
 };
 
@@ -130,17 +133,10 @@ static size_t align_up(size_t x, size_t a)
 
 static LinearWs carve_ws(void* base, int K, int N, int MT)
 {
+    (void)N;
     LinearWs w{};
-    size_t   off  = 0;
-    auto     take = [&](size_t bytes) {
-        void* p = base ? (char*)base + off : nullptr;
-        off += align_up(bytes, 256);
-        return p;
-    };
-    w.counters = (int*)take((size_t)(N / kBN) * 4 + 256);
-    w.xp       = take((size_t)K * MT * 2);
-    w.partials = (float*)take((size_t)(N / kBN) * 16 * MT * kBN * 4);
-    w.total    = off;
+    w.xp    = base;
+    w.total = align_up((size_t)K * MT * 2, 256);
     return w;
 }
 
@@ -149,18 +145,35 @@ static int launch(const Params& p, cudaStream_t st)
 {
     const int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
     const int WB_pad = (WB + 1023) & ~1023;
-    const int smem   = p.stages * (WB_pad + p.MT * 256);
+    const int smem   = p.stages * (WB_pad + p.MT * 256) + (p.splits > 1 ? p.MT * kBN * 4 : 0);
     auto      kern   = gemm_kernel<T, FMT>;
-    static int configured = 0;
-    if (configured < smem) {
+    static bool configured = false;
+    if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
         if (e != cudaSuccess) {
             return fail_cuda(e, "cudaFuncSetAttribute(gemm_kernel)");
         }
-        configured = 227 * 1024;
+        configured = true;
     }
-    dim3 grid(p.N / kBN, p.splits);
-    kern<<<grid, kThreads, smem, st>>>(p);
+    if (smem > 227 * 1024 - 2048) {
+        return fail(B200_ERR_UNSUPPORTED, "gemm: shared memory budget exceeded");
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = dim3(p.N / kBN, p.splits, 1);
+    cfg.blockDim         = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = p.splits;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs                = attr;
+    cfg.numAttrs             = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) {
+        return fail_cuda(e, "cudaLaunchKernelEx(gemm_kernel)");
+    }
     return check_launch("gemm_kernel");
 }
 
@@ -256,7 +269,7 @@ extern "C" int b200_pack_activations(const void* x, int64_t ldx, int m, int k, i
 }
 
 static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y, int64_t ldy, int epilogue,
-                          int out_mode, int out_mt, float* partials, int* counters, cudaStream_t st)
+                          int out_mode, int out_mt, cudaStream_t st)
 {
     if (mt < 16 || mt > 128 || mt % 16) {
         return fail(B200_ERR_UNSUPPORTED, "padded token count must be a multiple of 16 in [16, 128]");
@@ -268,15 +281,13 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.w        = (const uint8_t*)d->prepared;
     p.xp       = xp;
     p.y        = y;
-    p.partials = partials;
-    p.counters = counters;
     p.bias     = d->bias;
     p.N        = d->output_dim;
     p.K        = d->input_dim;
     p.MT       = mt;
     p.M        = m;
     p.splits   = pick_splits(p.N, p.K, mt);
-    p.stages   = pick_stages(d->weight_format, mt);
+    p.stages   = pick_stages(d->weight_format, mt, p.splits);
     if (d->weight_format == kDense) {
         p.tmem_cols = mt <= 32 ? 32 : (mt <= 64 ? 64 : 128);
         p.a_col     = 0;
@@ -318,7 +329,7 @@ extern "C" int b200_linear_forward(const b200_linear_desc* d, const void* x, int
     if (int e = b200_pack_activations(x, ldx, m, d->input_dim, mt, d->dtype, w.xp, stream)) {
         return e;
     }
-    return forward_packed(d, w.xp, mt, m, y, ldy, epilogue, 0, 0, w.partials, w.counters, st);
+    return forward_packed(d, w.xp, mt, m, y, ldy, epilogue, 0, 0, st);
 }
 
 extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y,
@@ -331,10 +342,7 @@ extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void*
     if (!d->prepared || !xp || !y) {
         return fail(B200_ERR_INVALID_ARG, "prepared / xp / y is NULL");
     }
-    LinearWs w = carve_ws(workspace, d->input_dim, d->output_dim, mt);
-    if (!workspace || workspace_bytes < w.total) {
-        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_linear_workspace_bytes)");
-    }
-    return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
-                          w.counters, (cudaStream_t)stream);
+    (void)workspace;
+    (void)workspace_bytes;
+    return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, (cudaStream_t)stream);
 }

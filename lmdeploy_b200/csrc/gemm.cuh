@@ -89,13 +89,11 @@ struct Params {
     const uint8_t* w;   // prepared weight stream
     const void*    xp;  // packed activations [K/8][MT][8] T
     void*          y;
-    float*         partials;  // [n_tile][split][MT][128] fp32
-    int*           counters;  // [n_tile], zero before first use; reset by the kernel
     const void*    bias;      // [N] T or null
     int            N, K;
     int            MT;  // padded token count (multiple of 16, <= 128)
     int            M;   // real tokens
-    int            splits;
+    int            splits;  // K splits = thread-block cluster size along grid.y (1, 2, 4 or 8)
     int            stages;
     int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
     int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
@@ -143,6 +141,48 @@ B200_DEVICE void finalize(const Params& p, int tok, int n_g, float acc)
     }
 }
 
+// two adjacent accumulator values (columns n_g, n_g + 1; n_g even) of one token
+template<class T>
+B200_DEVICE void finalize_pair(const Params& p, int tok, int n_g, float a0, float a1)
+{
+    using Ops = TypeOps<T>;
+    if (tok >= p.M) {
+        return;
+    }
+    if (p.bias) {
+        a0 += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g]);
+        a1 += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g + 1]);
+    }
+    if (p.epilogue == 1) {
+        const float silu = a0 / (1.f + expf(-a0));
+        store_out<T>(p, tok, n_g >> 1, silu * a1);
+    }
+    else {
+        T* y = reinterpret_cast<T*>(p.y);
+        T* d = p.out_mode == 0 ? y + (size_t)tok * p.ldy + n_g : y + ((size_t)(n_g >> 3) * p.out_mt + tok) * 8 + (n_g & 7);
+        *reinterpret_cast<uint32_t*>(d) = Ops::pack2(a0, a1);
+    }
+}
+
+B200_DEVICE uint32_t mapa_shared(uint32_t addr, int cta_rank)
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
+    return r;
+}
+B200_DEVICE void st_shared_cluster_f32(uint32_t addr, float v)
+{
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+B200_DEVICE void cluster_arrive_release()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+B200_DEVICE void cluster_wait_acquire()
+{
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 template<class T, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 {
@@ -151,9 +191,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     __shared__ uint64_t                       bar_full[kMaxStages], bar_empty[kMaxStages], bar_aready[kMaxStages];
     __shared__ uint64_t                       bar_dready;
     __shared__ uint32_t                       s_tmem;
-    __shared__ int                            s_last;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
     const int nt = blockIdx.x, sp = blockIdx.y;
     const int kgs = p.K / kKG;
     const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
@@ -181,6 +220,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tmem = s_tmem;
+    if (p.splits > 1) {
+        // every CTA of the cluster must be running before anyone stores into its shared memory
+        cluster_arrive_release();
+        cluster_wait_acquire();
+    }
     if (threadIdx.x == 64) GEMM_TRACE(4, 1);
 
     if (warp == 0) {
@@ -206,40 +250,51 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     }
     else if (warp == 1) {
         // ================================ MMA issuer ================================
-        if (lane == 0) {
-            const uint32_t idesc = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
-            int      s  = 0;
-            uint32_t ph = 0;
-            for (int i = 0; i < nk; ++i) {
-                GEMM_WAIT(smem_u32(&bar_full[s]), ph, 2, i);
-                if (FMT != kDense) {
-                    GEMM_WAIT(smem_u32(&bar_aready[s]), ph, 3, i);
-                }
-                umma::fence_after_sync();
-                GEMM_TRACE(3, i);
-                const uint32_t sbase = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t xbase = sbase + WB_pad;
+        // The whole warp runs this loop under warp-uniform control flow and one elected lane issues; every operand
+        // is derived from uniform values, so ptxas keeps descriptors in uniform registers and a k-step costs two
+        // uniform adds + UTCHMMA (a lane-0 branch makes it rebuild and R2UR every descriptor: ~100 cycles per MMA,
+        // which made the issue thread, not HBM, the bound of the whole kernel).
+        const uint32_t idesc  = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
+        const uint32_t b_step = (uint32_t)(2 * p.MT * 16) >> 4;  // descriptor start-address units per k-step
+        const uint32_t a_step = (uint32_t)(2 * kBN * 16) >> 4;
+        const uint32_t smem0  = smem_u32(smem);
+        int            s      = 0;
+        uint32_t       ph     = 0;
+        for (int i = 0; i < nk; ++i) {
+            GEMM_WAIT(smem_u32(&bar_full[s]), ph, 2, i);
+            if (FMT != kDense) {
+                GEMM_WAIT(smem_u32(&bar_aready[s]), ph, 3, i);
+            }
+            umma::fence_after_sync();
+            if (lane == 0) GEMM_TRACE(3, i);
+            const uint32_t sbase = smem0 + (uint32_t)s * (uint32_t)stage_bytes;
+            const uint64_t bd0   = umma::make_smem_desc(sbase + WB_pad, p.MT * 16, 128);
+            const uint64_t ad0   = umma::make_smem_desc(sbase, kBN * 16, 128);
+            const uint32_t a_tm  = tmem + p.a_col + s * 64;
+            if (elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < kKG / 16; ++ks) {
-                    const uint64_t bd = umma::make_smem_desc(xbase + ks * 2 * (p.MT * 16), p.MT * 16, 128);
                     const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
                     if (FMT == kDense) {
-                        const uint64_t ad = umma::make_smem_desc(sbase + ks * 2 * (kBN * 16), kBN * 16, 128);
-                        umma::mma_f16_ss(tmem, ad, bd, idesc, acc);
+                        umma::mma_f16_ss(tmem, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * b_step), idesc, acc);
                     }
                     else {
-                        umma::mma_f16_ts(tmem, tmem + p.a_col + s * 64 + ks * 8, bd, idesc, acc);
+                        umma::mma_f16_ts(tmem, a_tm + ks * 8, bd0 + (uint64_t)(ks * b_step), idesc, acc);
                     }
                 }
                 umma::commit(smem_u32(&bar_empty[s]));
-                GEMM_TRACE(5, i);
-                if (++s == p.stages) {
-                    s = 0;
-                    ph ^= 1;
-                }
             }
+            __syncwarp();
+            if (lane == 0) GEMM_TRACE(5, i);
+            if (++s == p.stages) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        if (elect_one()) {
             umma::commit(smem_u32(&bar_dready));
         }
+        __syncwarp();
     }
     else {
         // ================================ dequant warps ================================
@@ -283,63 +338,64 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 }
             }
         }
-        // ================================ epilogue (group 0) ================================
-        if (grp == 0) {
-            GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
-            umma::fence_after_sync();
-            if (threadIdx.x == 64) GEMM_TRACE(4, 2);
-            const int n_g = nt * kBN + n_local;
-            if (p.splits == 1) {
-                for (int t0 = 0; t0 < p.MT; t0 += 16) {
-                    uint32_t v[16];
-                    umma::ld_32x32b_x16(trow + t0, v);
-                    umma::wait_ld();
+        // ================================ epilogue, part 1 (all 8 warps) ================================
+        // warps 2-5 take tokens [0, MT/2), warps 6-9 tokens [MT/2, MT) of the 32 accumulator rows their TMEM lane
+        // quarter holds.  splits == 1: straight to the output.  splits > 1 (thread-block cluster along K): each
+        // value goes to the shared memory of the cluster CTA that owns its token (reduce-scatter over DSMEM).
+        GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
+        umma::fence_after_sync();
+        if (threadIdx.x == 64) GEMM_TRACE(4, 2);
+        const int n_g  = nt * kBN + n_local;
+        const int half = p.MT >> 1;
+        if (p.splits == 1) {
+            for (int t0 = grp * half; t0 < (grp + 1) * half; t0 += 8) {
+                uint32_t v[8];
+                umma::ld_32x32b_x8(trow + t0, v);
+                umma::wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
-                }
+                for (int i = 0; i < 8; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
             }
-            else {
-                float* ws = p.partials + ((size_t)nt * p.splits + sp) * p.MT * kBN;
-                for (int t0 = 0; t0 < p.MT; t0 += 16) {
-                    uint32_t v[16];
-                    umma::ld_32x32b_x16(trow + t0, v);
-                    umma::wait_ld();
+        }
+        else {
+            const int      tps = p.MT / p.splits;  // tokens owned per cluster CTA
+            const uint32_t red = smem_u32(smem) + (uint32_t)p.stages * (uint32_t)stage_bytes;
+            // my slot in every owner's buffer: red[src = sp][tl][n]
+            const uint32_t mine = red + (uint32_t)((sp * tps) * kBN + n_local) * 4u;
+            for (int t0 = grp * half; t0 < (grp + 1) * half; t0 += 8) {
+                uint32_t v[8];
+                umma::ld_32x32b_x8(trow + t0, v);
+                umma::wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) ws[(size_t)(t0 + i) * kBN + n_local] = __uint_as_float(v[i]);
-                }
-                __threadfence();
-                named_bar_sync(1, 128);
-                if (threadIdx.x == 64) {
-                    const int old = atomicAdd(&p.counters[nt], 1);
-                    s_last        = (old == p.splits - 1);
-                }
-                named_bar_sync(1, 128);
-                if (s_last) {
-                    __threadfence();
-                    const float* base = p.partials + (size_t)nt * p.splits * p.MT * kBN + n_local;
-                    // 8 tokens x all splits of independent loads in flight per thread (one L2 round trip per batch)
-                    for (int t0 = 0; t0 < p.MT; t0 += 8) {
-                        float acc[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-                        for (int k = 0; k < p.splits; ++k) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) v[j] = __ldcg(base + ((size_t)k * p.MT + t0 + j) * kBN);
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) acc[j] += v[j];
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) finalize<T>(p, t0 + j, n_g, acc[j]);
-                    }
-                    if (threadIdx.x == 64) {
-                        p.counters[nt] = 0;
-                    }
+                for (int i = 0; i < 8; ++i) {
+                    const int      t     = t0 + i;
+                    const int      owner = t / tps;
+                    const uint32_t dst   = mapa_shared(mine + (uint32_t)((t - owner * tps) * kBN) * 4u, owner);
+                    st_shared_cluster_f32(dst, __uint_as_float(v[i]));
                 }
             }
         }
     }
     if (threadIdx.x == 64) GEMM_TRACE(4, 3);
+    if (p.splits > 1) {
+        // ================================ epilogue, part 2: owner-side ordered sum ================================
+        cluster_arrive_release();
+        cluster_wait_acquire();
+        if (warp >= 2) {
+            const int      tps  = p.MT / p.splits;
+            const int      tid  = threadIdx.x - 64;  // 0..255
+            const uint8_t* redp = smem + (size_t)p.stages * stage_bytes;
+            for (int idx = tid; idx < tps * (kBN / 2); idx += 256) {
+                const int tl = idx / (kBN / 2), np = idx % (kBN / 2);
+                float2    acc = make_float2(0.f, 0.f);
+                for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
+                    const float2 v = *reinterpret_cast<const float2*>(redp + ((size_t)(r * tps + tl) * kBN + 2 * np) * 4);
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                finalize_pair<T>(p, sp * tps + tl, nt * kBN + 2 * np, acc.x, acc.y);
+            }
+        }
+    }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) {

@@ -123,7 +123,7 @@ int main(int argc, char** argv)
         CK(cudaEventElapsedTime(&ms, e0, e1));
         const double us = ms * 1e3 / iters;
         printf("%-8s K=%5d N=%5d m=%d splits=%d stages=%d  %8.2f us  %7.1f GB/s (weights %.1f MB)\n", s.name, s.K, s.N, m,
-               b200::gemm::pick_splits(s.N, s.K, mt), b200::gemm::pick_stages(s.fmt, mt), us, wbytes / us * 1e-3,
+               b200::gemm::pick_splits(s.N, s.K, mt), b200::gemm::pick_stages(s.fmt, mt, b200::gemm::pick_splits(s.N, s.K, mt)), us, wbytes / us * 1e-3,
                wbytes / 1e6);
 #ifdef B200_GEMM_TRACE
         if (dump) {
