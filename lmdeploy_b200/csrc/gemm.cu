@@ -94,31 +94,54 @@ __global__ void pack_x_kernel(T* xp, const T* x, int M, int MT, int K, int64_t l
     }
 }
 
-static int pick_splits(int N, int K, int MT)
-{
-    // K is split over a thread-block cluster (1, 2, 4 or 8 CTAs along grid.y) whose partial sums meet in shared
-    // memory (gemm.cuh epilogue).  Largest cluster that still fits one wave of (148 SMs x resident CTAs) and
-    // leaves every CTA at least 4 K-groups (2 for the largest K); a pure function of the shape => deterministic.
-    const int nts = N / kBN, kgs = K / kKG;
-    const int slots = 148 * (MT <= 64 ? 2 : 1);
-    int       s   = 1;
-    while (s < 8 && nts * (s * 2) <= slots && kgs / (s * 2) >= 4 && MT % (s * 2) == 0) {
-        s *= 2;
-    }
-    return s;
-}
+struct Plan {
+    int tiles, splits, nw, nx, na, tmem_cols, a_col, smem;
+};
 
-static int pick_stages(int fmt, int MT, int splits)
+// Launch plan: a pure function of (format, shape, padded tokens) => deterministic results.
+//   * u4 with N % 256 == 0: two n-tiles per CTA (shared activation tile), ONE CTA per SM with the whole
+//     shared-memory / TMEM budget spent on ring depth (the pipeline, not a second CTA, hides the latency);
+//   * otherwise one n-tile per CTA; u4 with MT <= 64 keeps to 256 TMEM columns / ~113 KB so two CTAs fit an SM;
+//   * K is split over a thread-block cluster of 1/2/4/8 CTAs (largest that still fits one wave and leaves every
+//     CTA >= 4 K-groups); the rings double as the split-K exchange buffer.
+static Plan make_plan(int fmt, int MT, int N, int K)
 {
     const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
     const int WB_pad = (WB + 1023) & ~1023;
-    const int stage  = WB_pad + MT * 256;
-    const int budget = 220 * 1024 - (splits > 1 ? MT * kBN * 4 : 0);
-    int       st     = std::min(kMaxStages, budget / stage);
-    if (fmt != kDense && MT <= 64) {
-        st = std::min(st, 3);  // 3 x 64 A columns + 64 D columns = 256 TMEM columns -> 2 CTAs / SM
+    const int XB     = MT * 256;
+    Plan      pl{};
+    pl.tiles         = (fmt == kU4 && N % (2 * kBN) == 0) ? 2 : 1;
+    const bool two_per_sm = pl.tiles == 1 && fmt != kDense && MT <= 64;
+    const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
+    const int  slots = 148 * (two_per_sm ? 2 : 1);
+    pl.splits = 1;
+    while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4 && MT % (pl.splits * 2) == 0) {
+        pl.splits *= 2;
     }
-    return std::max(2, st);
+    const int budget = (two_per_sm ? 113 : 224) * 1024 - 1024;
+    const int wslot  = WB_pad * pl.tiles;
+    // both rings want ~5-6 slots in flight (each loop is ~2.5-3k cycles of latency per slot)
+    pl.nx = std::min(kMaxX, std::max(3, (budget * 2 / 5) / XB));
+    pl.nw = std::min(kMaxW, (budget - pl.nx * XB) / wslot);
+    if (pl.nw < 3) {
+        pl.nw = 3;
+        pl.nx = std::max(2, std::min(kMaxX, (budget - pl.nw * wslot) / XB));
+    }
+    pl.smem = pl.nw * wslot + pl.nx * XB;
+    const int d_cols = (MT <= 64 ? 64 : 128) * pl.tiles;
+    if (fmt == kDense) {
+        pl.tmem_cols = MT <= 32 ? 32 : (MT <= 64 ? 64 : 128);
+        pl.a_col = 0, pl.na = 1;
+    }
+    else if (two_per_sm) {
+        pl.tmem_cols = 256, pl.a_col = 64, pl.na = 3;
+    }
+    else {
+        pl.tmem_cols = 512, pl.a_col = d_cols;
+        pl.na        = std::min(kASlots, (512 - d_cols) / 64);
+        pl.na -= pl.na % pl.tiles;
+    }
+    return pl;
 }
 
 struct LinearWs {
@@ -140,13 +163,10 @@ static LinearWs carve_ws(void* base, int K, int N, int MT)
     return w;
 }
 
-template<class T, int FMT>
-static int launch(const Params& p, cudaStream_t st)
+template<class T, int FMT, int TILES>
+static int launch(const Params& p, int smem, cudaStream_t st)
 {
-    const int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
-    const int WB_pad = (WB + 1023) & ~1023;
-    const int smem   = p.stages * (WB_pad + p.MT * 256) + (p.splits > 1 ? p.MT * kBN * 4 : 0);
-    auto      kern   = gemm_kernel<T, FMT>;
+    auto        kern       = gemm_kernel<T, FMT, TILES>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
@@ -159,7 +179,7 @@ static int launch(const Params& p, cudaStream_t st)
         return fail(B200_ERR_UNSUPPORTED, "gemm: shared memory budget exceeded");
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim          = dim3(p.N / kBN, p.splits, 1);
+    cfg.gridDim          = dim3(p.N / (kBN * TILES), p.splits, 1);
     cfg.blockDim         = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream           = st;
@@ -286,26 +306,21 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.K        = d->input_dim;
     p.MT       = mt;
     p.M        = m;
-    p.splits   = pick_splits(p.N, p.K, mt);
-    p.stages   = pick_stages(d->weight_format, mt, p.splits);
-    if (d->weight_format == kDense) {
-        p.tmem_cols = mt <= 32 ? 32 : (mt <= 64 ? 64 : 128);
-        p.a_col     = 0;
-    }
-    else {
-        const int need = mt <= 64 ? 64 + p.stages * 64 : 128 + p.stages * 64;
-        p.tmem_cols    = need <= 256 ? 256 : 512;
-        p.a_col        = mt <= 64 ? 64 : 128;
-    }
+    const Plan rg = make_plan(d->weight_format, mt, p.N, p.K);
+    p.splits = rg.splits, p.nw = rg.nw, p.nx = rg.nx, p.na = rg.na;
+    p.tmem_cols = rg.tmem_cols, p.a_col = rg.a_col;
     p.epilogue = epilogue;
     p.out_mode = out_mode;
     p.ldy      = (int)ldy;
     p.out_mt   = out_mt;
     const bool bf = d->dtype == B200_DTYPE_BF16;
     if (d->weight_format == kU4) {
-        return bf ? launch<nv_bfloat16, kU4>(p, st) : launch<half, kU4>(p, st);
+        if (rg.tiles == 2) {
+            return bf ? launch<nv_bfloat16, kU4, 2>(p, rg.smem, st) : launch<half, kU4, 2>(p, rg.smem, st);
+        }
+        return bf ? launch<nv_bfloat16, kU4, 1>(p, rg.smem, st) : launch<half, kU4, 1>(p, rg.smem, st);
     }
-    return bf ? launch<nv_bfloat16, kDense>(p, st) : launch<half, kDense>(p, st);
+    return bf ? launch<nv_bfloat16, kDense, 1>(p, rg.smem, st) : launch<half, kDense, 1>(p, rg.smem, st);
 }
 
 extern "C" int b200_linear_forward(const b200_linear_desc* d, const void* x, int64_t ldx, int m, void* y, int64_t ldy,

@@ -7,15 +7,18 @@
 //     Y^T[N_out, tokens] = W^T[N_out, K] . X^T[K, tokens]
 // so the streamed operand (weights) sits on the UMMA M side (128 output features per CTA) and the tiny
 // activation tile is UMMA N (16..128 tokens).  Per 128-wide K group (= one AWQ quant group):
-//   * a producer thread issues two 1-D TMA bulk copies: one contiguous 8.5 KB block of packed u4 weights +
-//     their fused (scale, -zero*scale) pairs, and the contiguous activation tile (already in UMMA
-//     K-major "interleaved" layout in global memory);
+//   * warp 0 streams the packed weights (one contiguous 8.5 KB 1-D TMA bulk copy per group: u4 data + fused
+//     (scale, -zero*scale) pairs) into a deep W ring; warp 10 streams the activation tiles (already in the
+//     UMMA K-major "interleaved" layout in global memory, L2 resident) into a separate X ring.  The rings are
+//     decoupled because their lifetimes differ: a W slot is free as soon as it has been de-quantised (long
+//     before its MMAs retire) and it is the DRAM-latency-bound stream, so it gets the depth;
 //   * 8 dequant warps unpack u4 -> f16 with lop3 and apply w = fma(q, s, t) in f16 (bit-identical to the
 //     reference's transform, transform.h:48-74 / cast.cu:155) and write the A operand straight into
-//     TENSOR MEMORY with tcgen05.st (no shared-memory round trip for the dequantised weights);
-//   * one thread issues tcgen05.mma (A from TMEM, B from smem), fp32 accumulators in TMEM;
-//   * the epilogue reads accumulators with tcgen05.ld, does the deterministic split-K fix-up through an
-//     fp32 workspace (last-arriving CTA reduces in split order), bias / gated-SiLU, and writes fp16/bf16.
+//     TENSOR MEMORY with tcgen05.st (3-slot ring; no shared-memory round trip for the dequantised weights);
+//   * warp 1 issues tcgen05.mma (A from TMEM, B from smem) from a warp-uniform loop, fp32 accumulators in TMEM;
+//   * K is split over a thread-block cluster (grid.y); the partial accumulators are reduce-scattered by token
+//     through distributed shared memory and summed in rank order (deterministic), then bias / gated-SiLU and the
+//     fp16/bf16 store.  No global workspace, no second kernel.
 // The kernel is HBM-bound at decode batch sizes: algorithmic bytes = packed weight stream, read once.
 #pragma once
 
@@ -26,10 +29,16 @@ namespace gemm {
 
 constexpr int kBN        = 128;  // output features per CTA (UMMA M)
 constexpr int kKG        = 128;  // K per pipeline stage (= quant group size)
-constexpr int kMaxStages = 4;
-constexpr int kThreads   = 320;  // warp0 TMA, warp1 MMA/TMEM, warps2-5 dequant A + epilogue, warps6-9 dequant B
-// TMEM budget: D accumulators occupy columns [0, MT); the dequantised A operand uses 64 columns per stage starting
-// at column a_col.  MT <= 64 with 3 stages fits 256 columns, so two CTAs can be resident per SM.
+constexpr int kMaxW     = 8;    // W ring slots (barrier arrays)
+constexpr int kMaxX     = 6;    // X ring slots
+constexpr int kASlots   = 4;    // max TMEM A-operand ring slots (64 columns each); Params::na in use
+constexpr int kDqWarps  = 16;   // dequant warps: 4 per TMEM lane quarter, one 32-wide k-chunk each
+constexpr int kXWarp    = 2 + kDqWarps;
+constexpr int kMmaWarp2 = kXWarp + 1;  // second MMA issuer (tile 1 of a two-tile CTA)
+constexpr int kThreads  = 32 * (kMmaWarp2 + 1);  // warp0 W-TMA, warp1 MMA/TMEM, warps2-17 dequant (+ epilogue), warp18 X-TMA,
+                                                 // warp19 MMA of tile 1
+// TMEM budget: D accumulators occupy columns [0, MT); the dequantised A operand ring starts at column a_col.
+// MT <= 64: 64 + 3 x 64 = 256 columns, so two CTAs can be resident per SM.
 
 enum WeightFormat : int
 {
@@ -45,7 +54,7 @@ constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // data + block scale (T,
 // Development aid (tools/gemm_trace.cu compiles this TU with -DB200_GEMM_TRACE): per-role clock64 stamps of the
 // first kTraceCtas CTAs.  Absent from the product build.
 #ifdef B200_GEMM_TRACE
-constexpr int kTraceCtas = 8, kTraceRoles = 6, kTraceSlots = 128;
+constexpr int kTraceCtas = 8, kTraceRoles = 8, kTraceSlots = 128;
 __device__ long long g_trace[kTraceCtas][kTraceRoles][kTraceSlots];
 #define GEMM_TRACE(role, slot)                                                                                         \
     do {                                                                                                               \
@@ -94,7 +103,8 @@ struct Params {
     int            MT;  // padded token count (multiple of 16, <= 128)
     int            M;   // real tokens
     int            splits;  // K splits = thread-block cluster size along grid.y (1, 2, 4 or 8)
-    int            stages;
+    int            nw, nx;  // W / X ring depths
+    int            na;      // TMEM A-ring slots (multiple of TILES)
     int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
     int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
     int            ldy;
@@ -132,7 +142,7 @@ B200_DEVICE void finalize(const Params& p, int tok, int n_g, float acc)
     if (p.epilogue == 1) {
         const float other = __shfl_xor_sync(0xffffffffu, acc, 1);
         if ((n_g & 1) == 0 && tok < p.M) {
-            const float silu = acc / (1.f + expf(-acc));
+            const float silu = __fdividef(acc, 1.f + __expf(-acc));
             store_out<T>(p, tok, n_g >> 1, silu * other);
         }
     }
@@ -154,7 +164,7 @@ B200_DEVICE void finalize_pair(const Params& p, int tok, int n_g, float a0, floa
         a1 += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g + 1]);
     }
     if (p.epilogue == 1) {
-        const float silu = a0 / (1.f + expf(-a0));
+        const float silu = __fdividef(a0, 1.f + __expf(-a0));
         store_out<T>(p, tok, n_g >> 1, silu * a1);
     }
     else {
@@ -174,6 +184,14 @@ B200_DEVICE void st_shared_cluster_f32(uint32_t addr, float v)
 {
     asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+B200_DEVICE void st_shared_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+B200_DEVICE void st_shared_cluster_v2(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared::cluster.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 B200_DEVICE void cluster_arrive_release()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -183,223 +201,324 @@ B200_DEVICE void cluster_wait_acquire()
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-template<class T, int FMT>
+// TILES = n-tiles (128 output features each) per CTA.  TILES == 2 shares every activation tile between two weight
+// tiles: the X stream (2x the W bytes at 64 tokens) is what saturates the L2->SM path, so this halves the ingest
+// per weight byte.  TMEM: D accumulators of tile t at column t * d_stride, then an A ring of p.na 64-column slots
+// used round-robin by (k-group, tile).
+template<class T, int FMT, int TILES>
 __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 {
     using Ops = TypeOps<T>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ uint64_t                       bar_full[kMaxStages], bar_empty[kMaxStages], bar_aready[kMaxStages];
-    __shared__ uint64_t                       bar_dready;
-    __shared__ uint32_t                       s_tmem;
+    __shared__ uint64_t bar_wfull[kMaxW], bar_wempty[kMaxW];
+    __shared__ uint64_t bar_xfull[kMaxX], bar_xempty[kMaxX];
+    __shared__ uint64_t bar_aready[kASlots], bar_aempty[kASlots];
+    __shared__ uint64_t bar_dready;
+    __shared__ uint32_t s_tmem;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
-    const int nt = blockIdx.x, sp = blockIdx.y;
+    const int nt0 = blockIdx.x * TILES, sp = blockIdx.y;
     const int kgs = p.K / kKG;
     const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
     const int nk = kg1 - kg0;
     if (threadIdx.x == 64) GEMM_TRACE(4, 0);
 
-    constexpr int WB     = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
-    const int     XB     = p.MT * 256;  // 16 k8-chunks x MT x 16 B
-    const int     WB_pad = (WB + 1023) & ~1023;
-    const int     stage_bytes = WB_pad + XB;
+    constexpr int  WB       = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    constexpr int  WB_pad   = (WB + 1023) & ~1023;
+    constexpr int  WSLOT    = WB_pad * TILES;
+    constexpr bool kDequant = FMT != kDense;
+    const int      NAt      = p.na / TILES;  // A-ring slots per tile (tile t owns slots [t * NAt, (t + 1) * NAt))
+    static_assert(kDequant || TILES == 1, "dense weights use one tile per CTA");
+    const int      XB       = p.MT * 256;  // 16 k8-chunks x MT x 16 B
+    const uint32_t w_ring   = smem_u32(smem);
+    const uint32_t x_ring   = w_ring + (uint32_t)p.nw * WSLOT;
+    const int      d_stride = p.MT <= 64 ? 64 : 128;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxStages; ++s) {
-            mbar_init(smem_u32(&bar_full[s]), 1);
-            mbar_init(smem_u32(&bar_empty[s]), 1);
-            mbar_init(smem_u32(&bar_aready[s]), 256);
+        for (int s = 0; s < kMaxW; ++s) {
+            mbar_init(smem_u32(&bar_wfull[s]), 1);
+            mbar_init(smem_u32(&bar_wempty[s]), kDequant ? kDqWarps * 32 : 1);
         }
-        mbar_init(smem_u32(&bar_dready), 1);
+        for (int s = 0; s < kMaxX; ++s) {
+            mbar_init(smem_u32(&bar_xfull[s]), 1);
+            mbar_init(smem_u32(&bar_xempty[s]), TILES);
+        }
+        for (int s = 0; s < kASlots; ++s) {
+            mbar_init(smem_u32(&bar_aready[s]), kDqWarps * 32 / TILES);
+            mbar_init(smem_u32(&bar_aempty[s]), 1);
+        }
+        mbar_init(smem_u32(&bar_dready), TILES);
         fence_mbar_init();
     }
-    if (warp == 1) {
-        umma::tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
-    }
-    umma::fence_before_sync();
     __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem = s_tmem;
-    if (p.splits > 1) {
-        // every CTA of the cluster must be running before anyone stores into its shared memory
-        cluster_arrive_release();
-        cluster_wait_acquire();
-    }
-    if (threadIdx.x == 64) GEMM_TRACE(4, 1);
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
+        // ================================ W producer (starts before TMEM is allocated) ================================
         if (lane == 0) {
             const uint64_t pol_w = make_evict_first_policy();
             int      s  = 0;
             uint32_t ph = 0;
+            const uint8_t* src = p.w + ((size_t)nt0 * kgs + kg0) * WB;
             for (int i = 0; i < nk; ++i) {
-                GEMM_WAIT(smem_u32(&bar_empty[s]), ph ^ 1, 1, i);
+                GEMM_WAIT(smem_u32(&bar_wempty[s]), ph ^ 1, 1, i);
                 GEMM_TRACE(0, i);
-                const uint32_t bar = smem_u32(&bar_full[s]);
-                const uint32_t dst = smem_u32(smem + (size_t)s * stage_bytes);
-                mbar_expect_tx(bar, WB + XB);
-                bulk_g2s_hint(dst, p.w + ((size_t)nt * kgs + kg0 + i) * WB, WB, bar, pol_w);
-                bulk_g2s(dst + WB_pad, reinterpret_cast<const uint8_t*>(p.xp) + (size_t)(kg0 + i) * XB, XB, bar);
-                if (++s == p.stages) {
+                const uint32_t bar = smem_u32(&bar_wfull[s]);
+                mbar_expect_tx(bar, WB * TILES);
+#pragma unroll
+                for (int t = 0; t < TILES; ++t) {
+                    bulk_g2s_hint(w_ring + (uint32_t)s * WSLOT + t * WB_pad, src + ((size_t)t * kgs + i) * WB, WB, bar,
+                                  pol_w);
+                }
+                if (++s == p.nw) {
                     s = 0;
                     ph ^= 1;
                 }
             }
         }
     }
-    else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        // The whole warp runs this loop under warp-uniform control flow and one elected lane issues; every operand
-        // is derived from uniform values, so ptxas keeps descriptors in uniform registers and a k-step costs two
-        // uniform adds + UTCHMMA (a lane-0 branch makes it rebuild and R2UR every descriptor: ~100 cycles per MMA,
-        // which made the issue thread, not HBM, the bound of the whole kernel).
-        const uint32_t idesc  = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
-        const uint32_t b_step = (uint32_t)(2 * p.MT * 16) >> 4;  // descriptor start-address units per k-step
-        const uint32_t a_step = (uint32_t)(2 * kBN * 16) >> 4;
-        const uint32_t smem0  = smem_u32(smem);
-        int            s      = 0;
-        uint32_t       ph     = 0;
-        for (int i = 0; i < nk; ++i) {
-            GEMM_WAIT(smem_u32(&bar_full[s]), ph, 2, i);
-            if (FMT != kDense) {
-                GEMM_WAIT(smem_u32(&bar_aready[s]), ph, 3, i);
-            }
-            umma::fence_after_sync();
-            if (lane == 0) GEMM_TRACE(3, i);
-            const uint32_t sbase = smem0 + (uint32_t)s * (uint32_t)stage_bytes;
-            const uint64_t bd0   = umma::make_smem_desc(sbase + WB_pad, p.MT * 16, 128);
-            const uint64_t ad0   = umma::make_smem_desc(sbase, kBN * 16, 128);
-            const uint32_t a_tm  = tmem + p.a_col + s * 64;
-            if (elect_one()) {
-#pragma unroll
-                for (int ks = 0; ks < kKG / 16; ++ks) {
-                    const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
-                    if (FMT == kDense) {
-                        umma::mma_f16_ss(tmem, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * b_step), idesc, acc);
-                    }
-                    else {
-                        umma::mma_f16_ts(tmem, a_tm + ks * 8, bd0 + (uint64_t)(ks * b_step), idesc, acc);
-                    }
+    else if (warp == kXWarp) {
+        // ================================ X producer ================================
+        if (lane == 0) {
+            int      s  = 0;
+            uint32_t ph = 0;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xp) + (size_t)kg0 * XB;
+            for (int i = 0; i < nk; ++i) {
+                GEMM_WAIT(smem_u32(&bar_xempty[s]), ph ^ 1, 6, i);
+                GEMM_TRACE(6, i);
+                const uint32_t bar = smem_u32(&bar_xfull[s]);
+                mbar_expect_tx(bar, XB);
+                bulk_g2s(x_ring + (uint32_t)s * XB, src + (size_t)i * XB, XB, bar);
+                if (++s == p.nx) {
+                    s = 0;
+                    ph ^= 1;
                 }
-                umma::commit(smem_u32(&bar_empty[s]));
-            }
-            __syncwarp();
-            if (lane == 0) GEMM_TRACE(5, i);
-            if (++s == p.stages) {
-                s = 0;
-                ph ^= 1;
             }
         }
-        if (elect_one()) {
-            umma::commit(smem_u32(&bar_dready));
-        }
-        __syncwarp();
     }
     else {
-        // ================================ dequant warps ================================
-        const int      grp       = (warp - 2) >> 2;              // 0: warps 2-5, 1: warps 6-9
-        const int      lane_base = 32 * (warp & 3);              // TMEM lanes this warp may touch
-        const int      n_local   = lane_base + lane;
-        const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
-        if constexpr (FMT == kU4) {
-            // Every dequant warp takes part in EVERY stage (warps 2-5: k-chunk 0, warps 6-9: k-chunk 1 of the
-            // 128-wide group), so each thread observes every phase of bar_full[s] (a parity wait is ambiguous for
-            // a waiter that skips phases) and the per-stage dequant latency is halved.
-            const int c  = grp;
-            int       s  = 0;
-            uint32_t  ph = 0;
-            for (int i = 0; i < nk; ++i) {
-                GEMM_WAIT(smem_u32(&bar_full[s]), ph, 4, i);
-                if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(1, i);
-                const uint32_t wsm = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
-                const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const uint4 v = lds128(wsm + ((c * 2 + hh) * 128 + n_local) * 16);
-                    uint32_t    r[16];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        uint32_t h[4];
-                        Ops::cvt_u4x8((&v.x)[u], h);
-#pragma unroll
-                        for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
-                    }
-                    umma::st_32x32b_x16(trow + p.a_col + s * 64 + c * 32 + hh * 16, r);
-                }
-                umma::wait_st();
-                umma::fence_before_sync();
-                mbar_arrive(smem_u32(&bar_aready[s]));
-                if ((warp == 2 || warp == 6) && lane == 0) GEMM_TRACE(2, i);
-                if (++s == p.stages) {
-                    s = 0;
-                    ph ^= 1;
-                }
-            }
+        // the MMA and dequant warps need the TMEM base address
+        if (warp == 1) {
+            umma::tmem_alloc(smem_u32(&s_tmem), p.tmem_cols);
         }
-        // ================================ epilogue, part 1 (all 8 warps) ================================
-        // warps 2-5 take tokens [0, MT/2), warps 6-9 tokens [MT/2, MT) of the 32 accumulator rows their TMEM lane
-        // quarter holds.  splits == 1: straight to the output.  splits > 1 (thread-block cluster along K): each
-        // value goes to the shared memory of the cluster CTA that owns its token (reduce-scatter over DSMEM).
-        GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
+        umma::fence_before_sync();
+        named_bar_sync(1, (2 + kDqWarps) * 32);
         umma::fence_after_sync();
-        if (threadIdx.x == 64) GEMM_TRACE(4, 2);
-        const int n_g  = nt * kBN + n_local;
-        const int half = p.MT >> 1;
-        if (p.splits == 1) {
-            for (int t0 = grp * half; t0 < (grp + 1) * half; t0 += 8) {
-                uint32_t v[8];
-                umma::ld_32x32b_x8(trow + t0, v);
-                umma::wait_ld();
+        const uint32_t tmem = s_tmem;
+        if (threadIdx.x == 64) GEMM_TRACE(4, 1);
+
+        if (warp == 1 || warp == kMmaWarp2) {
+            // ================================ MMA issuers (one warp per n-tile) ================================
+            // The whole warp runs this loop under warp-uniform control flow and one elected lane issues; every
+            // operand is derived from uniform values, so ptxas keeps descriptors in uniform registers and a k-step
+            // costs two uniform adds + UTCHMMA.  A UTCHMMA still costs ~50 issue cycles, more than the 32 tensor
+            // cycles of a 128x64x16 MMA, so each tile of a two-tile CTA gets its own issuing warp.
+            const int t = warp == 1 ? 0 : 1;
+            if (t < TILES) {
+                const uint32_t idesc  = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
+                const uint32_t b_step = (uint32_t)(2 * p.MT * 16) >> 4;  // descriptor start-address units per k-step
+                const uint32_t a_step = (uint32_t)(2 * kBN * 16) >> 4;
+                const uint32_t d_tm   = tmem + t * d_stride;
+                const int      a0     = t * NAt;
+                int            sw = 0, sx = 0, sa = 0;
+                uint32_t       phw = 0, phx = 0, pha = 0;
+                for (int i = 0; i < nk; ++i) {
+                    GEMM_WAIT(smem_u32(&bar_xfull[sx]), phx, 2, i);
+                    if (kDequant) {
+                        GEMM_WAIT(smem_u32(&bar_aready[a0 + sa]), pha, 3, i);
+                    }
+                    else {
+                        GEMM_WAIT(smem_u32(&bar_wfull[sw]), phw, 7, i);
+                    }
+                    umma::fence_after_sync();
+                    if (lane == 0 && t == 0) GEMM_TRACE(3, i);
+                    const uint64_t bd0  = umma::make_smem_desc(x_ring + (uint32_t)sx * XB, p.MT * 16, 128);
+                    const uint64_t ad0  = umma::make_smem_desc(w_ring + (uint32_t)sw * WSLOT, kBN * 16, 128);
+                    const uint32_t a_tm = tmem + p.a_col + (a0 + sa) * 64;
+                    if (elect_one()) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
+                        for (int ks = 0; ks < kKG / 16; ++ks) {
+                            const uint32_t acc = (i > 0 || ks > 0) ? 1u : 0u;
+                            if (kDequant) {
+                                umma::mma_f16_ts(d_tm, a_tm + ks * 8, bd0 + (uint64_t)(ks * b_step), idesc, acc);
+                            }
+                            else {
+                                umma::mma_f16_ss(d_tm, ad0 + (uint64_t)(ks * a_step), bd0 + (uint64_t)(ks * b_step),
+                                                 idesc, acc);
+                            }
+                        }
+                        if (kDequant) {
+                            umma::commit(smem_u32(&bar_aempty[a0 + sa]));
+                        }
+                        else {
+                            umma::commit(smem_u32(&bar_wempty[sw]));
+                        }
+                        umma::commit(smem_u32(&bar_xempty[sx]));
+                    }
+                    __syncwarp();
+                    if (lane == 0 && t == 0) GEMM_TRACE(5, i);
+                    if (++sa == NAt) {
+                        sa = 0;
+                        pha ^= 1;
+                    }
+                    if (++sx == p.nx) {
+                        sx = 0;
+                        phx ^= 1;
+                    }
+                    if (++sw == p.nw) {
+                        sw = 0;
+                        phw ^= 1;
+                    }
+                }
+                if (elect_one()) {
+                    umma::commit(smem_u32(&bar_dready));
+                }
+                __syncwarp();
             }
         }
         else {
-            const int      tps = p.MT / p.splits;  // tokens owned per cluster CTA
-            const uint32_t red = smem_u32(smem) + (uint32_t)p.stages * (uint32_t)stage_bytes;
-            // my slot in every owner's buffer: red[src = sp][tl][n]
-            const uint32_t mine = red + (uint32_t)((sp * tps) * kBN + n_local) * 4u;
-            for (int t0 = grp * half; t0 < (grp + 1) * half; t0 += 8) {
-                uint32_t v[8];
-                umma::ld_32x32b_x8(trow + t0, v);
-                umma::wait_ld();
+            // ================================ dequant warps ================================
+            // TILES == 1: 16 warps share the tile (4 per TMEM lane quarter, one 32-wide k-chunk each).
+            // TILES == 2: warps 2-9 own tile 0, warps 10-17 tile 1 (2 per lane quarter, two k-chunks each), so the
+            // two tiles of a k-group are de-quantised concurrently and every thread still observes every phase of the
+            // barriers it waits on.
+            const int      dw        = warp - 2;
+            const int      my_tile   = TILES == 2 ? (dw >> 3) : 0;
+            const int      kc0       = TILES == 2 ? ((dw >> 2) & 1) * 2 : (dw >> 2);  // first 32-wide k-chunk
+            constexpr int  NKC       = TILES == 2 ? 2 : 1;                            // k-chunks per thread
+            const int      lane_base = 32 * (warp & 3);   // TMEM lanes this warp may touch
+            const int      n_local   = lane_base + lane;
+            const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
+            if constexpr (FMT == kU4) {
+                const int a0 = my_tile * NAt;
+                int       sw = 0, sa = 0;
+                uint32_t  phw = 0, pha = 0;
+                for (int i = 0; i < nk; ++i) {
+                    GEMM_WAIT(smem_u32(&bar_wfull[sw]), phw, 4, i);
+                    if (warp == 2 && lane == 0) GEMM_TRACE(1, i);
+                    const uint32_t wsm = w_ring + (uint32_t)sw * WSLOT + my_tile * WB_pad;
+                    const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
+                    const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
+                    uint4          v[NKC];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int      t     = t0 + i;
-                    const int      owner = t / tps;
-                    const uint32_t dst   = mapa_shared(mine + (uint32_t)((t - owner * tps) * kBN) * 4u, owner);
-                    st_shared_cluster_f32(dst, __uint_as_float(v[i]));
+                    for (int q = 0; q < NKC; ++q) v[q] = lds128(wsm + ((kc0 + q) * 128 + n_local) * 16);
+                    // the TMEM slot must have been drained by the MMAs that used it last
+                    GEMM_WAIT(smem_u32(&bar_aempty[a0 + sa]), pha ^ 1, 8, i);
+                    umma::fence_after_sync();
+#pragma unroll
+                    for (int q = 0; q < NKC; ++q) {
+                        uint32_t r[16];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint32_t h[4];
+                            Ops::cvt_u4x8((&v[q].x)[u], h);
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                        }
+                        umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + (kc0 + q) * 16, r);
+                    }
+                    // the W slot is free once its bytes are in registers (the arrive releases the reads)
+                    mbar_arrive(smem_u32(&bar_wempty[sw]));
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    mbar_arrive(smem_u32(&bar_aready[a0 + sa]));
+                    if (warp == 2 && lane == 0) GEMM_TRACE(2, i);
+                    if (++sa == NAt) {
+                        sa = 0;
+                        pha ^= 1;
+                    }
+                    if (++sw == p.nw) {
+                        sw = 0;
+                        phw ^= 1;
+                    }
                 }
             }
+            // epilogue role: (tile, token half) of the accumulator rows in this warp's lane quarter
+            const int  epi_tile   = my_tile;
+            const int  epi_half   = TILES == 2 ? ((dw >> 2) & 1) : (dw >> 2);
+            const bool epi_active = TILES == 2 || (dw >> 2) < 2;
+            // ============================== epilogue, part 1 ==============================
+            // splits == 1: straight to the output.  splits > 1 (thread-block cluster along K): each value goes to the
+            // shared memory of the cluster CTA that owns its token (reduce-scatter over DSMEM).
+            GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
+            umma::fence_after_sync();
+            if (threadIdx.x == 64) GEMM_TRACE(4, 2);
+            const int half = p.MT >> 1;
+            const int tb = epi_half * half, te = tb + half;
+            const uint32_t drow = trow + epi_tile * d_stride;
+            if (p.splits == 1) {
+                if (epi_active) {
+                    const int n_g = (nt0 + epi_tile) * kBN + n_local;
+                    for (int t0 = tb; t0 < te; t0 += 8) {
+                        uint32_t v[8];
+                        umma::ld_32x32b_x8(drow + t0, v);
+                        umma::wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
+                    }
+                }
+            }
+            else {
+                // All MMAs of THIS CTA have retired (dready), so its rings are dead; the cluster barrier tells us
+                // the same about every peer before we overwrite their rings with partial sums.
+                cluster_arrive_release();
+                cluster_wait_acquire();
+                if (epi_active) {
+                    const int      tps  = p.MT / p.splits;  // tokens owned per cluster CTA; layout red[src][n][tps]
+                    const uint32_t mine = w_ring + (uint32_t)((sp * (kBN * TILES) + epi_tile * kBN + n_local) * tps) * 4u;
+                    for (int t0 = tb; t0 < te; t0 += 8) {
+                        uint32_t v[8];
+                        umma::ld_32x32b_x8(drow + t0, v);
+                        umma::wait_ld();
+                        if (tps >= 4) {
+#pragma unroll
+                            for (int j = 0; j < 8; j += 4) {
+                                const int      owner = (t0 + j) / tps;
+                                const uint32_t dst = mapa_shared(mine + (uint32_t)(t0 + j - owner * tps) * 4u, owner);
+                                st_shared_cluster_v4(dst, v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            }
+                        }
+                        else {  // tps == 2
+#pragma unroll
+                            for (int j = 0; j < 8; j += 2) {
+                                const int      owner = (t0 + j) / tps;
+                                const uint32_t dst = mapa_shared(mine + (uint32_t)(t0 + j - owner * tps) * 4u, owner);
+                                st_shared_cluster_v2(dst, v[j], v[j + 1]);
+                            }
+                        }
+                    }
+                }
+            }
+            if (threadIdx.x == 64) GEMM_TRACE(4, 3);
         }
     }
-    if (threadIdx.x == 64) GEMM_TRACE(4, 3);
     if (p.splits > 1) {
-        // ================================ epilogue, part 2: owner-side ordered sum ================================
+        if (warp == 0 || warp == 1 || warp == kXWarp || warp == kMmaWarp2) {
+            cluster_arrive_release();  // matches the dequant warps' first cluster barrier
+            cluster_wait_acquire();
+        }
+        // ============================== epilogue, part 2: owner-side ordered sum ==============================
         cluster_arrive_release();
         cluster_wait_acquire();
-        if (warp >= 2) {
-            const int      tps  = p.MT / p.splits;
-            const int      tid  = threadIdx.x - 64;  // 0..255
-            const uint8_t* redp = smem + (size_t)p.stages * stage_bytes;
-            for (int idx = tid; idx < tps * (kBN / 2); idx += 256) {
-                const int tl = idx / (kBN / 2), np = idx % (kBN / 2);
-                float2    acc = make_float2(0.f, 0.f);
+        if (warp >= 2 && warp < kXWarp) {
+            constexpr int ROWS = kBN * TILES;
+            const int     tps  = p.MT / p.splits;
+            const int     tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
+            const float*  red  = reinterpret_cast<const float*>(smem);
+            for (int idx = tid; idx < tps * (ROWS / 2); idx += kDqWarps * 32) {
+                const int np = idx / tps, tl = idx - np * tps;  // tl fastest: conflict-light smem reads
+                float     a0 = 0.f, a1 = 0.f;
                 for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
-                    const float2 v = *reinterpret_cast<const float2*>(redp + ((size_t)(r * tps + tl) * kBN + 2 * np) * 4);
-                    acc.x += v.x;
-                    acc.y += v.y;
+                    a0 += red[(size_t)(r * ROWS + 2 * np) * tps + tl];
+                    a1 += red[(size_t)(r * ROWS + 2 * np + 1) * tps + tl];
                 }
-                finalize_pair<T>(p, sp * tps + tl, nt * kBN + 2 * np, acc.x, acc.y);
+                finalize_pair<T>(p, sp * tps + tl, nt0 * kBN + 2 * np, a0, a1);
             }
         }
     }
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 1) {
-        umma::tmem_dealloc(tmem, p.tmem_cols);
+        umma::tmem_dealloc(s_tmem, p.tmem_cols);
     }
 }
 

@@ -106,7 +106,7 @@ int main(int argc, char** argv)
             int hang[8];
             CK(cudaMemcpyFromSymbol(hang, b200::gemm::g_hang, sizeof(hang)));
             if (hang[0]) {
-                printf("%-8s m=%d HANG: wait tag %d (1 empty/producer, 2 full/mma, 3 aready/mma, 4 full/dequant, 5 dready) "
+                printf("%-8s m=%d HANG: wait tag %d (1 wempty/wprod, 2 xfull/mma, 3 aready/mma, 4 wfull/dequant, 5 dready, 6 xempty/xprod, 7 wfull/mma, 8 aempty/dequant) "
                        "cta (%d,%d) iter %d thread %d parity %d\n",
                        s.name, m, hang[1], hang[2], hang[3], hang[4], hang[5], hang[6]);
                 memset(hang, 0, sizeof(hang));
@@ -122,9 +122,9 @@ int main(int argc, char** argv)
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
         const double us = ms * 1e3 / iters;
-        printf("%-8s K=%5d N=%5d m=%d splits=%d stages=%d  %8.2f us  %7.1f GB/s (weights %.1f MB)\n", s.name, s.K, s.N, m,
-               b200::gemm::pick_splits(s.N, s.K, mt), b200::gemm::pick_stages(s.fmt, mt, b200::gemm::pick_splits(s.N, s.K, mt)), us, wbytes / us * 1e-3,
-               wbytes / 1e6);
+        const b200::gemm::Plan pl = b200::gemm::make_plan(s.fmt, mt, s.N, s.K);
+        printf("%-8s K=%5d N=%5d m=%d tiles=%d splits=%d nw=%d nx=%d na=%d  %8.2f us  %7.1f GB/s (weights %.1f MB)\n", s.name,
+               s.K, s.N, m, pl.tiles, pl.splits, pl.nw, pl.nx, pl.na, us, wbytes / us * 1e-3, wbytes / 1e6);
 #ifdef B200_GEMM_TRACE
         if (dump) {
             using namespace b200::gemm;
@@ -140,10 +140,10 @@ int main(int argc, char** argv)
                 const long long t0 = h[c][4][0];
                 printf("  cta %d: start 0, tmem-alloc done %lld, dready %lld, epilogue done %lld\n", c, h[c][4][1] - t0,
                        h[c][4][2] - t0, h[c][4][3] - t0);
-                printf("    %4s %9s %9s %9s %9s %9s\n", "i", "tma-issue", "full", "a-ready", "mma-issue", "commit");
+                printf("    %4s %9s %9s %9s %9s %9s %9s\n", "i", "w-issue", "x-issue", "w-full", "a-ready", "mma-issue", "commit");
                 for (int i = 0; i < kTraceSlots && h[c][0][i]; ++i) {
-                    printf("    %4d %9lld %9lld %9lld %9lld %9lld\n", i, h[c][0][i] - t0, h[c][1][i] - t0, h[c][2][i] - t0,
-                           h[c][3][i] - t0, h[c][5][i] - t0);
+                    printf("    %4d %9lld %9lld %9lld %9lld %9lld %9lld\n", i, h[c][0][i] - t0, h[c][6][i] - t0, h[c][1][i] - t0,
+                           h[c][2][i] - t0, h[c][3][i] - t0, h[c][5][i] - t0);
                     if (i >= 40) break;
                 }
             }
