@@ -64,6 +64,11 @@ typedef struct {
     float yarn_attention_factor;
     float yarn_beta_fast;
     float yarn_beta_slow;
+    /* 0 (default): the arithmetic of the reference's RELEASE build -- exp2f / sincosf are the hardware
+     * approximations ex2.approx / sin.approx / cos.approx (--use_fast_math, kernels/attention/CMakeLists.txt:14-15),
+     * so K pages are bit-identical to a TurboMind build on the same GPU.
+     * 1: correctly rounded exp2 / sin / cos (reproducible off-GPU; what oracle/attention.py computes). */
+    int exact_math;
 } b200_rope_config;
 
 /* ------------------------------------------------------------------------------------------------

@@ -18,6 +18,7 @@ class RopeConfig(C.Structure):
         ("llama3_low_freq_factor", C.c_float), ("llama3_high_freq_factor", C.c_float),
         ("llama3_original_max_position_embeddings", C.c_int),
         ("yarn_attention_factor", C.c_float), ("yarn_beta_fast", C.c_float), ("yarn_beta_slow", C.c_float),
+        ("exact_math", C.c_int),
     ]
 
 

@@ -20,6 +20,7 @@ struct RopeConst {
     float attention_scaling;
     float llama3_alpha, llama3_beta;
     float yarn_div2, yarn_mulmin;
+    int   exact;  // b200_rope_config::exact_math
 };
 
 static RopeConst make_rope_const(const b200_rope_config& r)
@@ -30,6 +31,7 @@ static RopeConst make_rope_const(const b200_rope_config& r)
     c.scale_factor      = -std::log2(r.base) / r.dim;  // float log2, float divide
     c.inv_factor        = (r.type == 3) ? 1.f : ((r.factor != 0.f) ? (float)(1.0 / r.factor) : 1.f);
     c.attention_scaling = 1.f;
+    c.exact             = r.exact_math;
     if (r.type == 5) {
         float inv_diff = (float)(1.0 / (r.llama3_high_freq_factor - r.llama3_low_freq_factor));
         c.llama3_alpha = (float)(r.llama3_original_max_position_embeddings / (2 * 3.14159265358979323846) * inv_diff);
@@ -52,35 +54,76 @@ static RopeConst make_rope_const(const b200_rope_config& r)
     return c;
 }
 
-// inv_freq of the pair starting at even dim `idx` (rotary_embedding.h:10-52), with correctly rounded
-// exp2 (the reference release build uses ex2.approx; see DESIGN.md numerics contract).
+__device__ __forceinline__ float mul_ftz(float a, float b)
+{
+    float c;
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(c) : "f"(a), "f"(b));
+    return c;
+}
+__device__ __forceinline__ float fma_ftz(float a, float b, float c)
+{
+    float d;
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// inv_freq of the pair starting at even dim `idx` (rotary_embedding.h:10-52).
+// Default: the instruction sequence of the reference's release build (--use_fast_math: ex2.approx.ftz, ftz
+// multiplies, mul+add contracted to fma) so results are bit-identical to TurboMind on the same GPU; `exact`:
+// correctly rounded exp2 and un-fused fp32 ops (what the CPU oracle computes).
 __device__ __forceinline__ float rope_inv_freq(const RopeConst& r, int idx)
 {
-    const float e    = __fmul_rn((float)idx, r.scale_factor);
-    const float freq = (float)exp2((double)e);
+    if (r.exact) {
+        const float e    = __fmul_rn((float)idx, r.scale_factor);
+        const float freq = (float)exp2((double)e);
+        if (r.type == 5) {
+            float sm = fmaf(r.llama3_alpha, freq, -r.llama3_beta);
+            sm       = fmaxf(0.f, fminf(1.f, sm));
+            const float a = __fmul_rn(__fsub_rn(1.f, sm), freq);
+            const float b = __fmul_rn(a, r.inv_factor);
+            const float c = __fmul_rn(sm, freq);
+            return __fadd_rn(b, c);
+        }
+        if (r.type == 4) {
+            float alpha = __fsub_rn(__fmul_rn((float)idx, r.yarn_div2), r.yarn_mulmin);
+            alpha       = fmaxf(0.f, fminf(1.f, alpha));
+            const float t = __fmul_rn(__fmul_rn(freq, alpha), __fsub_rn(1.f, r.inv_factor));
+            return __fsub_rn(freq, t);
+        }
+        return __fmul_rn(r.inv_factor, freq);
+    }
+    const float freq = exp2_approx(mul_ftz((float)idx, r.scale_factor));
     if (r.type == 5) {
-        float sm = fmaf(r.llama3_alpha, freq, -r.llama3_beta);
+        // (1 - smooth) * freq * inv_factor + smooth * freq
+        float sm = fma_ftz(r.llama3_alpha, freq, -r.llama3_beta);
         sm       = fmaxf(0.f, fminf(1.f, sm));
-        const float a = __fmul_rn(__fsub_rn(1.f, sm), freq);
-        const float b = __fmul_rn(a, r.inv_factor);
-        const float c = __fmul_rn(sm, freq);
-        return __fadd_rn(b, c);
+        const float a = mul_ftz(mul_ftz(1.f - sm, freq), r.inv_factor);
+        return fma_ftz(sm, freq, a);
     }
     if (r.type == 4) {
-        float alpha = __fsub_rn(__fmul_rn((float)idx, r.yarn_div2), r.yarn_mulmin);
+        // freq - freq * alpha * (1 - inv_factor)
+        float alpha = fma_ftz((float)idx, r.yarn_div2, -r.yarn_mulmin);
         alpha       = fmaxf(0.f, fminf(1.f, alpha));
-        const float t = __fmul_rn(__fmul_rn(freq, alpha), __fsub_rn(1.f, r.inv_factor));
-        return __fsub_rn(freq, t);
+        const float t = mul_ftz(freq, alpha);
+        return fma_ftz(-t, 1.f - r.inv_factor, freq);
     }
-    return __fmul_rn(r.inv_factor, freq);
+    return mul_ftz(r.inv_factor, freq);
 }
 
 __device__ __forceinline__ float2 rope_cos_sin(const RopeConst& r, int idx, int pos)
 {
-    const float ang = __fmul_rn((float)pos, rope_inv_freq(r, idx));
-    double      s, c;
-    sincos((double)ang, &s, &c);
-    return make_float2(__fmul_rn((float)c, r.attention_scaling), __fmul_rn((float)s, r.attention_scaling));
+    if (r.exact) {
+        const float ang = __fmul_rn((float)pos, rope_inv_freq(r, idx));
+        double      s, c;
+        sincos((double)ang, &s, &c);
+        return make_float2(__fmul_rn((float)c, r.attention_scaling), __fmul_rn((float)s, r.attention_scaling));
+    }
+    // sincosf under --use_fast_math = sin.approx.ftz / cos.approx.ftz of the ftz product (no range reduction)
+    const float ang = mul_ftz((float)pos, rope_inv_freq(r, idx));
+    float       s, c;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+    return make_float2(mul_ftz(c, r.attention_scaling), mul_ftz(s, r.attention_scaling));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -234,8 +277,9 @@ __global__ void __launch_bounds__(128) kv_prologue_kernel(const PrologueParams p
             if (di + 2 * i < p.rope.dim) {
                 const T c = Ops::from_f32(cs[i].x), s = Ops::from_f32(cs[i].y);
                 const T a = x[2 * i], bb = x[2 * i + 1];
-                x[2 * i]     = Ops::sub(Ops::mul(c, a), Ops::mul(s, bb));
-                x[2 * i + 1] = Ops::add(Ops::mul(c, bb), Ops::mul(s, a));
+                // the reference binary contracts `c*x0 - s*x1` to HMUL2 + HFMA2 (SASS of oracle/_ref)
+                x[2 * i]     = Ops::fma(c, a, Ops::neg(Ops::mul(s, bb)));
+                x[2 * i + 1] = Ops::fma(c, bb, Ops::mul(s, a));
             }
         }
     };

@@ -102,8 +102,8 @@ struct Plan {
 //   * u4 with N % 256 == 0: two n-tiles per CTA (shared activation tile), ONE CTA per SM with the whole
 //     shared-memory / TMEM budget spent on ring depth (the pipeline, not a second CTA, hides the latency);
 //   * otherwise one n-tile per CTA; u4 with MT <= 64 keeps to 256 TMEM columns / ~113 KB so two CTAs fit an SM;
-//   * K is split over a thread-block cluster of 1/2/4/8 CTAs (largest that still fits one wave and leaves every
-//     CTA >= 4 K-groups); the rings double as the split-K exchange buffer.
+//   * K is split over 1/2/4/8 co-resident CTAs (largest count that still fits one wave and leaves every CTA
+//     >= 4 K-groups).
 static Plan make_plan(int fmt, int MT, int N, int K)
 {
     const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
@@ -144,8 +144,12 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     return pl;
 }
 
+constexpr size_t kCounterBytes = 64 * 1024;  // 2 ints per n-group, N <= 1M
+
 struct LinearWs {
+    int*   counters;
     void*  xp;
+    float* partials;
     size_t total;
 };
 
@@ -156,10 +160,19 @@ static size_t align_up(size_t x, size_t a)
 
 static LinearWs carve_ws(void* base, int K, int N, int MT)
 {
-    (void)N;
     LinearWs w{};
-    w.xp    = base;
-    w.total = align_up((size_t)K * MT * 2, 256);
+    size_t   off  = 0;
+    auto     take = [&](size_t bytes) {
+        void* p = base ? (char*)base + off : nullptr;
+        off += align_up(bytes, 256);
+        return p;
+    };
+    // fixed-size counter block so that linears of different shapes can share one workspace: a counter slot never
+    // aliases another linear's activation / partial region
+    w.counters = (int*)take(kCounterBytes);
+    w.xp       = take((size_t)K * MT * 2);
+    w.partials = (float*)take((size_t)N * 8 * MT * 4);  // up to 8 K-splits of an [MT][N] fp32 tile
+    w.total    = off;
     return w;
 }
 
@@ -183,13 +196,12 @@ static int launch(const Params& p, int smem, cudaStream_t st)
     cfg.blockDim         = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream           = st;
+    // split-K CTAs wait for each other (epilogue part 2): the launch must guarantee co-residency
     cudaLaunchAttribute attr[1];
-    attr[0].id               = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = p.splits;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs                = attr;
-    cfg.numAttrs             = 1;
+    attr[0].id              = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = p.splits > 1 ? 1 : 0;
+    cfg.attrs               = attr;
+    cfg.numAttrs            = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) {
         return fail_cuda(e, "cudaLaunchKernelEx(gemm_kernel)");
@@ -211,8 +223,8 @@ static int validate_desc(const b200_linear_desc* d)
     if (d->input_dim <= 0 || d->input_dim % kKG) {
         return fail(B200_ERR_UNSUPPORTED, "input_dim must be a multiple of 128");
     }
-    if (d->output_dim <= 0 || d->output_dim % kBN) {
-        return fail(B200_ERR_UNSUPPORTED, "output_dim must be a multiple of 128");
+    if (d->output_dim <= 0 || d->output_dim % kBN || (size_t)(d->output_dim / kBN) * 8 > kCounterBytes) {
+        return fail(B200_ERR_UNSUPPORTED, "output_dim must be a multiple of 128 (and <= 1M)");
     }
     if (d->weight_format == kU4 && d->group_size != 128) {
         return fail(B200_ERR_UNSUPPORTED, "u4 weights require group_size 128");
@@ -289,7 +301,7 @@ extern "C" int b200_pack_activations(const void* x, int64_t ldx, int m, int k, i
 }
 
 static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y, int64_t ldy, int epilogue,
-                          int out_mode, int out_mt, cudaStream_t st)
+                          int out_mode, int out_mt, float* partials, int* counters, cudaStream_t st)
 {
     if (mt < 16 || mt > 128 || mt % 16) {
         return fail(B200_ERR_UNSUPPORTED, "padded token count must be a multiple of 16 in [16, 128]");
@@ -302,6 +314,8 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.xp       = xp;
     p.y        = y;
     p.bias     = d->bias;
+    p.partials = partials;
+    p.counters = counters;
     p.N        = d->output_dim;
     p.K        = d->input_dim;
     p.MT       = mt;
@@ -344,7 +358,7 @@ extern "C" int b200_linear_forward(const b200_linear_desc* d, const void* x, int
     if (int e = b200_pack_activations(x, ldx, m, d->input_dim, mt, d->dtype, w.xp, stream)) {
         return e;
     }
-    return forward_packed(d, w.xp, mt, m, y, ldy, epilogue, 0, 0, st);
+    return forward_packed(d, w.xp, mt, m, y, ldy, epilogue, 0, 0, w.partials, w.counters, st);
 }
 
 extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y,
@@ -357,7 +371,10 @@ extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void*
     if (!d->prepared || !xp || !y) {
         return fail(B200_ERR_INVALID_ARG, "prepared / xp / y is NULL");
     }
-    (void)workspace;
-    (void)workspace_bytes;
-    return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, (cudaStream_t)stream);
+    LinearWs w = carve_ws(workspace, d->input_dim, d->output_dim, mt);
+    if (!workspace || workspace_bytes < w.total) {
+        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_linear_workspace_bytes)");
+    }
+    return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
+                          w.counters, (cudaStream_t)stream);
 }

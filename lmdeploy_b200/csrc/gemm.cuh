@@ -16,9 +16,10 @@
 //     reference's transform, transform.h:48-74 / cast.cu:155) and write the A operand straight into
 //     TENSOR MEMORY with tcgen05.st (3-slot ring; no shared-memory round trip for the dequantised weights);
 //   * warp 1 issues tcgen05.mma (A from TMEM, B from smem) from a warp-uniform loop, fp32 accumulators in TMEM;
-//   * K is split over a thread-block cluster (grid.y); the partial accumulators are reduce-scattered by token
-//     through distributed shared memory and summed in rank order (deterministic), then bias / gated-SiLU and the
-//     fp16/bf16 store.  No global workspace, no second kernel.
+//   * K is split over grid.y (co-resident CTAs, cooperative launch); the partial accumulators are reduce-scattered
+//     by token through an L2-resident fp32 exchange buffer and summed in rank order (deterministic), then bias /
+//     gated-SiLU and the fp16/bf16 store, all inside the same kernel.  (A thread-block-cluster + DSMEM exchange
+//     was measured first: correct, but launching 8-CTA clusters of full-SM CTAs costs ~20 us per kernel.)
 // The kernel is HBM-bound at decode batch sizes: algorithmic bytes = packed weight stream, read once.
 #pragma once
 
@@ -99,10 +100,12 @@ struct Params {
     const void*    xp;  // packed activations [K/8][MT][8] T
     void*          y;
     const void*    bias;      // [N] T or null
+    float*         partials;  // split-K exchange [n-group][split][MT][128 * TILES] fp32 (L2 resident)
+    int*           counters;  // [n-group][2] arrive / done, zero before first use; left zero by the kernel
     int            N, K;
     int            MT;  // padded token count (multiple of 16, <= 128)
     int            M;   // real tokens
-    int            splits;  // K splits = thread-block cluster size along grid.y (1, 2, 4 or 8)
+    int            splits;  // K splits along grid.y (1, 2, 4 or 8); > 1 needs a cooperative launch (co-residency)
     int            nw, nx;  // W / X ring depths
     int            na;      // TMEM A-ring slots (multiple of TILES)
     int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
@@ -174,33 +177,12 @@ B200_DEVICE void finalize_pair(const Params& p, int tok, int n_g, float a0, floa
     }
 }
 
-B200_DEVICE uint32_t mapa_shared(uint32_t addr, int cta_rank)
+B200_DEVICE int ld_acquire_gpu(const int* p)
 {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
-    return r;
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
-B200_DEVICE void st_shared_cluster_f32(uint32_t addr, float v)
-{
-    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-B200_DEVICE void st_shared_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-B200_DEVICE void st_shared_cluster_v2(uint32_t addr, uint32_t a, uint32_t b)
-{
-    asm volatile("st.shared::cluster.v2.b32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
-}
-B200_DEVICE void cluster_arrive_release()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-}
-B200_DEVICE void cluster_wait_acquire()
-{
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // TILES = n-tiles (128 output features each) per CTA.  TILES == 2 shares every activation tile between two weight
 // tiles: the X stream (2x the W bytes at 64 tokens) is what saturates the L2->SM path, so this halves the ingest
 // per weight byte.  TMEM: D accumulators of tile t at column t * d_stride, then an A ring of p.na 64-column slots
@@ -437,8 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             const int  epi_half   = TILES == 2 ? ((dw >> 2) & 1) : (dw >> 2);
             const bool epi_active = TILES == 2 || (dw >> 2) < 2;
             // ============================== epilogue, part 1 ==============================
-            // splits == 1: straight to the output.  splits > 1 (thread-block cluster along K): each value goes to the
-            // shared memory of the cluster CTA that owns its token (reduce-scatter over DSMEM).
+            // splits == 1: straight to the output.  splits > 1: fp32 partials to the L2-resident exchange buffer.
             GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
             umma::fence_after_sync();
             if (threadIdx.x == 64) GEMM_TRACE(4, 2);
@@ -457,61 +438,55 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     }
                 }
             }
-            else {
-                // All MMAs of THIS CTA have retired (dready), so its rings are dead; the cluster barrier tells us
-                // the same about every peer before we overwrite their rings with partial sums.
-                cluster_arrive_release();
-                cluster_wait_acquire();
-                if (epi_active) {
-                    const int      tps  = p.MT / p.splits;  // tokens owned per cluster CTA; layout red[src][n][tps]
-                    const uint32_t mine = w_ring + (uint32_t)((sp * (kBN * TILES) + epi_tile * kBN + n_local) * tps) * 4u;
-                    for (int t0 = tb; t0 < te; t0 += 8) {
-                        uint32_t v[8];
-                        umma::ld_32x32b_x8(drow + t0, v);
-                        umma::wait_ld();
-                        if (tps >= 4) {
+            else if (epi_active) {
+                // fp32 partial tile -> global exchange buffer [group][split][tok][row] (stays in L2)
+                constexpr int ROWS = kBN * TILES;
+                float* part = p.partials + ((size_t)blockIdx.x * p.splits + sp) * p.MT * ROWS + epi_tile * kBN + n_local;
+                for (int t0 = tb; t0 < te; t0 += 8) {
+                    uint32_t v[8];
+                    umma::ld_32x32b_x8(drow + t0, v);
+                    umma::wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 8; j += 4) {
-                                const int      owner = (t0 + j) / tps;
-                                const uint32_t dst = mapa_shared(mine + (uint32_t)(t0 + j - owner * tps) * 4u, owner);
-                                st_shared_cluster_v4(dst, v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            }
-                        }
-                        else {  // tps == 2
-#pragma unroll
-                            for (int j = 0; j < 8; j += 2) {
-                                const int      owner = (t0 + j) / tps;
-                                const uint32_t dst = mapa_shared(mine + (uint32_t)(t0 + j - owner * tps) * 4u, owner);
-                                st_shared_cluster_v2(dst, v[j], v[j + 1]);
-                            }
-                        }
-                    }
+                    for (int i = 0; i < 8; ++i) __stcg(part + (size_t)(t0 + i) * ROWS, __uint_as_float(v[i]));
                 }
             }
             if (threadIdx.x == 64) GEMM_TRACE(4, 3);
         }
     }
-    if (p.splits > 1) {
-        if (warp == 0 || warp == 1 || warp == kXWarp || warp == kMmaWarp2) {
-            cluster_arrive_release();  // matches the dequant warps' first cluster barrier
-            cluster_wait_acquire();
+    if (p.splits > 1 && warp >= 2 && warp < kXWarp) {
+        // ============================== epilogue, part 2: split-K reduce-scatter through L2 ==============================
+        // The `splits` CTAs of an n-group are co-resident (cooperative launch).  Each publishes its partial tile,
+        // then sums ITS token slice over all partials in rank order (deterministic) and writes the output.
+        constexpr int ROWS = kBN * TILES;
+        int*          ctr  = p.counters + 2 * blockIdx.x;
+        __threadfence();
+        named_bar_sync(2, kDqWarps * 32);
+        if (threadIdx.x == 64) {
+            atomicAdd(ctr, 1);
+            while (ld_acquire_gpu(ctr) < p.splits) {
+            }
         }
-        // ============================== epilogue, part 2: owner-side ordered sum ==============================
-        cluster_arrive_release();
-        cluster_wait_acquire();
-        if (warp >= 2 && warp < kXWarp) {
-            constexpr int ROWS = kBN * TILES;
-            const int     tps  = p.MT / p.splits;
-            const int     tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
-            const float*  red  = reinterpret_cast<const float*>(smem);
-            for (int idx = tid; idx < tps * (ROWS / 2); idx += kDqWarps * 32) {
-                const int np = idx / tps, tl = idx - np * tps;  // tl fastest: conflict-light smem reads
-                float     a0 = 0.f, a1 = 0.f;
-                for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
-                    a0 += red[(size_t)(r * ROWS + 2 * np) * tps + tl];
-                    a1 += red[(size_t)(r * ROWS + 2 * np + 1) * tps + tl];
-                }
-                finalize_pair<T>(p, sp * tps + tl, nt0 * kBN + 2 * np, a0, a1);
+        named_bar_sync(2, kDqWarps * 32);
+        const int    tps  = p.MT / p.splits;
+        const int    tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
+        const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)(sp * tps) * ROWS;
+        for (int idx = tid; idx < tps * (ROWS / 2); idx += kDqWarps * 32) {
+            const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+            float2    acc = make_float2(0.f, 0.f);
+            for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(base + (size_t)r * p.MT * ROWS + tl * ROWS) + np);
+                acc.x += v.x;
+                acc.y += v.y;
+            }
+            finalize_pair<T>(p, sp * tps + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
+        }
+        named_bar_sync(2, kDqWarps * 32);
+        if (threadIdx.x == 64) {
+            // the last CTA of the group to finish reading re-arms the counters for the next launch
+            if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
+                ctr[1] = 0;
+                __threadfence();
+                ctr[0] = 0;
             }
         }
     }

@@ -76,7 +76,9 @@ class DecodeModel:
     """Owns the prepared weights of one TP rank and the native b200_model handle."""
 
     def __init__(self, spec: ModelSpec, *, quant_policy=8, block_len=64, max_batch=64, tp_size=1, tp_rank=0,
-                 device=None):
+                 device=None, rope_exact_math=False):
+        """rope_exact_math: correctly rounded RoPE transcendentals (comparable with the CPU oracle) instead of the
+        reference release build's hardware approximations (the default; bit-identical K pages to TurboMind)."""
         self.lib = L.load()
         self.spec = spec
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
@@ -97,7 +99,7 @@ class DecodeModel:
         cfg.inv_sqrt_dh = float(torch.tensor(1.4426950408889634, dtype=torch.float32)
                                 / torch.sqrt(torch.tensor(float(spec.head_dim), dtype=torch.float32)))
         cfg.rope = L.RopeConfig(rope_type, spec.head_dim, spec.rope_theta, spec.rope_factor, 0, 1.0, 4.0, 8192, 1.0,
-                                32.0, 1.0)
+                                32.0, 1.0, 1 if rope_exact_math else 0)
         cfg.dtype, cfg.quant_policy, cfg.block_len = _DT[spec.dtype], quant_policy, block_len
         cfg.max_batch, cfg.tp_size, cfg.tp_rank = max_batch, tp_size, tp_rank
         self.cfg = cfg

@@ -148,8 +148,9 @@ def rope_inv_freq(rope: RopeParam):
 
 def apply_rope(x, pos, rope: RopeParam, dtype):
     """x: [..., D] float32 (exact in T); pos: int array broadcastable to x[..., 0].
-    Adjacent-pair rotation computed in T:  x0' = (T)c*x0 - (T)s*x1 ; x1' = (T)c*x1 + (T)s*x0
-    (rotary_embedding.h:168-181; each T op rounds once, no fusion)."""
+    Adjacent-pair rotation computed in T (rotary_embedding.h:168-181).  The reference binary contracts each
+    `(T)c*x0 - (T)s*x1` into HMUL2 + HFMA2 (mul.f16 / sub.f16 carry no .rn, so ptxas may fuse; checked in the SASS of
+    oracle/_ref: decoding_sm80_128 / ProcessKV_v2):  x0' = fma(c, x0, -RN(s*x1)) ; x1' = fma(c, x1, RN(s*x0))."""
     if rope.type == ROPE_NULL:
         return f32(x).copy()
     kp = rope.kernel_params()
@@ -164,8 +165,8 @@ def apply_rope(x, pos, rope: RopeParam, dtype):
     x = f32(x)
     nd = rope.dim
     x0, x1 = x[..., 0:nd:2], x[..., 1:nd:2]
-    y0 = t_sub(t_mul(cT, x0, dtype), t_mul(sT, x1, dtype), dtype)
-    y1 = t_add(t_mul(cT, x1, dtype), t_mul(sT, x0, dtype), dtype)
+    y0 = t_fma(cT, x0, -t_mul(sT, x1, dtype), dtype)
+    y1 = t_fma(cT, x1, t_mul(sT, x0, dtype), dtype)
     out = x.copy()
     out[..., 0:nd:2] = y0
     out[..., 1:nd:2] = y1

@@ -39,7 +39,10 @@ class PagedCase:
     """A batch of sequences with a paged KV cache filled by the oracle."""
 
     def __init__(self, *, batch_hist, num_heads, num_kv_heads, kv_bits, dtype=F16, block_len=64, layers=2,
-                 layer=1, rope=None, seed=0, bias=False, extra_blocks=3):
+                 layer=1, rope=None, seed=0, bias=False, extra_blocks=3, exact_math=True):
+        # exact_math: correctly rounded RoPE transcendentals on the device (comparable with the numpy oracle);
+        # False = the reference release build's arithmetic (compared against oracle/_ref, the reference kernels)
+        self.exact_math = exact_math
         self.rng = np.random.default_rng(seed)
         self.hist = np.asarray(batch_hist, np.int32)
         self.B = len(batch_hist)
@@ -133,7 +136,7 @@ class PagedCase:
         p.rope = L.RopeConfig(r.type, r.dim, r.base, r.factor, r.max_position_embeddings,
                               r.llama3_low_freq_factor, r.llama3_high_freq_factor,
                               r.llama3_original_max_position_embeddings, r.yarn_attention_factor,
-                              r.yarn_beta_fast, r.yarn_beta_slow)
+                              r.yarn_beta_fast, r.yarn_beta_slow, 1 if self.exact_math else 0)
         p.quant_policy = 0 if self.kv_bits == 16 else self.kv_bits
         p.dtype = 0 if self.dtype == F16 else 1
         nbytes = lib.b200_decode_attention_workspace_bytes(self.B, self.Hq, self.Hkv)

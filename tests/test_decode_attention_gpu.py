@@ -117,7 +117,7 @@ def test_full_size_sampled():
         p.layer_offset, p.block_len = layer * layout.layer_size(), 64
         p.num_heads, p.num_kv_heads, p.size_per_head = Hq, Hkv, D
         p.inv_sqrt_dh = float(np.float32(np.float32(1.4426950408889634) / np.float32(np.sqrt(np.float32(D)))))
-        p.rope = L.RopeConfig(rope.type, rope.dim, rope.base, 0.0, 0, 1.0, 4.0, 8192, 1.0, 32.0, 1.0)
+        p.rope = L.RopeConfig(rope.type, rope.dim, rope.base, 0.0, 0, 1.0, 4.0, 8192, 1.0, 32.0, 1.0, 1)  # exact_math
         p.quant_policy, p.dtype = 8, 0
         p.stream = torch.cuda.current_stream().cuda_stream
         return p

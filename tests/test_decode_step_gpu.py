@@ -24,7 +24,8 @@ def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_ra
     from lmdeploy_b200.turbomind import ModelSpec, DecodeModel
     spec = ModelSpec("tiny", "llama", w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab, 1e4,
                      weight_format=w.fmt)
-    m = DecodeModel(spec, quant_policy=quant_policy, max_batch=max_batch, tp_size=tp_size, tp_rank=tp_rank)
+    m = DecodeModel(spec, quant_policy=quant_policy, max_batch=max_batch, tp_size=tp_size, tp_rank=tp_rank,
+                    rope_exact_math=True)   # the numpy oracle cannot reproduce MUFU approximations
     sw = shard if shard is not None else w
 
     def lin(d):
