@@ -23,6 +23,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+# capture (profiles/): filled per config once measured
+TRAFFIC_NCU = {"c2": 281641216}
+
 CONFIGS = {
     # name: (spec, batch, ctx, kv quant policy)
     "c2": ("internlm2-7b", 64, 2048, 8),
@@ -208,10 +212,22 @@ def run_b200(args):
     step_gbs = sb["total"] / (ms_per_step * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "decode_attention_kernel", "achieved": attn["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": attn["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+        "frac": attn["gbs"] / peak, "traffic": TRAFFIC_NCU.get(args.config), "peak_source": peak_src,
         "bytes_per_launch": attn["bytes"], "us_per_launch": attn["us"],
         "step": {"algorithmic_bytes": sb["total"], "achieved_gbs_per_gpu": step_gbs, "frac": step_gbs / peak},
     }
+    # the kernel to beat: the reference's own decode attention (sm_100a rebuild of its sm80 mma.sync kernels,
+    # oracle/_ref) on the same pages, same device, same run -- measurement only, never on the product path
+    try:
+        from oracle import ref_lib
+        if ref_lib.available() and world == 1:
+            ref_us = runner.time_reference_attention(ref_lib, iters=args.attn_iters)
+            roofline["reference_kernel"] = {"what": "TurboMind dispatchDecoding (decoding_sm80_128 + reduce) rebuilt for "
+                                                    "sm_100a, same KV pages", "us_per_launch": ref_us,
+                                            "achieved": attn["bytes"] / (ref_us * 1e-6) / 1e9,
+                                            "speedup_ours": ref_us / attn["us"]}
+    except Exception as e:  # the checker library is optional on the bench path
+        roofline["reference_kernel"] = {"unavailable": str(e)[:200]}
 
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,

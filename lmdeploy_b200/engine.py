@@ -37,9 +37,10 @@ class StaticBatchRunner:
         self.h_in = torch.zeros(batch, dtype=torch.int32).pin_memory()
         self.h_out = torch.zeros(batch, dtype=torch.int32).pin_memory()
         self.cur_len = 0
-        # kernels per step: embedding, rmsnorm, plan, L x (qkv, prologue, attention, fix-up, wo, norm, w13, w2, norm),
-        # lm_head, argmax, advance
-        self.launches_per_step = 3 + 9 * spec.layers + 3
+        # kernels per step: embedding, rmsnorm, plan, rope table, L x (qkv, prologue, attention, fix-up, wo, norm, w13,
+        # w2, norm), lm_head, argmax stage 1 + 2, advance
+        self.launches_per_step = 4 + 9 * spec.layers + 4
+        self._graph = None
 
     def prefill_random(self, ctx):
         self.model.prefill_kv_random(self.pool, self.block_ptrs, self.cu_blocks, self.batch, ctx)
@@ -78,10 +79,16 @@ class StaticBatchRunner:
         return replay
 
     def step_host(self, host_tokens):
-        """One step through host buffers: H2D token ids (pinned), decode, D2H sampled ids."""
+        """One step through host buffers: H2D token ids (pinned), decode, D2H sampled ids.  Replays the captured
+        step when make_device_step(graph=True) built one (the graph reads token_ids / writes out_tokens in place)."""
         self.h_in.copy_(torch.from_numpy(host_tokens))
         self.token_ids.copy_(self.h_in, non_blocking=True)
-        self._step(advance=True)
+        if self._graph is not None:
+            assert self.cur_len <= self.max_len, "runner out of KV capacity"
+            self._graph.replay()
+            self.cur_len += 1
+        else:
+            self._step(advance=True)
         self.h_out.copy_(self.out_tokens, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.h_out.numpy().copy()
@@ -130,4 +137,29 @@ class StaticBatchRunner:
         us = e0.elapsed_time(e1) * 1e3 / iters
         q_bits = 16 if m.quant_policy == 0 else m.quant_policy
         nbytes = self.batch * k_len * 2 * m.kv_heads * (D * q_bits // 8 + (4 if m.quant_policy else 0))
+        self._attn_params = (p, qkv, out, ws, cu_k)   # kept alive for time_reference_attention
         return dict(us=us, bytes=nbytes, gbs=nbytes / (us * 1e-6) / 1e9)
+
+    def time_reference_attention(self, ref_lib, iters=20, layer=0):
+        """Benchmark aid: CUDA-event time of the REFERENCE's decode attention (its main kernel + its reduce, through
+        oracle/_ref; the caller passes the oracle.ref_lib module) on the very buffers time_attention_kernel used.
+        The reference call also runs its in-kernel prologue, ours was timed without prologue / fix-up, so the
+        comparison slightly favours ours by the (tiny) prologue; both read the same KV bytes."""
+        p = self._attn_params[0]
+        m = self.model
+        ref = ref_lib.load()
+        p.debug_flags = 0
+        a, keep = ref_lib.args_from_b200(p, torch)
+        layers = m.spec.layers
+        for i in range(3):
+            a.layer_offset = ((layer + i) % layers) * m.layer_bytes
+            assert ref.ref_decode_attention(C.byref(a)) == 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            a.layer_offset = ((layer + i) % layers) * m.layer_bytes
+            ref.ref_decode_attention(C.byref(a))
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / iters
