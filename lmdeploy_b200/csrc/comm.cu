@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
     Peers peers, int rank, int world, int epoch, T* out, int out_mt, T* residual, const T* weight, const T* bias,
     int tokens, int dim, float eps, size_t data_offset)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops = TypeOps<T>;
     __threadfence_system();
     __syncthreads();
@@ -148,6 +150,8 @@ template<class T>
 __global__ void __launch_bounds__(kBlock) allreduce_sum_kernel(Peers peers, int rank, int world, int epoch, T* data,
                                                                size_t count, size_t data_offset)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops = TypeOps<T>;
     // stage: copy my data into my exchange buffer
     T* mine = reinterpret_cast<T*>((char*)peers.data[rank] + data_offset);
@@ -176,6 +180,8 @@ template<class T>
 __global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int rank, int world, int epoch, int* out,
                                                                const T* logits, int rows, int vocab, size_t data_offset)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops = TypeOps<T>;
     __shared__ float s_v[32];
     __shared__ int   s_i[32];
@@ -302,13 +308,13 @@ extern "C" int b200_comm_allreduce_residual_rmsnorm(b200_comm* c, void* out, int
     const int    ep  = ++c->epoch;
     const int    grid = comm_grid(tokens);
     if (dtype == B200_DTYPE_F16) {
-        allreduce_residual_rmsnorm_kernel<half><<<grid, kBlock, 0, st>>>(c->peers, c->rank, c->world, ep, (half*)out,
+        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kBlock), 0, st, c->peers, c->rank, c->world, ep, (half*)out,
                                                                          out_packed_mt, (half*)residual,
                                                                          (const half*)weight, (const half*)bias, tokens,
                                                                          dim, eps, off);
     }
     else {
-        allreduce_residual_rmsnorm_kernel<nv_bfloat16><<<grid, kBlock, 0, st>>>(
+        launch_k(allreduce_residual_rmsnorm_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, st, 
             c->peers, c->rank, c->world, ep, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual,
             (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, tokens, dim, eps, off);
     }
@@ -323,11 +329,11 @@ extern "C" int b200_comm_allreduce_sum(b200_comm* c, void* data, size_t count, i
     const int ep   = ++c->epoch;
     const int grid = (int)std::min<size_t>(kFlagSlots, (count / 8 + kBlock - 1) / kBlock);
     if (dtype == B200_DTYPE_F16) {
-        allreduce_sum_kernel<half><<<grid, kBlock, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, ep,
+        launch_k(allreduce_sum_kernel<half>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep,
                                                                               (half*)data, count, 0);
     }
     else {
-        allreduce_sum_kernel<nv_bfloat16><<<grid, kBlock, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, ep,
+        launch_k(allreduce_sum_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep,
                                                                                      (nv_bfloat16*)data, count, 0);
     }
     return check_launch("allreduce_sum_kernel");
@@ -343,12 +349,12 @@ extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const v
     // (value, index) pairs live in the last 4 KB of the exchange buffer
     const size_t off = 0;
     if (dtype == B200_DTYPE_F16) {
-        argmax_exchange_kernel<half><<<rows, 1024, 0, (cudaStream_t)stream>>>(c->peers, c->rank, c->world, ep, out_tokens,
+        launch_k(argmax_exchange_kernel<half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep, out_tokens,
                                                                               (const half*)local_logits, rows,
                                                                               vocab_per_rank, off);
     }
     else {
-        argmax_exchange_kernel<nv_bfloat16><<<rows, 1024, 0, (cudaStream_t)stream>>>(
+        launch_k(argmax_exchange_kernel<nv_bfloat16>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, 
             c->peers, c->rank, c->world, ep, out_tokens, (const nv_bfloat16*)local_logits, rows, vocab_per_rank, off);
     }
     return check_launch("argmax_exchange_kernel");
@@ -357,6 +363,8 @@ extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const v
 // ---- step advance (device-side bookkeeping so a captured graph can iterate) ----
 __global__ void step_advance_kernel(int* token_ids, const int* out_tokens, int* cu_k_len, const uint8_t* finished, int batch)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     // single block: k_len[b] += 1 for unfinished sequences -> rebuild prefix
     __shared__ int s_len[1024];
     for (int b = threadIdx.x; b < batch; b += blockDim.x) {
@@ -382,6 +390,6 @@ extern "C" int b200_step_advance(const int* token_ids, const int* out_tokens, in
     if (!token_ids || !out_tokens || !cu_k_len || batch <= 0 || batch > 1024) {
         return fail(B200_ERR_INVALID_ARG, "step_advance: bad arguments");
     }
-    step_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>((int*)token_ids, out_tokens, cu_k_len, finished, batch);
+    launch_k(step_advance_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, (int*)token_ids, out_tokens, cu_k_len, finished, batch);
     return check_launch("step_advance_kernel");
 }

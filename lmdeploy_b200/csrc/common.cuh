@@ -110,6 +110,17 @@ B200_DEVICE bool elect_one()
     return pred != 0;
 }
 
+// Programmatic dependent launch (host_utils.h launch_k): allow the next kernel of the stream to start launching /
+// wait until every kernel this one depends on has completed and its writes are visible.
+B200_DEVICE void pdl_launch_dependents()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+B200_DEVICE void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 B200_DEVICE void named_bar_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

@@ -131,6 +131,8 @@ __device__ __forceinline__ float2 rope_cos_sin(const RopeConst& r, int idx, int 
 // ------------------------------------------------------------------------------------------------
 __global__ void plan_kernel(int* plan, const int* cu_k_len, const uint8_t* finished, int batch)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     // one block; serial scan by chunks of blockDim
     __shared__ int s_scan[1024];
     __shared__ int s_base;
@@ -167,6 +169,8 @@ __global__ void plan_kernel(int* plan, const int* cu_k_len, const uint8_t* finis
 // cos/sin of every new token's position, computed once per step and shared by all layers
 __global__ void rope_table_kernel(float2* table, RopeConst rope, const int* cu_q_len, const int* cu_k_len, int batch)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int tok = blockIdx.x;
     int       lo = 0, hi = batch;
     while (hi - lo > 1) {
@@ -224,6 +228,8 @@ __device__ __forceinline__ void load4(const T* p, T (&x)[4])
 template<class T, int KVBITS>
 __global__ void __launch_bounds__(128) kv_prologue_kernel(const PrologueParams p)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops      = TypeOps<T>;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -506,7 +512,7 @@ static int launch_prologue(const b200_attention_params* a, void* q_rot, cudaStre
     p.rope_table         = reinterpret_cast<const float2*>(a->rope_table);
     const int items      = (q_rot ? a->num_heads : 0) + a->num_kv_heads;
     dim3      grid(a->token_num, (items + 3) / 4);
-    kv_prologue_kernel<T, KVBITS><<<grid, 128, 0, st>>>(p);
+    launch_k(kv_prologue_kernel<T, KVBITS>, dim3(grid), dim3(128), 0, st, p);
     return check_launch("kv_prologue_kernel");
 }
 
@@ -520,7 +526,7 @@ static int launch_decode(const b200_attention_params* a)
     }
     const int* plan = a->plan;
     if (!plan) {
-        plan_kernel<<<1, 256, 0, st>>>(w.plan, a->cu_k_len, a->finished, a->batch_size);
+        launch_k(plan_kernel, dim3(1), dim3(256), 0, st, w.plan, a->cu_k_len, a->finished, a->batch_size);
         if (int e = check_launch("plan_kernel")) {
             return e;
         }
@@ -554,7 +560,7 @@ static int launch_decode(const b200_attention_params* a)
     p.num_kv_heads  = a->num_kv_heads;
     p.qk_scale      = a->inv_sqrt_dh;
     p.out_mt        = a->out_packed_mt;
-    decode_attention_kernel<T, KVBITS, STAGES><<<grid, kThreads, sizeof(SS), st>>>(p);
+    launch_k(decode_attention_kernel<T, KVBITS, STAGES>, dim3(grid), dim3(kThreads), sizeof(SS), st, p);
     if (int e = check_launch("decode_attention_kernel")) {
         return e;
     }
@@ -562,7 +568,7 @@ static int launch_decode(const b200_attention_params* a)
         return 0;
     }
     dim3 rgrid(a->num_kv_heads, a->batch_size);
-    decode_reduce_kernel<T><<<rgrid, 128, 0, st>>>(p, grid);
+    launch_k(decode_reduce_kernel<T>, dim3(rgrid), dim3(128), 0, st, p, grid);
     return check_launch("decode_reduce_kernel");
 }
 
@@ -598,7 +604,7 @@ extern "C" int b200_decode_attention_plan(int* plan, const int* cu_k_len, const 
     if (!plan || !cu_k_len || batch_size <= 0) {
         return fail(B200_ERR_INVALID_ARG, "bad plan arguments");
     }
-    plan_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(plan, cu_k_len, finished, batch_size);
+    launch_k(plan_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, plan, cu_k_len, finished, batch_size);
     return check_launch("plan_kernel");
 }
 
@@ -608,7 +614,7 @@ extern "C" int b200_rope_table(float* table, const b200_rope_config* rope, const
     if (!table || !rope || !cu_q_len || !cu_k_len || batch_size <= 0 || token_num <= 0) {
         return fail(B200_ERR_INVALID_ARG, "bad rope_table arguments");
     }
-    rope_table_kernel<<<token_num, kHeadDim / 2, 0, (cudaStream_t)stream>>>((float2*)table, make_rope_const(*rope),
+    launch_k(rope_table_kernel, dim3(token_num), dim3(kHeadDim / 2), 0, (cudaStream_t)stream, (float2*)table, make_rope_const(*rope),
                                                                             cu_q_len, cu_k_len, batch_size);
     return check_launch("rope_table_kernel");
 }

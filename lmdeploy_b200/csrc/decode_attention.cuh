@@ -418,6 +418,10 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // the tile plan, q and the page of the new token all come from kernels earlier in the step
+    pdl_launch_dependents();
+    pdl_wait();
+
     const int       Hkv   = p.num_kv_heads;
     const int       G     = p.num_heads / Hkv;
     const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
@@ -681,6 +685,8 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
 template<class T>
 __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops          = TypeOps<T>;
     const int       b   = blockIdx.y;
     const int       h   = blockIdx.x;

@@ -5,6 +5,7 @@
 #include "host_utils.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace b200 {
 namespace gemm {
@@ -196,12 +197,20 @@ static int launch(const Params& p, int smem, cudaStream_t st)
     cfg.blockDim         = dim3(kThreads, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream           = st;
-    // split-K CTAs wait for each other (epilogue part 2): the launch must guarantee co-residency
-    cudaLaunchAttribute attr[1];
-    attr[0].id              = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = p.splits > 1 ? 1 : 0;
-    cfg.attrs               = attr;
-    cfg.numAttrs            = 1;
+    // split-K CTAs wait for each other (epilogue part 2): the launch must guarantee co-residency.
+    // PDL (host_utils.h): the kernel prefetches weights before griddepcontrol.wait.
+    cudaLaunchAttribute attr[2];
+    int                 na = 0;
+    if (p.splits > 1 && !getenv("B200_GEMM_NO_COOP")) {
+        attr[na].id              = cudaLaunchAttributeCooperative;
+        attr[na].val.cooperative = 1;
+        ++na;
+    }
+    attr[na].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    ++na;
+    cfg.attrs    = attr;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) {
         return fail_cuda(e, "cudaLaunchKernelEx(gemm_kernel)");

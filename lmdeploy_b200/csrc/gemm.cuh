@@ -204,6 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
     const int nk = kg1 - kg0;
     if (threadIdx.x == 64) GEMM_TRACE(4, 0);
+    // PDL: let the next kernel start launching; everything up to the first activation load (barrier init, TMEM
+    // allocation, and the whole weight prefetch -- weights are constants) runs before griddepcontrol.wait.
+    pdl_launch_dependents();
 
     constexpr int  WB       = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
     constexpr int  WB_pad   = (WB + 1023) & ~1023;
@@ -264,6 +267,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             int      s  = 0;
             uint32_t ph = 0;
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xp) + (size_t)kg0 * XB;
+            pdl_wait();  // the activations come from the previous kernel
             for (int i = 0; i < nk; ++i) {
                 GEMM_WAIT(smem_u32(&bar_xempty[s]), ph ^ 1, 6, i);
                 GEMM_TRACE(6, i);
@@ -422,6 +426,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             // splits == 1: straight to the output.  splits > 1: fp32 partials to the L2-resident exchange buffer.
             GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
             umma::fence_after_sync();
+            pdl_wait();  // already satisfied (the MMAs consumed upstream activations); orders this thread's global
+                         // accesses (output / exchange buffers may still be read by an upstream kernel otherwise)
             if (threadIdx.x == 64) GEMM_TRACE(4, 2);
             const int half = p.MT >> 1;
             const int tb = epi_half * half, te = tb + half;

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <string>
 
 namespace b200 {
@@ -27,6 +29,32 @@ inline int check_launch(const char* kernel)
         return fail_cuda(e, kernel);
     }
     return 0;
+}
+
+// Every kernel of the decode step is launched with programmatic stream serialization (PDL): the next kernel's CTAs
+// may be scheduled -- and run their input-independent prologue: barrier init, TMEM allocation, weight prefetch --
+// while the previous kernel drains; each kernel executes griddepcontrol.wait before it touches upstream data
+// (common.cuh: pdl_wait / pdl_launch_dependents).  Captured into CUDA graphs as programmatic edges.
+inline bool pdl_enabled()
+{
+    static const bool on = getenv("B200_NO_PDL") == nullptr;
+    return on;
+}
+
+template<class... KArgs, class... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = grid;
+    cfg.blockDim         = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
 }
 
 #define B200_CUDA_TRY(expr)                                                                                            \

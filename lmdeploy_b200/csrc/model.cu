@@ -7,6 +7,7 @@
 // One call enqueues the whole step on a stream with no host synchronisation, so the caller can capture it in a
 // CUDA graph.  Activations between kernels live in the UMMA K-major tile layout so that every GEMM's B operand
 // is one contiguous TMA bulk copy.
+#include <cstdlib>
 #include "../../include/b200_turbomind.h"
 #include "host_utils.h"
 
@@ -57,6 +58,11 @@ static int round16(int x)
 
 extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
 {
+    // Every kernel of the step runs with the maximum shared-memory carveout, so the SMs are not re-partitioned
+    // (L1 <-> shared) between the 211 KB GEMM CTAs and the small glue kernels of a step.
+    if (!getenv("B200_NO_PREFER_SHARED")) {
+        cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
+    }
     if (!out || !c) {
         return fail(B200_ERR_INVALID_ARG, "model_create: NULL argument");
     }

@@ -53,6 +53,8 @@ template<class T, bool RESIDUAL>
 __global__ void __launch_bounds__(1024) rmsnorm_kernel(T* out, int out_mt, T* residual, const T* hidden, const T* w,
                                                        const T* bias, int dim, float eps)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops     = TypeOps<T>;
     const int tok = blockIdx.x;
     T*        r   = residual + (size_t)tok * dim;
@@ -103,6 +105,8 @@ __global__ void __launch_bounds__(1024) rmsnorm_kernel(T* out, int out_mt, T* re
 template<class T>
 __global__ void embedding_kernel(T* out, const T* table, const int* ids, int dim, int vocab)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int tok = blockIdx.x;
     int       id  = ids[tok];
     id            = min(max(id, 0), vocab - 1);
@@ -130,6 +134,8 @@ __device__ __forceinline__ void arg_better(float& bv, int& bi, float v, int i)
 template<class T>
 __global__ void __launch_bounds__(256) argmax_stage1_kernel(const T* logits, int vocab, int64_t ld)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     using Ops    = TypeOps<T>;
     const int row = blockIdx.x, ch = blockIdx.y;
     const int per = (vocab + kArgChunks - 1) / kArgChunks;
@@ -160,6 +166,8 @@ __global__ void __launch_bounds__(256) argmax_stage1_kernel(const T* logits, int
 
 __global__ void argmax_stage2_kernel(int* out, int rows)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) {
         return;
@@ -208,11 +216,11 @@ extern "C" int b200_rmsnorm(void* out, int out_packed_mt, const void* x, const v
         return fail(B200_ERR_UNSUPPORTED, "rmsnorm: dim too large");
     }
     if (dtype == B200_DTYPE_F16) {
-        rmsnorm_kernel<half, false><<<tokens, kBlock, 0, st>>>((half*)out, out_packed_mt, (half*)x, nullptr,
+        launch_k(rmsnorm_kernel<half, false>, dim3(tokens), dim3(kBlock), 0, st, (half*)out, out_packed_mt, (half*)x, nullptr,
                                                                (const half*)weight, nullptr, dim, eps);
     }
     else {
-        rmsnorm_kernel<nv_bfloat16, false><<<tokens, kBlock, 0, st>>>((nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)x,
+        launch_k(rmsnorm_kernel<nv_bfloat16, false>, dim3(tokens), dim3(kBlock), 0, st, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)x,
                                                                       nullptr, (const nv_bfloat16*)weight, nullptr, dim,
                                                                       eps);
     }
@@ -231,12 +239,12 @@ extern "C" int b200_residual_rmsnorm(void* out, int out_packed_mt, void* residua
         return fail(B200_ERR_UNSUPPORTED, "residual_rmsnorm: dim too large");
     }
     if (dtype == B200_DTYPE_F16) {
-        rmsnorm_kernel<half, true><<<tokens, kBlock, 0, st>>>((half*)out, out_packed_mt, (half*)residual,
+        launch_k(rmsnorm_kernel<half, true>, dim3(tokens), dim3(kBlock), 0, st, (half*)out, out_packed_mt, (half*)residual,
                                                               (const half*)hidden, (const half*)weight,
                                                               (const half*)bias, dim, eps);
     }
     else {
-        rmsnorm_kernel<nv_bfloat16, true><<<tokens, kBlock, 0, st>>>(
+        launch_k(rmsnorm_kernel<nv_bfloat16, true>, dim3(tokens), dim3(kBlock), 0, st, 
             (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual, (const nv_bfloat16*)hidden,
             (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, dim, eps);
     }
@@ -250,7 +258,7 @@ extern "C" int b200_embedding_lookup(void* out, const void* table, const int* to
     if (!out || !table || !token_ids || tokens <= 0 || dim % 8) {
         return fail(B200_ERR_INVALID_ARG, "bad embedding arguments");
     }
-    embedding_kernel<uint16_t><<<tokens, 256, 0, (cudaStream_t)stream>>>((uint16_t*)out, (const uint16_t*)table,
+    launch_k(embedding_kernel<uint16_t>, dim3(tokens), dim3(256), 0, (cudaStream_t)stream, (uint16_t*)out, (const uint16_t*)table,
                                                                          token_ids, dim, vocab);
     return check_launch("embedding_kernel");
 }
@@ -263,14 +271,14 @@ extern "C" int b200_argmax(int* out, const void* logits, int rows, int vocab, in
     cudaStream_t st = (cudaStream_t)stream;
     dim3         grid(rows, kArgChunks);
     if (dtype == B200_DTYPE_F16) {
-        argmax_stage1_kernel<half><<<grid, 256, 0, st>>>((const half*)logits, vocab, ld);
+        launch_k(argmax_stage1_kernel<half>, dim3(grid), dim3(256), 0, st, (const half*)logits, vocab, ld);
     }
     else {
-        argmax_stage1_kernel<nv_bfloat16><<<grid, 256, 0, st>>>((const nv_bfloat16*)logits, vocab, ld);
+        launch_k(argmax_stage1_kernel<nv_bfloat16>, dim3(grid), dim3(256), 0, st, (const nv_bfloat16*)logits, vocab, ld);
     }
     if (int e = check_launch("argmax_stage1_kernel")) {
         return e;
     }
-    argmax_stage2_kernel<<<(rows + 3) / 4, 128, 0, st>>>(out, rows);
+    launch_k(argmax_stage2_kernel, dim3((rows + 3) / 4), dim3(128), 0, st, out, rows);
     return check_launch("argmax_stage2_kernel");
 }

@@ -115,12 +115,24 @@ int main(int argc, char** argv)
             }
         }
 #endif
-        CK(cudaEventRecord(e0, st));
+        // steady-state time: the launches are captured into one CUDA graph (no CPU launch cost, warm i-cache),
+        // exactly how the decode step runs them
+        cudaGraph_t     graph;
+        cudaGraphExec_t gexec;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
         for (int i = 0; i < iters; ++i) run(i + 3);
+        CK(cudaStreamEndCapture(st, &graph));
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+        CK(cudaGraphLaunch(gexec, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventRecord(e0, st));
+        CK(cudaGraphLaunch(gexec, st));
         CK(cudaEventRecord(e1, st));
         CK(cudaStreamSynchronize(st));
         float ms;
         CK(cudaEventElapsedTime(&ms, e0, e1));
+        CK(cudaGraphExecDestroy(gexec));
+        CK(cudaGraphDestroy(graph));
         const double us = ms * 1e3 / iters;
         const b200::gemm::Plan pl = b200::gemm::make_plan(s.fmt, mt, s.N, s.K);
         printf("%-8s K=%5d N=%5d m=%d tiles=%d splits=%d nw=%d nx=%d na=%d  %8.2f us  %7.1f GB/s (weights %.1f MB)\n", s.name,
