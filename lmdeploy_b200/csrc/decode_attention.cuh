@@ -696,36 +696,49 @@ __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
     if (tiles == 0) {
         return;
     }
-    const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
-    const long long s0    = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
-    const long long s1    = s0 + tiles;
-    const int       cf    = (int)(((s0 + 1) * grid_main - 1) / total);
-    const int       cl    = (int)((s1 * grid_main - 1) / total);
+    // segment -> CTA range of the main kernel (64-bit divisions: once per block, by one thread)
+    __shared__ int s_cf, s_cl, s_first_slot;
+    if (threadIdx.x == 0) {
+        const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
+        const long long s0    = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
+        const long long s1    = s0 + tiles;
+        const int       cf    = (int)(((s0 + 1) * grid_main - 1) / total);
+        s_cf                  = cf;
+        s_cl                  = (int)((s1 * grid_main - 1) / total);
+        s_first_slot          = (total * cf / grid_main != s0) ? 1 : 0;
+    }
+    __syncthreads();
+    const int cf = s_cf, cl = s_cl;
     if (cf == cl) {
         return;  // written directly by the main kernel
     }
-    const long long lo_cf = total * cf / grid_main;
-    const float     c     = p.qk_scale;
-    for (int i = threadIdx.x; i < G * kHeadDim; i += blockDim.x) {
+    const float c = p.qk_scale;
+    // thread -> 4 consecutive dims of one head (float4 partial loads)
+    for (int i4 = threadIdx.x; i4 < G * kHeadDim / 4; i4 += blockDim.x) {
+        const int i  = i4 * 4;
         const int hd = i / kHeadDim;
         float     m  = -INFINITY;
         for (int cta = cf; cta <= cl; ++cta) {
-            const int slot = 2 * cta + ((cta == cf && lo_cf != s0) ? 1 : 0);
+            const int slot = 2 * cta + (cta == cf ? s_first_slot : 0);
             m              = fmaxf(m, p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]);
         }
-        float acc = 0.f, l = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float  l   = 0.f;
         for (int cta = cf; cta <= cl; ++cta) {
-            const int   slot = 2 * cta + ((cta == cf && lo_cf != s0) ? 1 : 0);
-            const float mk   = p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2];
-            const float lk   = p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2 + 1];
-            const float w    = (mk == -INFINITY) ? 0.f : exp2_approx((mk - m) * c);
-            l += w * lk;
-            acc += w * p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i];
+            const int    slot = 2 * cta + (cta == cf ? s_first_slot : 0);
+            const float2 ml   = *reinterpret_cast<const float2*>(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]);
+            const float  w    = (ml.x == -INFINITY) ? 0.f : exp2_approx((ml.x - m) * c);
+            const float4 o    = *reinterpret_cast<const float4*>(&p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i]);
+            l += w * ml.y;
+            acc.x += w * o.x, acc.y += w * o.y, acc.z += w * o.z, acc.w += w * o.w;
         }
         const int col = h * G * kHeadDim + i;
         T*        dst = reinterpret_cast<T*>(p.out)
                  + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + b) * 8 + (col & 7) : (size_t)b * p.out_stride + col);
-        *dst = Ops::from_f32(acc / l);
+        uint2 v;
+        v.x = Ops::pack2(acc.x / l, acc.y / l);
+        v.y = Ops::pack2(acc.z / l, acc.w / l);
+        *reinterpret_cast<uint2*>(dst) = v;
     }
 }
 

@@ -95,6 +95,8 @@ __global__ void pack_x_kernel(T* xp, const T* x, int M, int MT, int K, int64_t l
     }
 }
 
+constexpr int kMaxSplits = 16;
+
 struct Plan {
     int tiles, splits, nw, nx, na, tmem_cols, a_col, smem;
 };
@@ -102,9 +104,8 @@ struct Plan {
 // Launch plan: a pure function of (format, shape, padded tokens) => deterministic results.
 //   * u4 with N % 256 == 0: two n-tiles per CTA (shared activation tile), ONE CTA per SM with the whole
 //     shared-memory / TMEM budget spent on ring depth (the pipeline, not a second CTA, hides the latency);
-//   * otherwise one n-tile per CTA; u4 with MT <= 64 keeps to 256 TMEM columns / ~113 KB so two CTAs fit an SM;
-//   * K is split over 1/2/4/8 co-resident CTAs (largest count that still fits one wave and leaves every CTA
-//     >= 4 K-groups).
+//   * otherwise one n-tile per CTA (N not a multiple of 256, dense weights), also one CTA per SM;
+//   * K is split over 1/2/4/8 co-resident CTAs (largest count that fits one wave, every CTA >= 4 K-groups).
 static Plan make_plan(int fmt, int MT, int N, int K)
 {
     const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
@@ -112,11 +113,13 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     const int XB     = MT * 256;
     Plan      pl{};
     pl.tiles         = (fmt == kU4 && N % (2 * kBN) == 0) ? 2 : 1;
-    const bool two_per_sm = pl.tiles == 1 && fmt != kDense && MT <= 64;
+    const bool two_per_sm = false;  // 640-thread CTAs at ~90 registers: one CTA per SM in every configuration
     const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
     const int  slots = 148 * (two_per_sm ? 2 : 1);
+    // K splits: largest power of two (<= 8) that fits one wave and leaves every CTA >= 4 K-groups.  (Measured: 6 / 9
+    // splits fill 144 of 148 SMs but are slower -- the exchange traffic grows faster than the tail shrinks.)
     pl.splits = 1;
-    while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4 && MT % (pl.splits * 2) == 0) {
+    while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4) {
         pl.splits *= 2;
     }
     const int budget = (two_per_sm ? 113 : 224) * 1024 - 1024;
@@ -172,7 +175,7 @@ static LinearWs carve_ws(void* base, int K, int N, int MT)
     // aliases another linear's activation / partial region
     w.counters = (int*)take(kCounterBytes);
     w.xp       = take((size_t)K * MT * 2);
-    w.partials = (float*)take((size_t)N * 8 * MT * 4);  // up to 8 K-splits of an [MT][N] fp32 tile
+    w.partials = (float*)take((size_t)N * kMaxSplits * MT * 4);  // up to kMaxSplits K-splits of an [MT][N] fp32 tile
     w.total    = off;
     return w;
 }

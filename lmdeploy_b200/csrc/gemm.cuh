@@ -105,7 +105,7 @@ struct Params {
     int            N, K;
     int            MT;  // padded token count (multiple of 16, <= 128)
     int            M;   // real tokens
-    int            splits;  // K splits along grid.y (1, 2, 4 or 8); > 1 needs a cooperative launch (co-residency)
+    int            splits;  // K splits along grid.y (1 .. 16); > 1 needs a cooperative launch (co-residency)
     int            nw, nx;  // W / X ring depths
     int            na;      // TMEM A-ring slots (multiple of TILES)
     int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
@@ -378,15 +378,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 const int a0 = my_tile * NAt;
                 int       sw = 0, sa = 0;
                 uint32_t  phw = 0, pha = 0;
-                for (int i = 0; i < nk; ++i) {
-                    GEMM_WAIT(smem_u32(&bar_wfull[sw]), phw, 4, i);
+                // software pipeline: the packed weights of k-group i + 1 are fetched from shared memory while the
+                // tcgen05.st of k-group i is still in flight (one thread = one weight row x NKC 32-wide k-chunks)
+                uint32_t st2 = 0;
+                uint4    v[NKC];
+                auto     fetch = [&](int i, int slot, uint32_t phase) {
+                    GEMM_WAIT(smem_u32(&bar_wfull[slot]), phase, 4, i);
                     if (warp == 2 && lane == 0) GEMM_TRACE(1, i);
-                    const uint32_t wsm = w_ring + (uint32_t)sw * WSLOT + my_tile * WB_pad;
-                    const uint32_t st2 = lds32(wsm + 8192 + n_local * 4);
-                    const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
-                    uint4          v[NKC];
+                    const uint32_t wsm = w_ring + (uint32_t)slot * WSLOT + my_tile * WB_pad;
+                    st2                = lds32(wsm + 8192 + n_local * 4);
 #pragma unroll
                     for (int q = 0; q < NKC; ++q) v[q] = lds128(wsm + ((kc0 + q) * 128 + n_local) * 16);
+                };
+                if (nk > 0) {
+                    fetch(0, 0, 0);
+                }
+                for (int i = 0; i < nk; ++i) {
+                    const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
                     // the TMEM slot must have been drained by the MMAs that used it last
                     GEMM_WAIT(smem_u32(&bar_aempty[a0 + sa]), pha ^ 1, 8, i);
                     umma::fence_after_sync();
@@ -404,6 +412,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     }
                     // the W slot is free once its bytes are in registers (the arrive releases the reads)
                     mbar_arrive(smem_u32(&bar_wempty[sw]));
+                    if (++sw == p.nw) {
+                        sw = 0;
+                        phw ^= 1;
+                    }
+                    if (i + 1 < nk) {
+                        fetch(i + 1, sw, phw);
+                    }
                     umma::wait_st();
                     umma::fence_before_sync();
                     mbar_arrive(smem_u32(&bar_aready[a0 + sa]));
@@ -411,10 +426,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     if (++sa == NAt) {
                         sa = 0;
                         pha ^= 1;
-                    }
-                    if (++sw == p.nw) {
-                        sw = 0;
-                        phw ^= 1;
                     }
                 }
             }
@@ -473,10 +484,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             }
         }
         named_bar_sync(2, kDqWarps * 32);
-        const int    tps  = p.MT / p.splits;
+        // token ownership: split r sums tokens [MT * r / splits, MT * (r + 1) / splits)  (any split count works)
+        const int    t_lo = p.MT * sp / p.splits, t_hi = p.MT * (sp + 1) / p.splits;
         const int    tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
-        const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)(sp * tps) * ROWS;
-        for (int idx = tid; idx < tps * (ROWS / 2); idx += kDqWarps * 32) {
+        const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
+        for (int idx = tid; idx < (t_hi - t_lo) * (ROWS / 2); idx += kDqWarps * 32) {
             const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
             float2    acc = make_float2(0.f, 0.f);
             for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
@@ -484,7 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 acc.x += v.x;
                 acc.y += v.y;
             }
-            finalize_pair<T>(p, sp * tps + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
+            finalize_pair<T>(p, t_lo + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
         }
         named_bar_sync(2, kDqWarps * 32);
         if (threadIdx.x == 64) {
