@@ -166,7 +166,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---------------- phase A: device-resident steps (value) ----------------
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph
     runner.reset_lengths(ctx)
     step_fn = runner.make_device_step(graph=use_graph)
     for _ in range(args.warmup):

@@ -12,7 +12,9 @@
 //      normalises and writes the next GEMM's input tile;
 //   5. a second flag round ("done reading epoch e") guards the buffer against being overwritten by the next
 //      GEMM before every peer finished reading it.
-// Flags are monotonically increasing epochs, so no reset traffic is needed.
+// Flags are monotonically increasing epochs, so no reset traffic is needed.  The epoch lives in DEVICE memory, one
+// counter per CTA slot (every rank runs the same kernel sequence with the same grids, so slot i counts the same
+// on all ranks): a captured CUDA graph of the step replays correctly.
 #include "../../include/b200_turbomind.h"
 #include "common.cuh"
 #include "host_utils.h"
@@ -27,7 +29,25 @@ constexpr int kBlock     = 256;
 struct Peers {
     void* data[kMaxRanks];
     int*  flags[kMaxRanks];
+    int*  slot_epoch;  // [kFlagSlots] this rank's per-CTA-slot epoch counters (device memory)
 };
+
+// epoch of this launch for this CTA slot (read by thread 0, broadcast through shared memory)
+__device__ __forceinline__ int next_epoch(const Peers& peers)
+{
+    __shared__ int s_epoch;
+    if (threadIdx.x == 0) {
+        s_epoch = peers.slot_epoch[blockIdx.x] + 1;
+    }
+    __syncthreads();
+    return s_epoch;
+}
+__device__ __forceinline__ void commit_epoch(const Peers& peers, int epoch)
+{
+    if (threadIdx.x == 0) {
+        peers.slot_epoch[blockIdx.x] = epoch;
+    }
+}
 
 __device__ __forceinline__ void st_release_sys(int* p, int v)
 {
@@ -71,12 +91,13 @@ __device__ __forceinline__ void barrier_phase(const Peers& peers, int rank, int 
 
 template<class T>
 __global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
-    Peers peers, int rank, int world, int epoch, T* out, int out_mt, T* residual, const T* weight, const T* bias,
+    Peers peers, int rank, int world, T* out, int out_mt, T* residual, const T* weight, const T* bias,
     int tokens, int dim, float eps, size_t data_offset)
 {
     pdl_launch_dependents();
     pdl_wait();
     using Ops = TypeOps<T>;
+    const int epoch = next_epoch(peers);
     __threadfence_system();
     __syncthreads();
     barrier_phase(peers, rank, world, 0, epoch);
@@ -144,15 +165,17 @@ __global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
     }
     // everyone finished reading my buffer for this epoch?
     barrier_phase(peers, rank, world, 1, epoch);
+    commit_epoch(peers, epoch);
 }
 
 template<class T>
-__global__ void __launch_bounds__(kBlock) allreduce_sum_kernel(Peers peers, int rank, int world, int epoch, T* data,
+__global__ void __launch_bounds__(kBlock) allreduce_sum_kernel(Peers peers, int rank, int world, T* data,
                                                                size_t count, size_t data_offset)
 {
     pdl_launch_dependents();
     pdl_wait();
     using Ops = TypeOps<T>;
+    const int epoch = next_epoch(peers);
     // stage: copy my data into my exchange buffer
     T* mine = reinterpret_cast<T*>((char*)peers.data[rank] + data_offset);
     for (size_t i = (blockIdx.x * (size_t)kBlock + threadIdx.x) * 8; i < count; i += (size_t)gridDim.x * kBlock * 8) {
@@ -173,16 +196,18 @@ __global__ void __launch_bounds__(kBlock) allreduce_sum_kernel(Peers peers, int 
         *reinterpret_cast<uint4*>(data + i) = *reinterpret_cast<const uint4*>(&sum[0]);
     }
     barrier_phase(peers, rank, world, 1, epoch);
+    commit_epoch(peers, epoch);
 }
 
 // vocab-sharded greedy: local argmax (one CTA per row), exchange (value, index), pick global winner
 template<class T>
-__global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int rank, int world, int epoch, int* out,
+__global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int rank, int world, int* out,
                                                                const T* logits, int rows, int vocab, size_t data_offset)
 {
     pdl_launch_dependents();
     pdl_wait();
     using Ops = TypeOps<T>;
+    const int epoch = next_epoch(peers);
     __shared__ float s_v[32];
     __shared__ int   s_i[32];
     const int row = blockIdx.x;
@@ -236,6 +261,7 @@ __global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int 
         out[row] = gi;
     }
     barrier_phase(peers, rank, world, 1, epoch);
+    commit_epoch(peers, epoch);
 }
 
 }  // namespace comm
@@ -247,7 +273,6 @@ using namespace b200::comm;
 struct b200_comm {
     int    rank{}, world{};
     Peers  peers{};
-    int    epoch{0};
     size_t buf_bytes{};
 };
 
@@ -275,6 +300,14 @@ extern "C" int b200_comm_create(b200_comm** out, int rank, int world, void* cons
         c->peers.data[r]  = peer_data[r];
         c->peers.flags[r] = (int*)peer_flags[r];
     }
+    cudaError_t e = cudaMalloc((void**)&c->peers.slot_epoch, kFlagSlots * sizeof(int));
+    if (e == cudaSuccess) {
+        e = cudaMemset(c->peers.slot_epoch, 0, kFlagSlots * sizeof(int));
+    }
+    if (e != cudaSuccess) {
+        delete c;
+        return fail_cuda(e, "comm_create: epoch counters");
+    }
     *out = c;
     return 0;
 }
@@ -286,6 +319,9 @@ extern "C" void* b200_comm_local_buffer(b200_comm* c)
 
 extern "C" void b200_comm_destroy(b200_comm* c)
 {
+    if (c && c->peers.slot_epoch) {
+        cudaFree(c->peers.slot_epoch);
+    }
     delete c;
 }
 
@@ -305,17 +341,16 @@ extern "C" int b200_comm_allreduce_residual_rmsnorm(b200_comm* c, void* out, int
     const char* base = (const char*)c->peers.data[c->rank];
     const size_t off = (const char*)hidden_partial - base;
     cudaStream_t st  = (cudaStream_t)stream;
-    const int    ep  = ++c->epoch;
     const int    grid = comm_grid(tokens);
     if (dtype == B200_DTYPE_F16) {
-        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kBlock), 0, st, c->peers, c->rank, c->world, ep, (half*)out,
+        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kBlock), 0, st, c->peers, c->rank, c->world, (half*)out,
                                                                          out_packed_mt, (half*)residual,
                                                                          (const half*)weight, (const half*)bias, tokens,
                                                                          dim, eps, off);
     }
     else {
         launch_k(allreduce_residual_rmsnorm_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, st, 
-            c->peers, c->rank, c->world, ep, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual,
+            c->peers, c->rank, c->world, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual,
             (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, tokens, dim, eps, off);
     }
     return check_launch("allreduce_residual_rmsnorm_kernel");
@@ -326,14 +361,13 @@ extern "C" int b200_comm_allreduce_sum(b200_comm* c, void* data, size_t count, i
     if (!c || !data || count % 8) {
         return fail(B200_ERR_INVALID_ARG, "allreduce_sum: bad arguments");
     }
-    const int ep   = ++c->epoch;
     const int grid = (int)std::min<size_t>(kFlagSlots, (count / 8 + kBlock - 1) / kBlock);
     if (dtype == B200_DTYPE_F16) {
-        launch_k(allreduce_sum_kernel<half>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep,
+        launch_k(allreduce_sum_kernel<half>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world,
                                                                               (half*)data, count, 0);
     }
     else {
-        launch_k(allreduce_sum_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep,
+        launch_k(allreduce_sum_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, (cudaStream_t)stream, c->peers, c->rank, c->world,
                                                                                      (nv_bfloat16*)data, count, 0);
     }
     return check_launch("allreduce_sum_kernel");
@@ -345,17 +379,16 @@ extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const v
     if (!c || !out_tokens || !local_logits || rows <= 0 || rows > kFlagSlots) {
         return fail(B200_ERR_INVALID_ARG, "argmax_allgather: bad arguments (rows <= 128)");
     }
-    const int ep = ++c->epoch;
     // (value, index) pairs live in the last 4 KB of the exchange buffer
     const size_t off = 0;
     if (dtype == B200_DTYPE_F16) {
-        launch_k(argmax_exchange_kernel<half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, ep, out_tokens,
+        launch_k(argmax_exchange_kernel<half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, out_tokens,
                                                                               (const half*)local_logits, rows,
                                                                               vocab_per_rank, off);
     }
     else {
         launch_k(argmax_exchange_kernel<nv_bfloat16>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, 
-            c->peers, c->rank, c->world, ep, out_tokens, (const nv_bfloat16*)local_logits, rows, vocab_per_rank, off);
+            c->peers, c->rank, c->world, out_tokens, (const nv_bfloat16*)local_logits, rows, vocab_per_rank, off);
     }
     return check_launch("argmax_exchange_kernel");
 }
