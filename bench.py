@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
 # capture (profiles/): filled per config once measured
-TRAFFIC_NCU = {"c2": 281641216}
+TRAFFIC_NCU = {"c2": 282659584}   # profiles/r01b_attention_ncu.md
 
 CONFIGS = {
     # name: (spec, batch, ctx, kv quant policy)
