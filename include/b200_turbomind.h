@@ -232,7 +232,10 @@ B200_API size_t b200_comm_flags_bytes(void);
 B200_API int b200_comm_create(b200_comm** comm, int rank, int world_size, void* const* peer_data, void* const* peer_flags);
 B200_API void b200_comm_destroy(b200_comm* comm);
 /* this rank's exchange buffer: the GEMM that feeds a fused all-reduce must write its output here */
-B200_API void* b200_comm_local_buffer(b200_comm* comm);
+/* the exchange buffer has two halves used alternately by the two exchanges of a layer (no "done reading" round);
+ * b200_comm_set_geometry fixes where the second half starts */
+B200_API int b200_comm_set_geometry(b200_comm* comm, int max_tokens, int hidden);
+B200_API void* b200_comm_local_buffer(b200_comm* comm, int half);
 /* hidden_partial: this rank's [tokens, dim] partial sums (T).  On return (stream order):
  *   residual += sum_ranks(hidden_partial) (+ bias);  out = RMSNorm(residual) * weight  (packed if out_packed_mt > 0) */
 B200_API int b200_comm_allreduce_residual_rmsnorm(b200_comm* comm, void* out, int out_packed_mt, void* residual,

@@ -10,8 +10,9 @@
 //   4. each CTA owns a slice of tokens: it pulls the same slice from every peer with 16-byte peer loads, sums
 //      the ranks in rank order in T (bit-identical on every rank), adds the residual, reduces sum-of-squares,
 //      normalises and writes the next GEMM's input tile;
-//   5. a second flag round ("done reading epoch e") guards the buffer against being overwritten by the next
-//      GEMM before every peer finished reading it.
+//   5. no second ("done reading") flag round: the two exchanges of a layer use two different halves of the exchange
+//      buffer (b200_comm_local_buffer(comm, 0 / 1)), so a half is rewritten by a GEMM only after the NEXT exchange's
+//      arrival round, and arriving there implies having finished the reads of the previous one.
 // Flags are monotonically increasing epochs, so no reset traffic is needed.  The epoch lives in DEVICE memory, one
 // counter per CTA slot (every rank runs the same kernel sequence with the same grids, so slot i counts the same
 // on all ranks): a captured CUDA graph of the step replays correctly.
@@ -89,8 +90,14 @@ __device__ __forceinline__ void barrier_phase(const Peers& peers, int rank, int 
     __syncthreads();
 }
 
+constexpr int kArBlock   = 512;
+constexpr int kArMaxPass = 2;  // dim <= 512 * 8 * 2 = 8192
+
+// One CTA per token (grid-strided).  All peer loads of a token (world x passes 16-byte loads per thread) are issued
+// before the first add, so the exchange costs ONE NVLink round trip; the sum runs in rank order in T (bit-identical
+// on every rank), then residual add, sum of squares, normalisation -- the row never leaves registers.
 template<class T>
-__global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
+__global__ void __launch_bounds__(kArBlock) allreduce_residual_rmsnorm_kernel(
     Peers peers, int rank, int world, T* out, int out_mt, T* residual, const T* weight, const T* bias,
     int tokens, int dim, float eps, size_t data_offset)
 {
@@ -98,47 +105,58 @@ __global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
     pdl_wait();
     using Ops = TypeOps<T>;
     const int epoch = next_epoch(peers);
-    __threadfence_system();
-    __syncthreads();
+    // the partial tile was written by the previous kernel on this stream (complete => in L2, where peers read it)
     barrier_phase(peers, rank, world, 0, epoch);
 
-    __shared__ float s_part[kBlock / 32];
+    __shared__ float s_part[kArBlock / 32];
     __shared__ float s_total;
+    const int npass = (dim + kArBlock * 8 - 1) / (kArBlock * 8);
     for (int tok = blockIdx.x; tok < tokens; tok += gridDim.x) {
-        T*    r   = residual + (size_t)tok * dim;
+        T*    r = residual + (size_t)tok * dim;
+        uint4 v[kArMaxPass][kMaxRanks];
+#pragma unroll
+        for (int ps = 0; ps < kArMaxPass; ++ps) {
+            const int i = (ps * kArBlock + threadIdx.x) * 8;
+#pragma unroll
+            for (int q = 0; q < kMaxRanks; ++q) {
+                if (ps < npass && q < world && i < dim) {
+                    v[ps][q] = ld_peer_v4(reinterpret_cast<const T*>((const char*)peers.data[q] + data_offset)
+                                          + (size_t)tok * dim + i);
+                }
+            }
+        }
+        T     rv[kArMaxPass][8];
         float acc = 0.f;
-        for (int i = threadIdx.x * 8; i < dim; i += kBlock * 8) {
-            T sum[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) sum[j] = Ops::from_f32(0.f);
-            for (int q = 0; q < world; ++q) {
-                const T* src = reinterpret_cast<const T*>((const char*)peers.data[q] + data_offset) + (size_t)tok * dim + i;
-                T        v[8];
-                *reinterpret_cast<uint4*>(&v[0]) = ld_peer_v4(src);
-                if (q == 0) {
+        for (int ps = 0; ps < kArMaxPass; ++ps) {
+            const int i = (ps * kArBlock + threadIdx.x) * 8;
+            if (ps < npass && i < dim) {
+                T sum[8];
+                *reinterpret_cast<uint4*>(&sum[0]) = v[ps][0];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) sum[j] = v[j];
+                for (int q = 1; q < kMaxRanks; ++q) {
+                    if (q < world) {
+                        T pv[8];
+                        *reinterpret_cast<uint4*>(&pv[0]) = v[ps][q];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) sum[j] = Ops::add(sum[j], pv[j]);
+                    }
                 }
-                else {
+                *reinterpret_cast<uint4*>(&rv[ps][0]) = *reinterpret_cast<const uint4*>(r + i);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) sum[j] = Ops::add(sum[j], v[j]);
+                for (int j = 0; j < 8; ++j) rv[ps][j] = Ops::add(rv[ps][j], sum[j]);
+                if (bias) {
+                    T bv[8];
+                    *reinterpret_cast<uint4*>(&bv[0]) = *reinterpret_cast<const uint4*>(bias + i);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rv[ps][j] = Ops::add(rv[ps][j], bv[j]);
                 }
-            }
-            T rv[8];
-            *reinterpret_cast<uint4*>(&rv[0]) = *reinterpret_cast<const uint4*>(r + i);
+                *reinterpret_cast<uint4*>(r + i) = *reinterpret_cast<const uint4*>(&rv[ps][0]);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rv[j] = Ops::add(rv[j], sum[j]);
-            if (bias) {
-                T bv[8];
-                *reinterpret_cast<uint4*>(&bv[0]) = *reinterpret_cast<const uint4*>(bias + i);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) rv[j] = Ops::add(rv[j], bv[j]);
-            }
-            *reinterpret_cast<uint4*>(r + i) = *reinterpret_cast<const uint4*>(&rv[0]);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float f = Ops::to_f32(rv[j]);
-                acc           = fmaf(f, f, acc);
+                for (int j = 0; j < 8; ++j) {
+                    const float f = Ops::to_f32(rv[ps][j]);
+                    acc           = fmaf(f, f, acc);
+                }
             }
         }
 #pragma unroll
@@ -147,24 +165,25 @@ __global__ void __launch_bounds__(kBlock) allreduce_residual_rmsnorm_kernel(
         __syncthreads();
         if (threadIdx.x == 0) {
             float t = 0.f;
-            for (int i = 0; i < kBlock / 32; ++i) t += s_part[i];
+            for (int i = 0; i < kArBlock / 32; ++i) t += s_part[i];
             s_total = t;
         }
         __syncthreads();
         const float inv_rms = rsqrtf(s_total / (float)dim + eps);
-        for (int i = threadIdx.x * 8; i < dim; i += kBlock * 8) {
-            T rv[8], wv[8], ov[8];
-            *reinterpret_cast<uint4*>(&rv[0]) = *reinterpret_cast<const uint4*>(r + i);
-            *reinterpret_cast<uint4*>(&wv[0]) = *reinterpret_cast<const uint4*>(weight + i);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ov[j] = Ops::mul(Ops::from_f32(Ops::to_f32(rv[j]) * inv_rms), wv[j]);
-            T* dst = out_mt > 0 ? out + ((size_t)(i >> 3) * out_mt + tok) * 8 : out + (size_t)tok * dim + i;
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&ov[0]);
+        for (int ps = 0; ps < kArMaxPass; ++ps) {
+            const int i = (ps * kArBlock + threadIdx.x) * 8;
+            if (ps < npass && i < dim) {
+                T wv[8], ov[8];
+                *reinterpret_cast<uint4*>(&wv[0]) = *reinterpret_cast<const uint4*>(weight + i);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ov[j] = Ops::mul(Ops::from_f32(Ops::to_f32(rv[ps][j]) * inv_rms), wv[j]);
+                T* dst = out_mt > 0 ? out + ((size_t)(i >> 3) * out_mt + tok) * 8 : out + (size_t)tok * dim + i;
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(&ov[0]);
+            }
         }
         __syncthreads();
     }
-    // everyone finished reading my buffer for this epoch?
-    barrier_phase(peers, rank, world, 1, epoch);
     commit_epoch(peers, epoch);
 }
 
@@ -274,18 +293,28 @@ struct b200_comm {
     int    rank{}, world{};
     Peers  peers{};
     size_t buf_bytes{};
+    size_t half_bytes{};  // offset of the second half of the exchange buffer
 };
 
 extern "C" size_t b200_comm_buffer_bytes(int max_tokens, int hidden, int vocab_per_rank)
 {
     (void)vocab_per_rank;
-    size_t a = (size_t)max_tokens * hidden * 2;
-    return (a + 4095) / 4096 * 4096 + 4096;
+    size_t a = ((size_t)max_tokens * hidden * 2 + 4095) / 4096 * 4096;
+    return 2 * a + 4096;  // two halves (see b200_comm_local_buffer) + the argmax exchange page
 }
 
 extern "C" size_t b200_comm_flags_bytes(void)
 {
     return (size_t)2 * kMaxRanks * kFlagSlots * sizeof(int);
+}
+
+extern "C" int b200_comm_set_geometry(b200_comm* c, int max_tokens, int hidden)
+{
+    if (!c || max_tokens <= 0 || hidden <= 0) {
+        return fail(B200_ERR_INVALID_ARG, "comm_set_geometry: bad arguments");
+    }
+    c->half_bytes = ((size_t)max_tokens * hidden * 2 + 4095) / 4096 * 4096;
+    return 0;
 }
 
 extern "C" int b200_comm_create(b200_comm** out, int rank, int world, void* const* peer_data, void* const* peer_flags)
@@ -312,9 +341,9 @@ extern "C" int b200_comm_create(b200_comm** out, int rank, int world, void* cons
     return 0;
 }
 
-extern "C" void* b200_comm_local_buffer(b200_comm* c)
+extern "C" void* b200_comm_local_buffer(b200_comm* c, int half)
 {
-    return c ? c->peers.data[c->rank] : nullptr;
+    return c ? (char*)c->peers.data[c->rank] + (half ? c->half_bytes : 0) : nullptr;
 }
 
 extern "C" void b200_comm_destroy(b200_comm* c)
@@ -334,7 +363,7 @@ extern "C" int b200_comm_allreduce_residual_rmsnorm(b200_comm* c, void* out, int
                                                     const void* hidden_partial, const void* weight, const void* bias,
                                                     int tokens, int dim, float eps, int dtype, void* stream)
 {
-    if (!c || !out || !residual || !hidden_partial || !weight || tokens <= 0 || dim % 8) {
+    if (!c || !out || !residual || !hidden_partial || !weight || tokens <= 0 || dim % 8 || dim > kArBlock * 8 * kArMaxPass) {
         return fail(B200_ERR_INVALID_ARG, "allreduce_residual_rmsnorm: bad arguments");
     }
     // the partial must live inside this rank's exchange buffer
@@ -343,13 +372,13 @@ extern "C" int b200_comm_allreduce_residual_rmsnorm(b200_comm* c, void* out, int
     cudaStream_t st  = (cudaStream_t)stream;
     const int    grid = comm_grid(tokens);
     if (dtype == B200_DTYPE_F16) {
-        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kBlock), 0, st, c->peers, c->rank, c->world, (half*)out,
+        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kArBlock), 0, st, c->peers, c->rank, c->world, (half*)out,
                                                                          out_packed_mt, (half*)residual,
                                                                          (const half*)weight, (const half*)bias, tokens,
                                                                          dim, eps, off);
     }
     else {
-        launch_k(allreduce_residual_rmsnorm_kernel<nv_bfloat16>, dim3(grid), dim3(kBlock), 0, st, 
+        launch_k(allreduce_residual_rmsnorm_kernel<nv_bfloat16>, dim3(grid), dim3(kArBlock), 0, st, 
             c->peers, c->rank, c->world, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual,
             (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, tokens, dim, eps, off);
     }
@@ -379,8 +408,8 @@ extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const v
     if (!c || !out_tokens || !local_logits || rows <= 0 || rows > kFlagSlots) {
         return fail(B200_ERR_INVALID_ARG, "argmax_allgather: bad arguments (rows <= 128)");
     }
-    // (value, index) pairs live in the last 4 KB of the exchange buffer
-    const size_t off = 0;
+    // (value, index) pairs live in the page behind the two exchange halves
+    const size_t off = 2 * c->half_bytes;
     if (dtype == B200_DTYPE_F16) {
         launch_k(argmax_exchange_kernel<half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, out_tokens,
                                                                               (const half*)local_logits, rows,

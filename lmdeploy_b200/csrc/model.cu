@@ -38,7 +38,7 @@ struct b200_model {
     void* qkv{};
     void* attn_xp{};
     void* o{};
-    void* o_x{};  // GEMM output inside the comm exchange buffer (TP) -- overrides `o`
+    void* o_x[2]{};  // GEMM outputs inside the two halves of the comm exchange buffer (TP) -- override `o`
     void* act_xp{};
     void* logits{};
     void* attn_ws{};
@@ -47,6 +47,10 @@ struct b200_model {
     size_t lin_ws_bytes{};
     int*  plan{};
     float* rope_table{};
+    // B200_STEP_TRACE=1: CUDA-event time per operator of every (un-captured) step, printed to stderr -- the analogue of
+    // the reference's NVTX ranges around the same calls (utils/nvtx_utils.h:37-50)
+    bool trace_on{};
+    std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> trace;
 };
 
 using namespace b200;
@@ -60,6 +64,7 @@ extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
 {
     // Every kernel of the step runs with the maximum shared-memory carveout, so the SMs are not re-partitioned
     // (L1 <-> shared) between the 211 KB GEMM CTAs and the small glue kernels of a step.
+    // (measured: no effect on B200; kept switchable)
     if (!getenv("B200_NO_PREFER_SHARED")) {
         cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
     }
@@ -76,6 +81,7 @@ extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
         return fail(B200_ERR_UNSUPPORTED, "hidden / inter_size / vocab (per rank) must be multiples of 128");
     }
     auto* m   = new b200_model();
+    m->trace_on = getenv("B200_STEP_TRACE") != nullptr;
     m->cfg    = *c;
     m->layers.resize(c->num_layers);
     m->mt_cap = round16(c->max_batch);
@@ -198,7 +204,13 @@ extern "C" int b200_model_set_comm(b200_model* m, b200_comm* comm)
         return fail(B200_ERR_INVALID_ARG, "set_comm: NULL model");
     }
     m->comm = comm;
-    m->o_x  = comm ? b200_comm_local_buffer(comm) : nullptr;
+    if (comm) {
+        if (int e = b200_comm_set_geometry(comm, m->cfg.max_batch, m->cfg.hidden)) {
+            return e;
+        }
+    }
+    m->o_x[0] = comm ? b200_comm_local_buffer(comm, 0) : nullptr;
+    m->o_x[1] = comm ? b200_comm_local_buffer(comm, 1) : nullptr;
     return 0;
 }
 
@@ -224,6 +236,42 @@ extern "C" void* b200_model_buffer(b200_model* m, int which)
         }                                                                                                              \
     } while (0)
 
+#define TRY_T(cat, expr)                                                                                               \
+    do {                                                                                                               \
+        cudaEvent_t e0_{}, e1_{};                                                                                      \
+        if (m->trace_on) {                                                                                             \
+            cudaEventCreate(&e0_);                                                                                     \
+            cudaEventCreate(&e1_);                                                                                     \
+            cudaEventRecord(e0_, (cudaStream_t)stream);                                                                \
+        }                                                                                                              \
+        TRY(expr);                                                                                                     \
+        if (m->trace_on) {                                                                                             \
+            cudaEventRecord(e1_, (cudaStream_t)stream);                                                                \
+            m->trace.emplace_back(cat, e0_, e1_);                                                                      \
+        }                                                                                                              \
+    } while (0)
+
+static void report_trace(b200_model* m, void* stream)
+{
+    static const char* names[] = {"embed+norm+plan", "qkv gemm", "attention", "wo gemm", "norm/allreduce 1", "w13 gemm",
+                                  "w2 gemm", "norm/allreduce 2", "lm_head", "sample+advance"};
+    cudaStreamSynchronize((cudaStream_t)stream);
+    double tot[10] = {0};
+    for (auto& t : m->trace) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t));
+        tot[std::get<0>(t)] += ms;
+        cudaEventDestroy(std::get<1>(t));
+        cudaEventDestroy(std::get<2>(t));
+    }
+    m->trace.clear();
+    double sum = 0;
+    for (double v : tot) sum += v;
+    fprintf(stderr, "[b200 step trace rank %d] total %.3f ms |", m->cfg.tp_rank, sum);
+    for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.3f |", names[i], tot[i]);
+    fprintf(stderr, "\n");
+}
+
 extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in, void* stream)
 {
     if (!m || !in) {
@@ -241,12 +289,13 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
     const int qkv_dim = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
     const int es      = 2;
     const int L       = c.num_layers;
-    void*     o_buf   = m->o_x ? m->o_x : m->o;
+    void*     o_buf   = m->o_x[0] ? m->o_x[0] : m->o;   // wo output (exchange half 0 under TP)
+    void*     o_buf2  = m->o_x[1] ? m->o_x[1] : m->o;   // w2 output (exchange half 1 under TP)
 
-    TRY(b200_embedding_lookup(m->residual, m->embedding, in->token_ids, B, c.hidden, c.embedding_rows, c.dtype, stream));
-    TRY(b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, B, c.hidden, c.norm_eps, c.dtype, stream));
-    TRY(b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
-    TRY(b200_rope_table(m->rope_table, &c.rope, in->cu_q_len, in->cu_k_len, B, B, stream));
+    TRY_T(0, b200_embedding_lookup(m->residual, m->embedding, in->token_ids, B, c.hidden, c.embedding_rows, c.dtype, stream));
+    TRY_T(0, b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, B, c.hidden, c.norm_eps, c.dtype, stream));
+    TRY_T(0, b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
+    TRY_T(0, b200_rope_table(m->rope_table, &c.rope, in->cu_q_len, in->cu_k_len, B, B, stream));
 
     for (int l = 0; l < L; ++l) {
         const LayerW& W = m->layers[l];
@@ -254,7 +303,7 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
             return fail(B200_ERR_STATE, "decode_step: layer weights not set");
         }
         // ---- attention block ----
-        TRY(b200_linear_forward_packed(&W.qkv, m->xp, MT, B, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        TRY_T(1, b200_linear_forward_packed(&W.qkv, m->xp, MT, B, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         b200_attention_params a{};
         a.out    = m->attn_xp;
         a.q      = m->qkv;
@@ -270,44 +319,47 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
         a.rope = c.rope, a.quant_policy = c.quant_policy, a.dtype = c.dtype;
         a.workspace = m->attn_ws, a.workspace_bytes = m->attn_ws_bytes;
         a.plan = m->plan, a.rope_table = m->rope_table, a.out_packed_mt = MT, a.stream = stream;
-        TRY(b200_decode_attention(&a));
-        TRY(b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        TRY_T(2, b200_decode_attention(&a));
+        TRY_T(3, b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         // AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287)
         if (m->comm) {
-            TRY(b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
+            TRY_T(4, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
                                                      c.hidden, c.norm_eps, c.dtype, stream));
         }
         else {
-            TRY(b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
+            TRY_T(4, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
                                       c.dtype, stream));
         }
         // ---- FFN block ----
-        TRY(b200_linear_forward_packed(&W.w13, m->xp, MT, B, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
+        TRY_T(5, b200_linear_forward_packed(&W.w13, m->xp, MT, B, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
                                        stream));
-        TRY(b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        TRY_T(6, b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf2, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         const void* next_norm = (l + 1 < L) ? m->layers[l + 1].attn_norm : m->final_norm;
         if (m->comm) {
-            TRY(b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, next_norm, nullptr, B,
+            TRY_T(7, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B,
                                                      c.hidden, c.norm_eps, c.dtype, stream));
         }
         else {
-            TRY(b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
+            TRY_T(7, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
                                       stream));
         }
     }
     // PostEmbedding (language_model.cc:285-335) + greedy sampling
-    TRY(b200_linear_forward_packed(&m->lm_head, m->xp, MT, B, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
+    TRY_T(8, b200_linear_forward_packed(&m->lm_head, m->xp, MT, B, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
                                    stream));
     if (in->out_tokens) {
         if (m->comm && c.tp_size > 1) {
-            TRY(b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, B, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, B, c.vocab, c.dtype, stream));
         }
         else {
-            TRY(b200_argmax(in->out_tokens, m->logits, B, c.vocab, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_argmax(in->out_tokens, m->logits, B, c.vocab, c.vocab, c.dtype, stream));
         }
     }
     if (in->advance) {
-        TRY(b200_step_advance(in->token_ids, in->out_tokens, (int*)in->cu_k_len, in->finished, B, stream));
+        TRY_T(9, b200_step_advance(in->token_ids, in->out_tokens, (int*)in->cu_k_len, in->finished, B, stream));
+    }
+    if (m->trace_on) {
+        report_trace(m, stream);
     }
     return 0;
 }
