@@ -60,6 +60,20 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p)
     asm volatile("ld.acquire.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Flag traffic of the arrival round.  The payload a flag announces was written by the PREVIOUS kernel of the stream
+// (complete and in L2 before this kernel started), so the store needs no release fence (a system-scope release makes
+// the SM drain every outstanding access first); the payload reads that follow are ld.volatile (never L1-cached) and
+// are ordered after the spin by bar.sync.
+__device__ __forceinline__ void st_relaxed_sys(int* p, int v)
+{
+    asm volatile("st.relaxed.sys.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // 16-byte load that never hits a stale L1 line (peer memory is not coherent with the local L1)
 __device__ __forceinline__ uint4 ld_peer_v4(const void* p)
@@ -77,6 +91,18 @@ __device__ __forceinline__ int* flag_ptr(int* base, int phase, int src)
 
 // signal all peers + wait for all peers (called by one thread per CTA 0 .. then broadcast via grid?)
 // Every CTA performs its own signalling on its own flag slot (slot = blockIdx.x) so no grid sync is needed.
+// arrival round for payloads produced by an earlier kernel (see st_relaxed_sys)
+__device__ __forceinline__ void arrive_phase_relaxed(const Peers& peers, int rank, int world, int epoch)
+{
+    if (threadIdx.x < world) {
+        const int r = threadIdx.x;
+        st_relaxed_sys(flag_ptr(peers.flags[r], 0, rank) + blockIdx.x, epoch);
+        const int* f = flag_ptr(peers.flags[rank], 0, r) + blockIdx.x;
+        while (ld_relaxed_sys(f) < epoch) {}
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void barrier_phase(const Peers& peers, int rank, int world, int phase, int epoch)
 {
     if (threadIdx.x < world) {
@@ -106,7 +132,7 @@ __global__ void __launch_bounds__(kArBlock) allreduce_residual_rmsnorm_kernel(
     using Ops = TypeOps<T>;
     const int epoch = next_epoch(peers);
     // the partial tile was written by the previous kernel on this stream (complete => in L2, where peers read it)
-    barrier_phase(peers, rank, world, 0, epoch);
+    arrive_phase_relaxed(peers, rank, world, epoch);
 
     __shared__ float s_part[kArBlock / 32];
     __shared__ float s_total;
