@@ -165,8 +165,11 @@ B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
  *   LlamaLinear::Forward (models/llama/LlamaLinear.cu:226-273) -> gemm::Gemm::Run (kernels/gemm/gemm.h:23-41)
  * weight_format: 0 dense T [K,N]; 1 u4 AWQ (TurboMind pre-prepare layout: qweight int32 [K, N/8] with nibble i of
  *   word w = column 8w+i -- what lmdeploy/turbomind/weight_format.py:63-74 pack_u4_row produces -- plus
- *   scales T [K/g, N] and integer-valued zeros T [K/g, N], g = 128).
- * D[m, N] = x[m, K] . dequant(W) (+ bias); dequant is w = fma_T(q, s, -(z*s)_T) exactly as
+ *   scales T [K/g, N] and integer-valued zeros T [K/g, N], g = 128);
+ *   2 fp8: weight float8_e4m3fn bytes [K, N] (or [N, K] with weight_is_transposed) and `scales` = the f32 block
+ *   scales [K/128, N/128] (weight_scale_inv; zeros NULL) -- the non-sm90 path of the reference: block scales cast to
+ *   T and applied per K-group, w = T(e4m3) *_T T(scale) (models/linear_weight.cc:138-150, gemm/transform.h:92-97).
+ * D[m, N] = x[m, K] . dequant(W) (+ bias); u4 dequant is w = fma_T(q, s, -(z*s)_T) exactly as
  * kernels/gemm/transform.h:48-74 / cast.cu:155; accumulation fp32 on tcgen05 tensor cores.
  * epilogue: 0 none; 1 gated SiLU over element-interleaved (gate, up) columns -> [m, N/2]
  *   (kernels/gemm/epilogue.h:158-177).
@@ -177,9 +180,9 @@ B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
 typedef struct {
     int         input_dim;     /* K */
     int         output_dim;    /* N */
-    int         weight_format; /* 0 dense, 1 u4 */
+    int         weight_format; /* 0 dense T, 1 u4 (AWQ, g128), 2 fp8 e4m3 with 128x128 f32 block scales */
     int         dtype;         /* activation / scale type T */
-    int         group_size;    /* 128 for u4 */
+    int         group_size;    /* 128 (u4 quant group / fp8 scale block) */
     const void* prepared;      /* output of b200_linear_prepare */
     const void* bias;          /* [N] T or NULL */
 } b200_linear_desc;

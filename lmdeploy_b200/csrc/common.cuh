@@ -165,6 +165,7 @@ struct TypeOps<half> {
     static B200_DEVICE half sub(half a, half b) { return __hsub_rn(a, b); }
     static B200_DEVICE half fma(half a, half b, half c) { return __hfma(a, b, c); }
     static B200_DEVICE half neg(half a) { return __hneg(a); }
+    static B200_DEVICE half from_bits(uint16_t b) { return __ushort_as_half(b); }
     static B200_DEVICE uint32_t fma2(uint32_t a, uint32_t b, uint32_t c)
     {
         uint32_t d;
@@ -230,6 +231,7 @@ struct TypeOps<nv_bfloat16> {
     static B200_DEVICE nv_bfloat16 sub(nv_bfloat16 a, nv_bfloat16 b) { return __hsub_rn(a, b); }
     static B200_DEVICE nv_bfloat16 fma(nv_bfloat16 a, nv_bfloat16 b, nv_bfloat16 c) { return __hfma(a, b, c); }
     static B200_DEVICE nv_bfloat16 neg(nv_bfloat16 a) { return __hneg(a); }
+    static B200_DEVICE nv_bfloat16 from_bits(uint16_t b) { return __ushort_as_bfloat16(b); }
     static B200_DEVICE uint32_t fma2(uint32_t a, uint32_t b, uint32_t c)
     {
         uint32_t d;

@@ -60,6 +60,32 @@ __global__ void prepare_u4_kernel(uint8_t* dst, const uint32_t* qweight, const T
     }
 }
 
+// fp8 (e4m3 + 128x128 block scales, SURVEY 8a11 / linear_weight.cc:138-150): W u8 [K, N] (trans == 0) or [N, K]
+// (trans == 1), scale_inv f32 [K/128, N/128]  ->  per (nt, kg): data [k16:8][n:128][16 B], then the block scale cast to T
+template<class T>
+__global__ void prepare_fp8_kernel(uint8_t* dst, const uint8_t* w, const float* scale_inv, int K, int N, int trans)
+{
+    using Ops        = TypeOps<T>;
+    const int    kgs = K / kKG, nts = N / kBN;
+    const size_t nb  = (size_t)nts * kgs * kFp8BlockBytes;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nb; idx += (size_t)gridDim.x * blockDim.x) {
+        const int    within = (int)(idx % kFp8BlockBytes);
+        const size_t blk    = idx / kFp8BlockBytes;
+        const int    kg = (int)(blk % kgs), nt = (int)(blk / kgs);
+        uint8_t      out = 0;
+        if (within < kBN * kKG) {
+            const int j = within & 15, n = (within >> 4) & 127, k16 = within >> 11;
+            const int k = kg * kKG + k16 * 16 + j, ng = nt * kBN + n;
+            out         = trans ? w[(size_t)ng * K + k] : w[(size_t)k * N + ng];
+        }
+        else if (within < kBN * kKG + 2) {
+            const T s = Ops::from_f32(scale_inv[(size_t)kg * nts + nt]);
+            out       = reinterpret_cast<const uint8_t*>(&s)[within - kBN * kKG];
+        }
+        dst[idx] = out;
+    }
+}
+
 // dense: W [K, N] row-major (trans == 0) or [N, K] row-major (trans == 1) -> per (nt, kg): [k8:16][n:128][8] T
 template<class T>
 __global__ void prepare_dense_kernel(T* dst, const T* w, int K, int N, int trans)
@@ -112,7 +138,7 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     const int WB_pad = (WB + 1023) & ~1023;
     const int XB     = MT * 256;
     Plan      pl{};
-    pl.tiles         = (fmt == kU4 && N % (2 * kBN) == 0) ? 2 : 1;
+    pl.tiles         = (fmt != kDense && N % (2 * kBN) == 0) ? 2 : 1;
     const bool two_per_sm = false;  // 640-thread CTAs at ~90 registers: one CTA per SM in every configuration
     const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
     const int  slots = 148 * (two_per_sm ? 2 : 1);
@@ -241,8 +267,11 @@ static int validate_desc(const b200_linear_desc* d)
     if (d->weight_format == kU4 && d->group_size != 128) {
         return fail(B200_ERR_UNSUPPORTED, "u4 weights require group_size 128");
     }
-    if (d->weight_format != kU4 && d->weight_format != kDense) {
-        return fail(B200_ERR_UNSUPPORTED, "weight_format must be 0 (dense) or 1 (u4 awq)");
+    if (d->weight_format != kU4 && d->weight_format != kDense && d->weight_format != kFp8) {
+        return fail(B200_ERR_UNSUPPORTED, "weight_format must be 0 (dense), 1 (u4 awq) or 2 (fp8 e4m3, 128x128 block scales)");
+    }
+    if (d->weight_format == kFp8 && d->group_size != 128) {
+        return fail(B200_ERR_UNSUPPORTED, "fp8 weights require 128x128 scale blocks");
     }
     if (d->dtype != B200_DTYPE_F16 && d->dtype != B200_DTYPE_BF16) {
         return fail(B200_ERR_INVALID_ARG, "dtype must be 0 or 1");
@@ -256,7 +285,7 @@ extern "C" size_t b200_linear_prepared_bytes(const b200_linear_desc* d)
         return 0;
     }
     const size_t blocks = (size_t)(d->output_dim / kBN) * (d->input_dim / kKG);
-    return blocks * (d->weight_format == kU4 ? kU4BlockBytes : kDenseBlockBytes);
+    return blocks * (d->weight_format == kU4 ? kU4BlockBytes : (d->weight_format == kFp8 ? kFp8BlockBytes : kDenseBlockBytes));
 }
 
 extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight, const void* scales, const void* zeros,
@@ -282,6 +311,19 @@ extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight
             prepare_u4_kernel<nv_bfloat16><<<1024, 256, 0, st>>>((uint8_t*)prepared, (const uint32_t*)weight,
                                                                  (const nv_bfloat16*)scales,
                                                                  (const nv_bfloat16*)zeros, K, N);
+        }
+    }
+    else if (d->weight_format == kFp8) {
+        if (!scales) {
+            return fail(B200_ERR_INVALID_ARG, "fp8 weights need the f32 block scales (weight_scale_inv)");
+        }
+        if (d->dtype == B200_DTYPE_F16) {
+            prepare_fp8_kernel<half><<<2048, 256, 0, st>>>((uint8_t*)prepared, (const uint8_t*)weight, (const float*)scales,
+                                                           K, N, weight_is_transposed);
+        }
+        else {
+            prepare_fp8_kernel<nv_bfloat16><<<2048, 256, 0, st>>>((uint8_t*)prepared, (const uint8_t*)weight,
+                                                                  (const float*)scales, K, N, weight_is_transposed);
         }
     }
     else {
@@ -345,6 +387,12 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
             return bf ? launch<nv_bfloat16, kU4, 2>(p, rg.smem, st) : launch<half, kU4, 2>(p, rg.smem, st);
         }
         return bf ? launch<nv_bfloat16, kU4, 1>(p, rg.smem, st) : launch<half, kU4, 1>(p, rg.smem, st);
+    }
+    if (d->weight_format == kFp8) {
+        if (rg.tiles == 2) {
+            return bf ? launch<nv_bfloat16, kFp8, 2>(p, rg.smem, st) : launch<half, kFp8, 2>(p, rg.smem, st);
+        }
+        return bf ? launch<nv_bfloat16, kFp8, 1>(p, rg.smem, st) : launch<half, kFp8, 1>(p, rg.smem, st);
     }
     return bf ? launch<nv_bfloat16, kDense, 1>(p, rg.smem, st) : launch<half, kDense, 1>(p, rg.smem, st);
 }

@@ -50,7 +50,7 @@ enum WeightFormat : int
 
 constexpr int kU4BlockBytes    = 8192 + 512;           // one (n-tile, k-group): data + fused params
 constexpr int kDenseBlockBytes = kBN * kKG * 2;        // 32 KB
-constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // data + block scale (T, padded to 16 B)
+constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // e4m3 data [k16:8][n:128][16 B] + block scale (T, padded to 16 B)
 
 // Development aid (tools/gemm_trace.cu compiles this TU with -DB200_GEMM_TRACE): per-role clock64 stamps of the
 // first kTraceCtas CTAs.  Absent from the product build.
@@ -119,6 +119,15 @@ struct Params {
 B200_DEVICE int w_block_bytes(int fmt)
 {
     return fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+}
+
+// two e4m3 bytes (low 16 bits of `x`) -> two floats (exact): cvt.rn.f16x2.e4m3x2 then f16 -> f32
+B200_DEVICE float2 cvt_e4m3x2_f32(uint32_t x)
+{
+    uint32_t h2;
+    asm("{\n\t.reg .b16 t;\n\tcvt.u16.u32 t, %1;\n\tcvt.rn.f16x2.e4m3x2 %0, t;\n\t}" : "=r"(h2) : "r"(x));
+    const half2 h = reinterpret_cast<const half2&>(h2);
+    return make_float2(__low2float(h), __high2float(h));
 }
 
 template<class T>
@@ -374,21 +383,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             const int      lane_base = 32 * (warp & 3);   // TMEM lanes this warp may touch
             const int      n_local   = lane_base + lane;
             const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
-            if constexpr (FMT == kU4) {
+            if constexpr (kDequant) {
                 const int a0 = my_tile * NAt;
                 int       sw = 0, sa = 0;
                 uint32_t  phw = 0, pha = 0;
                 // software pipeline: the packed weights of k-group i + 1 are fetched from shared memory while the
                 // tcgen05.st of k-group i is still in flight (one thread = one weight row x NKC 32-wide k-chunks)
-                uint32_t st2 = 0;
-                uint4    v[NKC];
-                auto     fetch = [&](int i, int slot, uint32_t phase) {
+                constexpr int UNITS = FMT == kU4 ? 1 : 2;  // 16-byte units per 32-wide k-chunk (u4: 32 nibbles; fp8: 2 x 16 B)
+                uint32_t      st2   = 0;                   // u4: (scale, -zero*scale) as T2;  fp8: block scale as T (low half)
+                uint4         v[NKC][UNITS];
+                auto          fetch = [&](int i, int slot, uint32_t phase) {
                     GEMM_WAIT(smem_u32(&bar_wfull[slot]), phase, 4, i);
                     if (warp == 2 && lane == 0) GEMM_TRACE(1, i);
                     const uint32_t wsm = w_ring + (uint32_t)slot * WSLOT + my_tile * WB_pad;
-                    st2                = lds32(wsm + 8192 + n_local * 4);
+                    if constexpr (FMT == kU4) {
+                        st2 = lds32(wsm + 8192 + n_local * 4);
 #pragma unroll
-                    for (int q = 0; q < NKC; ++q) v[q] = lds128(wsm + ((kc0 + q) * 128 + n_local) * 16);
+                        for (int q = 0; q < NKC; ++q) v[q][0] = lds128(wsm + ((kc0 + q) * 128 + n_local) * 16);
+                    }
+                    else {
+                        st2 = lds32(wsm + 16384);
+#pragma unroll
+                        for (int q = 0; q < NKC; ++q) {
+                            v[q][0] = lds128(wsm + ((2 * (kc0 + q)) * 128 + n_local) * 16);
+                            v[q][1] = lds128(wsm + ((2 * (kc0 + q) + 1) * 128 + n_local) * 16);
+                        }
+                    }
                 };
                 if (nk > 0) {
                     fetch(0, 0, 0);
@@ -401,12 +421,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 #pragma unroll
                     for (int q = 0; q < NKC; ++q) {
                         uint32_t r[16];
+                        if constexpr (FMT == kU4) {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            uint32_t h[4];
-                            Ops::cvt_u4x8((&v[q].x)[u], h);
+                            for (int u = 0; u < 4; ++u) {
+                                uint32_t h[4];
+                                Ops::cvt_u4x8((&v[q][0].x)[u], h);
 #pragma unroll
-                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                                for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                            }
+                        }
+                        else {
+                            // w = T(e4m3) *_T T(block scale): both factors are exact in fp32, so one fp32 multiply
+                            // rounded once to T is the T multiply of the reference (transform.h:92-97)
+                            const float sc = Ops::to_f32(Ops::from_bits((uint16_t)(st2 & 0xffffu)));
+#pragma unroll
+                            for (int u = 0; u < UNITS; ++u) {
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) {
+                                    const uint32_t w4 = (&v[q][u].x)[x];
+                                    const float2   lo = cvt_e4m3x2_f32(w4 & 0xffffu);
+                                    const float2   hi = cvt_e4m3x2_f32(w4 >> 16);
+                                    r[u * 8 + x * 2]     = Ops::pack2(lo.x * sc, lo.y * sc);
+                                    r[u * 8 + x * 2 + 1] = Ops::pack2(hi.x * sc, hi.y * sc);
+                                }
+                            }
                         }
                         umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + (kc0 + q) * 16, r);
                     }

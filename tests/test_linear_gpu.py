@@ -42,6 +42,11 @@ class DevLinear:
             ds, dz = to_dev_T(scales, dtype), to_dev_T(zeros, dtype)
             L.check(lib.b200_linear_prepare(C.byref(self.d), qw.data_ptr(), ds.data_ptr(), dz.data_ptr(), 0,
                                             self.prepared.data_ptr(), st), "prepare")
+        elif fmt == 2:
+            dw = torch.from_numpy(np.ascontiguousarray(weight)).cuda()           # e4m3 bits, uint8
+            ds = torch.from_numpy(np.ascontiguousarray(scales, np.float32)).cuda()
+            L.check(lib.b200_linear_prepare(C.byref(self.d), dw.data_ptr(), ds.data_ptr(), None, transposed,
+                                            self.prepared.data_ptr(), st), "prepare")
         else:
             dw = to_dev_T(weight, dtype)
             L.check(lib.b200_linear_prepare(C.byref(self.d), dw.data_ptr(), None, None, transposed,
@@ -151,3 +156,26 @@ def test_linearity_property_full_size(lib):
     cols = rng.choice(N, 64, replace=False)
     wd = OL.dequant_u4(q[:, cols], s[:, cols], z[:, cols], F16)
     _assert_close(y1[:, cols], OL.linear(x, wd, F16))
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("shape", [(1024, 256), (512, 384), (4096, 4096)])
+@pytest.mark.parametrize("m", [1, 64])
+def test_fp8_block_scaled(lib, shape, m, dtype):
+    """FP8 (e4m3, 128x128 f32 block scales) weight-only linear, the non-sm90 path of the reference:
+    w = T(e4m3) *_T T(scale_block) (transform.h:92-97, linear_weight.cc:138-150), T x T -> fp32 accumulate."""
+    K, N = shape
+    rng = np.random.default_rng(K + N + m)
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    # per-block scale = amax / 448 (the usual fp8 block quantiser), weights stored as e4m3 of w / scale
+    wb = w.reshape(K // 128, 128, N // 128, 128)
+    scale = (np.abs(wb).max(axis=(1, 3)) / 448.0).astype(np.float32)
+    w8 = OL.f32_to_e4m3(w / np.repeat(np.repeat(scale, 128, 0), 128, 1))
+    lin = DevLinear(lib, K, N, 2, dtype, w8, scales=scale)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), dtype)
+    got = lin.forward(x)
+    ref = OL.linear(x, OL.dequant_fp8(w8, scale, 128, dtype), dtype)
+    _assert_close(got, ref, atol=2e-4 if dtype == F16 else 2e-3, rtol=2e-3 if dtype == F16 else 1.6e-2)
+    # the transposed ([N, K]) loader layout must prepare to the same stream
+    lin_t = DevLinear(lib, K, N, 2, dtype, np.ascontiguousarray(w8.T), scales=scale, transposed=1)
+    assert (lin_t.prepared == lin.prepared).all()
