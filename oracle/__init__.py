@@ -9,15 +9,23 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline``
 CPU baseline.  Nothing under ``lmdeploy_b200/`` imports it; the product path
 fails loudly when the CUDA library is missing.
 
-Parity pinning: the reference stores NO golden vectors for this path
- -- its own tests compute expectations on the fly -- and the
-reference cannot be imported or run in this container (no built ``_turbomind``).
-The oracle is therefore pinned by (a) bit-level known-answer tests derived by
-hand from the reference's PTX-level definitions (tests/test_oracle_kat.py),
-(b) the reference's own acceptance gates re-stated as tests, and (c) the
-cross-check fixtures in tests/golden/ generated by oracle/gen_golden.py using
-the reference's pure-torch semantic twins where they exist.  Where a reference
-GPU build uses hardware approximations (ex2.approx, sin.approx, rcp.approx under
---use_fast_math) the oracle uses the correctly rounded operation; see DESIGN.md
-section "numerics contract".
+Parity pinning: PINNED against the reference itself.  The reference stores no golden
+vectors for this path and its build system cannot be configured
+offline, but its decode-attention translation units compile from their sources in place:
+oracle/ref_build/ builds them (unmodified, from /root/reference) into
+oracle/_ref/libtm_ref_attention.so, and
+  * tests/golden/ref_attention_*.npz are inputs/outputs of those reference kernels
+    recorded on a B200 by tools/make_golden.py; tests/test_golden_cpu.py checks this
+    numpy oracle against them on CPU (V bytes + params bit-identical; K bytes >= 97 %
+    identical and at most one quantisation step apart -- the GPU's ex2/sin/cos.approx
+    units, which the reference's --use_fast_math build uses for RoPE, cannot be
+    reproduced on a CPU, so the oracle uses the correctly rounded functions; attention
+    output within 2e-3);
+  * tests/test_ref_attention_gpu.py runs the CUDA kernels and the reference kernels on
+    the same device buffers (KV pages bit-identical, outputs within 2e-3).
+The GEMM / norm / TP restatements (oracle/linear.py) have no compiled reference to run
+(the reference's quantised GEMM kernels compile to empty bodies for sm_100a and need its
+tuner): they are pinned by the bit-level known-answer tests in tests/test_oracle_kat.py
+and the reference's own acceptance gates only -- "parity unpinned" against a reference
+build for those functions.
 """
