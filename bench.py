@@ -110,7 +110,7 @@ def run_reference(args):
     from oracle import cpu_baseline
     name, batch, ctx, qp = CONFIGS[args.config]
     spec = SPECS[name]
-    cores = os.cpu_count()
+    cores = cpu_baseline.usable_cores()
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=1, threads=cores)
     reps = max(1, min(args.steps, 3))
@@ -245,7 +245,7 @@ def run_b200(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline
-        r = cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=1, threads=os.cpu_count())
+        r = cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=1, threads=cpu_baseline.usable_cores())
         line["cpu_baseline"] = {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": r["threads"], "kind": "port",
                                 "sample": r["sample"]}
     if rank == 0:

@@ -99,11 +99,24 @@ class CpuLayer:
         return residual
 
 
+def usable_cores(cap=32):
+    """Host threads that can actually run: min(affinity mask, cgroup CPU quota), capped (torch-CPU ops of this size
+    stop scaling -- and collapse under oversubscription -- long before 128 threads)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, cap))
+
+
 def time_decode(spec, batch, ctx, kv_quant=True, layers_sample=1, reps=1, threads=None, seed=0):
     """Time `layers_sample` decoder layers + lm_head of `spec` at (batch, ctx) on the host cores.
     Returns dict(tokens_per_s (full-model extrapolation), t_layer, t_head, threads, sample)."""
-    import os
-    threads = threads or os.cpu_count()
+    threads = threads or usable_cores()
     torch.set_num_threads(threads)
     gen = torch.Generator().manual_seed(seed)
     D = 128
