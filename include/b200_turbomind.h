@@ -199,6 +199,14 @@ B200_API int b200_linear_forward(const b200_linear_desc* desc, const void* x, in
 B200_API int b200_linear_forward_packed(const b200_linear_desc* desc, const void* xp, int mt, int m, void* y, int64_t ldy,
                                int epilogue, int out_packed_mt, void* workspace, size_t workspace_bytes,
                                void* stream);
+/* GEMM with the residual add + RMSNorm of unified_decoder.cc:278-287 fused into its split-K epilogue:
+ *   residual[m, N] += x . W (+ bias)   (added in T);   out = T(float(residual) * inv_rms(row)) * norm_weight
+ * `out` is token-major [m, N] (out_packed_mt == 0) or the packed tile layout.  Returns B200_ERR_UNSUPPORTED when the
+ * launch plan of this shape has no K split (callers then run b200_linear_forward_packed + b200_residual_rmsnorm). */
+B200_API int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_desc* desc, const void* xp, int mt, int m,
+                                                void* residual, const void* norm_weight, float eps, void* out,
+                                                int out_packed_mt, void* workspace, size_t workspace_bytes,
+                                                void* stream);
 B200_API int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

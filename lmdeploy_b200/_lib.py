@@ -104,6 +104,9 @@ def load():
                                         C.c_int64, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200_linear_forward_packed.argtypes = [C.POINTER(LinearDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200_linear_forward_packed_residual_rmsnorm.argtypes = [
+        C.POINTER(LinearDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+        C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200_pack_activations.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
     lib.b200_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,

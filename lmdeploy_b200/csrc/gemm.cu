@@ -178,8 +178,10 @@ constexpr size_t kCounterBytes = 64 * 1024;  // 2 ints per n-group, N <= 1M
 
 struct LinearWs {
     int*   counters;
+    int*   norm_ctr;
     void*  xp;
     float* partials;
+    float* ssq;
     size_t total;
 };
 
@@ -200,8 +202,10 @@ static LinearWs carve_ws(void* base, int K, int N, int MT)
     // fixed-size counter block so that linears of different shapes can share one workspace: a counter slot never
     // aliases another linear's activation / partial region
     w.counters = (int*)take(kCounterBytes);
+    w.norm_ctr = w.counters ? w.counters + kCounterBytes / 8 : nullptr;  // second half of the counter block
     w.xp       = take((size_t)K * MT * 2);
     w.partials = (float*)take((size_t)N * kMaxSplits * MT * 4);  // up to kMaxSplits K-splits of an [MT][N] fp32 tile
+    w.ssq      = (float*)take((size_t)(N / kBN) * 128 * 4);      // fused RMSNorm: per n-group partial sums of squares
     w.total    = off;
     return w;
 }
@@ -261,7 +265,7 @@ static int validate_desc(const b200_linear_desc* d)
     if (d->input_dim <= 0 || d->input_dim % kKG) {
         return fail(B200_ERR_UNSUPPORTED, "input_dim must be a multiple of 128");
     }
-    if (d->output_dim <= 0 || d->output_dim % kBN || (size_t)(d->output_dim / kBN) * 8 > kCounterBytes) {
+    if (d->output_dim <= 0 || d->output_dim % kBN || (size_t)(d->output_dim / kBN) * 8 > kCounterBytes / 2) {
         return fail(B200_ERR_UNSUPPORTED, "output_dim must be a multiple of 128 (and <= 1M)");
     }
     if (d->weight_format == kU4 && d->group_size != 128) {
@@ -354,13 +358,22 @@ extern "C" int b200_pack_activations(const void* x, int64_t ldx, int m, int k, i
     return check_launch("pack_x_kernel");
 }
 
+struct NormFusion {
+    void*       residual;
+    const void* weight;
+    float       eps;
+    float*      ssq;
+    int*        ctr;
+};
+
 static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int m, void* y, int64_t ldy, int epilogue,
-                          int out_mode, int out_mt, float* partials, int* counters, cudaStream_t st)
+                          int out_mode, int out_mt, float* partials, int* counters, cudaStream_t st,
+                          const NormFusion* nf = nullptr)
 {
     if (mt < 16 || mt > 128 || mt % 16) {
         return fail(B200_ERR_UNSUPPORTED, "padded token count must be a multiple of 16 in [16, 128]");
     }
-    if (epilogue != 0 && epilogue != 1) {
+    if (epilogue != 0 && epilogue != 1 && !(epilogue == 2 && nf)) {
         return fail(B200_ERR_INVALID_ARG, "epilogue must be 0 (none) or 1 (gated SiLU)");
     }
     Params p{};
@@ -377,6 +390,15 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     const Plan rg = make_plan(d->weight_format, mt, p.N, p.K);
     p.splits = rg.splits, p.nw = rg.nw, p.nx = rg.nx, p.na = rg.na;
     p.tmem_cols = rg.tmem_cols, p.a_col = rg.a_col;
+    if (epilogue == 2) {
+        // the fused residual + RMSNorm epilogue lives in the split-K exchange: it needs splits > 1 and a bounded number
+        // of (token, column) items per thread; callers fall back to the separate kernel otherwise
+        const int ntok_max = (mt + rg.splits - 1) / rg.splits;
+        if (rg.splits == 1 || ntok_max * (kBN * rg.tiles / 2) > kNormMaxItems * kDqWarps * 32 || ntok_max > 32) {
+            return fail(B200_ERR_UNSUPPORTED, "fused residual+RMSNorm epilogue not available for this shape");
+        }
+        p.residual = nf->residual, p.norm_w = nf->weight, p.norm_eps = nf->eps, p.ssq = nf->ssq, p.norm_ctr = nf->ctr;
+    }
     p.epilogue = epilogue;
     p.out_mode = out_mode;
     p.ldy      = (int)ldy;
@@ -437,4 +459,24 @@ extern "C" int b200_linear_forward_packed(const b200_linear_desc* d, const void*
     }
     return forward_packed(d, xp, mt, m, y, ldy, epilogue, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
                           w.counters, (cudaStream_t)stream);
+}
+
+extern "C" int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_desc* d, const void* xp, int mt, int m,
+                                                           void* residual, const void* norm_weight, float eps, void* out,
+                                                           int out_packed_mt, void* workspace, size_t workspace_bytes,
+                                                           void* stream)
+{
+    if (int e = validate_desc(d)) {
+        return e;
+    }
+    if (!d->prepared || !xp || !residual || !norm_weight || !out) {
+        return fail(B200_ERR_INVALID_ARG, "prepared / xp / residual / norm_weight / out is NULL");
+    }
+    LinearWs w = carve_ws(workspace, d->input_dim, d->output_dim, mt);
+    if (!workspace || workspace_bytes < w.total) {
+        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_linear_workspace_bytes)");
+    }
+    NormFusion nf{residual, norm_weight, eps, w.ssq, w.norm_ctr};
+    return forward_packed(d, xp, mt, m, out, d->output_dim, 2, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
+                          w.counters, (cudaStream_t)stream, &nf);
 }

@@ -30,6 +30,7 @@ namespace gemm {
 
 constexpr int kBN        = 128;  // output features per CTA (UMMA M)
 constexpr int kKG        = 128;  // K per pipeline stage (= quant group size)
+constexpr int kNormMaxItems = 4;  // fused residual+RMSNorm epilogue: (token, column-pair) items per thread
 constexpr int kMaxW     = 8;    // W ring slots (barrier arrays)
 constexpr int kMaxX     = 6;    // X ring slots
 constexpr int kASlots   = 4;    // max TMEM A-operand ring slots (64 columns each); Params::na in use
@@ -108,7 +109,13 @@ struct Params {
     int            splits;  // K splits along grid.y (1 .. 16); > 1 needs a cooperative launch (co-residency)
     int            nw, nx;  // W / X ring depths
     int            na;      // TMEM A-ring slots (multiple of TILES)
-    int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs)
+    int            epilogue;  // 0 none, 1 gated SiLU (columns interleaved gate/up -> N/2 outputs),
+                              // 2 residual add + RMSNorm of the full row (splits > 1 only; see epilogue part 2)
+    void*          residual;  // epilogue 2: [M][N] T, updated in place (r += y)
+    const void*    norm_w;    // epilogue 2: [N] T
+    float          norm_eps;
+    float*         ssq;       // epilogue 2: [n-group][MT] partial sums of squares (L2 exchange)
+    int*           norm_ctr;  // epilogue 2: [splits][2] arrive / done counters of the n-groups owning the same tokens
     int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
     int            ldy;
     int            out_mt;
@@ -526,15 +533,118 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         const int    t_lo = p.MT * sp / p.splits, t_hi = p.MT * (sp + 1) / p.splits;
         const int    tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
         const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
-        for (int idx = tid; idx < (t_hi - t_lo) * (ROWS / 2); idx += kDqWarps * 32) {
-            const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
-            float2    acc = make_float2(0.f, 0.f);
-            for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
-                const float2 v = __ldcg(reinterpret_cast<const float2*>(base + (size_t)r * p.MT * ROWS + tl * ROWS) + np);
-                acc.x += v.x;
-                acc.y += v.y;
+        if (p.epilogue != 2) {
+            for (int idx = tid; idx < (t_hi - t_lo) * (ROWS / 2); idx += kDqWarps * 32) {
+                const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+                float2    acc = make_float2(0.f, 0.f);
+                for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
+                    const float2 v =
+                        __ldcg(reinterpret_cast<const float2*>(base + (size_t)r * p.MT * ROWS + tl * ROWS) + np);
+                    acc.x += v.x;
+                    acc.y += v.y;
+                }
+                finalize_pair<T>(p, t_lo + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
             }
-            finalize_pair<T>(p, t_lo + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
+        }
+        else {
+            // ---- fused residual add + RMSNorm (replaces invokeBiasResidualRMSNorm, rms_norm.cu:287-363) ----
+            // This CTA owns tokens [t_lo, t_hi) x ROWS columns; the row's sum of squares is completed through a
+            // tiny L2 exchange with the other n-groups that own the same tokens (all co-resident).
+            constexpr int kMaxItems = kNormMaxItems;  // host guarantees ntok * ROWS / 2 <= kMaxItems * 512
+            constexpr int WPT       = ROWS / 64;      // warps per token (ROWS / 2 pairs, 32 per warp)
+            __shared__ float s_ss[32][WPT];
+            __shared__ float s_inv[32];
+            const int ntok = t_hi - t_lo;
+            const int wq   = ((threadIdx.x - 64) >> 5) % WPT;  // warp slot within a token
+            float2    rr[kMaxItems];
+            T*        res = reinterpret_cast<T*>(p.residual);
+#pragma unroll
+            for (int k = 0; k < kMaxItems; ++k) {
+                const int idx = tid + k * (kDqWarps * 32);
+                rr[k]         = make_float2(0.f, 0.f);
+                if (idx < ntok * (ROWS / 2)) {
+                    const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+                    const int tok = t_lo + tl, n_g = nt0 * kBN + 2 * np;
+                    float2    acc = make_float2(0.f, 0.f);
+                    for (int r = 0; r < p.splits; ++r) {
+                        const float2 v =
+                            __ldcg(reinterpret_cast<const float2*>(base + (size_t)r * p.MT * ROWS + tl * ROWS) + np);
+                        acc.x += v.x;
+                        acc.y += v.y;
+                    }
+                    if (p.bias) {
+                        acc.x += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g]);
+                        acc.y += Ops::to_f32(reinterpret_cast<const T*>(p.bias)[n_g + 1]);
+                    }
+                    float ss = 0.f;
+                    if (tok < p.M) {
+                        T h0 = Ops::from_f32(acc.x), h1 = Ops::from_f32(acc.y);  // the GEMM output, rounded to T
+                        T* rp = res + (size_t)tok * p.N + n_g;
+                        T  r2[2];
+                        *reinterpret_cast<uint32_t*>(&r2[0]) = *reinterpret_cast<const uint32_t*>(rp);
+                        r2[0] = Ops::add(r2[0], h0);  // residual add in T (rms_norm.cu:317)
+                        r2[1] = Ops::add(r2[1], h1);
+                        *reinterpret_cast<uint32_t*>(rp) = *reinterpret_cast<const uint32_t*>(&r2[0]);
+                        rr[k] = make_float2(Ops::to_f32(r2[0]), Ops::to_f32(r2[1]));
+                        ss    = fmaf(rr[k].x, rr[k].x, rr[k].y * rr[k].y);
+                    }
+#pragma unroll
+                    for (int m = 16; m >= 1; m >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, m);
+                    if (lane == 0) {
+                        s_ss[tl][wq] = ss;  // the 32 idx of a warp belong to one token (ROWS / 2 is a multiple of 32)
+                    }
+                }
+            }
+            named_bar_sync(2, kDqWarps * 32);
+            if (tid < ntok) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < WPT; ++w) t += s_ss[tid][w];
+                __stcg(p.ssq + (size_t)blockIdx.x * p.MT + t_lo + tid, t);
+            }
+            __threadfence();
+            named_bar_sync(2, kDqWarps * 32);
+            int* nctr = p.norm_ctr + 2 * sp;
+            if (threadIdx.x == 64) {
+                atomicAdd(nctr, 1);
+                while (ld_acquire_gpu(nctr) < (int)gridDim.x) {
+                }
+            }
+            named_bar_sync(2, kDqWarps * 32);
+            if (tid < ntok) {
+                float t = 0.f;
+                for (int g = 0; g < (int)gridDim.x; ++g) t += __ldcg(p.ssq + (size_t)g * p.MT + t_lo + tid);  // fixed order
+                s_inv[tid] = rsqrtf(t / (float)p.N + p.norm_eps);
+            }
+            named_bar_sync(2, kDqWarps * 32);
+            const T* nw = reinterpret_cast<const T*>(p.norm_w);
+            T*       y  = reinterpret_cast<T*>(p.y);
+#pragma unroll
+            for (int k = 0; k < kMaxItems; ++k) {
+                const int idx = tid + k * (kDqWarps * 32);
+                if (idx < ntok * (ROWS / 2)) {
+                    const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+                    const int tok = t_lo + tl, n_g = nt0 * kBN + 2 * np;
+                    if (tok < p.M) {
+                        const float inv = s_inv[tl];
+                        T           w2[2], o2[2];
+                        *reinterpret_cast<uint32_t*>(&w2[0]) = *reinterpret_cast<const uint32_t*>(nw + n_g);
+                        o2[0] = Ops::mul(Ops::from_f32(rr[k].x * inv), w2[0]);  // T(float(r) * inv_rms) * w
+                        o2[1] = Ops::mul(Ops::from_f32(rr[k].y * inv), w2[1]);
+                        T* d = p.out_mode == 0 ? y + (size_t)tok * p.ldy + n_g :
+                                                 y + ((size_t)(n_g >> 3) * p.out_mt + tok) * 8 + (n_g & 7);
+                        *reinterpret_cast<uint32_t*>(d) = *reinterpret_cast<const uint32_t*>(&o2[0]);
+                    }
+                }
+            }
+            named_bar_sync(2, kDqWarps * 32);
+            if (threadIdx.x == 64) {
+                if (atomicAdd(nctr + 1, 1) == (int)gridDim.x - 1) {
+                    nctr[1] = 0;
+                    __threadfence();
+                    nctr[0] = 0;
+                }
+            }
         }
         named_bar_sync(2, kDqWarps * 32);
         if (threadIdx.x == 64) {

@@ -50,6 +50,8 @@ struct b200_model {
     // B200_STEP_TRACE=1: CUDA-event time per operator of every (un-captured) step, printed to stderr -- the analogue of
     // the reference's NVTX ranges around the same calls (utils/nvtx_utils.h:37-50)
     bool trace_on{};
+    bool fuse_norm{false};  // B200_FUSED_NORM=1: residual+RMSNorm inside the wo / w2 GEMM epilogue (measured: no faster
+                            // than the PDL-overlapped separate kernel -- 4.275 vs 4.260 ms/step -- so off by default)
     std::vector<std::tuple<int, cudaEvent_t, cudaEvent_t>> trace;
 };
 
@@ -82,6 +84,7 @@ extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
     }
     auto* m   = new b200_model();
     m->trace_on = getenv("B200_STEP_TRACE") != nullptr;
+    m->fuse_norm = getenv("B200_FUSED_NORM") != nullptr;
     m->cfg    = *c;
     m->layers.resize(c->num_layers);
     m->mt_cap = round16(c->max_batch);
@@ -320,28 +323,57 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
         a.workspace = m->attn_ws, a.workspace_bytes = m->attn_ws_bytes;
         a.plan = m->plan, a.rope_table = m->rope_table, a.out_packed_mt = MT, a.stream = stream;
         TRY_T(2, b200_decode_attention(&a));
-        TRY_T(3, b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
-        // AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287)
-        if (m->comm) {
-            TRY_T(4, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
-                                                     c.hidden, c.norm_eps, c.dtype, stream));
+        // wo GEMM + AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287).  Single GPU: the residual add and the
+        // RMSNorm are fused into the GEMM's split-K epilogue when the launch plan has one.
+        bool fused1 = false;
+        if (!m->comm && m->fuse_norm) {
+            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.wo, m->attn_xp, MT, B, m->residual, W.ffn_norm,
+                                                                       c.norm_eps, m->xp, MT, m->lin_ws, m->lin_ws_bytes,
+                                                                       stream);
+            if (rc == 0) {
+                fused1 = true;
+            }
+            else if (rc != B200_ERR_UNSUPPORTED) {
+                return rc;
+            }
         }
-        else {
-            TRY_T(4, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
-                                      c.dtype, stream));
+        if (!fused1) {
+            TRY_T(3, b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+            if (m->comm) {
+                TRY_T(4, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
+                                                              c.hidden, c.norm_eps, c.dtype, stream));
+            }
+            else {
+                TRY_T(4, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
+                                               c.dtype, stream));
+            }
         }
         // ---- FFN block ----
         TRY_T(5, b200_linear_forward_packed(&W.w13, m->xp, MT, B, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
                                        stream));
-        TRY_T(6, b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf2, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         const void* next_norm = (l + 1 < L) ? m->layers[l + 1].attn_norm : m->final_norm;
-        if (m->comm) {
-            TRY_T(7, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B,
-                                                     c.hidden, c.norm_eps, c.dtype, stream));
+        bool        fused2    = false;
+        if (!m->comm && m->fuse_norm) {
+            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.w2, m->act_xp, MT, B, m->residual, next_norm,
+                                                                       c.norm_eps, m->xp, MT, m->lin_ws, m->lin_ws_bytes,
+                                                                       stream);
+            if (rc == 0) {
+                fused2 = true;
+            }
+            else if (rc != B200_ERR_UNSUPPORTED) {
+                return rc;
+            }
         }
-        else {
-            TRY_T(7, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
-                                      stream));
+        if (!fused2) {
+            TRY_T(6, b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf2, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+            if (m->comm) {
+                TRY_T(7, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B,
+                                                              c.hidden, c.norm_eps, c.dtype, stream));
+            }
+            else {
+                TRY_T(7, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
+                                               stream));
+            }
         }
     }
     // PostEmbedding (language_model.cc:285-335) + greedy sampling

@@ -179,3 +179,46 @@ def test_fp8_block_scaled(lib, shape, m, dtype):
     # the transposed ([N, K]) loader layout must prepare to the same stream
     lin_t = DevLinear(lib, K, N, 2, dtype, np.ascontiguousarray(w8.T), scales=scale, transposed=1)
     assert (lin_t.prepared == lin.prepared).all()
+
+
+@pytest.mark.parametrize("m", [64, 17])
+@pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (2048, 4096)])
+def test_fused_residual_rmsnorm_epilogue(lib, shape, m):
+    """wo / w2 GEMM with the residual add + RMSNorm fused into the split-K epilogue
+    (b200_linear_forward_packed_residual_rmsnorm) vs linear -> residual_rmsnorm of the oracle."""
+    import torch
+    from lmdeploy_b200 import _lib as L
+    K, N = shape
+    rng = np.random.default_rng(K + m)
+    q, s, z = _mk_u4(rng, K, N)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), F16)
+    residual = rn(rng.standard_normal((m, N)).astype(np.float32), F16)
+    nw = rn((1 + 0.1 * rng.standard_normal(N)).astype(np.float32), F16)
+    mt = (m + 15) // 16 * 16
+    dx = to_dev_T(x, F16)
+    xp = torch.zeros(K // 8, mt, 8, dtype=torch.float16, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    L.check(lib.b200_pack_activations(dx.data_ptr(), K, m, K, mt, 0, xp.data_ptr(), st), "pack")
+    d_res = to_dev_T(residual, F16)
+    d_nw = to_dev_T(nw, F16)
+    out = torch.zeros(m, N, dtype=torch.float16, device="cuda")
+    rc = lib.b200_linear_forward_packed_residual_rmsnorm(C.byref(lin.d), xp.data_ptr(), mt, m, d_res.data_ptr(),
+                                                         d_nw.data_ptr(), C.c_float(1e-5), out.data_ptr(), 0,
+                                                         lin.ws.data_ptr(), lin.ws.numel(), st)
+    L.check(rc, "b200_linear_forward_packed_residual_rmsnorm")
+    torch.cuda.synchronize()
+    y = OL.linear(x, OL.dequant_u4(q, s, z, F16), F16)
+    ref_out, ref_res = OL.residual_rmsnorm(y, residual, nw, 1e-5, F16)
+    got_res, got_out = from_dev_T(d_res, F16), from_dev_T(out, F16)
+    # the GEMM output may differ from the oracle by one fp16 ulp (fp32 summation order), which moves the residual by
+    # at most one ulp of its own magnitude
+    _assert_close(got_res, ref_res, atol=2e-3, rtol=2e-3)
+    _assert_close(got_out, ref_out, atol=4e-3, rtol=4e-3)
+    # second call on the same workspace (self-resetting counters)
+    d_res2 = to_dev_T(residual, F16)
+    L.check(lib.b200_linear_forward_packed_residual_rmsnorm(C.byref(lin.d), xp.data_ptr(), mt, m, d_res2.data_ptr(),
+                                                            d_nw.data_ptr(), C.c_float(1e-5), out.data_ptr(), 0,
+                                                            lin.ws.data_ptr(), lin.ws.numel(), st), "second call")
+    torch.cuda.synchronize()
+    assert (from_dev_T(d_res2, F16) == got_res).all() and (from_dev_T(out, F16) == got_out).all()
