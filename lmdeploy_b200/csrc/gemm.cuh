@@ -7,15 +7,18 @@
 //     Y^T[N_out, tokens] = W^T[N_out, K] . X^T[K, tokens]
 // so the streamed operand (weights) sits on the UMMA M side (128 output features per CTA) and the tiny
 // activation tile is UMMA N (16..128 tokens).  Per 128-wide K group (= one AWQ quant group):
-//   * warp 0 streams the packed weights (one contiguous 8.5 KB 1-D TMA bulk copy per group: u4 data + fused
-//     (scale, -zero*scale) pairs) into a deep W ring; warp 10 streams the activation tiles (already in the
-//     UMMA K-major "interleaved" layout in global memory, L2 resident) into a separate X ring.  The rings are
-//     decoupled because their lifetimes differ: a W slot is free as soon as it has been de-quantised (long
-//     before its MMAs retire) and it is the DRAM-latency-bound stream, so it gets the depth;
-//   * 8 dequant warps unpack u4 -> f16 with lop3 and apply w = fma(q, s, t) in f16 (bit-identical to the
-//     reference's transform, transform.h:48-74 / cast.cu:155) and write the A operand straight into
-//     TENSOR MEMORY with tcgen05.st (3-slot ring; no shared-memory round trip for the dequantised weights);
-//   * warp 1 issues tcgen05.mma (A from TMEM, B from smem) from a warp-uniform loop, fp32 accumulators in TMEM;
+//   * warp 0 streams the packed weights (one contiguous 8.5 KB 1-D TMA bulk copy per (n-tile, group): u4 data +
+//     fused (scale, -zero*scale) pairs; fp8: 16 KB e4m3 + block scale) into a deep W ring; warp 18 streams the
+//     activation tiles (already in the UMMA K-major "interleaved" layout in global memory, L2 resident) into a
+//     separate X ring.  The rings are decoupled because their lifetimes differ: a W slot is free as soon as it has
+//     been de-quantised (long before its MMAs retire) and it is the DRAM-latency-bound stream, so it gets the depth.
+//     A CTA normally owns TWO n-tiles (256 output features) that share every activation tile;
+//   * 16 dequant warps (one group of 8 per n-tile) unpack u4 -> f16 with lop3 and apply w = fma(q, s, t) in f16
+//     (bit-identical to the reference's transform, transform.h:48-74 / cast.cu:155; fp8: T(e4m3) *_T T(scale)) and
+//     write the A operand straight into TENSOR MEMORY with tcgen05.st (ring of 64-column slots; no shared-memory
+//     round trip for the dequantised weights); the loop is software-pipelined (next group's LDS under this group's st);
+//   * warps 1 and 19 (one per n-tile) issue tcgen05.mma (A from TMEM, B from smem) from a warp-uniform loop -- one
+//     elected lane, descriptors in uniform registers -- fp32 accumulators in TMEM;
 //   * K is split over grid.y (co-resident CTAs, cooperative launch); the partial accumulators are reduce-scattered
 //     by token through an L2-resident fp32 exchange buffer and summed in rank order (deterministic), then bias /
 //     gated-SiLU and the fp16/bf16 store, all inside the same kernel.  (A thread-block-cluster + DSMEM exchange
@@ -39,8 +42,8 @@ constexpr int kXWarp    = 2 + kDqWarps;
 constexpr int kMmaWarp2 = kXWarp + 1;  // second MMA issuer (tile 1 of a two-tile CTA)
 constexpr int kThreads  = 32 * (kMmaWarp2 + 1);  // warp0 W-TMA, warp1 MMA/TMEM, warps2-17 dequant (+ epilogue), warp18 X-TMA,
                                                  // warp19 MMA of tile 1
-// TMEM budget: D accumulators occupy columns [0, MT); the dequantised A operand ring starts at column a_col.
-// MT <= 64: 64 + 3 x 64 = 256 columns, so two CTAs can be resident per SM.
+// TMEM budget (one CTA per SM): D accumulators of tile t at column t * d_stride (64 or 128 columns each), then the
+// A-operand ring of Params::na 64-column slots starting at column a_col (gemm.cu: make_plan).
 
 enum WeightFormat : int
 {

@@ -1,4 +1,4 @@
-// Standalone probe: validates the UMMA descriptor / TMEM layout assumptions used by gemm_w4.cu on a real
+// Standalone probe: validates the UMMA descriptor / TMEM layout assumptions used by lmdeploy_b200/csrc/gemm.cuh on a real
 // sm_100a device.  Build: nvcc -std=c++17 -gencode arch=compute_100a,code=sm_100a -o build/umma_probe tools/umma_probe.cu
 // Prints one line per variant: max |D - expected|.  (Development tool; not part of the product path.)
 #include "../lmdeploy_b200/csrc/umma.cuh"
