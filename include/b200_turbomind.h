@@ -207,6 +207,9 @@ B200_API int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_desc*
                                                 void* residual, const void* norm_weight, float eps, void* out,
                                                 int out_packed_mt, void* workspace, size_t workspace_bytes,
                                                 void* stream);
+/* launch plan of a shape (host only; no device work): out8 = {n-tiles per CTA, K splits, W ring, X ring, TMEM A slots,
+ * TMEM columns, first A column, dynamic shared memory bytes}.  A pure function of (format, K, N, padded m). */
+B200_API int b200_linear_plan(const b200_linear_desc* desc, int m, int* out8);
 B200_API int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -107,6 +107,8 @@ def load():
     lib.b200_linear_forward_packed_residual_rmsnorm.argtypes = [
         C.POINTER(LinearDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
         C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.b200_linear_plan.argtypes = [C.POINTER(LinearDesc), C.c_int, C.POINTER(C.c_int)]
+    lib.b200_linear_plan.restype = C.c_int
     lib.b200_pack_activations.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
     lib.b200_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,

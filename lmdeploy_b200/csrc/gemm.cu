@@ -480,3 +480,19 @@ extern "C" int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_des
     return forward_packed(d, xp, mt, m, out, d->output_dim, 2, out_packed_mt > 0 ? 1 : 0, out_packed_mt, w.partials,
                           w.counters, (cudaStream_t)stream, &nf);
 }
+
+// Host-only introspection of the launch plan (tests/test_linear_plan_cpu.py checks its invariants without a GPU).
+extern "C" int b200_linear_plan(const b200_linear_desc* d, int m, int* out8)
+{
+    if (int e = validate_desc(d)) {
+        return e;
+    }
+    if (!out8 || m <= 0 || m > 128) {
+        return fail(B200_ERR_INVALID_ARG, "linear_plan: bad arguments");
+    }
+    const int  mt = std::max(16, (m + 15) / 16 * 16);
+    const Plan pl = make_plan(d->weight_format, mt, d->output_dim, d->input_dim);
+    out8[0] = pl.tiles, out8[1] = pl.splits, out8[2] = pl.nw, out8[3] = pl.nx, out8[4] = pl.na;
+    out8[5] = pl.tmem_cols, out8[6] = pl.a_col, out8[7] = pl.smem;
+    return 0;
+}

@@ -1,0 +1,70 @@
+"""Host logic of the GEMM launcher (no GPU): the launch plan b200_linear_plan returns must respect the hardware
+budgets the kernel relies on, for every shape of the hot path and for a random sweep."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from lmdeploy_b200 import _lib as L
+
+SMS, SMEM_MAX, TMEM_COLS = 148, 227 * 1024 - 2048, 512
+W_BLOCK = {0: 32768, 1: 8704, 2: 16400}      # bytes of one (n-tile, k-group) of prepared weights per format
+
+
+def _plan(lib, K, N, fmt, m):
+    d = L.LinearDesc(K, N, fmt, 0, 128, None, None)
+    out = (C.c_int * 8)()
+    rc = lib.b200_linear_plan(C.byref(d), m, out)
+    assert rc == 0, lib.b200_last_error()
+    return dict(zip(("tiles", "splits", "nw", "nx", "na", "tmem_cols", "a_col", "smem"), list(out)))
+
+
+def _check(p, K, N, fmt, m):
+    mt = max(16, (m + 15) // 16 * 16)
+    kgs, rows = K // 128, 128 * p["tiles"]
+    assert p["tiles"] in (1, 2) and N % rows == 0
+    assert fmt != 0 or p["tiles"] == 1                          # dense: one tile (static_assert in the kernel)
+    ctas = N // rows * p["splits"]
+    assert p["splits"] in (1, 2, 4, 8)
+    if p["splits"] > 1:
+        assert ctas <= SMS, "split-K CTAs wait for each other: they must be co-resident (one CTA per SM)"
+        assert kgs // p["splits"] >= 4
+    wslot = ((W_BLOCK[fmt] + 1023) & ~1023) * p["tiles"]
+    assert p["smem"] == p["nw"] * wslot + p["nx"] * mt * 256 <= SMEM_MAX
+    assert 3 <= p["nw"] <= 8 and 2 <= p["nx"] <= 6
+    d_cols = (64 if mt <= 64 else 128) * p["tiles"]
+    if fmt == 0:
+        assert p["tmem_cols"] >= mt and p["tmem_cols"] in (32, 64, 128)
+    else:
+        assert p["a_col"] >= d_cols and p["a_col"] + 64 * p["na"] <= p["tmem_cols"] <= TMEM_COLS
+        assert p["na"] % p["tiles"] == 0 and p["na"] // p["tiles"] >= 1
+
+
+HOT_PATH = [  # (K, N, fmt) of the BASELINE.json configs, TP 1..8
+    (4096, 6144, 1), (4096, 4096, 1), (4096, 28672, 1), (14336, 4096, 1), (4096, 92544, 0),      # InternLM2-7B
+    (2048, 3072, 1), (2048, 4096, 1), (4096, 14336, 1), (7168, 4096, 1),                          # ... TP2
+    (4096, 768, 1), (512, 4096, 1), (4096, 3584, 1), (1792, 4096, 1), (4096, 11648, 0),          # ... TP8
+    (6144, 8192, 1), (6144, 6144, 1), (6144, 32768, 1), (16384, 6144, 1),                         # InternLM2-20B
+    (4096, 6144, 0), (4096, 4096, 0), (4096, 28672, 0), (14336, 4096, 0), (4096, 128256, 0),     # Llama-3-8B fp16
+    (8192, 1280, 2), (1024, 8192, 2), (8192, 7168, 2), (3584, 8192, 2),                           # Llama-3-70B fp8, TP8
+]
+
+
+@pytest.mark.parametrize("m", [1, 16, 64, 128])
+def test_plan_budgets_hot_path(lib, m):
+    for K, N, fmt in HOT_PATH:
+        _check(_plan(lib, K, N, fmt, m), K, N, fmt, m)
+
+
+def test_plan_budgets_random_sweep(lib):
+    rng = np.random.default_rng(0)
+    for _ in range(400):
+        K, N = 128 * int(rng.integers(1, 160)), 128 * int(rng.integers(1, 800))
+        fmt, m = int(rng.integers(0, 3)), int(rng.integers(1, 129))
+        _check(_plan(lib, K, N, fmt, m), K, N, fmt, m)
+
+
+def test_plan_is_a_pure_function(lib):
+    a = [_plan(lib, 14336, 4096, 1, 64) for _ in range(3)]
+    assert a[0] == a[1] == a[2] and a[0]["tiles"] == 2 and a[0]["splits"] == 8
+    assert _plan(lib, 4096, 28672, 1, 64)["splits"] == 1          # 112 two-tile CTAs already fill the wave
