@@ -84,8 +84,12 @@ class CpuLayer:
         k = qkv[:, Hq * D:(Hq + Hkv) * D].view(B, Hkv, D)
         q, k = rope_adjacent(q, hist, theta, D), rope_adjacent(k, hist, theta, D)
         # paged gather + dequant (TurboMind format x = q*scale + zero)
-        K = kv["kq"].index_select(2, kv["perm"]).to(torch.float32) * kv["ks"][..., None] + kv["kz"][..., None]
-        V = kv["vq"].index_select(2, kv["perm"]).to(torch.float32) * kv["vs"][..., None] + kv["vz"][..., None]
+        def gather(q, s, z):
+            p = kv["perm"]
+            return q.index_select(2, p).to(torch.float32) * s.index_select(2, p)[..., None] + z.index_select(2, p)[..., None]
+
+        K = gather(kv["kq"], kv["ks"], kv["kz"])
+        V = gather(kv["vq"], kv["vs"], kv["vz"])
         G = Hq // Hkv
         qg = q.view(B, Hkv, G, D)
         s = torch.einsum("bhgd,bhtd->bhgt", qg, K) / math.sqrt(D)
