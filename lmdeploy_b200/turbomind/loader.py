@@ -2,8 +2,9 @@
 
 Restates the loader transforms of the reference for the two architectures on the hot path
 (lmdeploy/turbomind/models/internlm2.py:32-135, models/llama.py:44-99):
-  * AWQ 'gemm' tensors are unpacked with the AWQ nibble order [0,4,1,5,2,6,3,7] and re-packed row-plain
-    (weight_format.py:47-74, 219-247); fp16 HF linears [N,K] are transposed to [K,N];
+  * every linear is read through checkpoint_formats.FormatResolver: AWQ 'gemm', GPTQ (sym, no act-order) and
+    compressed-tensors pack-quantized int4 all become uint4 [K,N] + scales/zeros [K/128,N] and are re-packed
+    row-plain (weight_format.py:47-74, 200-346); fp16 HF linears [N,K] are transposed to [K,N];
   * InternLM2 `wqkv` is de-interleaved from the per-kv-group layout [q0..q(g-1) k v] (internlm2.py:32-49);
   * q / k output channels are permuted from HF half-split RoPE to TurboMind's adjacent-pair RoPE
     (models/utils.py:306-324) -- for quantised weights the same column permutation is applied to qweight,
@@ -17,25 +18,16 @@ import os
 
 import torch
 
+from .checkpoint_formats import (AWQ_NIBBLE_OF_COLUMN, INT4_METHODS, FormatResolver, Lin, pack_u4_row,  # noqa: F401
+                                 parse_quantization_config, unpack_last)
 from .specs import ModelSpec
 
-AWQ_ORDER = [0, 4, 1, 5, 2, 6, 3, 7]
+_Lin = Lin
 
 
 def awq_unpack(x):
     """int32 [R, C/8] -> uint8 [R, C]   (_unpack_awq_gemm, weight_format.py:56-60)."""
-    shifts = torch.tensor([4 * n for n in AWQ_ORDER], dtype=torch.int32)
-    return ((x.unsqueeze(-1) >> shifts) & 0xF).reshape(x.shape[0], -1).to(torch.uint8)
-
-
-def pack_u4_row(q):
-    """uint8 [K, N] -> int32 [K, N/8], nibble i = column 8w+i   (weight_format.py:63-74)."""
-    g = q.reshape(q.shape[0], -1, 8).to(torch.int64)
-    w = torch.zeros(g.shape[:2], dtype=torch.int64)
-    for i in range(8):
-        w |= g[:, :, i] << (4 * i)
-    w = torch.where(w >= 2 ** 31, w - 2 ** 32, w)
-    return w.to(torch.int32)
+    return unpack_last(x, AWQ_NIBBLE_OF_COLUMN)
 
 
 def rope_perm(num_heads, head_dim, rope_dim=None):
@@ -46,45 +38,8 @@ def rope_perm(num_heads, head_dim, rope_dim=None):
     return torch.cat([rot, idx[:, rope_dim:]], dim=1).reshape(-1)
 
 
-class _Lin:
-    """A linear in TM orientation: q uint8 [K,N] + scales/zeros [K/g,N]  or  w [K,N]."""
-
-    def __init__(self, q=None, scales=None, zeros=None, w=None):
-        self.q, self.scales, self.zeros, self.w = q, scales, zeros, w
-
-    @property
-    def quant(self):
-        return self.q is not None
-
-    def cols(self, idx):
-        if self.quant:
-            return _Lin(self.q[:, idx], self.scales[:, idx], self.zeros[:, idx])
-        return _Lin(w=self.w[:, idx])
-
-    def rows(self, lo, hi, group=128):
-        if self.quant:
-            return _Lin(self.q[lo:hi], self.scales[lo // group:hi // group], self.zeros[lo // group:hi // group])
-        return _Lin(w=self.w[lo:hi])
-
-    @staticmethod
-    def cat(parts):
-        if parts[0].quant:
-            return _Lin(torch.cat([p.q for p in parts], 1), torch.cat([p.scales for p in parts], 1),
-                        torch.cat([p.zeros for p in parts], 1))
-        return _Lin(w=torch.cat([p.w for p in parts], 1))
-
-    def to_tm(self, device, dtype):
-        if self.quant:
-            return dict(weight=pack_u4_row(self.q.contiguous()).to(device), scales=self.scales.to(device, dtype).contiguous(),
-                        zeros=self.zeros.to(device, dtype).contiguous())
-        return dict(weight=self.w.to(device, dtype).contiguous())
-
-
-def _get_linear(tensors, prefix, awq):
-    if awq:
-        return _Lin(awq_unpack(tensors[prefix + ".qweight"]), tensors[prefix + ".scales"].to(torch.float32),
-                    awq_unpack(tensors[prefix + ".qzeros"]).to(torch.float32))
-    return _Lin(w=tensors[prefix + ".weight"].to(torch.float32).t().contiguous())
+def resolver_for(spec: ModelSpec):
+    return FormatResolver(None if spec.weight_format == "fp16" else (spec.checkpoint_format or spec.weight_format))
 
 
 def spec_from_config(cfg):
@@ -92,12 +47,12 @@ def spec_from_config(cfg):
     name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama"}.get(arch)
     if name is None:
         raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama)")
-    q = cfg.get("quantization_config") or {}
-    fmt = "fp16"
-    if q:
-        if q.get("quant_method") != "awq" or q.get("bits") != 4 or q.get("group_size") != 128:
-            raise NotImplementedError("only AWQ 4-bit group-128 checkpoints are supported")
-        fmt = "awq"
+    method, _group = parse_quantization_config(cfg.get("quantization_config"))
+    if method == "fp8":
+        raise NotImplementedError("fp8 checkpoints: the block-scaled fp8 GEMM exists (b200_linear_forward, "
+                                  "weight_format 2) but the decode-step driver does not run the un-fused "
+                                  "gate/up + activation layout it needs yet (DESIGN.md section 6b)")
+    fmt = "awq" if method in INT4_METHODS else "fp16"        # one on-GPU format for every int4 checkpoint family
     rs = cfg.get("rope_scaling") or {}
     rope_type = "llama3" if rs.get("rope_type", rs.get("type")) == "llama3" else "default"
     head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
@@ -107,35 +62,40 @@ def spec_from_config(cfg):
                      inter=cfg["intermediate_size"], vocab=cfg["vocab_size"],
                      rope_theta=float(cfg.get("rope_theta", 10000.0)), head_dim=head_dim,
                      norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope_type,
-                     rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt)
+                     rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt,
+                     checkpoint_format=method)
 
 
 def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
     """-> dict(w_qkv, wo, w1w3, w2 : _Lin ; attention_norm, ffn_norm : tensor) for TP rank `rank`."""
     D, Hq, Hkv = spec.head_dim, spec.heads, spec.kv_heads
-    awq = spec.weight_format == "awq"
+    rd = resolver_for(spec)
+
+    def _get_linear(prefix):
+        return rd.read(tensors, prefix)
+
     if spec.arch == "internlm2":
         p = f"model.layers.{i}."
-        wqkv = _get_linear(tensors, p + "attention.wqkv", awq)
+        wqkv = _get_linear(p + "attention.wqkv")
         g = Hq // Hkv
         idx = torch.arange(Hkv * (g + 2) * D).view(Hkv, g + 2, D)
         q = wqkv.cols(idx[:, :g].reshape(-1))
         k = wqkv.cols(idx[:, g].reshape(-1))
         v = wqkv.cols(idx[:, g + 1].reshape(-1))
-        wo = _get_linear(tensors, p + "attention.wo", awq)
-        w1 = _get_linear(tensors, p + "feed_forward.w1", awq)
-        w3 = _get_linear(tensors, p + "feed_forward.w3", awq)
-        w2 = _get_linear(tensors, p + "feed_forward.w2", awq)
+        wo = _get_linear(p + "attention.wo")
+        w1 = _get_linear(p + "feed_forward.w1")
+        w3 = _get_linear(p + "feed_forward.w3")
+        w2 = _get_linear(p + "feed_forward.w2")
         an, fn = tensors[p + "attention_norm.weight"], tensors[p + "ffn_norm.weight"]
     else:
         p = f"model.layers.{i}."
-        q = _get_linear(tensors, p + "self_attn.q_proj", awq)
-        k = _get_linear(tensors, p + "self_attn.k_proj", awq)
-        v = _get_linear(tensors, p + "self_attn.v_proj", awq)
-        wo = _get_linear(tensors, p + "self_attn.o_proj", awq)
-        w1 = _get_linear(tensors, p + "mlp.gate_proj", awq)
-        w3 = _get_linear(tensors, p + "mlp.up_proj", awq)
-        w2 = _get_linear(tensors, p + "mlp.down_proj", awq)
+        q = _get_linear(p + "self_attn.q_proj")
+        k = _get_linear(p + "self_attn.k_proj")
+        v = _get_linear(p + "self_attn.v_proj")
+        wo = _get_linear(p + "self_attn.o_proj")
+        w1 = _get_linear(p + "mlp.gate_proj")
+        w3 = _get_linear(p + "mlp.up_proj")
+        w2 = _get_linear(p + "mlp.down_proj")
         an, fn = tensors[p + "input_layernorm.weight"], tensors[p + "post_attention_layernorm.weight"]
     q = q.cols(rope_perm(Hq, D))
     k = k.cols(rope_perm(Hkv, D))

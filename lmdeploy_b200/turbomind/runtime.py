@@ -121,12 +121,12 @@ class DecodeModel:
             pass
 
     # ------------------------------------------------------------------ weights
-    @property
-    def _fmt(self):
-        return {"awq": 1, "fp16": 0}[self.spec.weight_format]
-
     def _set_linear(self, layer, which, K, N, weight, scales=None, zeros=None, transposed=False, fmt=None):
-        fmt = self._fmt if fmt is None else fmt
+        # per-linear format: a quantised checkpoint may keep individual linears dense (`modules_to_not_convert`)
+        if fmt is None:
+            fmt = L.FMT_U4 if scales is not None else L.FMT_DENSE
+        if fmt == L.FMT_U4 and (scales is None or zeros is None):
+            raise ValueError("a u4 linear needs scales and zero points")
         pl = PreparedLinear(self.lib, K, N, fmt, self.spec.dtype, self.device)
         pl.prepare(self.lib, weight, scales, zeros, transposed)
         L.check(self.lib.b200_model_set_linear(self.handle, layer, which, C.byref(pl.desc)), "set_linear")

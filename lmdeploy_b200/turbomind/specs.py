@@ -18,8 +18,9 @@ class ModelSpec:
     norm_eps: float = 1e-5
     rope_type: str = "default"      # 'default' | 'llama3'
     rope_factor: float = 0.0
-    weight_format: str = "awq"      # 'awq' (u4 g128) | 'fp16' | 'fp8'
+    weight_format: str = "awq"      # on-GPU weight format: 'awq' (u4 g128, any int4 checkpoint family) | 'fp16' | 'fp8'
     dtype: str = "f16"
+    checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
 
     def tiny(self, layers=2):
         return replace(self, layers=layers)

@@ -15,17 +15,51 @@ from lmdeploy_b200.turbomind import loader as LD
 H, L, HQ, HKV, I, V, D = 512, 2, 4, 2, 512, 256, 128
 
 
-def make_checkpoint(arch, awq, seed=0):
+def pack_plain_last(q):
+    """uint8 [R, C] -> int32 [R, C/8], nibble i = element 8w+i of the last axis."""
+    return OL.pack_u4_row(q)
+
+
+def quantize_symmetric_u4(w, group=128):
+    """GPTQ-sym / compressed-tensors style: zero point 8, q = clamp(rne(w/s) + 8, 0, 15)."""
+    K, N = w.shape
+    wg = w.reshape(K // group, group, N)
+    s = np.maximum(np.abs(wg).max(1), 1e-5) / np.float32(7)
+    s = rn(s.astype(np.float32), F16)
+    q = np.clip(np.rint(wg / s[:, None]) + 8, 0, 15).astype(np.uint8).reshape(K, N)
+    return q, s, np.full_like(s, 8)
+
+
+FAMILIES = (None, "awq", "gptq", "compressed-tensors")
+
+
+def make_checkpoint(arch, family, seed=0):
+    """family: None (fp16) | 'awq' | 'gptq' | 'compressed-tensors'; True/False are accepted for 'awq'/None."""
+    family = {True: "awq", False: None}.get(family, family)
     rng = np.random.default_rng(seed)
     t, deq = {}, {}
 
     def add(name, K, N):
         w = (rng.standard_normal((K, N)) * 0.3 / np.sqrt(K)).astype(np.float32)
-        if awq:
+        if family == "awq":
             q, s, z = OL.quantize_groupwise_u4(w, 128)
             t[name + ".qweight"] = torch.from_numpy(OL.awq_pack(q))
             t[name + ".qzeros"] = torch.from_numpy(OL.awq_pack(z.astype(np.uint8)))
             t[name + ".scales"] = torch.from_numpy(s.astype(np.float16))
+            deq[name] = OL.dequant_u4(q, s, z, F16)
+        elif family == "gptq":
+            q, s, z = quantize_symmetric_u4(w)
+            # qweight packs 8 consecutive K rows per word; qzeros packs (zero - 1) along N
+            t[name + ".qweight"] = torch.from_numpy(pack_plain_last(np.ascontiguousarray(q.T)).T.copy())
+            t[name + ".qzeros"] = torch.from_numpy(pack_plain_last((z - 1).astype(np.uint8)))
+            t[name + ".scales"] = torch.from_numpy(s.astype(np.float16))
+            t[name + ".g_idx"] = torch.arange(K, dtype=torch.int32) // 128
+            deq[name] = OL.dequant_u4(q, s, z, F16)
+        elif family == "compressed-tensors":
+            q, s, z = quantize_symmetric_u4(w)
+            t[name + ".weight_packed"] = torch.from_numpy(pack_plain_last(np.ascontiguousarray(q.T)))   # [N, K/8]
+            t[name + ".weight_scale"] = torch.from_numpy(np.ascontiguousarray(s.T).astype(np.float16))  # [N, K/g]
+            t[name + ".weight_shape"] = torch.tensor([N, K])
             deq[name] = OL.dequant_u4(q, s, z, F16)
         else:
             w = rn(w, F16)
@@ -55,9 +89,18 @@ def make_checkpoint(arch, awq, seed=0):
     cfg = {"architectures": ["InternLM2ForCausalLM" if arch == "internlm2" else "LlamaForCausalLM"],
            "hidden_size": H, "num_hidden_layers": L, "num_attention_heads": HQ, "num_key_value_heads": HKV,
            "intermediate_size": I, "vocab_size": V, "rms_norm_eps": 1e-5, "rope_theta": 10000.0}
-    if awq:
+    if family == "awq":
         cfg["quantization_config"] = {"quant_method": "awq", "bits": 4, "group_size": 128, "zero_point": True,
                                       "version": "gemm"}
+    elif family == "gptq":
+        cfg["quantization_config"] = {"quant_method": "gptq", "bits": 4, "group_size": 128, "sym": True,
+                                      "desc_act": False}
+    elif family == "compressed-tensors":
+        cfg["quantization_config"] = {"quant_method": "compressed-tensors", "format": "pack-quantized",
+                                      "config_groups": {"group_0": {"format": "pack-quantized", "targets": ["Linear"],
+                                                                    "weights": {"num_bits": 4, "type": "int",
+                                                                                "group_size": 128, "symmetric": True,
+                                                                                "strategy": "group"}}}}
     return cfg, t, deq
 
 
@@ -145,12 +188,13 @@ def to_tiny(spec, cfg_tensors, tp=1, rank=0):
 
 
 @pytest.mark.parametrize("arch", ["internlm2", "llama"])
-@pytest.mark.parametrize("awq", [True, False])
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("tp", [1, 2])
-def test_loader_transforms_preserve_model_semantics(arch, awq, tp):
-    cfg, t, deq = make_checkpoint(arch, awq, seed=1)
+def test_loader_transforms_preserve_model_semantics(arch, family, tp):
+    cfg, t, deq = make_checkpoint(arch, family, seed=1)
     spec = LD.spec_from_config(cfg)
-    assert spec.weight_format == ("awq" if awq else "fp16") and spec.arch == arch
+    assert spec.weight_format == ("awq" if family else "fp16") and spec.arch == arch
+    assert spec.checkpoint_format == family
     tokens = [5, 17, 200, 3, 99]
     ref = hf_forward(arch, t, deq, tokens)
     shards = [to_tiny(spec, t, tp, r) for r in range(tp)]
