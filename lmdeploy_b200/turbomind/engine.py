@@ -43,7 +43,7 @@ class TurboMind:
         self.pool = KvCachePool(num_blocks, spec.layers, self.model.kv_heads, spec.head_dim, self.block_len,
                                 cfg.quant_policy, device=dev)
         self.scheduler = Scheduler(max_batch=self.max_batch, block_len=self.block_len, num_blocks=num_blocks,
-                                   session_len=self.session_len)
+                                   session_len=self.session_len, prefix_caching=cfg.enable_prefix_caching)
         B = self.max_batch
         self._max_blocks = (self.session_len + self.block_len - 1) // self.block_len
         self.d_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -89,16 +89,14 @@ class TurboMind:
             return []
         B = len(batch)
         ptrs, nblk = [], [0]
-        for i, s in enumerate(batch):
-            self.h_tokens[i] = s.next_input()
-            self.h_cu_k[i + 1] = self.h_cu_k[i] + (s.cached + 1) if i else (s.cached + 1)
-            ptrs += [self.pool.ptr(b) for b in s.blocks]
-            nblk.append(len(ptrs))
         self.h_cu_k[0] = 0
         acc = 0
         for i, s in enumerate(batch):
-            acc += s.cached + 1
+            self.h_tokens[i] = s.next_input()
+            acc += s.cached + 1                      # keys visible to this step: cached history + the fed token
             self.h_cu_k[i + 1] = acc
+            ptrs += [self.pool.ptr(b) for b in s.blocks]
+            nblk.append(len(ptrs))
         self.h_cu_blocks[:B + 1] = torch.tensor(nblk, dtype=torch.int32)
         self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
         self.d_tokens[:B].copy_(self.h_tokens[:B], non_blocking=True)
@@ -111,6 +109,10 @@ class TurboMind:
         self.h_out[:B].copy_(self.d_out[:B], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return sched.update(batch, self.h_out[:B].tolist())
+
+    def get_schedule_metrics(self, index=0):
+        """ScheduleMetrics of this rank (TurboMind.get_schedule_metrics, lmdeploy/turbomind/turbomind.py)."""
+        return self.scheduler.metrics()
 
     def new_session_id(self):
         with self._lock:

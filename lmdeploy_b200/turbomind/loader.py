@@ -124,14 +124,62 @@ def convert_globals(spec: ModelSpec, tensors, tp=1, rank=0):
     return dict(tok_embeddings=emb, norm=norm, output=o[rank * vl:(rank + 1) * vl].t().contiguous())
 
 
+class LazyCheckpoint:
+    """Read-only name -> tensor mapping over the *.safetensors shards of a checkpoint directory.  Tensors are read from
+    disk on access (safetensors memory-maps the shard) and not retained, so converting layer i holds only layer i in
+    host memory -- a 70B checkpoint does not fit twice.  Shard lookup follows `model.safetensors.index.json` when it
+    exists (its `weight_map`), else the headers of every shard (lmdeploy/turbomind/checkpoint.py does the same
+    per-shard iteration through safe_open)."""
+
+    def __init__(self, path):
+        from safetensors import safe_open
+        self._open = safe_open
+        self.path = path
+        self._shard_of = {}
+        index = os.path.join(path, "model.safetensors.index.json")
+        shards = sorted(f for f in os.listdir(path) if f.endswith(".safetensors"))
+        if not shards:
+            raise FileNotFoundError(f"no *.safetensors files in {path}")
+        if os.path.exists(index):
+            with open(index) as fh:
+                self._shard_of = dict(json.load(fh)["weight_map"])
+            missing = sorted(set(self._shard_of.values()) - set(shards))
+            if missing:
+                raise FileNotFoundError(f"{index} names shards that are not in {path}: {missing}")
+        else:
+            for f in shards:
+                with safe_open(os.path.join(path, f), framework="pt", device="cpu") as fh:
+                    for k in fh.keys():
+                        self._shard_of[k] = f
+        self._handles = {}
+
+    def _handle(self, shard):
+        h = self._handles.get(shard)
+        if h is None:
+            h = self._handles[shard] = self._open(os.path.join(self.path, shard), framework="pt", device="cpu")
+        return h
+
+    def __contains__(self, name):
+        return name in self._shard_of
+
+    def __getitem__(self, name):
+        return self._handle(self._shard_of[name]).get_tensor(name)
+
+    def get(self, name, default=None):
+        return self[name] if name in self._shard_of else default
+
+    def keys(self):
+        return self._shard_of.keys()
+
+    def __len__(self):
+        return len(self._shard_of)
+
+
 def read_checkpoint(path):
-    from safetensors.torch import load_file
-    cfg = json.load(open(os.path.join(path, "config.json")))
-    tensors = {}
-    for f in sorted(os.listdir(path)):
-        if f.endswith(".safetensors"):
-            tensors.update(load_file(os.path.join(path, f)))
-    return cfg, tensors
+    """-> (config dict, LazyCheckpoint)."""
+    with open(os.path.join(path, "config.json")) as fh:
+        cfg = json.load(fh)
+    return cfg, LazyCheckpoint(path)
 
 
 def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0):

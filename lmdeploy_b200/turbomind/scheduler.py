@@ -7,8 +7,17 @@ crosses a block boundary, finished sequences are retired and their blocks return
 
 Prompt tokens are consumed through the same decode step one token per step ("prefill-by-decode"): the decode
 kernel appends K/V for the token it is given, so feeding prompt tokens reproduces causal prefill exactly.  A tiled
-prefill attention kernel is SURVEY section 8f rank 1 ("next"), not part of this hot path."""
-from collections import deque
+prefill attention kernel is SURVEY section 8f rank 1 ("next"), not part of this hot path.
+
+Prefix caching (TurbomindEngineConfig.enable_prefix_caching, lmdeploy/messages.py:238-239; the reference indexes
+logical blocks in src/turbomind/engine/prefix_trie.h): K/V of position p depends only on tokens [0, p], so a FULL block
+is identified by (identity of the preceding block, its block_len tokens).  Full blocks are published to an exact
+index when they fill; a new request re-uses the longest chain of published blocks covering its prompt (always leaving
+at least the last prompt token to be fed, so the step that produces its first logits still runs) and starts with
+`cached` already advanced -- those tokens are never fed.  Shared blocks are read-only by construction: a decode step
+writes only position `cached`, which lies in the first private block.  Unreferenced published blocks stay resident
+and are evicted oldest-first only when the free list runs dry."""
+from collections import OrderedDict, deque
 from dataclasses import dataclass, field
 from typing import Deque, Dict, List, Optional
 
@@ -27,6 +36,11 @@ class Sequence:
     generated: List[int] = field(default_factory=list)
     finished: bool = False
     finish_reason: Optional[str] = None
+    reused_tokens: int = 0        # prompt tokens served from the prefix cache (never fed)
+    chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
+
+    def token_at(self, pos):
+        return self.prompt[pos] if pos < len(self.prompt) else self.generated[pos - len(self.prompt)]
 
     def next_input(self):
         if self.fed < len(self.prompt):
@@ -42,8 +56,11 @@ class BlockAllocator:
     def __init__(self, num_blocks):
         self.free = list(range(num_blocks - 1, -1, -1))
         self.total = num_blocks
+        self.evict = None             # optional callable(n) -> blocks reclaimed from a cache layered on top
 
     def allocate(self, n):
+        if n > len(self.free) and self.evict is not None:
+            self.free.extend(self.evict(n - len(self.free)))
         if n > len(self.free):
             return None
         return [self.free.pop() for _ in range(n)]
@@ -56,13 +73,97 @@ class BlockAllocator:
         return len(self.free)
 
 
+class PrefixCache:
+    """Exact index of full KV blocks.  A published block has a node id; its key is (parent node id, tokens)."""
+    ROOT = 0
+
+    def __init__(self, block_len):
+        self.block_len = block_len
+        self.index: Dict[tuple, int] = {}            # (parent node, tokens) -> node
+        self.block_of: Dict[int, int] = {}           # node -> physical block
+        self.node_of: Dict[int, int] = {}            # physical block -> node
+        self.key_of: Dict[int, tuple] = {}           # node -> key
+        self.refs: Dict[int, int] = {}               # physical block -> live sequences holding it
+        self.idle: "OrderedDict[int, None]" = OrderedDict()   # published, unreferenced blocks, oldest first
+        self._next_node = 1
+        self.hits = self.queries = 0                 # in tokens
+
+    def match(self, tokens, limit):
+        """Longest chain of published blocks covering tokens[:limit] -> (blocks, nodes); takes a reference on each."""
+        blocks, nodes, parent = [], [], self.ROOT
+        bl = self.block_len
+        self.queries += len(tokens)
+        for j in range(limit // bl):
+            node = self.index.get((parent, tuple(tokens[j * bl:(j + 1) * bl])))
+            if node is None:
+                break
+            b = self.block_of[node]
+            self.refs[b] = self.refs.get(b, 0) + 1
+            self.idle.pop(b, None)
+            blocks.append(b)
+            nodes.append(node)
+            parent = node
+        self.hits += len(blocks) * bl
+        return blocks, nodes
+
+    def publish(self, parent, tokens, block):
+        """Index `block` (just filled with `tokens` after chain `parent`).  Returns its node id; if identical content is
+        already indexed (two requests raced through the same prefix) the existing node is returned and `block` stays
+        private to its owner."""
+        key = (parent, tuple(tokens))
+        node = self.index.get(key)
+        if node is not None:
+            return node
+        node = self._next_node
+        self._next_node += 1
+        self.index[key] = node
+        self.block_of[node] = block
+        self.node_of[block] = node
+        self.key_of[node] = key
+        self.refs[block] = 1
+        return node
+
+    def release(self, blocks):
+        """Drop one reference per block; returns the blocks that are NOT cached (to go back to the free list)."""
+        private = []
+        for b in blocks:
+            if b in self.node_of:
+                self.refs[b] -= 1
+                if self.refs[b] == 0:
+                    self.idle[b] = None
+            else:
+                private.append(b)
+        return private
+
+    def evict(self, n):
+        """Forget up to n unreferenced blocks, oldest first.  Descendants of a forgotten node become unreachable (their
+        keys name a node id that no longer resolves) and age out the same way."""
+        out = []
+        while self.idle and len(out) < n:
+            b, _ = self.idle.popitem(last=False)
+            node = self.node_of.pop(b)
+            del self.index[self.key_of.pop(node)]
+            del self.block_of[node]
+            del self.refs[b]
+            out.append(b)
+        return out
+
+    @property
+    def num_idle(self):
+        return len(self.idle)
+
+
 class Scheduler:
-    def __init__(self, *, max_batch, block_len, num_blocks, session_len):
+    def __init__(self, *, max_batch, block_len, num_blocks, session_len, prefix_caching=False):
         self.max_batch, self.block_len, self.session_len = max_batch, block_len, session_len
         self.alloc = BlockAllocator(num_blocks)
+        self.prefix = PrefixCache(block_len) if prefix_caching else None
+        if self.prefix is not None:
+            self.alloc.evict = self.prefix.evict
         self.waiting: Deque[Sequence] = deque()
         self.active: List[Sequence] = []
         self.sessions: Dict[int, Sequence] = {}
+        self.tick = 0                 # schedule() calls so far
 
     def add(self, seq: Sequence):
         if seq.session_id in self.sessions:
@@ -79,17 +180,22 @@ class Scheduler:
         if seq and not seq.finished:
             seq.finished, seq.finish_reason = True, "cancel"
 
+    def _release(self, seq):
+        blocks = seq.blocks if self.prefix is None else self.prefix.release(seq.blocks)
+        self.alloc.release(blocks)
+        seq.blocks = []
+
     def _blocks_needed(self, seq, upto_tokens):
         return (upto_tokens + self.block_len - 1) // self.block_len - len(seq.blocks)
 
     def schedule(self):
         """Form the batch of this step.  Returns the list of sequences that run (each feeds one token)."""
+        self.tick += 1
         # retire
         still = []
         for s in self.active:
             if s.finished:
-                self.alloc.release(s.blocks)
-                s.blocks = []
+                self._release(s)
                 self.sessions.pop(s.session_id, None)
             else:
                 still.append(s)
@@ -110,8 +216,15 @@ class Scheduler:
                 self.waiting.popleft()
                 self.sessions.pop(s.session_id, None)
                 continue
-            got = self.alloc.allocate(self._blocks_needed(s, 1))
+            if self.prefix is not None and not s.blocks:
+                # never the whole prompt: its last token must be fed to produce the first logits
+                s.blocks, s.chain = self.prefix.match(s.prompt, len(s.prompt) - 1)
+                s.cached = s.fed = s.reused_tokens = len(s.blocks) * self.block_len
+            got = self.alloc.allocate(self._blocks_needed(s, s.cached + 1))
             if got is None:
+                if self.prefix is not None:            # give the references back; retry from scratch next step
+                    self._release(s)
+                    s.chain, s.cached, s.fed, s.reused_tokens = [], 0, 0, 0
                 break
             s.blocks += got
             self.waiting.popleft()
@@ -126,6 +239,11 @@ class Scheduler:
             s.cached += 1
             if s.fed < len(s.prompt):
                 s.fed += 1
+            if self.prefix is not None and s.cached % self.block_len == 0:
+                j = s.cached // self.block_len - 1           # the block that just filled
+                if len(s.chain) == j:
+                    toks = [s.token_at(p) for p in range(j * self.block_len, s.cached)]
+                    s.chain.append(self.prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
             if s.fed < len(s.prompt):
                 continue                   # still consuming the prompt; sampled token is discarded
             if s.max_new_tokens == 0:
@@ -144,3 +262,15 @@ class Scheduler:
     @property
     def has_work(self):
         return bool(self.waiting) or any(not s.finished for s in self.active)
+
+    def metrics(self):
+        """Counterpart of TurboMind.get_schedule_metrics -> ScheduleMetrics (src/turbomind/python/bind.cpp:530-537, 990-994):
+        same field names, plus the raw block counts they derive from."""
+        idle = self.prefix.num_idle if self.prefix is not None else 0
+        used = self.alloc.total - self.alloc.num_free - idle
+        hit = self.prefix.hits / self.prefix.queries if self.prefix is not None and self.prefix.queries else 0.0
+        return dict(total_seqs=len(self.sessions), active_seqs=sum(not s.finished for s in self.active),
+                    waiting_seqs=sum(not s.finished for s in self.waiting),
+                    cache_usage=used / self.alloc.total if self.alloc.total else 0.0, prefix_cache_hit_rate=hit,
+                    scheduler_tick=self.tick, total_blocks=self.alloc.total, free_blocks=self.alloc.num_free,
+                    cached_blocks=idle, active_blocks=used)

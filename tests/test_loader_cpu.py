@@ -220,3 +220,39 @@ def test_awq_unpack_matches_oracle():
     q = rng.integers(0, 16, (8, 32)).astype(np.uint8)
     w = OL.awq_pack(q)
     assert (LD.awq_unpack(torch.from_numpy(w)).numpy() == q).all()
+
+
+def test_lazy_checkpoint_reads_sharded_and_indexed_directories(tmp_path):
+    import json
+    from safetensors.torch import save_file
+    cfg, t, _ = make_checkpoint("llama", "awq", seed=3)
+    names = sorted(t)
+    half = len(names) // 2
+    d1 = tmp_path / "headers"
+    d1.mkdir()
+    save_file({k: t[k].contiguous() for k in names[:half]}, str(d1 / "model-00001-of-00002.safetensors"))
+    save_file({k: t[k].contiguous() for k in names[half:]}, str(d1 / "model-00002-of-00002.safetensors"))
+    (d1 / "config.json").write_text(json.dumps(cfg))
+    c1, lazy = LD.read_checkpoint(str(d1))
+    assert c1 == cfg and len(lazy) == len(t) and set(lazy.keys()) == set(t)
+    assert "nope" not in lazy and lazy.get("nope") is None
+    for k in (names[0], names[-1], names[half]):
+        assert torch.equal(lazy[k], t[k])
+    # with an index file the weight_map decides; a shard it names but that is absent is an error up front
+    d2 = tmp_path / "indexed"
+    d2.mkdir()
+    save_file({k: t[k].contiguous() for k in names}, str(d2 / "model-00001-of-00001.safetensors"))
+    (d2 / "config.json").write_text(json.dumps(cfg))
+    (d2 / "model.safetensors.index.json").write_text(json.dumps(
+        {"metadata": {}, "weight_map": {k: "model-00001-of-00001.safetensors" for k in names}}))
+    _, lazy2 = LD.read_checkpoint(str(d2))
+    assert torch.equal(lazy2[names[1]], t[names[1]])
+    (d2 / "model.safetensors.index.json").write_text(json.dumps({"weight_map": {names[0]: "gone.safetensors"}}))
+    with pytest.raises(FileNotFoundError, match="gone.safetensors"):
+        LD.read_checkpoint(str(d2))
+    # the converted layer is the same whether it comes from the in-memory dict or the lazy reader
+    spec = LD.spec_from_config(cfg)
+    a, b = LD.convert_layer(spec, t, 1), LD.convert_layer(spec, lazy, 1)
+    for k in ("w_qkv", "wo", "w1w3", "w2"):
+        assert torch.equal(a[k].q, b[k].q) and torch.equal(a[k].scales, b[k].scales) and torch.equal(a[k].zeros, b[k].zeros)
+    assert torch.equal(a["ffn_norm"], b["ffn_norm"])

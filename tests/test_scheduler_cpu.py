@@ -121,3 +121,144 @@ def test_product_fails_loudly_without_library(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.B200LibraryError):
         _lib.load()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# prefix caching
+# ---------------------------------------------------------------------------------------------------------------
+class FakeKvModel:
+    """Stands in for the decode step: `store[block][offset]` plays the KV page (it records the token whose K/V would be
+    written there) and the sampled token is a hash of everything the sequence can see through ITS block table -- so a
+    wrong, stale or shared-but-overwritten block changes the output."""
+
+    def __init__(self, num_blocks, block_len, vocab=50000):
+        self.store = [[None] * block_len for _ in range(num_blocks)]
+        self.block_len, self.vocab = block_len, vocab
+        self.fed = 0
+
+    def step(self, batch):
+        out = []
+        for s in batch:
+            pos = s.cached
+            self.store[s.blocks[pos // self.block_len]][pos % self.block_len] = s.next_input()
+            self.fed += 1
+        for s in batch:
+            h = 1469598103934665603
+            for p in range(s.cached + 1):
+                t = self.store[s.blocks[p // self.block_len]][p % self.block_len]
+                assert t is not None, "read of a KV slot nobody wrote"
+                h = ((h ^ (t + 1)) * 1099511628211) % (1 << 64)
+            out.append(h % self.vocab)
+        return out
+
+
+def generate(prompts, *, prefix_caching, num_blocks=64, block_len=4, max_batch=4, max_new=6, waves=1):
+    sched = Scheduler(max_batch=max_batch, block_len=block_len, num_blocks=num_blocks, session_len=4096,
+                      prefix_caching=prefix_caching)
+    model = FakeKvModel(num_blocks, block_len)
+    results, sid = [], 0
+    for _ in range(waves):
+        seqs = []
+        for p in prompts:
+            sid += 1
+            seqs.append(Sequence(session_id=sid, prompt=list(p), max_new_tokens=max_new, stop_token_ids=[],
+                                 ignore_eos=True, eos_id=None))
+            sched.add(seqs[-1])
+        while sched.has_work:
+            batch = sched.schedule()
+            assert batch
+            # a block may be shared, but then only below every holder's write position
+            for s in batch:
+                wb = s.blocks[s.cached // block_len]
+                assert sum(wb in o.blocks for o in sched.active) == 1, "a shared block is about to be written"
+            sched.update(batch, model.step(batch))
+        sched.schedule()
+        results.append([list(s.generated) for s in seqs])
+    return results, model, sched
+
+
+def test_prefix_cache_reuses_blocks_and_preserves_outputs():
+    system = list(range(100, 100 + 11))                       # 11 shared tokens: 2 full blocks of 4 + 3
+    prompts = [system + [7, 8, 9], system + [7, 1], system[:9] + [5, 5, 5, 5], [3, 1, 4, 1, 5]]
+    base, m0, _ = generate(prompts, prefix_caching=False, waves=2)
+    got, m1, sched = generate(prompts, prefix_caching=True, waves=2)
+    assert got == base                                         # identical generations, both waves
+    assert m1.fed < m0.fed                                     # and fewer tokens fed
+    # second wave: every prompt finds all of its full blocks except the one holding its last token
+    expect_reuse = sum(((len(p) - 1) // 4) * 4 for p in prompts)
+    assert m0.fed - m1.fed >= expect_reuse
+    met = sched.metrics()
+    assert 0 < met["prefix_cache_hit_rate"] < 1 and met["active_seqs"] == 0 and met["active_blocks"] == 0
+    assert met["free_blocks"] + met["cached_blocks"] == met["total_blocks"]
+
+
+def test_prefix_cache_never_covers_the_last_prompt_token():
+    prompt = list(range(1, 9))                                 # exactly 2 blocks of 4
+    sched = Scheduler(max_batch=2, block_len=4, num_blocks=16, session_len=64, prefix_caching=True)
+    model = FakeKvModel(16, 4)
+    outs = []
+    for sid in (1, 2):
+        s = Sequence(session_id=sid, prompt=list(prompt), max_new_tokens=2, stop_token_ids=[], ignore_eos=True, eos_id=None)
+        sched.add(s)
+        while sched.has_work:
+            b = sched.schedule()
+            sched.update(b, model.step(b))
+        outs.append((s.generated, s.reused_tokens))
+    assert outs[0][0] == outs[1][0]
+    assert outs[0][1] == 0 and outs[1][1] == 4                 # block 0 only: block 1 holds the last prompt token
+
+
+def test_prefix_cache_eviction_under_pressure_keeps_accounting_exact():
+    # pool of 6 blocks, block_len 4: cached blocks of finished requests must be reclaimed for new, unrelated ones
+    sched = Scheduler(max_batch=1, block_len=4, num_blocks=6, session_len=64, prefix_caching=True)
+    model = FakeKvModel(6, 4)
+    gens = {}
+    for sid in range(1, 8):
+        prompt = [sid * 10 + i for i in range(9)]              # distinct prompts, 3 blocks each
+        s = Sequence(session_id=sid, prompt=prompt, max_new_tokens=3, stop_token_ids=[], ignore_eos=True, eos_id=None)
+        sched.add(s)
+        while sched.has_work:
+            b = sched.schedule()
+            assert b, "admission starved although idle cached blocks could be evicted"
+            sched.update(b, model.step(b))
+        sched.schedule()
+        assert s.finish_reason == "length" and len(s.generated) == 3
+        gens[sid] = list(s.generated)
+        m = sched.metrics()
+        assert m["free_blocks"] + m["cached_blocks"] == 6 and m["active_blocks"] == 0
+    # the same prompts without caching give the same tokens
+    base, _, _ = generate([[sid * 10 + i for i in range(9)] for sid in range(1, 8)], prefix_caching=False, num_blocks=6,
+                          max_batch=1, max_new=3)
+    assert [gens[i] for i in range(1, 8)] == base[0]
+
+
+def test_concurrent_identical_prompts_do_not_share_a_block_being_written():
+    prompts = [[9, 8, 7, 6, 5, 4, 3, 2, 1]] * 3
+    base, _, _ = generate(prompts, prefix_caching=False, max_batch=3)
+    got, _, sched = generate(prompts, prefix_caching=True, max_batch=3)
+    assert got == base
+    # all three ran concurrently from scratch (nothing was published when they were admitted): no reuse
+    assert sched.prefix.hits == 0
+
+
+def test_cancel_and_retire_return_references():
+    sched = Scheduler(max_batch=2, block_len=4, num_blocks=8, session_len=64, prefix_caching=True)
+    model = FakeKvModel(8, 4)
+    a = Sequence(session_id=1, prompt=list(range(1, 10)), max_new_tokens=50, stop_token_ids=[], ignore_eos=True, eos_id=None)
+    sched.add(a)
+    for _ in range(9):
+        b = sched.schedule()
+        sched.update(b, model.step(b))
+    c = Sequence(session_id=2, prompt=list(range(1, 10)), max_new_tokens=50, stop_token_ids=[], ignore_eos=True, eos_id=None)
+    sched.add(c)
+    b = sched.schedule()
+    assert c.reused_tokens == 8 and c.blocks[:2] == a.blocks[:2]
+    sched.update(b, model.step(b))
+    sched.cancel(1)
+    b = sched.schedule()                                       # retires a; c keeps the shared blocks alive
+    assert [s.session_id for s in b] == [2]
+    assert all(sched.prefix.refs[x] == 1 for x in c.blocks[:2])
+    sched.cancel(2)
+    sched.schedule()
+    m = sched.metrics()
+    assert m["active_blocks"] == 0 and m["free_blocks"] + m["cached_blocks"] == 8 and m["total_seqs"] == 0
