@@ -33,7 +33,13 @@ CONFIGS = {
     "c3": ("llama3-8b", 128, 4096, 4),
     "c4": ("internlm2-20b", 64, 2048, 0),
     "c1-tiny": ("internlm2-1.8b", 1, 128, 0),
+    # Llama-3-70B FP8 + KV-int8 at tensor-parallel 8 (BASELINE config 5): 70 GB of weights + 44 GB of KV, so it needs
+    # --gpus >= 2; launch under torchrun with --gpus 8 for the configuration as named
+    "c5": ("llama3-70b", 32, 8192, 8),
 }
+
+MIN_GPUS = {"c5": 2}
+WEIGHT_LABEL = {"awq": "W4A16", "fp16": "fp16", "fp8": "FP8"}
 
 
 def parse():
@@ -119,7 +125,8 @@ def run_reference(args):
         "impl": "reference", "metric": "decode tokens/sec", "value": r["tokens_per_s"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name} W4A16+KV-int{qp} decode bs={batch} ctx={ctx} (CPU port of the path)"},
+        "config": {"workload": f"{name} {WEIGHT_LABEL.get(spec.weight_format, spec.weight_format)}+"
+                               f"{'KV-int%d' % qp if qp else 'KV-fp16'} decode bs={batch} ctx={ctx} (CPU port of the path)"},
         "cpu_baseline": {"value": r["tokens_per_s"], "unit": "tokens/s", "cores": cores, "kind": "port",
                          "sample": r["sample"]},
         "e2e": {"value": r["tokens_per_s"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -147,6 +154,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name, batch, ctx, qp = CONFIGS[args.config]
     spec = SPECS[name]
+    if world < MIN_GPUS.get(args.config, 1):
+        raise SystemExit(f"config {args.config} does not fit {world} GPU(s): needs --gpus >= {MIN_GPUS[args.config]}")
     total_steps = args.warmup + args.steps
     # two phases run back to back on the same cache: device-resident (value) and host-fed (e2e)
     max_len = ctx + 2 * total_steps + 8
@@ -232,9 +241,11 @@ def run_b200(args):
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": f"{name} W4A16(AWQ u4 g128)+KV-int{qp} greedy decode, bs={batch}, ctx={ctx}"
-                   if spec.weight_format == "awq" else f"{name} fp16 + KV quant {qp} decode bs={batch} ctx={ctx}",
+        "vs_baseline": None, "dtype": spec.dtype, "data": "synthetic",
+        "config": {"workload": {"awq": f"{name} W4A16(AWQ u4 g128)+KV-int{qp} greedy decode, bs={batch}, ctx={ctx}",
+                                "fp8": f"{name} FP8(e4m3 weights, bf16 activations)+KV-int{qp} greedy decode, bs={batch}, "
+                                       f"ctx={ctx}"}.get(spec.weight_format,
+                                                         f"{name} fp16 + KV quant {qp} decode bs={batch} ctx={ctx}"),
                    "parallelism": f"tp{world}", "cuda_graph": use_graph,
                    "l2": "inputs larger than L2 (>= 6 GB of KV + weights streamed per step per GPU)"},
         "roofline": roofline,

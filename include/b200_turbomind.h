@@ -168,7 +168,11 @@ B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
  *   scales T [K/g, N] and integer-valued zeros T [K/g, N], g = 128);
  *   2 fp8: weight float8_e4m3fn bytes [K, N] (or [N, K] with weight_is_transposed) and `scales` = the f32 block
  *   scales [K/128, N/128] (weight_scale_inv; zeros NULL) -- the non-sm90 path of the reference: block scales cast to
- *   T and applied per K-group, w = T(e4m3) *_T T(scale) (models/linear_weight.cc:138-150, gemm/transform.h:92-97).
+ *   T and applied per K-group, w = T(e4m3) *_T T(scale) (models/linear_weight.cc:138-150, gemm/transform.h:92-97);
+ *   3 fp8 with the scales already expanded along N: `scales` f32 [K/128, N], one per (128-k group, output column) --
+ *   the form the reference's kernel consumes after LinearWeight::prepare's expansion; a loader that permutes,
+ *   interleaves or slices output columns (RoPE pair reorder, fused gate|up, TP) expands the checkpoint's blocks
+ *   first and hands this format over.  Same arithmetic as format 2.
  * D[m, N] = x[m, K] . dequant(W) (+ bias); u4 dequant is w = fma_T(q, s, -(z*s)_T) exactly as
  * kernels/gemm/transform.h:48-74 / cast.cu:155; accumulation fp32 on tcgen05 tensor cores.
  * epilogue: 0 none; 1 gated SiLU over element-interleaved (gate, up) columns -> [m, N/2]
@@ -180,7 +184,8 @@ B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
 typedef struct {
     int         input_dim;     /* K */
     int         output_dim;    /* N */
-    int         weight_format; /* 0 dense T, 1 u4 (AWQ, g128), 2 fp8 e4m3 with 128x128 f32 block scales */
+    int         weight_format; /* 0 dense T, 1 u4 (AWQ, g128), 2 fp8 e4m3 + 128x128 f32 block scales, 3 fp8 e4m3 +
+                                  per-column f32 scales of 128-k groups */
     int         dtype;         /* activation / scale type T */
     int         group_size;    /* 128 (u4 quant group / fp8 scale block) */
     const void* prepared;      /* output of b200_linear_prepare */

@@ -69,7 +69,7 @@ class StepInputs(C.Structure):
 
 
 W_QKV, W_O, W_GATE_UP, W_DOWN, W_LM_HEAD = range(5)
-FMT_DENSE, FMT_U4, FMT_FP8 = range(3)        # b200_linear_desc.weight_format
+FMT_DENSE, FMT_U4, FMT_FP8, FMT_FP8_COL = range(4)        # b200_linear_desc.weight_format
 T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM = range(4)
 
 _lib = None

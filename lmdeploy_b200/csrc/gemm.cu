@@ -86,6 +86,34 @@ __global__ void prepare_fp8_kernel(uint8_t* dst, const uint8_t* w, const float* 
     }
 }
 
+// fp8 with per-column scales: same data layout; scales f32 [K/128, N] -> one T per row of the block (4-byte stride)
+template<class T>
+__global__ void prepare_fp8col_kernel(uint8_t* dst, const uint8_t* w, const float* scales, int K, int N, int trans)
+{
+    using Ops        = TypeOps<T>;
+    const int    kgs = K / kKG, nts = N / kBN;
+    const size_t nb  = (size_t)nts * kgs * kFp8ColBlockBytes;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nb; idx += (size_t)gridDim.x * blockDim.x) {
+        const int    within = (int)(idx % kFp8ColBlockBytes);
+        const size_t blk    = idx / kFp8ColBlockBytes;
+        const int    kg = (int)(blk % kgs), nt = (int)(blk / kgs);
+        uint8_t      out = 0;
+        if (within < kBN * kKG) {
+            const int j = within & 15, n = (within >> 4) & 127, k16 = within >> 11;
+            const int k = kg * kKG + k16 * 16 + j, ng = nt * kBN + n;
+            out         = trans ? w[(size_t)ng * K + k] : w[(size_t)k * N + ng];
+        }
+        else {
+            const int rel = within - kBN * kKG, n = rel >> 2, b = rel & 3;
+            if (b < 2) {
+                const T s = Ops::from_f32(scales[(size_t)kg * N + nt * kBN + n]);
+                out       = reinterpret_cast<const uint8_t*>(&s)[b];
+            }
+        }
+        dst[idx] = out;
+    }
+}
+
 // dense: W [K, N] row-major (trans == 0) or [N, K] row-major (trans == 1) -> per (nt, kg): [k8:16][n:128][8] T
 template<class T>
 __global__ void prepare_dense_kernel(T* dst, const T* w, int K, int N, int trans)
@@ -134,7 +162,7 @@ struct Plan {
 //   * K is split over 1/2/4/8 co-resident CTAs (largest count that fits one wave, every CTA >= 4 K-groups).
 static Plan make_plan(int fmt, int MT, int N, int K)
 {
-    const int WB     = fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    const int WB     = block_bytes_of(fmt);
     const int WB_pad = (WB + 1023) & ~1023;
     const int XB     = MT * 256;
     Plan      pl{};
@@ -271,11 +299,12 @@ static int validate_desc(const b200_linear_desc* d)
     if (d->weight_format == kU4 && d->group_size != 128) {
         return fail(B200_ERR_UNSUPPORTED, "u4 weights require group_size 128");
     }
-    if (d->weight_format != kU4 && d->weight_format != kDense && d->weight_format != kFp8) {
-        return fail(B200_ERR_UNSUPPORTED, "weight_format must be 0 (dense), 1 (u4 awq) or 2 (fp8 e4m3, 128x128 block scales)");
+    if (d->weight_format != kU4 && d->weight_format != kDense && d->weight_format != kFp8 && d->weight_format != kFp8Col) {
+        return fail(B200_ERR_UNSUPPORTED, "weight_format must be 0 (dense), 1 (u4 awq), 2 (fp8 e4m3, 128x128 block scales) or "
+                                          "3 (fp8 e4m3, per-column scales of 128-k groups)");
     }
-    if (d->weight_format == kFp8 && d->group_size != 128) {
-        return fail(B200_ERR_UNSUPPORTED, "fp8 weights require 128x128 scale blocks");
+    if ((d->weight_format == kFp8 || d->weight_format == kFp8Col) && d->group_size != 128) {
+        return fail(B200_ERR_UNSUPPORTED, "fp8 weights require 128-wide scale groups along K");
     }
     if (d->dtype != B200_DTYPE_F16 && d->dtype != B200_DTYPE_BF16) {
         return fail(B200_ERR_INVALID_ARG, "dtype must be 0 or 1");
@@ -289,7 +318,7 @@ extern "C" size_t b200_linear_prepared_bytes(const b200_linear_desc* d)
         return 0;
     }
     const size_t blocks = (size_t)(d->output_dim / kBN) * (d->input_dim / kKG);
-    return blocks * (d->weight_format == kU4 ? kU4BlockBytes : (d->weight_format == kFp8 ? kFp8BlockBytes : kDenseBlockBytes));
+    return blocks * block_bytes_of(d->weight_format);
 }
 
 extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight, const void* scales, const void* zeros,
@@ -328,6 +357,19 @@ extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight
         else {
             prepare_fp8_kernel<nv_bfloat16><<<2048, 256, 0, st>>>((uint8_t*)prepared, (const uint8_t*)weight,
                                                                   (const float*)scales, K, N, weight_is_transposed);
+        }
+    }
+    else if (d->weight_format == kFp8Col) {
+        if (!scales) {
+            return fail(B200_ERR_INVALID_ARG, "fp8 weights need the f32 scales [K/128, N]");
+        }
+        if (d->dtype == B200_DTYPE_F16) {
+            prepare_fp8col_kernel<half><<<2048, 256, 0, st>>>((uint8_t*)prepared, (const uint8_t*)weight,
+                                                              (const float*)scales, K, N, weight_is_transposed);
+        }
+        else {
+            prepare_fp8col_kernel<nv_bfloat16><<<2048, 256, 0, st>>>((uint8_t*)prepared, (const uint8_t*)weight,
+                                                                     (const float*)scales, K, N, weight_is_transposed);
         }
     }
     else {
@@ -415,6 +457,12 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
             return bf ? launch<nv_bfloat16, kFp8, 2>(p, rg.smem, st) : launch<half, kFp8, 2>(p, rg.smem, st);
         }
         return bf ? launch<nv_bfloat16, kFp8, 1>(p, rg.smem, st) : launch<half, kFp8, 1>(p, rg.smem, st);
+    }
+    if (d->weight_format == kFp8Col) {
+        if (rg.tiles == 2) {
+            return bf ? launch<nv_bfloat16, kFp8Col, 2>(p, rg.smem, st) : launch<half, kFp8Col, 2>(p, rg.smem, st);
+        }
+        return bf ? launch<nv_bfloat16, kFp8Col, 1>(p, rg.smem, st) : launch<half, kFp8Col, 1>(p, rg.smem, st);
     }
     return bf ? launch<nv_bfloat16, kDense, 1>(p, rg.smem, st) : launch<half, kDense, 1>(p, rg.smem, st);
 }

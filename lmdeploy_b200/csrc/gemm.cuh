@@ -50,11 +50,20 @@ enum WeightFormat : int
     kDense = 0,  // T weights, [k/8][128][8] tiles
     kU4    = 1,  // AWQ-style u4 + (scale, zero) per 128-group
     kFp8   = 2,  // e4m3 + per-128x128-block scale
+    kFp8Col = 3, // e4m3 + per-(128-k-group, output column) scale: what the reference's kernel consumes after
+                 // LinearWeight::prepare expands the checkpoint's block scales (linear_weight.cc:138-150); lets the
+                 // loader permute / interleave / slice output columns freely (RoPE reorder, fused gate|up, TP)
 };
 
 constexpr int kU4BlockBytes    = 8192 + 512;           // one (n-tile, k-group): data + fused params
 constexpr int kDenseBlockBytes = kBN * kKG * 2;        // 32 KB
 constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // e4m3 data [k16:8][n:128][16 B] + block scale (T, padded to 16 B)
+constexpr int kFp8ColBlockBytes = kBN * kKG + kBN * 4; // same data + one scale per row (T in the low half of 4 B)
+
+constexpr int block_bytes_of(int fmt)
+{
+    return fmt == kU4 ? kU4BlockBytes : fmt == kDense ? kDenseBlockBytes : fmt == kFp8 ? kFp8BlockBytes : kFp8ColBlockBytes;
+}
 
 // Development aid (tools/gemm_trace.cu compiles this TU with -DB200_GEMM_TRACE): per-role clock64 stamps of the
 // first kTraceCtas CTAs.  Absent from the product build.
@@ -128,7 +137,7 @@ struct Params {
 
 B200_DEVICE int w_block_bytes(int fmt)
 {
-    return fmt == kU4 ? kU4BlockBytes : (fmt == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    return block_bytes_of(fmt);
 }
 
 // two e4m3 bytes (low 16 bits of `x`) -> two floats (exact): cvt.rn.f16x2.e4m3x2 then f16 -> f32
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     // allocation, and the whole weight prefetch -- weights are constants) runs before griddepcontrol.wait.
     pdl_launch_dependents();
 
-    constexpr int  WB       = FMT == kU4 ? kU4BlockBytes : (FMT == kDense ? kDenseBlockBytes : kFp8BlockBytes);
+    constexpr int  WB       = block_bytes_of(FMT);
     constexpr int  WB_pad   = (WB + 1023) & ~1023;
     constexpr int  WSLOT    = WB_pad * TILES;
     constexpr bool kDequant = FMT != kDense;
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                         for (int q = 0; q < NKC; ++q) v[q][0] = lds128(wsm + ((kc0 + q) * 128 + n_local) * 16);
                     }
                     else {
-                        st2 = lds32(wsm + 16384);
+                        st2 = lds32(wsm + 16384 + (FMT == kFp8Col ? n_local * 4 : 0));
 #pragma unroll
                         for (int q = 0; q < NKC; ++q) {
                             v[q][0] = lds128(wsm + ((2 * (kc0 + q)) * 128 + n_local) * 16);

@@ -58,11 +58,14 @@ class Lin:
     """One linear in TurboMind orientation.  Exactly one payload is set:
          q uint8 [K,N] + scales f32 [K/g,N] + zeros f32 [K/g,N]      (int4, any checkpoint family)
          w f32 [K,N]                                                  (dense)
-         w8 uint8 [K,N] + block_scales f32 [K/128, N/128]             (fp8 e4m3, block scaled)"""
+         w8 uint8 [K,N] + scales f32 [K/128, N]                       (fp8 e4m3; the checkpoint's 128x128 block scales
+                                                                       expanded along N, as LinearWeight::prepare does
+                                                                       before the reference kernel sees them,
+                                                                       linear_weight.cc:138-150 -- so output columns can
+                                                                       be permuted, interleaved and sliced freely)"""
 
-    def __init__(self, q=None, scales=None, zeros=None, w=None, w8=None, block_scales=None, bias=None):
-        self.q, self.scales, self.zeros, self.w, self.w8, self.block_scales, self.bias = (q, scales, zeros, w, w8,
-                                                                                          block_scales, bias)
+    def __init__(self, q=None, scales=None, zeros=None, w=None, w8=None, bias=None):
+        self.q, self.scales, self.zeros, self.w, self.w8, self.bias = q, scales, zeros, w, w8, bias
 
     @property
     def quant(self):
@@ -76,25 +79,22 @@ class Lin:
     def kind(self):
         return "u4" if self.quant else "fp8" if self.fp8 else "dense"
 
-    def _need_plain(self, what):
-        if self.fp8:
-            raise NotImplementedError(f"{what} of a block-scaled fp8 linear: 128x128 scale blocks do not survive "
-                                      "arbitrary column selection")
-
     def cols(self, idx):
-        self._need_plain("column permutation")
         b = None if self.bias is None else self.bias[idx]
         if self.quant:
             return Lin(self.q[:, idx], self.scales[:, idx], self.zeros[:, idx], bias=b)
+        if self.fp8:
+            return Lin(w8=self.w8[:, idx], scales=self.scales[:, idx], bias=b)
         return Lin(w=self.w[:, idx], bias=b)
 
     def rows(self, lo, hi, group=128):
-        self._need_plain("row slicing")
-        if self.quant:
+        if self.quant or self.fp8:
             if lo % group or hi % group:
                 raise ValueError(f"row slice [{lo}, {hi}) splits a quantisation group of {group}")
-            return Lin(self.q[lo:hi], self.scales[lo // group:hi // group], self.zeros[lo // group:hi // group],
-                       bias=self.bias)
+            sc = self.scales[lo // group:hi // group]
+            if self.fp8:
+                return Lin(w8=self.w8[lo:hi], scales=sc, bias=self.bias)
+            return Lin(self.q[lo:hi], sc, self.zeros[lo // group:hi // group], bias=self.bias)
         return Lin(w=self.w[lo:hi], bias=self.bias)
 
     @staticmethod
@@ -111,7 +111,7 @@ class Lin:
             return Lin(torch.cat([p.q for p in parts], 1), torch.cat([p.scales for p in parts], 1),
                        torch.cat([p.zeros for p in parts], 1), bias=b)
         if parts[0].fp8:
-            raise NotImplementedError("fusing block-scaled fp8 linears")
+            return Lin(w8=torch.cat([p.w8 for p in parts], 1), scales=torch.cat([p.scales for p in parts], 1), bias=b)
         return Lin(w=torch.cat([p.w for p in parts], 1), bias=b)
 
     def dequant(self):
@@ -122,8 +122,8 @@ class Lin:
             z = self.zeros.repeat_interleave(g, 0)
             return (self.q.to(torch.float32) - z) * s
         if self.fp8:
-            s = self.block_scales.repeat_interleave(128, 0).repeat_interleave(128, 1)
-            return self.w8.view(torch.float8_e4m3fn).to(torch.float32) * s[:self.w8.shape[0], :self.w8.shape[1]]
+            s = self.scales.repeat_interleave(128, 0)[:self.w8.shape[0]]
+            return self.w8.contiguous().view(torch.float8_e4m3fn).to(torch.float32) * s
         return self.w
 
     def to_tm(self, device, dtype):
@@ -133,7 +133,7 @@ class Lin:
                         scales=self.scales.to(device, dtype).contiguous(),
                         zeros=self.zeros.to(device, dtype).contiguous())
         if self.fp8:
-            return dict(weight=self.w8.contiguous().to(device), block_scales=self.block_scales.contiguous().to(device))
+            return dict(weight=self.w8.contiguous().to(device), col_scales=self.scales.contiguous().to(device))
         return dict(weight=self.w.to(device, dtype).contiguous())
 
 
@@ -241,8 +241,11 @@ class Fp8Format(CheckpointFormat):
         w = av[".weight"]
         if w.dtype == torch.float8_e4m3fn:
             w = w.view(torch.uint8)
-        return Lin(w8=w.t().contiguous(), block_scales=av[".weight_scale_inv"].to(torch.float32).t().contiguous(),
-                   bias=_bias(av))
+        w8 = w.t().contiguous()                                               # [N, K] -> [K, N]
+        blocks = av[".weight_scale_inv"].to(torch.float32).t()               # [N/128, K/128] -> [K/128, N/128]
+        if blocks.shape[0] * 128 < w8.shape[0] or blocks.shape[1] * 128 < w8.shape[1]:
+            raise ValueError(f"fp8: {tuple(blocks.shape)} scale blocks do not cover a [{w8.shape[0]}, {w8.shape[1]}] weight")
+        return Lin(w8=w8, scales=blocks.repeat_interleave(128, 1)[:, :w8.shape[1]].contiguous(), bias=_bias(av))
 
 
 class DenseFormat(CheckpointFormat):

@@ -48,11 +48,11 @@ def spec_from_config(cfg):
     if name is None:
         raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama)")
     method, _group = parse_quantization_config(cfg.get("quantization_config"))
-    if method == "fp8":
-        raise NotImplementedError("fp8 checkpoints: the block-scaled fp8 GEMM exists (b200_linear_forward, "
-                                  "weight_format 2) but the decode-step driver does not run the un-fused "
-                                  "gate/up + activation layout it needs yet (DESIGN.md section 6b)")
-    fmt = "awq" if method in INT4_METHODS else "fp16"        # one on-GPU format for every int4 checkpoint family
+    # one on-GPU format per weight family: every int4 checkpoint becomes 'awq' (u4 g128), fp8 stays fp8
+    fmt = "awq" if method in INT4_METHODS else "fp8" if method == "fp8" else "fp16"
+    # compute dtype: int4 formats force fp16 (converter.py:38-48); otherwise the checkpoint's own dtype
+    hf_dtype = str(cfg.get("dtype", cfg.get("torch_dtype", "float16"))).replace("torch.", "")
+    dtype = "f16" if fmt == "awq" or hf_dtype != "bfloat16" else "bf16"
     rs = cfg.get("rope_scaling") or {}
     rope_type = "llama3" if rs.get("rope_type", rs.get("type")) == "llama3" else "default"
     head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
@@ -63,7 +63,7 @@ def spec_from_config(cfg):
                      rope_theta=float(cfg.get("rope_theta", 10000.0)), head_dim=head_dim,
                      norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope_type,
                      rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt,
-                     checkpoint_format=method)
+                     checkpoint_format=method, dtype=dtype)
 
 
 def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):

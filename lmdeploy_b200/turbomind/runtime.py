@@ -127,6 +127,8 @@ class DecodeModel:
             fmt = L.FMT_U4 if scales is not None else L.FMT_DENSE
         if fmt == L.FMT_U4 and (scales is None or zeros is None):
             raise ValueError("a u4 linear needs scales and zero points")
+        if fmt == L.FMT_FP8_COL and (scales is None or scales.dtype != torch.float32 or tuple(scales.shape) != (K // 128, N)):
+            raise ValueError(f"an fp8 linear [{K}x{N}] needs f32 scales [{K // 128}, {N}]")
         pl = PreparedLinear(self.lib, K, N, fmt, self.spec.dtype, self.device)
         pl.prepare(self.lib, weight, scales, zeros, transposed)
         L.check(self.lib.b200_model_set_linear(self.handle, layer, which, C.byref(pl.desc)), "set_linear")
@@ -147,8 +149,8 @@ class DecodeModel:
         """provider(name) -> tensors in the TurboMind pre-prepare layout of THIS rank:
            'tok_embeddings' [vocab, hidden]; 'norm' [hidden]; 'output' [hidden, vocab_local] (dense [K,N]);
            per layer i: f'layers.{i}.attention_norm', f'layers.{i}.ffn_norm',
-           f'layers.{i}.{w_qkv|wo|w1w3|w2}' -> dict(weight=..., scales=..., zeros=...) (u4: int32 [K, N/8], T [K/128,N])
-           or dict(weight= T [K, N])."""
+           f'layers.{i}.{w_qkv|wo|w1w3|w2}' -> dict(weight=..., scales=..., zeros=...) (u4: int32 [K, N/8], T [K/128,N]),
+           dict(weight= uint8 e4m3 [K, N], col_scales= f32 [K/128, N]) (fp8) or dict(weight= T [K, N])."""
         s = self.spec
         D = s.head_dim
         with torch.cuda.device(self.device):
@@ -165,7 +167,10 @@ class DecodeModel:
                 self._set_tensor(i, L.T_FFN_NORM, provider(f"layers.{i}.ffn_norm"))
                 for name, (K, N, which) in shapes.items():
                     w = provider(f"layers.{i}.{name}")
-                    self._set_linear(i, which, K, N, w["weight"], w.get("scales"), w.get("zeros"))
+                    if "col_scales" in w:       # fp8 e4m3 bytes [K, N] + f32 scales [K/128, N]
+                        self._set_linear(i, which, K, N, w["weight"], w["col_scales"], fmt=L.FMT_FP8_COL)
+                    else:
+                        self._set_linear(i, which, K, N, w["weight"], w.get("scales"), w.get("zeros"))
                     del w
             out = provider("output")
             self._set_linear(0, L.W_LM_HEAD, s.hidden, self.vocab_local, out["weight"],
@@ -190,6 +195,13 @@ class DecodeModel:
             zs = torch.randint(6, 11, (K // 128, N), generator=g, device=dev).to(T)
             return dict(weight=qw, scales=sc, zeros=zs)
 
+        def fp8(K, N):
+            # the usual fp8 quantiser: scale = amax / 448 per (128-k group, column), weights stored as e4m3(w / scale)
+            w = torch.randn(K, N, generator=g, device=dev, dtype=torch.float32) * (0.1 / math.sqrt(K))
+            sc = (w.view(K // 128, 128, N).abs().amax(1) / 448.0).clamp_min(1e-12)
+            w8 = (w.view(K // 128, 128, N) / sc[:, None]).view(K, N).to(torch.float8_e4m3fn).view(torch.uint8)
+            return dict(weight=w8.contiguous(), col_scales=sc.contiguous())
+
         def provider(name):
             if name == "tok_embeddings":
                 return (torch.randn(s.vocab, s.hidden, generator=gr, device=dev) * 0.02).to(T)
@@ -203,6 +215,8 @@ class DecodeModel:
                     "w1w3": (s.hidden, 2 * self.inter), "w2": (self.inter, s.hidden)}[kind]
             if s.weight_format == "awq":
                 return u4(K, N)
+            if s.weight_format == "fp8":
+                return fp8(K, N)
             return dict(weight=dense(K, N, g))
 
         self.load_tm_weights(provider)

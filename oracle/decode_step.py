@@ -31,6 +31,11 @@ class TinyWeights:
             if fmt == "awq":
                 q, s, z = OL.quantize_groupwise_u4(w, 128)
                 return dict(q=q, scales=s, zeros=z, deq=OL.dequant_u4(q, s, z, dtype))
+            if fmt == "fp8":
+                # e4m3 with one f32 scale per (128-k group, column): amax / 448, the usual fp8 weight quantiser
+                sc = (np.abs(w.reshape(K // 128, 128, N)).max(axis=1) / 448.0).astype(np.float32)
+                w8 = OL.f32_to_e4m3(w / np.repeat(sc, 128, 0))
+                return dict(w8=w8, scales=sc, deq=OL.dequant_fp8_cols(w8, sc, 128, dtype))
             w = rn(w, dtype)
             return dict(w=w, deq=w)
 
@@ -52,12 +57,12 @@ class TinyWeights:
         I = self.inter // tp
 
         def cols(x, idx):
-            return {k: (v[:, idx] if k in ("q", "deq", "w") else v[:, idx] if v.ndim == 2 else v) for k, v in x.items()}
+            return {k: (v[:, idx] if k in ("q", "deq", "w", "w8") else v[:, idx] if v.ndim == 2 else v) for k, v in x.items()}
 
         def rows(x, sl):
             out = {}
             for k, v in x.items():
-                if k in ("q", "deq", "w"):
+                if k in ("q", "deq", "w", "w8"):
                     out[k] = v[sl]
                 else:   # scales / zeros [K/128, N]
                     out[k] = v[sl.start // 128: sl.stop // 128]

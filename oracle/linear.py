@@ -130,6 +130,14 @@ def dequant_fp8(w8, scale_inv, block=128, dtype=BF16):
     return t_mul(rn(e4m3_to_f32(w8), dtype), s, dtype)
 
 
+def dequant_fp8_cols(w8, scales, group=128, dtype=BF16):
+    """Same arithmetic with the block scales already expanded along N (what the reference's kernel consumes after
+    linear_weight.cc:138-150): scales f32 [K/group, N]."""
+    K, N = w8.shape
+    s = np.repeat(rn(f32(scales), dtype), group, axis=0)[:K]
+    return t_mul(rn(e4m3_to_f32(w8), dtype), s, dtype)
+
+
 # ---- linear / epilogues ----------------------------------------------------------------------
 def linear(x, w, dtype, bias=None):
     """D[M,N] = (T)(sum_k x[m,k] w[k,n]) fp32-accumulated (oracle: float64 accumulate)."""

@@ -12,6 +12,12 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
 
 
+# GPU tests written after this round's GPU budget was spent: they have compiled but never run on a device.  They are
+# skipped unless asked for, so a first-run failure cannot mask the verified suite behind `pytest -x`.
+pending_first_gpu_run = pytest.mark.skipif(not os.environ.get("B200_RUN_UNVERIFIED"),
+                                           reason="first GPU run pending: set B200_RUN_UNVERIFIED=1")
+
+
 @pytest.fixture(scope="session")
 def lib():
     """The C-ABI library (builds it if the .so is absent -- nvcc cross-compiles without a GPU)."""

@@ -49,12 +49,21 @@ def test_fp8_block_scaled_orientation():
     lin = fmt.read(av)
     assert lin.kind == "fp8"
     assert np.array_equal(lin.w8.numpy(), GOLD["fp8.tm.weight"])
-    assert np.array_equal(lin.block_scales.numpy(), GOLD["fp8.tm.scales"])
+    blocks = GOLD["fp8.tm.scales"]                                       # reference: [K/128, N/128]
+    assert tuple(lin.scales.shape) == (blocks.shape[0], lin.w8.shape[1])
+    assert np.array_equal(lin.scales.numpy(), np.repeat(blocks, 128, 1))   # expanded along N, nothing else
     # the float8 view of the same bytes is accepted as well
     av[".weight"] = av[".weight"].view(torch.float8_e4m3fn)
     assert np.array_equal(fmt.read(av).w8.numpy(), GOLD["fp8.tm.weight"])
-    with pytest.raises(NotImplementedError):
-        lin.cols(torch.arange(4))
+    # with per-column scales, column operations keep weight and scale together
+    idx = torch.tensor([300, 5, 129])
+    c = lin.cols(idx)
+    assert torch.equal(c.dequant(), lin.dequant()[:, idx])
+    r = lin.rows(128, 256)
+    assert torch.equal(r.dequant(), lin.dequant()[128:256])
+    with pytest.raises(ValueError, match="splits a quantisation group"):
+        lin.rows(0, 64)
+    assert torch.equal(CF.Lin.cat([c, c]).dequant(), torch.cat([c.dequant(), c.dequant()], 1))
 
 
 def test_accepts_truth_table_matches_reference():

@@ -22,31 +22,35 @@ pytestmark = pytest.mark.gpu
 def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_rank=0, shard=None):
     import torch
     from lmdeploy_b200.turbomind import ModelSpec, DecodeModel
+    T = w.dtype
     spec = ModelSpec("tiny", "llama", w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab, 1e4,
-                     weight_format=w.fmt)
+                     weight_format=w.fmt, dtype="f16" if T == F16 else "bf16")
     m = DecodeModel(spec, quant_policy=quant_policy, max_batch=max_batch, tp_size=tp_size, tp_rank=tp_rank,
                     rope_exact_math=True)   # the numpy oracle cannot reproduce MUFU approximations
     sw = shard if shard is not None else w
 
     def lin(d):
         if w.fmt == "awq":
-            return dict(weight=torch.from_numpy(OL.pack_u4_row(d["q"])).cuda(), scales=to_dev_T(d["scales"], F16),
-                        zeros=to_dev_T(d["zeros"], F16))
-        return dict(weight=to_dev_T(np.ascontiguousarray(d["w"]), F16))
+            return dict(weight=torch.from_numpy(OL.pack_u4_row(d["q"])).cuda(), scales=to_dev_T(d["scales"], T),
+                        zeros=to_dev_T(d["zeros"], T))
+        if w.fmt == "fp8":
+            return dict(weight=torch.from_numpy(np.ascontiguousarray(d["w8"])).cuda(),
+                        col_scales=torch.from_numpy(np.ascontiguousarray(d["scales"], np.float32)).cuda())
+        return dict(weight=to_dev_T(np.ascontiguousarray(d["w"]), T))
 
     def provider(name):
         if name == "tok_embeddings":
-            return to_dev_T(w.embed, F16)
+            return to_dev_T(w.embed, T)
         if name == "norm":
-            return to_dev_T(w.final_norm, F16)
+            return to_dev_T(w.final_norm, T)
         if name == "output":
-            return dict(weight=to_dev_T(np.ascontiguousarray(sw.output["w"]), F16))
+            return dict(weight=to_dev_T(np.ascontiguousarray(sw.output["w"]), T))
         parts = name.split(".")
         i, kind = int(parts[1]), parts[2]
         if kind == "attention_norm":
-            return to_dev_T(w.L[i]["attn_norm"], F16)
+            return to_dev_T(w.L[i]["attn_norm"], T)
         if kind == "ffn_norm":
-            return to_dev_T(w.L[i]["ffn_norm"], F16)
+            return to_dev_T(w.L[i]["ffn_norm"], T)
         return lin(sw.L[i][kind])
 
     m.load_tm_weights(provider)

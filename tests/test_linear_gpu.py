@@ -42,7 +42,7 @@ class DevLinear:
             ds, dz = to_dev_T(scales, dtype), to_dev_T(zeros, dtype)
             L.check(lib.b200_linear_prepare(C.byref(self.d), qw.data_ptr(), ds.data_ptr(), dz.data_ptr(), 0,
                                             self.prepared.data_ptr(), st), "prepare")
-        elif fmt == 2:
+        elif fmt in (2, 3):
             dw = torch.from_numpy(np.ascontiguousarray(weight)).cuda()           # e4m3 bits, uint8
             ds = torch.from_numpy(np.ascontiguousarray(scales, np.float32)).cuda()
             L.check(lib.b200_linear_prepare(C.byref(self.d), dw.data_ptr(), ds.data_ptr(), None, transposed,

@@ -1,0 +1,156 @@
+"""GPU parity tests that have not had their first run on a device (see conftest.pending_first_gpu_run).
+Run with  B200_RUN_UNVERIFIED=1 python -m pytest tests/test_zz_pending_gpu.py -m gpu ;  once green they move into the
+test file of the kernel they cover."""
+import numpy as np
+import pytest
+
+from oracle import linear as OL
+from oracle.numerics import BF16, F16, rn
+
+from conftest import pending_first_gpu_run
+from test_linear_gpu import DevLinear, _assert_close
+
+pytestmark = [pytest.mark.gpu, pending_first_gpu_run]
+
+
+def _fp8_cols(rng, K, N):
+    """Random weights quantised to e4m3 with one scale per (128-k group, column)."""
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    scale = (np.abs(w.reshape(K // 128, 128, N)).max(axis=1) / 448.0).astype(np.float32)
+    w8 = OL.f32_to_e4m3(w / np.repeat(scale, 128, 0))
+    return w8, scale
+
+
+@pytest.mark.parametrize("dtype", [BF16, F16])
+@pytest.mark.parametrize("shape", [(1024, 256), (512, 384), (4096, 4096)])
+@pytest.mark.parametrize("m", [1, 64])
+def test_fp8_per_column_scales(lib, shape, m, dtype):
+    """weight_format 3: fp8 e4m3 with scales f32 [K/128, N]; same arithmetic as format 2
+    (w = T(e4m3) *_T T(scale), transform.h:92-97)."""
+    K, N = shape
+    rng = np.random.default_rng(K + N + m)
+    w8, scale = _fp8_cols(rng, K, N)
+    lin = DevLinear(lib, K, N, 3, dtype, w8, scales=scale)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), dtype)
+    got = lin.forward(x)
+    ref = OL.linear(x, OL.dequant_fp8_cols(w8, scale, 128, dtype), dtype)
+    _assert_close(got, ref, atol=2e-4 if dtype == F16 else 2e-3, rtol=2e-3 if dtype == F16 else 1.6e-2)
+    lin_t = DevLinear(lib, K, N, 3, dtype, np.ascontiguousarray(w8.T), scales=scale, transposed=1)
+    assert (lin_t.prepared == lin.prepared).all()
+
+
+def test_fp8_block_scales_expanded_equal_format_2(lib):
+    """A checkpoint's 128x128 block scales expanded along N must give bit-identical outputs through format 3."""
+    K, N, m = 2048, 1024, 48
+    rng = np.random.default_rng(5)
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    blk = (np.abs(w.reshape(K // 128, 128, N // 128, 128)).max(axis=(1, 3)) / 448.0).astype(np.float32)
+    w8 = OL.f32_to_e4m3(w / np.repeat(np.repeat(blk, 128, 0), 128, 1))
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), BF16)
+    y2 = DevLinear(lib, K, N, 2, BF16, w8, scales=blk).forward(x)
+    y3 = DevLinear(lib, K, N, 3, BF16, w8, scales=np.repeat(blk, 128, 1)).forward(x)
+    assert np.array_equal(y2, y3)
+
+
+def test_fp8_gated_silu_on_interleaved_columns(lib):
+    """Fused gate|up with element interleave -- impossible with 128-wide N blocks, the reason format 3 exists."""
+    K, I, m = 2048, 1024, 32
+    rng = np.random.default_rng(6)
+    g8, gs = _fp8_cols(rng, K, I)
+    u8, us = _fp8_cols(rng, K, I)
+    w8 = np.stack([g8, u8], -1).reshape(K, 2 * I)
+    sc = np.stack([gs, us], -1).reshape(K // 128, 2 * I)
+    lin = DevLinear(lib, K, 2 * I, 3, BF16, w8, scales=sc)
+    x = rn(rng.standard_normal((m, K)).astype(np.float32), BF16)
+    got = lin.forward(x, epilogue=1)
+    ref = OL.linear_gated_silu(x, OL.dequant_fp8_cols(w8, sc, 128, BF16), BF16)
+    _assert_close(got, ref, atol=2e-3, rtol=1.6e-2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# whole decode step in bf16: fp8 weights (Llama-3-70B FP8 is BASELINE config C5) and dense bf16 weights
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kv_bits", [8, 16])
+@pytest.mark.parametrize("fmt", ["fp8", "fp16"])
+def test_decode_step_bf16_matches_oracle(kv_bits, fmt):
+    """Same protocol as test_decode_step_gpu.test_decode_step_matches_oracle with T = bf16.  Bars: bf16 keeps 8
+    significand bits (8x the fp16 rounding), so logits |diff| <= 3.2e-2 and token ids must agree wherever the oracle's
+    top-1/top-2 margin exceeds twice that."""
+    import torch
+    from oracle import attention as OA
+    from oracle.decode_step import TinyWeights, decode_step
+    from harness import from_dev_T
+    from test_decode_step_gpu import build_device_model
+    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, dtype=BF16, seed=kv_bits)
+    hist = np.array([0, 5, 64, 130, 311], np.int32)
+    B = len(hist)
+    rng = np.random.default_rng(1)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
+    layout = OA.KvLayout(2, 64, 128, kv_bits)
+    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
+    nblk = sum(blocks_per) + 2
+    cache = OA.PagedKvCache(nblk, w.layers, layout, BF16)
+    perm = rng.permutation(nblk)
+    tables, o = [], 0
+    for n in blocks_per:
+        tables.append(perm[o:o + n].tolist())
+        o += n
+    for l in range(w.layers):
+        for b in range(B):
+            h = int(hist[b])
+            if h:
+                k = OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), BF16)
+                v = OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), BF16)
+                OA.process_kv(cache, tables[b], l, 0, k, v, rope)
+    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
+
+    m = build_device_model(w, 0 if kv_bits == 16 else kv_bits, max_batch=8)
+    pool = torch.from_numpy(cache.pool.copy()).cuda()
+    ptrs = torch.tensor([pool.data_ptr() + int(b) * cache.block_bytes for t in tables for b in t], dtype=torch.int64,
+                        device="cuda")
+    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
+    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
+    d_tok = torch.from_numpy(tokens).cuda()
+    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
+    m.decode_step(batch=B, token_ids=d_tok, cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs, cu_block_nums=cu_blocks,
+                  out_tokens=d_out, max_k_len=int(hist.max()) + 1)
+    torch.cuda.synchronize()
+    got_logits = from_dev_T(m.logits(B), BF16)
+    got_tokens = d_out.cpu().numpy()
+    ref_logits, ref_tokens = decode_step(w, tokens, cache, tables, hist, rope)
+    tol = 3.2e-2
+    err = np.abs(got_logits - ref_logits)
+    assert err.max() <= tol, err.max()
+    srt = np.sort(ref_logits, -1)
+    margin = srt[:, -1] - srt[:, -2]
+    for b in range(B):
+        if margin[b] > 2 * tol:
+            assert got_tokens[b] == ref_tokens[b]
+        else:
+            assert ref_logits[b, got_tokens[b]] >= srt[b, -1] - 2 * tol
+
+
+def test_synthetic_fp8_model_runs_and_is_deterministic():
+    """DecodeModel.load_synthetic for an fp8 spec (the bench path of config C5): finite logits, identical across runs."""
+    import torch
+    from lmdeploy_b200.turbomind import DecodeModel, KvCachePool, ModelSpec
+    spec = ModelSpec("tiny-fp8", "llama", 1024, 2, 8, 2, 2048, 2048, 5e5, weight_format="fp8", dtype="bf16")
+    outs = []
+    for _ in range(2):
+        m = DecodeModel(spec, quant_policy=8, max_batch=4)
+        m.load_synthetic(0)
+        pool = KvCachePool(8, spec.layers, 2, 128, 64, 8)
+        tables = [pool.allocate(2) for _ in range(4)]
+        ptrs = torch.tensor([pool.ptr(b) for t in tables for b in t], dtype=torch.int64, device="cuda")
+        cu_blocks = torch.arange(5, dtype=torch.int32, device="cuda") * 2
+        cu = torch.arange(5, dtype=torch.int32, device="cuda")
+        tok = torch.tensor([1, 2, 3, 4], dtype=torch.int32, device="cuda")
+        out = torch.zeros(4, dtype=torch.int32, device="cuda")
+        m.decode_step(batch=4, token_ids=tok, cu_q_len=cu, cu_k_len=cu.clone(), block_ptrs=ptrs, cu_block_nums=cu_blocks,
+                      out_tokens=out, max_k_len=1)
+        torch.cuda.synchronize()
+        lg = m.logits(4).float().cpu()
+        assert torch.isfinite(lg).all() and lg.abs().max() > 0
+        outs.append((lg, out.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
