@@ -160,6 +160,15 @@ struct Plan {
 //     shared-memory / TMEM budget spent on ring depth (the pipeline, not a second CTA, hides the latency);
 //   * otherwise one n-tile per CTA (N not a multiple of 256, dense weights), also one CTA per SM;
 //   * K is split over 1/2/4/8 co-resident CTAs (largest count that fits one wave, every CTA >= 4 K-groups).
+#ifdef B200_GEMM_TOOL
+// tools/gemm_sweep.cu compiles this TU with -DB200_GEMM_TOOL to measure the plan space: fields > 0 replace the
+// heuristic's choice.  Never compiled into the product library.
+struct PlanOverride {
+    int tiles, splits, nw, nx;
+};
+static PlanOverride g_plan_override{};
+#endif
+
 static Plan make_plan(int fmt, int MT, int N, int K)
 {
     const int WB     = block_bytes_of(fmt);
@@ -167,6 +176,11 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     const int XB     = MT * 256;
     Plan      pl{};
     pl.tiles         = (fmt != kDense && N % (2 * kBN) == 0) ? 2 : 1;
+#ifdef B200_GEMM_TOOL
+    if (g_plan_override.tiles > 0 && fmt != kDense && N % (kBN * g_plan_override.tiles) == 0) {
+        pl.tiles = g_plan_override.tiles;
+    }
+#endif
     const bool two_per_sm = false;  // 640-thread CTAs at ~90 registers: one CTA per SM in every configuration
     const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
     const int  slots = 148 * (two_per_sm ? 2 : 1);
@@ -176,6 +190,11 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4) {
         pl.splits *= 2;
     }
+#ifdef B200_GEMM_TOOL
+    if (g_plan_override.splits > 0) {
+        pl.splits = g_plan_override.splits;
+    }
+#endif
     const int budget = (two_per_sm ? 113 : 224) * 1024 - 1024;
     const int wslot  = WB_pad * pl.tiles;
     // both rings want ~5-6 slots in flight (each loop is ~2.5-3k cycles of latency per slot)
@@ -185,6 +204,11 @@ static Plan make_plan(int fmt, int MT, int N, int K)
         pl.nw = 3;
         pl.nx = std::max(2, std::min(kMaxX, (budget - pl.nw * wslot) / XB));
     }
+#ifdef B200_GEMM_TOOL
+    if (g_plan_override.nw > 0 && g_plan_override.nx > 0) {
+        pl.nw = std::min(kMaxW, g_plan_override.nw), pl.nx = std::min(kMaxX, g_plan_override.nx);
+    }
+#endif
     pl.smem = pl.nw * wslot + pl.nx * XB;
     const int d_cols = (MT <= 64 ? 64 : 128) * pl.tiles;
     if (fmt == kDense) {

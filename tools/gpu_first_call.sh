@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of a round: everything that was written or changed without a device gets its first run, each step under
+# its own timeout so one hang cannot eat the call.  Outputs land in gpurun_out/.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+set -u
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+run() { # name, timeout seconds, command...
+    local name=$1 t=$2; shift 2
+    echo "=== $name"
+    timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
+    echo "exit $? ($name)"; tail -n 6 "gpurun_out/$name.log"
+}
+run verified_suite 900 python -m pytest tests -x -q -m gpu
+B200_RUN_UNVERIFIED=1 run pending_suite 300 python -m pytest tests/test_zz_pending_gpu.py -q -m gpu
+[ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
+[ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
+run bench 420 python bench.py
