@@ -15,4 +15,5 @@ run verified_suite 900 python -m pytest tests -x -q -m gpu
 B200_RUN_UNVERIFIED=1 run pending_suite 300 python -m pytest tests/test_zz_pending_gpu.py -q -m gpu
 [ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
 [ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
+[ -x build/tma_issue_rate ] && run tma_issue_rate 120 build/tma_issue_rate
 run bench 420 python bench.py
