@@ -156,6 +156,18 @@ B200_API int b200_decode_attention(const b200_attention_params* params);
  * sequence into the paged cache.  Same argument block; `q`, `out` are ignored. */
 B200_API int b200_process_kv(const b200_attention_params* params);
 
+/* Prefill ("context") attention of a chunk of q_len >= 1 new tokens per sequence: causal over keys
+ * [0, history_len + i] for query i.  Replaces, for that chunk, invokeProcessKV_v2 + invokeFlattenKV_v2
+ * (kernels/attention/kv_cache_utils_v2.cu:18-420) + dispatchAttention<T> (kernels/attention/attention.cu,
+ * attention_universal.h:355-553 with the prefill mainloop): the call (1) adds bias, applies RoPE to q and k, quantises
+ * k/v and stores them at positions [history_len, history_len + q_len) of the pages, (2) attends each query over the
+ * pages (de-quantised on the fly) on tcgen05 tensor cores.  Same argument block as decode; cu_q_len / cu_k_len give
+ * q_len and history_len + q_len per sequence; `out` is token-major [token_num, num_heads * 128] (out_packed_mt must be
+ * 0); workspace = b200_prefill_attention_workspace_bytes(token_num, num_heads); `plan`, `rope_table`, `max_k_len`
+ * are not used. */
+B200_API size_t b200_prefill_attention_workspace_bytes(int token_num, int num_heads);
+B200_API int b200_prefill_attention(const b200_attention_params* params);
+
 /* Number of CTAs the attention kernel launches on the current device (for tests / profiling). */
 B200_API int b200_decode_attention_grid(int quant_policy, int dtype);
 

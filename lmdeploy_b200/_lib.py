@@ -94,6 +94,9 @@ def load():
     lib.b200_decode_attention_plan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.b200_decode_attention.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_process_kv.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_prefill_attention.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_prefill_attention_workspace_bytes.restype = C.c_size_t
+    lib.b200_prefill_attention_workspace_bytes.argtypes = [C.c_int, C.c_int]
     lib.b200_decode_attention_grid.argtypes = [C.c_int, C.c_int]
     lib.b200_linear_prepared_bytes.restype = C.c_size_t
     lib.b200_linear_prepared_bytes.argtypes = [C.POINTER(LinearDesc)]

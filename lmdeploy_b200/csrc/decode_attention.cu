@@ -2,6 +2,7 @@
 #include "../../include/b200_turbomind.h"
 #include "decode_attention.cuh"
 #include "host_utils.h"
+#include "prefill_attention.cuh"
 
 #include <cmath>
 #include <mutex>
@@ -572,6 +573,57 @@ static int launch_decode(const b200_attention_params* a)
     return check_launch("decode_reduce_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------
+// prefill: prologue (bias + RoPE + KV quantise/store + rotated Q) then the tcgen05 causal attention kernel
+// ------------------------------------------------------------------------------------------------
+static size_t prefill_workspace_bytes(int token_num, int num_heads)
+{
+    return align_up((size_t)token_num * num_heads * kHeadDim * 2, 256);
+}
+
+template<class T, int KVBITS>
+static int launch_prefill(const b200_attention_params* a)
+{
+    cudaStream_t st = (cudaStream_t)a->stream;
+    if (!a->workspace || a->workspace_bytes < prefill_workspace_bytes(a->token_num, a->num_heads)) {
+        return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_prefill_attention_workspace_bytes)");
+    }
+    if (a->out_packed_mt > 0) {
+        return fail(B200_ERR_UNSUPPORTED, "prefill attention writes row-major output only");
+    }
+    const int G = a->num_heads / a->num_kv_heads;
+    if (G > kPfRows) {
+        return fail(B200_ERR_UNSUPPORTED, "GQA group size > 128");
+    }
+    void* q_rot = a->workspace;
+    if (int e = launch_prologue<T, KVBITS>(a, q_rot, st)) {
+        return e;
+    }
+    auto kern = prefill_attention_kernel<T, KVBITS>;
+    static std::once_flag once;  // per (T, KVBITS) instantiation
+    std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem); });
+    PrefillParams p{};
+    p.q_rot         = q_rot;
+    p.out           = a->out;
+    p.out_stride    = (int64_t)a->num_heads * kHeadDim;
+    p.block_ptrs    = (char**)a->block_ptrs;
+    p.cu_block_nums = a->cu_block_nums;
+    p.cu_q_len      = a->cu_q_len;
+    p.cu_k_len      = a->cu_k_len;
+    p.layer_offset  = a->layer_offset;
+    p.block_len     = a->block_len;
+    p.batch         = a->batch_size;
+    p.num_heads     = a->num_heads;
+    p.num_kv_heads  = a->num_kv_heads;
+    p.qk_scale      = a->inv_sqrt_dh;
+    // sequence lengths live on the device: the grid is the upper bound sum_b ceil(q_len_b / TQ) <= token_num / TQ + batch,
+    // surplus CTAs exit at once
+    const int TQ = kPfRows / G;
+    dim3      grid(a->token_num / TQ + a->batch_size, a->num_kv_heads);
+    launch_k(kern, dim3(grid), dim3(kPfThreads), (size_t)kPfSmem, st, p);
+    return check_launch("prefill_attention_kernel");
+}
+
 template<class F>
 static int dispatch(int dtype, int quant_policy, F&& f)
 {
@@ -638,6 +690,25 @@ extern "C" int b200_process_kv(const b200_attention_params* a)
     return dispatch(a->dtype, a->quant_policy, [&](auto t, auto bits) {
         using T = decltype(t);
         return launch_prologue<T, decltype(bits)::value>(a, nullptr, (cudaStream_t)a->stream);
+    });
+}
+
+extern "C" size_t b200_prefill_attention_workspace_bytes(int token_num, int num_heads)
+{
+    return prefill_workspace_bytes(token_num, num_heads);
+}
+
+extern "C" int b200_prefill_attention(const b200_attention_params* a)
+{
+    if (int e = validate(a, false)) {
+        return e;
+    }
+    if (a->token_num <= 0 || a->batch_size <= 0) {
+        return fail(B200_ERR_INVALID_ARG, "prefill: token_num and batch_size must be positive");
+    }
+    return dispatch(a->dtype, a->quant_policy, [&](auto t, auto bits) {
+        using T = decltype(t);
+        return launch_prefill<T, decltype(bits)::value>(a);
     });
 }
 

@@ -407,3 +407,46 @@ def process_kv(cache: PagedKvCache, block_table, layer, start, k, v, rope: RopeP
     k = apply_rope(k, np.broadcast_to(pos, (S, Hkv)), rope, dtype)
     for h in range(Hkv):
         cache.write_tokens(block_table, layer, h, start, k[:, h], f32(v[:, h]))
+
+
+# --------------------------------------------------------------------------------------
+# prefill (context) attention
+# --------------------------------------------------------------------------------------
+def prefill_attention(qkv, cache: PagedKvCache, block_tables, q_lens, k_lens, layer, num_heads, num_kv_heads,
+                      rope: RopeParam, inv_sqrt_dh=None, q_bias=None, k_bias=None, v_bias=None):
+    """Chunked causal prefill for one layer: the reference writes the chunk's K/V into the pages
+    (ProcessKV_v2, kv_cache_utils_v2.cu:18-210), reads them back de-quantised (FlattenKV_v2) and runs causal attention
+    over keys [0, history + i] for query i of the chunk (attention_universal.h:355-553 with the prefill mainloop;
+    same softmax arithmetic as decode).
+    qkv: [sum(q_lens), (Hq + 2 Hkv) * D] float32 exact in T, sequences concatenated; history_b = k_lens[b] - q_lens[b].
+    Returns out [sum(q_lens), Hq*D] float32 exact in T.  Mutates `cache`."""
+    dtype = cache.dtype
+    L = cache.layout
+    D = L.head_dim
+    if inv_sqrt_dh is None:
+        inv_sqrt_dh = np.float32(np.float32(1.4426950408889634) / np.float32(np.sqrt(np.float32(D))))
+    G = num_heads // num_kv_heads
+    T = qkv.shape[0]
+    out = np.zeros((T, num_heads, D), np.float32)
+    t0 = 0
+    for b, (ql, kl) in enumerate(zip(q_lens, k_lens)):
+        ql, kl = int(ql), int(kl)
+        hist = kl - ql
+        rows = qkv[t0:t0 + ql]
+        q = rows[:, : num_heads * D].reshape(ql, num_heads, D)
+        k = rows[:, num_heads * D: (num_heads + num_kv_heads) * D].reshape(ql, num_kv_heads, D)
+        v = rows[:, (num_heads + num_kv_heads) * D:].reshape(ql, num_kv_heads, D)
+        if q_bias is not None:
+            q = t_add(q, q_bias.reshape(1, num_heads, D), dtype)
+        pos = (hist + np.arange(ql))[:, None]
+        q = apply_rope(q, np.broadcast_to(pos, (ql, num_heads)), rope, dtype)
+        process_kv(cache, block_tables[b], layer, hist, k, v, rope, k_bias, v_bias)
+        for h in range(num_kv_heads):
+            K, V = cache.read_tokens(block_tables[b], layer, h, kl)
+            for i in range(ql):
+                n = hist + i + 1
+                for g in range(G):
+                    o, _, _, _ = softmax_pv(q[i, h * G + g], K[:n], V[:n], inv_sqrt_dh, dtype)
+                    out[t0 + i, h * G + g] = o
+        t0 += ql
+    return out.reshape(T, num_heads * D)
