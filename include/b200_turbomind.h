@@ -335,6 +335,12 @@ B200_API int b200_model_set_comm(b200_model* model, b200_comm* comm);
 /* internal activations for tests: 0 logits [max_batch, vocab], 1 residual, 2 last GEMM output, 3 qkv */
 B200_API void* b200_model_buffer(b200_model* model, int which);
 B200_API int b200_model_decode_step(b200_model* model, const b200_step_inputs* inputs, void* stream);
+/* Mixed step (chunked prefill, "dynamic split-fuse": unified_attention_layer.cc:310, 613-651): `token_num` rows,
+ * sequence b owns rows [cu_q_len[b], cu_q_len[b+1]) (its q_len new tokens, 1 for a decoding sequence);
+ * inputs->token_ids and out_tokens have token_num entries (the caller samples from the LAST row of each sequence);
+ * cu_k_len counts the new tokens; batch_size <= token_num <= max_batch; inputs->advance must be 0.  Attention runs
+ * through b200_prefill_attention, every other operator is row-wise and shared with b200_model_decode_step. */
+B200_API int b200_model_chunk_step(b200_model* model, const b200_step_inputs* inputs, int token_num, void* stream);
 B200_API int b200_step_advance(const int* token_ids, const int* out_tokens, int* cu_k_len, const uint8_t* finished,
                       int batch, void* stream);
 

@@ -146,6 +146,7 @@ def load():
     lib.b200_model_buffer.restype = C.c_void_p
     lib.b200_model_buffer.argtypes = [C.c_void_p, C.c_int]
     lib.b200_model_decode_step.argtypes = [C.c_void_p, C.POINTER(StepInputs), C.c_void_p]
+    lib.b200_model_chunk_step.argtypes = [C.c_void_p, C.POINTER(StepInputs), C.c_int, C.c_void_p]
     lib.b200_step_advance.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.b200_ipc_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
     lib.b200_ipc_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]

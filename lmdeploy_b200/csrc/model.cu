@@ -275,30 +275,29 @@ static void report_trace(b200_model* m, void* stream)
     fprintf(stderr, "\n");
 }
 
-extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in, void* stream)
+// One forward step over R token rows of B sequences.  Decode: R == B, one row per sequence.  Chunked prefill /
+// mixed step (`chunk`): sequence b owns rows [cu_q_len[b], cu_q_len[b+1]); the attention of the step runs through
+// b200_prefill_attention (causal over each sequence's pages), everything else is row-wise and identical.
+static int run_step(b200_model* m, const b200_step_inputs* in, int R, bool chunk, void* stream)
 {
-    if (!m || !in) {
-        return fail(B200_ERR_INVALID_ARG, "decode_step: NULL argument");
-    }
     const b200_model_config& c = m->cfg;
     const int                B = in->batch_size;
-    if (B <= 0 || B > c.max_batch) {
-        return fail(B200_ERR_INVALID_ARG, "decode_step: batch_size out of range");
-    }
     if (!m->embedding || !m->final_norm || !m->lm_head.prepared) {
         return fail(B200_ERR_STATE, "decode_step: model weights not set");
     }
-    const int MT      = round16(B);
+    const int MT      = round16(R);
     const int qkv_dim = (c.num_heads + 2 * c.num_kv_heads) * c.head_dim;
     const int es      = 2;
     const int L       = c.num_layers;
     void*     o_buf   = m->o_x[0] ? m->o_x[0] : m->o;   // wo output (exchange half 0 under TP)
     void*     o_buf2  = m->o_x[1] ? m->o_x[1] : m->o;   // w2 output (exchange half 1 under TP)
 
-    TRY_T(0, b200_embedding_lookup(m->residual, m->embedding, in->token_ids, B, c.hidden, c.embedding_rows, c.dtype, stream));
-    TRY_T(0, b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, B, c.hidden, c.norm_eps, c.dtype, stream));
-    TRY_T(0, b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
-    TRY_T(0, b200_rope_table(m->rope_table, &c.rope, in->cu_q_len, in->cu_k_len, B, B, stream));
+    TRY_T(0, b200_embedding_lookup(m->residual, m->embedding, in->token_ids, R, c.hidden, c.embedding_rows, c.dtype, stream));
+    TRY_T(0, b200_rmsnorm(m->xp, MT, m->residual, m->layers[0].attn_norm, R, c.hidden, c.norm_eps, c.dtype, stream));
+    if (!chunk) {
+        TRY_T(0, b200_decode_attention_plan(m->plan, in->cu_k_len, in->finished, B, stream));
+    }
+    TRY_T(0, b200_rope_table(m->rope_table, &c.rope, in->cu_q_len, in->cu_k_len, B, R, stream));
 
     for (int l = 0; l < L; ++l) {
         const LayerW& W = m->layers[l];
@@ -306,7 +305,7 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
             return fail(B200_ERR_STATE, "decode_step: layer weights not set");
         }
         // ---- attention block ----
-        TRY_T(1, b200_linear_forward_packed(&W.qkv, m->xp, MT, B, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        TRY_T(1, b200_linear_forward_packed(&W.qkv, m->xp, MT, R, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
         b200_attention_params a{};
         a.out    = m->attn_xp;
         a.q      = m->qkv;
@@ -316,18 +315,27 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
         a.cu_q_len = in->cu_q_len, a.cu_k_len = in->cu_k_len, a.finished = in->finished;
         a.block_ptrs = in->block_ptrs, a.cu_block_nums = in->cu_block_nums;
         a.layer_offset = l * in->layer_stride_bytes, a.block_len = c.block_len;
-        a.token_num = B, a.batch_size = B, a.max_k_len = in->max_k_len;
+        a.token_num = R, a.batch_size = B, a.max_k_len = in->max_k_len;
         a.num_heads = c.num_heads, a.num_kv_heads = c.num_kv_heads, a.size_per_head = c.head_dim;
         a.inv_sqrt_dh = c.inv_sqrt_dh, a.window_size = 0;
         a.rope = c.rope, a.quant_policy = c.quant_policy, a.dtype = c.dtype;
         a.workspace = m->attn_ws, a.workspace_bytes = m->attn_ws_bytes;
         a.plan = m->plan, a.rope_table = m->rope_table, a.out_packed_mt = MT, a.stream = stream;
-        TRY_T(2, b200_decode_attention(&a));
+        if (!chunk) {
+            TRY_T(2, b200_decode_attention(&a));
+        }
+        else {
+            // row-major into the (currently idle) GEMM output buffer, then into the packed layout the wo GEMM reads
+            const int attn_dim = c.num_heads * c.head_dim;
+            a.out = m->o, a.out_packed_mt = 0, a.plan = nullptr;
+            TRY_T(2, b200_prefill_attention(&a));
+            TRY_T(2, b200_pack_activations(m->o, attn_dim, R, attn_dim, MT, c.dtype, m->attn_xp, stream));
+        }
         // wo GEMM + AllreduceResidualRMSnorm #1 (unified_decoder.cc:278-287).  Single GPU: the residual add and the
         // RMSNorm are fused into the GEMM's split-K epilogue when the launch plan has one.
         bool fused1 = false;
         if (!m->comm && m->fuse_norm) {
-            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.wo, m->attn_xp, MT, B, m->residual, W.ffn_norm,
+            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.wo, m->attn_xp, MT, R, m->residual, W.ffn_norm,
                                                                        c.norm_eps, m->xp, MT, m->lin_ws, m->lin_ws_bytes,
                                                                        stream);
             if (rc == 0) {
@@ -338,23 +346,23 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
             }
         }
         if (!fused1) {
-            TRY_T(3, b200_linear_forward_packed(&W.wo, m->attn_xp, MT, B, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+            TRY_T(3, b200_linear_forward_packed(&W.wo, m->attn_xp, MT, R, o_buf, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
             if (m->comm) {
-                TRY_T(4, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B,
+                TRY_T(4, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, R,
                                                               c.hidden, c.norm_eps, c.dtype, stream));
             }
             else {
-                TRY_T(4, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, B, c.hidden, c.norm_eps,
+                TRY_T(4, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf, W.ffn_norm, nullptr, R, c.hidden, c.norm_eps,
                                                c.dtype, stream));
             }
         }
         // ---- FFN block ----
-        TRY_T(5, b200_linear_forward_packed(&W.w13, m->xp, MT, B, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
+        TRY_T(5, b200_linear_forward_packed(&W.w13, m->xp, MT, R, m->act_xp, c.inter_size, 1, MT, m->lin_ws, m->lin_ws_bytes,
                                        stream));
         const void* next_norm = (l + 1 < L) ? m->layers[l + 1].attn_norm : m->final_norm;
         bool        fused2    = false;
         if (!m->comm && m->fuse_norm) {
-            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.w2, m->act_xp, MT, B, m->residual, next_norm,
+            const int rc = b200_linear_forward_packed_residual_rmsnorm(&W.w2, m->act_xp, MT, R, m->residual, next_norm,
                                                                        c.norm_eps, m->xp, MT, m->lin_ws, m->lin_ws_bytes,
                                                                        stream);
             if (rc == 0) {
@@ -365,33 +373,58 @@ extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in,
             }
         }
         if (!fused2) {
-            TRY_T(6, b200_linear_forward_packed(&W.w2, m->act_xp, MT, B, o_buf2, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+            TRY_T(6, b200_linear_forward_packed(&W.w2, m->act_xp, MT, R, o_buf2, c.hidden, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
             if (m->comm) {
-                TRY_T(7, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B,
+                TRY_T(7, b200_comm_allreduce_residual_rmsnorm(m->comm, m->xp, MT, m->residual, o_buf2, next_norm, nullptr, R,
                                                               c.hidden, c.norm_eps, c.dtype, stream));
             }
             else {
-                TRY_T(7, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf2, next_norm, nullptr, B, c.hidden, c.norm_eps, c.dtype,
+                TRY_T(7, b200_residual_rmsnorm(m->xp, MT, m->residual, o_buf2, next_norm, nullptr, R, c.hidden, c.norm_eps, c.dtype,
                                                stream));
             }
         }
     }
     // PostEmbedding (language_model.cc:285-335) + greedy sampling
-    TRY_T(8, b200_linear_forward_packed(&m->lm_head, m->xp, MT, B, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
+    TRY_T(8, b200_linear_forward_packed(&m->lm_head, m->xp, MT, R, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
                                    stream));
     if (in->out_tokens) {
         if (m->comm && c.tp_size > 1) {
-            TRY_T(9, b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, B, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, R, c.vocab, c.dtype, stream));
         }
         else {
-            TRY_T(9, b200_argmax(in->out_tokens, m->logits, B, c.vocab, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_argmax(in->out_tokens, m->logits, R, c.vocab, c.vocab, c.dtype, stream));
         }
     }
-    if (in->advance) {
+    if (in->advance && !chunk) {
         TRY_T(9, b200_step_advance(in->token_ids, in->out_tokens, (int*)in->cu_k_len, in->finished, B, stream));
     }
     if (m->trace_on) {
         report_trace(m, stream);
     }
     return 0;
+}
+
+extern "C" int b200_model_decode_step(b200_model* m, const b200_step_inputs* in, void* stream)
+{
+    if (!m || !in) {
+        return fail(B200_ERR_INVALID_ARG, "decode_step: NULL argument");
+    }
+    if (in->batch_size <= 0 || in->batch_size > m->cfg.max_batch) {
+        return fail(B200_ERR_INVALID_ARG, "decode_step: batch_size out of range");
+    }
+    return run_step(m, in, in->batch_size, false, stream);
+}
+
+extern "C" int b200_model_chunk_step(b200_model* m, const b200_step_inputs* in, int token_num, void* stream)
+{
+    if (!m || !in) {
+        return fail(B200_ERR_INVALID_ARG, "chunk_step: NULL argument");
+    }
+    if (in->batch_size <= 0 || token_num < in->batch_size || token_num > m->cfg.max_batch) {
+        return fail(B200_ERR_INVALID_ARG, "chunk_step: need batch_size <= token_num <= max_batch rows");
+    }
+    if (in->advance) {
+        return fail(B200_ERR_UNSUPPORTED, "chunk_step: device-side advance is a decode-only feature");
+    }
+    return run_step(m, in, token_num, true, stream);
 }

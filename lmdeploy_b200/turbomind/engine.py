@@ -4,6 +4,7 @@ Mirrors lmdeploy/turbomind/turbomind.py (TurboMind :108-566, TurboMindInstance :
 weights + KV pool, instances that stream tokens for a session.  The model forward is the native decode step
 (libb200tm.so); scheduling is lmdeploy_b200.turbomind.scheduler."""
 import asyncio
+import os
 import threading
 from typing import List, Optional
 
@@ -42,8 +43,13 @@ class TurboMind:
                 num_blocks = int(free * cfg.cache_max_entry_count) // (self.model.layer_bytes * spec.layers)
         self.pool = KvCachePool(num_blocks, spec.layers, self.model.kv_heads, spec.head_dim, self.block_len,
                                 cfg.quant_policy, device=dev)
+        # Chunked prefill (several prompt tokens of a sequence per step through b200_model_chunk_step) is opt-in until
+        # the prefill attention kernel has had its GPU parity run: B200_CHUNKED_PREFILL=<tokens per sequence per step>.
+        # Default: one prompt token per step through the decode kernel (exact).
+        chunk = int(os.environ.get("B200_CHUNKED_PREFILL", "1"))
         self.scheduler = Scheduler(max_batch=self.max_batch, block_len=self.block_len, num_blocks=num_blocks,
-                                   session_len=self.session_len, prefix_caching=cfg.enable_prefix_caching)
+                                   session_len=self.session_len, prefix_caching=cfg.enable_prefix_caching,
+                                   prefill_chunk=min(chunk, cfg.max_prefill_token_num), token_budget=self.max_batch)
         B = self.max_batch
         self._max_blocks = (self.session_len + self.block_len - 1) // self.block_len
         self.d_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
@@ -55,6 +61,7 @@ class TurboMind:
         self.h_tokens = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.h_out = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.h_cu_k = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self.h_cu_q = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
         self.h_cu_blocks = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
         self.h_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64).pin_memory()
         self._lock = threading.Lock()
@@ -88,27 +95,33 @@ class TurboMind:
         if not batch:
             return []
         B = len(batch)
-        ptrs, nblk = [], [0]
+        ptrs, nblk, cu_q = [], [0], [0]
         self.h_cu_k[0] = 0
         acc = 0
         for i, s in enumerate(batch):
-            self.h_tokens[i] = s.next_input()
-            acc += s.cached + 1                      # keys visible to this step: cached history + the fed token
+            toks = s.next_inputs()
+            self.h_tokens[cu_q[-1]:cu_q[-1] + len(toks)] = torch.tensor(toks, dtype=torch.int32)
+            cu_q.append(cu_q[-1] + len(toks))
+            acc += s.cached + len(toks)              # keys visible to this step: cached history + the fed tokens
             self.h_cu_k[i + 1] = acc
             ptrs += [self.pool.ptr(b) for b in s.blocks]
             nblk.append(len(ptrs))
+        T = cu_q[-1]                                 # token rows of the step (== B when every sequence feeds one)
+        self.h_cu_q[:B + 1] = torch.tensor(cu_q, dtype=torch.int32)
         self.h_cu_blocks[:B + 1] = torch.tensor(nblk, dtype=torch.int32)
         self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
-        self.d_tokens[:B].copy_(self.h_tokens[:B], non_blocking=True)
+        self.d_tokens[:T].copy_(self.h_tokens[:T], non_blocking=True)
+        self.d_cu_q[:B + 1].copy_(self.h_cu_q[:B + 1], non_blocking=True)
         self.d_cu_k[:B + 1].copy_(self.h_cu_k[:B + 1], non_blocking=True)
         self.d_cu_blocks[:B + 1].copy_(self.h_cu_blocks[:B + 1], non_blocking=True)
         self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
         self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
                                block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
-                               max_k_len=max(s.cached for s in batch) + 1)
-        self.h_out[:B].copy_(self.d_out[:B], non_blocking=True)
+                               max_k_len=max(s.cached + s.step_tokens for s in batch), token_num=T)
+        self.h_out[:T].copy_(self.d_out[:T], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return sched.update(batch, self.h_out[:B].tolist())
+        out = self.h_out[:T].tolist()
+        return sched.update(batch, [out[cu_q[i + 1] - 1] for i in range(B)])     # sample = last row of each sequence
 
     def get_schedule_metrics(self, index=0):
         """ScheduleMetrics of this rank (TurboMind.get_schedule_metrics, lmdeploy/turbomind/turbomind.py)."""

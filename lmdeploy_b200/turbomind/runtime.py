@@ -227,8 +227,10 @@ class DecodeModel:
         L.check(self.lib.b200_model_set_comm(self.handle, comm_handle), "set_comm")
 
     def decode_step(self, *, batch, token_ids, cu_q_len, cu_k_len, block_ptrs, cu_block_nums, out_tokens,
-                    max_k_len, finished=None, advance=False, stream=None):
-        """All arguments are device tensors (int32 / int64 for block_ptrs / uint8 for finished)."""
+                    max_k_len, finished=None, advance=False, stream=None, token_num=None):
+        """All arguments are device tensors (int32 / int64 for block_ptrs / uint8 for finished).
+        token_num > batch: a mixed prefill/decode step (b200_model_chunk_step) -- token_ids / out_tokens have token_num
+        rows and cu_q_len gives each sequence's rows."""
         si = L.StepInputs()
         si.batch_size = batch
         si.token_ids, si.cu_q_len, si.cu_k_len = token_ids.data_ptr(), cu_q_len.data_ptr(), cu_k_len.data_ptr()
@@ -239,6 +241,9 @@ class DecodeModel:
         si.out_tokens = out_tokens.data_ptr() if out_tokens is not None else None
         si.advance = 1 if advance else 0
         st = (stream or torch.cuda.current_stream()).cuda_stream
+        if token_num is not None and token_num != batch:
+            L.check(self.lib.b200_model_chunk_step(self.handle, C.byref(si), int(token_num), st), "b200_model_chunk_step")
+            return
         L.check(self.lib.b200_model_decode_step(self.handle, C.byref(si), st), "b200_model_decode_step")
 
     def logits(self, batch):

@@ -5,9 +5,12 @@ Plays the role of Engine::Impl::InternalThreadEntry / Scheduler::Schedule in the
 waiting requests are admitted while batch slots and KV blocks are available, a sequence gets a new block when it
 crosses a block boundary, finished sequences are retired and their blocks returned.
 
-Prompt tokens are consumed through the same decode step one token per step ("prefill-by-decode"): the decode
-kernel appends K/V for the token it is given, so feeding prompt tokens reproduces causal prefill exactly.  A tiled
-prefill attention kernel is SURVEY section 8f rank 1 ("next"), not part of this hot path.
+Prompt tokens are consumed through the same step as decode tokens.  By default one prompt token per step
+("prefill-by-decode": the decode kernel appends K/V for the token it is given, so feeding prompt tokens reproduces
+causal prefill exactly).  With `prefill_chunk` > 1 a sequence still in its prompt feeds up to that many tokens in one
+step, mixed with the decoding sequences of the batch (the reference's chunked prefill / "dynamic split-fuse",
+unified_attention_layer.cc:310, 613-651); the step's token count never exceeds `token_budget` -- the row capacity of
+the device step (b200_model_decode_step handles <= 128 rows).
 
 Prefix caching (TurbomindEngineConfig.enable_prefix_caching, lmdeploy/messages.py:238-239; the reference indexes
 logical blocks in src/turbomind/engine/prefix_trie.h): K/V of position p depends only on tokens [0, p], so a FULL block
@@ -37,6 +40,7 @@ class Sequence:
     finished: bool = False
     finish_reason: Optional[str] = None
     reused_tokens: int = 0        # prompt tokens served from the prefix cache (never fed)
+    step_tokens: int = 1          # tokens this sequence feeds in the step being formed / executed
     chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
 
     def token_at(self, pos):
@@ -46,6 +50,12 @@ class Sequence:
         if self.fed < len(self.prompt):
             return self.prompt[self.fed]
         return self.generated[-1]
+
+    def next_inputs(self):
+        """The `step_tokens` tokens of this step (more than one only inside the prompt)."""
+        if self.fed < len(self.prompt):
+            return self.prompt[self.fed:self.fed + self.step_tokens]
+        return [self.generated[-1]]
 
     @property
     def in_prefill(self):
@@ -154,8 +164,11 @@ class PrefixCache:
 
 
 class Scheduler:
-    def __init__(self, *, max_batch, block_len, num_blocks, session_len, prefix_caching=False):
+    def __init__(self, *, max_batch, block_len, num_blocks, session_len, prefix_caching=False, prefill_chunk=1,
+                 token_budget=None):
         self.max_batch, self.block_len, self.session_len = max_batch, block_len, session_len
+        self.prefill_chunk = max(1, int(prefill_chunk))
+        self.token_budget = max(max_batch, token_budget or max_batch)
         self.alloc = BlockAllocator(num_blocks)
         self.prefix = PrefixCache(block_len) if prefix_caching else None
         if self.prefix is not None:
@@ -189,7 +202,8 @@ class Scheduler:
         return (upto_tokens + self.block_len - 1) // self.block_len - len(seq.blocks)
 
     def schedule(self):
-        """Form the batch of this step.  Returns the list of sequences that run (each feeds one token)."""
+        """Form the batch of this step.  Returns the sequences that run; each feeds `step_tokens` tokens (1 unless it
+        is inside its prompt and prefill_chunk > 1)."""
         self.tick += 1
         # retire
         still = []
@@ -229,21 +243,37 @@ class Scheduler:
             s.blocks += got
             self.waiting.popleft()
             self.active.append(s)
-        return [s for s in self.active if not s.finished]
+        batch = [s for s in self.active if not s.finished]
+        budget = self.token_budget - len(batch)
+        for s in batch:
+            s.step_tokens = 1
+            rem = len(s.prompt) - s.fed
+            if self.prefill_chunk > 1 and rem > 1 and budget > 0:
+                extra = min(self.prefill_chunk - 1, rem - 1, budget)
+                need = self._blocks_needed(s, s.cached + 1 + extra)
+                got = self.alloc.allocate(need) if need > 0 else []
+                if got is None:
+                    continue               # no room for a longer chunk now: one token this step
+                s.blocks += got
+                s.step_tokens += extra
+                budget -= extra
+        return batch
 
     def update(self, batch: List[Sequence], sampled: List[int]):
-        """Account for one executed step: every sequence cached one more token; sequences past their prompt
-        emit the sampled token."""
+        """Account for one executed step: every sequence cached its `step_tokens` tokens; `sampled[i]` is the token
+        sampled from the LAST row of sequence i, emitted once the sequence is past its prompt."""
         events = []
         for s, tok in zip(batch, sampled):
-            s.cached += 1
-            if s.fed < len(s.prompt):
-                s.fed += 1
-            if self.prefix is not None and s.cached % self.block_len == 0:
-                j = s.cached // self.block_len - 1           # the block that just filled
-                if len(s.chain) == j:
-                    toks = [s.token_at(p) for p in range(j * self.block_len, s.cached)]
-                    s.chain.append(self.prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
+            n = s.step_tokens
+            before = s.cached
+            s.cached += n
+            s.fed = min(len(s.prompt), s.fed + n)
+            s.step_tokens = 1
+            if self.prefix is not None:
+                for j in range(before // self.block_len, s.cached // self.block_len):       # blocks that just filled
+                    if len(s.chain) == j:
+                        toks = [s.token_at(p) for p in range(j * self.block_len, (j + 1) * self.block_len)]
+                        s.chain.append(self.prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
             if s.fed < len(s.prompt):
                 continue                   # still consuming the prompt; sampled token is discarded
             if s.max_new_tokens == 0:

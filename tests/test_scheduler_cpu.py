@@ -262,3 +262,110 @@ def test_cancel_and_retire_return_references():
     sched.schedule()
     m = sched.metrics()
     assert m["active_blocks"] == 0 and m["free_blocks"] + m["cached_blocks"] == 8 and m["total_seqs"] == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# chunked prefill (several prompt tokens of a sequence per step, mixed with decoding sequences)
+# ---------------------------------------------------------------------------------------------------------------
+class FakeChunkModel(FakeKvModel):
+    """FakeKvModel for steps in which a sequence feeds `step_tokens` tokens: writes them at positions cached ..
+    cached + n - 1 and samples from what the LAST of them can see (causal)."""
+
+    def step(self, batch):
+        rows = 0
+        for s in batch:
+            toks = s.next_inputs()
+            assert len(toks) == s.step_tokens >= 1
+            for i, t in enumerate(toks):
+                pos = s.cached + i
+                self.store[s.blocks[pos // self.block_len]][pos % self.block_len] = t
+            rows += len(toks)
+            self.fed += len(toks)
+        self.max_rows = max(getattr(self, "max_rows", 0), rows)
+        out = []
+        for s in batch:
+            h = 1469598103934665603
+            for p in range(s.cached + s.step_tokens):
+                t = self.store[s.blocks[p // self.block_len]][p % self.block_len]
+                assert t is not None
+                h = ((h ^ (t + 1)) * 1099511628211) % (1 << 64)
+            out.append(h % self.vocab)
+        return out
+
+
+def run_chunked(prompts, *, prefill_chunk, token_budget=None, prefix_caching=False, max_batch=4, block_len=4, num_blocks=64,
+                max_new=5):
+    sched = Scheduler(max_batch=max_batch, block_len=block_len, num_blocks=num_blocks, session_len=4096,
+                      prefix_caching=prefix_caching, prefill_chunk=prefill_chunk, token_budget=token_budget)
+    model = FakeChunkModel(num_blocks, block_len)
+    seqs = [Sequence(session_id=i + 1, prompt=list(p), max_new_tokens=max_new, stop_token_ids=[], ignore_eos=True,
+                     eos_id=None) for i, p in enumerate(prompts)]
+    for s in seqs:
+        sched.add(s)
+    steps = 0
+    while sched.has_work:
+        batch = sched.schedule()
+        assert batch
+        assert sum(s.step_tokens for s in batch) <= sched.token_budget
+        for s in batch:
+            assert len(s.blocks) * block_len >= s.cached + s.step_tokens
+            assert s.step_tokens == 1 or s.fed + s.step_tokens <= len(s.prompt)
+        sched.update(batch, model.step(batch))
+        steps += 1
+    sched.schedule()
+    assert sched.alloc.num_free + (sched.prefix.num_idle if sched.prefix else 0) == num_blocks
+    return [list(s.generated) for s in seqs], steps, model
+
+
+PROMPTS = [list(range(10, 10 + 23)), [7], list(range(50, 50 + 9)), list(range(10, 10 + 17)) + [99, 98]]
+
+
+def test_chunked_prefill_gives_the_same_tokens_in_fewer_steps():
+    base, steps1, _ = run_chunked(PROMPTS, prefill_chunk=1)
+    for chunk in (2, 5, 8, 64):
+        got, steps, model = run_chunked(PROMPTS, prefill_chunk=chunk, token_budget=16)
+        assert got == base, chunk
+        assert steps < steps1
+        assert model.max_rows <= 16
+    # budget == max_batch leaves no room for longer chunks once the batch is full, but still terminates correctly
+    got, _, model = run_chunked(PROMPTS, prefill_chunk=8, token_budget=4)
+    assert got == base and model.max_rows <= 4
+
+
+def test_chunked_prefill_with_prefix_cache_publishes_every_filled_block():
+    base, _, _ = run_chunked(PROMPTS, prefill_chunk=1)
+    got, _, _ = run_chunked(PROMPTS, prefill_chunk=8, token_budget=32, prefix_caching=True)
+    assert got == base
+    # second identical wave on one scheduler: the shared 16-token prefix of prompts 0 and 3 and every full block of each
+    # prompt must be found, although they were written several blocks per step
+    sched = Scheduler(max_batch=2, block_len=4, num_blocks=64, session_len=4096, prefix_caching=True, prefill_chunk=8,
+                      token_budget=16)
+    model = FakeChunkModel(64, 4)
+    outs = []
+    for wave in range(2):
+        seqs = [Sequence(session_id=wave * 10 + i, prompt=list(p), max_new_tokens=3, stop_token_ids=[], ignore_eos=True,
+                         eos_id=None) for i, p in enumerate(PROMPTS)]
+        for s in seqs:
+            sched.add(s)
+        while sched.has_work:
+            b = sched.schedule()
+            sched.update(b, model.step(b))
+        sched.schedule()
+        outs.append([list(s.generated) for s in seqs])
+        reused = [s.reused_tokens for s in seqs]
+    assert outs[0] == outs[1]
+    assert reused == [((len(p) - 1) // 4) * 4 for p in PROMPTS]
+
+
+def test_chunk_never_swallows_the_last_prompt_token_early():
+    # the step that feeds the last prompt token is the one whose sample is kept; a chunk may end exactly there
+    sched = Scheduler(max_batch=1, block_len=4, num_blocks=8, session_len=64, prefill_chunk=4, token_budget=8)
+    s = Sequence(session_id=1, prompt=[1, 2, 3, 4, 5, 6], max_new_tokens=2, stop_token_ids=[], ignore_eos=True, eos_id=None)
+    sched.add(s)
+    sizes = []
+    model = FakeChunkModel(8, 4)
+    while sched.has_work:
+        b = sched.schedule()
+        sizes.append(b[0].step_tokens)
+        sched.update(b, model.step(b))
+    assert sizes == [4, 2, 1] and len(s.generated) == 2
