@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round: everything that was written or changed without a device gets its first run, each step under
 # its own timeout so one hang cannot eat the call.  Outputs land in gpurun_out/.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+#   bash tools/build_tools.sh && gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
@@ -16,4 +16,5 @@ B200_RUN_UNVERIFIED=1 run pending_suite 300 python -m pytest tests/test_zz_pendi
 [ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
 [ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
 [ -x build/tma_issue_rate ] && run tma_issue_rate 120 build/tma_issue_rate
+[ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
 run bench 420 python bench.py

@@ -13,7 +13,7 @@ constexpr int M = 128, N = 16, K = 32;
 __global__ void __launch_bounds__(128) probe(const half* A, const half* B, float* D, int variant)
 {
     __shared__ __align__(128) uint8_t sA[M * K * 2];
-    __shared__ __align__(128) uint8_t sB[N * K * 2];
+    __shared__ __align__(128) uint8_t sB[N * K * 2 + 256];  // + room for the padded-stride variants
     __shared__ uint64_t               bar;
     __shared__ uint32_t               tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -22,9 +22,14 @@ __global__ void __launch_bounds__(128) probe(const half* A, const half* B, float
         int m = i / K, k = i % K;
         ((half*)sA)[(k / 8) * (M * 8) + m * 8 + k % 8] = A[m * K + k];
     }
+    // variants 4/5: the stride between 8-row groups (SBO) is 144 B instead of 128 B -- core matrices stay 128 B
+    // contiguous but successive ones start on different banks (would make the transposed V stores of the prefill
+    // attention kernel conflict-free).  Does the hardware accept an SBO that is not a multiple of 128 B?
+    const uint32_t b_sbo = variant >= 4 ? 144 : 128;
+    const uint32_t b_lbo = (N / 8) * b_sbo;
     for (int i = tid; i < N * K; i += 128) {
         int n = i / K, k = i % K;
-        ((half*)sB)[(k / 8) * (N * 8) + n * 8 + k % 8] = B[n * K + k];
+        *(half*)(sB + (k / 8) * b_lbo + (n / 8) * b_sbo + (n % 8) * 16 + (k % 8) * 2) = B[n * K + k];
     }
     if (tid == 0) {
         mbar_init(smem_u32(&bar), 1);
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(128) probe(const half* A, const half* B, float
     umma::fence_after_sync();
     const uint32_t tb    = tmem_base;
     const uint32_t d_col = 0, a_col = 32;
-    const bool     ts    = variant >= 2;
+    const bool     ts    = (variant & 2) != 0 || variant == 5;
     if (ts) {
         // A -> TMEM: lane = row, column c holds (k=2c, k=2c+1)
         uint32_t r[16];
@@ -56,12 +61,14 @@ __global__ void __launch_bounds__(128) probe(const half* A, const half* B, float
     umma::fence_after_sync();
     if (tid == 0) {
         const uint32_t idesc = umma::make_idesc_f16(M, N, false);
-        const bool     swap  = (variant & 1);
+        const bool     swap  = variant < 4 && (variant & 1);
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t a_addr = smem_u32(sA) + ks * 2 * (M * 16);
-            const uint32_t b_addr = smem_u32(sB) + ks * 2 * (N * 16);
+            const uint32_t b_addr = smem_u32(sB) + ks * 2 * b_lbo;
             uint64_t ad = swap ? umma::make_smem_desc(a_addr, 128, M * 16) : umma::make_smem_desc(a_addr, M * 16, 128);
-            uint64_t bd = swap ? umma::make_smem_desc(b_addr, 128, N * 16) : umma::make_smem_desc(b_addr, N * 16, 128);
+            uint64_t bd = variant >= 4 ? umma::make_smem_desc(b_addr, b_lbo, b_sbo) :
+                          swap         ? umma::make_smem_desc(b_addr, 128, N * 16) :
+                                         umma::make_smem_desc(b_addr, N * 16, 128);
             if (ts) {
                 umma::mma_f16_ts(tb + d_col, tb + a_col + ks * 8, bd, idesc, ks > 0);
             }
@@ -105,9 +112,10 @@ int main()
     cudaMalloc(&dD, M * N * 4);
     cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice);
-    const char* names[4] = {"SS lbo=kstride sbo=128", "SS lbo=128 sbo=kstride", "TS(A tmem) B lbo=kstride sbo=128",
-                            "TS(A tmem) B lbo=128 sbo=kstride"};
-    for (int v = 0; v < 4; ++v) {
+    const char* names[6] = {"SS lbo=kstride sbo=128", "SS lbo=128 sbo=kstride", "TS(A tmem) B lbo=kstride sbo=128",
+                            "TS(A tmem) B lbo=128 sbo=kstride", "SS, B with sbo=144 (padded core-matrix stride)",
+                            "TS(A tmem), B with sbo=144"};
+    for (int v = 0; v < 6; ++v) {
         cudaMemset(dD, 0xff, M * N * 4);
         probe<<<1, 128>>>(dA, dB, dD, v);
         cudaError_t e = cudaDeviceSynchronize();
