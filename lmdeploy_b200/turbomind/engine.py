@@ -17,6 +17,26 @@ from .scheduler import Scheduler, Sequence
 from .specs import SPECS, ModelSpec
 
 
+def marshal_step(batch, block_ptr):
+    """Argument arrays of one (mixed) step for `batch` = [Sequence]: sequence i feeds its `step_tokens` next tokens as
+    rows [cu_q_len[i], cu_q_len[i+1]); cu_k_len counts cached history + the fed tokens (AttentionParams::cu_k_len
+    includes the new tokens); block_ptrs is the concatenation of the sequences' block tables through `block_ptr`."""
+    tokens, cu_q, cu_k, ptrs, cu_blocks = [], [0], [0], [], [0]
+    for s in batch:
+        toks = s.next_inputs()
+        if len(toks) != s.step_tokens:
+            raise RuntimeError(f"session {s.session_id}: scheduled {s.step_tokens} tokens but {len(toks)} are available")
+        if not s.blocks:
+            raise RuntimeError(f"session {s.session_id} runs without KV blocks")
+        tokens += [int(t) for t in toks]
+        cu_q.append(cu_q[-1] + len(toks))
+        cu_k.append(cu_k[-1] + s.cached + len(toks))
+        ptrs += [block_ptr(b) for b in s.blocks]
+        cu_blocks.append(len(ptrs))
+    return dict(token_ids=tokens, token_num=len(tokens), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
+                cu_block_nums=cu_blocks, max_k_len=max(s.cached + s.step_tokens for s in batch))
+
+
 class TurboMind:
     def __init__(self, spec: ModelSpec, engine_config: Optional[TurbomindEngineConfig] = None, *, model: DecodeModel = None,
                  eos_id: Optional[int] = None, num_blocks: Optional[int] = None, seed=0):
@@ -95,20 +115,12 @@ class TurboMind:
         if not batch:
             return []
         B = len(batch)
-        ptrs, nblk, cu_q = [], [0], [0]
-        self.h_cu_k[0] = 0
-        acc = 0
-        for i, s in enumerate(batch):
-            toks = s.next_inputs()
-            self.h_tokens[cu_q[-1]:cu_q[-1] + len(toks)] = torch.tensor(toks, dtype=torch.int32)
-            cu_q.append(cu_q[-1] + len(toks))
-            acc += s.cached + len(toks)              # keys visible to this step: cached history + the fed tokens
-            self.h_cu_k[i + 1] = acc
-            ptrs += [self.pool.ptr(b) for b in s.blocks]
-            nblk.append(len(ptrs))
-        T = cu_q[-1]                                 # token rows of the step (== B when every sequence feeds one)
+        st = marshal_step(batch, self.pool.ptr)
+        T, cu_q, ptrs = st["token_num"], st["cu_q_len"], st["block_ptrs"]
+        self.h_tokens[:T] = torch.tensor(st["token_ids"], dtype=torch.int32)
         self.h_cu_q[:B + 1] = torch.tensor(cu_q, dtype=torch.int32)
-        self.h_cu_blocks[:B + 1] = torch.tensor(nblk, dtype=torch.int32)
+        self.h_cu_k[:B + 1] = torch.tensor(st["cu_k_len"], dtype=torch.int32)
+        self.h_cu_blocks[:B + 1] = torch.tensor(st["cu_block_nums"], dtype=torch.int32)
         self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
         self.d_tokens[:T].copy_(self.h_tokens[:T], non_blocking=True)
         self.d_cu_q[:B + 1].copy_(self.h_cu_q[:B + 1], non_blocking=True)
@@ -117,7 +129,7 @@ class TurboMind:
         self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
         self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
                                block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
-                               max_k_len=max(s.cached + s.step_tokens for s in batch), token_num=T)
+                               max_k_len=st["max_k_len"], token_num=T)
         self.h_out[:T].copy_(self.d_out[:T], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         out = self.h_out[:T].tolist()

@@ -369,3 +369,31 @@ def test_chunk_never_swallows_the_last_prompt_token_early():
         sizes.append(b[0].step_tokens)
         sched.update(b, model.step(b))
     assert sizes == [4, 2, 1] and len(s.generated) == 2
+
+
+def test_marshal_step_describes_the_batch_the_way_the_c_abi_reads_it():
+    """Re-derive every sequence's (new tokens, history, block table) from the marshalled arrays with the C ABI's own
+    conventions (b200_attention_params: rows [cu_q_len[b], cu_q_len[b+1]), k_len = cu_k_len[b+1] - cu_k_len[b]
+    INCLUDING the new tokens, blocks [cu_block_nums[b], cu_block_nums[b+1]))."""
+    from lmdeploy_b200.turbomind.engine import marshal_step
+    sched = Scheduler(max_batch=4, block_len=4, num_blocks=64, session_len=4096, prefill_chunk=6, token_budget=12)
+    model = FakeChunkModel(64, 4)
+    for i, p in enumerate(PROMPTS):
+        sched.add(Sequence(session_id=i + 1, prompt=list(p), max_new_tokens=4, stop_token_ids=[], ignore_eos=True, eos_id=None))
+    seen_multi = False
+    while sched.has_work:
+        batch = sched.schedule()
+        st = marshal_step(batch, lambda b: 1000 + 16 * b)
+        assert st["token_num"] == len(st["token_ids"]) == st["cu_q_len"][-1] <= 12
+        for i, s in enumerate(batch):
+            rows = st["token_ids"][st["cu_q_len"][i]:st["cu_q_len"][i + 1]]
+            k_len = st["cu_k_len"][i + 1] - st["cu_k_len"][i]
+            blocks = st["block_ptrs"][st["cu_block_nums"][i]:st["cu_block_nums"][i + 1]]
+            assert rows == s.next_inputs() and len(rows) == s.step_tokens
+            assert k_len - len(rows) == s.cached                       # history_len of the attention call
+            assert blocks == [1000 + 16 * b for b in s.blocks]
+            assert len(blocks) * 4 >= k_len                            # every key position has a page
+            seen_multi |= len(rows) > 1
+        assert st["max_k_len"] == max(st["cu_k_len"][i + 1] - st["cu_k_len"][i] for i in range(len(batch)))
+        sched.update(batch, model.step(batch))
+    assert seen_multi
