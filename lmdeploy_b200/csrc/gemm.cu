@@ -286,7 +286,7 @@ static int launch(const Params& p, int smem, cudaStream_t st)
     // PDL (host_utils.h): the kernel prefetches weights before griddepcontrol.wait.
     cudaLaunchAttribute attr[2];
     int                 na = 0;
-    if (p.splits > 1 && !getenv("B200_GEMM_NO_COOP")) {
+    if (p.splits > 1) {
         attr[na].id              = cudaLaunchAttributeCooperative;
         attr[na].val.cooperative = 1;
         ++na;

@@ -64,12 +64,6 @@ static int round16(int x)
 
 extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
 {
-    // Every kernel of the step runs with the maximum shared-memory carveout, so the SMs are not re-partitioned
-    // (L1 <-> shared) between the 211 KB GEMM CTAs and the small glue kernels of a step.
-    // (measured: no effect on B200; kept switchable)
-    if (!getenv("B200_NO_PREFER_SHARED")) {
-        cudaDeviceSetCacheConfig(cudaFuncCachePreferShared);
-    }
     if (!out || !c) {
         return fail(B200_ERR_INVALID_ARG, "model_create: NULL argument");
     }
