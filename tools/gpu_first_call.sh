@@ -17,4 +17,5 @@ B200_RUN_UNVERIFIED=1 run pending_suite 300 python -m pytest tests/test_zz_pendi
 [ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
 [ -x build/tma_issue_rate ] && run tma_issue_rate 120 build/tma_issue_rate
 [ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
+run ref_gemm_bench 300 python tools/ref_gemm_bench.py 64 20
 run bench 420 python bench.py
