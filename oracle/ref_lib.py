@@ -35,11 +35,29 @@ class RefAttnArgs(C.Structure):
                 ("partial_ML", C.c_void_p), ("dtype", C.c_int), ("stream", C.c_void_p)]
 
 
+PREFILL_LIB_PATH = os.path.join(ROOT, "_ref", "libtm_ref_prefill.so")
+
 _lib = None
+_prefill_lib = None
 
 
 def available():
     return os.path.exists(LIB_PATH)
+
+
+def prefill_available():
+    return os.path.exists(PREFILL_LIB_PATH)
+
+
+def load_prefill():
+    """libtm_ref_prefill.so: the reference's ProcessKV + FlattenKV + dispatchAttention for a chunk
+    (oracle/ref_build/ref_prefill_shim.cu)."""
+    global _prefill_lib
+    if _prefill_lib is None:
+        _prefill_lib = C.CDLL(PREFILL_LIB_PATH)
+        _prefill_lib.ref_prefill_attention.argtypes = [C.POINTER(RefAttnArgs), C.c_void_p, C.c_int]
+        _prefill_lib.ref_prefill_attention.restype = C.c_int
+    return _prefill_lib
 
 
 def load():

@@ -159,7 +159,7 @@ def test_synthetic_fp8_model_runs_and_is_deterministic():
 # ---------------------------------------------------------------------------------------------------------------
 # prefill (context) attention: b200_prefill_attention vs oracle.attention.prefill_attention
 # ---------------------------------------------------------------------------------------------------------------
-def _prefill_case(lib, *, q_lens, hists, Hq, Hkv, kv_bits, dtype, seed=0, bias=False, rope=None):
+def _prefill_case(lib, *, q_lens, hists, Hq, Hkv, kv_bits, dtype, seed=0, bias=False, rope=None, against_reference=False):
     import ctypes as C
     import torch
     from lmdeploy_b200 import _lib as L
@@ -218,6 +218,7 @@ def _prefill_case(lib, *, q_lens, hists, Hq, Hkv, kv_bits, dtype, seed=0, bias=F
                           rope.llama3_low_freq_factor, rope.llama3_high_freq_factor,
                           rope.llama3_original_max_position_embeddings, rope.yarn_attention_factor, rope.yarn_beta_fast,
                           rope.yarn_beta_slow, 1)
+    p.rope.exact_math = 0 if against_reference else 1
     p.quant_policy, p.dtype = (0 if kv_bits == 16 else kv_bits), (0 if dtype == F16 else 1)
     ws = torch.zeros(lib.b200_prefill_attention_workspace_bytes(T, Hq), dtype=torch.uint8, device="cuda")
     p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
@@ -225,6 +226,23 @@ def _prefill_case(lib, *, q_lens, hists, Hq, Hkv, kv_bits, dtype, seed=0, bias=F
     L.check(lib.b200_prefill_attention(C.byref(p)), "b200_prefill_attention")
     torch.cuda.synchronize()
     got, got_pool = from_dev_T(d_out, dtype), d_pool.cpu().numpy()
+
+    if against_reference:
+        # the reference's ProcessKV + FlattenKV + dispatchAttention on a fresh copy of the same pages
+        from oracle import ref_lib
+        ref = ref_lib.load_prefill()
+        d_pool2 = torch.from_numpy(cache.pool.copy()).cuda()
+        d_ptrs2 = torch.tensor([d_pool2.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t],
+                               dtype=torch.int64, device="cuda")
+        d_out2 = torch.zeros_like(d_out)
+        p.block_ptrs, p.out = d_ptrs2.data_ptr(), d_out2.data_ptr()
+        a, keep = ref_lib.args_from_b200(p, torch, max_q_len=int(q_lens.max()))
+        k_sum = int(k_lens.sum())
+        tmp_kv = torch.zeros(Hkv * 2 * (k_sum + 64) * D, dtype=d_qkv.dtype, device="cuda")
+        rc = ref.ref_prefill_attention(C.byref(a), tmp_kv.data_ptr(), k_sum)
+        torch.cuda.synchronize()
+        assert rc == 0
+        return got, from_dev_T(d_out2, dtype), got_pool, d_pool2.cpu().numpy()
 
     # ---- oracle (mutates its cache the same way) ----
     ref = OA.prefill_attention(qkv, cache, tables, q_lens, k_lens, layer, Hq, Hkv, rope,
@@ -368,3 +386,17 @@ def test_gated_silu_matches_reference_gemm(lib):
     _assert_close(theirs, ref, atol=4e-4, rtol=4e-3)
     _assert_close(ours, ref, atol=4e-4, rtol=4e-3)
     rl.close(), g.close()
+
+
+@pytest.mark.parametrize("kv_bits", [8, 4, 16])
+def test_prefill_attention_matches_reference_kernels(lib, kv_bits):
+    """Ours against the REFERENCE ITSELF (oracle/_ref/libtm_ref_prefill.so: invokeProcessKV_v2 + invokeFlattenKV_v2 +
+    dispatchAttention compiled in place) on the same inputs, rope.exact_math = 0: pages bit-identical, outputs <= 2e-3."""
+    from oracle import ref_lib
+    if not ref_lib.prefill_available():
+        pytest.skip("oracle/_ref/libtm_ref_prefill.so not built")
+    got, ref, pool, ref_pool = _prefill_case(lib, q_lens=[70, 1, 33, 200], hists=[0, 130, 64, 0], Hq=8, Hkv=2, kv_bits=kv_bits,
+                                             dtype=F16, seed=kv_bits, against_reference=True)
+    assert np.array_equal(pool, ref_pool)
+    assert np.isfinite(got).all() and np.isfinite(ref).all()
+    assert np.abs(got - ref).max() <= 2e-3
