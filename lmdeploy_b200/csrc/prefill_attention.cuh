@@ -49,7 +49,14 @@ constexpr int kPfThreads = 128;
 constexpr int kPfD       = 128;
 constexpr int kPfQBytes  = kPfRows * kPfD * 2;
 constexpr int kPfKBytes  = kPfKeys * kPfD * 2;
-constexpr int kPfVBytes  = kPfKeys * kPfD * 2;
+// V^T tile [key/8][d/8][8 d][8 keys]: a thread writes one whole 128-byte core matrix (8 chunks), so with the canonical
+// 128-byte stride between core matrices every 16-byte store of a warp lands on the same four banks (8-way conflict).
+// kPfVPad = 16 staggers successive core matrices by one bank group (SBO = 144) and makes the stores conflict-free --
+// to be switched on once tools/umma_probe.cu (variants 4/5) has shown the tensor core accepts such an SBO.
+constexpr int kPfVPad    = 0;
+constexpr int kPfVSbo    = 128 + kPfVPad;          // byte stride between 8-dim groups of one key group
+constexpr int kPfVLbo    = (kPfD / 8) * kPfVSbo;   // byte stride between 8-key groups
+constexpr int kPfVBytes  = (kPfKeys / 8) * kPfVLbo;
 // The second K/V buffer is reserved for the pipelined version; it also pins residency at two CTAs per SM, which is
 // what the 2 x 256 TMEM columns allow.
 constexpr int kPfSmem    = kPfQBytes + 2 * (kPfKBytes + kPfVBytes);
@@ -227,7 +234,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attention_kernel(const Pre
                     uint32_t       y[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) y[q] = __byte_perm(a[2 * q][i >> 1], a[2 * q + 1][i >> 1], sel);
-                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(v_op + (kg * kPfD + dg * 8 + i) * 16), "r"(y[0]),
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(v_op + kg * kPfVLbo + dg * kPfVSbo + i * 16), "r"(y[0]),
                                  "r"(y[1]), "r"(y[2]), "r"(y[3])
                                  : "memory");
                 }
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__(kPfThreads) prefill_attention_kernel(const Pre
             umma::fence_after_sync();
 #pragma unroll
             for (int ks = 0; ks < kPfKeys / 16; ++ks) {
-                const uint64_t bd = umma::make_smem_desc(v_op + ks * 2 * (kPfD * 16), kPfD * 16, 128);
+                const uint64_t bd = umma::make_smem_desc(v_op + ks * 2 * kPfVLbo, kPfVLbo, kPfVSbo);
                 umma::mma_f16_ts(tmem + kPfColO, tmem + kPfColP + ks * 8, bd, idesc_o, ks > 0);
             }
             umma::commit(smem_u32(&bar_o));

@@ -47,7 +47,9 @@ def pf_load8(pool_row, kv_bits, dim0, scale, zero):
     return OA.t_fma(q, np.float32(scale), np.float32(zero), F16)
 
 
-def emulate(pool, block_bytes, tables, cu_q, cu_k, layer_offset, block_len, Hq, Hkv, kv_bits, q_rot, qk_scale):
+def emulate(pool, block_bytes, tables, cu_q, cu_k, layer_offset, block_len, Hq, Hkv, kv_bits, q_rot, qk_scale, v_pad=0):
+    v_sbo = 128 + v_pad                  # kPfVSbo / kPfVLbo of the kernel (kPfVPad = v_pad)
+    v_lbo = (D // 8) * v_sbo
     G = Hq // Hkv
     TQ = ROWS // G
     kRow = D * kv_bits // 8
@@ -96,7 +98,7 @@ def emulate(pool, block_bytes, tables, cu_q, cu_k, layer_offset, block_len, Hq, 
                 kp = blk + Hkv * 2 * head_data_sz + (h * 2) * head_param_sz + bt0 * 4
                 vp = kp + head_param_sz
                 k_op = np.zeros(KEYS * D * 2, np.uint8)
-                v_op = np.zeros(KEYS * D * 2, np.uint8)
+                v_op = np.zeros((KEYS // 8) * v_lbo, np.uint8)
 
                 def params(base, key):
                     if kv_bits == 16:
@@ -123,9 +125,9 @@ def emulate(pool, block_bytes, tables, cu_q, cu_k, layer_offset, block_len, Hq, 
                     for i in range(8):
                         # y[q] = byte_perm(a[2q][i>>1], a[2q+1][i>>1], sel): (key 2q, key 2q+1) of dim i
                         y = [a[kk][(i >> 1) * 2 + (i & 1)] for kk in range(8)]
-                        put16(v_op, (kg * D + dg * 8 + i) * 16, y)
+                        put16(v_op, kg * v_lbo + dg * v_sbo + i * 16, y)
                 K = read_operand(k_op, KEYS, D, KEYS * 16, 128).astype(np.float64)       # B of S: N = keys, K = d
-                Vt = read_operand(v_op, D, KEYS, D * 16, 128).astype(np.float64)         # B of PV: N = d, K = keys
+                Vt = read_operand(v_op, D, KEYS, v_lbo, v_sbo).astype(np.float64)       # B of PV: N = d, K = keys
                 S = (Q @ K.T).astype(np.float32)
                 kidx = key0 + np.arange(KEYS)[None, :]
                 Sm = np.where(kidx <= pos_q[:, None], S, -np.inf)
@@ -144,9 +146,9 @@ def emulate(pool, block_bytes, tables, cu_q, cu_k, layer_offset, block_len, Hq, 
     return out
 
 
-@pytest.mark.parametrize("kv_bits", [8, 4, 16])
-@pytest.mark.parametrize("heads", [(4, 1), (2, 2), (6, 1)])
-def test_kernel_index_math_reproduces_the_oracle(kv_bits, heads):
+@pytest.mark.parametrize("kv_bits,heads,v_pad", [(8, (4, 1), 0), (4, (4, 1), 0), (16, (4, 1), 0), (8, (2, 2), 0),
+                                                 (4, (6, 1), 0), (16, (6, 1), 0), (8, (4, 1), 16), (16, (2, 2), 16)])
+def test_kernel_index_math_reproduces_the_oracle(kv_bits, heads, v_pad):
     Hq, Hkv = heads
     rng = np.random.default_rng(kv_bits * 10 + Hq)
     q_lens, hists = np.array([37, 1, 70]), np.array([0, 70, 30])
@@ -181,7 +183,7 @@ def test_kernel_index_math_reproduces_the_oracle(kv_bits, heads):
     cu_k = np.concatenate([[0], np.cumsum(k_lens)]).tolist()
     c = float(np.float32(np.float32(1.4426950408889634) / np.float32(np.sqrt(np.float32(D)))))
     got = emulate(cache.pool.reshape(-1), cache.block_bytes, tables, cu_q, cu_k, cache.layer_offset(layer), block_len, Hq, Hkv,
-                  kv_bits, q_rot, c)
+                  kv_bits, q_rot, c, v_pad)
     assert np.isfinite(got).all()
     # tiled online softmax vs the oracle's single pass: a few fp16 ulps of an O(1) output
     assert np.abs(got - ref).max() <= 2e-3
