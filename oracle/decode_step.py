@@ -114,3 +114,24 @@ def decode_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables,
         x, residual = OL.allreduce_residual_rmsnorm(parts, residual, nxt, eps, dtype)
     logits = np.concatenate([OL.linear(x, sw.output["deq"], dtype) for sw in shards], axis=1)
     return logits, logits.argmax(-1)
+
+
+def chunk_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables, q_lens, k_lens, rope, eps=1e-5):
+    """Mixed prefill/decode step (b200_model_chunk_step; the reference's chunked prefill, unified_attention_layer.cc
+    :613-651): sequence b contributes q_lens[b] consecutive rows, k_lens[b] counts them.  Every operator except attention
+    is row-wise and identical to decode_step; attention is oracle.attention.prefill_attention.  Returns
+    (logits [sum(q_lens), vocab], argmax per row); the caller samples from the last row of each sequence."""
+    dtype = w.dtype
+    residual = w.embed[np.asarray(token_ids)]
+    x = OL.rmsnorm(residual, w.L[0]["attn_norm"], eps, dtype)
+    for l in range(w.layers):
+        lw = w.L[l]
+        qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+        attn = OA.prefill_attention(qkv, cache, block_tables, q_lens, k_lens, l, w.heads, w.kv_heads, rope)
+        x, residual = OL.allreduce_residual_rmsnorm([OL.linear(attn, lw["wo"]["deq"], dtype)], residual,
+                                                    lw["ffn_norm"], eps, dtype)
+        a = OL.linear_gated_silu(x, lw["w1w3"]["deq"], dtype)
+        nxt = w.L[l + 1]["attn_norm"] if l + 1 < w.layers else w.final_norm
+        x, residual = OL.allreduce_residual_rmsnorm([OL.linear(a, lw["w2"]["deq"], dtype)], residual, nxt, eps, dtype)
+    logits = OL.linear(x, w.output["deq"], dtype)
+    return logits, logits.argmax(-1)

@@ -35,3 +35,31 @@ def test_prefill_chunk_equals_token_by_token_decode(kv_bits, dtype):
         t0 += ql
     assert np.array_equal(got, np.stack(rows))
     assert np.array_equal(caches[0].pool, caches[1].pool)
+
+
+def test_chunk_step_equals_token_by_token_decode_steps():
+    """Model level: one mixed step (a 6-token prompt chunk + a decoding sequence) leaves the same pages and gives, row for
+    row, the same logits as feeding those tokens through decode_step one at a time."""
+    from oracle.decode_step import TinyWeights, chunk_step, decode_step
+    w = TinyWeights(hidden=256, layers=2, heads=2, kv_heads=1, inter=256, vocab=256, fmt="awq", seed=4)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
+    lay = OA.KvLayout(1, 64, 128, 8)
+    caches = [OA.PagedKvCache(4, w.layers, lay, F16) for _ in range(2)]
+    rng = np.random.default_rng(0)
+    # sequence 1 already has 70 cached tokens (fed one by one into both caches)
+    hist_tokens = rng.integers(0, 256, 70)
+    for c in caches:
+        for i, t in enumerate(hist_tokens):
+            decode_step(w, np.array([t]), c, [[1, 3]], np.array([i], np.int32), rope)
+    prompt = rng.integers(0, 256, 6)
+    nxt = np.array([17])
+    tokens = np.concatenate([prompt, nxt])
+    got, _ = chunk_step(w, tokens, caches[0], [[0], [1, 3]], [6, 1], [6, 71], rope)
+    rows = []
+    for i, t in enumerate(prompt):
+        lg, _ = decode_step(w, np.array([t]), caches[1], [[0]], np.array([i], np.int32), rope)
+        rows.append(lg[0])
+    lg, _ = decode_step(w, nxt, caches[1], [[1, 3]], np.array([70], np.int32), rope)
+    rows.append(lg[0])
+    assert np.array_equal(got, np.stack(rows))
+    assert np.array_equal(caches[0].pool, caches[1].pool)

@@ -20,6 +20,7 @@ run pending_ref_gemm 240 $P -k "reference_gemm"
 run pending_bf16_steps 300 $P -k "bf16_matches_oracle or synthetic_fp8"
 run pending_prefill_oracle 420 $P -k "prefill_attention_matches_oracle or prefill_single or prefill_attention_bf16"
 run pending_prefill_reference 240 $P -k "prefill_attention_matches_reference"
+run pending_chunk_step 300 $P -k "chunk_step"
 run pending_engine 420 $P -k "engine"
 unset B200_RUN_UNVERIFIED
 [ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
