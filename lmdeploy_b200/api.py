@@ -1,4 +1,5 @@
 """pipeline(): the user entry point, same shape as lmdeploy.pipeline (lmdeploy/api.py:15-82, pipeline.py:33-95)."""
+from dataclasses import replace
 from typing import List, Optional, Union
 
 from .messages import GenerationConfig, Response, TurbomindEngineConfig
@@ -29,6 +30,11 @@ class Pipeline:
                                               and isinstance(prompts[0], int))
         plist = [prompts] if single else list(prompts)
         ids = [self._encode(p) for p in plist]
+        if gen_config is not None and (gen_config.stop_words or gen_config.bad_words):
+            if self.tokenizer is None:
+                raise ValueError("stop_words need a tokenizer: pass stop_token_ids instead")
+            gen_config = replace(gen_config)
+            gen_config.convert_stop_bad_words_to_ids(self.tokenizer)
         seqs = batched_generate(self.engine, ids, gen_config)
         out = []
         for i, s in enumerate(seqs):

@@ -45,6 +45,44 @@ class GenerationConfig:
     logprobs: Optional[int] = None
     output_logits: Optional[str] = None
 
+    def convert_stop_bad_words_to_ids(self, tokenizer):
+        """stop_words -> stop_token_ids with the reference's rule (lmdeploy/messages.py:154-174 and
+        Tokenizer.indexes_containing_token, lmdeploy/tokenizer.py:152-190, 539-547): a word must encode to ONE token;
+        every vocabulary entry whose token string contains it stops generation (' ' is looked up as the sentencepiece
+        marker); more than 5 candidates are narrowed to the ids that decode to exactly the word.  `tokenizer` is a
+        HuggingFace tokenizer (encode / decode / get_vocab)."""
+        def ids_of(words):
+            out = []
+            for word in words or []:
+                if not isinstance(word, str):
+                    raise TypeError(f"stop_words must be a list of str but got {type(word)}")
+                if len(tokenizer.encode(word, add_special_tokens=False)) > 1:
+                    continue                       # multi-token words cannot be stop words (same as the reference)
+                needle = "\u2581" if word == " " else word
+                ids = [i for tok, i in tokenizer.get_vocab().items() if needle in tok]
+                if len(ids) > 5:
+                    ids = [i for i in sorted(ids) if tokenizer.decode([i]) == word][:5]
+                if not ids:
+                    ids = tokenizer.encode(word, add_special_tokens=False)
+                    ids = ids if len(ids) == 1 else []
+                out += ids
+            return out
+
+        if self.bad_words or self.bad_token_ids:
+            raise NotImplementedError("bad_words need a logits processor; the decode hot path samples greedily on the device")
+        merged = set(ids_of(self.stop_words)) | set(self.stop_token_ids or [])
+        self.stop_token_ids = sorted(merged) or None
+
+    def update_from_hf_gen_cfg(self, generation_config, tokenizer_eos_token_id):
+        """Add the tokenizer's and generation_config.json's eos ids to stop_token_ids (lmdeploy/messages.py:176-193)."""
+        ids = set(self.stop_token_ids or [])
+        if tokenizer_eos_token_id is not None:
+            ids.add(int(tokenizer_eos_token_id))
+        eos = (generation_config or {}).get("eos_token_id")
+        if eos is not None:
+            ids.update([eos] if isinstance(eos, int) else eos)
+        self.stop_token_ids = sorted(ids)
+
     def __post_init__(self):
         if self.max_new_tokens is not None and self.max_new_tokens < 0:
             raise ValueError("max_new_tokens must be >= 0")
