@@ -227,6 +227,14 @@ B200_API int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_desc*
 /* launch plan of a shape (host only; no device work): out8 = {n-tiles per CTA, K splits, W ring, X ring, TMEM A slots,
  * TMEM columns, first A column, dynamic shared memory bytes}.  A pure function of (format, K, N, padded m). */
 B200_API int b200_linear_plan(const b200_linear_desc* desc, int m, int* out8);
+/* Tuned launch plans -- the counterpart of the reference's GEMM tuning cache (gemm::Gemm::Export / Import,
+ * kernels/gemm/gemm.h:43-45, dispatch_cache.cu).  `path`: text file of lines
+ *   PLAN <weight_format> <padded tokens> <N> <K> <n-tiles per CTA> <K splits> <W ring slots> <X ring slots>
+ * (ring slots 0 0 = keep the heuristic's depths; '#' starts a comment).  Every entry is validated against the budgets
+ * the kernel relies on; one invalid entry rejects the file and leaves the current table unchanged.  Returns the number
+ * of entries (>= 0) or a negative b200_status.  NULL clears the table.  Results stay deterministic: the plan is still a
+ * pure function of (format, shape, tokens) for a given table.  Not thread-safe against concurrent forward calls. */
+B200_API int b200_linear_load_plans(const char* path);
 B200_API int b200_pack_activations(const void* x, int64_t ldx, int m, int k, int mt, int dtype, void* xp, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

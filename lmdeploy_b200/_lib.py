@@ -68,6 +68,7 @@ class StepInputs(C.Structure):
     ]
 
 
+ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_STATE = -1, -2, -3, -4          # b200_status
 W_QKV, W_O, W_GATE_UP, W_DOWN, W_LM_HEAD = range(5)
 FMT_DENSE, FMT_U4, FMT_FP8, FMT_FP8_COL = range(4)        # b200_linear_desc.weight_format
 T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM = range(4)
@@ -113,6 +114,8 @@ def load():
         C.c_void_p, C.c_size_t, C.c_void_p]
     lib.b200_linear_plan.argtypes = [C.POINTER(LinearDesc), C.c_int, C.POINTER(C.c_int)]
     lib.b200_linear_plan.restype = C.c_int
+    lib.b200_linear_load_plans.argtypes = [C.c_char_p]
+    lib.b200_linear_load_plans.restype = C.c_int
     lib.b200_pack_activations.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                           C.c_void_p]
     lib.b200_rmsnorm.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int,

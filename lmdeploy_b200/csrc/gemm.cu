@@ -6,6 +6,10 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
 
 namespace b200 {
 namespace gemm {
@@ -160,14 +164,40 @@ struct Plan {
 //     shared-memory / TMEM budget spent on ring depth (the pipeline, not a second CTA, hides the latency);
 //   * otherwise one n-tile per CTA (N not a multiple of 256, dense weights), also one CTA per SM;
 //   * K is split over 1/2/4/8 co-resident CTAs (largest count that fits one wave, every CTA >= 4 K-groups).
-#ifdef B200_GEMM_TOOL
-// tools/gemm_sweep.cu compiles this TU with -DB200_GEMM_TOOL to measure the plan space: fields > 0 replace the
-// heuristic's choice.  Never compiled into the product library.
+// A plan the heuristic below is told to use instead of its own choice: fields > 0 replace the heuristic's value.
 struct PlanOverride {
     int tiles, splits, nw, nx;
 };
+
+#ifdef B200_GEMM_TOOL
+// tools/gemm_sweep.cu compiles this TU with -DB200_GEMM_TOOL to measure the plan space.  Never compiled into the
+// product library.
 static PlanOverride g_plan_override{};
 #endif
+
+// Tuned plans per (format, padded tokens, N, K): the counterpart of the reference's GEMM dispatch cache
+// (kernels/gemm/dispatch_cache.cu; Gemm::Export / Gemm::Import, gemm.h:43-45).  Filled by b200_linear_load_plans from
+// a text file that tools/gemm_sweep.cu can write ("PLAN fmt mt N K tiles splits nw nx" lines); empty = heuristic only.
+struct PlanKey {
+    int fmt, mt, N, K;
+    bool operator<(const PlanKey& o) const
+    {
+        return std::tie(fmt, mt, N, K) < std::tie(o.fmt, o.mt, o.N, o.K);
+    }
+};
+static std::map<PlanKey, PlanOverride> g_plan_table;
+static std::mutex                      g_plan_mutex;
+
+static bool lookup_plan(int fmt, int MT, int N, int K, PlanOverride* out)
+{
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto                        it = g_plan_table.find(PlanKey{fmt, MT, N, K});
+    if (it == g_plan_table.end()) {
+        return false;
+    }
+    *out = it->second;
+    return true;
+}
 
 static Plan make_plan(int fmt, int MT, int N, int K)
 {
@@ -176,11 +206,16 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     const int XB     = MT * 256;
     Plan      pl{};
     pl.tiles         = (fmt != kDense && N % (2 * kBN) == 0) ? 2 : 1;
+    PlanOverride ov{};
+    lookup_plan(fmt, MT, N, K, &ov);
 #ifdef B200_GEMM_TOOL
-    if (g_plan_override.tiles > 0 && fmt != kDense && N % (kBN * g_plan_override.tiles) == 0) {
-        pl.tiles = g_plan_override.tiles;
+    if (g_plan_override.tiles > 0 || g_plan_override.splits > 0 || g_plan_override.nw > 0) {
+        ov = g_plan_override;
     }
 #endif
+    if (ov.tiles > 0 && fmt != kDense && N % (kBN * ov.tiles) == 0) {
+        pl.tiles = ov.tiles;
+    }
     const bool two_per_sm = false;  // 640-thread CTAs at ~90 registers: one CTA per SM in every configuration
     const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
     const int  slots = 148 * (two_per_sm ? 2 : 1);
@@ -190,11 +225,9 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4) {
         pl.splits *= 2;
     }
-#ifdef B200_GEMM_TOOL
-    if (g_plan_override.splits > 0) {
-        pl.splits = g_plan_override.splits;
+    if (ov.splits > 0) {
+        pl.splits = ov.splits;
     }
-#endif
     const int budget = (two_per_sm ? 113 : 224) * 1024 - 1024;
     const int wslot  = WB_pad * pl.tiles;
     // both rings want ~5-6 slots in flight (each loop is ~2.5-3k cycles of latency per slot)
@@ -204,11 +237,9 @@ static Plan make_plan(int fmt, int MT, int N, int K)
         pl.nw = 3;
         pl.nx = std::max(2, std::min(kMaxX, (budget - pl.nw * wslot) / XB));
     }
-#ifdef B200_GEMM_TOOL
-    if (g_plan_override.nw > 0 && g_plan_override.nx > 0) {
-        pl.nw = std::min(kMaxW, g_plan_override.nw), pl.nx = std::min(kMaxX, g_plan_override.nx);
+    if (ov.nw > 0 && ov.nx > 0) {
+        pl.nw = std::min(kMaxW, ov.nw), pl.nx = std::min(kMaxX, ov.nx);
     }
-#endif
     pl.smem = pl.nw * wslot + pl.nx * XB;
     const int d_cols = (MT <= 64 ? 64 : 128) * pl.tiles;
     if (fmt == kDense) {
@@ -554,6 +585,70 @@ extern "C" int b200_linear_forward_packed_residual_rmsnorm(const b200_linear_des
 }
 
 // Host-only introspection of the launch plan (tests/test_linear_plan_cpu.py checks its invariants without a GPU).
+// Checks one tuned plan against the budgets the kernel relies on (the same ones tests/test_linear_plan_cpu.py asserts).
+static bool plan_entry_ok(const PlanKey& k, const PlanOverride& v)
+{
+    if (k.fmt < kDense || k.fmt > kFp8Col || k.mt < 16 || k.mt > 128 || k.mt % 16 || k.N <= 0 || k.N % kBN || k.K <= 0
+        || k.K % kKG) {
+        return false;
+    }
+    if (v.tiles < 1 || v.tiles > 2 || (k.fmt == kDense && v.tiles != 1) || k.N % (kBN * v.tiles)) {
+        return false;
+    }
+    const int nts = k.N / (kBN * v.tiles), kgs = k.K / kKG;
+    if (v.splits < 1 || v.splits > kMaxSplits || v.splits > kgs || (v.splits > 1 && nts * v.splits > 148)) {
+        return false;
+    }
+    if ((v.nw > 0) != (v.nx > 0)) {
+        return false;
+    }
+    if (v.nw > 0) {
+        const int WB_pad = (block_bytes_of(k.fmt) + 1023) & ~1023;
+        if (v.nw < 3 || v.nw > kMaxW || v.nx < 2 || v.nx > kMaxX || v.nw * WB_pad * v.tiles + v.nx * k.mt * 256 > 223 * 1024) {
+            return false;
+        }
+    }
+    return true;
+}
+
+extern "C" int b200_linear_load_plans(const char* path)
+{
+    if (!path) {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plan_table.clear();
+        return 0;
+    }
+    FILE* f = fopen(path, "r");
+    if (!f) {
+        return fail(B200_ERR_INVALID_ARG, "linear_load_plans: cannot open the plan file");
+    }
+    std::map<PlanKey, PlanOverride> table;
+    char                            line[256];
+    int                             lineno = 0;
+    while (fgets(line, sizeof(line), f)) {
+        ++lineno;
+        PlanKey      k{};
+        PlanOverride v{};
+        if (line[0] == '#' || line[0] == '\n') {
+            continue;
+        }
+        if (sscanf(line, "PLAN %d %d %d %d %d %d %d %d", &k.fmt, &k.mt, &k.N, &k.K, &v.tiles, &v.splits, &v.nw, &v.nx) != 8
+            || !plan_entry_ok(k, v)) {
+            fclose(f);
+            last_error_ref() = "linear_load_plans: invalid entry at line " + std::to_string(lineno);
+            return B200_ERR_INVALID_ARG;
+        }
+        table[k] = v;
+    }
+    fclose(f);
+    const int n = (int)table.size();
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        g_plan_table.swap(table);
+    }
+    return n;
+}
+
 extern "C" int b200_linear_plan(const b200_linear_desc* d, int m, int* out8)
 {
     if (int e = validate_desc(d)) {

@@ -7,6 +7,7 @@ Mirrors the roles of (reference, for orientation):
 All compute is in libb200tm.so (hand-written sm_100a CUDA); torch is used only for device memory and streams.
 """
 import ctypes as C
+import os
 import math
 
 import torch
@@ -80,6 +81,11 @@ class DecodeModel:
         """rope_exact_math: correctly rounded RoPE transcendentals (comparable with the CPU oracle) instead of the
         reference release build's hardware approximations (the default; bit-identical K pages to TurboMind)."""
         self.lib = L.load()
+        plans = os.environ.get("B200_GEMM_PLANS")     # tuned GEMM launch plans (tools/gemm_sweep.cu writes the lines)
+        if plans:
+            n = self.lib.b200_linear_load_plans(plans.encode())
+            if n < 0:
+                raise L.B200LibraryError(f"B200_GEMM_PLANS={plans}: {self.lib.b200_last_error().decode()}")
         self.spec = spec
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.tp_size, self.tp_rank = tp_size, tp_rank

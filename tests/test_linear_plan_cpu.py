@@ -8,7 +8,7 @@ import pytest
 from lmdeploy_b200 import _lib as L
 
 SMS, SMEM_MAX, TMEM_COLS = 148, 227 * 1024 - 2048, 512
-W_BLOCK = {0: 32768, 1: 8704, 2: 16400}      # bytes of one (n-tile, k-group) of prepared weights per format
+W_BLOCK = {0: 32768, 1: 8704, 2: 16400, 3: 16896}      # bytes of one (n-tile, k-group) of prepared weights per format
 
 
 def _plan(lib, K, N, fmt, m):
@@ -68,3 +68,59 @@ def test_plan_is_a_pure_function(lib):
     a = [_plan(lib, 14336, 4096, 1, 64) for _ in range(3)]
     assert a[0] == a[1] == a[2] and a[0]["tiles"] == 2 and a[0]["splits"] == 8
     assert _plan(lib, 4096, 28672, 1, 64)["splits"] == 1          # 112 two-tile CTAs already fill the wave
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tuned plan table (counterpart of the reference's GEMM dispatch cache)
+# ---------------------------------------------------------------------------------------------------------------
+def test_plan_table_overrides_the_heuristic_and_is_validated(lib, tmp_path):
+    K, N, fmt, m = 4096, 6144, 1, 64
+    base = _plan(lib, K, N, fmt, m)
+    assert (base["tiles"], base["splits"]) == (2, 4)
+    f = tmp_path / "plans.txt"
+    f.write_text("# tuned on a B200\nPLAN 1 64 6144 4096 1 2 0 0\nPLAN 1 64 4096 4096 2 4 5 4\n")
+    try:
+        assert lib.b200_linear_load_plans(str(f).encode()) == 2
+        p = _plan(lib, K, N, fmt, m)
+        assert (p["tiles"], p["splits"]) == (1, 2)
+        _check_budgets_only(p, K, N, fmt, m)
+        p2 = _plan(lib, 4096, 4096, 1, 64)
+        assert (p2["tiles"], p2["splits"], p2["nw"], p2["nx"]) == (2, 4, 5, 4)
+        # other shapes and token counts are untouched
+        assert _plan(lib, K, N, fmt, 16) == _plan_fresh(lib, K, N, fmt, 16, loaded=str(f))
+        assert _plan(lib, 14336, 4096, 1, 64)["splits"] == 8
+        # an invalid entry rejects the whole file and keeps the current table
+        bad = tmp_path / "bad.txt"
+        for text in ("PLAN 1 64 6144 4096 2 8 0 0\n",          # 24 groups x 8 splits > 148 co-resident CTAs
+                     "PLAN 0 64 4096 4096 2 1 0 0\n",          # dense weights: one tile per CTA
+                     "PLAN 1 64 6144 4096 2 4 8 6\n",          # rings beyond shared memory
+                     "PLAN 1 60 6144 4096 2 4 0 0\n",          # padded tokens are multiples of 16
+                     "PLAN 1 64 6144 4096 2 64 0 0\n",         # more splits than K-groups
+                     "garbage\n"):
+            bad.write_text(text)
+            assert lib.b200_linear_load_plans(str(bad).encode()) == L.ERR_INVALID_ARG, text
+            assert _plan(lib, K, N, fmt, m)["splits"] == 2
+        assert lib.b200_linear_load_plans(str(tmp_path / "missing.txt").encode()) == L.ERR_INVALID_ARG
+    finally:
+        assert lib.b200_linear_load_plans(None) == 0
+    assert _plan(lib, K, N, fmt, m) == base
+
+
+def _plan_fresh(lib, K, N, fmt, m, loaded):
+    """The heuristic's own plan for a shape the loaded table does not mention."""
+    lib.b200_linear_load_plans(None)
+    p = _plan(lib, K, N, fmt, m)
+    lib.b200_linear_load_plans(loaded.encode())
+    return p
+
+
+def _check_budgets_only(p, K, N, fmt, m):
+    """_check without the heuristic-specific expectations (splits power of two, >= 4 K-groups per split)."""
+    mt = max(16, (m + 15) // 16 * 16)
+    rows = 128 * p["tiles"]
+    assert N % rows == 0 and (p["splits"] == 1 or N // rows * p["splits"] <= SMS) and p["splits"] <= K // 128
+    wslot = ((W_BLOCK[fmt] + 1023) & ~1023) * p["tiles"]
+    assert p["smem"] == p["nw"] * wslot + p["nx"] * mt * 256 <= SMEM_MAX
+    d_cols = (64 if mt <= 64 else 128) * p["tiles"]
+    assert p["a_col"] >= d_cols and p["a_col"] + 64 * p["na"] <= p["tmem_cols"] <= TMEM_COLS
+    assert p["na"] % p["tiles"] == 0 and p["na"] // p["tiles"] >= 1

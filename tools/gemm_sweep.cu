@@ -143,6 +143,7 @@ int main(int argc, char** argv)
                s.K, s.N, m, def.tiles, def.splits, def.nw, def.nx, t_def, wbytes / t_def * 1e-3);
         double best = t_def;
         char   best_desc[128] = "default";
+        char   best_plan[128] = "";
         const int kgs = s.K / 128;
         for (int tiles = 1; tiles <= (s.fmt == 0 ? 1 : 2); ++tiles) {
             if (s.N % (128 * tiles)) {
@@ -178,12 +179,20 @@ int main(int argc, char** argv)
                     if (t < best) {
                         best = t;
                         snprintf(best_desc, sizeof(best_desc), "tiles=%d splits=%d nw=%d nx=%d", pl.tiles, pl.splits, pl.nw, pl.nx);
+                        // only plans whose output matched the default's to fp16 rounding noise are worth recording
+                        if (diff <= 1e-2f) {
+                            snprintf(best_plan, sizeof(best_plan), "PLAN %d %d %d %d %d %d %d %d", s.fmt, mt, s.N, s.K, pl.tiles,
+                                     pl.splits, pl.nw, pl.nx);
+                        }
                     }
                 }
             }
         }
         printf("  -> best %s: %.2f us (default %.2f us, %.1f%% faster), %.1f GB/s of weights\n", best_desc, best, t_def,
                (1 - best / t_def) * 100, wbytes / best * 1e-3);
+        if (best_plan[0] && best < 0.97 * t_def) {
+            printf("%s\n", best_plan);  // grep '^PLAN' > plans.txt; B200_GEMM_PLANS=plans.txt or b200_linear_load_plans()
+        }
         g_plan_override = {};
         for (void* p : w) CK(cudaFree(p));
         CK(cudaFree(xp));
