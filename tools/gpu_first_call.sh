@@ -29,3 +29,8 @@ unset B200_RUN_UNVERIFIED
 [ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
 run ref_gemm_bench 300 python tools/ref_gemm_bench.py 64 20
 run bench 420 python bench.py
+# the sweep's winners as a tuned plan table, and the step with it
+cat gpurun_out/gemm_sweep_*.log 2>/dev/null | grep '^PLAN' > gpurun_out/plans.txt
+if [ -s gpurun_out/plans.txt ]; then
+    B200_GEMM_PLANS=gpurun_out/plans.txt run bench_tuned_plans 420 python bench.py --no-cpu-baseline
+fi
