@@ -86,6 +86,8 @@ class TurboMind:
         self.h_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64).pin_memory()
         self._lock = threading.Lock()
         self._next_session = 0
+        self._use_graphs = os.environ.get("B200_ENGINE_GRAPHS", "1") != "0"
+        self._graphs, self._seen_sizes = {}, set()
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, engine_config=None, **kw):
@@ -127,9 +129,28 @@ class TurboMind:
         self.d_cu_k[:B + 1].copy_(self.h_cu_k[:B + 1], non_blocking=True)
         self.d_cu_blocks[:B + 1].copy_(self.h_cu_blocks[:B + 1], non_blocking=True)
         self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
-        self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
-                               block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
-                               max_k_len=st["max_k_len"], token_num=T)
+        def launch():
+            self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
+                                   block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
+                                   max_k_len=st["max_k_len"], token_num=T)
+
+        # A pure decode step is shape-static given the batch size (every argument lives in a fixed device buffer, the
+        # attention work partition is computed on the device), so its ~300 launches are replayed from a CUDA graph per
+        # batch size -- captured the second time that size is seen (the first run doubles as the warm-up).
+        if T == B and self._use_graphs:
+            g = self._graphs.get(B)
+            if g is None and B in self._seen_sizes:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch()
+                self._graphs[B] = g
+            if g is not None:
+                g.replay()
+            else:
+                launch()
+                self._seen_sizes.add(B)
+        else:
+            launch()
         self.h_out[:T].copy_(self.d_out[:T], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         out = self.h_out[:T].tolist()

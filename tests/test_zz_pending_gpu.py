@@ -317,6 +317,16 @@ def test_engine_continuous_batching_is_deterministic(monkeypatch):
     assert a == b and all(len(x) == 12 for x in a)
 
 
+def test_engine_cuda_graph_replay_equals_eager_launches(monkeypatch):
+    monkeypatch.setenv("B200_ENGINE_GRAPHS", "0")
+    eager = _generate(_tiny_engine(monkeypatch), max_new=20)
+    monkeypatch.setenv("B200_ENGINE_GRAPHS", "1")
+    eng = _tiny_engine(monkeypatch)
+    graphed = _generate(eng, max_new=20)
+    assert eng._graphs, "no decode step was replayed from a graph"
+    assert eager == graphed                                   # same kernels, same order, same buffers
+
+
 def test_engine_prefix_caching_does_not_change_tokens(monkeypatch):
     base = _generate(_tiny_engine(monkeypatch))
     eng = _tiny_engine(monkeypatch, prefix=True)
