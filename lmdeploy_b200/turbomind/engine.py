@@ -17,11 +17,13 @@ from .scheduler import Scheduler, Sequence
 from .specs import SPECS, ModelSpec
 
 
-def marshal_step(batch, block_ptr):
+def marshal_step(batch, block_ptr=None):
     """Argument arrays of one (mixed) step for `batch` = [Sequence]: sequence i feeds its `step_tokens` next tokens as
     rows [cu_q_len[i], cu_q_len[i+1]); cu_k_len counts cached history + the fed tokens (AttentionParams::cu_k_len
-    includes the new tokens); block_ptrs is the concatenation of the sequences' block tables through `block_ptr`."""
-    tokens, cu_q, cu_k, ptrs, cu_blocks = [], [0], [0], [], [0]
+    includes the new tokens); block_ids is the concatenation of the sequences' block tables (pool indices -- what a TP
+    leader broadcasts; every rank maps them to addresses of its own pool) and block_ptrs their addresses through
+    `block_ptr` when one is given."""
+    tokens, cu_q, cu_k, ids, cu_blocks = [], [0], [0], [], [0]
     for s in batch:
         toks = s.next_inputs()
         if len(toks) != s.step_tokens:
@@ -31,19 +33,25 @@ def marshal_step(batch, block_ptr):
         tokens += [int(t) for t in toks]
         cu_q.append(cu_q[-1] + len(toks))
         cu_k.append(cu_k[-1] + s.cached + len(toks))
-        ptrs += [block_ptr(b) for b in s.blocks]
-        cu_blocks.append(len(ptrs))
-    return dict(token_ids=tokens, token_num=len(tokens), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
-                cu_block_nums=cu_blocks, max_k_len=max(s.cached + s.step_tokens for s in batch))
+        ids += list(s.blocks)
+        cu_blocks.append(len(ids))
+    st = dict(batch_size=len(batch), token_ids=tokens, token_num=len(tokens), cu_q_len=cu_q, cu_k_len=cu_k, block_ids=ids,
+              cu_block_nums=cu_blocks, max_k_len=max(s.cached + s.step_tokens for s in batch))
+    if block_ptr is not None:
+        st["block_ptrs"] = [block_ptr(b) for b in ids]
+    return st
 
 
 class TurboMind:
     def __init__(self, spec: ModelSpec, engine_config: Optional[TurbomindEngineConfig] = None, *, model: DecodeModel = None,
-                 eos_id: Optional[int] = None, num_blocks: Optional[int] = None, seed=0):
+                 eos_id: Optional[int] = None, num_blocks: Optional[int] = None, seed=0, channel=None):
         cfg = engine_config or TurbomindEngineConfig()
-        if cfg.tp != 1 and model is None:
-            raise NotImplementedError("tp > 1: launch one process per GPU (torchrun) and pass a TP-sharded DecodeModel "
-                                      "(see bench.py / lmdeploy_b200.turbomind.tp.TpGroup)")
+        if cfg.tp != 1 and (model is None or channel is None):
+            raise NotImplementedError("tp > 1: launch one process per GPU (torchrun), give every rank its TP-sharded "
+                                      "DecodeModel (lmdeploy_b200.turbomind.tp.TpGroup) and a StepChannel "
+                                      "(lmdeploy_b200.turbomind.tp_engine); rank 0 drives step(), the others "
+                                      "serve_follower()")
+        self.channel = channel
         self.config = cfg
         self.spec = spec
         self.eos_id = eos_id
@@ -111,16 +119,35 @@ class TurboMind:
 
     # ------------------------------------------------------------------ one engine step
     def step(self):
-        """Schedule + run one decode step for the active batch; returns [(sequence, token|None)] events."""
+        """Schedule + run one step for the active batch; returns [(sequence, token|None)] events.  Under tensor
+        parallelism only the leader (rank 0) calls this; it publishes the step's arrays to the followers first."""
         sched = self.scheduler
         batch = sched.schedule()
         if not batch:
             return []
-        B = len(batch)
-        st = marshal_step(batch, self.pool.ptr)
-        T, cu_q, ptrs = st["token_num"], st["cu_q_len"], st["block_ptrs"]
+        st = marshal_step(batch)
+        if self.channel is not None:
+            self.channel.publish(st)
+        out = self._execute(st)
+        cu_q = st["cu_q_len"]
+        return sched.update(batch, [out[cu_q[i + 1] - 1] for i in range(len(batch))])   # sample = last row of each sequence
+
+    def serve_follower(self):
+        """Tensor-parallel rank > 0: execute the steps the leader publishes until it shuts the channel down.  Every rank
+        owns a KV pool of the same geometry, so the leader's block ids are valid here; the sampled ids are the same on
+        every rank (vocab-sharded argmax exchange) and are ignored by the followers."""
+        while True:
+            st = self.channel.receive()
+            if st is None:
+                return
+            self._execute(st)
+
+    def _execute(self, st):
+        """Upload one step's arrays, run it on this rank's model shard, return the sampled id of every row."""
+        B, T = st["batch_size"], st["token_num"]
+        ptrs = [self.pool.ptr(b) for b in st["block_ids"]]
         self.h_tokens[:T] = torch.tensor(st["token_ids"], dtype=torch.int32)
-        self.h_cu_q[:B + 1] = torch.tensor(cu_q, dtype=torch.int32)
+        self.h_cu_q[:B + 1] = torch.tensor(st["cu_q_len"], dtype=torch.int32)
         self.h_cu_k[:B + 1] = torch.tensor(st["cu_k_len"], dtype=torch.int32)
         self.h_cu_blocks[:B + 1] = torch.tensor(st["cu_block_nums"], dtype=torch.int32)
         self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
@@ -129,6 +156,7 @@ class TurboMind:
         self.d_cu_k[:B + 1].copy_(self.h_cu_k[:B + 1], non_blocking=True)
         self.d_cu_blocks[:B + 1].copy_(self.h_cu_blocks[:B + 1], non_blocking=True)
         self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
+
         def launch():
             self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
                                    block_ptrs=self.d_block_ptrs, cu_block_nums=self.d_cu_blocks, out_tokens=self.d_out,
@@ -153,8 +181,16 @@ class TurboMind:
             launch()
         self.h_out[:T].copy_(self.d_out[:T], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        out = self.h_out[:T].tolist()
-        return sched.update(batch, [out[cu_q[i + 1] - 1] for i in range(B)])     # sample = last row of each sequence
+        return self.h_out[:T].tolist()
+
+    def close(self):
+        """Release tensor-parallel followers (if any) and the communicator."""
+        if self.channel is not None and self.channel.is_leader:
+            self.channel.shutdown()
+        tp = getattr(self, "_tp", None)
+        if tp is not None:
+            tp.close()
+            self._tp = None
 
     def get_schedule_metrics(self, index=0):
         """ScheduleMetrics of this rank (TurboMind.get_schedule_metrics, lmdeploy/turbomind/turbomind.py)."""

@@ -89,3 +89,81 @@ def test_tp2_gloo_matches_single_process_oracle():
     c1 = OA.PagedKvCache(2, w.layers, OA.KvLayout(2, 64, 128, 8), F16)
     ref1, _ = decode_step(w, np.array([3, 9]), c1, [[0], [1]], np.array([0, 0], np.int32), rope)
     assert np.abs(ref1 - ref).max() < 2e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# engine control plane: rank 0 schedules and publishes every step, the other rank follows
+# ---------------------------------------------------------------------------------------------------------------
+def _engine_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lmdeploy_b200.turbomind.engine import marshal_step
+    from lmdeploy_b200.turbomind.scheduler import Scheduler, Sequence
+    from lmdeploy_b200.turbomind.tp_engine import StepChannel
+    block_len, num_blocks = 4, 32
+    store = [[None] * block_len for _ in range(num_blocks)]        # this rank's "KV pool": which token sits where
+
+    def execute(st):
+        """What TurboMind._execute does with the arrays, on a toy pool: write the fed tokens at their positions through
+        the block table, then 'sample' a hash of everything each sequence can see."""
+        out = []
+        for i in range(st["batch_size"]):
+            rows = st["token_ids"][st["cu_q_len"][i]:st["cu_q_len"][i + 1]]
+            k_len = st["cu_k_len"][i + 1] - st["cu_k_len"][i]
+            blocks = st["block_ids"][st["cu_block_nums"][i]:st["cu_block_nums"][i + 1]]
+            hist = k_len - len(rows)
+            for j, t in enumerate(rows):
+                store[blocks[(hist + j) // block_len]][(hist + j) % block_len] = t
+            h = 1469598103934665603
+            for p in range(k_len):
+                h = ((h ^ (store[blocks[p // block_len]][p % block_len] + 1)) * 1099511628211) % (1 << 64)
+            out += [0] * (len(rows) - 1) + [h % 50000]
+        return out
+
+    ch = StepChannel(rank, world)
+    steps = 0
+    if ch.is_leader:
+        sched = Scheduler(max_batch=3, block_len=block_len, num_blocks=num_blocks, session_len=256, prefill_chunk=5,
+                          token_budget=8, prefix_caching=True)
+        prompts = [list(range(10, 23)), [7], list(range(10, 20)) + [1, 2]]
+        seqs = [Sequence(session_id=i, prompt=p, max_new_tokens=4, stop_token_ids=[], ignore_eos=True, eos_id=None)
+                for i, p in enumerate(prompts)]
+        for s in seqs:
+            sched.add(s)
+        while sched.has_work:
+            batch = sched.schedule()
+            st = marshal_step(batch)
+            ch.publish(st)
+            out = execute(st)
+            sched.update(batch, [out[st["cu_q_len"][i + 1] - 1] for i in range(len(batch))])
+            steps += 1
+        ch.shutdown()
+        q.put((rank, steps, [list(s.generated) for s in seqs], store))
+    else:
+        while True:
+            st = ch.receive()
+            if st is None:
+                break
+            execute(st)
+            steps += 1
+        assert not ch.open
+        q.put((rank, steps, None, store))
+    dist.destroy_process_group()
+
+
+def test_engine_leader_publishes_every_step_and_followers_mirror_the_kv_pool():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_engine_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, steps0, generated, store0), (_, steps1, _, store1) = res
+    assert steps0 == steps1 > 0
+    assert store0 == store1                       # the follower wrote exactly what the leader wrote, where it wrote it
+    assert all(len(g) == 4 for g in generated)
