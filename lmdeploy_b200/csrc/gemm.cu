@@ -167,6 +167,7 @@ struct Plan {
 // A plan the heuristic below is told to use instead of its own choice: fields > 0 replace the heuristic's value.
 struct PlanOverride {
     int tiles, splits, nw, nx;
+    int variant;  // tool builds only (gemm.cuh Params::variant)
 };
 
 #ifdef B200_GEMM_TOOL
@@ -209,7 +210,7 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     PlanOverride ov{};
     lookup_plan(fmt, MT, N, K, &ov);
 #ifdef B200_GEMM_TOOL
-    if (g_plan_override.tiles > 0 || g_plan_override.splits > 0 || g_plan_override.nw > 0) {
+    if (g_plan_override.tiles > 0 || g_plan_override.splits > 0 || g_plan_override.nw > 0 || g_plan_override.variant) {
         ov = g_plan_override;
     }
 #endif
@@ -486,6 +487,9 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.M        = m;
     const Plan rg = make_plan(d->weight_format, mt, p.N, p.K);
     p.splits = rg.splits, p.nw = rg.nw, p.nx = rg.nx, p.na = rg.na;
+#ifdef B200_GEMM_TOOL
+    p.variant = g_plan_override.variant;
+#endif
     p.tmem_cols = rg.tmem_cols, p.a_col = rg.a_col;
     if (epilogue == 2) {
         // the fused residual + RMSNorm epilogue lives in the split-K exchange: it needs splits > 1 and a bounded number

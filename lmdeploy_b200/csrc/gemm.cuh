@@ -133,6 +133,10 @@ struct Params {
     int            out_mt;
     int            tmem_cols;  // 256 or 512 (power of two)
     int            a_col;      // first TMEM column of the A-operand ring
+#ifdef B200_GEMM_TOOL
+    int            variant;    // tools/gemm_sweep.cu only: bit 0 = the W producer issues a slot's copies from several
+                               // lanes at once, bit 1 = ... and each tile's block as two half-size copies
+#endif
 };
 
 B200_DEVICE int w_block_bytes(int fmt)
@@ -267,6 +271,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 
     if (warp == 0) {
         // ================================ W producer (starts before TMEM is allocated) ================================
+#ifdef B200_GEMM_TOOL
+        if (p.variant & 3) {
+            // Experiment: is the producer bound by the ~300 cycles it takes ONE lane to issue a bulk copy?  Lane 0 waits
+            // for the slot and arms the barrier; the copies of the slot are then issued by 2 or 4 lanes in parallel.
+            const uint64_t pol_w  = make_evict_first_policy();
+            const int      parts  = (p.variant & 2) ? 2 : 1;         // copies per tile block
+            const int      PB     = WB / parts;                      // 8704 / 2 = 4352: still a multiple of 16
+            const int      n_copy = TILES * parts;
+            int            s      = 0;
+            uint32_t       ph     = 0;
+            const uint8_t* src    = p.w + ((size_t)nt0 * kgs + kg0) * WB;
+            for (int i = 0; i < nk; ++i) {
+                const uint32_t bar = smem_u32(&bar_wfull[s]);
+                if (lane == 0) {
+                    GEMM_WAIT(smem_u32(&bar_wempty[s]), ph ^ 1, 1, i);
+                    mbar_expect_tx(bar, WB * TILES);
+                }
+                __syncwarp();
+                if (lane < n_copy) {
+                    const int t = lane / parts, h = lane % parts;
+                    bulk_g2s_hint(w_ring + (uint32_t)s * WSLOT + t * WB_pad + h * PB, src + ((size_t)t * kgs + i) * WB + h * PB,
+                                  PB, bar, pol_w);
+                }
+                if (++s == p.nw) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        else
+#endif
         if (lane == 0) {
             const uint64_t pol_w = make_evict_first_policy();
             int      s  = 0;

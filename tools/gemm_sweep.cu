@@ -141,6 +141,26 @@ int main(int argc, char** argv)
         CK(cudaStreamSynchronize(st));
         printf("%-8s %-5s K=%5d N=%5d m=%d  default: tiles=%d splits=%d nw=%d nx=%d  %7.2f us  %7.1f GB/s\n", s.model, s.name,
                s.K, s.N, m, def.tiles, def.splits, def.nw, def.nx, t_def, wbytes / t_def * 1e-3);
+        // producer experiments on the default plan (gemm.cuh, Params::variant)
+        for (int variant = 1; variant <= 3 && s.fmt != 0; ++variant) {
+            if ((variant & 2) && b200::gemm::block_bytes_of(s.fmt) % 32) {
+                continue;  // half of the block must still be a multiple of the 16-byte bulk-copy granule
+            }
+            g_plan_override         = {};
+            g_plan_override.variant = variant;
+            const double t = time_plan();
+            CK(cudaMemsetAsync(d_diff, 0, 4, st));
+            run(0, y);
+            max_diff_kernel<<<256, 256, 0, st>>>((const half*)y, (const half*)y_ref, out_elems, d_diff);
+            float diff;
+            CK(cudaMemcpyAsync(&diff, d_diff, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            printf("    W-producer variant %d (%s): %7.2f us  (%+5.1f%%)  max|y - y_default| = %g\n", variant,
+                   variant == 1 ? "one lane per tile" : variant == 2 ? "two half copies per tile, one lane" :
+                                                                       "two half copies per tile, four lanes",
+                   t, (t / t_def - 1) * 100, diff);
+        }
+        g_plan_override = {};
         double best = t_def;
         char   best_desc[128] = "default";
         char   best_plan[128] = "";
@@ -155,13 +175,13 @@ int main(int argc, char** argv)
                     continue;  // cooperative launch needs one wave; K-groups divide evenly
                 }
                 for (int depth = 0; depth < 3; ++depth) {
-                    g_plan_override = {tiles, splits, 0, 0};
+                    g_plan_override = {tiles, splits, 0, 0, 0};
                     const Plan base = make_plan(s.fmt, mt, s.N, s.K);
                     if (depth == 1) {  // deeper X ring, shallower W ring
-                        g_plan_override = {tiles, splits, std::max(3, base.nw - 2), std::min(6, base.nx + 1)};
+                        g_plan_override = {tiles, splits, std::max(3, base.nw - 2), std::min(6, base.nx + 1), 0};
                     }
                     else if (depth == 2) {  // shallower X ring, deeper W ring
-                        g_plan_override = {tiles, splits, std::min(8, base.nw + 1), std::max(2, base.nx - 1)};
+                        g_plan_override = {tiles, splits, std::min(8, base.nw + 1), std::max(2, base.nx - 1), 0};
                     }
                     const Plan pl = make_plan(s.fmt, mt, s.N, s.K);
                     if (pl.smem > 226 * 1024 || (depth && pl.nw == base.nw && pl.nx == base.nx)) {
