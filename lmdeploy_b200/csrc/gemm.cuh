@@ -135,7 +135,8 @@ struct Params {
     int            a_col;      // first TMEM column of the A-operand ring
 #ifdef B200_GEMM_TOOL
     int            variant;    // tools/gemm_sweep.cu only: bit 0 = the W producer issues a slot's copies from several
-                               // lanes at once, bit 1 = ... and each tile's block as two half-size copies
+                               // lanes at once, bit 1 = ... and each tile's block as two half-size copies,
+                               // bit 2 = the X producer issues the activation tile as four copies from four lanes
 #endif
 };
 
@@ -326,6 +327,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     }
     else if (warp == kXWarp) {
         // ================================ X producer ================================
+#ifdef B200_GEMM_TOOL
+        if (p.variant & 4) {
+            // Experiment: the activation tile of a slot as four quarter-size copies issued by four lanes.
+            int            s   = 0;
+            uint32_t       ph  = 0;
+            const int      QB  = XB / 4;  // MT * 64 bytes: a multiple of 16
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.xp) + (size_t)kg0 * XB;
+            pdl_wait();
+            for (int i = 0; i < nk; ++i) {
+                const uint32_t bar = smem_u32(&bar_xfull[s]);
+                if (lane == 0) {
+                    GEMM_WAIT(smem_u32(&bar_xempty[s]), ph ^ 1, 6, i);
+                    mbar_expect_tx(bar, XB);
+                }
+                __syncwarp();
+                if (lane < 4) {
+                    bulk_g2s(x_ring + (uint32_t)s * XB + lane * QB, src + (size_t)i * XB + lane * QB, QB, bar);
+                }
+                if (++s == p.nx) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        else
+#endif
         if (lane == 0) {
             int      s  = 0;
             uint32_t ph = 0;
