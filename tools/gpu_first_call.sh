@@ -1,7 +1,7 @@
 #!/bin/bash
 # First GPU call of a round: everything that was written or changed without a device gets its first run, each step under
 # its own timeout so one hang cannot eat the call.  Outputs land in gpurun_out/.
-#   bash tools/build_tools.sh && gpurun --timeout 1500 -- 'bash tools/gpu_first_call.sh'
+#   bash tools/build_tools.sh && gpurun --timeout 2700 -- 'bash tools/gpu_first_call.sh'   (typically ~15 min; every step has its own limit)
 set -u
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
