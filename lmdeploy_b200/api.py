@@ -18,8 +18,16 @@ class Pipeline:
                 self.tokenizer = AutoTokenizer.from_pretrained(model_path)
 
     def _encode(self, prompt):
+        """A prompt is a list of token ids, a string, or OpenAI-style messages [{"role": ..., "content": ...}, ...]
+        (rendered with the tokenizer's chat template, as the reference's pipeline does through its chat templates,
+        lmdeploy/pipeline.py / lmdeploy/model.py)."""
+        if isinstance(prompt, (list, tuple)) and prompt and isinstance(prompt[0], dict):
+            if self.tokenizer is None:
+                raise ValueError("chat messages need a tokenizer")
+            ids = self.tokenizer.apply_chat_template(list(prompt), add_generation_prompt=True, tokenize=True)
+            return list(ids["input_ids"] if isinstance(ids, dict) else ids)
         if isinstance(prompt, (list, tuple)):
-            return list(prompt)
+            return [int(t) for t in prompt]
         if self.tokenizer is None:
             raise ValueError("no tokenizer: pass prompts as lists of token ids")
         return self.tokenizer.encode(prompt)
@@ -27,7 +35,7 @@ class Pipeline:
     def __call__(self, prompts: Union[str, List[int], List[str], List[List[int]]],
                  gen_config: Optional[GenerationConfig] = None, **kw):
         single = isinstance(prompts, str) or (isinstance(prompts, (list, tuple)) and prompts
-                                              and isinstance(prompts[0], int))
+                                              and isinstance(prompts[0], (int, dict)))
         plist = [prompts] if single else list(prompts)
         ids = [self._encode(p) for p in plist]
         if gen_config is not None and (gen_config.stop_words or gen_config.bad_words):

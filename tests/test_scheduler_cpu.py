@@ -444,3 +444,28 @@ def test_stop_words_become_stop_token_ids_with_the_reference_rule():
     g = GenerationConfig(stop_token_ids=[5])
     g.update_from_hf_gen_cfg({"eos_token_id": [1, 9]}, tokenizer_eos_token_id=1)
     assert g.stop_token_ids == [1, 5, 9]
+
+
+def test_pipeline_prompt_forms_without_a_device():
+    """Pipeline._encode / single-vs-batch detection: token ids, text, chat messages (no engine is constructed)."""
+    from lmdeploy_b200.api import Pipeline
+
+    class Tok(_FakeTokenizer):
+        def apply_chat_template(self, messages, add_generation_prompt=True, tokenize=True):
+            assert add_generation_prompt and tokenize
+            out = [0]
+            for m in messages:
+                out += self.encode(m["content"])
+            return out + [1]
+
+    p = Pipeline.__new__(Pipeline)
+    p.tokenizer = Tok()
+    assert p._encode([5, 6, 7]) == [5, 6, 7]
+    assert p._encode("!!") == [5]
+    assert p._encode([{"role": "user", "content": "!"}, {"role": "assistant", "content": "!!"}]) == [0, 4, 5, 1]
+    p.tokenizer = None
+    assert p._encode((1, 2)) == [1, 2]
+    with pytest.raises(ValueError):
+        p._encode("text")
+    with pytest.raises(ValueError):
+        p._encode([{"role": "user", "content": "x"}])
