@@ -214,8 +214,8 @@ static Plan make_plan(int fmt, int MT, int N, int K)
         ov = g_plan_override;
     }
 #endif
-    if (ov.tiles > 0 && fmt != kDense && N % (kBN * ov.tiles) == 0) {
-        pl.tiles = ov.tiles;
+    if (ov.tiles > 0 && fmt != kDense && N % (kBN * ov.tiles) == 0 && (ov.tiles <= 2 || MT <= 64)) {
+        pl.tiles = ov.tiles;  // 4 tiles (tool builds only): 4 x 64 accumulator columns, so <= 64 tokens
     }
     const bool two_per_sm = false;  // 640-thread CTAs at ~90 registers: one CTA per SM in every configuration
     const int  nts = N / (kBN * pl.tiles), kgs = K / kKG;
@@ -506,6 +506,11 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.out_mt   = out_mt;
     const bool bf = d->dtype == B200_DTYPE_BF16;
     if (d->weight_format == kU4) {
+#ifdef B200_GEMM_TOOL
+        if (rg.tiles == 4) {
+            return bf ? launch<nv_bfloat16, kU4, 4>(p, rg.smem, st) : launch<half, kU4, 4>(p, rg.smem, st);
+        }
+#endif
         if (rg.tiles == 2) {
             return bf ? launch<nv_bfloat16, kU4, 2>(p, rg.smem, st) : launch<half, kU4, 2>(p, rg.smem, st);
         }

@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     constexpr int  WB_pad   = (WB + 1023) & ~1023;
     constexpr int  WSLOT    = WB_pad * TILES;
     constexpr bool kDequant = FMT != kDense;
+    constexpr int  kMmaWarps = TILES >= 2 ? 2 : 1;  // MMA-issuing warps (TILES == 4, tool builds: two tiles per warp)
+    static_assert(TILES == 1 || TILES == 2 || TILES == 4, "1, 2 or (tool builds) 4 n-tiles per CTA");
     const int      NAt      = p.na / TILES;  // A-ring slots per tile (tile t owns slots [t * NAt, (t + 1) * NAt))
     static_assert(kDequant || TILES == 1, "dense weights use one tile per CTA");
     const int      XB       = p.MT * 256;  // 16 k8-chunks x MT x 16 B
@@ -259,13 +261,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         }
         for (int s = 0; s < kMaxX; ++s) {
             mbar_init(smem_u32(&bar_xfull[s]), 1);
-            mbar_init(smem_u32(&bar_xempty[s]), TILES);
+            mbar_init(smem_u32(&bar_xempty[s]), kMmaWarps);
         }
         for (int s = 0; s < kASlots; ++s) {
             mbar_init(smem_u32(&bar_aready[s]), kDqWarps * 32 / TILES);
             mbar_init(smem_u32(&bar_aempty[s]), 1);
         }
-        mbar_init(smem_u32(&bar_dready), TILES);
+        mbar_init(smem_u32(&bar_dready), kMmaWarps);
         fence_mbar_init();
     }
     __syncthreads();
@@ -389,7 +391,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             // costs two uniform adds + UTCHMMA.  A UTCHMMA still costs ~50 issue cycles, more than the 32 tensor
             // cycles of a 128x64x16 MMA, so each tile of a two-tile CTA gets its own issuing warp.
             const int t = warp == 1 ? 0 : 1;
-            if (t < TILES) {
+            if constexpr (TILES == 4) {
+                // Four tiles share each activation tile (ingest 1.5 W instead of 2 W per weight byte).  Each issuing warp
+                // owns two tiles and alternates between them inside a k-group; TMEM leaves one A slot per tile
+                // (4 x 64 accumulator columns + 4 x 64), so a tile's next de-quantisation overlaps the other tile's MMAs.
+                const uint32_t idesc  = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
+                const uint32_t b_step = (uint32_t)(2 * p.MT * 16) >> 4;
+                int            sx = 0, sa = 0;
+                uint32_t       phx = 0, pha = 0;
+                for (int i = 0; i < nk; ++i) {
+                    GEMM_WAIT(smem_u32(&bar_xfull[sx]), phx, 2, i);
+                    const uint64_t bd0 = umma::make_smem_desc(x_ring + (uint32_t)sx * XB, p.MT * 16, 128);
+#pragma unroll
+                    for (int tt = 0; tt < 2; ++tt) {
+                        const int      tile = 2 * t + tt;
+                        const int      slot = tile * NAt + sa;
+                        const uint32_t d_tm = tmem + tile * d_stride;
+                        const uint32_t a_tm = tmem + p.a_col + slot * 64;
+                        GEMM_WAIT(smem_u32(&bar_aready[slot]), pha, 3, i);
+                        umma::fence_after_sync();
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < kKG / 16; ++ks) {
+                                umma::mma_f16_ts(d_tm, a_tm + ks * 8, bd0 + (uint64_t)(ks * b_step), idesc,
+                                                 (i > 0 || ks > 0) ? 1u : 0u);
+                            }
+                            umma::commit(smem_u32(&bar_aempty[slot]));
+                            if (tt == 1) {
+                                umma::commit(smem_u32(&bar_xempty[sx]));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (++sa == NAt) {
+                        sa = 0;
+                        pha ^= 1;
+                    }
+                    if (++sx == p.nx) {
+                        sx = 0;
+                        phx ^= 1;
+                    }
+                }
+                if (elect_one()) {
+                    umma::commit(smem_u32(&bar_dready));
+                }
+                __syncwarp();
+            }
+            else if (t < TILES) {
                 const uint32_t idesc  = umma::make_idesc_f16(kBN, p.MT, std::is_same<T, nv_bfloat16>::value);
                 const uint32_t b_step = (uint32_t)(2 * p.MT * 16) >> 4;  // descriptor start-address units per k-step
                 const uint32_t a_step = (uint32_t)(2 * kBN * 16) >> 4;
@@ -458,9 +506,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             // two tiles of a k-group are de-quantised concurrently and every thread still observes every phase of the
             // barriers it waits on.
             const int      dw        = warp - 2;
-            const int      my_tile   = TILES == 2 ? (dw >> 3) : 0;
-            const int      kc0       = TILES == 2 ? ((dw >> 2) & 1) * 2 : (dw >> 2);  // first 32-wide k-chunk
-            constexpr int  NKC       = TILES == 2 ? 2 : 1;                            // k-chunks per thread
+            // TILES == 4 (tool builds): 4 warps per tile (one per lane quarter), all four k-chunks each.
+            const int      my_tile   = TILES == 4 ? (dw >> 2) : TILES == 2 ? (dw >> 3) : 0;
+            const int      kc0       = TILES == 4 ? 0 : TILES == 2 ? ((dw >> 2) & 1) * 2 : (dw >> 2);  // first 32-wide k-chunk
+            constexpr int  NKC       = TILES == 4 ? 4 : TILES == 2 ? 2 : 1;                            // k-chunks per thread
             const int      lane_base = 32 * (warp & 3);   // TMEM lanes this warp may touch
             const int      n_local   = lane_base + lane;
             const uint32_t trow      = tmem + ((uint32_t)lane_base << 16);
@@ -550,8 +599,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             }
             // epilogue role: (tile, token half) of the accumulator rows in this warp's lane quarter
             const int  epi_tile   = my_tile;
-            const int  epi_half   = TILES == 2 ? ((dw >> 2) & 1) : (dw >> 2);
-            const bool epi_active = TILES == 2 || (dw >> 2) < 2;
+            const int  epi_half   = TILES == 4 ? 0 : TILES == 2 ? ((dw >> 2) & 1) : (dw >> 2);
+            const bool epi_active = TILES >= 2 || (dw >> 2) < 2;
             // ============================== epilogue, part 1 ==============================
             // splits == 1: straight to the output.  splits > 1: fp32 partials to the L2-resident exchange buffer.
             GEMM_WAIT(smem_u32(&bar_dready), 0, 5, 0);
@@ -559,7 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             pdl_wait();  // already satisfied (the MMAs consumed upstream activations); orders this thread's global
                          // accesses (output / exchange buffers may still be read by an upstream kernel otherwise)
             if (threadIdx.x == 64) GEMM_TRACE(4, 2);
-            const int half = p.MT >> 1;
+            const int half = TILES == 4 ? p.MT : p.MT >> 1;  // TILES == 4: one warp per (tile, lane quarter) takes every token
             const int tb = epi_half * half, te = tb + half;
             const uint32_t drow = trow + epi_tile * d_stride;
             if (p.splits == 1) {

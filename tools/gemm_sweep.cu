@@ -168,8 +168,9 @@ int main(int argc, char** argv)
         char   best_desc[128] = "default";
         char   best_plan[128] = "";
         const int kgs = s.K / 128;
-        for (int tiles = 1; tiles <= (s.fmt == 0 ? 1 : 2); ++tiles) {
-            if (s.N % (128 * tiles)) {
+        for (int tiles : {1, 2, 4}) {
+            // 4 tiles per CTA: tool-only kernel variant (u4, <= 64 tokens); dense weights: one tile
+            if (s.N % (128 * tiles) || (s.fmt == 0 && tiles > 1) || (tiles == 4 && (s.fmt != 1 || mt > 64))) {
                 continue;
             }
             const int nts = s.N / (128 * tiles);
