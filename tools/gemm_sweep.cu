@@ -4,7 +4,7 @@
 // table for this shape?" (the reference does the same search at run time: gemm/tuner, dispatch_cache.cu).
 //   nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --expt-relaxed-constexpr \
 //        -DB200_GEMM_TOOL -o build/gemm_sweep tools/gemm_sweep.cu
-//   build/gemm_sweep [model: 7b|20b|8b|70b-tp8|all] [m=64] [iters=20]
+//   build/gemm_sweep [model: 7b|20b|8b|70b-tp8|all] [m=64] [iters=20] [tiles mask=3]
 #include "../lmdeploy_b200/csrc/capi_common.cu"
 #include "../lmdeploy_b200/csrc/gemm.cu"
 
@@ -65,6 +65,8 @@ int main(int argc, char** argv)
     const std::string model = argc > 1 ? argv[1] : "7b";
     const int         m     = argc > 2 ? atoi(argv[2]) : 64;
     const int         iters = argc > 3 ? atoi(argv[3]) : 20;
+    const int         tmask = argc > 4 ? atoi(argv[4]) : 3;  // which tiles-per-CTA values to sweep: bit0 1, bit1 2, bit2 4
+                                                             // (4 = the tool-only kernel variant: run it in its own call)
     const int         mt    = (m + 15) / 16 * 16;
     setvbuf(stdout, nullptr, _IONBF, 0);
     cudaStream_t st;
@@ -143,7 +145,7 @@ int main(int argc, char** argv)
                s.K, s.N, m, def.tiles, def.splits, def.nw, def.nx, t_def, wbytes / t_def * 1e-3);
         // producer experiments on the default plan (gemm.cuh, Params::variant)
         for (int variant : {1, 2, 4, 5, 6}) {
-            if (s.fmt == 0) {
+            if (s.fmt == 0 || !(tmask & 3)) {
                 break;
             }
             if ((variant & 2) && b200::gemm::block_bytes_of(s.fmt) % 32) {
@@ -170,7 +172,7 @@ int main(int argc, char** argv)
         const int kgs = s.K / 128;
         for (int tiles : {1, 2, 4}) {
             // 4 tiles per CTA: tool-only kernel variant (u4, <= 64 tokens); dense weights: one tile
-            if (s.N % (128 * tiles) || (s.fmt == 0 && tiles > 1) || (tiles == 4 && (s.fmt != 1 || mt > 64))) {
+            if (!(tmask & tiles) || s.N % (128 * tiles) || (s.fmt == 0 && tiles > 1) || (tiles == 4 && (s.fmt != 1 || mt > 64))) {
                 continue;
             }
             const int nts = s.N / (128 * tiles);

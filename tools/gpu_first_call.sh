@@ -25,12 +25,13 @@ run pending_engine 420 $P -k "engine"
 unset B200_RUN_UNVERIFIED
 [ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
 [ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
+[ -x build/gemm_sweep ] && run gemm_sweep_7b_4tiles 120 build/gemm_sweep 7b 64 20 4     # tool-only 4-tile kernel, own process
 [ -x build/tma_issue_rate ] && run tma_issue_rate 120 build/tma_issue_rate
 [ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
 run ref_gemm_bench 300 python tools/ref_gemm_bench.py 64 20
 run bench 420 python bench.py
 # the sweep's winners as a tuned plan table, and the step with it
-cat gpurun_out/gemm_sweep_*.log 2>/dev/null | grep '^PLAN' > gpurun_out/plans.txt
+cat gpurun_out/gemm_sweep_7b.log gpurun_out/gemm_sweep_70b.log 2>/dev/null | grep '^PLAN' > gpurun_out/plans.txt
 if [ -s gpurun_out/plans.txt ]; then
     B200_GEMM_PLANS=gpurun_out/plans.txt run bench_tuned_plans 420 python bench.py --no-cpu-baseline
 fi
