@@ -469,3 +469,90 @@ def test_pipeline_prompt_forms_without_a_device():
         p._encode("text")
     with pytest.raises(ValueError):
         p._encode([{"role": "user", "content": "x"}])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# randomized: prefix caching x chunked prefill x memory pressure x cancellation
+# ---------------------------------------------------------------------------------------------------------------
+def _drive(prompts, max_new, *, num_blocks, max_batch, prefill_chunk, token_budget, prefix_caching, cancel_at, arrivals,
+           block_len=4):
+    """Run a workload to completion; returns {session: (generated, finish_reason)}.  Sequences arrive at given steps,
+    one session may be cancelled at a given step.  Invariants are asserted every step."""
+    sched = Scheduler(max_batch=max_batch, block_len=block_len, num_blocks=num_blocks, session_len=4096,
+                      prefix_caching=prefix_caching, prefill_chunk=prefill_chunk, token_budget=token_budget)
+    model = FakeChunkModel(num_blocks, block_len)
+    seqs = {}
+    step = 0
+    pending = sorted(range(len(prompts)), key=lambda i: arrivals[i])
+    while pending or sched.has_work:
+        while pending and arrivals[pending[0]] <= step:
+            i = pending.pop(0)
+            seqs[i] = Sequence(session_id=i, prompt=list(prompts[i]), max_new_tokens=max_new[i], stop_token_ids=[],
+                               ignore_eos=True, eos_id=None)
+            sched.add(seqs[i])
+        if cancel_at is not None and cancel_at[1] == step:
+            sched.cancel(cancel_at[0])
+        batch = sched.schedule()
+        if not batch:
+            if not pending and not sched.has_work:
+                break
+            step += 1
+            assert step < 5000, "scheduler makes no progress"
+            continue
+        assert len(batch) <= max_batch and sum(s.step_tokens for s in batch) <= sched.token_budget
+        owners = {}
+        for s in sched.active:
+            for j, b in enumerate(s.blocks):
+                owners.setdefault(b, []).append((s, j))
+        for b, who in owners.items():
+            if len(who) > 1:        # shared: must be a published block, entirely below every holder's write position
+                assert sched.prefix is not None and b in sched.prefix.node_of
+                for s, j in who:
+                    assert (j + 1) * block_len <= s.cached
+        for s in batch:
+            assert len(s.blocks) * block_len >= s.cached + s.step_tokens
+        idle = sched.prefix.num_idle if sched.prefix else 0
+        assert len(owners) + sched.alloc.num_free + idle == num_blocks
+        sched.update(batch, model.step(batch))
+        step += 1
+        assert step < 5000
+    sched.schedule()
+    idle = sched.prefix.num_idle if sched.prefix else 0
+    assert sched.alloc.num_free + idle == num_blocks and not sched.sessions
+    return {i: (list(s.generated), s.finish_reason) for i, s in seqs.items()}
+
+
+def test_randomized_workloads_agree_with_the_plain_scheduler():
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    prompt = st.lists(st.integers(0, 5), min_size=1, max_size=22)        # tiny alphabet: many shared prefixes
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(prompts=st.lists(prompt, min_size=1, max_size=6), data=st.data())
+    def run(prompts, data):
+        n = len(prompts)
+        max_new = [data.draw(st.integers(0, 5)) for _ in range(n)]
+        arrivals = [data.draw(st.integers(0, 12)) for _ in range(n)]
+        max_batch = data.draw(st.integers(1, 4))
+        chunk = data.draw(st.sampled_from([1, 2, 5, 64]))
+        budget = data.draw(st.integers(max_batch, 12))
+        roomy = sum((len(p) + m + 3) // 4 + 1 for p, m in zip(prompts, max_new)) + 2
+        base = _drive(prompts, max_new, num_blocks=roomy, max_batch=max_batch, prefill_chunk=1, token_budget=None,
+                      prefix_caching=False, cancel_at=None, arrivals=arrivals)
+        got = _drive(prompts, max_new, num_blocks=roomy, max_batch=max_batch, prefill_chunk=chunk, token_budget=budget,
+                     prefix_caching=True, cancel_at=None, arrivals=arrivals)
+        assert got == base
+        # under memory pressure and with a cancellation the run must still terminate with exact accounting, and every
+        # sequence that finished normally must have produced the same tokens
+        tight = max((len(p) + m + 3) // 4 + 1 for p, m in zip(prompts, max_new)) + data.draw(st.integers(0, 3))
+        cancel = (data.draw(st.integers(0, n - 1)), data.draw(st.integers(0, 20))) if data.draw(st.booleans()) else None
+        pressed = _drive(prompts, max_new, num_blocks=tight, max_batch=max_batch, prefill_chunk=chunk, token_budget=budget,
+                         prefix_caching=True, cancel_at=cancel, arrivals=arrivals)
+        for i, (gen, why) in pressed.items():
+            if why in ("stop",) or (why == "length" and len(gen) == max_new[i]):
+                assert gen == base[i][0]
+            else:
+                assert gen == base[i][0][:len(gen)]          # cut short (cancelled / out of KV memory): a prefix
+
+    run()
