@@ -28,8 +28,11 @@ constexpr int kMaxDepth = 16;
 // One warp per CTA, one CTA per SM.  `depth` slots of `bytes` each; `iters` rounds.  issue_lanes == 1: lane 0 issues
 // every copy of a round back to back; issue_lanes == depth: lane i issues the copy of slot i.
 // out[blockIdx.x] = {cycles spent issuing (sum over rounds, issuing lane max), total cycles}
+// scatter != 0: the chunks of a CTA's region are visited in a pseudo-random order (multiplicative hash of the chunk
+// index) instead of sequentially -- what a paged KV cache with a shuffled block table looks like to HBM.
 __global__ void __launch_bounds__(32) ingest_kernel(const uint8_t* src, size_t src_stride_per_cta, size_t src_bytes_per_cta,
-                                                    int bytes, int depth, int iters, int issue_lanes, long long* out)
+                                                    int bytes, int depth, int iters, int issue_lanes, long long* out,
+                                                    int scatter)
 {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t                       bar[kMaxDepth];
@@ -40,6 +43,14 @@ __global__ void __launch_bounds__(32) ingest_kernel(const uint8_t* src, size_t s
     }
     __syncwarp();
     const uint8_t* base  = src + (size_t)blockIdx.x * src_stride_per_cta;
+    const size_t   nchunk = src_bytes_per_cta / bytes;
+    auto           where = [&](size_t linear_off) -> size_t {
+        if (!scatter) {
+            return linear_off % src_bytes_per_cta;
+        }
+        const size_t c = (linear_off / bytes) % nchunk;
+        return ((c * 2654435761ull + 12345u * blockIdx.x) % nchunk) * (size_t)bytes;
+    };
     size_t         off   = 0;
     long long      t_iss = 0;
     const long long t0   = clock64();
@@ -50,8 +61,7 @@ __global__ void __launch_bounds__(32) ingest_kernel(const uint8_t* src, size_t s
                 const long long a = clock64();
                 for (int s = 0; s < depth; ++s) {
                     mbar_expect_tx(smem_u32(&bar[s]), bytes);
-                    bulk_g2s(smem_u32(smem) + s * bytes, base + (off + (size_t)s * bytes) % src_bytes_per_cta, bytes,
-                             smem_u32(&bar[s]));
+                    bulk_g2s(smem_u32(smem) + s * bytes, base + where(off + (size_t)s * bytes), bytes, smem_u32(&bar[s]));
                 }
                 t_iss += clock64() - a;
             }
@@ -59,8 +69,7 @@ __global__ void __launch_bounds__(32) ingest_kernel(const uint8_t* src, size_t s
         else if (lane < depth) {
             const long long a = clock64();
             mbar_expect_tx(smem_u32(&bar[lane]), bytes);
-            bulk_g2s(smem_u32(smem) + lane * bytes, base + (off + (size_t)lane * bytes) % src_bytes_per_cta, bytes,
-                     smem_u32(&bar[lane]));
+            bulk_g2s(smem_u32(smem) + lane * bytes, base + where(off + (size_t)lane * bytes), bytes, smem_u32(&bar[lane]));
             t_iss += clock64() - a;
         }
         off += (size_t)depth * bytes;
@@ -116,7 +125,7 @@ int main()
                     for (int rep = 0; rep < 2; ++rep) {  // first run warms the instruction cache (and L2 for the hot case)
                         CK(cudaEventRecord(e0));
                         ingest_kernel<<<sms, 32, bytes * depth>>>(l2 ? d_l2 : d_hbm, l2 ? 0 : per_cta, per_cta, bytes, depth,
-                                                                 iters, lanes, d_out);
+                                                                 iters, lanes, d_out, 0);
                         CK(cudaEventRecord(e1));
                         CK(cudaDeviceSynchronize());
                     }
@@ -135,6 +144,33 @@ int main()
                     }
                 }
             }
+        }
+    }
+    // (3) Paged-KV access pattern: every SM streams its own region of HBM in chunks of one (block, head) K or V tile
+    // (8 KB for int8 KV, block_len 64), several copies in flight, chunks visited sequentially vs in shuffled order; with
+    // 3 resident warps per SM (the attention kernel runs 3 CTAs per SM).  If "shuffled" sits near 0.75 of "sequential",
+    // the decode-attention kernel is at the ceiling of this access pattern and only a larger contiguous unit
+    // (block_len 128 -> 16 KB) can lift it.
+    printf("\npaged-KV pattern (HBM, %d CTAs = 3 per SM, 8 copies in flight each, issued by 8 lanes):\n", 3 * sms);
+    long long* d_out3;
+    CK(cudaMalloc(&d_out3, sizeof(long long) * 2 * 3 * sms));
+    for (int bytes : {4096, 8192, 16384}) {
+        for (int scatter = 0; scatter < 2; ++scatter) {
+            const int    depth   = 8;
+            const size_t per_cta = hbm_bytes / (3 * sms) / 32768 * 32768;
+            const int    iters   = (int)std::min<size_t>(2000, per_cta / ((size_t)bytes * depth));
+            for (int rep = 0; rep < 2; ++rep) {
+                CK(cudaEventRecord(e0));
+                ingest_kernel<<<3 * sms, 32, bytes * depth>>>(d_hbm, per_cta, per_cta, bytes, depth, iters, depth, d_out3,
+                                                               scatter);
+                CK(cudaEventRecord(e1));
+                CK(cudaDeviceSynchronize());
+            }
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            const double total_bytes = (double)3 * sms * iters * depth * bytes;
+            printf("  chunk %6d B  %-10s  %7.2f TB/s  (%.1f MB in %.1f us)\n", bytes, scatter ? "shuffled" : "sequential",
+                   total_bytes / (ms * 1e-3) / 1e12, total_bytes / 1e6, ms * 1e3);
         }
     }
     return 0;
