@@ -6,6 +6,8 @@ The continuous-batching engine (lmdeploy_b200.turbomind.engine) is built from th
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 import torch
 
@@ -24,6 +26,8 @@ class StaticBatchRunner:
                                 device=dev)
         # random block placement exercises paging (kernels/attention/test_attention.cu:119-129 does the same)
         perm = np.random.default_rng(seed).permutation(nblk).reshape(batch, self.blocks_per_seq)
+        if os.environ.get("B200_BENCH_SEQUENTIAL_PAGES"):      # diagnostic: how much does the shuffled placement cost HBM?
+            perm = np.arange(nblk).reshape(batch, self.blocks_per_seq)
         self.tables = perm
         self.block_ptrs = torch.tensor(self.pool.base + perm.reshape(-1).astype(np.int64) * self.pool.block_bytes,
                                        dtype=torch.int64, device=dev)
