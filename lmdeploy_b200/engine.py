@@ -5,7 +5,6 @@ block pool, the block tables and the per-step device bookkeeping, and can replay
 The continuous-batching engine (lmdeploy_b200.turbomind.engine) is built from the same pieces.
 """
 import ctypes as C
-
 import os
 
 import numpy as np
