@@ -490,6 +490,10 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
 #ifdef B200_GEMM_TOOL
     p.variant = g_plan_override.variant;
 #endif
+#ifdef B200_GEMM_TRACE
+    static int trace_launch = 0;
+    p.trace_launch          = trace_launch++;
+#endif
     p.tmem_cols = rg.tmem_cols, p.a_col = rg.a_col;
     if (epilogue == 2) {
         // the fused residual + RMSNorm epilogue lives in the split-K exchange: it needs splits > 1 and a bounded number

@@ -75,6 +75,21 @@ __device__ long long g_trace[kTraceCtas][kTraceRoles][kTraceSlots];
         const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                                            \
         if (_c < kTraceCtas && (slot) < kTraceSlots) g_trace[_c][role][slot] = clock64();                              \
     } while (0)
+// wall-clock (ns) begin / end of EVERY CTA of the last kWallLaunches launches: the anatomy of back-to-back kernels under
+// a CUDA graph + PDL (how long after kernel i's last CTA ends does kernel i+1's first CTA start, how skewed are the starts)
+constexpr int kWallLaunches = 16, kWallCtas = 160;
+__device__ unsigned long long g_wall[kWallLaunches][kWallCtas][2];
+B200_DEVICE unsigned long long wall_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define GEMM_WALL(p, which)                                                                                            \
+    do {                                                                                                               \
+        const int _c = blockIdx.y * gridDim.x + blockIdx.x;                                                            \
+        if (threadIdx.x == 0 && _c < kWallCtas) g_wall[(p).trace_launch % kWallLaunches][_c][which] = wall_ns();       \
+    } while (0)
 // watchdog wait: records (tag, cta, iteration) of the first wait that does not complete and traps
 __device__ int           g_hang[8];
 __device__ volatile int* g_hang_host;  // mapped pinned host memory: survives a dead context
@@ -105,6 +120,9 @@ B200_DEVICE void mbar_wait_dbg(uint32_t bar, uint32_t parity, int tag, int it)
 #define GEMM_TRACE(role, slot)                                                                                         \
     do {                                                                                                               \
     } while (0)
+#define GEMM_WALL(p, which)                                                                                            \
+    do {                                                                                                               \
+    } while (0)
 #define GEMM_WAIT(bar, parity, tag, it) mbar_wait(bar, parity)
 #endif
 
@@ -133,6 +151,9 @@ struct Params {
     int            out_mt;
     int            tmem_cols;  // 256 or 512 (power of two)
     int            a_col;      // first TMEM column of the A-operand ring
+#ifdef B200_GEMM_TRACE
+    int            trace_launch;  // tools/gemm_trace.cu: running launch number (GEMM_WALL)
+#endif
 #ifdef B200_GEMM_TOOL
     int            variant;    // tools/gemm_sweep.cu only: bit 0 = the W producer issues a slot's copies from several
                                // lanes at once, bit 1 = ... and each tile's block as two half-size copies,
@@ -237,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     const int kg0 = kgs * sp / p.splits, kg1 = kgs * (sp + 1) / p.splits;
     const int nk = kg1 - kg0;
     if (threadIdx.x == 64) GEMM_TRACE(4, 0);
+    GEMM_WALL(p, 0);
     // PDL: let the next kernel start launching; everything up to the first activation load (barrier init, TMEM
     // allocation, and the whole weight prefetch -- weights are constants) runs before griddepcontrol.wait.
     pdl_launch_dependents();
@@ -784,6 +806,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     if (warp == 1) {
         umma::tmem_dealloc(s_tmem, p.tmem_cols);
     }
+    GEMM_WALL(p, 1);
 }
 
 }  // namespace gemm

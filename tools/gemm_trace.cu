@@ -6,6 +6,7 @@
 #include "../lmdeploy_b200/csrc/capi_common.cu"
 #include "../lmdeploy_b200/csrc/gemm.cu"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -138,6 +139,38 @@ int main(int argc, char** argv)
         printf("%-8s K=%5d N=%5d m=%d tiles=%d splits=%d nw=%d nx=%d na=%d  %8.2f us  %7.1f GB/s (weights %.1f MB)\n", s.name,
                s.K, s.N, m, pl.tiles, pl.splits, pl.nw, pl.nx, pl.na, us, wbytes / us * 1e-3, wbytes / 1e6);
 #ifdef B200_GEMM_TRACE
+        {
+            // wall-clock anatomy of the last launches of the graph replay above (launch numbers are baked into the
+            // captured kernel parameters; the replay overwrote the stamps of the capture-free warm-up launches)
+            using namespace b200::gemm;
+            static unsigned long long wall[kWallLaunches][kWallCtas][2];
+            CK(cudaMemcpyFromSymbol(wall, g_wall, sizeof(wall)));
+            const int ctas = std::min(kWallCtas, (int)((s.N / (128 * pl.tiles)) * pl.splits));
+            // order the recorded launches by their first CTA start
+            std::vector<std::pair<unsigned long long, int>> order;
+            for (int l = 0; l < kWallLaunches; ++l) {
+                unsigned long long b = ~0ull;
+                for (int c = 0; c < ctas; ++c) b = std::min(b, wall[l][c][0]);
+                if (b != ~0ull && b != 0) order.push_back({b, l});
+            }
+            std::sort(order.begin(), order.end());
+            printf("  wall clock of %d consecutive launches (ns): [first CTA start .. last CTA start] -> [first CTA end .. last "
+                   "CTA end], gap = this launch's first start - previous launch's last end\n", (int)order.size());
+            unsigned long long prev_end = 0, t00 = order.empty() ? 0 : order[0].first;
+            for (size_t i = 0; i < order.size(); ++i) {
+                const int          l  = order[i].second;
+                unsigned long long s0 = ~0ull, s1 = 0, e0 = ~0ull, e1 = 0;
+                for (int c = 0; c < ctas; ++c) {
+                    s0 = std::min(s0, wall[l][c][0]), s1 = std::max(s1, wall[l][c][0]);
+                    e0 = std::min(e0, wall[l][c][1]), e1 = std::max(e1, wall[l][c][1]);
+                }
+                if (i >= order.size() - 6) {
+                    printf("    launch %2zu: start %7llu .. %7llu  end %7llu .. %7llu   CTA lifetime %5llu   gap %6lld\n", i, s0 - t00,
+                           s1 - t00, e0 - t00, e1 - t00, e1 - s0, prev_end ? (long long)(s0 - prev_end) : 0ll);
+                }
+                prev_end = e1;
+            }
+        }
         if (dump) {
             using namespace b200::gemm;
             static long long h[kTraceCtas][kTraceRoles][kTraceSlots];

@@ -26,6 +26,7 @@ unset B200_RUN_UNVERIFIED
 [ -x build/gemm_sweep ] && run gemm_sweep_7b 240 build/gemm_sweep 7b 64 20
 [ -x build/gemm_sweep ] && run gemm_sweep_70b 120 build/gemm_sweep 70b-tp8 32 20
 [ -x build/gemm_sweep ] && run gemm_sweep_7b_4tiles 120 build/gemm_sweep 7b 64 20 4     # tool-only 4-tile kernel, own process
+[ -x build/gemm_trace ] && run gemm_trace_wall 120 build/gemm_trace 64 20 0     # wall-clock anatomy of back-to-back GEMM launches
 [ -x build/tma_issue_rate ] && run tma_issue_rate 120 build/tma_issue_rate
 [ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
 run ref_gemm_bench 300 python tools/ref_gemm_bench.py 64 20
