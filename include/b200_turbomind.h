@@ -318,7 +318,10 @@ typedef struct {
 } b200_model_config;
 
 enum { B200_W_QKV = 0, B200_W_O = 1, B200_W_GATE_UP = 2, B200_W_DOWN = 3, B200_W_LM_HEAD = 4 };
-enum { B200_T_EMBEDDING = 0, B200_T_FINAL_NORM = 1, B200_T_ATTN_NORM = 2, B200_T_FFN_NORM = 3 };
+/* B200_T_QKV_BIAS: optional per-layer [(num_heads + 2 num_kv_heads) * head_dim] T, laid out like a w_qkv output row.
+ * Added to q / k / v by the attention prologue in T, where the reference adds it (AttentionParams::q_bias/k_bias/v_bias
+ * from w_qkv->bias, unified_attention_layer.cc:495-497) -- Qwen2-family checkpoints. */
+enum { B200_T_EMBEDDING = 0, B200_T_FINAL_NORM = 1, B200_T_ATTN_NORM = 2, B200_T_FFN_NORM = 3, B200_T_QKV_BIAS = 4 };
 
 typedef struct {
     int            batch_size;

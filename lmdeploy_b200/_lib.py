@@ -71,7 +71,7 @@ class StepInputs(C.Structure):
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_STATE = -1, -2, -3, -4          # b200_status
 W_QKV, W_O, W_GATE_UP, W_DOWN, W_LM_HEAD = range(5)
 FMT_DENSE, FMT_U4, FMT_FP8, FMT_FP8_COL = range(4)        # b200_linear_desc.weight_format
-T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM = range(4)
+T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM, T_QKV_BIAS = range(5)
 
 _lib = None
 

@@ -20,6 +20,7 @@ struct LayerW {
     b200_linear_desc qkv{}, wo{}, w13{}, w2{};
     const void*      attn_norm{};
     const void*      ffn_norm{};
+    const void*      qkv_bias{};  // optional (Qwen2 family)
 };
 
 }  // namespace b200
@@ -189,6 +190,9 @@ extern "C" int b200_model_set_tensor(b200_model* m, int layer, int which, const 
     else if (which == B200_T_FFN_NORM) {
         m->layers[layer].ffn_norm = ptr;
     }
+    else if (which == B200_T_QKV_BIAS) {
+        m->layers[layer].qkv_bias = ptr;
+    }
     else {
         return fail(B200_ERR_INVALID_ARG, "set_tensor: bad tensor id");
     }
@@ -306,6 +310,11 @@ static int run_step(b200_model* m, const b200_step_inputs* in, int R, bool chunk
         a.k      = (char*)m->qkv + (size_t)c.num_heads * c.head_dim * es;
         a.v      = (char*)m->qkv + (size_t)(c.num_heads + c.num_kv_heads) * c.head_dim * es;
         a.stride = qkv_dim;
+        if (W.qkv_bias) {
+            a.q_bias = W.qkv_bias;
+            a.k_bias = (const char*)W.qkv_bias + (size_t)c.num_heads * c.head_dim * es;
+            a.v_bias = (const char*)W.qkv_bias + (size_t)(c.num_heads + c.num_kv_heads) * c.head_dim * es;
+        }
         a.cu_q_len = in->cu_q_len, a.cu_k_len = in->cu_k_len, a.finished = in->finished;
         a.block_ptrs = in->block_ptrs, a.cu_block_nums = in->cu_block_nums;
         a.layer_offset = l * in->layer_stride_bytes, a.block_len = c.block_len;

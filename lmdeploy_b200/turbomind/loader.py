@@ -44,9 +44,16 @@ def resolver_for(spec: ModelSpec):
 
 def spec_from_config(cfg):
     arch = cfg["architectures"][0]
-    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama"}.get(arch)
+    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2"}.get(arch)
     if name is None:
-        raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama)")
+        raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama / Qwen2 dense)")
+    if cfg.get("num_experts") or cfg.get("use_sliding_window"):
+        raise NotImplementedError("MoE / sliding-window variants are outside the hot-path scope")
+    # q/k/v bias: always for Qwen2 (lmdeploy/turbomind/models/qwen2.py:78-97 bundles it with the linears), optional for
+    # Llama-style configs; a bias on o_proj / mlp is not supported
+    qkv_bias = name == "qwen2" or bool(cfg.get("attention_bias", False))
+    if cfg.get("mlp_bias", False):
+        raise NotImplementedError("mlp_bias checkpoints are not supported")
     method, _group = parse_quantization_config(cfg.get("quantization_config"))
     # one on-GPU format per weight family: every int4 checkpoint becomes 'awq' (u4 g128), fp8 stays fp8
     fmt = "awq" if method in INT4_METHODS else "fp8" if method == "fp8" else "fp16"
@@ -63,7 +70,7 @@ def spec_from_config(cfg):
                      rope_theta=float(cfg.get("rope_theta", 10000.0)), head_dim=head_dim,
                      norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope_type,
                      rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt,
-                     checkpoint_format=method, dtype=dtype)
+                     checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias)
 
 
 def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
@@ -106,9 +113,18 @@ def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
     cols = torch.arange(rank * it, (rank + 1) * it)
     gate, up = w1.cols(cols), w3.cols(cols)
     inter_idx = torch.stack([torch.arange(it), it + torch.arange(it)], 1).reshape(-1)
-    return dict(w_qkv=_Lin.cat([qs, ks, vs]), wo=wo.rows(rank * hq * D, (rank + 1) * hq * D),
-                w1w3=_Lin.cat([gate, up]).cols(inter_idx), w2=w2.rows(rank * it, (rank + 1) * it),
-                attention_norm=an, ffn_norm=fn)
+    w_qkv = _Lin.cat([qs, ks, vs])
+    if spec.qkv_bias and w_qkv.bias is None:
+        raise KeyError(f"layer {i}: the config announces q/k/v biases but the checkpoint has none")
+    if wo.bias is not None or w2.bias is not None or gate.bias is not None:
+        raise NotImplementedError(f"layer {i}: biases on o_proj / mlp linears are not supported")
+    out = dict(w_qkv=w_qkv, wo=wo.rows(rank * hq * D, (rank + 1) * hq * D),
+               w1w3=_Lin.cat([gate, up]).cols(inter_idx), w2=w2.rows(rank * it, (rank + 1) * it),
+               attention_norm=an, ffn_norm=fn)
+    if spec.qkv_bias:
+        out["qkv_bias"] = w_qkv.bias          # applied by the attention prologue, not by the GEMM
+        w_qkv.bias = None
+    return out
 
 
 def convert_globals(spec: ModelSpec, tensors, tp=1, rank=0):
@@ -203,7 +219,7 @@ def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1
             cache.clear()
             cache[i] = convert_layer(spec, tensors, i, tp, rank)
         x = cache[i][kind]
-        return x.to_tm(dev, T) if isinstance(x, _Lin) else x
+        return x.to_tm(dev, T) if isinstance(x, _Lin) else x            # norms / qkv_bias: plain tensors
 
     model.load_tm_weights(provider)
     eos = cfg.get("eos_token_id")

@@ -171,6 +171,11 @@ class DecodeModel:
             for i in range(s.layers):
                 self._set_tensor(i, L.T_ATTN_NORM, provider(f"layers.{i}.attention_norm"))
                 self._set_tensor(i, L.T_FFN_NORM, provider(f"layers.{i}.ffn_norm"))
+                if s.qkv_bias:
+                    b = provider(f"layers.{i}.qkv_bias")
+                    if tuple(b.shape) != ((self.heads + 2 * self.kv_heads) * D,):
+                        raise ValueError(f"layers.{i}.qkv_bias has shape {tuple(b.shape)}")
+                    self._set_tensor(i, L.T_QKV_BIAS, b)
                 for name, (K, N, which) in shapes.items():
                     w = provider(f"layers.{i}.{name}")
                     if "col_scales" in w:       # fp8 e4m3 bytes [K, N] + f32 scales [K/128, N]
@@ -213,6 +218,8 @@ class DecodeModel:
                 return (torch.randn(s.vocab, s.hidden, generator=gr, device=dev) * 0.02).to(T)
             if name == "norm" or name.endswith("_norm"):
                 return (1.0 + 0.02 * torch.randn(s.hidden, generator=gr, device=dev)).to(T)
+            if name.endswith("qkv_bias"):
+                return (0.1 * torch.randn((self.heads + 2 * self.kv_heads) * s.head_dim, generator=g, device=dev)).to(T)
             if name == "output":
                 return dict(weight=dense(s.hidden, self.vocab_local, g))
             kind = name.split(".")[-1]

@@ -6,7 +6,7 @@ from dataclasses import dataclass, replace
 @dataclass(frozen=True)
 class ModelSpec:
     name: str
-    arch: str                 # 'internlm2' | 'llama'
+    arch: str                 # 'internlm2' | 'llama' | 'qwen2'
     hidden: int
     layers: int
     heads: int
@@ -21,6 +21,7 @@ class ModelSpec:
     weight_format: str = "awq"      # on-GPU weight format: 'awq' (u4 g128, any int4 checkpoint family) | 'fp16' | 'fp8'
     dtype: str = "f16"
     checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
+    qkv_bias: bool = False          # q/k/v projections carry a bias (Qwen2 family), applied by the attention prologue
 
     def tiny(self, layers=2):
         return replace(self, layers=layers)

@@ -20,7 +20,8 @@ from .numerics import F16, rn, f32
 class TinyWeights:
     """Random weights of a small llama-family model in TurboMind's loader-visible layout."""
 
-    def __init__(self, *, hidden, layers, heads, kv_heads, inter, vocab, fmt="awq", dtype=F16, seed=0, head_dim=128):
+    def __init__(self, *, hidden, layers, heads, kv_heads, inter, vocab, fmt="awq", dtype=F16, seed=0, head_dim=128,
+                 qkv_bias=False):
         rng = np.random.default_rng(seed)
         self.hidden, self.layers, self.heads, self.kv_heads = hidden, layers, heads, kv_heads
         self.inter, self.vocab, self.fmt, self.dtype, self.D = inter, vocab, fmt, dtype, head_dim
@@ -48,6 +49,8 @@ class TinyWeights:
                 ffn_norm=rn((1 + 0.02 * rng.standard_normal(hidden)).astype(np.float32), dtype),
                 w_qkv=lin(hidden, (heads + 2 * kv_heads) * D), wo=lin(heads * D, hidden),
                 w1w3=lin(hidden, 2 * inter), w2=lin(inter, hidden)))
+            if qkv_bias:   # Qwen2 family: added to q/k/v by the attention prologue (unified_attention_layer.cc:495-497)
+                self.L[-1]["qkv_bias"] = rn((rng.standard_normal((heads + 2 * kv_heads) * D) * 0.1).astype(np.float32), dtype)
         out = rn((rng.standard_normal((hidden, vocab)) * 0.1 / np.sqrt(hidden)).astype(np.float32), dtype)
         self.output = dict(w=out, deq=out)
 
@@ -78,7 +81,8 @@ class TinyWeights:
             ki = self.heads * D + np.arange(rank * Hkv * D, (rank + 1) * Hkv * D)
             vi = (self.heads + self.kv_heads) * D + np.arange(rank * Hkv * D, (rank + 1) * Hkv * D)
             gu = np.arange(rank * 2 * I, (rank + 1) * 2 * I)      # interleaved (gate, up) pairs stay together
-            sh.L.append(dict(attn_norm=lw["attn_norm"], ffn_norm=lw["ffn_norm"],
+            extra = {"qkv_bias": lw["qkv_bias"][np.concatenate([qi, ki, vi])]} if "qkv_bias" in lw else {}
+            sh.L.append(dict(attn_norm=lw["attn_norm"], ffn_norm=lw["ffn_norm"], **extra,
                              w_qkv=cols(lw["w_qkv"], np.concatenate([qi, ki, vi])),
                              wo=rows(lw["wo"], slice(rank * Hq * D, (rank + 1) * Hq * D)),
                              w1w3=cols(lw["w1w3"], gu),
@@ -86,6 +90,14 @@ class TinyWeights:
         vs = slice(rank * sh.vocab_local, (rank + 1) * sh.vocab_local)
         sh.output = {k: v[:, vs] for k, v in self.output.items()}
         return sh
+
+
+def _bias_args(w, lw):
+    b = lw.get("qkv_bias")
+    if b is None:
+        return {}
+    nq, nk = w.heads * w.D, w.kv_heads * w.D
+    return dict(q_bias=b[:nq], k_bias=b[nq:nq + nk], v_bias=b[nq + nk:])
 
 
 def decode_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables, hist, rope, eps=1e-5, tp_shards=None,
@@ -102,7 +114,7 @@ def decode_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables,
         for r, sw in enumerate(shards):
             lw = sw.L[l]
             qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
-            attn = OA.decode_attention(qkv, kvc[r], block_tables, hist, l, sw.heads, sw.kv_heads, rope)
+            attn = OA.decode_attention(qkv, kvc[r], block_tables, hist, l, sw.heads, sw.kv_heads, rope, **_bias_args(sw, lw))
             parts.append(OL.linear(attn, lw["wo"]["deq"], dtype))
         x, residual = OL.allreduce_residual_rmsnorm(parts, residual, w.L[l]["ffn_norm"], eps, dtype)
         parts = []
@@ -127,7 +139,8 @@ def chunk_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables, 
     for l in range(w.layers):
         lw = w.L[l]
         qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
-        attn = OA.prefill_attention(qkv, cache, block_tables, q_lens, k_lens, l, w.heads, w.kv_heads, rope)
+        attn = OA.prefill_attention(qkv, cache, block_tables, q_lens, k_lens, l, w.heads, w.kv_heads, rope,
+                                    **_bias_args(w, lw))
         x, residual = OL.allreduce_residual_rmsnorm([OL.linear(attn, lw["wo"]["deq"], dtype)], residual,
                                                     lw["ffn_norm"], eps, dtype)
         a = OL.linear_gated_silu(x, lw["w1w3"]["deq"], dtype)

@@ -87,6 +87,9 @@ def make_checkpoint(arch, family, seed=0):
             norms = (p + "attention_norm.weight", p + "ffn_norm.weight")
         else:
             p = f"model.layers.{i}."
+            if arch == "qwen2":
+                for nm, n in (("q_proj", HQ * D), ("k_proj", HKV * D), ("v_proj", HKV * D)):
+                    t[p + f"self_attn.{nm}.bias"] = torch.from_numpy((rng.standard_normal(n) * 0.2).astype(np.float16))
             add(p + "self_attn.q_proj", H, HQ * D), add(p + "self_attn.k_proj", H, HKV * D)
             add(p + "self_attn.v_proj", H, HKV * D), add(p + "self_attn.o_proj", HQ * D, H)
             add(p + "mlp.gate_proj", H, I), add(p + "mlp.up_proj", H, I), add(p + "mlp.down_proj", I, H)
@@ -95,10 +98,12 @@ def make_checkpoint(arch, family, seed=0):
             t[n] = torch.from_numpy((1 + 0.05 * rng.standard_normal(H)).astype(np.float16))
     emb = "model.tok_embeddings.weight" if arch == "internlm2" else "model.embed_tokens.weight"
     head = "output.weight" if arch == "internlm2" else "lm_head.weight"
-    t[emb] = torch.from_numpy((rng.standard_normal((V, H)) * 0.5).astype(np.float16))
+    t[emb] = torch.from_numpy((rng.standard_normal((V, H)) * (0.5 if arch != "qwen2" else 0.05)).astype(np.float16))
     t["model.norm.weight"] = torch.from_numpy((1 + 0.05 * rng.standard_normal(H)).astype(np.float16))
-    t[head] = torch.from_numpy((rng.standard_normal((V, H)) * 0.3 / np.sqrt(H)).astype(np.float16))
-    cfg = {"architectures": ["InternLM2ForCausalLM" if arch == "internlm2" else "LlamaForCausalLM"],
+    if arch != "qwen2":          # the Qwen2 test checkpoint ties lm_head to the embeddings (tie_word_embeddings)
+        t[head] = torch.from_numpy((rng.standard_normal((V, H)) * 0.3 / np.sqrt(H)).astype(np.float16))
+    cfg = {"architectures": [{"internlm2": "InternLM2ForCausalLM", "llama": "LlamaForCausalLM",
+                              "qwen2": "Qwen2ForCausalLM"}[arch]], "tie_word_embeddings": arch == "qwen2",
            "hidden_size": H, "num_hidden_layers": L, "num_attention_heads": HQ, "num_key_value_heads": HKV,
            "intermediate_size": I, "vocab_size": V, "rms_norm_eps": 1e-5, "rope_theta": 10000.0}
     if family == "awq":
@@ -149,9 +154,11 @@ def hf_forward(arch, t, deq, tokens):
             n2 = f(p + "ffn_norm.weight")
         else:
             h = norm(x, f(p + "input_layernorm.weight"))
-            q = (h @ deq[p + "self_attn.q_proj"]).reshape(S, HQ, D)
-            k = (h @ deq[p + "self_attn.k_proj"]).reshape(S, HKV, D)
-            v = (h @ deq[p + "self_attn.v_proj"]).reshape(S, HKV, D)
+            bq, bk, bv = [f(p + f"self_attn.{nm}.bias") if p + f"self_attn.{nm}.bias" in t else 0.0
+                          for nm in ("q_proj", "k_proj", "v_proj")]
+            q = (h @ deq[p + "self_attn.q_proj"] + bq).reshape(S, HQ, D)
+            k = (h @ deq[p + "self_attn.k_proj"] + bk).reshape(S, HKV, D)
+            v = (h @ deq[p + "self_attn.v_proj"] + bv).reshape(S, HKV, D)
             wo, w1, w3, w2 = (deq[p + "self_attn.o_proj"], deq[p + "mlp.gate_proj"], deq[p + "mlp.up_proj"],
                               deq[p + "mlp.down_proj"])
             n2 = f(p + "post_attention_layernorm.weight")
@@ -169,7 +176,8 @@ def hf_forward(arch, t, deq, tokens):
         gate, up = h @ w1, h @ w3
         x = x + (gate / (1 + np.exp(-gate)) * up) @ w2
     x = norm(x, f("model.norm.weight"))
-    head = f("output.weight" if arch == "internlm2" else "lm_head.weight")
+    hname = "output.weight" if arch == "internlm2" else "lm_head.weight"
+    head = f(hname) if hname in t else emb
     return x @ head.T
 
 
@@ -201,13 +209,14 @@ def to_tiny(spec, cfg_tensors, tp=1, rank=0):
 
     for i in range(L):
         c = LD.convert_layer(spec, t, i, tp, rank)
+        extra = {"qkv_bias": rn(c["qkv_bias"].to(torch.float32).numpy(), T)} if "qkv_bias" in c else {}
         w.L.append(dict(attn_norm=c["attention_norm"].to(torch.float32).numpy(),
-                        ffn_norm=c["ffn_norm"].to(torch.float32).numpy(),
+                        ffn_norm=c["ffn_norm"].to(torch.float32).numpy(), **extra,
                         w_qkv=lin(c["w_qkv"]), wo=lin(c["wo"]), w1w3=lin(c["w1w3"]), w2=lin(c["w2"])))
     return w
 
 
-@pytest.mark.parametrize("arch", ["internlm2", "llama"])
+@pytest.mark.parametrize("arch", ["internlm2", "llama", "qwen2"])
 @pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("tp", [1, 2])
 def test_loader_transforms_preserve_model_semantics(arch, family, tp):
@@ -215,11 +224,12 @@ def test_loader_transforms_preserve_model_semantics(arch, family, tp):
     spec = LD.spec_from_config(cfg)
     assert spec.weight_format == {None: "fp16", "fp8": "fp8"}.get(family, "awq") and spec.arch == arch
     assert spec.checkpoint_format == family and spec.dtype == ("bf16" if family == "fp8" else "f16")
+    assert spec.qkv_bias == (arch == "qwen2")
     T = BF16 if family == "fp8" else F16
     # logits are O(1); measured max error 5e-4 (fp16) / 5e-3 (bf16: 8 significand bits, 8x the rounding per operation)
-    tol = 4e-3 if T == F16 else 3e-2
     tokens = [5, 17, 200, 3, 99]
     ref = hf_forward(arch, t, deq, tokens)
+    tol = (4e-3 if T == F16 else 3e-2) * max(1.0, float(np.abs(ref).max()))      # relative for the larger tied-head logits
     shards = [to_tiny(spec, t, tp, r) for r in range(tp)]
     full = shards[0] if tp == 1 else to_tiny(spec, t, 1, 0)
     rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=D, base=10000.0)

@@ -471,3 +471,47 @@ def test_chunk_step_matches_oracle(kv_bits):
     for t in range(T):
         if srt[t, -1] - srt[t, -2] > 8e-3:
             assert got_tokens[t] == ref_tokens[t]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Qwen2 family: q/k/v bias applied by the attention prologue inside the decode step (B200_T_QKV_BIAS)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", ["awq", "fp16"])
+def test_decode_step_with_qkv_bias_matches_oracle(fmt):
+    import torch
+    from oracle import attention as OA
+    from oracle.decode_step import TinyWeights, decode_step
+    from harness import from_dev_T
+    from test_decode_step_gpu import build_device_model
+    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, seed=13, qkv_bias=True)
+    hist = np.array([0, 7, 64, 200], np.int32)
+    B = len(hist)
+    rng = np.random.default_rng(4)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)     # build_device_model's theta
+    layout = OA.KvLayout(2, 64, 128, 8)
+    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
+    cache = OA.PagedKvCache(sum(blocks_per) + 1, w.layers, layout, F16)
+    tables, o = [], 0
+    for n in blocks_per:
+        tables.append(list(range(o, o + n)))
+        o += n
+    for l in range(w.layers):
+        for b in range(B):
+            if hist[b]:
+                OA.process_kv(cache, tables[b], l, 0, OA.rn(rng.standard_normal((int(hist[b]), 2, 128)).astype(np.float32), F16),
+                              OA.rn(rng.standard_normal((int(hist[b]), 2, 128)).astype(np.float32), F16), rope)
+    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
+    m = build_device_model(w, 8, max_batch=8)
+    pool = torch.from_numpy(cache.pool.copy()).cuda()
+    ptrs = torch.tensor([pool.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t], dtype=torch.int64, device="cuda")
+    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
+    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
+    m.decode_step(batch=B, token_ids=torch.from_numpy(tokens).cuda(), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
+                  cu_block_nums=cu_blocks, out_tokens=d_out, max_k_len=int(hist.max()) + 1)
+    torch.cuda.synchronize()
+    got = from_dev_T(m.logits(B), F16)
+    ref, _ = decode_step(w, tokens, cache, tables, hist, rope)
+    assert np.abs(got - ref).max() <= 4e-3
+    assert (pool.cpu().numpy() == cache.pool).mean() > 0.999
