@@ -32,6 +32,8 @@ SPECS = {
     "internlm2-7b": ModelSpec("internlm2-7b", "internlm2", 4096, 32, 32, 8, 14336, 92544, 1e6),
     "internlm2-20b": ModelSpec("internlm2-20b", "internlm2", 6144, 48, 48, 8, 16384, 92544, 1e6),
     "llama3-8b": ModelSpec("llama3-8b", "llama", 4096, 32, 32, 8, 14336, 128256, 5e5, weight_format="fp16"),
+    # Qwen2-7B: q/k/v bias, GQA group 7 (public HF config; lmdeploy/turbomind/models/qwen2.py)
+    "qwen2-7b": ModelSpec("qwen2-7b", "qwen2", 3584, 28, 28, 4, 18944, 152064, 1e6, qkv_bias=True),
     "llama3-70b": ModelSpec("llama3-70b", "llama", 8192, 80, 64, 8, 28672, 128256, 5e5, weight_format="fp8",
                             dtype="bf16"),
 }

@@ -515,3 +515,16 @@ def test_decode_step_with_qkv_bias_matches_oracle(fmt):
     ref, _ = decode_step(w, tokens, cache, tables, hist, rope)
     assert np.abs(got - ref).max() <= 4e-3
     assert (pool.cpu().numpy() == cache.pool).mean() > 0.999
+
+
+@pytest.mark.parametrize("heads", [(14, 2), (6, 2), (5, 1)])
+def test_decode_attention_odd_gqa_groups(heads):
+    """GQA groups 7 (Qwen2-7B), 3 and 5: the decode kernel pads the group to the MMA's 8 columns; the verified suite
+    covers groups 1, 4 and 8."""
+    from harness import PagedCase
+    hq, hkv = heads
+    case = PagedCase(batch_hist=[0, 63, 64, 300, 1000], num_heads=hq, num_kv_heads=hkv, kv_bits=8, seed=hq, bias=True)
+    out, pool = case.run_device()
+    ref = case.run_oracle()
+    assert (pool == case.cache.pool).all()
+    assert np.abs(out - ref).max() <= 2e-3
