@@ -14,13 +14,14 @@ Restates the loader transforms of the reference for the two architectures on the
     (builders/_base.py:102-113, attention.py:65-76, ffn.py:238-243).
 All functions are pure tensor code (CPU-testable); only `load_hf_checkpoint` touches the GPU."""
 import json
+import math
 import os
 
 import torch
 
 from .checkpoint_formats import (AWQ_NIBBLE_OF_COLUMN, INT4_METHODS, FormatResolver, Lin, pack_u4_row,  # noqa: F401
                                  parse_quantization_config, unpack_last)
-from .specs import ModelSpec
+from .specs import ModelSpec, RopeSpec
 
 _Lin = Lin
 
@@ -42,6 +43,57 @@ def resolver_for(spec: ModelSpec):
     return FormatResolver(None if spec.weight_format == "fp16" else (spec.checkpoint_format or spec.weight_format))
 
 
+def _yarn_mscale(scale, mscale=1.0):
+    return 1.0 if scale <= 1 else 0.1 * mscale * math.log(scale) + 1.0
+
+
+def parse_rope(cfg, head_dim):
+    """HF config -> RopeSpec, field for field what parse_rope_param produces (lmdeploy/turbomind/models/utils.py:76-166):
+    transformers >= 5 `rope_parameters` or the older `rope_theta` + `rope_scaling`; partial_rotary_factor; linear / llama3 /
+    yarn scaling (yarn: attention_factor from mscale / mscale_all_dim when not given, factor re-derived from the original
+    context length)."""
+    rp = cfg.get("rope_parameters")
+    if rp is not None:
+        scaling, theta = rp, float(rp.get("rope_theta", 10000.0))
+    else:
+        scaling, theta = cfg.get("rope_scaling"), float(cfg.get("rope_theta", 10000.0))
+    max_pos = int(cfg.get("max_position_embeddings", 0))
+    prf = (rp or {}).get("partial_rotary_factor")
+    if prf is None:
+        prf = float(cfg.get("partial_rotary_factor", 1.0))
+    kw = dict(type="default", dim=int(head_dim * prf), base=theta)
+    if scaling:
+        rtype = scaling.get("rope_type") or scaling.get("type") or "default"
+        factor = float(scaling.get("factor", 0.0) or 0.0)
+        if rtype in ("default", "mrope"):
+            if scaling.get("mrope_section"):
+                raise NotImplementedError("multimodal rope (mrope_section) is outside the hot-path scope")
+        elif rtype == "linear":
+            kw.update(type="linear", factor=factor)
+        elif rtype == "llama3":
+            kw.update(type="llama3", factor=factor, low_freq_factor=float(scaling.get("low_freq_factor", 1.0)),
+                      high_freq_factor=float(scaling.get("high_freq_factor", 1.0)),
+                      original_max_position_embeddings=int(scaling.get("original_max_position_embeddings", 0)))
+        elif rtype == "yarn":
+            af = scaling.get("attention_factor")
+            if af is None:
+                ms, msa = scaling.get("mscale"), scaling.get("mscale_all_dim")
+                af = _yarn_mscale(factor, ms) / _yarn_mscale(factor, msa) if ms is not None and msa is not None \
+                    else _yarn_mscale(factor)
+            orig = scaling.get("original_max_position_embeddings")
+            if orig is not None:
+                factor = max_pos / orig
+            else:
+                orig = max_pos
+            kw.update(type="yarn", factor=float(factor), max_position_embeddings=int(orig), attention_factor=float(af),
+                      beta_fast=float(scaling.get("beta_fast", 32.0)), beta_slow=float(scaling.get("beta_slow", 1.0)))
+        elif rtype == "dynamic":
+            raise NotImplementedError("dynamic-NTK rope is not supported by the sm_100a kernels")
+        else:
+            raise NotImplementedError(f"unsupported rope type {rtype!r}")
+    return RopeSpec(**kw)
+
+
 def spec_from_config(cfg):
     arch = cfg["architectures"][0]
     name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2"}.get(arch)
@@ -60,16 +112,15 @@ def spec_from_config(cfg):
     # compute dtype: int4 formats force fp16 (converter.py:38-48); otherwise the checkpoint's own dtype
     hf_dtype = str(cfg.get("dtype", cfg.get("torch_dtype", "float16"))).replace("torch.", "")
     dtype = "f16" if fmt == "awq" or hf_dtype != "bfloat16" else "bf16"
-    rs = cfg.get("rope_scaling") or {}
-    rope_type = "llama3" if rs.get("rope_type", rs.get("type")) == "llama3" else "default"
     head_dim = cfg.get("head_dim") or cfg["hidden_size"] // cfg["num_attention_heads"]
+    rope = parse_rope(cfg, head_dim)
     return ModelSpec(name=os.path.basename(cfg.get("_name_or_path", name)) or name, arch=name,
                      hidden=cfg["hidden_size"], layers=cfg["num_hidden_layers"], heads=cfg["num_attention_heads"],
                      kv_heads=cfg.get("num_key_value_heads", cfg["num_attention_heads"]),
                      inter=cfg["intermediate_size"], vocab=cfg["vocab_size"],
-                     rope_theta=float(cfg.get("rope_theta", 10000.0)), head_dim=head_dim,
-                     norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope_type,
-                     rope_factor=float(rs.get("factor", 0.0)) if rope_type == "llama3" else 0.0, weight_format=fmt,
+                     rope_theta=rope.base, head_dim=head_dim,
+                     norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope.type, rope_factor=rope.factor, rope=rope,
+                     weight_format=fmt,
                      checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias)
 
 
@@ -104,8 +155,9 @@ def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
         w3 = _get_linear(p + "mlp.up_proj")
         w2 = _get_linear(p + "mlp.down_proj")
         an, fn = tensors[p + "input_layernorm.weight"], tensors[p + "post_attention_layernorm.weight"]
-    q = q.cols(rope_perm(Hq, D))
-    k = k.cols(rope_perm(Hkv, D))
+    rope_dim = spec.rope.dim if spec.rope is not None else D        # partial rotary: only the rotated dims are reordered
+    q = q.cols(rope_perm(Hq, D, rope_dim))
+    k = k.cols(rope_perm(Hkv, D, rope_dim))
     hq, hkv, it = Hq // tp, Hkv // tp, spec.inter // tp
     qs = q.cols(torch.arange(rank * hq * D, (rank + 1) * hq * D))
     ks = k.cols(torch.arange(rank * hkv * D, (rank + 1) * hkv * D))

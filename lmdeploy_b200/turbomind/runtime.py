@@ -13,7 +13,7 @@ import math
 import torch
 
 from .. import _lib as L
-from .specs import ModelSpec
+from .specs import ModelSpec, RopeSpec
 
 _TORCH_T = {"f16": torch.float16, "bf16": torch.bfloat16}
 _DT = {"f16": 0, "bf16": 1}
@@ -96,7 +96,6 @@ class DecodeModel:
         self.vocab_pad = (spec.vocab + 128 * tp_size - 1) // (128 * tp_size) * (128 * tp_size)
         self.vocab_local = self.vocab_pad // tp_size
         self.T = _TORCH_T[spec.dtype]
-        rope_type = {"default": 1, "llama3": 5}[spec.rope_type]
         cfg = L.ModelConfig()
         cfg.num_layers, cfg.hidden = spec.layers, spec.hidden
         cfg.num_heads, cfg.num_kv_heads, cfg.head_dim = self.heads, self.kv_heads, spec.head_dim
@@ -104,8 +103,12 @@ class DecodeModel:
         cfg.norm_eps = spec.norm_eps
         cfg.inv_sqrt_dh = float(torch.tensor(1.4426950408889634, dtype=torch.float32)
                                 / torch.sqrt(torch.tensor(float(spec.head_dim), dtype=torch.float32)))
-        cfg.rope = L.RopeConfig(rope_type, spec.head_dim, spec.rope_theta, spec.rope_factor, 0, 1.0, 4.0, 8192, 1.0,
-                                32.0, 1.0, 1 if rope_exact_math else 0)
+        r = spec.rope or RopeSpec(type=spec.rope_type, dim=spec.head_dim, base=spec.rope_theta, factor=spec.rope_factor)
+        if r.type not in RopeSpec.TYPE_ID:
+            raise NotImplementedError(f"rope type {r.type!r} (supported: {sorted(RopeSpec.TYPE_ID)})")
+        cfg.rope = L.RopeConfig(RopeSpec.TYPE_ID[r.type], r.dim, r.base, r.factor, r.max_position_embeddings,
+                                r.low_freq_factor, r.high_freq_factor, r.original_max_position_embeddings,
+                                r.attention_factor, r.beta_fast, r.beta_slow, 1 if rope_exact_math else 0)
         cfg.dtype, cfg.quant_policy, cfg.block_len = _DT[spec.dtype], quant_policy, block_len
         cfg.max_batch, cfg.tp_size, cfg.tp_rank = max_batch, tp_size, tp_rank
         self.cfg = cfg

@@ -4,6 +4,25 @@ from dataclasses import dataclass, replace
 
 
 @dataclass(frozen=True)
+class RopeSpec:
+    """RoPE parameters as the reference parses them from an HF config (lmdeploy/turbomind/models/utils.py:76-166) and
+    hands them to init_rope_kernel_param (src/turbomind/models/attention_weight.cc:37-93)."""
+    type: str = "default"               # 'default' | 'linear' | 'llama3' | 'yarn'   ('dynamic' NTK is not supported)
+    dim: int = 128                      # rotated dims = head_dim * partial_rotary_factor
+    base: float = 10000.0
+    factor: float = 0.0
+    max_position_embeddings: int = 0    # yarn: the ORIGINAL context length
+    low_freq_factor: float = 1.0        # llama3
+    high_freq_factor: float = 4.0
+    original_max_position_embeddings: int = 8192
+    attention_factor: float = 1.0       # yarn
+    beta_fast: float = 32.0
+    beta_slow: float = 1.0
+
+    TYPE_ID = {"default": 1, "linear": 2, "yarn": 4, "llama3": 5}
+
+
+@dataclass(frozen=True)
 class ModelSpec:
     name: str
     arch: str                 # 'internlm2' | 'llama' | 'qwen2'
@@ -22,6 +41,7 @@ class ModelSpec:
     dtype: str = "f16"
     checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
     qkv_bias: bool = False          # q/k/v projections carry a bias (Qwen2 family), applied by the attention prologue
+    rope: RopeSpec = None           # full RoPE description (checkpoints); None = rope_type / rope_theta / rope_factor above
 
     def tiny(self, layers=2):
         return replace(self, layers=layers)
