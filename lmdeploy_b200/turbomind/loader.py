@@ -96,10 +96,13 @@ def parse_rope(cfg, head_dim):
 
 def spec_from_config(cfg):
     arch = cfg["architectures"][0]
-    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2"}.get(arch)
+    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2",
+            "MistralForCausalLM": "llama"}.get(arch)          # Mistral dense = Llama tensor names (no sliding window, below)
     if name is None:
         raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama / Qwen2 dense)")
-    if cfg.get("num_experts") or cfg.get("use_sliding_window"):
+    window = cfg.get("sliding_window")
+    if cfg.get("num_experts") or cfg.get("num_local_experts") or cfg.get("use_sliding_window") or \
+            (arch == "MistralForCausalLM" and window and window < cfg.get("max_position_embeddings", 0)):
         raise NotImplementedError("MoE / sliding-window variants are outside the hot-path scope")
     # q/k/v bias: always for Qwen2 (lmdeploy/turbomind/models/qwen2.py:78-97 bundles it with the linears), optional for
     # Llama-style configs; a bias on o_proj / mlp is not supported

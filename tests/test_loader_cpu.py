@@ -333,3 +333,17 @@ def test_rope_scaling_is_parsed_like_the_reference():
 def test_partial_rotary_reorders_only_the_rotated_dims():
     p = LD.rope_perm(1, 8, 4).tolist()
     assert p == [0, 2, 1, 3, 4, 5, 6, 7]
+
+
+def test_architecture_admission():
+    base = {"hidden_size": 512, "num_hidden_layers": 2, "num_attention_heads": 4, "num_key_value_heads": 2,
+            "intermediate_size": 512, "vocab_size": 256, "max_position_embeddings": 32768}
+    assert LD.spec_from_config(dict(base, architectures=["MistralForCausalLM"], sliding_window=None)).arch == "llama"
+    assert LD.spec_from_config(dict(base, architectures=["Qwen2ForCausalLM"])).qkv_bias
+    assert LD.spec_from_config(dict(base, architectures=["LlamaForCausalLM"], attention_bias=True)).qkv_bias
+    for bad in (dict(architectures=["MistralForCausalLM"], sliding_window=4096),
+                dict(architectures=["Qwen2ForCausalLM"], use_sliding_window=True),
+                dict(architectures=["MixtralForCausalLM"]), dict(architectures=["Qwen2MoeForCausalLM"]),
+                dict(architectures=["LlamaForCausalLM"], mlp_bias=True)):
+        with pytest.raises(NotImplementedError):
+            LD.spec_from_config(dict(base, **bad))
