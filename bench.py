@@ -238,6 +238,19 @@ def run_b200(args):
     except Exception as e:  # the checker library is optional on the bench path
         roofline["reference_kernel"] = {"unavailable": str(e)[:200]}
 
+    # opt-in (B200_BENCH_REF_GEMM=1, until the library has had its first clean GPU run): the reference's own tuned
+    # W4A16 GEMM (oracle/_ref/libtm_ref_gemm.so) next to ours on this model's four linears -- measurement only
+    if os.environ.get("B200_BENCH_REF_GEMM") and world == 1 and spec.weight_format == "awq":
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import ref_gemm_bench
+            D = spec.head_dim
+            shapes = [("qkv", spec.hidden, (spec.heads + 2 * spec.kv_heads) * D, 0), ("wo", spec.heads * D, spec.hidden, 0),
+                      ("w1w3", spec.hidden, 2 * spec.inter, 1), ("w2", spec.inter, spec.hidden, 0)]
+            roofline["reference_gemm"] = ref_gemm_bench.measure(batch, args.attn_iters, shapes, verbose=False)
+        except Exception as e:
+            roofline["reference_gemm"] = {"unavailable": str(e)[:200]}
+
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

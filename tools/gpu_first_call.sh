@@ -31,6 +31,7 @@ unset B200_RUN_UNVERIFIED
 [ -x build/umma_probe ] && run umma_probe 60 build/umma_probe
 run ref_gemm_bench 300 python tools/ref_gemm_bench.py 64 20
 run bench 420 python bench.py
+B200_BENCH_REF_GEMM=1 run bench_with_ref_gemm 420 python bench.py --no-cpu-baseline --steps 16 --warmup 4
 run bench_c3 420 python bench.py --config c3 --no-cpu-baseline --steps 16 --warmup 4    # Llama-3-8B fp16 + KV-int4, bs 128, 4K ctx
 B200_BENCH_SEQUENTIAL_PAGES=1 run bench_sequential_pages 300 python bench.py --no-cpu-baseline --steps 16 --warmup 4
 # the sweep's winners as a tuned plan table, and the step with it

@@ -36,17 +36,13 @@ def graph_time(fn, iters):
     return e0.elapsed_time(e1) * 1e3 / iters
 
 
-def main():
-    m = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+def measure(m=64, iters=20, shapes=SHAPES, verbose=True):
+    """-> {name: dict(reference_us, ours_us, weight_bytes, max_abs_diff)} for the given (name, K, N, gated_silu) shapes."""
     lib = L.load()
-    if not RG.available():
-        print("oracle/_ref/libtm_ref_gemm.so is not built")
-        return 1
-    print(RG.load().ref_gemm_version().decode())
     rg = RG.RefGemm()
     gen = torch.Generator(device="cuda").manual_seed(0)
-    for name, K, N, epi in SHAPES:
+    results = {}
+    for name, K, N, epi in shapes:
         copies = max(2, (400 << 20) // (K * N // 2))
         x = torch.randn(m, K, generator=gen, device="cuda").half()
         qs, ss, zs, ref_lin, ours = [], [], [], [], []
@@ -91,12 +87,25 @@ def main():
         # (different random weights per copy; copy 0 on both sides)
         diff = (y_ref.float() - y_our.float()).abs().max().item()
         wb = K * N / 2 + K // 128 * N * 4
-        print(f"{name:5s} K={K:5d} N={N:5d} m={m}: reference {t_ref:7.2f} us ({wb / t_ref * 1e-3:6.0f} GB/s)   "
-              f"ours {t_our:7.2f} us ({wb / t_our * 1e-3:6.0f} GB/s)   ours/ref speed-up {t_ref / t_our:4.2f}x   "
-              f"max|y_ref - y_ours| {diff:.3g}")
+        results[name] = dict(K=K, N=N, reference_us=t_ref, ours_us=t_our, weight_bytes=int(wb), max_abs_diff=diff)
+        if verbose:
+            print(f"{name:5s} K={K:5d} N={N:5d} m={m}: reference {t_ref:7.2f} us ({wb / t_ref * 1e-3:6.0f} GB/s)   "
+                  f"ours {t_our:7.2f} us ({wb / t_our * 1e-3:6.0f} GB/s)   ours/ref speed-up {t_ref / t_our:4.2f}x   "
+                  f"max|y_ref - y_ours| {diff:.3g}")
         for r in ref_lin:
             r.close()
     rg.close()
+    return results
+
+
+def main():
+    m = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+    if not RG.available():
+        print("oracle/_ref/libtm_ref_gemm.so is not built")
+        return 1
+    print(RG.load().ref_gemm_version().decode())
+    measure(m, iters)
     return 0
 
 
