@@ -45,6 +45,25 @@ def available():
     return os.path.exists(LIB_PATH)
 
 
+NORM_LIB_PATH = os.path.join(ROOT, "_ref", "libtm_ref_norm.so")
+_norm_lib = None
+
+
+def norm_available():
+    return os.path.exists(NORM_LIB_PATH)
+
+
+def load_norm():
+    """libtm_ref_norm.so: the reference's invokeBiasResidualRMSNorm (oracle/ref_build/ref_norm_shim.cu)."""
+    global _norm_lib
+    if _norm_lib is None:
+        _norm_lib = C.CDLL(NORM_LIB_PATH)
+        _norm_lib.ref_bias_residual_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                                        C.c_float, C.c_int, C.c_void_p]
+        _norm_lib.ref_bias_residual_rmsnorm.restype = C.c_int
+    return _norm_lib
+
+
 def prefill_available():
     return os.path.exists(PREFILL_LIB_PATH)
 
