@@ -44,6 +44,24 @@ class GenerationConfig:
     skip_special_tokens: bool = True
     logprobs: Optional[int] = None
     output_logits: Optional[str] = None
+    # accepted for keyword compatibility with the reference; anything but the default is refused (not on the decode
+    # hot path: logits processors, guided decoding, hidden-state / ppl outputs, disaggregated serving, MoE routing)
+    spaces_between_special_tokens: bool = True
+    response_format: Optional[dict] = None
+    logits_processors: Optional[list] = None
+    output_last_hidden_state: Optional[str] = None
+    include_stop_str_in_output: bool = False
+    return_ppl: bool = False
+    with_cache: bool = False
+    preserve_cache: bool = False
+    migration_request: Optional[object] = None
+    return_routed_experts: bool = False
+    repetition_ngram_size: int = 0
+    repetition_ngram_threshold: int = 0
+
+    _UNSUPPORTED = {"response_format": None, "logits_processors": None, "output_last_hidden_state": None, "return_ppl": False,
+                    "with_cache": False, "preserve_cache": False, "migration_request": None, "return_routed_experts": False,
+                    "repetition_ngram_size": 0, "repetition_ngram_threshold": 0, "logprobs": None, "output_logits": None}
 
     def convert_stop_bad_words_to_ids(self, tokenizer):
         """stop_words -> stop_token_ids with the reference's rule (lmdeploy/messages.py:154-174 and
@@ -89,6 +107,11 @@ class GenerationConfig:
         # the decode hot path implements greedy sampling (top_k == 1, generation/sampling.cc:113-126)
         if self.do_sample and self.top_k != 1:
             raise NotImplementedError("lmdeploy_b200 implements the greedy decode path (top_k=1 / do_sample=False)")
+        for name, default in self._UNSUPPORTED.items():
+            if getattr(self, name) != default:
+                raise NotImplementedError(f"GenerationConfig.{name} is not supported on the greedy decode hot path")
+        if self.n != 1:
+            raise NotImplementedError("GenerationConfig.n > 1 is not supported")
 
 
 @dataclass
@@ -117,6 +140,25 @@ class TurbomindEngineConfig:
     communicator: str = "native"                 # 'native' (NVLink peer kernels); 'nccl' is not on this path
     hf_overrides: Optional[dict] = None
     enable_metrics: bool = True
+    # accepted for keyword compatibility with the reference (lmdeploy/messages.py TurbomindEngineConfig); the parallel /
+    # multi-node / recurrent-cache knobs below must keep their defaults on this path
+    cp: int = 1
+    ep: int = 1
+    device_num: Optional[int] = None
+    attn_tp_size: Optional[int] = None
+    attn_cp_size: Optional[int] = None
+    attn_dp_size: Optional[int] = None
+    mlp_tp_size: Optional[int] = None
+    mlp_dp_size: Optional[int] = None
+    outer_dp_size: Optional[int] = None
+    nnodes: int = 1
+    node_rank: int = 0
+    dist_init_addr: Optional[str] = None
+    cache_checkpoint_interval: int = 4096
+    cache_prompt: str = "auto"
+    cache_prompt_boundary_skip: int = 1
+    cache_generation: str = "auto"
+    language_model_only: bool = False
 
     def __post_init__(self):
         if self.dtype not in ("auto", "float16", "bfloat16"):
@@ -133,6 +175,15 @@ class TurbomindEngineConfig:
             raise ValueError("max_batch_size must be in [1, 128] on the decode hot path")
         if self.dp != 1:
             raise NotImplementedError("data parallel = independent replicas; launch one engine per replica")
+        if self.cp != 1 or self.ep != 1 or self.nnodes != 1 or (self.attn_cp_size or 1) != 1 or \
+                (self.attn_dp_size or 1) != 1 or (self.mlp_dp_size or 1) != 1 or (self.outer_dp_size or 1) != 1:
+            raise NotImplementedError("context / expert / data parallelism and multi-node launches are outside the hot path "
+                                      "(tensor parallelism over one NVSwitch box only)")
+        for name in ("attn_tp_size", "mlp_tp_size"):
+            if getattr(self, name) not in (None, self.tp):
+                raise NotImplementedError(f"{name} must equal tp")
+        if self.communicator not in ("native", "nccl", "cuda-ipc"):
+            raise ValueError(f"unknown communicator {self.communicator!r}")
 
 
 @dataclass

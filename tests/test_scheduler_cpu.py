@@ -556,3 +556,30 @@ def test_randomized_workloads_agree_with_the_plain_scheduler():
                 assert gen == base[i][0][:len(gen)]          # cut short (cancelled / out of KV memory): a prefix
 
     run()
+
+
+def test_config_keyword_surface_matches_the_reference():
+    """Every field of the reference's TurbomindEngineConfig / GenerationConfig (tests/golden/ref_config_fields.json, read
+    from lmdeploy/messages.py by tools/make_config_golden.py) is accepted here with the same default, so user code that
+    constructs them switches packages unchanged; the one deliberate difference is named."""
+    import dataclasses
+    import json
+    import os
+    import lmdeploy_b200.messages as M
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "ref_config_fields.json")))
+    deliberate = {("TurbomindEngineConfig", "communicator"): "'native'"}     # the NVLink peer-memory kernels, not NCCL
+    for cls, fields in ref.items():
+        ours = {f.name: f for f in dataclasses.fields(getattr(M, cls))}
+        assert set(fields) <= set(ours), sorted(set(fields) - set(ours))
+        for name, default in fields.items():
+            got = repr(ours[name].default)
+            want = deliberate.get((cls, name), default)
+            assert got.replace('"', "'") == str(want).replace('"', "'"), (cls, name, got, want)
+    M.TurbomindEngineConfig(communicator="nccl")            # accepted: selects nothing else
+    for kw in (dict(cp=2), dict(ep=2), dict(nnodes=2), dict(attn_tp_size=2), dict(attn_dp_size=2)):
+        with pytest.raises(NotImplementedError):
+            M.TurbomindEngineConfig(**kw)
+    for kw in (dict(response_format={"type": "json_schema"}), dict(logits_processors=[print]), dict(return_ppl=True),
+               dict(logprobs=5), dict(n=2), dict(repetition_ngram_size=3)):
+        with pytest.raises(NotImplementedError):
+            M.GenerationConfig(**kw)
