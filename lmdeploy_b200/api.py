@@ -47,8 +47,10 @@ class Pipeline:
         out = []
         for i, s in enumerate(seqs):
             text = self.tokenizer.decode(s.generated) if self.tokenizer is not None else ""
+            reason = {"cancel": "abort"}.get(s.finish_reason, s.finish_reason)      # the reference's vocabulary
             out.append(Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
-                                finish_reason=s.finish_reason, token_ids=list(s.generated), index=i))
+                                finish_reason=reason, token_ids=list(s.generated), index=i,
+                                cached_tokens=s.reused_tokens))
         return out[0] if single else out
 
     def close(self):

@@ -14,14 +14,20 @@ class QuantPolicy(enum.IntEnum):
 
 
 class ResponseType(enum.Enum):
-    SUCCESS = "success"
-    FINISH = "finish"
-    ENGINE_STOP_ERROR = "engine stop error"
-    SESSION_REPEAT = "session repeat"
-    SESSION_NOT_EXIST = "session not exist"
-    INPUT_LENGTH_ERROR = "input length error"
-    INTERNAL_ENGINE_ERROR = "internal engine error"
-    CANCEL = "cancel"
+    """Same members as the reference (lmdeploy/messages.py ResponseType)."""
+    SUCCESS = enum.auto()
+    FINISH = enum.auto()
+    ENGINE_STOP_ERROR = enum.auto()
+    SESSION_REPEAT = enum.auto()
+    SESSION_NOT_EXIST = enum.auto()
+    HANDLER_NOT_EXIST = enum.auto()
+    INPUT_LENGTH_ERROR = enum.auto()
+    INTERNAL_ENGINE_ERROR = enum.auto()
+    CANCEL = enum.auto()
+    PREFIX_CACHE_CONFLICT = enum.auto()
+    NO_QUEUE = enum.auto()
+    NOT_SUPPORTED = enum.auto()
+    OUT_OF_MEMORY = enum.auto()
 
 
 @dataclass
@@ -188,16 +194,31 @@ class TurbomindEngineConfig:
 
 @dataclass
 class Response:
-    text: str
-    generate_token_len: int
-    input_token_len: int
+    """Fields of the reference's Response; finish_reason is one of 'stop' | 'length' | 'error' | 'abort'."""
+    text: str = None
+    generate_token_len: int = None
+    input_token_len: int = None
     finish_reason: Optional[str] = None
     token_ids: List[int] = field(default_factory=list)
+    logprobs: Optional[list] = None          # not produced on the greedy hot path
+    logits: Optional[object] = None
+    last_hidden_state: Optional[object] = None
     index: int = 0
+    routed_experts: Optional[object] = None
+    cached_tokens: int = 0                   # prompt tokens served from the prefix cache
+    error_code: Optional[str] = None
+    error_message: Optional[str] = None
 
 
 @dataclass
 class EngineOutput:
-    status: ResponseType
-    token_ids: List[int]
+    status: ResponseType = None
+    token_ids: List[int] = None
     num_token: int = 0
+    logprobs: Optional[list] = None
+    logits: Optional[object] = None
+    last_hidden_state: Optional[object] = None
+    cache_block_ids: Optional[List[int]] = None
+    req_metrics: Optional[object] = None
+    routed_experts: Optional[object] = None
+    ce_loss: Optional[float] = None
