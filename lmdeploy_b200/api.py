@@ -3,7 +3,7 @@ from dataclasses import replace
 from typing import List, Optional, Union
 
 from .messages import GenerationConfig, Response, TurbomindEngineConfig
-from .turbomind.engine import TurboMind, batched_generate
+from .turbomind.engine import TurboMind, batched_generate, stream_generate
 
 
 class Pipeline:
@@ -32,30 +32,74 @@ class Pipeline:
             raise ValueError("no tokenizer: pass prompts as lists of token ids")
         return self.tokenizer.encode(prompt)
 
-    def __call__(self, prompts: Union[str, List[int], List[str], List[List[int]]],
-                 gen_config: Optional[GenerationConfig] = None, **kw):
+    def _prepare(self, prompts, gen_config):
         single = isinstance(prompts, str) or (isinstance(prompts, (list, tuple)) and prompts
                                               and isinstance(prompts[0], (int, dict)))
         plist = [prompts] if single else list(prompts)
         ids = [self._encode(p) for p in plist]
-        if gen_config is not None and (gen_config.stop_words or gen_config.bad_words):
-            if self.tokenizer is None:
-                raise ValueError("stop_words need a tokenizer: pass stop_token_ids instead")
-            gen_config = replace(gen_config)
-            gen_config.convert_stop_bad_words_to_ids(self.tokenizer)
-        seqs = batched_generate(self.engine, ids, gen_config)
+        cfgs = gen_config if isinstance(gen_config, (list, tuple)) else [gen_config] * len(ids)
         out = []
-        for i, s in enumerate(seqs):
-            text = self.tokenizer.decode(s.generated) if self.tokenizer is not None else ""
-            reason = {"cancel": "abort"}.get(s.finish_reason, s.finish_reason)      # the reference's vocabulary
-            out.append(Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
-                                finish_reason=reason, token_ids=list(s.generated), index=i,
-                                cached_tokens=s.reused_tokens))
+        for g in cfgs:
+            if g is not None and (g.stop_words or g.bad_words):
+                if self.tokenizer is None:
+                    raise ValueError("stop_words need a tokenizer: pass stop_token_ids instead")
+                g = replace(g)
+                g.convert_stop_bad_words_to_ids(self.tokenizer)
+            out.append(g)
+        return single, ids, out
+
+    def _response(self, i, s, token_ids):
+        reason = {"cancel": "abort"}.get(s.finish_reason, s.finish_reason)          # the reference's vocabulary
+        text = self.tokenizer.decode(token_ids) if self.tokenizer is not None and token_ids else ""
+        return Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
+                        finish_reason=reason if s.finished else None, token_ids=list(token_ids), index=i,
+                        cached_tokens=s.reused_tokens)
+
+    def infer(self, prompts: Union[str, List[int], List[str], List[List[int]], List[dict]],
+              gen_config: Union[GenerationConfig, List[GenerationConfig], None] = None, do_preprocess: bool = True,
+              adapter_name: Optional[str] = None, use_tqdm: bool = False, **kw):
+        """Same call shape as the reference's Pipeline.infer (lmdeploy/pipeline.py:97-139): a prompt or a list of
+        prompts (text, token ids or chat messages), one GenerationConfig or one per prompt -> Response / [Response]."""
+        if adapter_name is not None:
+            raise NotImplementedError("LoRA adapters are outside the hot-path scope")
+        single, ids, cfgs = self._prepare(prompts, gen_config)
+        seqs = batched_generate(self.engine, ids, cfgs)
+        out = [self._response(i, s, s.generated) for i, s in enumerate(seqs)]
         return out[0] if single else out
+
+    __call__ = infer
+
+    def batch_infer(self, *args, **kw):
+        return self.infer(*args, **kw)
+
+    def stream_infer(self, prompts, sessions=None, gen_config=None, do_preprocess: bool = True,
+                     adapter_name: Optional[str] = None, stream_response: bool = True, **kw):
+        """Generator of Response objects (lmdeploy/pipeline.py:145-178): with stream_response every yield carries the tokens
+        a prompt produced since its previous yield (`index` tells which prompt; finish_reason is set on its last one);
+        without it one final Response per prompt."""
+        if adapter_name is not None or sessions is not None:
+            raise NotImplementedError("sessions / adapters are outside the hot-path scope")
+        _, ids, cfgs = self._prepare(prompts, gen_config)
+        acc = {}
+        for i, s, new in stream_generate(self.engine, ids, cfgs):
+            if stream_response:
+                if new or s.finished:
+                    yield self._response(i, s, new)
+            else:
+                acc.setdefault(i, []).extend(new)
+                if s.finished:
+                    yield self._response(i, s, acc[i])
 
     def close(self):
         self.engine = None
 
 
-def pipeline(model_path: str, backend_config: Optional[TurbomindEngineConfig] = None, **kw) -> Pipeline:
+def pipeline(model_path: str, backend_config: Optional[TurbomindEngineConfig] = None, chat_template_config=None,
+             log_level: str = "WARNING", max_log_len: Optional[int] = None, trust_remote_code: bool = False,
+             speculative_config=None, allowed_media_domains=None, **kw) -> Pipeline:
+    """Same signature as lmdeploy.pipeline (lmdeploy/api.py:15-82).  chat_template_config: the tokenizer's own chat
+    template is used; log_level / max_log_len / trust_remote_code / allowed_media_domains have nothing to act on here;
+    speculative decoding is not on this path."""
+    if speculative_config is not None:
+        raise NotImplementedError("speculative decoding is outside the hot-path scope")
     return Pipeline(model_path, backend_config, **kw)

@@ -236,10 +236,45 @@ class TurboMindInstance:
         self.engine.scheduler.cancel(session_id)
 
 
-def batched_generate(engine: TurboMind, prompts: List[List[int]], gen_config: GenerationConfig = None):
-    """Run a list of token-id prompts to completion with continuous batching; returns per-prompt generated ids."""
-    inst = engine.create_instance()
-    seqs = [inst._submit(engine.new_session_id(), p, gen_config) for p in prompts]
+def _per_prompt(gen_config, n):
+    if isinstance(gen_config, (list, tuple)):
+        if len(gen_config) != n:
+            raise ValueError(f"{len(gen_config)} generation configs for {n} prompts")
+        return list(gen_config)
+    return [gen_config] * n
+
+
+def batched_generate(engine, prompts: List[List[int]], gen_config=None):
+    """Run a list of token-id prompts to completion with continuous batching; returns the Sequence of every prompt.
+    gen_config: one GenerationConfig for all prompts or one per prompt."""
+    inst = TurboMindInstance(engine)
+    cfgs = _per_prompt(gen_config, len(prompts))
+    seqs = [inst._submit(engine.new_session_id(), p, g) for p, g in zip(prompts, cfgs)]
     while engine.scheduler.has_work:
         engine.step()
     return seqs
+
+
+def stream_generate(engine, prompts: List[List[int]], gen_config=None):
+    """Continuous batching with per-token delivery: yields (prompt index, Sequence, new token ids) after every engine step
+    in which that prompt produced tokens; the last yield of a prompt has Sequence.finished set (it carries the final tokens,
+    or an empty list when the prompt ended without producing any in that step -- cancelled, out of KV memory)."""
+    inst = TurboMindInstance(engine)
+    cfgs = _per_prompt(gen_config, len(prompts))
+    seqs = [inst._submit(engine.new_session_id(), p, g) for p, g in zip(prompts, cfgs)]
+    sent = [0] * len(seqs)
+    done = [False] * len(seqs)
+    while not all(done):
+        if engine.scheduler.has_work:
+            engine.step()
+        for i, s in enumerate(seqs):
+            if done[i]:
+                continue
+            if len(s.generated) > sent[i]:
+                new = s.generated[sent[i]:]
+                sent[i] = len(s.generated)
+                done[i] = s.finished                 # the chunk that carries the last token is the final one
+                yield i, s, list(new)
+            elif s.finished:
+                done[i] = True
+                yield i, s, []

@@ -583,3 +583,61 @@ def test_config_keyword_surface_matches_the_reference():
                dict(logprobs=5), dict(n=2), dict(repetition_ngram_size=3)):
         with pytest.raises(NotImplementedError):
             M.GenerationConfig(**kw)
+
+
+class _FakeEngine:
+    """The three things the pipeline layer uses of TurboMind -- scheduler, eos_id, step(), new_session_id() -- over the
+    fake KV model, so Pipeline.infer / stream_infer run on CPU."""
+
+    def __init__(self, **sched_kw):
+        self.scheduler = Scheduler(max_batch=3, block_len=4, num_blocks=64, session_len=256, **sched_kw)
+        self.model = FakeChunkModel(64, 4, vocab=12)             # tiny vocabulary: stop tokens get hit
+        self.eos_id = None
+        self._sid = 0
+
+    def new_session_id(self):
+        self._sid += 1
+        return self._sid
+
+    def step(self):
+        batch = self.scheduler.schedule()
+        if batch:
+            return self.scheduler.update(batch, self.model.step(batch))
+        return []
+
+
+def _fake_pipeline(**sched_kw):
+    from lmdeploy_b200.api import Pipeline
+    p = Pipeline.__new__(Pipeline)
+    p.engine, p.tokenizer = _FakeEngine(**sched_kw), None
+    return p
+
+
+def test_pipeline_infer_and_stream_infer_agree():
+    prompts = [[3, 1, 4, 1, 5, 9, 2, 6], [2, 7], [1, 8, 2, 8, 1, 8]]
+    cfgs = [GenerationConfig(max_new_tokens=n, ignore_eos=True) for n in (5, 9, 1)]
+    full = _fake_pipeline().infer(prompts, cfgs)
+    assert [r.index for r in full] == [0, 1, 2] and [r.generate_token_len for r in full] == [5, 9, 1]
+    assert all(r.finish_reason == "length" and r.input_token_len == len(p) for r, p in zip(full, prompts))
+    single = _fake_pipeline().infer(prompts[0], cfgs[0])
+    assert single.token_ids == full[0].token_ids                # a single prompt returns a single Response
+    # streamed: the concatenation of a prompt's chunks is its full answer; exactly one final chunk per prompt
+    chunks = list(_fake_pipeline().stream_infer(prompts, gen_config=cfgs))
+    for i in range(3):
+        mine = [c for c in chunks if c.index == i]
+        assert sum((c.token_ids for c in mine), []) == full[i].token_ids
+        assert [c.finish_reason for c in mine][:-1] == [None] * (len(mine) - 1) and mine[-1].finish_reason == "length"
+    # non-streaming mode of stream_infer: one Response per prompt
+    finals = list(_fake_pipeline().stream_infer(prompts, gen_config=cfgs, stream_response=False))
+    assert sorted((r.index, tuple(r.token_ids)) for r in finals) == [(i, tuple(full[i].token_ids)) for i in range(3)]
+    # per-prompt stop tokens; a cancelled request reports 'abort'
+    stop = full[1].token_ids[3]
+    r = _fake_pipeline().infer([prompts[1]], [GenerationConfig(max_new_tokens=9, stop_token_ids=[stop])])[0]
+    assert r.finish_reason == "stop" and r.token_ids == full[1].token_ids[:full[1].token_ids.index(stop) + 1]
+    with pytest.raises(ValueError):
+        _fake_pipeline().infer(prompts, cfgs[:2])
+    # prefix cache: the second identical request reports its reused tokens
+    p = _fake_pipeline(prefix_caching=True)
+    a = p.infer([prompts[0]], cfgs[0])[0]
+    b = p.infer([prompts[0]], cfgs[0])[0]
+    assert a.token_ids == b.token_ids and a.cached_tokens == 0 and b.cached_tokens == 4
