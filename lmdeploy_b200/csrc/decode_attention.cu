@@ -600,8 +600,10 @@ static int launch_prefill(const b200_attention_params* a)
         return e;
     }
     auto kern = prefill_attention_kernel<T, KVBITS>;
-    static std::once_flag once;  // per (T, KVBITS) instantiation
-    std::call_once(once, [&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem); });
+    // per launch (cheap, and correct for a process that drives several devices)
+    if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPfSmem); e != cudaSuccess) {
+        return fail_cuda(e, "cudaFuncSetAttribute(prefill_attention_kernel)");
+    }
     PrefillParams p{};
     p.q_rot         = q_rot;
     p.out           = a->out;
