@@ -8,7 +8,7 @@ cd "$(dirname "$0")/.."
 run() { # name, timeout seconds, command...
     local name=$1 t=$2; shift 2
     echo "=== $name"
-    timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1
+    timeout -k 10 "$t" "$@" > "gpurun_out/$name.log" 2>&1
     echo "exit $? ($name)"; tail -n 6 "gpurun_out/$name.log"
 }
 run verified_suite 900 python -m pytest tests -x -q -m gpu
