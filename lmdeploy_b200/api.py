@@ -90,8 +90,20 @@ class Pipeline:
                 if s.finished:
                     yield self._response(i, s, acc[i])
 
+    def get_ppl(self, input_ids):
+        raise NotImplementedError("get_ppl needs per-position logits of the prompt (return_ppl path); the decode hot path "
+                                  "keeps only the sampled row")
+
     def close(self):
-        self.engine = None
+        eng, self.engine = self.engine, None
+        if eng is not None and hasattr(eng, "close"):
+            eng.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback):
+        self.close()
 
 
 def pipeline(model_path: str, backend_config: Optional[TurbomindEngineConfig] = None, chat_template_config=None,
