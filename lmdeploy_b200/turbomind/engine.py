@@ -56,7 +56,8 @@ class TurboMind:
         self.spec = spec
         self.eos_id = eos_id
         self.max_batch = cfg.max_batch_size or 64
-        self.session_len = cfg.session_len or 4096
+        # the reference defaults session_len to the model's context length (turbomind.py: session_len from the HF config)
+        self.session_len = cfg.session_len or spec.max_position_embeddings or 4096
         self.block_len = cfg.cache_block_seq_len
         self.model = model or DecodeModel(spec, quant_policy=cfg.quant_policy, block_len=self.block_len,
                                           max_batch=self.max_batch)

@@ -124,7 +124,8 @@ def spec_from_config(cfg):
                      rope_theta=rope.base, head_dim=head_dim,
                      norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope.type, rope_factor=rope.factor, rope=rope,
                      weight_format=fmt,
-                     checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias)
+                     checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias,
+                     max_position_embeddings=int(cfg.get("max_position_embeddings", 0)))
 
 
 def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):

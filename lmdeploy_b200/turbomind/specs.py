@@ -42,6 +42,7 @@ class ModelSpec:
     checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
     qkv_bias: bool = False          # q/k/v projections carry a bias (Qwen2 family), applied by the attention prologue
     rope: RopeSpec = None           # full RoPE description (checkpoints); None = rope_type / rope_theta / rope_factor above
+    max_position_embeddings: int = 0   # the checkpoint's context length (0 = unknown): default session_len of the engine
 
     def tiny(self, layers=2):
         return replace(self, layers=layers)
