@@ -67,7 +67,9 @@ class GenerationConfig:
 
     _UNSUPPORTED = {"response_format": None, "logits_processors": None, "output_last_hidden_state": None, "return_ppl": False,
                     "with_cache": False, "preserve_cache": False, "migration_request": None, "return_routed_experts": False,
-                    "repetition_ngram_size": 0, "repetition_ngram_threshold": 0, "logprobs": None, "output_logits": None}
+                    "repetition_ngram_size": 0, "repetition_ngram_threshold": 0, "logprobs": None, "output_logits": None,
+                    # these change the GREEDY token too (they act on the logits before the argmax), so they cannot be ignored
+                    "repetition_penalty": 1.0, "min_new_tokens": None}
 
     def convert_stop_bad_words_to_ids(self, tokenizer):
         """stop_words -> stop_token_ids with the reference's rule (lmdeploy/messages.py:154-174 and

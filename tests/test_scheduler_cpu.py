@@ -641,3 +641,11 @@ def test_pipeline_infer_and_stream_infer_agree():
     a = p.infer([prompts[0]], cfgs[0])[0]
     b = p.infer([prompts[0]], cfgs[0])[0]
     assert a.token_ids == b.token_ids and a.cached_tokens == 0 and b.cached_tokens == 4
+
+
+def test_options_that_would_change_greedy_tokens_are_refused():
+    GenerationConfig(temperature=0.3, top_p=0.8, top_k=40, min_p=0.1)          # sampling knobs are inert without do_sample
+    GenerationConfig(do_sample=True, top_k=1)                                   # top_k = 1 is greedy
+    for kw in (dict(repetition_penalty=1.1), dict(min_new_tokens=4), dict(do_sample=True, top_k=40)):
+        with pytest.raises(NotImplementedError):
+            GenerationConfig(**kw)
