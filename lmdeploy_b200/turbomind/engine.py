@@ -212,7 +212,9 @@ class TurboMindInstance:
 
     def _submit(self, session_id, input_ids, gen_config):
         g = gen_config or GenerationConfig()
-        seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=g.max_new_tokens,
+        # max_new_tokens = None: until the session is full (the scheduler clamps to session_len), as the reference does
+        budget = g.max_new_tokens if g.max_new_tokens is not None else 1 << 30
+        seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=budget,
                        stop_token_ids=list(g.stop_token_ids or []), ignore_eos=g.ignore_eos, eos_id=self.engine.eos_id)
         self.engine.scheduler.add(seq)
         return seq

@@ -649,3 +649,10 @@ def test_options_that_would_change_greedy_tokens_are_refused():
     for kw in (dict(repetition_penalty=1.1), dict(min_new_tokens=4), dict(do_sample=True, top_k=40)):
         with pytest.raises(NotImplementedError):
             GenerationConfig(**kw)
+
+
+def test_unbounded_generation_stops_at_the_session_length():
+    p = _fake_pipeline()
+    p.engine.scheduler.session_len = 20
+    r = p.infer([[1, 2, 3, 4, 5]], GenerationConfig(max_new_tokens=None, ignore_eos=True))[0]
+    assert r.finish_reason == "length" and r.input_token_len + r.generate_token_len == 20
