@@ -53,7 +53,8 @@ class Pipeline:
         text = self.tokenizer.decode(token_ids) if self.tokenizer is not None and token_ids else ""
         return Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
                         finish_reason=reason if s.finished else None, token_ids=list(token_ids), index=i,
-                        cached_tokens=s.reused_tokens)
+                        cached_tokens=s.reused_tokens, error_code="input_length" if s.error else None,
+                        error_message=s.error)
 
     def infer(self, prompts: Union[str, List[int], List[str], List[List[int]], List[dict]],
               gen_config: Union[GenerationConfig, List[GenerationConfig], None] = None, do_preprocess: bool = True,

@@ -13,7 +13,7 @@ import torch
 
 from ..messages import EngineOutput, GenerationConfig, ResponseType, TurbomindEngineConfig
 from .runtime import DecodeModel, KvCachePool
-from .scheduler import Scheduler, Sequence
+from .scheduler import InputLengthError, Scheduler, Sequence
 from .specs import SPECS, ModelSpec
 
 
@@ -220,7 +220,14 @@ class TurboMindInstance:
         return seq
 
     def stream_infer(self, session_id, input_ids, gen_config: GenerationConfig = None, **kw):
-        seq = self._submit(session_id, input_ids, gen_config)
+        try:
+            seq = self._submit(session_id, input_ids, gen_config)
+        except InputLengthError:
+            yield EngineOutput(ResponseType.INPUT_LENGTH_ERROR, [], 0)
+            return
+        except KeyError:
+            yield EngineOutput(ResponseType.SESSION_REPEAT, [], 0)
+            return
         sent = 0
         while not seq.finished:
             self.engine.step()
@@ -247,12 +254,23 @@ def _per_prompt(gen_config, n):
     return [gen_config] * n
 
 
+def _submit_or_reject(inst, engine, prompt, gen_config):
+    """A prompt that cannot be admitted becomes a finished Sequence with finish_reason 'error' (the others still run)."""
+    try:
+        return inst._submit(engine.new_session_id(), prompt, gen_config)
+    except InputLengthError as e:
+        seq = Sequence(session_id=-1, prompt=list(map(int, prompt)), max_new_tokens=0, stop_token_ids=[], ignore_eos=True,
+                       eos_id=None)
+        seq.finished, seq.finish_reason, seq.error = True, "error", str(e)
+        return seq
+
+
 def batched_generate(engine, prompts: List[List[int]], gen_config=None):
     """Run a list of token-id prompts to completion with continuous batching; returns the Sequence of every prompt.
     gen_config: one GenerationConfig for all prompts or one per prompt."""
     inst = TurboMindInstance(engine)
     cfgs = _per_prompt(gen_config, len(prompts))
-    seqs = [inst._submit(engine.new_session_id(), p, g) for p, g in zip(prompts, cfgs)]
+    seqs = [_submit_or_reject(inst, engine, p, g) for p, g in zip(prompts, cfgs)]
     while engine.scheduler.has_work:
         engine.step()
     return seqs
@@ -264,7 +282,7 @@ def stream_generate(engine, prompts: List[List[int]], gen_config=None):
     or an empty list when the prompt ended without producing any in that step -- cancelled, out of KV memory)."""
     inst = TurboMindInstance(engine)
     cfgs = _per_prompt(gen_config, len(prompts))
-    seqs = [inst._submit(engine.new_session_id(), p, g) for p, g in zip(prompts, cfgs)]
+    seqs = [_submit_or_reject(inst, engine, p, g) for p, g in zip(prompts, cfgs)]
     sent = [0] * len(seqs)
     done = [False] * len(seqs)
     while not all(done):

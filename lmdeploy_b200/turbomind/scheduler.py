@@ -41,6 +41,7 @@ class Sequence:
     finish_reason: Optional[str] = None
     reused_tokens: int = 0        # prompt tokens served from the prefix cache (never fed)
     step_tokens: int = 1          # tokens this sequence feeds in the step being formed / executed
+    error: Optional[str] = None   # why the request was rejected (finish_reason 'error')
     chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
 
     def token_at(self, pos):
@@ -60,6 +61,10 @@ class Sequence:
     @property
     def in_prefill(self):
         return self.fed < len(self.prompt) - 1
+
+
+class InputLengthError(ValueError):
+    """The prompt alone fills the session (the reference answers ResponseType.INPUT_LENGTH_ERROR)."""
 
 
 class BlockAllocator:
@@ -183,6 +188,8 @@ class Scheduler:
             raise KeyError(f"session {seq.session_id} already exists")
         if len(seq.prompt) == 0:
             raise ValueError("empty prompt")
+        if len(seq.prompt) >= self.session_len:
+            raise InputLengthError(f"prompt of {len(seq.prompt)} tokens does not fit session_len {self.session_len}")
         if len(seq.prompt) + seq.max_new_tokens > self.session_len:
             seq.max_new_tokens = max(0, self.session_len - len(seq.prompt))
         self.sessions[seq.session_id] = seq
@@ -198,14 +205,8 @@ class Scheduler:
         self.alloc.release(blocks)
         seq.blocks = []
 
-    def _blocks_needed(self, seq, upto_tokens):
-        return (upto_tokens + self.block_len - 1) // self.block_len - len(seq.blocks)
-
-    def schedule(self):
-        """Form the batch of this step.  Returns the sequences that run; each feeds `step_tokens` tokens (1 unless it
-        is inside its prompt and prefill_chunk > 1)."""
-        self.tick += 1
-        # retire
+    def _retire(self):
+        """Give back the blocks and the session slot of every finished active sequence."""
         still = []
         for s in self.active:
             if s.finished:
@@ -214,6 +215,15 @@ class Scheduler:
             else:
                 still.append(s)
         self.active = still
+
+    def _blocks_needed(self, seq, upto_tokens):
+        return (upto_tokens + self.block_len - 1) // self.block_len - len(seq.blocks)
+
+    def schedule(self):
+        """Form the batch of this step.  Returns the sequences that run; each feeds `step_tokens` tokens (1 unless it
+        is inside its prompt and prefill_chunk > 1)."""
+        self.tick += 1
+        self._retire()
         # grow active sequences that cross a block boundary (need room for token index `cached`)
         for s in self.active:
             need = self._blocks_needed(s, s.cached + 1)
@@ -287,6 +297,7 @@ class Scheduler:
             elif len(s.generated) >= s.max_new_tokens or s.cached + 1 > self.session_len:
                 s.finished, s.finish_reason = True, "length"
             events.append((s, int(tok)))
+        self._retire()                     # an idle engine holds no blocks of finished requests
         return events
 
     @property

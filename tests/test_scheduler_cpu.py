@@ -656,3 +656,18 @@ def test_unbounded_generation_stops_at_the_session_length():
     p.engine.scheduler.session_len = 20
     r = p.infer([[1, 2, 3, 4, 5]], GenerationConfig(max_new_tokens=None, ignore_eos=True))[0]
     assert r.finish_reason == "length" and r.input_token_len + r.generate_token_len == 20
+
+
+def test_a_prompt_that_fills_the_session_is_rejected_alone():
+    p = _fake_pipeline()
+    p.engine.scheduler.session_len = 12
+    ok, bad = [1, 2, 3], list(range(12))
+    res = p.infer([ok, bad], GenerationConfig(max_new_tokens=3, ignore_eos=True))
+    assert res[0].finish_reason == "length" and len(res[0].token_ids) == 3
+    assert res[1].finish_reason == "error" and res[1].error_code == "input_length" and "session_len 12" in res[1].error_message
+    assert res[1].token_ids == [] and p.engine.scheduler.metrics()["total_seqs"] == 0
+    # instance level: the reference's status code
+    from lmdeploy_b200.messages import ResponseType
+    from lmdeploy_b200.turbomind.engine import TurboMindInstance
+    outs = list(TurboMindInstance(p.engine).stream_infer(99, bad, GenerationConfig(max_new_tokens=3)))
+    assert [o.status for o in outs] == [ResponseType.INPUT_LENGTH_ERROR]
