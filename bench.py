@@ -63,46 +63,143 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def _gpu_uuid(torch, local):
+    """'GPU-xxxxxxxx-…' of torch device `local` (NVML / nvidia-smi enumerate ALL GPUs; CUDA_VISIBLE_DEVICES may not)."""
+    try:
+        u = str(torch.cuda.get_device_properties(local).uuid)
+        return u if u.startswith("GPU-") else "GPU-" + u
+    except Exception:
+        return None
+
+
 class ClockSampler:
-    """Samples SM clock + throttle reasons with nvidia-smi while the timed region runs."""
+    """SM clock + throttle reasons of one GPU, sampled WHILE the timed region runs.
 
-    def __init__(self, index=0):
-        self.rows = []
-        self.proc = None
-        self.index = index
+    Primary backend: NVML in this process (pynvml), one sample every 2 ms from a thread, so even a 50 ms timed region
+    (TP8) holds tens of samples.  Fallback: `nvidia-smi -lms`, started by start() BEFORE the warm-up because the tool
+    takes about a second to come up on an 8-GPU box (an N=8 run of round 1 ended with zero samples that way).  Either
+    way only samples stamped inside [begin, end] of the `with` block count."""
 
-    def __enter__(self):
+    # NVML clocks-event-reason bits (nvml.h; stable ABI)
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+    SMI_REASONS = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, index=0, uuid=None, nvml=None, period_s=0.002):
+        self.index, self.uuid, self.period_s = index, uuid, period_s
+        self.samples = []             # (t, sm_mhz, reasons set)
+        self.sm_max = None
+        self.t_begin = self.t_end = None
+        self.backend = None
+        self._stop = threading.Event()
+        self._thread = self._proc = self._nvml = self._handle = None
+        self._nvml_module = nvml
+
+    # -- backends ------------------------------------------------------------------------------------------------
+    def _open_nvml(self):
+        nv = self._nvml_module
+        if nv is None:
+            import pynvml as nv
+        nv.nvmlInit()
+        handle = None
+        if self.uuid:
+            for u in (self.uuid, self.uuid.encode() if isinstance(self.uuid, str) else self.uuid):
+                try:
+                    handle = nv.nvmlDeviceGetHandleByUUID(u)
+                    break
+                except Exception:
+                    handle = None
+        if handle is None:
+            handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+        self._reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        self.sm_max = int(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        self._nvml, self._handle = nv, handle
+        self._sample_nvml()           # one call up front: a broken query fails here, not in the thread
+        self.samples.clear()
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        mhz = int(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+        mask = int(self._reasons_fn(self._handle))
+        self.samples.append((time.perf_counter(), mhz, {n for n, b in self.REASON_BITS.items() if mask & b}))
+
+    def _loop_nvml(self):
+        while not self._stop.is_set():
+            try:
+                self._sample_nvml()
+            except Exception:
+                return
+            self._stop.wait(self.period_s)
+
+    def _open_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        sel = self.uuid if self.uuid else str(self.index)
+        self._proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", sel,
+                                       "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+    def _loop_smi(self):
+        for line in self._proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            if not r or not r[0].isdigit():
+                continue
+            if len(r) > 1 and r[1].isdigit():
+                self.sm_max = max(self.sm_max or 0, int(r[1]))
+            reasons = {n for i, n in enumerate(self.SMI_REASONS) if len(r) > 2 + i and r[2 + i].lower().startswith("active")}
+            self.samples.append((time.perf_counter(), int(r[0]), reasons))
+
+    # -- lifecycle -----------------------------------------------------------------------------------------------
+    def start(self):
+        """Bring the backend up (call before the warm-up).  Idempotent; never raises."""
+        if self.backend is not None:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            self._open_nvml()
+            self.backend, target = "nvml", self._loop_nvml
         except Exception:
-            self.proc = None
+            try:
+                self._open_smi()
+                self.backend, target = "nvidia-smi", self._loop_smi
+            except Exception:
+                self.backend = "none"
+                return self
+        self._thread = threading.Thread(target=target, daemon=True)
+        self._thread.start()
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+    def wait_ready(self, limit_s=5.0):
+        """Block (bounded) until the fallback tool printed its first row.  Call BEFORE the barrier that precedes the
+        timed region, never inside it: ranks must enter the region together."""
+        self.start()
+        if self.backend == "nvidia-smi":
+            t0 = time.perf_counter()
+            while not self.samples and time.perf_counter() - t0 < limit_s and self._proc.poll() is None:
+                time.sleep(0.01)
+        return self
+
+    def __enter__(self):
+        self.start()
+        self.t_begin = time.perf_counter()
+        return self
 
     def __exit__(self, *a):
-        if self.proc:
-            time.sleep(0.15)
-            self.proc.terminate()
+        self.t_end = time.perf_counter()
+        if self.backend == "nvidia-smi":
+            time.sleep(0.03)                      # one more period: a row that describes the tail of the region
+        self._stop.set()
+        if self._proc is not None:
+            self._proc.terminate()
+        if self._thread is not None:
+            self._thread.join(timeout=1.0)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for i, n in enumerate(names):
-                if len(r) > 2 + i and r[2 + i].lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        slack = 0.03 if self.backend == "nvidia-smi" else 0.0
+        inside = [s for s in self.samples
+                  if self.t_begin is not None and self.t_begin <= s[0] <= (self.t_end or float("inf")) + slack]
+        sm = sorted(s[1] for s in inside)
+        reasons = set().union(*[s[2] for s in inside]) if inside else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(reasons),
+                "samples": len(sm), "source": self.backend}
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -178,11 +275,13 @@ def run_b200(args):
     use_graph = not args.no_graph
     runner.reset_lengths(ctx)
     step_fn = runner.make_device_step(graph=use_graph)
+    clocks = ClockSampler(local, uuid=_gpu_uuid(torch, local)).start()
     for _ in range(args.warmup):
         step_fn()
+    clocks.wait_ready()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
+    with clocks:
         ev0.record()
         for _ in range(args.steps):
             step_fn()
