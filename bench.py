@@ -238,8 +238,7 @@ def run_reference(args):
 def run_b200(args):
     import torch
     import torch.distributed as dist
-    from lmdeploy_b200 import _lib as L
-    from lmdeploy_b200.turbomind import SPECS, DecodeModel, KvCachePool
+    from lmdeploy_b200.turbomind import SPECS, DecodeModel
     from lmdeploy_b200.turbomind.tp import TpGroup
     from lmdeploy_b200.engine import StaticBatchRunner
 

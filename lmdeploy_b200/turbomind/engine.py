@@ -8,7 +8,6 @@ import os
 import threading
 from typing import List, Optional
 
-import numpy as np
 import torch
 
 from ..messages import EngineOutput, GenerationConfig, ResponseType, TurbomindEngineConfig
