@@ -96,6 +96,7 @@ def load():
     lib.b200_decode_attention.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_process_kv.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_prefill_attention.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_rope_table.argtypes = [C.c_void_p, C.POINTER(RopeConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_prefill_attention_workspace_bytes.restype = C.c_size_t
     lib.b200_prefill_attention_workspace_bytes.argtypes = [C.c_int, C.c_int]
     lib.b200_decode_attention_grid.argtypes = [C.c_int, C.c_int]

@@ -53,3 +53,43 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, os.path.join(dp, f)
+
+
+def _prototypes():
+    """name -> (return type text, [parameter texts]) of every B200_API declaration in the header."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "b200_turbomind.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", " ", hdr, flags=re.S)
+    out = {}
+    for ret, name, args in re.findall(r"B200_API\s+([\w\s\*]+?)\b(b200_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        out[name] = (" ".join(ret.split()), params)
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes(lib):
+    """Every function the binding declares argtypes for takes as many parameters as the header says, pointer parameters are
+    declared as pointers (never a bare int: ctypes would truncate a 64-bit address), and non-int returns carry a restype."""
+    import ctypes as C
+    protos = _prototypes()
+    assert len(protos) >= 30
+    declared = 0
+    for name, (ret, params) in protos.items():
+        fn = getattr(lib, name)
+        if ret in ("size_t", "const char*", "const char *"):
+            assert fn.restype is not C.c_int, f"{name} returns {ret} but the binding leaves restype at c_int"
+        if fn.argtypes is None:
+            # undeclared argtypes pass Python ints as 32-bit: only acceptable when nothing pointer-like is passed
+            assert not any("*" in p or "[" in p for p in params), f"{name} takes pointers but the binding declares no argtypes"
+            continue
+        declared += 1
+        assert len(fn.argtypes) == len(params), (name, params, fn.argtypes)
+        for p, t in zip(params, fn.argtypes):
+            is_ptr = "*" in p or "[" in p            # an array parameter decays to a pointer
+            t_ptr = t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) == "P"
+            assert is_ptr == bool(t_ptr), (name, p, t)
+            if not is_ptr:
+                want = {"int": C.c_int, "float": C.c_float, "size_t": C.c_size_t, "int64_t": C.c_int64}[p.split()[-2] if len(p.split()) > 1 else p]
+                assert t is want, (name, p, t)
+    assert declared >= 25
