@@ -19,14 +19,14 @@ from harness import to_dev_T, from_dev_T
 pytestmark = pytest.mark.gpu
 
 
-def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_rank=0, shard=None):
+def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_rank=0, shard=None, rope_exact_math=True):
     import torch
     from lmdeploy_b200.turbomind import ModelSpec, DecodeModel
     T = w.dtype
     spec = ModelSpec("tiny", "llama", w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab, 1e4,
                      weight_format=w.fmt, dtype="f16" if T == F16 else "bf16", qkv_bias="qkv_bias" in w.L[0])
     m = DecodeModel(spec, quant_policy=quant_policy, max_batch=max_batch, tp_size=tp_size, tp_rank=tp_rank,
-                    rope_exact_math=True)   # the numpy oracle cannot reproduce MUFU approximations
+                    rope_exact_math=rope_exact_math)   # True: the numpy oracle cannot reproduce MUFU approximations
     sw = shard if shard is not None else w
 
     def lin(d):

@@ -18,6 +18,7 @@ P="python -m pytest tests/test_zz_pending_gpu.py -q -m gpu -p no:cacheprovider"
 run pending_fp8_linear 240 $P -k "fp8_per_column or fp8_block_scales or fp8_gated"
 run pending_ref_gemm 240 $P -k "reference_gemm"
 run pending_ref_norm 120 $P -k "rmsnorm_matches_reference"
+run pending_l2_reference_step 300 $P -s -k "assembled_from_reference_kernels"
 run pending_bf16_steps 300 $P -k "bf16_matches_oracle or synthetic_fp8 or qkv_bias or odd_gqa"
 run pending_prefill_oracle 420 $P -k "prefill_attention_matches_oracle or prefill_single or prefill_attention_bf16"
 run pending_prefill_reference 240 $P -k "prefill_attention_matches_reference"
