@@ -61,7 +61,11 @@ def parse_rope(cfg, head_dim):
     prf = (rp or {}).get("partial_rotary_factor")
     if prf is None:
         prf = float(cfg.get("partial_rotary_factor", 1.0))
-    kw = dict(type="default", dim=int(head_dim * prf), base=theta)
+    # `factor` 1.0 and the MODEL's context length for every type: what copy_rope_config hands the C++ config
+    # (models/utils.py:170-187).  Note the yarn quirk this preserves: the correction range is computed from the
+    # config's max_position_embeddings, not from rope_scaling.original_max_position_embeddings (which only re-derives
+    # the factor) -- tests/golden/ref_rope_configs.json records the reference's own outputs.
+    kw = dict(type="default", dim=int(head_dim * prf), base=theta, factor=1.0, max_position_embeddings=max_pos)
     if scaling:
         rtype = scaling.get("rope_type") or scaling.get("type") or "default"
         factor = float(scaling.get("factor", 0.0) or 0.0)
@@ -83,9 +87,7 @@ def parse_rope(cfg, head_dim):
             orig = scaling.get("original_max_position_embeddings")
             if orig is not None:
                 factor = max_pos / orig
-            else:
-                orig = max_pos
-            kw.update(type="yarn", factor=float(factor), max_position_embeddings=int(orig), attention_factor=float(af),
+            kw.update(type="yarn", factor=float(factor), attention_factor=float(af),
                       beta_fast=float(scaling.get("beta_fast", 32.0)), beta_slow=float(scaling.get("beta_slow", 1.0)))
         elif rtype == "dynamic":
             raise NotImplementedError("dynamic-NTK rope is not supported by the sm_100a kernels")

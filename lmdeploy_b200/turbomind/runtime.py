@@ -104,11 +104,7 @@ class DecodeModel:
         cfg.inv_sqrt_dh = float(torch.tensor(1.4426950408889634, dtype=torch.float32)
                                 / torch.sqrt(torch.tensor(float(spec.head_dim), dtype=torch.float32)))
         r = spec.rope or RopeSpec(type=spec.rope_type, dim=spec.head_dim, base=spec.rope_theta, factor=spec.rope_factor)
-        if r.type not in RopeSpec.TYPE_ID:
-            raise NotImplementedError(f"rope type {r.type!r} (supported: {sorted(RopeSpec.TYPE_ID)})")
-        cfg.rope = L.RopeConfig(RopeSpec.TYPE_ID[r.type], r.dim, r.base, r.factor, r.max_position_embeddings,
-                                r.low_freq_factor, r.high_freq_factor, r.original_max_position_embeddings,
-                                r.attention_factor, r.beta_fast, r.beta_slow, 1 if rope_exact_math else 0)
+        cfg.rope = L.RopeConfig(**r.config_fields(), exact_math=1 if rope_exact_math else 0)
         cfg.dtype, cfg.quant_policy, cfg.block_len = _DT[spec.dtype], quant_policy, block_len
         cfg.max_batch, cfg.tp_size, cfg.tp_rank = max_batch, tp_size, tp_rank
         self.cfg = cfg

@@ -11,7 +11,7 @@ class RopeSpec:
     dim: int = 128                      # rotated dims = head_dim * partial_rotary_factor
     base: float = 10000.0
     factor: float = 0.0
-    max_position_embeddings: int = 0    # yarn: the ORIGINAL context length
+    max_position_embeddings: int = 0    # the model's context length (yarn correction range; see loader.parse_rope)
     low_freq_factor: float = 1.0        # llama3
     high_freq_factor: float = 4.0
     original_max_position_embeddings: int = 8192
@@ -20,6 +20,17 @@ class RopeSpec:
     beta_slow: float = 1.0
 
     TYPE_ID = {"default": 1, "linear": 2, "yarn": 4, "llama3": 5}
+
+    def config_fields(self):
+        """Field values of b200_rope_config (include/b200_turbomind.h) in declaration order, without exact_math --
+        the counterpart of copy_rope_config (lmdeploy/turbomind/models/utils.py:170-187)."""
+        if self.type not in self.TYPE_ID:
+            raise NotImplementedError(f"rope type {self.type!r} (supported: {sorted(self.TYPE_ID)})")
+        return dict(type=self.TYPE_ID[self.type], dim=self.dim, base=self.base, factor=self.factor,
+                    max_position_embeddings=self.max_position_embeddings,
+                    llama3_low_freq_factor=self.low_freq_factor, llama3_high_freq_factor=self.high_freq_factor,
+                    llama3_original_max_position_embeddings=self.original_max_position_embeddings,
+                    yarn_attention_factor=self.attention_factor, yarn_beta_fast=self.beta_fast, yarn_beta_slow=self.beta_slow)
 
 
 @dataclass(frozen=True)

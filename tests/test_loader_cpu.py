@@ -1,6 +1,7 @@
 """Loader transforms (HF checkpoint -> TurboMind pre-prepare layout) checked end to end on CPU:
 an HF-semantics reference forward (separate q/k/v, half-split RoPE, gate/up, plain attention) on the ORIGINAL
 checkpoint tensors must agree with the oracle's TurboMind-semantics decode step on the CONVERTED tensors."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -292,42 +293,27 @@ def test_lazy_checkpoint_reads_sharded_and_indexed_directories(tmp_path):
 
 
 def test_rope_scaling_is_parsed_like_the_reference():
-    """parse_rope against hand-evaluated parse_rope_param outcomes (lmdeploy/turbomind/models/utils.py:76-166)."""
-    import math
-    base = {"max_position_embeddings": 131072, "rope_theta": 500000.0}
-    r = LD.parse_rope(dict(base), 128)
-    assert (r.type, r.dim, r.base, r.factor) == ("default", 128, 500000.0, 0.0)
-    # Llama-3.1
-    r = LD.parse_rope(dict(base, rope_scaling={"factor": 8.0, "low_freq_factor": 1.0, "high_freq_factor": 4.0,
-                                               "original_max_position_embeddings": 8192, "rope_type": "llama3"}), 128)
-    assert (r.type, r.factor, r.low_freq_factor, r.high_freq_factor, r.original_max_position_embeddings) == \
-        ("llama3", 8.0, 1.0, 4.0, 8192)
-    # linear, old-style key
-    r = LD.parse_rope(dict(base, rope_scaling={"type": "linear", "factor": 2.0}), 128)
-    assert (r.type, r.factor) == ("linear", 2.0)
-    # yarn with an original context: the factor is re-derived, the attention factor comes from mscale(factor given)
-    r = LD.parse_rope(dict(base, rope_scaling={"type": "yarn", "factor": 4.0, "original_max_position_embeddings": 32768}), 128)
-    assert r.type == "yarn" and r.factor == 131072 / 32768 and r.max_position_embeddings == 32768
-    assert math.isclose(r.attention_factor, 0.1 * math.log(4.0) + 1.0) and (r.beta_fast, r.beta_slow) == (32.0, 1.0)
-    # yarn with mscale / mscale_all_dim (DeepSeek style) and explicit betas
-    r = LD.parse_rope(dict(base, rope_scaling={"rope_type": "yarn", "factor": 40.0, "mscale": 1.0, "mscale_all_dim": 0.707,
-                                               "beta_fast": 16, "beta_slow": 2}), 64)
-    want = (0.1 * 1.0 * math.log(40.0) + 1.0) / (0.1 * 0.707 * math.log(40.0) + 1.0)
-    assert math.isclose(r.attention_factor, want) and r.max_position_embeddings == 131072 and r.factor == 40.0
-    assert (r.beta_fast, r.beta_slow, r.dim) == (16.0, 2.0, 64)
-    # explicit attention_factor wins
-    r = LD.parse_rope(dict(base, rope_scaling={"rope_type": "yarn", "factor": 2.0, "attention_factor": 1.25}), 128)
-    assert r.attention_factor == 1.25
-    # partial rotary + transformers >= 5 rope_parameters
-    r = LD.parse_rope({"max_position_embeddings": 4096, "partial_rotary_factor": 0.5}, 128)
-    assert r.dim == 64
-    r = LD.parse_rope({"max_position_embeddings": 4096,
-                       "rope_parameters": {"rope_theta": 1e6, "rope_type": "linear", "factor": 4.0,
-                                           "partial_rotary_factor": 0.25}}, 128)
-    assert (r.type, r.base, r.factor, r.dim) == ("linear", 1e6, 4.0, 32)
-    for bad in ({"rope_type": "dynamic", "factor": 2.0}, {"rope_type": "longrope"}, {"type": "mrope", "mrope_section": [16, 24, 24]}):
-        with pytest.raises(NotImplementedError):
-            LD.parse_rope(dict(base, rope_scaling=bad), 128)
+    """parse_rope -> RopeSpec -> b200_rope_config against what the reference's OWN parse_rope_param + copy_rope_config
+    write into its C++ RopeConfig for the same HF configs (tests/golden/ref_rope_configs.json, recorded by
+    tools/make_rope_golden.py executing lmdeploy/turbomind/models/utils.py:76-187).  Includes the reference's yarn
+    behaviour: the correction range uses the config's max_position_embeddings, `original_max_position_embeddings` only
+    re-derives the factor (Qwen2.5-style configs end up with factor 1.0)."""
+    import json
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_rope_configs.json")))
+    assert len(golden) >= 14
+    checked = 0
+    for name, g in golden.items():
+        if "raises" in g or g["rope_config"]["type"] == 3:        # unknown types / dynamic NTK: refused here, loudly
+            with pytest.raises(NotImplementedError):
+                LD.parse_rope(g["config"], g["head_dim"]).config_fields()
+            continue
+        got = LD.parse_rope(g["config"], g["head_dim"]).config_fields()
+        for field, want in g["rope_config"].items():           # every field the reference assigns for this rope type
+            assert got[field] == pytest.approx(want, rel=1e-12), (name, field, got[field], want)
+            checked += 1
+    assert checked >= 70
+    with pytest.raises(NotImplementedError):                      # multimodal rope is outside the hot-path scope
+        LD.parse_rope({"max_position_embeddings": 4096, "rope_scaling": {"type": "mrope", "mrope_section": [16, 24, 24]}}, 128)
 
 
 def test_partial_rotary_reorders_only_the_rotated_dims():
