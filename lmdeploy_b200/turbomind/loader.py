@@ -130,6 +130,17 @@ def spec_from_config(cfg):
                      max_position_embeddings=int(cfg.get("max_position_embeddings", 0)))
 
 
+def kv_heads_for_tp(kv_heads, tp):
+    """KV head count after the replication that makes it divisible by the TP size (the reference's loader repeats each
+    KV head, lmdeploy/turbomind/builders/attention.py:30-50 `_repeat_kv_heads`: 4 KV heads on 8 GPUs become 8)."""
+    if kv_heads % tp == 0:
+        return kv_heads
+    target = (kv_heads + tp - 1) // tp * tp
+    if target % kv_heads:
+        raise NotImplementedError(f"{kv_heads} KV heads cannot be replicated evenly over tp={tp}")
+    return target
+
+
 def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
     """-> dict(w_qkv, wo, w1w3, w2 : _Lin ; attention_norm, ffn_norm : tensor) for TP rank `rank`."""
     D, Hq, Hkv = spec.head_dim, spec.heads, spec.kv_heads
@@ -164,7 +175,11 @@ def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
     rope_dim = spec.rope.dim if spec.rope is not None else D        # partial rotary: only the rotated dims are reordered
     q = q.cols(rope_perm(Hq, D, rope_dim))
     k = k.cols(rope_perm(Hkv, D, rope_dim))
-    hq, hkv, it = Hq // tp, Hkv // tp, spec.inter // tp
+    rep = kv_heads_for_tp(Hkv, tp) // Hkv
+    if rep > 1:     # every KV head `rep` times in a row: q head j keeps reading (a copy of) kv head j // (Hq / Hkv)
+        idx = torch.arange(Hkv * D).view(Hkv, D).repeat_interleave(rep, 0).reshape(-1)
+        k, v = k.cols(idx), v.cols(idx)
+    hq, hkv, it = Hq // tp, Hkv * rep // tp, spec.inter // tp
     qs = q.cols(torch.arange(rank * hq * D, (rank + 1) * hq * D))
     ks = k.cols(torch.arange(rank * hkv * D, (rank + 1) * hkv * D))
     vs = v.cols(torch.arange(rank * hkv * D, (rank + 1) * hkv * D))
@@ -260,8 +275,10 @@ def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1
     from .runtime import DecodeModel, _TORCH_T
     cfg, tensors = read_checkpoint(path)
     spec = spec_from_config(cfg)
-    model = DecodeModel(spec, quant_policy=quant_policy, block_len=block_len, max_batch=max_batch, tp_size=tp,
-                        tp_rank=rank)
+    import dataclasses
+    # the device model sees the replicated KV head count; convert_layer replicates from the checkpoint's own
+    model = DecodeModel(dataclasses.replace(spec, kv_heads=kv_heads_for_tp(spec.kv_heads, tp)), quant_policy=quant_policy,
+                        block_len=block_len, max_batch=max_batch, tp_size=tp, tp_rank=rank)
     dev, T = model.device, _TORCH_T[spec.dtype]
     glob = convert_globals(spec, tensors, tp, rank)
     cache = {}

@@ -186,7 +186,7 @@ def to_tiny(spec, cfg_tensors, tp=1, rank=0):
     """loader output -> oracle TinyWeights (TurboMind layout)."""
     t = cfg_tensors
     w = TinyWeights.__new__(TinyWeights)
-    w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab = H, L, HQ // tp, HKV // tp, I // tp, V
+    w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab = H, L, HQ // tp, LD.kv_heads_for_tp(HKV, tp) // tp, I // tp, V
     T = BF16 if spec.dtype == "bf16" else F16
     w.fmt, w.dtype, w.D = spec.weight_format, T, D
     glob = LD.convert_globals(spec, t, tp, rank)
@@ -219,7 +219,7 @@ def to_tiny(spec, cfg_tensors, tp=1, rank=0):
 
 @pytest.mark.parametrize("arch", ["internlm2", "llama", "qwen2"])
 @pytest.mark.parametrize("family", FAMILIES)
-@pytest.mark.parametrize("tp", [1, 2])
+@pytest.mark.parametrize("tp", [1, 2, 4])        # 4 > the 2 KV heads: each is replicated (builders/attention.py:30-50)
 def test_loader_transforms_preserve_model_semantics(arch, family, tp):
     cfg, t, deq = make_checkpoint(arch, family, seed=1)
     spec = LD.spec_from_config(cfg)
@@ -234,7 +234,7 @@ def test_loader_transforms_preserve_model_semantics(arch, family, tp):
     shards = [to_tiny(spec, t, tp, r) for r in range(tp)]
     full = shards[0] if tp == 1 else to_tiny(spec, t, 1, 0)
     rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=D, base=10000.0)
-    caches = [OA.PagedKvCache(2, L, OA.KvLayout(HKV // tp, 64, D, 16), T) for _ in range(tp)]
+    caches = [OA.PagedKvCache(2, L, OA.KvLayout(LD.kv_heads_for_tp(HKV, tp) // tp, 64, D, 16), T) for _ in range(tp)]
     for pos, tok in enumerate(tokens):
         logits, _ = decode_step(full, np.array([tok]), caches[0], [[0]], np.array([pos], np.int32), rope,
                                 tp_shards=shards if tp > 1 else None, caches=caches if tp > 1 else None)
@@ -333,3 +333,20 @@ def test_architecture_admission():
                 dict(architectures=["LlamaForCausalLM"], mlp_bias=True)):
         with pytest.raises(NotImplementedError):
             LD.spec_from_config(dict(base, **bad))
+
+
+def test_kv_heads_are_replicated_to_a_tp_multiple():
+    assert [LD.kv_heads_for_tp(8, tp) for tp in (1, 2, 4, 8)] == [8, 8, 8, 8]
+    assert LD.kv_heads_for_tp(4, 8) == 8 and LD.kv_heads_for_tp(2, 8) == 8 and LD.kv_heads_for_tp(1, 4) == 4
+    with pytest.raises(NotImplementedError):
+        LD.kv_heads_for_tp(3, 2)                 # 4 is not a multiple of 3: the reference asserts here too
+    # the replicated layout: rank r of tp=4 over 2 KV heads reads KV head r // 2 -- the one its q head belongs to
+    cfg, t, _ = make_checkpoint("llama", None, seed=3)
+    spec = LD.spec_from_config(cfg)
+    full = LD.convert_layer(spec, t, 0, 1, 0)["w_qkv"].w
+    for r in range(4):
+        shard = LD.convert_layer(spec, t, 0, 4, r)["w_qkv"].w
+        assert tuple(shard.shape) == (H, 3 * D)
+        assert torch.equal(shard[:, :D], full[:, r * D:(r + 1) * D])                                    # q head r
+        assert torch.equal(shard[:, D:2 * D], full[:, (HQ + r // 2) * D:(HQ + r // 2 + 1) * D])          # its K head
+        assert torch.equal(shard[:, 2 * D:], full[:, (HQ + HKV + r // 2) * D:(HQ + HKV + r // 2 + 1) * D])
