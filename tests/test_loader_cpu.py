@@ -350,3 +350,52 @@ def test_kv_heads_are_replicated_to_a_tp_multiple():
         assert torch.equal(shard[:, :D], full[:, r * D:(r + 1) * D])                                    # q head r
         assert torch.equal(shard[:, D:2 * D], full[:, (HQ + r // 2) * D:(HQ + r // 2 + 1) * D])          # its K head
         assert torch.equal(shard[:, 2 * D:], full[:, (HQ + HKV + r // 2) * D:(HQ + HKV + r // 2 + 1) * D])
+
+
+def test_column_layouts_match_the_reference_loader_functions():
+    """w_qkv / w1w3 column order per TP rank against the reference's OWN tensor functions (_split_qkv_gqa,
+    _reorder_rotary_emb, _repeat_kv_heads, fuse_qkv, _interleave_w1w3) executed on index tensors by
+    tools/make_layout_golden.py -> tests/golden/ref_loader_layouts.json.  Here convert_layer runs on checkpoints whose
+    weights ARE the source column ids."""
+    import json
+    golden = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_loader_layouts.json")))
+    hidden, inter = 128, 512
+    checked = 0
+
+    def checkpoint(arch, Hq, Hkv, Dh):
+        ids = lambda lo, n: (lo + torch.arange(n, dtype=torch.float32))[:, None].repeat(1, hidden)      # [out, in]
+        o = torch.zeros(hidden, Hq * Dh)
+        gate, up, down = ids(0, inter), ids(inter, inter), torch.zeros(hidden, inter)
+        ones = torch.ones(hidden)
+        p = "model.layers.0."
+        if arch == "internlm2":
+            return {p + "attention.wqkv.weight": ids(0, (Hq + 2 * Hkv) * Dh), p + "attention.wo.weight": o,
+                    p + "feed_forward.w1.weight": gate, p + "feed_forward.w3.weight": up, p + "feed_forward.w2.weight": down,
+                    p + "attention_norm.weight": ones, p + "ffn_norm.weight": ones}
+        return {p + "self_attn.q_proj.weight": ids(0, Hq * Dh), p + "self_attn.k_proj.weight": ids(Hq * Dh, Hkv * Dh),
+                p + "self_attn.v_proj.weight": ids((Hq + Hkv) * Dh, Hkv * Dh), p + "self_attn.o_proj.weight": o,
+                p + "mlp.gate_proj.weight": gate, p + "mlp.up_proj.weight": up, p + "mlp.down_proj.weight": down,
+                p + "input_layernorm.weight": ones, p + "post_attention_layernorm.weight": ones}
+
+    def spec_for(arch, Hq, Hkv, Dh, rope_dim):
+        return LD.spec_from_config({"architectures": ["InternLM2ForCausalLM" if arch == "internlm2" else "LlamaForCausalLM"],
+                                    "hidden_size": hidden, "num_hidden_layers": 1, "num_attention_heads": Hq,
+                                    "num_key_value_heads": Hkv, "head_dim": Dh, "intermediate_size": inter, "vocab_size": 128,
+                                    "partial_rotary_factor": rope_dim / Dh, "torch_dtype": "float32"})
+
+    for g in golden["qkv"]:
+        spec = spec_for(g["arch"], g["heads"], g["kv_heads"], g["head_dim"], g["rope_dim"])
+        t = checkpoint(g["arch"], g["heads"], g["kv_heads"], g["head_dim"])
+        for r, want in enumerate(g["ranks"]):
+            w = LD.convert_layer(spec, t, 0, g["tp"], r)["w_qkv"].w
+            assert (w == w[0]).all()
+            assert w[0].to(torch.int64).tolist() == want, (g["arch"], g["heads"], g["kv_heads"], g["rope_dim"], g["tp"], r)
+            checked += 1
+    for g in golden["ffn"]:
+        spec, t = spec_for("llama", 4, 2, 128, 128), checkpoint("llama", 4, 2, 128)
+        for r, want in enumerate(g["ranks"]):
+            assert g["inter"] == inter
+            w = LD.convert_layer(spec, t, 0, g["tp"], r)["w1w3"].w
+            assert w[0].to(torch.int64).tolist() == want, ("ffn", g["tp"], r)
+            checked += 1
+    assert checked >= 30
