@@ -13,6 +13,11 @@ class QuantPolicy(enum.IntEnum):
     INT8 = 8
 
 
+# max_batch_size left unset: the reference asks get_max_batch_size('cuda') (lmdeploy/utils.py:394-417), whose table has no
+# entry for a B200 and answers 128 (tests/golden/ref_engine_defaults.json) -- also the row limit of the decode step
+DEFAULT_MAX_BATCH_SIZE = 128
+
+
 class ResponseType(enum.Enum):
     """Same members as the reference (lmdeploy/messages.py ResponseType)."""
     SUCCESS = enum.auto()

@@ -10,7 +10,7 @@ from typing import List, Optional
 
 import torch
 
-from ..messages import EngineOutput, GenerationConfig, ResponseType, TurbomindEngineConfig
+from ..messages import DEFAULT_MAX_BATCH_SIZE, EngineOutput, GenerationConfig, ResponseType, TurbomindEngineConfig
 from .runtime import DecodeModel, KvCachePool
 from .scheduler import InputLengthError, Scheduler, Sequence
 from .specs import SPECS, ModelSpec
@@ -54,9 +54,10 @@ class TurboMind:
         self.config = cfg
         self.spec = spec
         self.eos_id = eos_id
-        self.max_batch = cfg.max_batch_size or 64
-        # the reference defaults session_len to the model's context length (turbomind.py: session_len from the HF config)
-        self.session_len = cfg.session_len or spec.max_position_embeddings or 4096
+        self.max_batch = cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE
+        # session_len left unset: what _get_and_verify_max_len derives from the HF config (converter.py get_tm_config step 4;
+        # loader.default_session_len), 2048 when the config names no context length
+        self.session_len = cfg.session_len or spec.session_len or spec.max_position_embeddings or 2048
         self.block_len = cfg.cache_block_seq_len
         self.model = model or DecodeModel(spec, quant_policy=cfg.quant_policy, block_len=self.block_len,
                                           max_batch=self.max_batch)
@@ -110,7 +111,7 @@ class TurboMind:
             cfg = engine_config or TurbomindEngineConfig()
             spec, model, eos = load_hf_checkpoint(pretrained_model_name_or_path, quant_policy=cfg.quant_policy,
                                                   block_len=cfg.cache_block_seq_len,
-                                                  max_batch=cfg.max_batch_size or 64)
+                                                  max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE)
             return cls(spec, cfg, model=model, eos_id=eos, **kw)
         raise FileNotFoundError(pretrained_model_name_or_path)
 

@@ -96,6 +96,20 @@ def parse_rope(cfg, head_dim):
     return RopeSpec(**kw)
 
 
+_CONTEXT_LENGTH_KEYS = ("max_position_embeddings", "n_positions", "max_seq_len", "seq_length", "model_max_length",
+                        "max_sequence_length", "max_seq_length", "seq_len")
+
+
+def default_session_len(cfg):
+    """Session length when the user sets none: the minimum over the context-length keys the config carries (looked up
+    in the language-model sub-config when there is one), 2048 when it carries none -- lmdeploy/utils.py:321-391
+    `_get_and_verify_max_len(hf_config, None)`, pinned by tests/golden/ref_engine_defaults.json."""
+    for key in ("language_config", "llm_config", "text_config"):
+        cfg = cfg.get(key, cfg)
+    found = [cfg[k] for k in _CONTEXT_LENGTH_KEYS if cfg.get(k) is not None]
+    return int(min(found)) if found else 2048
+
+
 def spec_from_config(cfg):
     arch = cfg["architectures"][0]
     name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2",
@@ -127,7 +141,8 @@ def spec_from_config(cfg):
                      norm_eps=float(cfg.get("rms_norm_eps", 1e-5)), rope_type=rope.type, rope_factor=rope.factor, rope=rope,
                      weight_format=fmt,
                      checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias,
-                     max_position_embeddings=int(cfg.get("max_position_embeddings", 0)))
+                     max_position_embeddings=int(cfg.get("max_position_embeddings", 0)),
+                     session_len=default_session_len(cfg))
 
 
 def kv_heads_for_tp(kv_heads, tp):

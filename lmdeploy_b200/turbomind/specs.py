@@ -53,7 +53,8 @@ class ModelSpec:
     checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
     qkv_bias: bool = False          # q/k/v projections carry a bias (Qwen2 family), applied by the attention prologue
     rope: RopeSpec = None           # full RoPE description (checkpoints); None = rope_type / rope_theta / rope_factor above
-    max_position_embeddings: int = 0   # the checkpoint's context length (0 = unknown): default session_len of the engine
+    max_position_embeddings: int = 0   # config.max_position_embeddings (0 = unknown); feeds the RoPE config
+    session_len: int = 0               # default session length the reference derives from the config (0 = unknown)
 
     def tiny(self, layers=2):
         return replace(self, layers=layers)

@@ -53,7 +53,7 @@ def launch(spec_or_path, engine_config=None, *, seed=0):
 
     import torch
 
-    from ..messages import TurbomindEngineConfig
+    from ..messages import DEFAULT_MAX_BATCH_SIZE, TurbomindEngineConfig
     from .engine import TurboMind
     from .runtime import DecodeModel
     from .specs import SPECS
@@ -71,11 +71,11 @@ def launch(spec_or_path, engine_config=None, *, seed=0):
     if isinstance(spec_or_path, str) and spec_or_path not in SPECS:
         from .loader import load_hf_checkpoint
         spec, model, eos = load_hf_checkpoint(spec_or_path, quant_policy=cfg.quant_policy, block_len=cfg.cache_block_seq_len,
-                                              max_batch=cfg.max_batch_size or 64, tp=world, rank=rank)
+                                              max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE, tp=world, rank=rank)
     else:
         spec = SPECS[spec_or_path] if isinstance(spec_or_path, str) else spec_or_path
         model = DecodeModel(spec, quant_policy=cfg.quant_policy, block_len=cfg.cache_block_seq_len,
-                            max_batch=cfg.max_batch_size or 64, tp_size=world, tp_rank=rank)
+                            max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE, tp_size=world, tp_rank=rank)
         model.load_synthetic(seed)
     tp = TpGroup(model, rank, world)
     channel = StepChannel(rank, world, control)

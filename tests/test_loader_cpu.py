@@ -399,3 +399,19 @@ def test_column_layouts_match_the_reference_loader_functions():
             assert w[0].to(torch.int64).tolist() == want, ("ffn", g["tp"], r)
             checked += 1
     assert checked >= 30
+
+
+def test_engine_defaults_follow_the_reference():
+    """session_len / max_batch_size when the user leaves them unset: tests/golden/ref_engine_defaults.json holds what the
+    reference's own _get_and_verify_max_len and get_max_batch_size return (tools/make_engine_defaults_golden.py)."""
+    import json
+    from lmdeploy_b200.messages import DEFAULT_MAX_BATCH_SIZE
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_engine_defaults.json")))
+    assert len(g["session_len"]) >= 7
+    for name, case in g["session_len"].items():
+        assert LD.default_session_len(case["config"]) == case["value"], name
+    assert DEFAULT_MAX_BATCH_SIZE == g["max_batch_size"]["NVIDIA B200"]
+    cfg, _, _ = make_checkpoint("llama", None, seed=0)
+    cfg = dict(cfg, max_position_embeddings=131072, model_max_length=8192)
+    spec = LD.spec_from_config(cfg)
+    assert spec.session_len == 8192 and spec.max_position_embeddings == 131072       # RoPE still sees the config's own value
