@@ -92,7 +92,7 @@ class GenerationConfig:
                 needle = "\u2581" if word == " " else word
                 ids = [i for tok, i in tokenizer.get_vocab().items() if needle in tok]
                 if len(ids) > 5:
-                    ids = [i for i in sorted(ids) if tokenizer.decode([i]) == word][:5]
+                    ids = [i for i in sorted(ids) if tokenizer.decode([i]) == needle][:5]   # (the marker, as the reference)
                 if not ids:
                     ids = tokenizer.encode(word, add_special_tokens=False)
                     ids = ids if len(ids) == 1 else []

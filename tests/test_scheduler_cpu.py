@@ -399,51 +399,30 @@ def test_marshal_step_describes_the_batch_the_way_the_c_abi_reads_it():
     assert seen_multi
 
 
-class _FakeTokenizer:
-    """The three methods convert_stop_bad_words_to_ids uses, over a toy sentencepiece-style vocabulary."""
-    VOCAB = {"<s>": 0, "</s>": 1, "▁Hello": 2, "▁": 3, "!": 4, "!!": 5, "▁wor": 6, "ld": 7, "\n": 8, "\n\n": 9,
-             "a!": 10, "b!": 11, "c!": 12, "d!": 13}
-
-    def get_vocab(self):
-        return dict(self.VOCAB)
-
-    def encode(self, text, add_special_tokens=True):
-        inv = sorted(self.VOCAB, key=len, reverse=True)
-        text = text.replace(" ", "▁")
-        out = []
-        while text:
-            for tok in inv:
-                if text.startswith(tok):
-                    out.append(self.VOCAB[tok])
-                    text = text[len(tok):]
-                    break
-            else:
-                raise ValueError(text)
-        return out
-
-    def decode(self, ids):
-        inv = {i: t for t, i in self.VOCAB.items()}
-        return "".join(inv[i] for i in ids).replace("▁", " ")
+from fake_tokenizer import FakeTokenizer as _FakeTokenizer  # noqa: E402
 
 
 def test_stop_words_become_stop_token_ids_with_the_reference_rule():
+    """Against tests/golden/ref_stop_words.json: the reference's OWN GenerationConfig.convert_stop_bad_words_to_ids /
+    update_from_hf_gen_cfg and Tokenizer.indexes_containing_token, executed by tools/make_stopwords_golden.py over the
+    toy vocabulary of tests/fake_tokenizer.py (substring matches, the ' ' -> sentencepiece marker rule, narrowing of
+    more than five candidates, multi-token phrases dropped, ids beyond the vocabulary)."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_stop_words.json")))
+    assert g["vocab"] == _FakeTokenizer.VOCAB
     tok = _FakeTokenizer()
-    g = GenerationConfig(stop_words=["\n", "ld", " Hello wor"], stop_token_ids=[1])
-    g.convert_stop_bad_words_to_ids(tok)
-    # "\n" is contained in tokens 8 and 9; "ld" in 7; the two-token phrase is ignored; the explicit id is kept
-    assert g.stop_token_ids == [1, 7, 8, 9]
-    # more than five vocabulary entries contain "!": narrowed to the ids that decode to exactly "!"
-    g = GenerationConfig(stop_words=["!"])
-    g.convert_stop_bad_words_to_ids(tok)
-    assert g.stop_token_ids == [4]
-    g = GenerationConfig(stop_words=[" "])
-    g.convert_stop_bad_words_to_ids(tok)
-    assert set(g.stop_token_ids) == {2, 3, 6}
-    with pytest.raises(NotImplementedError):
+    assert len(g["stop_words"]) >= 8
+    for case in g["stop_words"]:
+        cfg = GenerationConfig(stop_words=case.get("stop_words"), stop_token_ids=case.get("stop_token_ids"))
+        cfg.convert_stop_bad_words_to_ids(tok)
+        assert cfg.stop_token_ids == case["result"], case
+    for case in g["eos"]:
+        cfg = GenerationConfig(stop_token_ids=case["stop_token_ids"])
+        cfg.update_from_hf_gen_cfg(case["generation_config"], case["tokenizer_eos"])
+        assert cfg.stop_token_ids == case["result"], case
+    with pytest.raises(NotImplementedError):                  # the one deliberate refusal: bad words need a logits processor
         GenerationConfig(bad_words=["x"]).convert_stop_bad_words_to_ids(tok)
-    g = GenerationConfig(stop_token_ids=[5])
-    g.update_from_hf_gen_cfg({"eos_token_id": [1, 9]}, tokenizer_eos_token_id=1)
-    assert g.stop_token_ids == [1, 5, 9]
 
 
 def test_pipeline_prompt_forms_without_a_device():
