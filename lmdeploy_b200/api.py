@@ -48,11 +48,29 @@ class Pipeline:
             out.append(g)
         return single, ids, out
 
-    def _response(self, i, s, token_ids):
+    # ---- responses: what the reference's AsyncEngine.generate makes of the engine's output
+    # (lmdeploy/serve/core/async_engine.py:656-790): the stop token that ended a sequence is NOT part of the response
+    # (token_ids, text, generate_token_len) unless include_stop_str_in_output, in which case the closing chunk carries it;
+    # a stream is content chunks with finish_reason None followed by ONE closing chunk with the finish_reason.
+    def _decode(self, ids, g, special=None):
+        if self.tokenizer is None or not ids:
+            return ""
+        skip = (g.skip_special_tokens if g is not None else True) if special is None else special
+        return self.tokenizer.decode(list(ids), skip_special_tokens=skip)
+
+    @staticmethod
+    def _hidden_stop(s):
+        """1 if the sequence ended on a stop token (it is then the last generated id), else 0."""
+        return 1 if s.finished and s.finish_reason == "stop" and s.generated else 0
+
+    def _closing(self, i, s, g, shown):
+        """The closing Response of a prompt: finish_reason, and the stop token when the user asked to see it."""
         reason = {"cancel": "abort"}.get(s.finish_reason, s.finish_reason)          # the reference's vocabulary
-        text = self.tokenizer.decode(token_ids) if self.tokenizer is not None and token_ids else ""
-        return Response(text=text, generate_token_len=len(s.generated), input_token_len=len(s.prompt),
-                        finish_reason=reason if s.finished else None, token_ids=list(token_ids), index=i,
+        ids = []
+        if self._hidden_stop(s) and g is not None and g.include_stop_str_in_output:
+            ids = s.generated[-1:]
+        return Response(text=self._decode(ids, g, special=False), generate_token_len=shown + len(ids),
+                        input_token_len=len(s.prompt), finish_reason=reason, token_ids=list(ids), index=i,
                         cached_tokens=s.reused_tokens, error_code="input_length" if s.error else None,
                         error_message=s.error)
 
@@ -65,7 +83,13 @@ class Pipeline:
             raise NotImplementedError("LoRA adapters are outside the hot-path scope")
         single, ids, cfgs = self._prepare(prompts, gen_config)
         seqs = batched_generate(self.engine, ids, cfgs)
-        out = [self._response(i, s, s.generated) for i, s in enumerate(seqs)]
+        out = []
+        for i, (s, g) in enumerate(zip(seqs, cfgs)):
+            shown = s.generated[:len(s.generated) - self._hidden_stop(s)]
+            r = self._closing(i, s, g, len(shown))
+            r.token_ids = list(shown) + r.token_ids
+            r.text = self._decode(shown, g) + r.text
+            out.append(r)
         return out[0] if single else out
 
     __call__ = infer
@@ -75,21 +99,35 @@ class Pipeline:
 
     def stream_infer(self, prompts, sessions=None, gen_config=None, do_preprocess: bool = True,
                      adapter_name: Optional[str] = None, stream_response: bool = True, **kw):
-        """Generator of Response objects (lmdeploy/pipeline.py:145-178): with stream_response every yield carries the tokens
-        a prompt produced since its previous yield (`index` tells which prompt; finish_reason is set on its last one);
-        without it one final Response per prompt."""
+        """Generator of Response objects (lmdeploy/pipeline.py:145-178), `index` tells which prompt.  Content chunks
+        (finish_reason None) carry the tokens and the text a prompt produced since its previous chunk -- every step with
+        stream_response, once at the end without it -- and one closing chunk per prompt carries the finish_reason."""
         if adapter_name is not None or sessions is not None:
             raise NotImplementedError("sessions / adapters are outside the hot-path scope")
         _, ids, cfgs = self._prepare(prompts, gen_config)
-        acc = {}
+        shown, text, held = {}, {}, {}
         for i, s, new in stream_generate(self.engine, ids, cfgs):
-            if stream_response:
-                if new or s.finished:
-                    yield self._response(i, s, new)
-            else:
-                acc.setdefault(i, []).extend(new)
-                if s.finished:
-                    yield self._response(i, s, acc[i])
+            g = cfgs[i]
+            if s.finished and self._hidden_stop(s):
+                new = new[:-1]
+            held.setdefault(i, []).extend(new)
+            shown[i] = shown.get(i, 0) + len(new)
+            if held[i] and (stream_response or s.finished):
+                # text delta of the whole visible sequence, so characters that span tokens come out whole; a trailing
+                # replacement character means an unfinished byte sequence: hold the text back until it completes
+                vis = s.generated[:shown[i]]
+                full = self._decode(vis, g)
+                prev = text.get(i, "")
+                delta = full[len(prev):] if full.startswith(prev) else full
+                if delta.endswith("\ufffd") and not s.finished:
+                    delta = ""
+                else:
+                    text[i] = full
+                yield Response(text=delta, generate_token_len=shown[i], input_token_len=len(s.prompt), finish_reason=None,
+                               token_ids=list(held[i]), index=i, cached_tokens=s.reused_tokens)
+                held[i] = []
+            if s.finished:
+                yield self._closing(i, s, g, shown.get(i, 0))
 
     def get_ppl(self, input_ids):
         raise NotImplementedError("get_ppl needs per-position logits of the prompt (return_ppl path); the decode hot path "

@@ -228,14 +228,17 @@ class TurboMindInstance:
         except KeyError:
             yield EngineOutput(ResponseType.SESSION_REPEAT, [], 0)
             return
+        # EngineOutput.token_ids = "the newly generated token ids in each iteration" (lmdeploy/messages.py:721-743,
+        # turbomind.py async_stream_infer: output_ids_buf[prev_len:seq_len]); a stop token is part of them.  num_token is
+        # the running total.
         sent = 0
         while not seq.finished:
             self.engine.step()
-            if len(seq.generated) > sent:
-                sent = len(seq.generated)
-                yield EngineOutput(ResponseType.SUCCESS, list(seq.generated), sent)
+            if len(seq.generated) > sent and not seq.finished:
+                new, sent = seq.generated[sent:], len(seq.generated)
+                yield EngineOutput(ResponseType.SUCCESS, list(new), sent)
         yield EngineOutput(ResponseType.FINISH if seq.finish_reason != "cancel" else ResponseType.CANCEL,
-                           list(seq.generated), len(seq.generated))
+                           list(seq.generated[sent:]), len(seq.generated))
 
     async def async_stream_infer(self, session_id, input_ids, gen_config: GenerationConfig = None, **kw):
         for out in self.stream_infer(session_id, input_ids, gen_config):

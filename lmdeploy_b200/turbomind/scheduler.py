@@ -291,7 +291,10 @@ class Scheduler:
                 events.append((s, None))
                 continue
             s.generated.append(int(tok))
-            stop = (not s.ignore_eos and s.eos_id is not None and tok == s.eos_id) or (tok in s.stop_token_ids)
+            # ignore_eos switches off EVERY stop id, user stop words included: the reference only hands stop_ids to its
+            # engine when ignore_eos is off (lmdeploy/turbomind/turbomind.py `_get_generation_config`); the stop token
+            # itself is appended to the sequence, the pipeline layer hides it from the response
+            stop = not s.ignore_eos and ((s.eos_id is not None and tok == s.eos_id) or tok in s.stop_token_ids)
             if stop:
                 s.finished, s.finish_reason = True, "stop"
             elif len(s.generated) >= s.max_new_tokens or s.cached + 1 > self.session_len:

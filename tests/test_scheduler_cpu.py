@@ -606,13 +606,31 @@ def test_pipeline_infer_and_stream_infer_agree():
         mine = [c for c in chunks if c.index == i]
         assert sum((c.token_ids for c in mine), []) == full[i].token_ids
         assert [c.finish_reason for c in mine][:-1] == [None] * (len(mine) - 1) and mine[-1].finish_reason == "length"
-    # non-streaming mode of stream_infer: one Response per prompt
+        assert all(c.token_ids for c in mine[:-1]) and mine[-1].token_ids == [] and mine[-1].text == ""      # closing chunk
+        assert [c.generate_token_len for c in mine[:-1]] == list(range(1, len(mine))) and \
+            mine[-1].generate_token_len == full[i].generate_token_len
+    # non-streaming mode of stream_infer: one content chunk with everything + the closing chunk, per prompt
     finals = list(_fake_pipeline().stream_infer(prompts, gen_config=cfgs, stream_response=False))
-    assert sorted((r.index, tuple(r.token_ids)) for r in finals) == [(i, tuple(full[i].token_ids)) for i in range(3)]
+    assert sorted((r.index, tuple(r.token_ids), r.finish_reason) for r in finals if r.finish_reason is None) == \
+        [(i, tuple(full[i].token_ids), None) for i in range(3)]
+    assert sorted((r.index, r.finish_reason) for r in finals if r.finish_reason) == [(i, "length") for i in range(3)]
     # per-prompt stop tokens; a cancelled request reports 'abort'
     stop = full[1].token_ids[3]
+    # the stop token ends the sequence and stays out of the response (async_engine.py:717-720), unless asked for
+    cut = full[1].token_ids.index(stop)
     r = _fake_pipeline().infer([prompts[1]], [GenerationConfig(max_new_tokens=9, stop_token_ids=[stop])])[0]
-    assert r.finish_reason == "stop" and r.token_ids == full[1].token_ids[:full[1].token_ids.index(stop) + 1]
+    assert r.finish_reason == "stop" and r.token_ids == full[1].token_ids[:cut] and r.generate_token_len == cut
+    r = _fake_pipeline().infer([prompts[1]], [GenerationConfig(max_new_tokens=9, stop_token_ids=[stop],
+                                                               include_stop_str_in_output=True)])[0]
+    assert r.finish_reason == "stop" and r.token_ids == full[1].token_ids[:cut + 1] and r.generate_token_len == cut + 1
+    ch = list(_fake_pipeline().stream_infer([prompts[1]], gen_config=[GenerationConfig(max_new_tokens=9, stop_token_ids=[stop])]))
+    assert sum((c.token_ids for c in ch), []) == full[1].token_ids[:cut] and ch[-1].finish_reason == "stop" and ch[-1].token_ids == []
+    ch = list(_fake_pipeline().stream_infer([prompts[1]], gen_config=[GenerationConfig(max_new_tokens=9, stop_token_ids=[stop],
+                                                                                    include_stop_str_in_output=True)]))
+    assert ch[-1].token_ids == [stop] and ch[-1].generate_token_len == cut + 1
+    # ignore_eos switches every stop id off (turbomind.py _get_generation_config hands stop_ids over only without it)
+    r = _fake_pipeline().infer([prompts[1]], [GenerationConfig(max_new_tokens=9, stop_token_ids=[stop], ignore_eos=True)])[0]
+    assert r.finish_reason == "length" and r.token_ids == full[1].token_ids
     with pytest.raises(ValueError):
         _fake_pipeline().infer(prompts, cfgs[:2])
     # prefix cache: the second identical request reports its reused tokens
@@ -650,3 +668,22 @@ def test_a_prompt_that_fills_the_session_is_rejected_alone():
     from lmdeploy_b200.turbomind.engine import TurboMindInstance
     outs = list(TurboMindInstance(p.engine).stream_infer(99, bad, GenerationConfig(max_new_tokens=3)))
     assert [o.status for o in outs] == [ResponseType.INPUT_LENGTH_ERROR]
+
+
+def test_streamed_text_and_engine_outputs_are_incremental():
+    from lmdeploy_b200.messages import ResponseType
+    from lmdeploy_b200.turbomind.engine import TurboMindInstance
+    prompt, cfg = [2, 7, 1], GenerationConfig(max_new_tokens=8, ignore_eos=True, skip_special_tokens=False)
+    p = _fake_pipeline()
+    p.tokenizer = _FakeTokenizer()
+    whole = p.infer([prompt], cfg)[0]
+    assert whole.text == p.tokenizer.decode(whole.token_ids) and len(whole.token_ids) == 8
+    p2 = _fake_pipeline()
+    p2.tokenizer = _FakeTokenizer()
+    chunks = list(p2.stream_infer([prompt], gen_config=cfg))
+    assert "".join(c.text for c in chunks) == whole.text and sum((c.token_ids for c in chunks), []) == whole.token_ids
+    # engine level: EngineOutput.token_ids are the NEW ids of the iteration (lmdeploy/messages.py:721-743), num_token the total
+    outs = list(TurboMindInstance(_fake_pipeline().engine).stream_infer(7, prompt, cfg))
+    assert [o.status for o in outs[:-1]] == [ResponseType.SUCCESS] * (len(outs) - 1) and outs[-1].status == ResponseType.FINISH
+    assert sum((o.token_ids for o in outs), []) == whole.token_ids
+    assert [o.num_token for o in outs] == sorted(o.num_token for o in outs) and outs[-1].num_token == 8
