@@ -1,5 +1,4 @@
 """pipeline(): the user entry point, same shape as lmdeploy.pipeline (lmdeploy/api.py:15-82, pipeline.py:33-95)."""
-from dataclasses import replace
 from typing import List, Optional, Union
 
 from .messages import GenerationConfig, Response, TurbomindEngineConfig
@@ -11,11 +10,19 @@ class Pipeline:
         self.backend_config = backend_config or TurbomindEngineConfig()
         self.engine = TurboMind.from_pretrained(model_path, self.backend_config, **kw)
         self.tokenizer = tokenizer
-        if tokenizer is None:
-            import os
-            if os.path.isdir(model_path) and os.path.exists(os.path.join(model_path, "tokenizer.json")):
+        self.hf_gen_cfg = {}
+        import os
+        if os.path.isdir(model_path):
+            if tokenizer is None and os.path.exists(os.path.join(model_path, "tokenizer.json")):
                 from transformers import AutoTokenizer
                 self.tokenizer = AutoTokenizer.from_pretrained(model_path)
+            # generation_config.json carries the chat models' real end-of-turn ids (Llama-3: [128001, 128009]); the
+            # reference merges them into every request's stop ids (AsyncEngine.hf_gen_cfg, async_engine.py:417-437)
+            gpath = os.path.join(model_path, "generation_config.json")
+            if os.path.exists(gpath):
+                import json
+                with open(gpath) as fh:
+                    self.hf_gen_cfg = json.load(fh)
 
     def _encode(self, prompt):
         """A prompt is a list of token ids, a string, or OpenAI-style messages [{"role": ..., "content": ...}, ...]
@@ -38,14 +45,12 @@ class Pipeline:
         plist = [prompts] if single else list(prompts)
         ids = [self._encode(p) for p in plist]
         cfgs = gen_config if isinstance(gen_config, (list, tuple)) else [gen_config] * len(ids)
-        out = []
-        for g in cfgs:
-            if g is not None and (g.stop_words or g.bad_words):
-                if self.tokenizer is None:
-                    raise ValueError("stop_words need a tokenizer: pass stop_token_ids instead")
-                g = replace(g)
-                g.convert_stop_bad_words_to_ids(self.tokenizer)
-            out.append(g)
+        if len(cfgs) != len(ids):
+            raise ValueError(f"{len(cfgs)} generation configs for {len(ids)} prompts")
+        session_len = getattr(self.engine, "session_len", None) or self.engine.scheduler.session_len
+        eos = getattr(self.tokenizer, "eos_token_id", None) if self.tokenizer is not None else self.engine.eos_id
+        out = [(g or GenerationConfig()).determined(len(p), session_len, self.tokenizer, getattr(self, "hf_gen_cfg", None), eos)
+               for g, p in zip(cfgs, ids)]
         return single, ids, out
 
     # ---- responses: what the reference's AsyncEngine.generate makes of the engine's output

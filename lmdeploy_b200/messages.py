@@ -18,6 +18,11 @@ class QuantPolicy(enum.IntEnum):
 DEFAULT_MAX_BATCH_SIZE = 128
 
 
+class ConfigError(ValueError, AssertionError):
+    """An invalid config value.  The reference validates with `assert` (lmdeploy/messages.py:195-205, 345-367), so code
+    written against it may catch AssertionError; code written against this package catches ValueError.  Both work."""
+
+
 class ResponseType(enum.Enum):
     """Same members as the reference (lmdeploy/messages.py ResponseType)."""
     SUCCESS = enum.auto()
@@ -72,9 +77,9 @@ class GenerationConfig:
 
     _UNSUPPORTED = {"response_format": None, "logits_processors": None, "output_last_hidden_state": None, "return_ppl": False,
                     "with_cache": False, "preserve_cache": False, "migration_request": None, "return_routed_experts": False,
-                    "repetition_ngram_size": 0, "repetition_ngram_threshold": 0, "logprobs": None, "output_logits": None,
-                    # these change the GREEDY token too (they act on the logits before the argmax), so they cannot be ignored
-                    "repetition_penalty": 1.0, "min_new_tokens": None}
+                    "logprobs": None, "output_logits": None,
+                    # acts on the logits before the argmax whatever do_sample says, so it cannot be ignored
+                    "min_new_tokens": None}
 
     def convert_stop_bad_words_to_ids(self, tokenizer):
         """stop_words -> stop_token_ids with the reference's rule (lmdeploy/messages.py:154-174 and
@@ -115,16 +120,51 @@ class GenerationConfig:
         self.stop_token_ids = sorted(ids)
 
     def __post_init__(self):
+        # the reference's own checks (lmdeploy/messages.py:195-205)
+        if type(self.n) is not int or self.n <= 0:
+            raise ConfigError("n is not a positive integer")
+        if not 0 <= self.top_p <= 1:
+            raise ConfigError("top_p must be in [0, 1]")
+        if self.top_k < 0:
+            raise ConfigError("top_k can not be a negative integer")
+        if not 0 <= self.temperature <= 2:
+            raise ConfigError("temperature must be in [0, 2]")
+        if not 0 <= self.min_p <= 1:
+            raise ConfigError(f"min_p should be in range [0, 1], but found {self.min_p}")
+        if self.repetition_ngram_size <= 0 or self.repetition_ngram_threshold <= 0:
+            self.repetition_ngram_size = self.repetition_ngram_threshold = 0
         if self.max_new_tokens is not None and self.max_new_tokens < 0:
-            raise ValueError("max_new_tokens must be >= 0")
-        # the decode hot path implements greedy sampling (top_k == 1, generation/sampling.cc:113-126)
-        if self.do_sample and self.top_k != 1:
-            raise NotImplementedError("lmdeploy_b200 implements the greedy decode path (top_k=1 / do_sample=False)")
+            raise ConfigError("max_new_tokens must be >= 0")
+        # The decode hot path samples greedily (top_k == 1, generation/sampling.cc:113-126).  With do_sample=False -- the
+        # default -- the reference decodes greedily WHATEVER top_k / top_p / temperature / repetition_penalty say
+        # (async_engine.py `_determine_gen_config` resets them), so those are accepted; asking for real sampling is refused.
+        if self.do_sample and (self.top_k != 1 or self.repetition_penalty != 1.0):
+            raise NotImplementedError("lmdeploy_b200 implements the greedy decode path: do_sample=True needs top_k=1 and "
+                                      "repetition_penalty=1.0")
+        if self.repetition_ngram_size:
+            raise NotImplementedError("GenerationConfig.repetition_ngram_size is not supported on the greedy decode hot path")
         for name, default in self._UNSUPPORTED.items():
             if getattr(self, name) != default:
                 raise NotImplementedError(f"GenerationConfig.{name} is not supported on the greedy decode hot path")
-        if self.n != 1:
-            raise NotImplementedError("GenerationConfig.n > 1 is not supported")
+
+    def determined(self, input_len, session_len, tokenizer=None, hf_gen_cfg=None, eos_token_id=None):
+        """The per-request copy the engine receives -- AsyncEngine._determine_gen_config
+        (lmdeploy/serve/core/async_engine.py:417-437): stop words -> ids, eos ids of generation_config.json and of the
+        tokenizer merged into stop_token_ids, greedy normalisation when do_sample is off, n > 1 falls back to 1,
+        max_new_tokens None = whatever the session still holds."""
+        import copy
+        g = copy.copy(self)
+        if g.stop_words or g.bad_words or g.bad_token_ids:
+            if tokenizer is None and (g.stop_words or g.bad_words):
+                raise ValueError("stop_words need a tokenizer: pass stop_token_ids instead")
+            g.convert_stop_bad_words_to_ids(tokenizer)
+        g.update_from_hf_gen_cfg(hf_gen_cfg or {}, eos_token_id)
+        if not g.do_sample:
+            g.top_k, g.temperature, g.repetition_penalty = 1, 1.0, 1.0
+        g.n = 1
+        if g.max_new_tokens is None:
+            g.max_new_tokens = max(0, session_len - input_len)
+        return g
 
 
 @dataclass
@@ -175,13 +215,13 @@ class TurbomindEngineConfig:
 
     def __post_init__(self):
         if self.dtype not in ("auto", "float16", "bfloat16"):
-            raise ValueError(f"unsupported dtype {self.dtype}")
+            raise ConfigError(f"unsupported dtype {self.dtype}")
         if self.tp < 1 or (self.tp & (self.tp - 1)):
-            raise ValueError("tp must be a power of two >= 1")
+            raise ConfigError("tp must be a power of two >= 1")
         if self.quant_policy not in (0, 4, 8):
-            raise ValueError("invalid quant_policy (0, 4, 8)")
+            raise ConfigError("invalid quant_policy (0, 4, 8)")
         if self.cache_max_entry_count <= 0:
-            raise ValueError("invalid cache_max_entry_count")
+            raise ConfigError("invalid cache_max_entry_count")
         if self.cache_block_seq_len % 64:
             raise ValueError("cache_block_seq_len must be a multiple of 64")
         if self.max_batch_size is not None and not (1 <= self.max_batch_size <= 128):

@@ -559,9 +559,19 @@ def test_config_keyword_surface_matches_the_reference():
         with pytest.raises(NotImplementedError):
             M.TurbomindEngineConfig(**kw)
     for kw in (dict(response_format={"type": "json_schema"}), dict(logits_processors=[print]), dict(return_ppl=True),
-               dict(logprobs=5), dict(n=2), dict(repetition_ngram_size=3)):
+               dict(logprobs=5), dict(repetition_ngram_size=3, repetition_ngram_threshold=2)):
         with pytest.raises(NotImplementedError):
             M.GenerationConfig(**kw)
+    # the reference's own validation (messages.py:195-205), raised as an error that is both ValueError and AssertionError
+    for kw in (dict(n=0), dict(top_p=1.5), dict(top_k=-1), dict(temperature=2.5), dict(min_p=-0.1)):
+        with pytest.raises(AssertionError):
+            M.GenerationConfig(**kw)
+        with pytest.raises(ValueError):
+            M.GenerationConfig(**kw)
+    g = M.GenerationConfig(repetition_ngram_size=3)               # threshold 0: the pair is reset, as the reference does
+    assert (g.repetition_ngram_size, g.repetition_ngram_threshold) == (0, 0)
+    with pytest.raises(AssertionError):
+        M.TurbomindEngineConfig(cache_max_entry_count=0)
 
 
 class _FakeEngine:
@@ -643,7 +653,8 @@ def test_pipeline_infer_and_stream_infer_agree():
 def test_options_that_would_change_greedy_tokens_are_refused():
     GenerationConfig(temperature=0.3, top_p=0.8, top_k=40, min_p=0.1)          # sampling knobs are inert without do_sample
     GenerationConfig(do_sample=True, top_k=1)                                   # top_k = 1 is greedy
-    for kw in (dict(repetition_penalty=1.1), dict(min_new_tokens=4), dict(do_sample=True, top_k=40)):
+    GenerationConfig(repetition_penalty=1.1)        # reset to 1.0 for greedy requests by the reference (_determine_gen_config)
+    for kw in (dict(do_sample=True, top_k=1, repetition_penalty=1.1), dict(min_new_tokens=4), dict(do_sample=True, top_k=40)):
         with pytest.raises(NotImplementedError):
             GenerationConfig(**kw)
 
@@ -687,3 +698,33 @@ def test_streamed_text_and_engine_outputs_are_incremental():
     assert [o.status for o in outs[:-1]] == [ResponseType.SUCCESS] * (len(outs) - 1) and outs[-1].status == ResponseType.FINISH
     assert sum((o.token_ids for o in outs), []) == whole.token_ids
     assert [o.num_token for o in outs] == sorted(o.num_token for o in outs) and outs[-1].num_token == 8
+
+
+def test_request_config_is_determined_like_the_reference():
+    """GenerationConfig.determined = AsyncEngine._determine_gen_config (async_engine.py:417-437)."""
+    tok = _FakeTokenizer()
+    g = GenerationConfig(temperature=0.3, top_k=40, repetition_penalty=1.2, n=3, max_new_tokens=None, stop_words=["ld"],
+                         stop_token_ids=[9])
+    d = g.determined(input_len=10, session_len=64, tokenizer=tok, hf_gen_cfg={"eos_token_id": [1, 14]}, eos_token_id=1)
+    assert (d.top_k, d.temperature, d.repetition_penalty, d.n, d.max_new_tokens) == (1, 1.0, 1.0, 1, 54)
+    assert d.stop_token_ids == [1, 7, 9, 14]
+    assert (g.top_k, g.n, g.max_new_tokens, g.stop_token_ids) == (40, 3, None, [9])          # the user's object is untouched
+    d = GenerationConfig(do_sample=True, top_k=1, temperature=0.5).determined(70, 64)
+    assert d.temperature == 0.5 and d.max_new_tokens == 512 and d.stop_token_ids == []
+    assert GenerationConfig(max_new_tokens=None).determined(70, 64).max_new_tokens == 0
+    with pytest.raises(ValueError):
+        GenerationConfig(stop_words=["x"]).determined(1, 64)                                  # no tokenizer
+
+
+def test_pipeline_merges_generation_config_eos_ids(tmp_path):
+    """generation_config.json's eos ids stop generation (Llama-3 chat models end turns with an id that is only there)."""
+    p = _fake_pipeline()
+    base = p.infer([[2, 7]], GenerationConfig(max_new_tokens=9))[0]
+    assert base.finish_reason == "length"
+    stop = base.token_ids[3]
+    p = _fake_pipeline()
+    p.hf_gen_cfg = {"eos_token_id": [stop, 99]}
+    r = p.infer([[2, 7]], GenerationConfig(max_new_tokens=9))[0]
+    assert r.finish_reason == "stop" and r.token_ids == base.token_ids[:base.token_ids.index(stop)]
+    r = p.infer([[2, 7]], GenerationConfig(max_new_tokens=9, ignore_eos=True))[0]
+    assert r.finish_reason == "length" and r.token_ids == base.token_ids
