@@ -1,7 +1,7 @@
 """pipeline(): the user entry point, same shape as lmdeploy.pipeline (lmdeploy/api.py:15-82, pipeline.py:33-95)."""
 from typing import List, Optional, Union
 
-from .messages import GenerationConfig, Response, TurbomindEngineConfig
+from .messages import GenerationConfig, Response, Session, TurbomindEngineConfig
 from .turbomind.engine import TurboMind, batched_generate, stream_generate
 
 
@@ -133,6 +133,47 @@ class Pipeline:
                 held[i] = []
             if s.finished:
                 yield self._closing(i, s, g, shown.get(i, 0))
+
+    # ---- multi-turn chat (lmdeploy/pipeline.py:186-266): the history is re-rendered through the chat template every
+    # turn; with enable_prefix_caching the earlier turns' KV blocks are reused instead of recomputed
+    def session(self) -> Session:
+        self._next_chat_session = getattr(self, "_next_chat_session", 0) + 1
+        return Session(self._next_chat_session - 1)
+
+    @staticmethod
+    def _history_to_messages(history, prompt):
+        messages = []
+        for user, assistant in history:
+            messages += user if isinstance(user, list) else [{"role": "user", "content": user}]
+            messages.append({"role": "assistant", "content": assistant})
+        return messages + (prompt if isinstance(prompt, list) else [{"role": "user", "content": prompt}])
+
+    def chat(self, prompt, session=None, gen_config: Optional[GenerationConfig] = None, stream_response=False,
+             adapter_name=None, **kw):
+        """One turn of a conversation: returns the updated Session (its .response holds the answer), or -- with
+        stream_response -- an iterator of Response chunks that updates the session when exhausted."""
+        if adapter_name is not None:
+            raise NotImplementedError("LoRA adapters are outside the hot-path scope")
+        if session is None:
+            session = self.session()
+        session.update(prompt=prompt, response=None)
+        messages = self._history_to_messages(session.history, prompt)
+        generator = self.stream_infer(messages, gen_config=gen_config, stream_response=stream_response)
+
+        def _gen():
+            resp = None
+            for out in generator:
+                # (a copy: the reference accumulates into the first chunk object it has already handed out)
+                resp = resp.extend(out) if resp else Response(**{**vars(out), "token_ids": list(out.token_ids)})
+                yield out
+            session.response = resp
+            session.history.append((session.prompt, resp.text))
+
+        if stream_response:
+            return _gen()
+        for _ in _gen():
+            pass
+        return session
 
     def get_ppl(self, input_ids):
         raise NotImplementedError("get_ppl needs per-position logits of the prompt (return_ppl path); the decode hot path "

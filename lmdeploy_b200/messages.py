@@ -257,6 +257,63 @@ class Response:
     error_message: Optional[str] = None
 
 
+    def extend(self, other: "Response") -> "Response":
+        """Merge a later chunk into this one (lmdeploy/messages.py:634-660): text, token ids and logprobs are
+        concatenated, everything else is taken from the later chunk.  Returns self."""
+        self.text += other.text
+        self.generate_token_len = other.generate_token_len
+        self.input_token_len = other.input_token_len
+        self.finish_reason = other.finish_reason
+        self.index = other.index
+        if other.token_ids:
+            self.token_ids += other.token_ids
+        if other.logprobs:
+            self.logprobs = (self.logprobs or []) + other.logprobs
+        self.routed_experts = other.routed_experts
+        self.error_code = other.error_code
+        self.error_message = other.error_message
+        return self
+
+
+@dataclass
+class ScheduleMetrics:
+    """The reference's ScheduleMetrics fields (lmdeploy/messages.py) plus the block counts they derive from."""
+    active_seqs: int = 0
+    waiting_seqs: int = 0
+    cache_usage: float = 0.0
+    prefix_cache_hit_rate: float = 0
+    scheduler_tick: int = 0
+    total_seqs: int = 0
+    total_blocks: int = 0
+    active_blocks: int = 0
+    cached_blocks: int = 0
+    free_blocks: int = 0
+
+
+class Session:
+    """A chat session of Pipeline.chat: the turns so far (lmdeploy/serve/managers/session_manager.py:17-75)."""
+
+    def __init__(self, session_id: int, **kwargs):
+        self.session_id = session_id
+        self.prompt = None
+        self.response: Optional[Response] = None
+        self.history: list = []                    # [(user prompt, assistant text)]
+        self.gen_config: Optional[GenerationConfig] = None
+        self.update(**kwargs)
+
+    def update(self, **kwargs):
+        self.prompt = kwargs.get("prompt", self.prompt)
+        self.response = kwargs.get("response", self.response)
+        self.gen_config = kwargs.get("gen_config", self.gen_config)
+
+    def reset(self):
+        self.prompt, self.response, self.history, self.gen_config = None, None, [], None
+
+    def __repr__(self):
+        return (f"Session(session_id={self.session_id}, history_len={len(self.history)}, "
+                f"has_response={self.response is not None}, has_gen_config={self.gen_config is not None})")
+
+
 @dataclass
 class EngineOutput:
     status: ResponseType = None

@@ -195,7 +195,8 @@ class TurboMind:
 
     def get_schedule_metrics(self, index=0):
         """ScheduleMetrics of this rank (TurboMind.get_schedule_metrics, lmdeploy/turbomind/turbomind.py)."""
-        return self.scheduler.metrics()
+        from ..messages import ScheduleMetrics
+        return ScheduleMetrics(**self.scheduler.metrics())
 
     def new_session_id(self):
         with self._lock:

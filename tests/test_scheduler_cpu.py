@@ -728,3 +728,34 @@ def test_pipeline_merges_generation_config_eos_ids(tmp_path):
     assert r.finish_reason == "stop" and r.token_ids == base.token_ids[:base.token_ids.index(stop)]
     r = p.infer([[2, 7]], GenerationConfig(max_new_tokens=9, ignore_eos=True))[0]
     assert r.finish_reason == "length" and r.token_ids == base.token_ids
+
+
+def test_chat_sessions_carry_the_history():
+    """Pipeline.chat (lmdeploy/pipeline.py:206-262): every turn renders history + prompt through the chat template."""
+    from lmdeploy_b200.messages import Response, Session
+    seen = []
+
+    class Tok(_FakeTokenizer):
+        def apply_chat_template(self, messages, add_generation_prompt=True, tokenize=True):
+            seen.append([(m["role"], m["content"]) for m in messages])
+            out = [0]
+            for m in messages:
+                out += self.encode(m["content"])
+            return out + [1]
+
+    p = _fake_pipeline()
+    p.tokenizer = Tok()
+    cfg = GenerationConfig(max_new_tokens=3, ignore_eos=True, skip_special_tokens=False)
+    s = p.chat("!", gen_config=cfg)
+    assert isinstance(s, Session) and len(s.history) == 1 and s.response.finish_reason == "length"
+    assert s.history[0] == ("!", s.response.text) and len(s.response.token_ids) == 3
+    chunks = list(p.chat("!!", session=s, gen_config=cfg, stream_response=True))
+    assert chunks[-1].finish_reason == "length" and len(s.history) == 2
+    assert seen[-1] == [("user", "!"), ("assistant", s.history[0][1]), ("user", "!!")]
+    assert s.history[1][1] == "".join(c.text for c in chunks)
+    # Response.extend merges chunks the way the reference does
+    a = Response(text="ab", generate_token_len=2, input_token_len=5, token_ids=[1, 2])
+    b = Response(text="c", generate_token_len=3, input_token_len=5, finish_reason="stop", token_ids=[3], index=4)
+    m = a.extend(b)
+    assert m is a and (m.text, m.token_ids, m.generate_token_len, m.finish_reason, m.index) == ("abc", [1, 2, 3], 3, "stop", 4)
+    assert p.session().session_id != p.session().session_id
