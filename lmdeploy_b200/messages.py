@@ -284,6 +284,7 @@ class ScheduleMetrics:
     prefix_cache_hit_rate: float = 0
     scheduler_tick: int = 0
     total_seqs: int = 0
+    preemptions: int = 0
     total_blocks: int = 0
     active_blocks: int = 0
     cached_blocks: int = 0

@@ -19,7 +19,11 @@ index when they fill; a new request re-uses the longest chain of published block
 at least the last prompt token to be fed, so the step that produces its first logits still runs) and starts with
 `cached` already advanced -- those tokens are never fed.  Shared blocks are read-only by construction: a decode step
 writes only position `cached`, which lies in the first private block.  Unreferenced published blocks stay resident
-and are evicted oldest-first only when the free list runs dry."""
+and are evicted oldest-first only when the free list runs dry.
+
+Out of KV memory: the youngest running sequence is preempted -- its blocks go back to the pool, it returns to the head
+of the waiting queue and, once its whole context fits again, refills its cache (prompt and the tokens it had generated)
+and continues.  No request ends early for lack of memory unless it alone outgrows the pool."""
 from collections import OrderedDict, deque
 from dataclasses import dataclass, field
 from typing import Deque, Dict, List, Optional
@@ -42,21 +46,25 @@ class Sequence:
     reused_tokens: int = 0        # prompt tokens served from the prefix cache (never fed)
     step_tokens: int = 1          # tokens this sequence feeds in the step being formed / executed
     error: Optional[str] = None   # why the request was rejected (finish_reason 'error')
+    preemptions: int = 0          # times this sequence lost its blocks to an older one and had to refill its cache
     chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
 
     def token_at(self, pos):
         return self.prompt[pos] if pos < len(self.prompt) else self.generated[pos - len(self.prompt)]
 
     def next_input(self):
-        if self.fed < len(self.prompt):
-            return self.prompt[self.fed]
-        return self.generated[-1]
+        return self.token_at(self.cached)
+
+    @property
+    def context_len(self):
+        """Tokens known so far: the prompt and what has been generated."""
+        return len(self.prompt) + len(self.generated)
 
     def next_inputs(self):
-        """The `step_tokens` tokens of this step (more than one only inside the prompt)."""
-        if self.fed < len(self.prompt):
-            return self.prompt[self.fed:self.fed + self.step_tokens]
-        return [self.generated[-1]]
+        """The `step_tokens` tokens of this step: positions [cached, cached + step_tokens) of prompt + generated.  One
+        token (the last generated) in steady decode; several only while the cache is being (re)filled -- inside the
+        prompt, or after a preemption dropped this sequence's blocks."""
+        return [self.token_at(p) for p in range(self.cached, min(self.cached + self.step_tokens, self.context_len))]
 
     @property
     def in_prefill(self):
@@ -182,6 +190,7 @@ class Scheduler:
         self.active: List[Sequence] = []
         self.sessions: Dict[int, Sequence] = {}
         self.tick = 0                 # schedule() calls so far
+        self.preemptions = 0          # sequences sent back to the waiting queue for lack of KV blocks
 
     def add(self, seq: Sequence):
         if seq.session_id in self.sessions:
@@ -216,6 +225,14 @@ class Scheduler:
                 still.append(s)
         self.active = still
 
+    def _preempt(self, seq):
+        self._release(seq)
+        seq.chain, seq.cached, seq.fed, seq.step_tokens = [], 0, 0, 1
+        seq.preemptions += 1
+        self.preemptions += 1
+        self.active.remove(seq)
+        self.waiting.appendleft(seq)
+
     def _blocks_needed(self, seq, upto_tokens):
         return (upto_tokens + self.block_len - 1) // self.block_len - len(seq.blocks)
 
@@ -225,30 +242,59 @@ class Scheduler:
         self.tick += 1
         self._retire()
         # grow active sequences that cross a block boundary (need room for token index `cached`)
-        for s in self.active:
+        # Out of KV memory: the YOUNGEST running sequence gives its blocks back and returns to the head of the waiting
+        # queue; it refills its cache (prompt + what it generated so far) when it is admitted again and continues -- the
+        # recompute flavour of the reference's preemption (SequenceManager frees the blocks of lower-priority sequences,
+        # src/turbomind/models/llama/SequenceManager.cc; there is no host swap on this path).  Published prefix blocks
+        # stay in the cache index, so with prefix caching a resumed sequence usually finds most of itself again.
+        preempted = False
+        for s in list(self.active):
+            if s not in self.active or s.finished:
+                continue
             need = self._blocks_needed(s, s.cached + 1)
-            if need > 0:
+            while need > 0:
                 got = self.alloc.allocate(need)
-                if got is None:            # out of KV memory: stop the youngest sequence (no swap on this path)
+                if got is not None:
+                    s.blocks += got
+                    break
+                victim = next((v for v in reversed(self.active) if not v.finished), None)
+                if victim is None or (victim is s and sum(not v.finished for v in self.active) == 1):
+                    # alone and still too long for the whole cache: nothing to wait for
                     s.finished, s.finish_reason = True, "length"
-                    continue
-                s.blocks += got
-        # admit
-        while self.waiting and len(self.active) < self.max_batch:
+                    break
+                self._preempt(victim)
+                preempted = True
+                if victim is s:
+                    break
+        self._retire()                     # a sequence stopped just above gives its blocks to this step's admissions
+        # admit (not in a step that had to preempt: the freed blocks belong to the sequences that stay)
+        while self.waiting and len(self.active) < self.max_batch and not preempted:
             s = self.waiting[0]
             if s.finished:                 # cancelled while waiting
                 self.waiting.popleft()
                 self.sessions.pop(s.session_id, None)
                 continue
             if self.prefix is not None and not s.blocks:
-                # never the whole prompt: its last token must be fed to produce the first logits
-                s.blocks, s.chain = self.prefix.match(s.prompt, len(s.prompt) - 1)
-                s.cached = s.fed = s.reused_tokens = len(s.blocks) * self.block_len
-            got = self.alloc.allocate(self._blocks_needed(s, s.cached + 1))
+                # never the whole context: its last token must be fed to produce the next logits
+                ctx = s.prompt + s.generated if s.generated else s.prompt
+                s.blocks, s.chain = self.prefix.match(ctx, len(ctx) - 1)
+                s.cached = len(s.blocks) * self.block_len
+                s.fed = min(len(s.prompt), s.cached)
+                s.reused_tokens = max(s.reused_tokens, s.fed)
+            # a resumed sequence comes back only when its whole context fits again (else it would be preempted next step)
+            upto = s.context_len + 1 if s.preemptions else s.cached + 1
+            if (upto + self.block_len - 1) // self.block_len > self.alloc.total:
+                # cannot fit even an empty cache: waiting would never end
+                self._release(s)
+                s.finished, s.finish_reason = True, "length"
+                self.waiting.popleft()
+                self.sessions.pop(s.session_id, None)
+                continue
+            got = self.alloc.allocate(self._blocks_needed(s, upto))
             if got is None:
                 if self.prefix is not None:            # give the references back; retry from scratch next step
                     self._release(s)
-                    s.chain, s.cached, s.fed, s.reused_tokens = [], 0, 0, 0
+                    s.chain, s.cached, s.fed = [], 0, 0
                 break
             s.blocks += got
             self.waiting.popleft()
@@ -257,7 +303,7 @@ class Scheduler:
         budget = self.token_budget - len(batch)
         for s in batch:
             s.step_tokens = 1
-            rem = len(s.prompt) - s.fed
+            rem = s.context_len - s.cached         # tokens still to feed, the one that produces the next logits included
             if self.prefill_chunk > 1 and rem > 1 and budget > 0:
                 extra = min(self.prefill_chunk - 1, rem - 1, budget)
                 need = self._blocks_needed(s, s.cached + 1 + extra)
@@ -284,8 +330,8 @@ class Scheduler:
                     if len(s.chain) == j:
                         toks = [s.token_at(p) for p in range(j * self.block_len, (j + 1) * self.block_len)]
                         s.chain.append(self.prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
-            if s.fed < len(s.prompt):
-                continue                   # still consuming the prompt; sampled token is discarded
+            if s.cached < s.context_len:
+                continue                   # still filling the cache (prompt, or refill after a preemption): sample discarded
             if s.max_new_tokens == 0:
                 s.finished, s.finish_reason = True, "length"
                 events.append((s, None))
@@ -316,5 +362,6 @@ class Scheduler:
         return dict(total_seqs=len(self.sessions), active_seqs=sum(not s.finished for s in self.active),
                     waiting_seqs=sum(not s.finished for s in self.waiting),
                     cache_usage=used / self.alloc.total if self.alloc.total else 0.0, prefix_cache_hit_rate=hit,
-                    scheduler_tick=self.tick, total_blocks=self.alloc.total, free_blocks=self.alloc.num_free,
+                    scheduler_tick=self.tick, preemptions=self.preemptions, total_blocks=self.alloc.total,
+                    free_blocks=self.alloc.num_free,
                     cached_blocks=idle, active_blocks=used)

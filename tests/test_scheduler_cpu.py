@@ -17,8 +17,9 @@ def run(sched, sampler, max_steps=10000):
     steps = 0
     while sched.has_work and steps < max_steps:
         batch = sched.schedule()
+        steps += 1
         if not batch:
-            break
+            continue          # e.g. a tick that only retired / preempted; the engine loop simply calls step() again
         assert len(batch) <= sched.max_batch
         # every running sequence owns enough blocks for the token it is about to cache
         for s in batch:
@@ -29,7 +30,7 @@ def run(sched, sampler, max_steps=10000):
         assert len(owned) + sched.alloc.num_free == sched.alloc.total
         trace.append([s.session_id for s in batch])
         sched.update(batch, [sampler(s) for s in batch])
-        steps += 1
+    assert steps < max_steps, "the scheduler stopped making progress"
     sched.schedule()          # final retirement
     return trace
 
@@ -759,3 +760,52 @@ def test_chat_sessions_carry_the_history():
     m = a.extend(b)
     assert m is a and (m.text, m.token_ids, m.generate_token_len, m.finish_reason, m.index) == ("abc", [1, 2, 3], 3, "stop", 4)
     assert p.session().session_id != p.session().session_id
+
+
+@pytest.mark.parametrize("prefix_caching", [False, True])
+def test_kv_exhaustion_preempts_the_youngest_and_nothing_is_lost(prefix_caching):
+    """3 sequences x 20 tokens = 15 blocks of 4, the pool has 9: the youngest running sequence gives its blocks back,
+    waits, refills its cache (prompt + what it had generated) and continues.  The KV-content-hashing fake model makes a
+    wrong refill visible: every sequence must produce exactly the tokens it produces with an unlimited pool."""
+    prompts = [[11, 12, 13, 14, 15, 16], [21, 22, 23, 24, 25, 26], [31, 32, 33, 34, 35, 36]]
+
+    def go(num_blocks):
+        sched = Scheduler(max_batch=4, block_len=4, num_blocks=num_blocks, session_len=4096, prefix_caching=prefix_caching)
+        model = FakeKvModel(num_blocks, 4)
+        seqs = [Sequence(session_id=i, prompt=list(p), max_new_tokens=14, stop_token_ids=[], ignore_eos=True, eos_id=None)
+                for i, p in enumerate(prompts)]
+        for q in seqs:
+            sched.add(q)
+        ticks = 0
+        while sched.has_work:
+            ticks += 1
+            assert ticks < 2000
+            batch = sched.schedule()
+            if not batch:
+                continue
+            for q in batch:
+                assert len(q.blocks) * 4 >= q.cached + 1
+            owned = [b for q in sched.active for b in set(q.blocks)]
+            if not prefix_caching:
+                assert len(owned) == len(set(owned))
+            sched.update(batch, model.step(batch))
+        return seqs, sched
+
+    free, _ = go(64)
+    tight, sched = go(9)
+    assert sched.preemptions > 0 and sum(q.preemptions for q in tight) == sched.preemptions
+    assert tight[0].preemptions == 0                            # the oldest sequence is never the victim
+    for a, b in zip(free, tight):
+        assert b.finish_reason == "length" and len(b.generated) == 14 and a.generated == b.generated
+    m = sched.metrics()
+    assert m["active_seqs"] == 0 and m["waiting_seqs"] == 0 and m["free_blocks"] + m["cached_blocks"] == 9
+
+
+def test_a_sequence_that_outgrows_the_whole_pool_ends_with_length():
+    sched = Scheduler(max_batch=2, block_len=4, num_blocks=3, session_len=4096)
+    a = Sequence(session_id=1, prompt=[1, 2, 3], max_new_tokens=50, stop_token_ids=[], ignore_eos=True, eos_id=None)
+    sched.add(a)
+    run(sched, lambda q: 7)
+    # 12 slots: 3 prompt tokens + 9 generated ones are cached, the 10th sampled token finds no block for its K/V
+    assert a.finished and a.finish_reason == "length" and len(a.generated) == 10 and a.preemptions == 0
+    assert sched.alloc.num_free == 3 and not sched.has_work
