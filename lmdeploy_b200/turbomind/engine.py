@@ -110,7 +110,7 @@ class TurboMind:
             from .loader import load_hf_checkpoint
             cfg = engine_config or TurbomindEngineConfig()
             spec, model, eos = load_hf_checkpoint(pretrained_model_name_or_path, quant_policy=cfg.quant_policy,
-                                                  block_len=cfg.cache_block_seq_len,
+                                                  block_len=cfg.cache_block_seq_len, hf_overrides=cfg.hf_overrides,
                                                   max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE)
             return cls(spec, cfg, model=model, eos_id=eos, **kw)
         raise FileNotFoundError(pretrained_model_name_or_path)
@@ -214,6 +214,11 @@ class TurboMindInstance:
     def _submit(self, session_id, input_ids, gen_config):
         g = gen_config or GenerationConfig()
         # max_new_tokens = None: until the session is full (the scheduler clamps to session_len), as the reference does
+        rope = getattr(getattr(self.engine, "spec", None), "rope", None)
+        if rope is not None and rope.dynamic_ntk_base(len(input_ids)) != rope.base:
+            raise NotImplementedError(f"a {len(input_ids)}-token prompt exceeds the model's trained context "
+                                      f"({rope.max_position_embeddings}); dynamic-NTK rescaling of the rope base per "
+                                      "request is not implemented on this path")
         budget = g.max_new_tokens if g.max_new_tokens is not None else 1 << 30
         seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=budget,
                        stop_token_ids=list(g.stop_token_ids or []), ignore_eos=g.ignore_eos, eos_id=self.engine.eos_id)

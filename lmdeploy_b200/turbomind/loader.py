@@ -90,7 +90,10 @@ def parse_rope(cfg, head_dim):
             kw.update(type="yarn", factor=float(factor), attention_factor=float(af),
                       beta_fast=float(scaling.get("beta_fast", 32.0)), beta_slow=float(scaling.get("beta_slow", 1.0)))
         elif rtype == "dynamic":
-            raise NotImplementedError("dynamic-NTK rope is not supported by the sm_100a kernels")
+            # dynamic NTK: a per-REQUEST base, fixed at admission from the prompt length (init_dynamic_ntk,
+            # unified_attention_layer.cc:228-243); prompts within the trained context keep the config's base, which is
+            # the only case served here (engine.TurboMindInstance refuses longer prompts, it does not mis-rotate them)
+            kw.update(type="dynamic", factor=factor)
         else:
             raise NotImplementedError(f"unsupported rope type {rtype!r}")
     return RopeSpec(**kw)
@@ -286,9 +289,22 @@ def read_checkpoint(path):
     return cfg, LazyCheckpoint(path)
 
 
-def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0):
+def deep_merge(base, override):
+    """TurbomindEngineConfig.hf_overrides: merged into config.json key by key, dicts recursively
+    (lmdeploy/turbomind/converter.py:59-70 `_deep_merge`), e.g. {"rope_scaling": {"type": "dynamic", "factor": 2.0}}."""
+    for k, v in override.items():
+        if isinstance(base.get(k), dict) and isinstance(v, dict):
+            deep_merge(base[k], v)
+        else:
+            base[k] = v
+    return base
+
+
+def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0, hf_overrides=None):
     from .runtime import DecodeModel, _TORCH_T
     cfg, tensors = read_checkpoint(path)
+    if hf_overrides:
+        deep_merge(cfg, hf_overrides)
     spec = spec_from_config(cfg)
     import dataclasses
     # the device model sees the replicated KV head count; convert_layer replicates from the checkpoint's own

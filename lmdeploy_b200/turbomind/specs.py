@@ -7,7 +7,7 @@ from dataclasses import dataclass, replace
 class RopeSpec:
     """RoPE parameters as the reference parses them from an HF config (lmdeploy/turbomind/models/utils.py:76-166) and
     hands them to init_rope_kernel_param (src/turbomind/models/attention_weight.cc:37-93)."""
-    type: str = "default"               # 'default' | 'linear' | 'llama3' | 'yarn'   ('dynamic' NTK is not supported)
+    type: str = "default"               # 'default' | 'linear' | 'llama3' | 'yarn' | 'dynamic' (prompts within the trained context)
     dim: int = 128                      # rotated dims = head_dim * partial_rotary_factor
     base: float = 10000.0
     factor: float = 0.0
@@ -21,9 +21,23 @@ class RopeSpec:
 
     TYPE_ID = {"default": 1, "linear": 2, "yarn": 4, "llama3": 5}
 
+    def dynamic_ntk_base(self, prompt_len):
+        """The rope base the reference gives a request of `prompt_len` prompt tokens under dynamic NTK scaling
+        (init_dynamic_ntk, src/turbomind/models/llama/unified_attention_layer.cc:228-243)."""
+        base = self.base
+        if self.type == "dynamic" and self.factor > 1.0 and prompt_len > self.max_position_embeddings:
+            f = self.factor * prompt_len / self.max_position_embeddings - (self.factor - 1.0)
+            base *= f ** (self.dim / (self.dim - 2.0))
+        return base
+
     def config_fields(self):
         """Field values of b200_rope_config (include/b200_turbomind.h) in declaration order, without exact_math --
         the counterpart of copy_rope_config (lmdeploy/turbomind/models/utils.py:170-187)."""
+        if self.type == "dynamic":
+            # the kernels see plain RoPE with the config's base and no position scaling -- exactly what the reference
+            # computes for a prompt that fits the trained context (RopeType::kDynamic: inv_factor = 1, base unchanged)
+            return dict(RopeSpec(type="default", dim=self.dim, base=self.base, factor=0.0,
+                                 max_position_embeddings=self.max_position_embeddings).config_fields())
         if self.type not in self.TYPE_ID:
             raise NotImplementedError(f"rope type {self.type!r} (supported: {sorted(self.TYPE_ID)})")
         return dict(type=self.TYPE_ID[self.type], dim=self.dim, base=self.base, factor=self.factor,

@@ -303,9 +303,24 @@ def test_rope_scaling_is_parsed_like_the_reference():
     assert len(golden) >= 14
     checked = 0
     for name, g in golden.items():
-        if "raises" in g or g["rope_config"]["type"] == 3:        # unknown types / dynamic NTK: refused here, loudly
+        if "raises" in g:                                          # unknown types: refused here too, loudly
             with pytest.raises(NotImplementedError):
                 LD.parse_rope(g["config"], g["head_dim"]).config_fields()
+            continue
+        if g["rope_config"]["type"] == 3:
+            # dynamic NTK: parsed field for field; the kernels are handed plain RoPE (what the reference computes for
+            # prompts within the trained context), longer prompts are refused at submission
+            r = LD.parse_rope(g["config"], g["head_dim"])
+            want = g["rope_config"]
+            assert (r.type, r.base, r.dim, r.factor, r.max_position_embeddings) == \
+                ("dynamic", want["base"], want["dim"], want["factor"], want["max_position_embeddings"])
+            f = r.config_fields()
+            assert (f["type"], f["factor"], f["base"]) == (1, 0.0, want["base"])
+            n = want["max_position_embeddings"]
+            assert r.dynamic_ntk_base(n) == r.base and r.dynamic_ntk_base(1) == r.base
+            # init_dynamic_ntk: base * (factor * len / max_pos - (factor - 1)) ** (dim / (dim - 2))
+            assert r.dynamic_ntk_base(2 * n) == pytest.approx(r.base * (2.0 * 2 - 1.0) ** (128 / 126.0), rel=1e-12)
+            checked += 5
             continue
         got = LD.parse_rope(g["config"], g["head_dim"]).config_fields()
         for field, want in g["rope_config"].items():           # every field the reference assigns for this rope type
@@ -415,3 +430,10 @@ def test_engine_defaults_follow_the_reference():
     cfg = dict(cfg, max_position_embeddings=131072, model_max_length=8192)
     spec = LD.spec_from_config(cfg)
     assert spec.session_len == 8192 and spec.max_position_embeddings == 131072       # RoPE still sees the config's own value
+
+
+def test_hf_overrides_are_merged_into_the_config():
+    cfg = {"a": 1, "rope_scaling": {"type": "linear", "factor": 2.0}, "text_config": {"x": {"y": 1, "z": 2}}}
+    out = LD.deep_merge(cfg, {"rope_scaling": {"type": "dynamic"}, "text_config": {"x": {"y": 5}}, "new": [1]})
+    assert out is cfg and cfg == {"a": 1, "rope_scaling": {"type": "dynamic", "factor": 2.0},
+                                  "text_config": {"x": {"y": 5, "z": 2}}, "new": [1]}

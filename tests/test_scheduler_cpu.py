@@ -809,3 +809,18 @@ def test_a_sequence_that_outgrows_the_whole_pool_ends_with_length():
     # 12 slots: 3 prompt tokens + 9 generated ones are cached, the 10th sampled token finds no block for its K/V
     assert a.finished and a.finish_reason == "length" and len(a.generated) == 10 and a.preemptions == 0
     assert sched.alloc.num_free == 3 and not sched.has_work
+
+
+def test_dynamic_ntk_prompts_beyond_the_trained_context_are_refused_not_mis_rotated():
+    from lmdeploy_b200.turbomind.engine import TurboMindInstance
+    from lmdeploy_b200.turbomind.specs import RopeSpec
+    import types
+    p = _fake_pipeline()
+    p.engine.spec = types.SimpleNamespace(rope=RopeSpec(type="dynamic", dim=128, base=1e6, factor=2.0, max_position_embeddings=8))
+    p.engine.scheduler.session_len = 64
+    inst = TurboMindInstance(p.engine)
+    inst._submit(1, list(range(8)), GenerationConfig(max_new_tokens=2))                # fits the trained context
+    with pytest.raises(NotImplementedError):
+        inst._submit(2, list(range(9)), GenerationConfig(max_new_tokens=2))
+    p.engine.spec.rope = RopeSpec(type="dynamic", dim=128, base=1e6, factor=1.0, max_position_embeddings=8)
+    inst._submit(3, list(range(9)), GenerationConfig(max_new_tokens=2))                # factor <= 1: the base never changes
