@@ -42,7 +42,6 @@ class StaticBatchRunner:
         self.cur_len = 0
         # kernels per step: embedding, rmsnorm, plan, rope table, L x (qkv, prologue, attention, fix-up, wo, norm, w13,
         # w2, norm), lm_head, argmax stage 1 + 2, advance  (B200_FUSED_NORM=1 folds the two norms into wo / w2: 7 per layer)
-        import os
         self.launches_per_step = 4 + (7 if (model.tp_size == 1 and os.environ.get("B200_FUSED_NORM")) else 9) * spec.layers + 4
         self._graph = None
 

@@ -1,0 +1,244 @@
+"""Dry run of the GPU-only HOST code on the CPU: DecodeModel (weight upload through the C ABI), StaticBatchRunner (the
+bench loop) and the TurboMind engine's device step, with the C library replaced by a recorder and torch.cuda by stand-ins.
+
+No arithmetic is checked here (the GPU tests do that); what this catches before a GPU box is spent on it is the class of
+mistake the host code can make on its own: a misspelt keyword into a ctypes structure, a tensor of the wrong shape or
+dtype handed to `b200_model_set_*`, a call with the wrong number of arguments (the recorder checks every call against the
+argtypes the binding declares), a buffer that is too small for the step it is given."""
+import contextlib
+import ctypes as C
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from lmdeploy_b200 import _lib as L
+
+
+class RecordingLib:
+    """Stands in for libb200tm.so.  Every b200_* symbol the real library exports exists here; a call is checked against
+    the declared argtypes (count, and that a pointer parameter never receives a Python float / a scalar parameter never a
+    tensor) and recorded."""
+
+    def __init__(self, real):
+        self.calls = []
+        self._real = real
+        self._handles = 0
+
+    def __getattr__(self, name):
+        if not name.startswith("b200_"):
+            raise AttributeError(name)
+        real_fn = getattr(self._real, name)          # AttributeError if the library has no such symbol
+        argtypes = real_fn.argtypes
+
+        def call(*args):
+            if argtypes is not None:
+                assert len(args) == len(argtypes), (name, len(args), len(argtypes))
+                for a, t in zip(args, argtypes):
+                    if t in (C.c_int, C.c_int64, C.c_size_t):
+                        assert isinstance(a, (int, np.integer)) and not isinstance(a, bool) or isinstance(a, bool), (name, a, t)
+                    elif t is C.c_float:
+                        assert isinstance(a, (int, float)), (name, a, t)
+                    elif t is C.c_void_p:
+                        assert a is None or isinstance(a, (int, C.c_void_p)) or hasattr(a, "_obj"), (name, type(a))
+            self.calls.append((name, args))
+            return self._result(name, args)
+        return call
+
+    def _result(self, name, args):
+        if name == "b200_last_error":
+            return b""
+        if name == "b200_version":
+            return b"recording stand-in sm_100a"
+        if name == "b200_linear_prepared_bytes":
+            d = args[0]._obj
+            per = {0: 2.0, 1: 0.53125, 2: 1.001, 3: 1.03125}[d.weight_format]
+            return int(d.input_dim * d.output_dim * per)
+        if name.endswith("_bytes"):
+            return 4096
+        if name == "b200_model_create":
+            self._handles += 1
+            args[0]._obj.value = 0x1000 * self._handles
+            cfg = args[1]._obj
+            assert 1 <= cfg.max_batch <= 128 and cfg.rope.type in (0, 1, 2, 4, 5) and cfg.rope.dim > 0
+            assert cfg.num_heads % cfg.num_kv_heads == 0 and cfg.head_dim == 128
+            return 0
+        if name == "b200_linear_load_plans":
+            return 0
+        return 0
+
+    def names(self):
+        return [c[0] for c in self.calls]
+
+
+@pytest.fixture
+def dry(monkeypatch, lib):
+    """`lib` (conftest) is the real library: loaded on the CPU for its symbol table and argtypes only."""
+    rec = RecordingLib(lib)
+    monkeypatch.setattr(L, "load", lambda: rec)
+    stream = types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: stream)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a, **k: (1 << 30, 2 << 30))
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
+
+    class Graph:
+        def replay(self):
+            rec.calls.append(("graph.replay", ()))
+    monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
+    monkeypatch.setattr(torch.cuda, "graph", lambda g, *a, **k: contextlib.nullcontext())
+    return rec
+
+
+def tiny(fmt, **kw):
+    from lmdeploy_b200.turbomind.specs import ModelSpec
+    return ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1000, 1e4, weight_format=fmt, **kw)
+
+
+@pytest.mark.parametrize("fmt,kw", [("awq", {}), ("fp16", {}), ("fp8", dict(dtype="bf16")), ("awq", dict(qkv_bias=True))])
+def test_model_upload_and_step_calls(dry, fmt, kw):
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+    spec = tiny(fmt, **kw)
+    m = DecodeModel(spec, quant_policy=8, max_batch=8, device="cpu")
+    m.load_synthetic(seed=0)
+    names = dry.names()
+    per_layer = 4
+    assert names.count("b200_model_set_linear") == spec.layers * per_layer + 1            # + lm_head
+    assert names.count("b200_linear_prepare") == spec.layers * per_layer + 1
+    assert names.count("b200_model_set_tensor") == 2 + spec.layers * (3 if spec.qkv_bias else 2)
+    fmts = [a[0]._obj.weight_format for n, a in dry.calls if n == "b200_linear_prepare"]
+    want = {"awq": L.FMT_U4, "fp16": L.FMT_DENSE, "fp8": L.FMT_FP8_COL}[fmt]
+    assert fmts[:-1] == [want] * (spec.layers * per_layer) and fmts[-1] == L.FMT_DENSE    # lm_head is dense T
+    # vocabulary padded to the GEMM's 128-column tile
+    lm = [a for n, a in dry.calls if n == "b200_linear_prepare"][-1][0]._obj
+    assert (lm.input_dim, lm.output_dim) == (512, 1024)
+    B = 3
+    i32 = lambda n: torch.zeros(n, dtype=torch.int32)
+    m.decode_step(batch=B, token_ids=i32(B), cu_q_len=i32(B + 1), cu_k_len=i32(B + 1), block_ptrs=torch.zeros(6, dtype=torch.int64),
+                  cu_block_nums=i32(B + 1), out_tokens=i32(B), max_k_len=70)
+    name, args = dry.calls[-1]
+    si = args[1]._obj
+    assert name == "b200_model_decode_step" and si.batch_size == B and si.max_k_len == 70 and si.advance == 0
+    assert si.layer_stride_bytes == m.layer_bytes and si.finished is None
+    m.decode_step(batch=B, token_ids=i32(7), cu_q_len=i32(B + 1), cu_k_len=i32(B + 1), block_ptrs=torch.zeros(6, dtype=torch.int64),
+                  cu_block_nums=i32(B + 1), out_tokens=i32(7), max_k_len=70, token_num=7)
+    assert dry.calls[-1][0] == "b200_model_chunk_step" and dry.calls[-1][1][2] == 7
+
+
+def test_static_batch_runner_bench_loop(dry):
+    """The calls bench.py makes, in order, on the device-resident and the host-fed path."""
+    from lmdeploy_b200.engine import StaticBatchRunner
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+    m = DecodeModel(tiny("awq"), quant_policy=8, max_batch=4, device="cpu")
+    m.load_synthetic(seed=0)
+    r = StaticBatchRunner(m, batch=4, max_len=200, seed=0)
+    assert r.block_ptrs.numel() == 4 * 4 and len(set(r.block_ptrs.tolist())) == 16
+    r.prefill_random(100)
+    assert r.cu_k.tolist() == [0, 101, 202, 303, 404] and r.cur_len == 101
+    n0 = len(dry.calls)
+    step = r.make_device_step(graph=True)
+    for _ in range(3):
+        step()
+    names = dry.names()[n0:]
+    assert names.count("b200_model_decode_step") == 2 and names.count("graph.replay") == 3       # warm-up + capture, then replays
+    assert r.cur_len == 101 + 1 + 3
+    out = r.step_host(np.array([1, 2, 3, 4], np.int32))
+    assert out.shape == (4,) and dry.names()[-1] == "graph.replay"
+    t = r.time_attention_kernel(150, iters=2) if hasattr(torch.cuda, "Event") and False else None
+    assert t is None
+    sb = m.step_bytes(4, 150)
+    assert sb["total"] == sum(v for k, v in sb.items() if k != "total") and sb["kv_read"] > 0
+    assert r.launches_per_step == 4 + 9 * 2 + 4
+
+
+def test_engine_device_step_marshals_what_the_scheduler_formed(dry, monkeypatch):
+    """TurboMind._execute: the arrays of a step land in the device buffers the C call receives, pure decode steps replay a
+    graph from their second occurrence, a mixed step goes through the chunk entry."""
+    from lmdeploy_b200.messages import GenerationConfig, TurbomindEngineConfig
+    from lmdeploy_b200.turbomind.engine import TurboMind, TurboMindInstance
+    monkeypatch.setenv("B200_CHUNKED_PREFILL", "4")
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+    model = DecodeModel(tiny("awq"), quant_policy=8, max_batch=8, device="cpu")
+    model.load_synthetic(seed=0)
+    eng = TurboMind(tiny("awq"), TurbomindEngineConfig(max_batch_size=8, session_len=256, cache_max_entry_count=32, quant_policy=8),
+                    model=model)
+    assert eng.pool.num_blocks == 32 and eng.d_block_ptrs.numel() == 8 * 4
+    inst = TurboMindInstance(eng)
+    a = inst._submit(1, [5, 6, 7, 8, 9, 10], GenerationConfig(max_new_tokens=6, ignore_eos=True))
+    b = inst._submit(2, [11, 12], GenerationConfig(max_new_tokens=7, ignore_eos=True))
+    n0 = len(dry.calls)
+    eng.step()                                   # a: 4 prompt tokens, b: 2 -> one mixed step of 6 rows
+    name, args = [c for c in dry.calls[n0:] if c[0].startswith("b200_model_")][-1]
+    assert name == "b200_model_chunk_step" and args[2] == 6 and args[1]._obj.batch_size == 2
+    assert eng.d_tokens[:6].tolist() == [5, 6, 7, 8, 11, 12] and eng.d_cu_q[:3].tolist() == [0, 4, 6]
+    assert eng.d_cu_k[:3].tolist() == [0, 4, 6] and eng.d_cu_blocks[:3].tolist() == [0, 1, 2]
+    assert eng.d_block_ptrs[:2].tolist() == [eng.pool.ptr(a.blocks[0]), eng.pool.ptr(b.blocks[0])]
+    assert b.generated == [0] and a.generated == []            # the recorder "samples" token 0 for every row
+    eng.step()                                   # a: its last 2 prompt tokens (chunk), b: decode -> mixed again
+    assert dry.calls[-1][0] == "b200_model_chunk_step" or "b200_model_chunk_step" in dry.names()[-3:]
+    n1 = len(dry.calls)
+    eng.step(), eng.step()                       # both decoding: eager the first time that batch size is seen, then a graph
+    names = dry.names()[n1:]
+    assert names.count("b200_model_decode_step") == 2 and names.count("graph.replay") == 1
+    while eng.scheduler.has_work:
+        eng.step()
+    assert a.finish_reason == b.finish_reason == "length" and (len(a.generated), len(b.generated)) == (6, 7)
+    m = eng.get_schedule_metrics()
+    assert m.active_seqs == 0 and m.free_blocks == 32
+
+
+def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys):
+    """bench.run_b200 end to end on a tiny geometry with the recording library: every key the driver reads is on the one
+    JSON line, with the right types -- the script itself is what the round-end run executes."""
+    import json
+    import os
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import bench
+    import lmdeploy_b200.turbomind as TM
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+
+    class CpuModel(DecodeModel):
+        def __init__(self, spec, **kw):
+            super().__init__(spec, device="cpu", **kw)
+
+    class Event:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def elapsed_time(self, other):
+            return 2.0
+    monkeypatch.setattr(torch.cuda, "Event", Event)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(TM, "DecodeModel", CpuModel)
+    monkeypatch.setitem(TM.SPECS, "tiny", tiny("awq"))
+    monkeypatch.setitem(bench.CONFIGS, "c2", ("tiny", 4, 100, 8))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(k, raising=False)
+    args = types.SimpleNamespace(gpus=1, steps=4, warmup=3, impl="b200", config="c2", no_graph=False, no_cpu_baseline=False,
+                                 attn_iters=2)
+    bench.run_b200(args)
+    lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 4 and d["warmup"] == 3 and d["higher_is_better"] is True
+    assert d["value"] == pytest.approx(4 * 4 / 2e-3) and d["ms_per_step"] == pytest.approx(0.5)
+    assert d["unit"] == "tokens/s" and d["dtype"] == "f16" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert set(d["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"} and d["roofline"]["bound"] == "hbm"
+    assert d["roofline"]["frac"] == pytest.approx(d["roofline"]["achieved"] / d["roofline"]["peak"])
+    assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] == 16
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert d["gpu_launches"] == (4 + 9 * 2 + 4) * 4 and "workload" in d["config"] and "model" not in d["config"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the timed loops ran through the captured graph: warm-up + timed + host-fed steps
+    assert dry.names().count("graph.replay") >= 3 + 4 + 3 + 4
