@@ -115,8 +115,10 @@ def default_session_len(cfg):
 
 def spec_from_config(cfg):
     arch = cfg["architectures"][0]
-    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "Qwen2ForCausalLM": "qwen2",
-            "MistralForCausalLM": "llama"}.get(arch)          # Mistral dense = Llama tensor names (no sliding window, below)
+    # lmdeploy/turbomind/supported_models.py SUPPORTED_ARCHS (dense text models of the hot-path scope); Mistral dense uses
+    # the Llama tensor names (no sliding window, below)
+    name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "InternLM3ForCausalLM": "llama",
+            "Qwen2ForCausalLM": "qwen2", "MistralForCausalLM": "llama"}.get(arch)
     if name is None:
         raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama / Qwen2 dense)")
     window = cfg.get("sliding_window")
@@ -289,6 +291,15 @@ def read_checkpoint(path):
     return cfg, LazyCheckpoint(path)
 
 
+def with_checkpoint_biases(spec, tensors):
+    """q/k/v biases are a property of the CHECKPOINT: the reference bundles whatever `.bias` tensors exist with their
+    linears (lmdeploy/turbomind/models/llama.py reads them through `_linear(prefix)`), whatever the config says."""
+    import dataclasses
+    key = "model.layers.0.attention.wqkv.bias" if spec.arch == "internlm2" else "model.layers.0.self_attn.q_proj.bias"
+    has = key in tensors
+    return spec if has == spec.qkv_bias else dataclasses.replace(spec, qkv_bias=has)
+
+
 def deep_merge(base, override):
     """TurbomindEngineConfig.hf_overrides: merged into config.json key by key, dicts recursively
     (lmdeploy/turbomind/converter.py:59-70 `_deep_merge`), e.g. {"rope_scaling": {"type": "dynamic", "factor": 2.0}}."""
@@ -306,6 +317,7 @@ def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1
     if hf_overrides:
         deep_merge(cfg, hf_overrides)
     spec = spec_from_config(cfg)
+    spec = with_checkpoint_biases(spec, tensors)
     import dataclasses
     # the device model sees the replicated KV head count; convert_layer replicates from the checkpoint's own
     model = DecodeModel(dataclasses.replace(spec, kv_heads=kv_heads_for_tp(spec.kv_heads, tp)), quant_policy=quant_policy,

@@ -437,3 +437,15 @@ def test_hf_overrides_are_merged_into_the_config():
     out = LD.deep_merge(cfg, {"rope_scaling": {"type": "dynamic"}, "text_config": {"x": {"y": 5}}, "new": [1]})
     assert out is cfg and cfg == {"a": 1, "rope_scaling": {"type": "dynamic", "factor": 2.0},
                                   "text_config": {"x": {"y": 5, "z": 2}}, "new": [1]}
+
+
+def test_biases_follow_the_checkpoint_and_internlm3_is_a_llama():
+    cfg, t, _ = make_checkpoint("qwen2", None, seed=2)
+    spec = LD.spec_from_config(dict(cfg, architectures=["LlamaForCausalLM"]))          # config says nothing about biases
+    assert not spec.qkv_bias and LD.with_checkpoint_biases(spec, t).qkv_bias            # the tensors do
+    cfg, t, _ = make_checkpoint("llama", None, seed=2)
+    spec = LD.spec_from_config(dict(cfg, attention_bias=True))
+    assert spec.qkv_bias and not LD.with_checkpoint_biases(spec, t).qkv_bias
+    spec = LD.spec_from_config(dict(cfg, architectures=["InternLM3ForCausalLM"],
+                                    rope_scaling={"rope_type": "dynamic", "factor": 6.0}, max_position_embeddings=32768))
+    assert spec.arch == "llama" and spec.rope.type == "dynamic" and spec.session_len == 32768
