@@ -252,6 +252,12 @@ B200_API int b200_residual_rmsnorm(void* out, int out_packed_mt, void* residual,
                           const void* bias, int tokens, int dim, float eps, int dtype, void* stream);
 B200_API int b200_embedding_lookup(void* out, const void* table, const int* token_ids, int tokens, int dim, int vocab,
                           int dtype, void* stream);
+/* Per-head RMSNorm of the q and k heads inside fused QKV rows, in place, before RoPE (Qwen3 family).  Replaces
+ * invokeQkRMSNorm (kernels/norm/rms_norm.cu:139-260; unified_attention_layer.cc:739).  qkv: [token_num, stride] T with a
+ * row = [num_heads x head_dim | num_kv_heads x head_dim | v ...]; q_weight / k_weight: [head_dim] T.  head_dim == 128.
+ * y = T(float(x) * rsqrt(mean(x^2) + eps)) *_T w, summed in the reference kernel's order (bit-identical). */
+B200_API int b200_qk_rmsnorm(void* qkv, int64_t stride, const void* q_weight, const void* k_weight, int token_num,
+                    int num_heads, int num_kv_heads, int head_dim, float eps, int dtype, void* stream);
 B200_API int b200_argmax(int* out, const void* logits, int rows, int vocab, int64_t ld, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -321,7 +327,17 @@ enum { B200_W_QKV = 0, B200_W_O = 1, B200_W_GATE_UP = 2, B200_W_DOWN = 3, B200_W
 /* B200_T_QKV_BIAS: optional per-layer [(num_heads + 2 num_kv_heads) * head_dim] T, laid out like a w_qkv output row.
  * Added to q / k / v by the attention prologue in T, where the reference adds it (AttentionParams::q_bias/k_bias/v_bias
  * from w_qkv->bias, unified_attention_layer.cc:495-497) -- Qwen2-family checkpoints. */
-enum { B200_T_EMBEDDING = 0, B200_T_FINAL_NORM = 1, B200_T_ATTN_NORM = 2, B200_T_FFN_NORM = 3, B200_T_QKV_BIAS = 4 };
+/* B200_T_Q_NORM / B200_T_K_NORM: optional per-layer [head_dim] T weights of the per-head q / k RMSNorm (Qwen3 family);
+ * when both are set the step runs b200_qk_rmsnorm on the QKV GEMM output (eps = norm_eps). */
+enum {
+    B200_T_EMBEDDING  = 0,
+    B200_T_FINAL_NORM = 1,
+    B200_T_ATTN_NORM  = 2,
+    B200_T_FFN_NORM   = 3,
+    B200_T_QKV_BIAS   = 4,
+    B200_T_Q_NORM     = 5,
+    B200_T_K_NORM     = 6
+};
 
 typedef struct {
     int            batch_size;

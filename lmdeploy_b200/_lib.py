@@ -71,7 +71,7 @@ class StepInputs(C.Structure):
 ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_STATE = -1, -2, -3, -4          # b200_status
 W_QKV, W_O, W_GATE_UP, W_DOWN, W_LM_HEAD = range(5)
 FMT_DENSE, FMT_U4, FMT_FP8, FMT_FP8_COL = range(4)        # b200_linear_desc.weight_format
-T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM, T_QKV_BIAS = range(5)
+T_EMBEDDING, T_FINAL_NORM, T_ATTN_NORM, T_FFN_NORM, T_QKV_BIAS, T_Q_NORM, T_K_NORM = range(7)
 
 _lib = None
 
@@ -96,6 +96,8 @@ def load():
     lib.b200_decode_attention.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_process_kv.argtypes = [C.POINTER(AttentionParams)]
     lib.b200_prefill_attention.argtypes = [C.POINTER(AttentionParams)]
+    lib.b200_qk_rmsnorm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_float, C.c_int, C.c_void_p]
     lib.b200_rope_table.argtypes = [C.c_void_p, C.POINTER(RopeConfig), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_prefill_attention_workspace_bytes.restype = C.c_size_t
     lib.b200_prefill_attention_workspace_bytes.argtypes = [C.c_int, C.c_int]

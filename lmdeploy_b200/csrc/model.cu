@@ -21,6 +21,8 @@ struct LayerW {
     const void*      attn_norm{};
     const void*      ffn_norm{};
     const void*      qkv_bias{};  // optional (Qwen2 family)
+    const void*      q_norm{};    // optional per-head q / k RMSNorm weights (Qwen3 family)
+    const void*      k_norm{};
 };
 
 }  // namespace b200
@@ -193,6 +195,12 @@ extern "C" int b200_model_set_tensor(b200_model* m, int layer, int which, const 
     else if (which == B200_T_QKV_BIAS) {
         m->layers[layer].qkv_bias = ptr;
     }
+    else if (which == B200_T_Q_NORM) {
+        m->layers[layer].q_norm = ptr;
+    }
+    else if (which == B200_T_K_NORM) {
+        m->layers[layer].k_norm = ptr;
+    }
     else {
         return fail(B200_ERR_INVALID_ARG, "set_tensor: bad tensor id");
     }
@@ -304,6 +312,10 @@ static int run_step(b200_model* m, const b200_step_inputs* in, int R, bool chunk
         }
         // ---- attention block ----
         TRY_T(1, b200_linear_forward_packed(&W.qkv, m->xp, MT, R, m->qkv, qkv_dim, 0, 0, m->lin_ws, m->lin_ws_bytes, stream));
+        if (W.q_norm && W.k_norm) {
+            TRY_T(1, b200_qk_rmsnorm(m->qkv, qkv_dim, W.q_norm, W.k_norm, R, c.num_heads, c.num_kv_heads, c.head_dim, c.norm_eps,
+                                     c.dtype, stream));
+        }
         b200_attention_params a{};
         a.out    = m->attn_xp;
         a.q      = m->qkv;

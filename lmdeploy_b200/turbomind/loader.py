@@ -118,9 +118,9 @@ def spec_from_config(cfg):
     # lmdeploy/turbomind/supported_models.py SUPPORTED_ARCHS (dense text models of the hot-path scope); Mistral dense uses
     # the Llama tensor names (no sliding window, below)
     name = {"InternLM2ForCausalLM": "internlm2", "LlamaForCausalLM": "llama", "InternLM3ForCausalLM": "llama",
-            "Qwen2ForCausalLM": "qwen2", "MistralForCausalLM": "llama"}.get(arch)
+            "Qwen2ForCausalLM": "qwen2", "Qwen3ForCausalLM": "qwen3", "MistralForCausalLM": "llama"}.get(arch)
     if name is None:
-        raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama / Qwen2 dense)")
+        raise NotImplementedError(f"architecture {arch} is outside the hot-path scope (InternLM2 / Llama / Qwen2 / Qwen3 dense)")
     window = cfg.get("sliding_window")
     if cfg.get("num_experts") or cfg.get("num_local_experts") or cfg.get("use_sliding_window") or \
             (arch == "MistralForCausalLM" and window and window < cfg.get("max_position_embeddings", 0)):
@@ -147,7 +147,7 @@ def spec_from_config(cfg):
                      weight_format=fmt,
                      checkpoint_format=method, dtype=dtype, qkv_bias=qkv_bias,
                      max_position_embeddings=int(cfg.get("max_position_embeddings", 0)),
-                     session_len=default_session_len(cfg))
+                     session_len=default_session_len(cfg), qk_norm=name == "qwen3")
 
 
 def kv_heads_for_tp(kv_heads, tp):
@@ -217,6 +217,12 @@ def convert_layer(spec: ModelSpec, tensors, i, tp=1, rank=0):
     if spec.qkv_bias:
         out["qkv_bias"] = w_qkv.bias          # applied by the attention prologue, not by the GEMM
         w_qkv.bias = None
+    if spec.qk_norm:
+        # [head_dim] weights shared by every head; their elements follow the RoPE reorder of the channels they scale
+        # (lmdeploy/turbomind/models/qwen3.py reorders q_norm / k_norm with reorder_rotary_emb like the projections)
+        perm = rope_perm(1, D, rope_dim)
+        out["q_norm"] = tensors[p + "self_attn.q_norm.weight"][perm]
+        out["k_norm"] = tensors[p + "self_attn.k_norm.weight"][perm]
     return out
 
 

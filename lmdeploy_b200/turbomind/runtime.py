@@ -175,6 +175,12 @@ class DecodeModel:
                     if tuple(b.shape) != ((self.heads + 2 * self.kv_heads) * D,):
                         raise ValueError(f"layers.{i}.qkv_bias has shape {tuple(b.shape)}")
                     self._set_tensor(i, L.T_QKV_BIAS, b)
+                if s.qk_norm:
+                    for which, nm in ((L.T_Q_NORM, "q_norm"), (L.T_K_NORM, "k_norm")):
+                        w = provider(f"layers.{i}.{nm}")
+                        if tuple(w.shape) != (D,):
+                            raise ValueError(f"layers.{i}.{nm} has shape {tuple(w.shape)}")
+                        self._set_tensor(i, which, w)
                 for name, (K, N, which) in shapes.items():
                     w = provider(f"layers.{i}.{name}")
                     if "col_scales" in w:       # fp8 e4m3 bytes [K, N] + f32 scales [K/128, N]
@@ -215,6 +221,8 @@ class DecodeModel:
         def provider(name):
             if name == "tok_embeddings":
                 return (torch.randn(s.vocab, s.hidden, generator=gr, device=dev) * 0.02).to(T)
+            if name.endswith("q_norm") or name.endswith("k_norm"):
+                return (1.0 + 0.1 * torch.randn(s.head_dim, generator=gr, device=dev)).to(T)
             if name == "norm" or name.endswith("_norm"):
                 return (1.0 + 0.02 * torch.randn(s.hidden, generator=gr, device=dev)).to(T)
             if name.endswith("qkv_bias"):

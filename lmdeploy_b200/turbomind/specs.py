@@ -66,6 +66,7 @@ class ModelSpec:
     dtype: str = "f16"
     checkpoint_format: str = None   # how the checkpoint packs it: 'awq' | 'gptq' | 'compressed-tensors' | None
     qkv_bias: bool = False          # q/k/v projections carry a bias (Qwen2 family), applied by the attention prologue
+    qk_norm: bool = False           # per-head RMSNorm of q and k before RoPE (Qwen3 family)
     rope: RopeSpec = None           # full RoPE description (checkpoints); None = rope_type / rope_theta / rope_factor above
     max_position_embeddings: int = 0   # config.max_position_embeddings (0 = unknown); feeds the RoPE config
     session_len: int = 0               # default session length the reference derives from the config (0 = unknown)

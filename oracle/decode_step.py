@@ -21,7 +21,7 @@ class TinyWeights:
     """Random weights of a small llama-family model in TurboMind's loader-visible layout."""
 
     def __init__(self, *, hidden, layers, heads, kv_heads, inter, vocab, fmt="awq", dtype=F16, seed=0, head_dim=128,
-                 qkv_bias=False):
+                 qkv_bias=False, qk_norm=False):
         rng = np.random.default_rng(seed)
         self.hidden, self.layers, self.heads, self.kv_heads = hidden, layers, heads, kv_heads
         self.inter, self.vocab, self.fmt, self.dtype, self.D = inter, vocab, fmt, dtype, head_dim
@@ -51,6 +51,10 @@ class TinyWeights:
                 w1w3=lin(hidden, 2 * inter), w2=lin(inter, hidden)))
             if qkv_bias:   # Qwen2 family: added to q/k/v by the attention prologue (unified_attention_layer.cc:495-497)
                 self.L[-1]["qkv_bias"] = rn((rng.standard_normal((heads + 2 * kv_heads) * D) * 0.1).astype(np.float32), dtype)
+        if qk_norm:        # Qwen3 family: per-head RMSNorm of q and k before RoPE (unified_attention_layer.cc:739)
+            for lw in self.L:
+                lw["q_norm"] = rn((1 + 0.1 * rng.standard_normal(D)).astype(np.float32), dtype)
+                lw["k_norm"] = rn((1 + 0.1 * rng.standard_normal(D)).astype(np.float32), dtype)
         out = rn((rng.standard_normal((hidden, vocab)) * 0.1 / np.sqrt(hidden)).astype(np.float32), dtype)
         self.output = dict(w=out, deq=out)
 
@@ -82,6 +86,7 @@ class TinyWeights:
             vi = (self.heads + self.kv_heads) * D + np.arange(rank * Hkv * D, (rank + 1) * Hkv * D)
             gu = np.arange(rank * 2 * I, (rank + 1) * 2 * I)      # interleaved (gate, up) pairs stay together
             extra = {"qkv_bias": lw["qkv_bias"][np.concatenate([qi, ki, vi])]} if "qkv_bias" in lw else {}
+            extra.update({k: lw[k] for k in ("q_norm", "k_norm") if k in lw})      # per-head weights: replicated
             sh.L.append(dict(attn_norm=lw["attn_norm"], ffn_norm=lw["ffn_norm"], **extra,
                              w_qkv=cols(lw["w_qkv"], np.concatenate([qi, ki, vi])),
                              wo=rows(lw["wo"], slice(rank * Hq * D, (rank + 1) * Hq * D)),
@@ -90,6 +95,14 @@ class TinyWeights:
         vs = slice(rank * sh.vocab_local, (rank + 1) * sh.vocab_local)
         sh.output = {k: v[:, vs] for k, v in self.output.items()}
         return sh
+
+
+def _qkv(x, w, lw, eps, dtype):
+    """QKV projection (+ the per-head q/k RMSNorm of the Qwen3 family)."""
+    qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+    if "q_norm" in lw:
+        qkv = OL.qk_rmsnorm(qkv, lw["q_norm"], lw["k_norm"], w.heads, w.kv_heads, w.D, eps, dtype)
+    return qkv
 
 
 def _bias_args(w, lw):
@@ -113,7 +126,7 @@ def decode_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables,
         parts = []
         for r, sw in enumerate(shards):
             lw = sw.L[l]
-            qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+            qkv = _qkv(x, sw, lw, eps, dtype)
             attn = OA.decode_attention(qkv, kvc[r], block_tables, hist, l, sw.heads, sw.kv_heads, rope, **_bias_args(sw, lw))
             parts.append(OL.linear(attn, lw["wo"]["deq"], dtype))
         x, residual = OL.allreduce_residual_rmsnorm(parts, residual, w.L[l]["ffn_norm"], eps, dtype)
@@ -138,7 +151,7 @@ def chunk_step(w: TinyWeights, token_ids, cache: OA.PagedKvCache, block_tables, 
     x = OL.rmsnorm(residual, w.L[0]["attn_norm"], eps, dtype)
     for l in range(w.layers):
         lw = w.L[l]
-        qkv = OL.linear(x, lw["w_qkv"]["deq"], dtype)
+        qkv = _qkv(x, w, lw, eps, dtype)
         attn = OA.prefill_attention(qkv, cache, block_tables, q_lens, k_lens, l, w.heads, w.kv_heads, rope,
                                     **_bias_args(w, lw))
         x, residual = OL.allreduce_residual_rmsnorm([OL.linear(attn, lw["wo"]["deq"], dtype)], residual,

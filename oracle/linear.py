@@ -173,6 +173,32 @@ def rmsnorm(x, w, eps, dtype):
     return t_mul(rn(f32(x * r), dtype), f32(w), dtype)
 
 
+def qk_rmsnorm(qkv, q_w, k_w, num_heads, num_kv_heads, head_dim, eps, dtype):
+    """Per-head RMSNorm of the q and k heads of fused QKV rows (Qwen3 family), as the reference's release build computes it
+    (invokeQkRMSNorm, rms_norm.cu:139-260; instruction order read from the compiled kernel): 16 lanes x 8 elements per
+    head; per lane an fp32 FMA chain over its 8 elements starting from 0; butterfly over lane distances 8, 4, 2, 1;
+    r = rsqrt(fma(sum, 1/dim, eps)); y = T(float(x) * r) *_T w.  (The hardware's rsqrt is an approximation: r may differ
+    from this restatement in its last fp32 bit, which moves an output by at most one T ulp.)  v is left untouched."""
+    assert head_dim == 128
+    qkv = f32(qkv).copy()
+    T = qkv.shape[0]
+    nqk = (num_heads + num_kv_heads) * head_dim
+    x = qkv[:, :nqk].reshape(T, num_heads + num_kv_heads, 16, 8)
+    s = np.zeros(x.shape[:3], np.float32)
+    for i in range(8):                                   # fma(x, x, s): one rounding (the product is exact in float64)
+        s = (x[..., i].astype(np.float64) ** 2 + s.astype(np.float64)).astype(np.float32)
+    for d in (8, 4, 2, 1):                               # butterfly: every lane ends with the same sum
+        s = f32(s + s[..., np.arange(16) ^ d])
+    ss = s[..., :1]
+    arg = (ss.astype(np.float64) * float(np.float32(1.0 / head_dim)) + float(np.float32(eps))).astype(np.float32)
+    r = f32(1.0 / np.sqrt(arg.astype(np.float64)))[..., None]
+    w = np.concatenate([np.broadcast_to(f32(q_w), (num_heads, head_dim)),
+                        np.broadcast_to(f32(k_w), (num_kv_heads, head_dim))]).reshape(1, -1, 16, 8)
+    y = t_mul(rn(f32(x * r), dtype), w, dtype)
+    qkv[:, :nqk] = y.reshape(T, nqk)
+    return qkv
+
+
 def residual_rmsnorm(hidden, residual, w, eps, dtype, bias=None):
     """BiasResidualRMSNorm (rms_norm.cu:287-363): residual <- residual + hidden (+bias) in T;
     hidden <- RMSNorm(residual) * w.  Returns (hidden_out, residual_out)."""

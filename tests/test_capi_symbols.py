@@ -36,6 +36,10 @@ def test_invalid_arguments_fail_loudly(lib):
     # step entry points refuse NULL handles before touching a device
     assert lib.b200_model_decode_step(None, None, None) == L.ERR_INVALID_ARG
     assert lib.b200_model_chunk_step(None, None, 4, None) == L.ERR_INVALID_ARG
+    # per-head q/k RMSNorm: argument checks happen before any device work
+    assert lib.b200_qk_rmsnorm(None, 1024, None, None, 4, 4, 2, 128, 1e-6, 0, None) == L.ERR_INVALID_ARG
+    assert lib.b200_qk_rmsnorm(8, 1024, 8, 8, 4, 4, 2, 64, 1e-6, 0, None) == L.ERR_UNSUPPORTED and b"head_dim" in lib.b200_last_error()
+    assert lib.b200_qk_rmsnorm(8, 512, 8, 8, 4, 4, 2, 128, 1e-6, 0, None) == L.ERR_INVALID_ARG           # stride < (4 + 2) * 128
     d = L.LinearDesc(4096, 4096, 7, 0, 128, None, None)                            # unknown weight format
     assert lib.b200_linear_prepared_bytes(C.byref(d)) == 0 and b"weight_format" in lib.b200_last_error()
     d = L.LinearDesc(4096, 4096, 3, 0, 64, None, None)                             # fp8 needs 128-wide K groups

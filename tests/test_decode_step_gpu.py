@@ -24,7 +24,8 @@ def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_ra
     from lmdeploy_b200.turbomind import ModelSpec, DecodeModel
     T = w.dtype
     spec = ModelSpec("tiny", "llama", w.hidden, w.layers, w.heads, w.kv_heads, w.inter, w.vocab, 1e4,
-                     weight_format=w.fmt, dtype="f16" if T == F16 else "bf16", qkv_bias="qkv_bias" in w.L[0])
+                     weight_format=w.fmt, dtype="f16" if T == F16 else "bf16", qkv_bias="qkv_bias" in w.L[0],
+                     qk_norm="q_norm" in w.L[0])
     m = DecodeModel(spec, quant_policy=quant_policy, max_batch=max_batch, tp_size=tp_size, tp_rank=tp_rank,
                     rope_exact_math=rope_exact_math)   # True: the numpy oracle cannot reproduce MUFU approximations
     sw = shard if shard is not None else w
@@ -53,6 +54,8 @@ def build_device_model(w: TinyWeights, quant_policy, max_batch, tp_size=1, tp_ra
             return to_dev_T(w.L[i]["ffn_norm"], T)
         if kind == "qkv_bias":
             return to_dev_T(sw.L[i]["qkv_bias"], T)
+        if kind in ("q_norm", "k_norm"):
+            return to_dev_T(sw.L[i][kind], T)
         return lin(sw.L[i][kind])
 
     m.load_tm_weights(provider)

@@ -91,6 +91,9 @@ def make_checkpoint(arch, family, seed=0):
             if arch == "qwen2":
                 for nm, n in (("q_proj", HQ * D), ("k_proj", HKV * D), ("v_proj", HKV * D)):
                     t[p + f"self_attn.{nm}.bias"] = torch.from_numpy((rng.standard_normal(n) * 0.2).astype(np.float16))
+            if arch == "qwen3":      # per-head RMSNorm weights of q and k, shared by every head
+                for nm in ("q_norm", "k_norm"):
+                    t[p + f"self_attn.{nm}.weight"] = torch.from_numpy((1 + 0.2 * rng.standard_normal(D)).astype(np.float16))
             add(p + "self_attn.q_proj", H, HQ * D), add(p + "self_attn.k_proj", H, HKV * D)
             add(p + "self_attn.v_proj", H, HKV * D), add(p + "self_attn.o_proj", HQ * D, H)
             add(p + "mlp.gate_proj", H, I), add(p + "mlp.up_proj", H, I), add(p + "mlp.down_proj", I, H)
@@ -104,7 +107,8 @@ def make_checkpoint(arch, family, seed=0):
     if arch != "qwen2":          # the Qwen2 test checkpoint ties lm_head to the embeddings (tie_word_embeddings)
         t[head] = torch.from_numpy((rng.standard_normal((V, H)) * 0.3 / np.sqrt(H)).astype(np.float16))
     cfg = {"architectures": [{"internlm2": "InternLM2ForCausalLM", "llama": "LlamaForCausalLM",
-                              "qwen2": "Qwen2ForCausalLM"}[arch]], "tie_word_embeddings": arch == "qwen2",
+                              "qwen2": "Qwen2ForCausalLM", "qwen3": "Qwen3ForCausalLM"}[arch]],
+           "tie_word_embeddings": arch == "qwen2", "head_dim": D,
            "hidden_size": H, "num_hidden_layers": L, "num_attention_heads": HQ, "num_key_value_heads": HKV,
            "intermediate_size": I, "vocab_size": V, "rms_norm_eps": 1e-5, "rope_theta": 10000.0}
     if family == "awq":
@@ -163,6 +167,9 @@ def hf_forward(arch, t, deq, tokens):
             wo, w1, w3, w2 = (deq[p + "self_attn.o_proj"], deq[p + "mlp.gate_proj"], deq[p + "mlp.up_proj"],
                               deq[p + "mlp.down_proj"])
             n2 = f(p + "post_attention_layernorm.weight")
+        if arch == "qwen3":      # HF Qwen3Attention: q_norm / k_norm over head_dim, then RoPE
+            q = norm(q, f(p + "self_attn.q_norm.weight"))
+            k = norm(k, f(p + "self_attn.k_norm.weight"))
         q, k = rope(q), rope(k)
         g = HQ // HKV
         out = np.zeros((S, HQ, D))
@@ -211,13 +218,14 @@ def to_tiny(spec, cfg_tensors, tp=1, rank=0):
     for i in range(L):
         c = LD.convert_layer(spec, t, i, tp, rank)
         extra = {"qkv_bias": rn(c["qkv_bias"].to(torch.float32).numpy(), T)} if "qkv_bias" in c else {}
+        extra.update({k: rn(c[k].to(torch.float32).numpy(), T) for k in ("q_norm", "k_norm") if k in c})
         w.L.append(dict(attn_norm=c["attention_norm"].to(torch.float32).numpy(),
                         ffn_norm=c["ffn_norm"].to(torch.float32).numpy(), **extra,
                         w_qkv=lin(c["w_qkv"]), wo=lin(c["wo"]), w1w3=lin(c["w1w3"]), w2=lin(c["w2"])))
     return w
 
 
-@pytest.mark.parametrize("arch", ["internlm2", "llama", "qwen2"])
+@pytest.mark.parametrize("arch", ["internlm2", "llama", "qwen2", "qwen3"])
 @pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("tp", [1, 2, 4])        # 4 > the 2 KV heads: each is replicated (builders/attention.py:30-50)
 def test_loader_transforms_preserve_model_semantics(arch, family, tp):
@@ -225,7 +233,7 @@ def test_loader_transforms_preserve_model_semantics(arch, family, tp):
     spec = LD.spec_from_config(cfg)
     assert spec.weight_format == {None: "fp16", "fp8": "fp8"}.get(family, "awq") and spec.arch == arch
     assert spec.checkpoint_format == family and spec.dtype == ("bf16" if family == "fp8" else "f16")
-    assert spec.qkv_bias == (arch == "qwen2")
+    assert spec.qkv_bias == (arch == "qwen2") and spec.qk_norm == (arch == "qwen3")
     T = BF16 if family == "fp8" else F16
     # logits are O(1); measured max error 5e-4 (fp16) / 5e-3 (bf16: 8 significand bits, 8x the rounding per operation)
     tokens = [5, 17, 200, 3, 99]
@@ -449,3 +457,21 @@ def test_biases_follow_the_checkpoint_and_internlm3_is_a_llama():
     spec = LD.spec_from_config(dict(cfg, architectures=["InternLM3ForCausalLM"],
                                     rope_scaling={"rope_type": "dynamic", "factor": 6.0}, max_position_embeddings=32768))
     assert spec.arch == "llama" and spec.rope.type == "dynamic" and spec.session_len == 32768
+
+
+def test_oracle_qk_rmsnorm_is_a_per_head_rmsnorm():
+    """The grouped-sum restatement (the compiled reference kernel's order) against a plain float64 RMSNorm per head."""
+    rng = np.random.default_rng(5)
+    Hq, Hkv = 4, 2
+    for T in (F16, BF16):
+        qkv = rn(rng.standard_normal((7, (Hq + 2 * Hkv) * 128)).astype(np.float32) * 3, T)
+        qw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), T)
+        kw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), T)
+        got = OL.qk_rmsnorm(qkv, qw, kw, Hq, Hkv, 128, 1e-6, T)
+        x = qkv[:, :(Hq + Hkv) * 128].reshape(7, Hq + Hkv, 128).astype(np.float64)
+        w = np.concatenate([np.tile(qw, (Hq, 1)), np.tile(kw, (Hkv, 1))]).astype(np.float64)
+        want = x / np.sqrt((x ** 2).mean(-1, keepdims=True) + 1e-6) * w
+        err = np.abs(got[:, :(Hq + Hkv) * 128].reshape(7, Hq + Hkv, 128) - want)
+        assert err.max() <= (4e-3 if T == F16 else 3e-2)            # two roundings to T of O(1..4) values
+        assert np.array_equal(got[:, (Hq + Hkv) * 128:], qkv[:, (Hq + Hkv) * 128:])      # v untouched
+        assert np.array_equal(rn(got, T), got)                                          # exact in T

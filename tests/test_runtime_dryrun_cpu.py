@@ -98,7 +98,8 @@ def tiny(fmt, **kw):
     return ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1000, 1e4, weight_format=fmt, **kw)
 
 
-@pytest.mark.parametrize("fmt,kw", [("awq", {}), ("fp16", {}), ("fp8", dict(dtype="bf16")), ("awq", dict(qkv_bias=True))])
+@pytest.mark.parametrize("fmt,kw", [("awq", {}), ("fp16", {}), ("fp8", dict(dtype="bf16")), ("awq", dict(qkv_bias=True)),
+                                    ("awq", dict(qk_norm=True))])
 def test_model_upload_and_step_calls(dry, fmt, kw):
     from lmdeploy_b200.turbomind.runtime import DecodeModel
     spec = tiny(fmt, **kw)
@@ -108,7 +109,10 @@ def test_model_upload_and_step_calls(dry, fmt, kw):
     per_layer = 4
     assert names.count("b200_model_set_linear") == spec.layers * per_layer + 1            # + lm_head
     assert names.count("b200_linear_prepare") == spec.layers * per_layer + 1
-    assert names.count("b200_model_set_tensor") == 2 + spec.layers * (3 if spec.qkv_bias else 2)
+    assert names.count("b200_model_set_tensor") == 2 + spec.layers * (2 + (1 if spec.qkv_bias else 0) + (2 if spec.qk_norm else 0))
+    if spec.qk_norm:
+        ids = [a[2] for n, a in dry.calls if n == "b200_model_set_tensor"]
+        assert ids.count(L.T_Q_NORM) == ids.count(L.T_K_NORM) == spec.layers
     fmts = [a[0]._obj.weight_format for n, a in dry.calls if n == "b200_linear_prepare"]
     want = {"awq": L.FMT_U4, "fp16": L.FMT_DENSE, "fp8": L.FMT_FP8_COL}[fmt]
     assert fmts[:-1] == [want] * (spec.layers * per_layer) and fmts[-1] == L.FMT_DENSE    # lm_head is dense T

@@ -651,3 +651,81 @@ def test_greedy_tokens_match_a_step_assembled_from_reference_kernels(kv_bits):
     same = (pools[0].cpu().numpy() == pools[1].cpu().numpy()).mean()
     assert same >= 0.999, same
     ref.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Qwen3 family: per-head q / k RMSNorm (b200_qk_rmsnorm, csrc/qk_norm.cu) and the decode step that uses it
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [F16, BF16])
+def test_qk_rmsnorm_matches_oracle(lib, dtype):
+    """The kernel reproduces the reference kernel's instruction order (FMA chain, butterfly, fma(sum, 1/dim, eps), rsqrt
+    approximation); the numpy restatement has an exact rsqrt, so an output may sit one T ulp away -- rarely."""
+    import ctypes as C
+    import torch
+    from lmdeploy_b200 import _lib as L
+    from harness import to_dev_T, from_dev_T
+    rng = np.random.default_rng(9)
+    Hq, Hkv, T = 8, 2, 37
+    width = (Hq + 2 * Hkv) * 128
+    qkv = rn((rng.standard_normal((T, width)) * 2).astype(np.float32), dtype)
+    qw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
+    kw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
+    d = to_dev_T(qkv, dtype)
+    dq, dk = to_dev_T(qw, dtype), to_dev_T(kw, dtype)
+    L.check(lib.b200_qk_rmsnorm(d.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6,
+                                0 if dtype == F16 else 1, torch.cuda.current_stream().cuda_stream), "b200_qk_rmsnorm")
+    torch.cuda.synchronize()
+    got = from_dev_T(d, dtype)
+    want = OL.qk_rmsnorm(qkv, qw, kw, Hq, Hkv, 128, 1e-6, dtype)
+    assert np.array_equal(got[:, (Hq + Hkv) * 128:], qkv[:, (Hq + Hkv) * 128:])           # v untouched
+    ulp = np.abs(want) * (2.0 ** -10 if dtype == F16 else 2.0 ** -7) + 1e-6
+    assert (np.abs(got - want) <= ulp).all()
+    assert (got != want).mean() < 0.02
+
+
+@pytest.mark.parametrize("fmt", ["awq", "fp16"])
+def test_decode_step_with_qk_norm_matches_oracle(fmt):
+    import torch
+    from oracle import attention as OA
+    from oracle.decode_step import TinyWeights, decode_step
+    from test_decode_step_gpu import build_device_model
+    from harness import from_dev_T
+    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, seed=17, qk_norm=True)
+    hist = np.array([0, 5, 64, 130], np.int32)
+    B = len(hist)
+    rng = np.random.default_rng(4)
+    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
+    layout = OA.KvLayout(2, 64, 128, 8)
+    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
+    nblk = sum(blocks_per) + 2
+    cache = OA.PagedKvCache(nblk, w.layers, layout, F16)
+    perm = rng.permutation(nblk)
+    tables, o = [], 0
+    for n in blocks_per:
+        tables.append(perm[o:o + n].tolist())
+        o += n
+    for l in range(w.layers):
+        for b in range(B):
+            h = int(hist[b])
+            if h:
+                OA.process_kv(cache, tables[b], l, 0, rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16),
+                              rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16), rope)
+    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
+    m = build_device_model(w, 8, max_batch=8)
+    pool = torch.from_numpy(cache.pool.copy()).cuda()
+    ptrs = torch.tensor([pool.data_ptr() + int(b) * cache.block_bytes for t in tables for b in t], dtype=torch.int64,
+                        device="cuda")
+    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
+    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
+    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
+    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
+    m.decode_step(batch=B, token_ids=torch.from_numpy(tokens).cuda(), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
+                  cu_block_nums=cu_blocks, out_tokens=d_out, max_k_len=int(hist.max()) + 1)
+    torch.cuda.synchronize()
+    got = from_dev_T(m.logits(B), F16)
+    ref, ref_tokens = decode_step(w, tokens, cache, tables, hist, rope, eps=m.cfg.norm_eps)
+    assert np.abs(got - ref).max() <= 4e-3
+    srt = np.sort(ref, -1)
+    for b in range(B):
+        if srt[b, -1] - srt[b, -2] > 8e-3:
+            assert d_out.cpu().numpy()[b] == ref_tokens[b]

@@ -20,6 +20,7 @@ run pending_ref_gemm 240 $P -k "reference_gemm"
 run pending_ref_norm 120 $P -k "rmsnorm_matches_reference"
 run pending_l2_reference_step 300 $P -s -k "assembled_from_reference_kernels"
 run pending_bf16_steps 300 $P -k "bf16_matches_oracle or synthetic_fp8 or qkv_bias or odd_gqa"
+run pending_qk_norm 240 $P -k "qk_rmsnorm or qk_norm"
 run pending_prefill_oracle 420 $P -k "prefill_attention_matches_oracle or prefill_single or prefill_attention_bf16"
 run pending_prefill_reference 240 $P -k "prefill_attention_matches_reference"
 run pending_chunk_step 300 $P -k "chunk_step"
