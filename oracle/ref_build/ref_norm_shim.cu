@@ -49,4 +49,22 @@ __attribute__((visibility("default"))) int ref_bias_residual_rmsnorm(void* resid
     return (int)cudaGetLastError();
 }
 
+// The reference's per-head q / k RMSNorm on fused QKV rows (rms_norm.cu:139-260, invokeQkRMSNorm; Qwen3 family), in place.
+// qkv: [token_num, stride] T; heads = q_heads + k_heads (+ whatever follows in the row is not touched).
+__attribute__((visibility("default"))) int ref_qk_rmsnorm(void* qkv, long stride, const void* q_weight, const void* k_weight,
+                                                          int token_num, int q_heads, int k_heads, int head_dim, float eps,
+                                                          int dtype, void* stream)
+{
+    using namespace turbomind;
+    const DataType dt = dtype == 0 ? kFloat16 : kBfloat16;
+    // the kernel addresses head h of token t at t * stride(0) + h * head_dim: a 3-D view over the q and k heads
+    Tensor x{qkv, core::Layout{{(ssize_t)token_num, (ssize_t)(q_heads + k_heads), (ssize_t)head_dim},
+                               {(ssize_t)stride, (ssize_t)head_dim, (ssize_t)1}},
+             dt, kDEVICE};
+    Tensor qw{const_cast<void*>(q_weight), core::Layout{{(ssize_t)head_dim}}, dt, kDEVICE};
+    Tensor kw{const_cast<void*>(k_weight), core::Layout{{(ssize_t)head_dim}}, dt, kDEVICE};
+    invokeQkRMSNorm(x, qw, kw, q_heads, k_heads, eps, false, (cudaStream_t)stream);
+    return (int)cudaGetLastError();
+}
+
 }  // extern "C"

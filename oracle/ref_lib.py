@@ -61,6 +61,10 @@ def load_norm():
         _norm_lib.ref_bias_residual_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                         C.c_float, C.c_int, C.c_void_p]
         _norm_lib.ref_bias_residual_rmsnorm.restype = C.c_int
+        if hasattr(_norm_lib, "ref_qk_rmsnorm"):          # invokeQkRMSNorm (Qwen3 family)
+            _norm_lib.ref_qk_rmsnorm.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                 C.c_int, C.c_float, C.c_int, C.c_void_p]
+            _norm_lib.ref_qk_rmsnorm.restype = C.c_int
     return _norm_lib
 
 

@@ -729,3 +729,32 @@ def test_decode_step_with_qk_norm_matches_oracle(fmt):
     for b in range(B):
         if srt[b, -1] - srt[b, -2] > 8e-3:
             assert d_out.cpu().numpy()[b] == ref_tokens[b]
+
+
+@pytest.mark.parametrize("dtype", [F16, BF16])
+def test_qk_rmsnorm_is_bit_identical_to_the_reference_kernel(lib, dtype):
+    """Ours against the REFERENCE's invokeQkRMSNorm (oracle/_ref/libtm_ref_norm.so) on the same buffers.  The kernel was
+    written to the reference's compiled instruction order, so the bar is equality, not a tolerance."""
+    import torch
+    from lmdeploy_b200 import _lib as L
+    from oracle import ref_lib
+    from harness import to_dev_T
+    if not ref_lib.norm_available():
+        pytest.skip("oracle/_ref/libtm_ref_norm.so not built")
+    ref = ref_lib.load_norm()
+    if not hasattr(ref, "ref_qk_rmsnorm"):
+        pytest.skip("libtm_ref_norm.so predates ref_qk_rmsnorm")
+    rng = np.random.default_rng(12)
+    for (Hq, Hkv, T) in ((8, 2, 37), (32, 8, 64), (28, 4, 5)):
+        width = (Hq + 2 * Hkv) * 128
+        qkv = rn((rng.standard_normal((T, width)) * rng.uniform(0.01, 30)).astype(np.float32), dtype)
+        qw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
+        kw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
+        a, b = to_dev_T(qkv, dtype), to_dev_T(qkv, dtype)
+        dq, dk = to_dev_T(qw, dtype), to_dev_T(kw, dtype)
+        st = torch.cuda.current_stream().cuda_stream
+        dt = 0 if dtype == F16 else 1
+        L.check(lib.b200_qk_rmsnorm(a.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6, dt, st), "ours")
+        assert ref.ref_qk_rmsnorm(b.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6, dt, st) == 0
+        torch.cuda.synchronize()
+        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (Hq, Hkv, T)
