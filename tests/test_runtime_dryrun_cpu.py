@@ -246,3 +246,64 @@ def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys):
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     # the timed loops ran through the captured graph: warm-up + timed + host-fed steps
     assert dry.names().count("graph.replay") >= 3 + 4 + 3 + 4
+
+
+@pytest.mark.parametrize("arch,family", [("internlm2", "awq"), ("llama", None), ("llama", "gptq"), ("llama", "compressed-tensors"),
+                                         ("llama", "fp8"), ("qwen2", "awq"), ("qwen3", None)])
+@pytest.mark.parametrize("tp", [1, 2])
+def test_checkpoint_directory_to_c_abi_upload(dry, monkeypatch, tmp_path, arch, family, tp):
+    """load_hf_checkpoint end to end without a device: config.json + safetensors -> format resolver -> layer conversion
+    -> Lin.to_tm -> DecodeModel.load_tm_weights -> b200_linear_prepare / b200_model_set_*.  Checks what the C ABI is
+    handed: formats, dims of this TP rank, dtypes and shapes of the buffers (the recorder cannot see device memory, so the
+    tensors are intercepted one level up)."""
+    import json
+    import sys
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from safetensors.torch import save_file
+    from test_loader_cpu import D, H, HKV, HQ, I, V, make_checkpoint
+    import lmdeploy_b200.turbomind.runtime as RT
+    from lmdeploy_b200.turbomind import loader as LD
+    cfg, t, _ = make_checkpoint(arch, family, seed=3)
+    (tmp_path / "config.json").write_text(json.dumps(dict(cfg, eos_token_id=[2, 7])))
+    save_file({k: v.contiguous() for k, v in t.items()}, str(tmp_path / "model.safetensors"))
+    seen = []
+    real_set_linear = RT.DecodeModel._set_linear
+
+    class CpuModel(RT.DecodeModel):
+        def __init__(self, spec, **kw):
+            super().__init__(spec, device="cpu", **kw)
+
+        def _set_linear(self, layer, which, K, N, weight, scales=None, zeros=None, transposed=False, fmt=None):
+            seen.append((layer, which, K, N, weight, scales, zeros, fmt))
+            return real_set_linear(self, layer, which, K, N, weight, scales, zeros, transposed, fmt)
+    monkeypatch.setattr(RT, "DecodeModel", CpuModel)
+    spec, model, eos = LD.load_hf_checkpoint(str(tmp_path), quant_policy=8, max_batch=8, tp=tp, rank=tp - 1)
+    assert eos == 2 and spec.arch == arch and model.tp_size == tp
+    hq, hkv, it = HQ // tp, LD.kv_heads_for_tp(HKV, tp) // tp, I // tp
+    want_dims = {L.W_QKV: (H, (hq + 2 * hkv) * D), L.W_O: (hq * D, H), L.W_GATE_UP: (H, 2 * it), L.W_DOWN: (it, H)}
+    int4 = family in ("awq", "gptq", "compressed-tensors")
+    T = torch.bfloat16 if family == "fp8" else torch.float16
+    per_layer = [s for s in seen if s[1] != L.W_LM_HEAD]
+    assert len(per_layer) == 4 * spec.layers and len(seen) == len(per_layer) + 1
+    for layer, which, K, N, w, sc, z, fmt in per_layer:
+        assert (K, N) == want_dims[which], (which, K, N)
+        if int4:
+            assert w.dtype == torch.int32 and tuple(w.shape) == (K, N // 8) and fmt is None
+            assert sc.dtype == z.dtype == T and tuple(sc.shape) == tuple(z.shape) == (K // 128, N)
+        elif family == "fp8":
+            assert w.dtype == torch.uint8 and tuple(w.shape) == (K, N) and fmt == L.FMT_FP8_COL
+            assert sc.dtype == torch.float32 and tuple(sc.shape) == (K // 128, N) and z is None
+        else:
+            assert w.dtype == T and tuple(w.shape) == (K, N) and sc is None and z is None
+        assert w.is_contiguous()
+    lm = seen[-1]
+    assert lm[1] == L.W_LM_HEAD and (lm[2], lm[3]) == (H, (V + 128 * tp - 1) // (128 * tp) * 128) and lm[4].dtype == T
+    fmts = [a[0]._obj.weight_format for n, a in dry.calls if n == "b200_linear_prepare"]
+    assert fmts[:-1] == [L.FMT_U4 if int4 else L.FMT_FP8_COL if family == "fp8" else L.FMT_DENSE] * (4 * spec.layers)
+    ids = [a[2] for n, a in dry.calls if n == "b200_model_set_tensor"]
+    assert ids.count(L.T_QKV_BIAS) == (spec.layers if arch == "qwen2" else 0)
+    assert ids.count(L.T_Q_NORM) == ids.count(L.T_K_NORM) == (spec.layers if arch == "qwen3" else 0)
+    cfgc = [a[1]._obj for n, a in dry.calls if n == "b200_model_create"][-1]
+    assert (cfgc.num_heads, cfgc.num_kv_heads, cfgc.inter_size, cfgc.tp_size, cfgc.tp_rank) == (hq, hkv, it, tp, tp - 1)
+    assert cfgc.dtype == (1 if family == "fp8" else 0) and cfgc.vocab == lm[3] and cfgc.embedding_rows == V
