@@ -307,3 +307,39 @@ def test_checkpoint_directory_to_c_abi_upload(dry, monkeypatch, tmp_path, arch, 
     cfgc = [a[1]._obj for n, a in dry.calls if n == "b200_model_create"][-1]
     assert (cfgc.num_heads, cfgc.num_kv_heads, cfgc.inter_size, cfgc.tp_size, cfgc.tp_rank) == (hq, hkv, it, tp, tp - 1)
     assert cfgc.dtype == (1 if family == "fp8" else 0) and cfgc.vocab == lm[3] and cfgc.embedding_rows == V
+
+
+def test_pipeline_over_a_checkpoint_directory(dry, monkeypatch, tmp_path):
+    """lmdeploy_b200.pipeline(<dir>) -> TurboMind.from_pretrained -> load_hf_checkpoint (hf_overrides applied) -> engine ->
+    infer, without a device: the recorder's step leaves token 0 in the output buffer, so every sampled id is 0."""
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from safetensors.torch import save_file
+    from test_loader_cpu import make_checkpoint
+    import lmdeploy_b200
+    import lmdeploy_b200.turbomind.runtime as RT
+    cfg, t, _ = make_checkpoint("llama", "awq", seed=1)
+    (tmp_path / "config.json").write_text(json.dumps(dict(cfg, max_position_embeddings=96)))
+    save_file({k: v.contiguous() for k, v in t.items()}, str(tmp_path / "model.safetensors"))
+
+    class CpuModel(RT.DecodeModel):
+        def __init__(self, spec, **kw):
+            super().__init__(spec, device="cpu", **kw)
+    monkeypatch.setattr(RT, "DecodeModel", CpuModel)
+    ecfg = lmdeploy_b200.TurbomindEngineConfig(max_batch_size=8, cache_max_entry_count=16, quant_policy=8,
+                                               hf_overrides={"rope_scaling": {"type": "dynamic", "factor": 2.0}})
+    with lmdeploy_b200.pipeline(str(tmp_path), ecfg) as pipe:
+        eng = pipe.engine
+        assert eng.spec.rope.type == "dynamic" and eng.session_len == 96 and eng.max_batch == 8 and eng.pool.num_blocks == 16
+        r = pipe([[5, 6, 7]], lmdeploy_b200.GenerationConfig(max_new_tokens=3))[0]
+        assert (r.finish_reason, r.token_ids, r.input_token_len, r.generate_token_len) == ("length", [0, 0, 0], 3, 3)
+        # eos ids of generation_config.json end the turn and stay out of the response
+        pipe.hf_gen_cfg = {"eos_token_id": [0, 9]}
+        r = pipe([5, 6, 7], lmdeploy_b200.GenerationConfig(max_new_tokens=3))
+        assert (r.finish_reason, r.token_ids, r.generate_token_len) == ("stop", [], 0)
+        # a prompt beyond the trained context would need a per-request rope base under dynamic NTK: refused
+        with pytest.raises(NotImplementedError):
+            pipe([list(range(97))], lmdeploy_b200.GenerationConfig(max_new_tokens=1))
+    assert pipe.engine is None
