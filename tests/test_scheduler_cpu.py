@@ -508,7 +508,7 @@ def test_randomized_workloads_agree_with_the_plain_scheduler():
 
     prompt = st.lists(st.integers(0, 5), min_size=1, max_size=22)        # tiny alphabet: many shared prefixes
 
-    @settings(max_examples=120, deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=150, deadline=None, suppress_health_check=list(HealthCheck))
     @given(prompts=st.lists(prompt, min_size=1, max_size=6), data=st.data())
     def run(prompts, data):
         n = len(prompts)
@@ -530,10 +530,12 @@ def test_randomized_workloads_agree_with_the_plain_scheduler():
         pressed = _drive(prompts, max_new, num_blocks=tight, max_batch=max_batch, prefill_chunk=chunk, token_budget=budget,
                          prefix_caching=True, cancel_at=cancel, arrivals=arrivals)
         for i, (gen, why) in pressed.items():
-            if why in ("stop",) or (why == "length" and len(gen) == max_new[i]):
-                assert gen == base[i][0]
+            if cancel is not None and i == cancel[0] and why == "cancel":
+                assert gen == base[i][0][:len(gen)]          # cut short by the cancellation: a prefix
             else:
-                assert gen == base[i][0][:len(gen)]          # cut short (cancelled / out of KV memory): a prefix
+                # every sequence fits the pool on its own, so memory pressure only preempts (the victim refills its
+                # cache later): nobody is cut short, everybody produces exactly the unpressed tokens
+                assert (gen, why) == base[i], (i, gen, why, base[i])
 
     run()
 
