@@ -16,81 +16,13 @@ import torch
 from lmdeploy_b200 import _lib as L
 
 
-class RecordingLib:
-    """Stands in for libb200tm.so.  Every b200_* symbol the real library exports exists here; a call is checked against
-    the declared argtypes (count, and that a pointer parameter never receives a Python float / a scalar parameter never a
-    tensor) and recorded."""
-
-    def __init__(self, real):
-        self.calls = []
-        self._real = real
-        self._handles = 0
-
-    def __getattr__(self, name):
-        if not name.startswith("b200_"):
-            raise AttributeError(name)
-        real_fn = getattr(self._real, name)          # AttributeError if the library has no such symbol
-        argtypes = real_fn.argtypes
-
-        def call(*args):
-            if argtypes is not None:
-                assert len(args) == len(argtypes), (name, len(args), len(argtypes))
-                for a, t in zip(args, argtypes):
-                    if t in (C.c_int, C.c_int64, C.c_size_t):
-                        assert isinstance(a, (int, np.integer)) and not isinstance(a, bool) or isinstance(a, bool), (name, a, t)
-                    elif t is C.c_float:
-                        assert isinstance(a, (int, float)), (name, a, t)
-                    elif t is C.c_void_p:
-                        assert a is None or isinstance(a, (int, C.c_void_p)) or hasattr(a, "_obj"), (name, type(a))
-            self.calls.append((name, args))
-            return self._result(name, args)
-        return call
-
-    def _result(self, name, args):
-        if name == "b200_last_error":
-            return b""
-        if name == "b200_version":
-            return b"recording stand-in sm_100a"
-        if name == "b200_linear_prepared_bytes":
-            d = args[0]._obj
-            per = {0: 2.0, 1: 0.53125, 2: 1.001, 3: 1.03125}[d.weight_format]
-            return int(d.input_dim * d.output_dim * per)
-        if name.endswith("_bytes"):
-            return 4096
-        if name == "b200_model_create":
-            self._handles += 1
-            args[0]._obj.value = 0x1000 * self._handles
-            cfg = args[1]._obj
-            assert 1 <= cfg.max_batch <= 128 and cfg.rope.type in (0, 1, 2, 4, 5) and cfg.rope.dim > 0
-            assert cfg.num_heads % cfg.num_kv_heads == 0 and cfg.head_dim == 128
-            return 0
-        if name == "b200_linear_load_plans":
-            return 0
-        return 0
-
-    def names(self):
-        return [c[0] for c in self.calls]
+from dryrun import RecordingLib, install  # noqa: E402,F401
 
 
 @pytest.fixture
 def dry(monkeypatch, lib):
     """`lib` (conftest) is the real library: loaded on the CPU for its symbol table and argtypes only."""
-    rec = RecordingLib(lib)
-    monkeypatch.setattr(L, "load", lambda: rec)
-    stream = types.SimpleNamespace(cuda_stream=0, synchronize=lambda: None)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: stream)
-    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
-    monkeypatch.setattr(torch.cuda, "device", lambda *a, **k: contextlib.nullcontext())
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a, **k: (1 << 30, 2 << 30))
-    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self, *a, **k: self)
-
-    class Graph:
-        def replay(self):
-            rec.calls.append(("graph.replay", ()))
-    monkeypatch.setattr(torch.cuda, "CUDAGraph", Graph)
-    monkeypatch.setattr(torch.cuda, "graph", lambda g, *a, **k: contextlib.nullcontext())
-    return rec
+    return install(monkeypatch.setattr, lib)
 
 
 def tiny(fmt, **kw):

@@ -3,6 +3,7 @@ decode step from loader-sharded weights, the two per-layer exchanges are real al
 all-gathered.  The result must equal the single-process oracle with TP semantics (rank-ordered sum)."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -167,3 +168,84 @@ def test_engine_leader_publishes_every_step_and_followers_mirror_the_kv_pool():
     assert steps0 == steps1 > 0
     assert store0 == store1                       # the follower wrote exactly what the leader wrote, where it wrote it
     assert all(len(g) == 4 for g in generated)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# tp_engine.launch() itself, in two processes, with the device replaced by the dry-run stand-ins (tests/dryrun.py):
+# the torchrun entry point a 2-GPU run will execute -- rendezvous, per-rank model shard, KV pool sizing by the
+# all-reduced minimum, leader drives generation, followers serve and return when the leader closes.
+# ---------------------------------------------------------------------------------------------------------------
+def _launch_worker(rank, world, port, q):
+    try:
+        os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                          MASTER_PORT=str(port))
+        import torch
+        import torch.distributed as dist
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from lmdeploy_b200 import _lib as L
+        import dryrun
+        real = L.load()
+        rec = dryrun.install(setattr, real)
+        import lmdeploy_b200.turbomind.runtime as RT
+        import lmdeploy_b200.turbomind.tp as TP
+        from lmdeploy_b200.messages import GenerationConfig, TurbomindEngineConfig
+        from lmdeploy_b200.turbomind.engine import batched_generate
+        from lmdeploy_b200.turbomind.specs import ModelSpec
+        from lmdeploy_b200.turbomind import tp_engine
+
+        class CpuModel(RT.DecodeModel):
+            def __init__(self, spec, **kw):
+                super().__init__(spec, device="cpu", **kw)
+
+        class NoLinks:                       # the NVLink communicator needs peers' device memory: not part of this dry run
+            def __init__(self, model, rank, world):
+                self.closed = False
+
+            def close(self):
+                self.closed = True
+        RT.DecodeModel = CpuModel
+        TP.TpGroup = NoLinks
+        init = dist.init_process_group
+        dist.init_process_group = lambda backend, **kw: init("gloo", rank=rank, world_size=world)
+        # ranks see different amounts of free memory: the pool must be sized by the smallest
+        torch.cuda.mem_get_info = lambda *a, **k: ((3 + rank) << 24, 1 << 30)
+        spec = ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1000, 1e4, weight_format="awq")
+        cfg = TurbomindEngineConfig(tp=world, max_batch_size=4, session_len=64, cache_max_entry_count=0.5, quant_policy=8)
+        eng = tp_engine.launch(spec, cfg)
+        steps = rec.names().count("b200_model_decode_step") + rec.names().count("graph.replay")
+        if rank == 0:
+            blocks = eng.pool.num_blocks
+            seqs = batched_generate(eng, [[1, 2, 3], [4, 5]], GenerationConfig(max_new_tokens=3, ignore_eos=True))
+            steps = rec.names().count("b200_model_decode_step") + rec.names().count("graph.replay")
+            eng.close()
+            q.put((rank, "ok", [s.generated for s in seqs], steps, blocks, eng._tp is None))
+        else:
+            q.put((rank, "ok", eng, steps, None, None))
+        dist.destroy_process_group()
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "error", traceback.format_exc(), 0, None, None))
+
+
+def test_tp_engine_launch_entry_point_in_two_processes():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_launch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in range(2):
+        r = q.get(timeout=240)
+        out[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+    assert out[0][1] == "ok", out[0][2]
+    assert out[1][1] == "ok", out[1][2]
+    assert out[0][2] == [[0, 0, 0], [0, 0, 0]]                   # the stand-in step leaves id 0 in the output buffer
+    assert out[1][2] is None                                     # followers get no engine back
+    assert out[0][3] == out[1][3] and out[0][3] >= 5             # every step the leader ran, the follower ran too
+    layer_bytes = 1 * 2 * 64 * (128 + 4) * 2                     # 1 kv head per rank, K|V, 64 tokens, int8 + params; 2 layers
+    assert out[0][4] == int((3 << 24) * 0.5) // layer_bytes      # sized by the rank with the least free memory
+    assert out[0][5] is True                                     # close() released the communicator
