@@ -11,10 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import dryrun  # noqa: E402
-from oracle.numerics import BF16, F16  # noqa: E402
 
-# one representative argument set per parametrised test (names as in the test signatures)
-ARGS = dict(shape=(1024, 256), m=3, dtype=F16, kv_bits=8, fmt="awq", heads=(8, 2), dim=4096)
 FACTORIES = ("tensor", "zeros", "ones", "empty", "arange", "randn", "randint", "full", "zeros_like", "empty_like")
 
 
@@ -86,24 +83,49 @@ def cpu_as_cuda(monkeypatch, lib):
     return rec
 
 
-def _pending_tests():
-    os.environ.setdefault("B200_RUN_UNVERIFIED", "")
-    import test_zz_pending_gpu as P
-    return [(n, f) for n, f in sorted(vars(P).items()) if n.startswith("test_") and callable(f)]
+GPU_MODULES = ("test_zz_pending_gpu", "test_decode_attention_gpu", "test_linear_gpu", "test_norm_gpu", "test_ref_attention_gpu",
+               "test_decode_step_gpu")          # test_tp_gpu spawns NCCL ranks: its host side is tests/test_tp_gloo.py
 
 
-@pytest.mark.parametrize("name", [n for n, _ in _pending_tests()])
-def test_pending_gpu_test_body_reaches_its_numeric_checks(cpu_as_cuda, lib, monkeypatch, name):
-    fn = dict(_pending_tests())[name]
-    kwargs = {}
+def _gpu_tests():
+    out = {}
+    for mod in GPU_MODULES:
+        m = __import__(mod)
+        for n, f in sorted(vars(m).items()):
+            if n.startswith("test_") and inspect.isfunction(f) and f.__module__ == mod:
+                out[f"{mod}::{n}"] = f
+    return out
+
+
+def _first_parameters(fn):
+    """The first value of every @pytest.mark.parametrize of the test."""
+    kw = {}
+    for mark in getattr(fn, "pytestmark", []):
+        if mark.name == "parametrize":
+            names = [x.strip() for x in mark.args[0].split(",")] if isinstance(mark.args[0], str) else list(mark.args[0])
+            first = mark.args[1][0]
+            first = getattr(first, "values", first)           # pytest.param(...)
+            kw.update(zip(names, first if len(names) > 1 else [first]))
+    return kw
+
+
+@pytest.mark.parametrize("name", sorted(_gpu_tests()))
+def test_gpu_test_body_reaches_its_numeric_checks(cpu_as_cuda, lib, monkeypatch, name):
+    """Pending AND verified GPU tests: the verified ones are what the round-end run executes with -x, so a host-side
+    regression in code they share with the product (runtime, harness) must be caught here, without a GPU."""
+    fn = _gpu_tests()[name]
+    name = name.split("::")[1]
+    kwargs = _first_parameters(fn)
     for p in inspect.signature(fn).parameters:
+        if p in kwargs:
+            continue
         if p == "lib":
             from lmdeploy_b200 import _lib as L
             kwargs[p] = L.load()                      # the recording stand-in
+        elif p == "ref":
+            kwargs[p] = cpu_as_cuda.ref               # fixture of test_ref_attention_gpu: the reference library
         elif p == "monkeypatch":
             kwargs[p] = monkeypatch
-        elif p in ARGS:
-            kwargs[p] = ARGS[p]
         else:
             pytest.fail(f"{name}: no dry-run value for parameter {p!r}")
     try:
