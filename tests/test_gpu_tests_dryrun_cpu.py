@@ -151,3 +151,12 @@ def test_gpu_test_body_reaches_its_numeric_checks(cpu_as_cuda, lib, monkeypatch,
         assert "ref_qk_rmsnorm" in calls
     if name == "test_residual_rmsnorm_matches_reference_kernel":
         assert "ref_bias_residual_rmsnorm" in calls
+
+
+def test_graft_entry_smoke_body(cpu_as_cuda, lib):
+    """__graft_entry__.smoke() -- the first thing the round-end GPU run executes -- up to its first numeric check."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as G
+    with pytest.raises(AssertionError, match="KV cache bytes differ|differs from the oracle"):
+        G.smoke()
+    assert "b200_decode_attention" in cpu_as_cuda.names()
