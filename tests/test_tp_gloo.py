@@ -249,3 +249,93 @@ def test_tp_engine_launch_entry_point_in_two_processes():
     layer_bytes = 1 * 2 * 64 * (128 + 4) * 2                     # 1 kv head per rank, K|V, 64 tokens, int8 + params; 2 layers
     assert out[0][4] == int((3 << 24) * 0.5) // layer_bytes      # sized by the rank with the least free memory
     assert out[0][5] is True                                     # close() released the communicator
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bench.py under torchrun (N > 1): rank 0 prints the one JSON line, timing is the maximum over ranks
+# ---------------------------------------------------------------------------------------------------------------
+def _bench_worker(rank, world, port, q):
+    try:
+        os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                          MASTER_PORT=str(port))
+        import contextlib
+        import io
+        import types
+        import torch
+        import torch.distributed as dist
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, os.path.join(root, "tests"))
+        sys.path.insert(0, root)
+        from lmdeploy_b200 import _lib as L
+        import dryrun
+        dryrun.install(setattr, L.load())
+        import bench
+        import lmdeploy_b200.turbomind as TM
+        import lmdeploy_b200.turbomind.runtime as RT
+        import lmdeploy_b200.turbomind.tp as TP
+        from lmdeploy_b200.turbomind.specs import ModelSpec
+
+        class CpuModel(RT.DecodeModel):
+            def __init__(self, spec, **kw):
+                super().__init__(spec, device="cpu", **kw)
+
+        class NoLinks:
+            def __init__(self, *a, **k):
+                pass
+
+            def close(self):
+                pass
+
+        class Event:
+            def __init__(self, *a, **k):
+                pass
+
+            def record(self, *a):
+                pass
+
+            def elapsed_time(self, other):
+                return 2.0 + rank                      # rank 1 is slower: the line must report ITS time
+        TM.DecodeModel, TP.TpGroup, torch.cuda.Event = CpuModel, NoLinks, Event
+        for name in ("tensor", "zeros", "arange", "randn", "randint", "empty"):
+            orig = getattr(torch, name)
+            setattr(torch, name, lambda *a, _o=orig, **k: _o(*a, **{**k, "device": "cpu"} if "device" in k else k))
+        gen = torch.Generator
+        torch.Generator = lambda device=None: gen()
+        init = dist.init_process_group
+        dist.init_process_group = lambda backend, **kw: init("gloo", rank=rank, world_size=world)
+        TM.SPECS["tiny"] = ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1000, 1e4, weight_format="awq")
+        bench.CONFIGS["c2"] = ("tiny", 4, 100, 8)
+        args = types.SimpleNamespace(gpus=world, steps=4, warmup=3, impl="b200", config="c2", no_graph=False,
+                                     no_cpu_baseline=False, attn_iters=2)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            bench.run_b200(args)
+        q.put((rank, "ok", buf.getvalue()))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "error", traceback.format_exc()))
+
+
+def test_bench_under_torchrun_prints_one_line_with_the_slowest_rank_time():
+    import json
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bench_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = {}
+    for _ in range(2):
+        r = q.get(timeout=300)
+        out[r[0]] = r
+    for p in procs:
+        p.join(timeout=60)
+    assert out[0][1] == "ok", out[0][2]
+    assert out[1][1] == "ok", out[1][2]
+    lines = [ln for ln in out[0][2].splitlines() if ln.startswith("{")]
+    assert len(lines) == 1 and not [ln for ln in out[1][2].splitlines() if ln.startswith("{")]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["config"]["parallelism"] == "tp2" and d["scaling"] == "strong"
+    assert d["ms_per_step"] == pytest.approx(3.0 / 4) and d["value"] == pytest.approx(4 * 4 / 3e-3)      # max over ranks
+    assert "cpu_baseline" not in d and d["e2e"]["value"] > 0 and "clocks" in d
