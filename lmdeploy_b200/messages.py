@@ -222,6 +222,28 @@ class TurbomindEngineConfig:
             raise ConfigError("invalid quant_policy (0, 4, 8)")
         if self.cache_max_entry_count <= 0:
             raise ConfigError("invalid cache_max_entry_count")
+        # the reference's remaining checks (lmdeploy/messages.py:345-367)
+        if self.rope_scaling_factor < 0:
+            raise ConfigError("invalid rope_scaling_factor")
+        if self.max_prefill_token_num < 0:
+            raise ConfigError("invalid max_prefill_token_num")
+        if self.num_tokens_per_iter < 0:
+            raise ConfigError("invalid num_tokens_per_iter")
+        if self.cache_prompt not in ("all", "auto"):
+            raise ConfigError("invalid cache_prompt")
+        if self.cache_generation not in ("all", "auto", "none"):
+            raise ConfigError("invalid cache_generation")
+        if self.cache_checkpoint_interval <= 0:
+            raise ConfigError("invalid cache_checkpoint_interval")
+        if self.cache_prompt_boundary_skip < 1:
+            raise ConfigError("invalid cache_prompt_boundary_skip")
+        if self.async_ not in (0, 1):
+            raise ConfigError("async_ must be 0 (disabled) or 1 (enabled)")
+        # options with an effect this path does not implement: refused, not ignored
+        if self.empty_init:
+            raise NotImplementedError("empty_init (weights supplied later, e.g. by an RL trainer) is outside the hot-path scope")
+        if self.devices is not None and list(self.devices) != list(range(self.tp)):
+            raise NotImplementedError("devices: select GPUs with CUDA_VISIBLE_DEVICES; ranks use devices 0..tp-1")
         if self.cache_block_seq_len % 64:
             raise ValueError("cache_block_seq_len must be a multiple of 64")
         if self.max_batch_size is not None and not (1 <= self.max_batch_size <= 128):

@@ -111,6 +111,7 @@ class TurboMind:
             cfg = engine_config or TurbomindEngineConfig()
             spec, model, eos = load_hf_checkpoint(pretrained_model_name_or_path, quant_policy=cfg.quant_policy,
                                                   block_len=cfg.cache_block_seq_len, hf_overrides=cfg.hf_overrides,
+                                                  model_format=cfg.model_format,
                                                   max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE)
             return cls(spec, cfg, model=model, eos_id=eos, **kw)
         raise FileNotFoundError(pretrained_model_name_or_path)

@@ -317,11 +317,17 @@ def deep_merge(base, override):
     return base
 
 
-def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0, hf_overrides=None):
+def load_hf_checkpoint(path, *, quant_policy=0, block_len=64, max_batch=64, tp=1, rank=0, hf_overrides=None, model_format=None):
     from .runtime import DecodeModel, _TORCH_T
     cfg, tensors = read_checkpoint(path)
     if hf_overrides:
         deep_merge(cfg, hf_overrides)
+    method = (cfg.get("quantization_config") or {}).get("quant_method")
+    if method is not None and model_format not in (None, method):
+        # get_tm_config: the user's model_format must agree with the checkpoint's own quantization_config (converter.py)
+        raise ValueError(f'mismatched quant method: user input "{model_format}" vs model quant_config "{method}"')
+    if method is None and model_format not in (None, "hf"):
+        raise ValueError(f'model_format "{model_format}" but the checkpoint carries no quantization_config')
     spec = spec_from_config(cfg)
     spec = with_checkpoint_biases(spec, tensors)
     import dataclasses

@@ -71,7 +71,7 @@ def launch(spec_or_path, engine_config=None, *, seed=0):
     if isinstance(spec_or_path, str) and spec_or_path not in SPECS:
         from .loader import load_hf_checkpoint
         spec, model, eos = load_hf_checkpoint(spec_or_path, quant_policy=cfg.quant_policy, block_len=cfg.cache_block_seq_len,
-                                              hf_overrides=cfg.hf_overrides,
+                                              hf_overrides=cfg.hf_overrides, model_format=cfg.model_format,
                                               max_batch=cfg.max_batch_size or DEFAULT_MAX_BATCH_SIZE, tp=world, rank=rank)
     else:
         spec = SPECS[spec_or_path] if isinstance(spec_or_path, str) else spec_or_path

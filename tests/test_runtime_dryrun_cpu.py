@@ -275,3 +275,26 @@ def test_pipeline_over_a_checkpoint_directory(dry, monkeypatch, tmp_path):
         with pytest.raises(NotImplementedError):
             pipe([list(range(97))], lmdeploy_b200.GenerationConfig(max_new_tokens=1))
     assert pipe.engine is None
+
+
+def test_model_format_must_agree_with_the_checkpoint(dry, monkeypatch, tmp_path):
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from safetensors.torch import save_file
+    from test_loader_cpu import make_checkpoint
+    import lmdeploy_b200.turbomind.runtime as RT
+    from lmdeploy_b200.turbomind import loader as LD
+    cfg, t, _ = make_checkpoint("llama", "awq", seed=1)
+    (tmp_path / "config.json").write_text(json.dumps(cfg))
+    save_file({k: v.contiguous() for k, v in t.items()}, str(tmp_path / "model.safetensors"))
+
+    class CpuModel(RT.DecodeModel):
+        def __init__(self, spec, **kw):
+            super().__init__(spec, device="cpu", **kw)
+    monkeypatch.setattr(RT, "DecodeModel", CpuModel)
+    with pytest.raises(ValueError, match="mismatched quant method"):
+        LD.load_hf_checkpoint(str(tmp_path), model_format="gptq")
+    spec, _, _ = LD.load_hf_checkpoint(str(tmp_path), model_format="awq", max_batch=4)
+    assert spec.checkpoint_format == "awq"

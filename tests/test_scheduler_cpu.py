@@ -826,3 +826,16 @@ def test_dynamic_ntk_prompts_beyond_the_trained_context_are_refused_not_mis_rota
         inst._submit(2, list(range(9)), GenerationConfig(max_new_tokens=2))
     p.engine.spec.rope = RopeSpec(type="dynamic", dim=128, base=1e6, factor=1.0, max_position_embeddings=8)
     inst._submit(3, list(range(9)), GenerationConfig(max_new_tokens=2))                # factor <= 1: the base never changes
+
+
+def test_engine_config_validation_and_refusals():
+    import lmdeploy_b200.messages as M
+    for kw in (dict(rope_scaling_factor=-1.0), dict(max_prefill_token_num=-1), dict(num_tokens_per_iter=-2), dict(cache_prompt="x"),
+               dict(cache_generation="some"), dict(cache_checkpoint_interval=0), dict(cache_prompt_boundary_skip=0),
+               dict(async_=2), dict(dtype="float32"), dict(tp=0)):
+        with pytest.raises(AssertionError):
+            M.TurbomindEngineConfig(**kw)
+    for kw in (dict(empty_init=True), dict(devices=[3]), dict(tp=2, devices=[0, 2])):
+        with pytest.raises(NotImplementedError):
+            M.TurbomindEngineConfig(**kw)
+    M.TurbomindEngineConfig(tp=2, devices=[0, 1], async_=0, use_logn_attn=True, rope_scaling_factor=2.0)     # inert in the reference too
