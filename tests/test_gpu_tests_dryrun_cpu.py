@@ -12,7 +12,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import dryrun  # noqa: E402
 
-FACTORIES = ("tensor", "zeros", "ones", "empty", "arange", "randn", "randint", "full", "zeros_like", "empty_like")
+FACTORIES = ("tensor", "zeros", "ones", "empty", "arange", "randn", "rand", "randint", "full", "zeros_like", "empty_like")
 
 
 @pytest.fixture
@@ -160,3 +160,16 @@ def test_graft_entry_smoke_body(cpu_as_cuda, lib):
     with pytest.raises(AssertionError, match="KV cache bytes differ|differs from the oracle"):
         G.smoke()
     assert "b200_decode_attention" in cpu_as_cuda.names()
+
+
+def test_reference_gemm_bench_tool_body(cpu_as_cuda, lib, capsys):
+    """tools/ref_gemm_bench.py (a step of the first GPU call of a round, and bench.py's optional reference-GEMM leg)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import ref_gemm_bench
+    res = ref_gemm_bench.measure(4, 2, [("wo", 2048, 4096, 0), ("w1w3", 2048, 4096, 1)], verbose=True)
+    assert set(res) == {"wo", "w1w3"} and set(res["wo"]) >= {"reference_us", "ours_us", "weight_bytes", "max_abs_diff"}
+    assert res["wo"]["weight_bytes"] == 2048 * 4096 // 2 + 2048 // 128 * 4096 * 4
+    assert "ours/ref speed-up" in capsys.readouterr().out
+    names = cpu_as_cuda.names()
+    assert "b200_pack_activations" in names and "b200_linear_forward_packed" in names
+    assert cpu_as_cuda.ref.calls.count("ref_linear_forward") >= 2 * (1 + 3 + 2 + 1)
