@@ -94,6 +94,12 @@ class Pipeline:
             r = self._closing(i, s, g, len(shown))
             r.token_ids = list(shown) + r.token_ids
             r.text = self._decode(shown, g) + r.text
+            n = len(r.token_ids)           # entries of a hidden stop token are dropped with it (async_engine.py:741-748)
+            if s.want_logprobs:
+                r.logprobs = s.logprobs[:n]
+            if s.want_logits and n:
+                import torch
+                r.logits = torch.stack(s.logits[:n])
             out.append(r)
         return out[0] if single else out
 
@@ -128,8 +134,15 @@ class Pipeline:
                     delta = ""
                 else:
                     text[i] = full
-                yield Response(text=delta, generate_token_len=shown[i], input_token_len=len(s.prompt), finish_reason=None,
-                               token_ids=list(held[i]), index=i, cached_tokens=s.reused_tokens)
+                r = Response(text=delta, generate_token_len=shown[i], input_token_len=len(s.prompt), finish_reason=None,
+                             token_ids=list(held[i]), index=i, cached_tokens=s.reused_tokens)
+                lo = shown[i] - len(held[i])
+                if s.want_logprobs:
+                    r.logprobs = s.logprobs[lo:shown[i]]
+                if s.want_logits:
+                    import torch
+                    r.logits = torch.stack(s.logits[lo:shown[i]])
+                yield r
                 held[i] = []
             if s.finished:
                 yield self._closing(i, s, g, shown.get(i, 0))

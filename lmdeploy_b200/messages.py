@@ -16,6 +16,7 @@ class QuantPolicy(enum.IntEnum):
 # max_batch_size left unset: the reference asks get_max_batch_size('cuda') (lmdeploy/utils.py:394-417), whose table has no
 # entry for a B200 and answers 128 (tests/golden/ref_engine_defaults.json) -- also the row limit of the decode step
 DEFAULT_MAX_BATCH_SIZE = 128
+MAX_LOGPROBS = 1024            # lmdeploy/turbomind/turbomind.py MAX_LOGPROBS
 
 
 class ConfigError(ValueError, AssertionError):
@@ -77,7 +78,6 @@ class GenerationConfig:
 
     _UNSUPPORTED = {"response_format": None, "logits_processors": None, "output_last_hidden_state": None, "return_ppl": False,
                     "with_cache": False, "preserve_cache": False, "migration_request": None, "return_routed_experts": False,
-                    "logprobs": None, "output_logits": None,
                     # acts on the logits before the argmax whatever do_sample says, so it cannot be ignored
                     "min_new_tokens": None}
 
@@ -141,6 +141,13 @@ class GenerationConfig:
         if self.do_sample and (self.top_k != 1 or self.repetition_penalty != 1.0):
             raise NotImplementedError("lmdeploy_b200 implements the greedy decode path: do_sample=True needs top_k=1 and "
                                       "repetition_penalty=1.0")
+        # extra outputs read from the step's logits buffer (one GPU): the sampled row's logits / its top log-probabilities
+        if self.output_logits not in (None, "generation"):
+            raise NotImplementedError("output_logits='all' needs the logits of every prompt position; 'generation' is supported")
+        if self.logprobs is not None:
+            if self.logprobs < 1:
+                raise ConfigError("logprobs must be a positive integer")
+            self.logprobs = min(int(self.logprobs), MAX_LOGPROBS)       # the reference clips the same way (turbomind.py)
         if self.repetition_ngram_size:
             raise NotImplementedError("GenerationConfig.repetition_ngram_size is not supported on the greedy decode hot path")
         for name, default in self._UNSUPPORTED.items():

@@ -132,7 +132,32 @@ class TurboMind:
             self.channel.publish(st)
         out = self._execute(st)
         cu_q = st["cu_q_len"]
-        return sched.update(batch, [out[cu_q[i + 1] - 1] for i in range(len(batch))])   # sample = last row of each sequence
+        rows = [cu_q[i + 1] - 1 for i in range(len(batch))]                              # sample = last row of each sequence
+        events = sched.update(batch, [out[r] for r in rows])
+        if any(s.want_logits or s.want_logprobs for s in batch):
+            self._collect_extras(batch, rows, events, st["token_num"])
+        return events
+
+    def _collect_extras(self, batch, rows, events, token_num):
+        """output_logits='generation' / logprobs=k: for every token accepted in this step, the fp32 logits of the row it was
+        sampled from and/or {token id: log-probability} of the k most likely ids plus the sampled one -- what the
+        reference returns (turbomind.py _get_logits / _get_logprobs).  Read from the step's logits buffer (T, one GPU)."""
+        row_of = {id(s): r for s, r in zip(batch, rows)}
+        lg = None
+        for s, tok in events:
+            if tok is None or not (s.want_logits or s.want_logprobs):
+                continue
+            if lg is None:
+                lg = self.model.logits(token_num)[:, :self.spec.vocab].float()
+            row = lg[row_of[id(s)]]
+            if s.want_logits:
+                s.logits.append(row.cpu())
+            if s.want_logprobs:
+                lp = torch.log_softmax(row, -1)
+                top = torch.topk(lp, min(s.want_logprobs, lp.numel()))
+                d = {int(i): float(v) for v, i in zip(top.values.tolist(), top.indices.tolist())}
+                d[int(tok)] = float(lp[int(tok)])
+                s.logprobs.append(d)
 
     def serve_follower(self):
         """Tensor-parallel rank > 0: execute the steps the leader publishes until it shuts the channel down.  Every rank
@@ -223,6 +248,9 @@ class TurboMindInstance:
         budget = g.max_new_tokens if g.max_new_tokens is not None else 1 << 30
         seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=budget,
                        stop_token_ids=list(g.stop_token_ids or []), ignore_eos=g.ignore_eos, eos_id=self.engine.eos_id)
+        seq.want_logits, seq.want_logprobs = g.output_logits == "generation", int(g.logprobs or 0)
+        if (seq.want_logits or seq.want_logprobs) and getattr(self.engine, "channel", None) is not None:
+            raise NotImplementedError("logits / logprobs outputs under tensor parallelism (the logits are vocabulary-sharded)")
         self.engine.scheduler.add(seq)
         return seq
 
@@ -242,10 +270,19 @@ class TurboMindInstance:
         while not seq.finished:
             self.engine.step()
             if len(seq.generated) > sent and not seq.finished:
-                new, sent = seq.generated[sent:], len(seq.generated)
-                yield EngineOutput(ResponseType.SUCCESS, list(new), sent)
+                new, lo, sent = seq.generated[sent:], sent, len(seq.generated)
+                yield EngineOutput(ResponseType.SUCCESS, list(new), sent, **self._extras(seq, lo, sent))
         yield EngineOutput(ResponseType.FINISH if seq.finish_reason != "cancel" else ResponseType.CANCEL,
-                           list(seq.generated[sent:]), len(seq.generated))
+                           list(seq.generated[sent:]), len(seq.generated), **self._extras(seq, sent, len(seq.generated)))
+
+    @staticmethod
+    def _extras(seq, lo, hi):
+        out = {}
+        if seq.want_logprobs:
+            out["logprobs"] = seq.logprobs[lo:hi]
+        if seq.want_logits and hi > lo:
+            out["logits"] = torch.stack(seq.logits[lo:hi])
+        return out
 
     async def async_stream_infer(self, session_id, input_ids, gen_config: GenerationConfig = None, **kw):
         for out in self.stream_infer(session_id, input_ids, gen_config):

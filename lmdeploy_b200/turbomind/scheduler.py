@@ -47,6 +47,10 @@ class Sequence:
     step_tokens: int = 1          # tokens this sequence feeds in the step being formed / executed
     error: Optional[str] = None   # why the request was rejected (finish_reason 'error')
     preemptions: int = 0          # times this sequence lost its blocks to an older one and had to refill its cache
+    want_logits: bool = False     # GenerationConfig.output_logits == 'generation': keep the sampled row's logits per token
+    want_logprobs: int = 0        # GenerationConfig.logprobs: keep that many top log-probabilities per token
+    logits: List = field(default_factory=list)
+    logprobs: List = field(default_factory=list)
     chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
 
     def token_at(self, pos):

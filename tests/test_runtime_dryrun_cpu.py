@@ -298,3 +298,44 @@ def test_model_format_must_agree_with_the_checkpoint(dry, monkeypatch, tmp_path)
         LD.load_hf_checkpoint(str(tmp_path), model_format="gptq")
     spec, _, _ = LD.load_hf_checkpoint(str(tmp_path), model_format="awq", max_batch=4)
     assert spec.checkpoint_format == "awq"
+
+
+def test_logits_and_logprobs_outputs(dry, monkeypatch):
+    """output_logits='generation' / logprobs=k: the engine reads the row each accepted token was sampled from out of the
+    step's logits buffer (stubbed here) -- fp32 logits over the REAL vocabulary, {id: logprob} of the top k plus the
+    sampled id; the pipeline drops the entries of a hidden stop token together with the token."""
+    from lmdeploy_b200.api import Pipeline
+    from lmdeploy_b200.messages import GenerationConfig, TurbomindEngineConfig
+    from lmdeploy_b200.turbomind.engine import TurboMind, TurboMindInstance
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+    model = DecodeModel(tiny("awq"), quant_policy=8, max_batch=8, device="cpu")
+    model.load_synthetic(seed=0)
+    eng = TurboMind(tiny("awq"), TurbomindEngineConfig(max_batch_size=8, session_len=64, cache_max_entry_count=16, quant_policy=8),
+                    model=model)
+    buf = (torch.arange(model.vocab_local, dtype=torch.float32)[None] * 0.01 + torch.arange(8, dtype=torch.float32)[:, None]).half()
+    monkeypatch.setattr(model, "logits", lambda n: buf[:n])
+    p = Pipeline.__new__(Pipeline)
+    p.engine, p.tokenizer = eng, None
+    cfg = GenerationConfig(max_new_tokens=3, ignore_eos=True, output_logits="generation", logprobs=2)
+    r, plain = p.infer([[5, 6, 7], [8, 9]], [cfg, GenerationConfig(max_new_tokens=2, ignore_eos=True)])
+    assert plain.logits is None and plain.logprobs is None
+    assert tuple(r.logits.shape) == (3, 1000) and r.logits.dtype == torch.float32          # the real vocabulary, not the padded one
+    assert torch.equal(r.logits[0], buf[0, :1000].float())                                 # sequence 0 samples from row 0
+    assert len(r.logprobs) == 3 and all(set(d) == {999, 998, 0} for d in r.logprobs)       # top-2 of an increasing row + sampled id 0
+    want = torch.log_softmax(buf[0, :1000].float(), -1)
+    assert r.logprobs[0][999] == pytest.approx(float(want[999])) and r.logprobs[0][0] == pytest.approx(float(want[0]))
+    # streamed: every content chunk carries the entries of its own tokens
+    chunks = list(p.stream_infer([[5, 6, 7]], gen_config=cfg))
+    assert [len(c.logprobs) for c in chunks[:-1]] == [1, 1, 1] and all(tuple(c.logits.shape) == (1, 1000) for c in chunks[:-1])
+    # a stop token is hidden with its entries (the recorder samples id 0, declared a stop id here)
+    r = p.infer([[5, 6, 7]], GenerationConfig(max_new_tokens=3, stop_token_ids=[0], output_logits="generation", logprobs=1))[0]
+    assert (r.finish_reason, r.token_ids, r.logprobs, r.logits) == ("stop", [], [], None)
+    # engine-level outputs, and the refusals
+    outs = list(TurboMindInstance(eng).stream_infer(77, [5, 6], cfg))
+    assert [len(o.logprobs) for o in outs] == [1, 1, 1] or sum(len(o.logprobs) for o in outs) == 3
+    with pytest.raises(NotImplementedError):
+        GenerationConfig(output_logits="all")
+    assert GenerationConfig(logprobs=5000).logprobs == 1024
+    eng.channel = object()
+    with pytest.raises(NotImplementedError):
+        TurboMindInstance(eng)._submit(78, [1, 2], cfg)

@@ -562,7 +562,8 @@ def test_config_keyword_surface_matches_the_reference():
         with pytest.raises(NotImplementedError):
             M.TurbomindEngineConfig(**kw)
     for kw in (dict(response_format={"type": "json_schema"}), dict(logits_processors=[print]), dict(return_ppl=True),
-               dict(logprobs=5), dict(repetition_ngram_size=3, repetition_ngram_threshold=2)):
+               dict(output_logits="all"), dict(output_last_hidden_state="all"),
+               dict(repetition_ngram_size=3, repetition_ngram_threshold=2)):
         with pytest.raises(NotImplementedError):
             M.GenerationConfig(**kw)
     # the reference's own validation (messages.py:195-205), raised as an error that is both ValueError and AssertionError
