@@ -5,8 +5,6 @@ No arithmetic is checked here (the GPU tests do that); what this catches before 
 mistake the host code can make on its own: a misspelt keyword into a ctypes structure, a tensor of the wrong shape or
 dtype handed to `b200_model_set_*`, a call with the wrong number of arguments (the recorder checks every call against the
 argtypes the binding declares), a buffer that is too small for the step it is given."""
-import contextlib
-import ctypes as C
 import types
 
 import numpy as np
@@ -16,7 +14,7 @@ import torch
 from lmdeploy_b200 import _lib as L
 
 
-from dryrun import RecordingLib, install  # noqa: E402,F401
+from dryrun import install  # noqa: E402
 
 
 @pytest.fixture
