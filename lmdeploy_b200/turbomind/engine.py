@@ -126,7 +126,13 @@ class TurboMind:
         sched = self.scheduler
         batch = sched.schedule()
         if not batch:
+            # a tick may legitimately form no batch (it only retired or preempted); a long run of them with work pending
+            # means the scheduler cannot make progress -- fail loudly instead of spinning in the callers' loops
+            self._idle_ticks = getattr(self, "_idle_ticks", 0) + 1
+            if sched.has_work and self._idle_ticks > 1000:
+                raise RuntimeError(f"scheduler stalled: {sched.metrics()}")
             return []
+        self._idle_ticks = 0
         st = marshal_step(batch)
         if self.channel is not None:
             self.channel.publish(st)
