@@ -49,6 +49,11 @@ def test_model_upload_and_step_calls(dry, fmt, kw):
     # vocabulary padded to the GEMM's 128-column tile
     lm = [a for n, a in dry.calls if n == "b200_linear_prepare"][-1][0]._obj
     assert (lm.input_dim, lm.output_dim) == (512, 1024)
+    # the rope block of a spec without an explicit RopeSpec: the literal the GPU-verified runs were made with
+    r = [a[1]._obj for n, a in dry.calls if n == "b200_model_create"][-1].rope
+    assert (r.type, r.dim, r.base, r.factor, r.max_position_embeddings, r.llama3_low_freq_factor, r.llama3_high_freq_factor,
+            r.llama3_original_max_position_embeddings, r.yarn_attention_factor, r.yarn_beta_fast, r.yarn_beta_slow,
+            r.exact_math) == (1, 128, 1e4, 0.0, 0, 1.0, 4.0, 8192, 1.0, 32.0, 1.0, 0)
     B = 3
     i32 = lambda n: torch.zeros(n, dtype=torch.int32)
     m.decode_step(batch=B, token_ids=i32(B), cu_q_len=i32(B + 1), cu_k_len=i32(B + 1), block_ptrs=torch.zeros(6, dtype=torch.int64),
