@@ -287,9 +287,12 @@ B200_API int b200_comm_allreduce_residual_rmsnorm(b200_comm* comm, void* out, in
                                          const void* hidden_partial, const void* weight, const void* bias, int tokens,
                                          int dim, float eps, int dtype, void* stream);
 /* Vocab-sharded greedy sampling: local argmax per rank, (value, index) pairs exchanged over peer memory,
- * every rank returns the global token id (replaces the logits all-gather of language_model.cc:306-334). */
+ * every rank returns the global token id (replaces the logits all-gather of language_model.cc:306-334).
+ * vocab_per_rank = row stride of the shard (padded); valid_per_rank = how many of this rank's columns are real
+ * vocabulary entries -- pad columns never win (the reference bounds its sampling by vocab_size, not
+ * vocab_size_padded: generation/sampling.cc:132). */
 B200_API int b200_comm_argmax_allgather(b200_comm* comm, int* out_tokens, const void* local_logits, int rows,
-                               int vocab_per_rank, int dtype, void* stream);
+                               int vocab_per_rank, int valid_per_rank, int dtype, void* stream);
 /* plain all-reduce(sum) of a [count] T buffer, in place (AllReduceSum). */
 B200_API int b200_comm_allreduce_sum(b200_comm* comm, void* data, size_t count, int dtype, void* stream);
 

@@ -141,7 +141,7 @@ def load():
     lib.b200_comm_allreduce_residual_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                          C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                                          C.c_int, C.c_void_p]
-    lib.b200_comm_argmax_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+    lib.b200_comm_argmax_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                                C.c_void_p]
     lib.b200_comm_allreduce_sum.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]
     lib.b200_model_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(ModelConfig)]

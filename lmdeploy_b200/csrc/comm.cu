@@ -38,7 +38,7 @@ __device__ __forceinline__ int next_epoch(const Peers& peers)
 {
     __shared__ int s_epoch;
     if (threadIdx.x == 0) {
-        s_epoch = peers.slot_epoch[blockIdx.x] + 1;
+        s_epoch = (int)((unsigned)peers.slot_epoch[blockIdx.x] + 1u);  // wraps modulo 2^32 (epoch_before)
     }
     __syncthreads();
     return s_epoch;
@@ -83,6 +83,13 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p)
     return v;
 }
 
+// Epochs grow by one per launch for the life of the communicator (2 L + 1 launches per step): compare them modulo
+// 2^32 so the waits stay correct when the counter wraps (a plain `flag < epoch` falls through at INT_MIN).
+__device__ __forceinline__ bool epoch_before(int flag, int epoch)
+{
+    return (int)((unsigned)flag - (unsigned)epoch) < 0;
+}
+
 // flag layout in every rank's flag array: [phase(2)][src rank(8)][kFlagSlots]
 __device__ __forceinline__ int* flag_ptr(int* base, int phase, int src)
 {
@@ -98,7 +105,10 @@ __device__ __forceinline__ void arrive_phase_relaxed(const Peers& peers, int ran
         const int r = threadIdx.x;
         st_relaxed_sys(flag_ptr(peers.flags[r], 0, rank) + blockIdx.x, epoch);
         const int* f = flag_ptr(peers.flags[rank], 0, r) + blockIdx.x;
-        while (ld_relaxed_sys(f) < epoch) {}
+        while (epoch_before(ld_relaxed_sys(f), epoch)) {}
+        // the relaxed spin + bar.sync give no system-scope acquire under the PTX memory model: one fence by the
+        // spinning threads orders the payload loads of the whole CTA (after the barrier) behind the observed flags
+        asm volatile("fence.acquire.sys;" ::: "memory");
     }
     __syncthreads();
 }
@@ -111,7 +121,7 @@ __device__ __forceinline__ void barrier_phase(const Peers& peers, int rank, int 
     }
     if (threadIdx.x < world) {
         const int* f = flag_ptr(peers.flags[rank], phase, threadIdx.x) + blockIdx.x;
-        while (ld_acquire_sys(f) < epoch) {}
+        while (epoch_before(ld_acquire_sys(f), epoch)) {}
     }
     __syncthreads();
 }
@@ -247,7 +257,8 @@ __global__ void __launch_bounds__(kBlock) allreduce_sum_kernel(Peers peers, int 
 // vocab-sharded greedy: local argmax (one CTA per row), exchange (value, index), pick global winner
 template<class T>
 __global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int rank, int world, int* out,
-                                                               const T* logits, int rows, int vocab, size_t data_offset)
+                                                               const T* logits, int rows, int vocab, int valid,
+                                                               size_t data_offset)
 {
     pdl_launch_dependents();
     pdl_wait();
@@ -259,7 +270,10 @@ __global__ void __launch_bounds__(1024) argmax_exchange_kernel(Peers peers, int 
     const T*  lp  = logits + (size_t)row * vocab;
     float     bv  = -INFINITY;
     int       bi  = 0x7fffffff;
-    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+    // only the first `valid` columns of this rank's shard are real vocabulary entries; the pad columns up to `vocab`
+    // hold logit 0 (zero lm_head rows) and must not win when every real logit is negative (sampling.cc:132 passes
+    // vocab_size next to vocab_size_padded for the same reason)
+    for (int i = threadIdx.x; i < valid; i += blockDim.x) {
         const float v = Ops::to_f32(lp[i]);
         if (v > bv || (v == bv && i < bi)) {
             bv = v, bi = i;
@@ -429,9 +443,10 @@ extern "C" int b200_comm_allreduce_sum(b200_comm* c, void* data, size_t count, i
 }
 
 extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const void* local_logits, int rows,
-                                          int vocab_per_rank, int dtype, void* stream)
+                                          int vocab_per_rank, int valid_per_rank, int dtype, void* stream)
 {
-    if (!c || !out_tokens || !local_logits || rows <= 0 || rows > kFlagSlots) {
+    if (!c || !out_tokens || !local_logits || rows <= 0 || rows > kFlagSlots || valid_per_rank < 0
+        || valid_per_rank > vocab_per_rank) {
         return fail(B200_ERR_INVALID_ARG, "argmax_allgather: bad arguments (rows <= 128)");
     }
     // (value, index) pairs live in the page behind the two exchange halves
@@ -439,11 +454,12 @@ extern "C" int b200_comm_argmax_allgather(b200_comm* c, int* out_tokens, const v
     if (dtype == B200_DTYPE_F16) {
         launch_k(argmax_exchange_kernel<half>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, c->peers, c->rank, c->world, out_tokens,
                                                                               (const half*)local_logits, rows,
-                                                                              vocab_per_rank, off);
+                                                                              vocab_per_rank, valid_per_rank, off);
     }
     else {
         launch_k(argmax_exchange_kernel<nv_bfloat16>, dim3(rows), dim3(1024), 0, (cudaStream_t)stream, 
-            c->peers, c->rank, c->world, out_tokens, (const nv_bfloat16*)local_logits, rows, vocab_per_rank, off);
+            c->peers, c->rank, c->world, out_tokens, (const nv_bfloat16*)local_logits, rows, vocab_per_rank,
+            valid_per_rank, off);
     }
     return check_launch("argmax_exchange_kernel");
 }

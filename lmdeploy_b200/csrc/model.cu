@@ -101,7 +101,9 @@ extern "C" int b200_model_create(b200_model** out, const b200_model_config* c)
     rc = rc ? rc : alloc(&m->xp, (size_t)MT * c->hidden * es);
     rc = rc ? rc : alloc(&m->qkv, (size_t)MB * qkv_dim * es);
     rc = rc ? rc : alloc(&m->attn_xp, (size_t)MT * c->num_heads * c->head_dim * es);
-    rc = rc ? rc : alloc(&m->o, (size_t)MB * c->hidden * es);
+    // `o` also receives the row-major prefill-attention output of a chunk step ([rows, num_heads * head_dim]), which
+    // is wider than `hidden` for Qwen3-style geometries
+    rc = rc ? rc : alloc(&m->o, (size_t)MB * std::max(c->hidden, c->num_heads * c->head_dim) * es);
     rc = rc ? rc : alloc(&m->act_xp, (size_t)MT * c->inter_size * es);
     rc = rc ? rc : alloc(&m->logits, (size_t)MB * c->vocab * es);
     m->attn_ws_bytes = b200_decode_attention_workspace_bytes(MB, c->num_heads, c->num_kv_heads);
@@ -403,11 +405,14 @@ static int run_step(b200_model* m, const b200_step_inputs* in, int R, bool chunk
     TRY_T(8, b200_linear_forward_packed(&m->lm_head, m->xp, MT, R, m->logits, c.vocab, 0, 0, m->lin_ws, m->lin_ws_bytes,
                                    stream));
     if (in->out_tokens) {
+        // c.vocab is the per-rank lm_head width padded to a multiple of 128; only the columns below the real vocabulary
+        // size (= rows of the embedding table) may be sampled (sampling.cc:132: vocab_size, not vocab_size_padded)
+        const int valid = std::max(0, std::min(c.vocab, c.embedding_rows - c.tp_rank * c.vocab));
         if (m->comm && c.tp_size > 1) {
-            TRY_T(9, b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, R, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_comm_argmax_allgather(m->comm, in->out_tokens, m->logits, R, c.vocab, valid, c.dtype, stream));
         }
         else {
-            TRY_T(9, b200_argmax(in->out_tokens, m->logits, R, c.vocab, c.vocab, c.dtype, stream));
+            TRY_T(9, b200_argmax(in->out_tokens, m->logits, R, valid, c.vocab, c.dtype, stream));
         }
     }
     if (in->advance && !chunk) {
