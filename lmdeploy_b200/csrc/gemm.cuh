@@ -276,6 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     const uint32_t x_ring   = w_ring + (uint32_t)p.nw * WSLOT;
     const int      d_stride = p.MT <= 64 ? 64 : 128;
 
+    if (threadIdx.x == 64) GEMM_TRACE(7, 4);
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxW; ++s) {
             mbar_init(smem_u32(&bar_wfull[s]), 1);
@@ -669,9 +670,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         __threadfence();
         named_bar_sync(2, kDqWarps * 32);
         if (threadIdx.x == 64) {
+            GEMM_TRACE(7, 0);
             atomicAdd(ctr, 1);
             while (ld_acquire_gpu(ctr) < p.splits) {
             }
+            GEMM_TRACE(7, 1);
         }
         named_bar_sync(2, kDqWarps * 32);
         // token ownership: split r sums tokens [MT * r / splits, MT * (r + 1) / splits)  (any split count works)
@@ -793,6 +796,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         }
         named_bar_sync(2, kDqWarps * 32);
         if (threadIdx.x == 64) {
+            GEMM_TRACE(7, 2);
             // the last CTA of the group to finish reading re-arms the counters for the next launch
             if (atomicAdd(ctr + 1, 1) == p.splits - 1) {
                 ctr[1] = 0;
@@ -806,6 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     if (warp == 1) {
         umma::tmem_dealloc(s_tmem, p.tmem_cols);
     }
+    if (threadIdx.x == 64) GEMM_TRACE(7, 3);
     GEMM_WALL(p, 1);
 }
 

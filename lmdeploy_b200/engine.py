@@ -96,8 +96,10 @@ class StaticBatchRunner:
         torch.cuda.current_stream().synchronize()
         return self.h_out.numpy().copy()
 
-    def time_attention_kernel(self, k_len, iters=20, layer=0):
-        """CUDA-event time of decode_attention_kernel alone (prologue / fix-up skipped) at context k_len.
+    def time_attention_kernel(self, k_len, iters=20, layer=0, full=False):
+        """CUDA-event time of the decode attention at context k_len: decode_attention_kernel alone (prologue / fix-up
+        skipped, the default) or -- full=True -- the whole b200_decode_attention call (prologue + main kernel + fix-up), which
+        is what compares with the reference's dispatchDecoding (in-kernel prologue + its reduce).
         Algorithmic bytes per launch = batch * k_len * 2 * Hkv * (D * kvbits / 8 + 4)."""
         m = self.model
         spec = m.spec
@@ -123,7 +125,7 @@ class StaticBatchRunner:
         p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
         p.stream = torch.cuda.current_stream().cuda_stream
         L.check(m.lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")     # full call once
-        p.debug_flags = 3
+        p.debug_flags = 0 if full else 3
         # rotate over layers so successive launches never hit L2-resident pages (each layer is >> L2 anyway)
         layers = spec.layers
         for i in range(3):
@@ -140,29 +142,5 @@ class StaticBatchRunner:
         us = e0.elapsed_time(e1) * 1e3 / iters
         q_bits = 16 if m.quant_policy == 0 else m.quant_policy
         nbytes = self.batch * k_len * 2 * m.kv_heads * (D * q_bits // 8 + (4 if m.quant_policy else 0))
-        self._attn_params = (p, qkv, out, ws, cu_k)   # kept alive for time_reference_attention
+        self._attn_params = (p, qkv, out, ws, cu_k)   # kept alive: bench.py times the reference kernel on the same buffers
         return dict(us=us, bytes=nbytes, gbs=nbytes / (us * 1e-6) / 1e9)
-
-    def time_reference_attention(self, ref_lib, iters=20, layer=0):
-        """Benchmark aid: CUDA-event time of the REFERENCE's decode attention (its main kernel + its reduce, through
-        oracle/_ref; the caller passes the oracle.ref_lib module) on the very buffers time_attention_kernel used.
-        The reference call also runs its in-kernel prologue, ours was timed without prologue / fix-up, so the
-        comparison slightly favours ours by the (tiny) prologue; both read the same KV bytes."""
-        p = self._attn_params[0]
-        m = self.model
-        ref = ref_lib.load()
-        p.debug_flags = 0
-        a, keep = ref_lib.args_from_b200(p, torch)
-        layers = m.spec.layers
-        for i in range(3):
-            a.layer_offset = ((layer + i) % layers) * m.layer_bytes
-            assert ref.ref_decode_attention(C.byref(a)) == 0
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(iters):
-            a.layer_offset = ((layer + i) % layers) * m.layer_bytes
-            ref.ref_decode_attention(C.byref(a))
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) * 1e3 / iters

@@ -23,19 +23,28 @@ def marshal_step(batch, block_ptr=None):
     leader broadcasts; every rank maps them to addresses of its own pool) and block_ptrs their addresses through
     `block_ptr` when one is given."""
     tokens, cu_q, cu_k, ids, cu_blocks = [], [0], [0], [], [0]
+    q = k = max_k = 0
     for s in batch:
-        toks = s.next_inputs()
-        if len(toks) != s.step_tokens:
-            raise RuntimeError(f"session {s.session_id}: scheduled {s.step_tokens} tokens but {len(toks)} are available")
+        n = s.step_tokens
+        if n == 1 and s.cached < s.context_len:      # steady decode: one row, the token at position `cached`
+            tokens.append(int(s.token_at(s.cached)))
+        else:
+            toks = s.next_inputs()
+            if len(toks) != n:
+                raise RuntimeError(f"session {s.session_id}: scheduled {n} tokens but {len(toks)} are available")
+            tokens += [int(t) for t in toks]
         if not s.blocks:
             raise RuntimeError(f"session {s.session_id} runs without KV blocks")
-        tokens += [int(t) for t in toks]
-        cu_q.append(cu_q[-1] + len(toks))
-        cu_k.append(cu_k[-1] + s.cached + len(toks))
-        ids += list(s.blocks)
+        q += n
+        k += s.cached + n
+        if s.cached + n > max_k:
+            max_k = s.cached + n
+        cu_q.append(q)
+        cu_k.append(k)
+        ids += s.blocks
         cu_blocks.append(len(ids))
     st = dict(batch_size=len(batch), token_ids=tokens, token_num=len(tokens), cu_q_len=cu_q, cu_k_len=cu_k, block_ids=ids,
-              cu_block_nums=cu_blocks, max_k_len=max(s.cached + s.step_tokens for s in batch))
+              cu_block_nums=cu_blocks, max_k_len=max_k)
     if block_ptr is not None:
         st["block_ptrs"] = [block_ptr(b) for b in ids]
     return st
@@ -72,27 +81,36 @@ class TurboMind:
                 num_blocks = int(free * cfg.cache_max_entry_count) // (self.model.layer_bytes * spec.layers)
         self.pool = KvCachePool(num_blocks, spec.layers, self.model.kv_heads, spec.head_dim, self.block_len,
                                 cfg.quant_policy, device=dev)
-        # Chunked prefill (several prompt tokens of a sequence per step through b200_model_chunk_step) is opt-in until
-        # the prefill attention kernel has had its GPU parity run: B200_CHUNKED_PREFILL=<tokens per sequence per step>.
-        # Default: one prompt token per step through the decode kernel (exact).
-        chunk = int(os.environ.get("B200_CHUNKED_PREFILL", "1"))
+        # Chunked prefill: a sequence still inside its prompt feeds up to B200_CHUNKED_PREFILL tokens (default 64) per step
+        # through b200_model_chunk_step (tcgen05 prefill attention; parity-green on a B200 against the oracle, the
+        # reference's own prefill kernels and token-by-token feeding: tests/test_prefill_attention_gpu.py,
+        # tests/test_engine_gpu.py) as long as the step's row budget (max_batch rows) has room.  1 = one prompt token per
+        # step through the decode kernel.
+        chunk = int(os.environ.get("B200_CHUNKED_PREFILL", "64"))
         self.scheduler = Scheduler(max_batch=self.max_batch, block_len=self.block_len, num_blocks=num_blocks,
                                    session_len=self.session_len, prefix_caching=cfg.enable_prefix_caching,
                                    prefill_chunk=min(chunk, cfg.max_prefill_token_num), token_budget=self.max_batch)
         B = self.max_batch
         self._max_blocks = (self.session_len + self.block_len - 1) // self.block_len
-        self.d_tokens = torch.zeros(B, dtype=torch.int32, device=dev)
+        # Per-step control arrays live in ONE int32 device buffer [tokens B | cu_q B+1 | cu_k B+1 | cu_blocks B+1] fed by one
+        # pinned staging buffer: a step costs a single ~1 KB H2D copy (plus the block table only when it changed) --
+        # the counterpart of the pinned staging in UnifiedAttentionLayer::Setup (unified_attention_layer.cc:288-305).
+        self._o_q, self._o_k, self._o_b, n_ctl = B, 2 * B + 1, 3 * B + 2, 4 * B + 3
+        self.d_ctl = torch.zeros(n_ctl, dtype=torch.int32, device=dev)
+        self.h_ctl = torch.zeros(n_ctl, dtype=torch.int32).pin_memory()
+        self._h_ctl = self.h_ctl.numpy()
+        self.d_tokens = self.d_ctl[:B]
+        self.d_cu_q = self.d_ctl[self._o_q:self._o_q + B + 1]
+        self.d_cu_k = self.d_ctl[self._o_k:self._o_k + B + 1]
+        self.d_cu_blocks = self.d_ctl[self._o_b:self._o_b + B + 1]
         self.d_out = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.d_cu_q = torch.arange(B + 1, dtype=torch.int32, device=dev)
-        self.d_cu_k = torch.zeros(B + 1, dtype=torch.int32, device=dev)
-        self.d_cu_blocks = torch.zeros(B + 1, dtype=torch.int32, device=dev)
         self.d_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64, device=dev)
-        self.h_tokens = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.h_out = torch.zeros(B, dtype=torch.int32).pin_memory()
-        self.h_cu_k = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
-        self.h_cu_q = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
-        self.h_cu_blocks = torch.zeros(B + 1, dtype=torch.int32).pin_memory()
+        self._h_out = self.h_out.numpy()
         self.h_block_ptrs = torch.zeros(B * self._max_blocks, dtype=torch.int64).pin_memory()
+        self._h_block_ptrs = self.h_block_ptrs.numpy()
+        self._last_block_ids = None
+        self.h2d_bytes = self.d2h_bytes = 0          # running totals of the step traffic (bench.py reports them per step)
         self._lock = threading.Lock()
         self._next_session = 0
         self._use_graphs = os.environ.get("B200_ENGINE_GRAPHS", "1") != "0"
@@ -178,17 +196,23 @@ class TurboMind:
     def _execute(self, st):
         """Upload one step's arrays, run it on this rank's model shard, return the sampled id of every row."""
         B, T = st["batch_size"], st["token_num"]
-        ptrs = [self.pool.ptr(b) for b in st["block_ids"]]
-        self.h_tokens[:T] = torch.tensor(st["token_ids"], dtype=torch.int32)
-        self.h_cu_q[:B + 1] = torch.tensor(st["cu_q_len"], dtype=torch.int32)
-        self.h_cu_k[:B + 1] = torch.tensor(st["cu_k_len"], dtype=torch.int32)
-        self.h_cu_blocks[:B + 1] = torch.tensor(st["cu_block_nums"], dtype=torch.int32)
-        self.h_block_ptrs[:len(ptrs)] = torch.tensor(ptrs, dtype=torch.int64)
-        self.d_tokens[:T].copy_(self.h_tokens[:T], non_blocking=True)
-        self.d_cu_q[:B + 1].copy_(self.h_cu_q[:B + 1], non_blocking=True)
-        self.d_cu_k[:B + 1].copy_(self.h_cu_k[:B + 1], non_blocking=True)
-        self.d_cu_blocks[:B + 1].copy_(self.h_cu_blocks[:B + 1], non_blocking=True)
-        self.d_block_ptrs[:len(ptrs)].copy_(self.h_block_ptrs[:len(ptrs)], non_blocking=True)
+        h = self._h_ctl
+        h[:T] = st["token_ids"]
+        h[self._o_q:self._o_q + B + 1] = st["cu_q_len"]
+        h[self._o_k:self._o_k + B + 1] = st["cu_k_len"]
+        h[self._o_b:self._o_b + B + 1] = st["cu_block_nums"]
+        self.d_ctl.copy_(self.h_ctl, non_blocking=True)
+        self.h2d_bytes += self.h_ctl.numel() * 4
+        ids = st["block_ids"]
+        if ids != self._last_block_ids:          # the block table changes only when a sequence crosses a block boundary
+            n = len(ids)
+            hp = self._h_block_ptrs[:n]
+            hp[:] = ids
+            hp *= self.pool.block_bytes
+            hp += self.pool.base
+            self.d_block_ptrs[:n].copy_(self.h_block_ptrs[:n], non_blocking=True)
+            self.h2d_bytes += n * 8
+            self._last_block_ids = ids
 
         def launch():
             self.model.decode_step(batch=B, token_ids=self.d_tokens, cu_q_len=self.d_cu_q, cu_k_len=self.d_cu_k,
@@ -212,9 +236,10 @@ class TurboMind:
                 self._seen_sizes.add(B)
         else:
             launch()
-        self.h_out[:T].copy_(self.d_out[:T], non_blocking=True)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+        self.d2h_bytes += self.h_out.numel() * 4
         torch.cuda.current_stream().synchronize()
-        return self.h_out[:T].tolist()
+        return self._h_out[:T].tolist()
 
     def close(self):
         """Release tensor-parallel followers (if any) and the communicator."""

@@ -29,7 +29,7 @@ from dataclasses import dataclass, field
 from typing import Deque, Dict, List, Optional
 
 
-@dataclass
+@dataclass(eq=False)       # identity semantics: sequences are compared and looked up as objects, never by value
 class Sequence:
     session_id: int
     prompt: List[int]

@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(ROOT, "_ref", "libtm_ref_gemm.so")
+# B200_REF_GEMM_LIB=ptx: the build whose kernel TUs hold compute_80 PTX only (JIT-compiled by the driver at load time, the way
+# the reference's wheels reach Blackwell); default: the ahead-of-time sm_100 SASS build of the same sources
+LIB_PATH = os.path.join(ROOT, "_ref", "libtm_ref_gemm_ptx.so" if os.environ.get("B200_REF_GEMM_LIB") == "ptx"
+                        else "libtm_ref_gemm.so")
 DISPATCH_DEFAULT, DISPATCH_MEASURE, DISPATCH_REUSE = 0, 1, 2
 
 _lib = None

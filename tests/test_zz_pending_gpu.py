@@ -12,340 +12,6 @@ from test_linear_gpu import DevLinear, _assert_close
 
 pytestmark = [pytest.mark.gpu, pending_first_gpu_run]
 
-
-def _fp8_cols(rng, K, N):
-    """Random weights quantised to e4m3 with one scale per (128-k group, column)."""
-    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
-    scale = (np.abs(w.reshape(K // 128, 128, N)).max(axis=1) / 448.0).astype(np.float32)
-    w8 = OL.f32_to_e4m3(w / np.repeat(scale, 128, 0))
-    return w8, scale
-
-
-@pytest.mark.parametrize("dtype", [BF16, F16])
-@pytest.mark.parametrize("shape", [(1024, 256), (512, 384), (4096, 4096)])
-@pytest.mark.parametrize("m", [1, 64])
-def test_fp8_per_column_scales(lib, shape, m, dtype):
-    """weight_format 3: fp8 e4m3 with scales f32 [K/128, N]; same arithmetic as format 2
-    (w = T(e4m3) *_T T(scale), transform.h:92-97)."""
-    K, N = shape
-    rng = np.random.default_rng(K + N + m)
-    w8, scale = _fp8_cols(rng, K, N)
-    lin = DevLinear(lib, K, N, 3, dtype, w8, scales=scale)
-    x = rn(rng.standard_normal((m, K)).astype(np.float32), dtype)
-    got = lin.forward(x)
-    ref = OL.linear(x, OL.dequant_fp8_cols(w8, scale, 128, dtype), dtype)
-    _assert_close(got, ref, atol=2e-4 if dtype == F16 else 2e-3, rtol=2e-3 if dtype == F16 else 1.6e-2)
-    lin_t = DevLinear(lib, K, N, 3, dtype, np.ascontiguousarray(w8.T), scales=scale, transposed=1)
-    assert (lin_t.prepared == lin.prepared).all()
-
-
-def test_fp8_block_scales_expanded_equal_format_2(lib):
-    """A checkpoint's 128x128 block scales expanded along N must give bit-identical outputs through format 3."""
-    K, N, m = 2048, 1024, 48
-    rng = np.random.default_rng(5)
-    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
-    blk = (np.abs(w.reshape(K // 128, 128, N // 128, 128)).max(axis=(1, 3)) / 448.0).astype(np.float32)
-    w8 = OL.f32_to_e4m3(w / np.repeat(np.repeat(blk, 128, 0), 128, 1))
-    x = rn(rng.standard_normal((m, K)).astype(np.float32), BF16)
-    y2 = DevLinear(lib, K, N, 2, BF16, w8, scales=blk).forward(x)
-    y3 = DevLinear(lib, K, N, 3, BF16, w8, scales=np.repeat(blk, 128, 1)).forward(x)
-    assert np.array_equal(y2, y3)
-
-
-def test_fp8_gated_silu_on_interleaved_columns(lib):
-    """Fused gate|up with element interleave -- impossible with 128-wide N blocks, the reason format 3 exists."""
-    K, I, m = 2048, 1024, 32
-    rng = np.random.default_rng(6)
-    g8, gs = _fp8_cols(rng, K, I)
-    u8, us = _fp8_cols(rng, K, I)
-    w8 = np.stack([g8, u8], -1).reshape(K, 2 * I)
-    sc = np.stack([gs, us], -1).reshape(K // 128, 2 * I)
-    lin = DevLinear(lib, K, 2 * I, 3, BF16, w8, scales=sc)
-    x = rn(rng.standard_normal((m, K)).astype(np.float32), BF16)
-    got = lin.forward(x, epilogue=1)
-    ref = OL.linear_gated_silu(x, OL.dequant_fp8_cols(w8, sc, 128, BF16), BF16)
-    _assert_close(got, ref, atol=2e-3, rtol=1.6e-2)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# whole decode step in bf16: fp8 weights (Llama-3-70B FP8 is BASELINE config C5) and dense bf16 weights
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kv_bits", [8, 16])
-@pytest.mark.parametrize("fmt", ["fp8", "fp16"])
-def test_decode_step_bf16_matches_oracle(kv_bits, fmt):
-    """Same protocol as test_decode_step_gpu.test_decode_step_matches_oracle with T = bf16.  Bars: bf16 keeps 8
-    significand bits (8x the fp16 rounding), so logits |diff| <= 3.2e-2 and token ids must agree wherever the oracle's
-    top-1/top-2 margin exceeds twice that."""
-    import torch
-    from oracle import attention as OA
-    from oracle.decode_step import TinyWeights, decode_step
-    from harness import from_dev_T
-    from test_decode_step_gpu import build_device_model
-    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, dtype=BF16, seed=kv_bits)
-    hist = np.array([0, 5, 64, 130, 311], np.int32)
-    B = len(hist)
-    rng = np.random.default_rng(1)
-    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
-    layout = OA.KvLayout(2, 64, 128, kv_bits)
-    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
-    nblk = sum(blocks_per) + 2
-    cache = OA.PagedKvCache(nblk, w.layers, layout, BF16)
-    perm = rng.permutation(nblk)
-    tables, o = [], 0
-    for n in blocks_per:
-        tables.append(perm[o:o + n].tolist())
-        o += n
-    for l in range(w.layers):
-        for b in range(B):
-            h = int(hist[b])
-            if h:
-                k = OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), BF16)
-                v = OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), BF16)
-                OA.process_kv(cache, tables[b], l, 0, k, v, rope)
-    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
-
-    m = build_device_model(w, 0 if kv_bits == 16 else kv_bits, max_batch=8)
-    pool = torch.from_numpy(cache.pool.copy()).cuda()
-    ptrs = torch.tensor([pool.data_ptr() + int(b) * cache.block_bytes for t in tables for b in t], dtype=torch.int64,
-                        device="cuda")
-    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
-    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
-    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
-    d_tok = torch.from_numpy(tokens).cuda()
-    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
-    m.decode_step(batch=B, token_ids=d_tok, cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs, cu_block_nums=cu_blocks,
-                  out_tokens=d_out, max_k_len=int(hist.max()) + 1)
-    torch.cuda.synchronize()
-    got_logits = from_dev_T(m.logits(B), BF16)
-    got_tokens = d_out.cpu().numpy()
-    ref_logits, ref_tokens = decode_step(w, tokens, cache, tables, hist, rope)
-    tol = 3.2e-2
-    err = np.abs(got_logits - ref_logits)
-    assert err.max() <= tol, err.max()
-    srt = np.sort(ref_logits, -1)
-    margin = srt[:, -1] - srt[:, -2]
-    for b in range(B):
-        if margin[b] > 2 * tol:
-            assert got_tokens[b] == ref_tokens[b]
-        else:
-            assert ref_logits[b, got_tokens[b]] >= srt[b, -1] - 2 * tol
-
-
-def test_synthetic_fp8_model_runs_and_is_deterministic():
-    """DecodeModel.load_synthetic for an fp8 spec (the bench path of config C5): finite logits, identical across runs."""
-    import torch
-    from lmdeploy_b200.turbomind import DecodeModel, KvCachePool, ModelSpec
-    spec = ModelSpec("tiny-fp8", "llama", 1024, 2, 8, 2, 2048, 2048, 5e5, weight_format="fp8", dtype="bf16")
-    outs = []
-    for _ in range(2):
-        m = DecodeModel(spec, quant_policy=8, max_batch=4)
-        m.load_synthetic(0)
-        pool = KvCachePool(8, spec.layers, 2, 128, 64, 8)
-        tables = [pool.allocate(2) for _ in range(4)]
-        ptrs = torch.tensor([pool.ptr(b) for t in tables for b in t], dtype=torch.int64, device="cuda")
-        cu_blocks = torch.arange(5, dtype=torch.int32, device="cuda") * 2
-        cu = torch.arange(5, dtype=torch.int32, device="cuda")
-        tok = torch.tensor([1, 2, 3, 4], dtype=torch.int32, device="cuda")
-        out = torch.zeros(4, dtype=torch.int32, device="cuda")
-        m.decode_step(batch=4, token_ids=tok, cu_q_len=cu, cu_k_len=cu.clone(), block_ptrs=ptrs, cu_block_nums=cu_blocks,
-                      out_tokens=out, max_k_len=1)
-        torch.cuda.synchronize()
-        lg = m.logits(4).float().cpu()
-        assert torch.isfinite(lg).all() and lg.abs().max() > 0
-        outs.append((lg, out.cpu()))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# prefill (context) attention: b200_prefill_attention vs oracle.attention.prefill_attention
-# ---------------------------------------------------------------------------------------------------------------
-def _prefill_case(lib, *, q_lens, hists, Hq, Hkv, kv_bits, dtype, seed=0, bias=False, rope=None, against_reference=False):
-    import ctypes as C
-    import torch
-    from lmdeploy_b200 import _lib as L
-    from oracle import attention as OA
-    from harness import rand_T, to_dev_T, from_dev_T
-    rng = np.random.default_rng(seed)
-    D, block_len, layers, layer = 128, 64, 2, 1
-    q_lens, hists = np.asarray(q_lens, np.int32), np.asarray(hists, np.int32)
-    k_lens = q_lens + hists
-    B = len(q_lens)
-    rope = rope or OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=10000.0)
-    layout = OA.KvLayout(head_num=Hkv, block_len=block_len, head_dim=D, q_bits=kv_bits)
-    blocks_per = [(int(k) + block_len - 1) // block_len for k in k_lens]
-    nblk = sum(blocks_per) + 2
-    cache = OA.PagedKvCache(nblk, layers, layout, dtype)
-    cache.pool[:] = rng.integers(0, 256, cache.pool.shape, dtype=np.uint8)      # pages start as garbage, not zeros
-    perm = rng.permutation(nblk)
-    tables, o = [], 0
-    for n in blocks_per:
-        tables.append(perm[o:o + n].tolist())
-        o += n
-    biases = None
-    if bias:
-        biases = (rand_T(rng, (Hq * D,), dtype, 0.1), rand_T(rng, (Hkv * D,), dtype, 0.1), rand_T(rng, (Hkv * D,), dtype, 0.1))
-    for b in range(B):
-        h = int(hists[b])
-        if h:
-            OA.process_kv(cache, tables[b], layer, 0, rand_T(rng, (h, Hkv, D), dtype), rand_T(rng, (h, Hkv, D), dtype), rope,
-                          None if not bias else biases[1], None if not bias else biases[2])
-    T = int(q_lens.sum())
-    qkv = rand_T(rng, (T, (Hq + 2 * Hkv) * D), dtype)
-
-    # ---- device ----
-    d_pool = torch.from_numpy(cache.pool.copy()).cuda()
-    ptrs = [d_pool.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t]
-    d_ptrs = torch.tensor(ptrs, dtype=torch.int64, device="cuda")
-    d_cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
-    d_cu_q = torch.tensor(np.concatenate([[0], np.cumsum(q_lens)]), dtype=torch.int32, device="cuda")
-    d_cu_k = torch.tensor(np.concatenate([[0], np.cumsum(k_lens)]), dtype=torch.int32, device="cuda")
-    d_qkv = to_dev_T(qkv, dtype)
-    d_out = torch.zeros(T, Hq * D, dtype=d_qkv.dtype, device="cuda")
-    p = L.AttentionParams()
-    base = d_qkv.data_ptr()
-    p.out, p.q, p.k, p.v = d_out.data_ptr(), base, base + Hq * D * 2, base + (Hq + Hkv) * D * 2
-    p.stride = (Hq + 2 * Hkv) * D
-    if bias:
-        d_bias = [to_dev_T(x, dtype) for x in biases]
-        p.q_bias, p.k_bias, p.v_bias = [t.data_ptr() for t in d_bias]
-    p.cu_q_len, p.cu_k_len = d_cu_q.data_ptr(), d_cu_k.data_ptr()
-    p.block_ptrs, p.cu_block_nums = d_ptrs.data_ptr(), d_cu_blocks.data_ptr()
-    p.layer_offset, p.block_len = cache.layer_offset(layer), block_len
-    p.token_num, p.batch_size, p.max_k_len = T, B, int(k_lens.max())
-    p.num_heads, p.num_kv_heads, p.size_per_head = Hq, Hkv, D
-    p.inv_sqrt_dh = float(np.float32(np.float32(1.4426950408889634) / np.float32(np.sqrt(np.float32(D)))))
-    p.rope = L.RopeConfig(rope.type, rope.dim, rope.base, rope.factor, rope.max_position_embeddings,
-                          rope.llama3_low_freq_factor, rope.llama3_high_freq_factor,
-                          rope.llama3_original_max_position_embeddings, rope.yarn_attention_factor, rope.yarn_beta_fast,
-                          rope.yarn_beta_slow, 1)
-    p.rope.exact_math = 0 if against_reference else 1
-    p.quant_policy, p.dtype = (0 if kv_bits == 16 else kv_bits), (0 if dtype == F16 else 1)
-    ws = torch.zeros(lib.b200_prefill_attention_workspace_bytes(T, Hq), dtype=torch.uint8, device="cuda")
-    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
-    p.stream = torch.cuda.current_stream().cuda_stream
-    L.check(lib.b200_prefill_attention(C.byref(p)), "b200_prefill_attention")
-    torch.cuda.synchronize()
-    got, got_pool = from_dev_T(d_out, dtype), d_pool.cpu().numpy()
-
-    if against_reference:
-        # the reference's ProcessKV + FlattenKV + dispatchAttention on a fresh copy of the same pages
-        from oracle import ref_lib
-        ref = ref_lib.load_prefill()
-        d_pool2 = torch.from_numpy(cache.pool.copy()).cuda()
-        d_ptrs2 = torch.tensor([d_pool2.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t],
-                               dtype=torch.int64, device="cuda")
-        d_out2 = torch.zeros_like(d_out)
-        p.block_ptrs, p.out = d_ptrs2.data_ptr(), d_out2.data_ptr()
-        a, keep = ref_lib.args_from_b200(p, torch, max_q_len=int(q_lens.max()))
-        k_sum = int(k_lens.sum())
-        tmp_kv = torch.zeros(Hkv * 2 * (k_sum + 64) * D, dtype=d_qkv.dtype, device="cuda")
-        rc = ref.ref_prefill_attention(C.byref(a), tmp_kv.data_ptr(), k_sum)
-        torch.cuda.synchronize()
-        assert rc == 0
-        return got, from_dev_T(d_out2, dtype), got_pool, d_pool2.cpu().numpy()
-
-    # ---- oracle (mutates its cache the same way) ----
-    ref = OA.prefill_attention(qkv, cache, tables, q_lens, k_lens, layer, Hq, Hkv, rope,
-                               q_bias=None if not bias else biases[0], k_bias=None if not bias else biases[1],
-                               v_bias=None if not bias else biases[2])
-    return got, ref, got_pool, cache.pool
-
-
-@pytest.mark.parametrize("kv_bits", [8, 4, 16])
-@pytest.mark.parametrize("heads", [(4, 1), (8, 2), (2, 2), (6, 1)])          # GQA groups 4, 4, 1 (MHA), 6 (126 rows used)
-def test_prefill_attention_matches_oracle(lib, kv_bits, heads):
-    """Ragged chunks: fresh prompts, chunked continuation over history, single-token chunk, chunk ending mid-tile and
-    mid-block, more query tokens than one 128-row tile holds.  Bars as for decode: KV pages bit-identical (the prologue
-    kernel is shared), outputs |diff| <= 2e-3 (fp16; tile order differs from the oracle's single pass)."""
-    Hq, Hkv = heads
-    got, ref, pool, ref_pool = _prefill_case(lib, q_lens=[70, 1, 33, 200, 5], hists=[0, 130, 64, 0, 63], Hq=Hq, Hkv=Hkv,
-                                             kv_bits=kv_bits, dtype=F16, seed=kv_bits + Hq)
-    assert np.array_equal(pool, ref_pool)
-    assert np.isfinite(got).all()
-    err = np.abs(got - ref)
-    assert err.max() <= 2e-3, (err.max(), np.unravel_index(err.argmax(), err.shape))
-
-
-@pytest.mark.parametrize("kv_bits", [8, 16])
-def test_prefill_attention_bf16_bias_llama3_rope(lib, kv_bits):
-    from oracle import attention as OA
-    rope = OA.RopeParam(type=OA.ROPE_LLAMA3, dim=128, base=5e5, factor=8.0, llama3_low_freq_factor=1.0,
-                        llama3_high_freq_factor=4.0, llama3_original_max_position_embeddings=8192)
-    got, ref, pool, ref_pool = _prefill_case(lib, q_lens=[150, 17], hists=[10, 300], Hq=8, Hkv=2, kv_bits=kv_bits,
-                                             dtype=BF16, seed=3, bias=True, rope=rope)
-    assert np.array_equal(pool, ref_pool)
-    err = np.abs(got - ref)
-    assert np.isfinite(got).all() and err.max() <= 1.6e-2, err.max()
-
-
-def test_prefill_single_prompt_crossing_one_block(lib):
-    """One 96-token prompt (two 64-token blocks, the second half full), no history."""
-    got, ref, pool, ref_pool = _prefill_case(lib, q_lens=[96], hists=[0], Hq=8, Hkv=2, kv_bits=8, dtype=F16, seed=11)
-    assert np.array_equal(pool, ref_pool) and np.abs(got - ref).max() <= 2e-3
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# engine level: continuous batching through TurboMind.step, prefix caching, chunked prefill
-# ---------------------------------------------------------------------------------------------------------------
-def _tiny_engine(monkeypatch, *, chunk=None, prefix=False):
-    from lmdeploy_b200.messages import TurbomindEngineConfig
-    from lmdeploy_b200.turbomind import ModelSpec
-    from lmdeploy_b200.turbomind.engine import TurboMind
-    if chunk:
-        monkeypatch.setenv("B200_CHUNKED_PREFILL", str(chunk))
-    else:
-        monkeypatch.delenv("B200_CHUNKED_PREFILL", raising=False)
-    spec = ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1024, 1e4, weight_format="awq")
-    cfg = TurbomindEngineConfig(max_batch_size=8, session_len=512, cache_max_entry_count=64, quant_policy=8,
-                                enable_prefix_caching=prefix)
-    return TurboMind(spec, cfg, seed=0)
-
-
-_PROMPTS = [[5, 9, 2, 77, 3], list(range(100, 100 + 70)), [1], list(range(100, 100 + 66)) + [4, 4]]
-
-
-def _generate(engine, max_new=12):
-    from lmdeploy_b200.messages import GenerationConfig
-    from lmdeploy_b200.turbomind.engine import batched_generate
-    seqs = batched_generate(engine, _PROMPTS, GenerationConfig(max_new_tokens=max_new, ignore_eos=True))
-    return [list(s.generated) for s in seqs]
-
-
-def test_engine_continuous_batching_is_deterministic(monkeypatch):
-    a = _generate(_tiny_engine(monkeypatch))
-    b = _generate(_tiny_engine(monkeypatch))
-    assert a == b and all(len(x) == 12 for x in a)
-
-
-def test_engine_cuda_graph_replay_equals_eager_launches(monkeypatch):
-    monkeypatch.setenv("B200_ENGINE_GRAPHS", "0")
-    eager = _generate(_tiny_engine(monkeypatch), max_new=20)
-    monkeypatch.setenv("B200_ENGINE_GRAPHS", "1")
-    eng = _tiny_engine(monkeypatch)
-    graphed = _generate(eng, max_new=20)
-    assert eng._graphs, "no decode step was replayed from a graph"
-    assert eager == graphed                                   # same kernels, same order, same buffers
-
-
-def test_engine_prefix_caching_does_not_change_tokens(monkeypatch):
-    base = _generate(_tiny_engine(monkeypatch))
-    eng = _tiny_engine(monkeypatch, prefix=True)
-    first, second = _generate(eng), _generate(eng)          # the second wave re-uses the published blocks
-    assert eng.get_schedule_metrics().prefix_cache_hit_rate > 0
-    # cached K/V were produced in a different batch composition: equal up to fp16 ties in the argmax
-    for x, y, z in zip(base, first, second):
-        assert x[:4] == y[:4] == z[:4]
-
-
-def test_engine_chunked_prefill_matches_token_by_token(monkeypatch):
-    base = _generate(_tiny_engine(monkeypatch))
-    eng = _tiny_engine(monkeypatch, chunk=32)
-    got = _generate(eng)
-    assert eng.scheduler.tick < 70 + 12                      # the 70-token prompt no longer costs 70 steps
-    for x, y in zip(base, got):
-        assert x[:4] == y[:4]
-
-
 # ---------------------------------------------------------------------------------------------------------------
 # W4A16 linear against the REFERENCE's own GEMM (oracle/_ref/libtm_ref_gemm.so) on the same device buffers
 # ---------------------------------------------------------------------------------------------------------------
@@ -396,180 +62,6 @@ def test_gated_silu_matches_reference_gemm(lib):
     _assert_close(theirs, ref, atol=4e-4, rtol=4e-3)
     _assert_close(ours, ref, atol=4e-4, rtol=4e-3)
     rl.close(), g.close()
-
-
-@pytest.mark.parametrize("kv_bits", [8, 4, 16])
-def test_prefill_attention_matches_reference_kernels(lib, kv_bits):
-    """Ours against the REFERENCE ITSELF (oracle/_ref/libtm_ref_prefill.so: invokeProcessKV_v2 + invokeFlattenKV_v2 +
-    dispatchAttention compiled in place) on the same inputs, rope.exact_math = 0: pages bit-identical, outputs <= 2e-3."""
-    from oracle import ref_lib
-    if not ref_lib.prefill_available():
-        pytest.skip("oracle/_ref/libtm_ref_prefill.so not built")
-    got, ref, pool, ref_pool = _prefill_case(lib, q_lens=[70, 1, 33, 200], hists=[0, 130, 64, 0], Hq=8, Hkv=2, kv_bits=kv_bits,
-                                             dtype=F16, seed=kv_bits, against_reference=True)
-    assert np.array_equal(pool, ref_pool)
-    assert np.isfinite(got).all() and np.isfinite(ref).all()
-    assert np.abs(got - ref).max() <= 2e-3
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# model level: b200_model_chunk_step (mixed prefill/decode rows) vs oracle.decode_step.chunk_step
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kv_bits", [8, 16])
-def test_chunk_step_matches_oracle(kv_bits):
-    """Three sequences in one step: a fresh 40-token prompt chunk, a decoding sequence with 130 cached tokens, a 9-token
-    continuation chunk over 64 cached tokens.  Bars as for the decode step: logits of EVERY row |diff| <= 4e-3, greedy ids
-    equal outside top-1/top-2 ties; pages >= 99.9 % identical bytes (deeper layers see GEMM outputs one ulp apart)."""
-    import torch
-    from oracle import attention as OA
-    from oracle.decode_step import TinyWeights, chunk_step
-    from harness import from_dev_T
-    from test_decode_step_gpu import build_device_model
-    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt="awq", seed=kv_bits)
-    q_lens, hists = np.array([40, 1, 9], np.int32), np.array([0, 130, 64], np.int32)
-    k_lens = q_lens + hists
-    B, T = len(q_lens), int(q_lens.sum())
-    rng = np.random.default_rng(2)
-    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
-    layout = OA.KvLayout(2, 64, 128, kv_bits)
-    blocks_per = [(int(k) + 63) // 64 for k in k_lens]
-    nblk = sum(blocks_per) + 2
-    cache = OA.PagedKvCache(nblk, w.layers, layout, F16)
-    perm = rng.permutation(nblk)
-    tables, o = [], 0
-    for n in blocks_per:
-        tables.append(perm[o:o + n].tolist())
-        o += n
-    for l in range(w.layers):
-        for b in range(B):
-            h = int(hists[b])
-            if h:
-                OA.process_kv(cache, tables[b], l, 0, OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16),
-                              OA.rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16), rope)
-    tokens = rng.integers(0, w.vocab, T).astype(np.int32)
-
-    m = build_device_model(w, 0 if kv_bits == 16 else kv_bits, max_batch=64)
-    pool = torch.from_numpy(cache.pool.copy()).cuda()
-    ptrs = torch.tensor([pool.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t], dtype=torch.int64,
-                        device="cuda")
-    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
-    cu_q = torch.tensor(np.concatenate([[0], np.cumsum(q_lens)]), dtype=torch.int32, device="cuda")
-    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(k_lens)]), dtype=torch.int32, device="cuda")
-    d_tok = torch.from_numpy(tokens).cuda()
-    d_out = torch.zeros(T, dtype=torch.int32, device="cuda")
-    m.decode_step(batch=B, token_ids=d_tok, cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs, cu_block_nums=cu_blocks,
-                  out_tokens=d_out, max_k_len=int(k_lens.max()), token_num=T)
-    torch.cuda.synchronize()
-    got_logits = from_dev_T(m.logits(T), F16)
-    got_tokens = d_out.cpu().numpy()
-    ref_logits, ref_tokens = chunk_step(w, tokens, cache, tables, q_lens, k_lens, rope)
-    same = (pool.cpu().numpy() == cache.pool).mean()
-    assert same > (0.999 if kv_bits != 16 else 0.995), same
-    err = np.abs(got_logits - ref_logits)
-    assert err.max() <= 4e-3, (err.max(), np.unravel_index(err.argmax(), err.shape))
-    srt = np.sort(ref_logits, -1)
-    for t in range(T):
-        if srt[t, -1] - srt[t, -2] > 8e-3:
-            assert got_tokens[t] == ref_tokens[t]
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# Qwen2 family: q/k/v bias applied by the attention prologue inside the decode step (B200_T_QKV_BIAS)
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("fmt", ["awq", "fp16"])
-def test_decode_step_with_qkv_bias_matches_oracle(fmt):
-    import torch
-    from oracle import attention as OA
-    from oracle.decode_step import TinyWeights, decode_step
-    from harness import from_dev_T
-    from test_decode_step_gpu import build_device_model
-    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, seed=13, qkv_bias=True)
-    hist = np.array([0, 7, 64, 200], np.int32)
-    B = len(hist)
-    rng = np.random.default_rng(4)
-    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)     # build_device_model's theta
-    layout = OA.KvLayout(2, 64, 128, 8)
-    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
-    cache = OA.PagedKvCache(sum(blocks_per) + 1, w.layers, layout, F16)
-    tables, o = [], 0
-    for n in blocks_per:
-        tables.append(list(range(o, o + n)))
-        o += n
-    for l in range(w.layers):
-        for b in range(B):
-            if hist[b]:
-                OA.process_kv(cache, tables[b], l, 0, OA.rn(rng.standard_normal((int(hist[b]), 2, 128)).astype(np.float32), F16),
-                              OA.rn(rng.standard_normal((int(hist[b]), 2, 128)).astype(np.float32), F16), rope)
-    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
-    m = build_device_model(w, 8, max_batch=8)
-    pool = torch.from_numpy(cache.pool.copy()).cuda()
-    ptrs = torch.tensor([pool.data_ptr() + int(x) * cache.block_bytes for t in tables for x in t], dtype=torch.int64, device="cuda")
-    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
-    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
-    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
-    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
-    m.decode_step(batch=B, token_ids=torch.from_numpy(tokens).cuda(), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
-                  cu_block_nums=cu_blocks, out_tokens=d_out, max_k_len=int(hist.max()) + 1)
-    torch.cuda.synchronize()
-    got = from_dev_T(m.logits(B), F16)
-    ref, _ = decode_step(w, tokens, cache, tables, hist, rope)
-    assert np.abs(got - ref).max() <= 4e-3
-    assert (pool.cpu().numpy() == cache.pool).mean() > 0.999
-
-
-@pytest.mark.parametrize("heads", [(14, 2), (6, 2), (5, 1)])
-def test_decode_attention_odd_gqa_groups(heads):
-    """GQA groups 7 (Qwen2-7B), 3 and 5: the decode kernel pads the group to the MMA's 8 columns; the verified suite
-    covers groups 1, 4 and 8."""
-    from harness import PagedCase
-    hq, hkv = heads
-    case = PagedCase(batch_hist=[0, 63, 64, 300, 1000], num_heads=hq, num_kv_heads=hkv, kv_bits=8, seed=hq, bias=True)
-    out, pool = case.run_device()
-    ref = case.run_oracle()
-    assert (pool == case.cache.pool).all()
-    assert np.abs(out - ref).max() <= 2e-3
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# residual + RMSNorm against the REFERENCE's own kernel (oracle/_ref/libtm_ref_norm.so)
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dim", [4096, 6144, 8192])
-@pytest.mark.parametrize("dtype", [F16, BF16])
-def test_residual_rmsnorm_matches_reference_kernel(lib, dim, dtype):
-    """b200_residual_rmsnorm vs invokeBiasResidualRMSNorm (kernels/norm/rms_norm.cu:287-363) on the same inputs: the
-    residual stream (one T add) bit-identical; the normalised output within 1 ulp of T (the fp32 sum-of-squares
-    reduction order differs: cub::BlockReduce there, warp shuffles here) and identical for >= 99.9 % of the elements."""
-    import ctypes as C
-    import torch
-    from lmdeploy_b200 import _lib as L
-    from oracle import ref_lib
-    from harness import to_dev_T, from_dev_T
-    if not ref_lib.norm_available():
-        pytest.skip("oracle/_ref/libtm_ref_norm.so not built")
-    ref = ref_lib.load_norm()
-    rng = np.random.default_rng(dim)
-    m = 64
-    res = rn(rng.standard_normal((m, dim)).astype(np.float32), dtype)
-    hid = rn(rng.standard_normal((m, dim)).astype(np.float32) * 0.3, dtype)
-    w = rn((1 + 0.05 * rng.standard_normal(dim)).astype(np.float32), dtype)
-    bias = rn((0.1 * rng.standard_normal(dim)).astype(np.float32), dtype)
-    st = torch.cuda.current_stream().cuda_stream
-    dt = 0 if dtype == F16 else 1
-    # ours
-    d_res, d_hid, d_w, d_b = (to_dev_T(x, dtype) for x in (res, hid, w, bias))
-    d_out = torch.zeros(m * dim, dtype=d_res.dtype, device="cuda")
-    L.check(lib.b200_residual_rmsnorm(d_out.data_ptr(), 0, d_res.data_ptr(), d_hid.data_ptr(), d_w.data_ptr(), d_b.data_ptr(),
-                                      m, dim, 1e-5, dt, st), "residual_rmsnorm")
-    # reference (in place: residual updated, hidden <- normalised)
-    r_res, r_hid = to_dev_T(res, dtype), to_dev_T(hid, dtype)
-    assert ref.ref_bias_residual_rmsnorm(r_res.data_ptr(), r_hid.data_ptr(), d_w.data_ptr(), d_b.data_ptr(), dim, m, 1e-5, dt,
-                                         st) == 0
-    torch.cuda.synchronize()
-    assert torch.equal(d_res.view(torch.int16), r_res.view(torch.int16))
-    a = d_out.view(torch.int16).to(torch.int32).reshape(m, dim)
-    b = r_hid.view(torch.int16).to(torch.int32).reshape(m, dim)
-    diff = (a - b).abs()            # same sign and neighbouring magnitudes: the bit patterns differ by at most 1
-    assert int(diff.max()) <= 1 and float((diff != 0).float().mean()) <= 1e-3
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -651,110 +143,3 @@ def test_greedy_tokens_match_a_step_assembled_from_reference_kernels(kv_bits):
     same = (pools[0].cpu().numpy() == pools[1].cpu().numpy()).mean()
     assert same >= 0.999, same
     ref.close()
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# Qwen3 family: per-head q / k RMSNorm (b200_qk_rmsnorm, csrc/qk_norm.cu) and the decode step that uses it
-# ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dtype", [F16, BF16])
-def test_qk_rmsnorm_matches_oracle(lib, dtype):
-    """The kernel reproduces the reference kernel's instruction order (FMA chain, butterfly, fma(sum, 1/dim, eps), rsqrt
-    approximation); the numpy restatement has an exact rsqrt, so an output may sit one T ulp away -- rarely."""
-    import ctypes as C
-    import torch
-    from lmdeploy_b200 import _lib as L
-    from harness import to_dev_T, from_dev_T
-    rng = np.random.default_rng(9)
-    Hq, Hkv, T = 8, 2, 37
-    width = (Hq + 2 * Hkv) * 128
-    qkv = rn((rng.standard_normal((T, width)) * 2).astype(np.float32), dtype)
-    qw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
-    kw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
-    d = to_dev_T(qkv, dtype)
-    dq, dk = to_dev_T(qw, dtype), to_dev_T(kw, dtype)
-    L.check(lib.b200_qk_rmsnorm(d.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6,
-                                0 if dtype == F16 else 1, torch.cuda.current_stream().cuda_stream), "b200_qk_rmsnorm")
-    torch.cuda.synchronize()
-    got = from_dev_T(d, dtype)
-    want = OL.qk_rmsnorm(qkv, qw, kw, Hq, Hkv, 128, 1e-6, dtype)
-    assert np.array_equal(got[:, (Hq + Hkv) * 128:], qkv[:, (Hq + Hkv) * 128:])           # v untouched
-    ulp = np.abs(want) * (2.0 ** -10 if dtype == F16 else 2.0 ** -7) + 1e-6
-    assert (np.abs(got - want) <= ulp).all()
-    assert (got != want).mean() < 0.02
-
-
-@pytest.mark.parametrize("fmt", ["awq", "fp16"])
-def test_decode_step_with_qk_norm_matches_oracle(fmt):
-    import torch
-    from oracle import attention as OA
-    from oracle.decode_step import TinyWeights, decode_step
-    from test_decode_step_gpu import build_device_model
-    from harness import from_dev_T
-    w = TinyWeights(hidden=512, layers=2, heads=4, kv_heads=2, inter=1024, vocab=1024, fmt=fmt, seed=17, qk_norm=True)
-    hist = np.array([0, 5, 64, 130], np.int32)
-    B = len(hist)
-    rng = np.random.default_rng(4)
-    rope = OA.RopeParam(type=OA.ROPE_DEFAULT, dim=128, base=1e4)
-    layout = OA.KvLayout(2, 64, 128, 8)
-    blocks_per = [(int(h) + 1 + 63) // 64 for h in hist]
-    nblk = sum(blocks_per) + 2
-    cache = OA.PagedKvCache(nblk, w.layers, layout, F16)
-    perm = rng.permutation(nblk)
-    tables, o = [], 0
-    for n in blocks_per:
-        tables.append(perm[o:o + n].tolist())
-        o += n
-    for l in range(w.layers):
-        for b in range(B):
-            h = int(hist[b])
-            if h:
-                OA.process_kv(cache, tables[b], l, 0, rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16),
-                              rn(rng.standard_normal((h, 2, 128)).astype(np.float32), F16), rope)
-    tokens = rng.integers(0, w.vocab, B).astype(np.int32)
-    m = build_device_model(w, 8, max_batch=8)
-    pool = torch.from_numpy(cache.pool.copy()).cuda()
-    ptrs = torch.tensor([pool.data_ptr() + int(b) * cache.block_bytes for t in tables for b in t], dtype=torch.int64,
-                        device="cuda")
-    cu_blocks = torch.tensor(np.concatenate([[0], np.cumsum(blocks_per)]), dtype=torch.int32, device="cuda")
-    cu_q = torch.arange(B + 1, dtype=torch.int32, device="cuda")
-    cu_k = torch.tensor(np.concatenate([[0], np.cumsum(hist + 1)]), dtype=torch.int32, device="cuda")
-    d_out = torch.zeros(B, dtype=torch.int32, device="cuda")
-    m.decode_step(batch=B, token_ids=torch.from_numpy(tokens).cuda(), cu_q_len=cu_q, cu_k_len=cu_k, block_ptrs=ptrs,
-                  cu_block_nums=cu_blocks, out_tokens=d_out, max_k_len=int(hist.max()) + 1)
-    torch.cuda.synchronize()
-    got = from_dev_T(m.logits(B), F16)
-    ref, ref_tokens = decode_step(w, tokens, cache, tables, hist, rope, eps=m.cfg.norm_eps)
-    assert np.abs(got - ref).max() <= 4e-3
-    srt = np.sort(ref, -1)
-    for b in range(B):
-        if srt[b, -1] - srt[b, -2] > 8e-3:
-            assert d_out.cpu().numpy()[b] == ref_tokens[b]
-
-
-@pytest.mark.parametrize("dtype", [F16, BF16])
-def test_qk_rmsnorm_is_bit_identical_to_the_reference_kernel(lib, dtype):
-    """Ours against the REFERENCE's invokeQkRMSNorm (oracle/_ref/libtm_ref_norm.so) on the same buffers.  The kernel was
-    written to the reference's compiled instruction order, so the bar is equality, not a tolerance."""
-    import torch
-    from lmdeploy_b200 import _lib as L
-    from oracle import ref_lib
-    from harness import to_dev_T
-    if not ref_lib.norm_available():
-        pytest.skip("oracle/_ref/libtm_ref_norm.so not built")
-    ref = ref_lib.load_norm()
-    if not hasattr(ref, "ref_qk_rmsnorm"):
-        pytest.skip("libtm_ref_norm.so predates ref_qk_rmsnorm")
-    rng = np.random.default_rng(12)
-    for (Hq, Hkv, T) in ((8, 2, 37), (32, 8, 64), (28, 4, 5)):
-        width = (Hq + 2 * Hkv) * 128
-        qkv = rn((rng.standard_normal((T, width)) * rng.uniform(0.01, 30)).astype(np.float32), dtype)
-        qw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
-        kw = rn((1 + 0.2 * rng.standard_normal(128)).astype(np.float32), dtype)
-        a, b = to_dev_T(qkv, dtype), to_dev_T(qkv, dtype)
-        dq, dk = to_dev_T(qw, dtype), to_dev_T(kw, dtype)
-        st = torch.cuda.current_stream().cuda_stream
-        dt = 0 if dtype == F16 else 1
-        L.check(lib.b200_qk_rmsnorm(a.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6, dt, st), "ours")
-        assert ref.ref_qk_rmsnorm(b.data_ptr(), width, dq.data_ptr(), dk.data_ptr(), T, Hq, Hkv, 128, 1e-6, dt, st) == 0
-        torch.cuda.synchronize()
-        assert torch.equal(a.view(torch.int16), b.view(torch.int16)), (Hq, Hkv, T)

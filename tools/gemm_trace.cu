@@ -185,6 +185,8 @@ int main(int argc, char** argv)
                 const long long t0 = h[c][4][0];
                 printf("  cta %d: start 0, tmem-alloc done %lld, dready %lld, epilogue done %lld\n", c, h[c][4][1] - t0,
                        h[c][4][2] - t0, h[c][4][3] - t0);
+                printf("    after pdl_launch_dependents %lld, partials written+fence %lld, all partials arrived %lld, reduce done %lld, "
+                       "kernel end %lld\n", h[c][7][4] - t0, h[c][7][0] - t0, h[c][7][1] - t0, h[c][7][2] - t0, h[c][7][3] - t0);
                 printf("    %4s %9s %9s %9s %9s %9s %9s\n", "i", "w-issue", "x-issue", "w-full", "a-ready", "mma-issue", "commit");
                 for (int i = 0; i < kTraceSlots && h[c][0][i]; ++i) {
                     printf("    %4d %9lld %9lld %9lld %9lld %9lld %9lld\n", i, h[c][0][i] - t0, h[c][6][i] - t0, h[c][1][i] - t0,
