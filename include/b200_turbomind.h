@@ -122,7 +122,9 @@ typedef struct {
     int              dtype;
 
     /* workspace: b200_decode_attention_workspace_bytes() bytes, 256-byte aligned.  Stands where
-     * split_cnt / partial_O / partial_ML (unified_attention_layer.cc:220-224) stand in the reference. */
+     * split_cnt / partial_O / partial_ML (unified_attention_layer.cc:220-224) stand in the reference.  Like the reference's
+     * GEMM barriers it must be ZERO when first used (it holds the arrival counters of the in-kernel fix-up, which every
+     * launch leaves at zero again; a call that plans internally also clears them). */
     void*  workspace;
     size_t workspace_bytes;
 
@@ -137,8 +139,10 @@ typedef struct {
      * b200_linear_forward_packed (fuses the repack in front of the `wo` GEMM); 0: token-major rows. */
     int out_packed_mt;
 
-    /* profiling aid: bit 0 = skip the prologue (q/k/v of this step already processed by a previous identical
-     * call), bit 1 = skip the fix-up kernel.  0 in production. */
+    /* profiling aid: bit 0 = skip the prologue (bias, RoPE, KV quantise + page store), bit 1 = skip the fix-up merge,
+     * bit 2 = run the three-kernel form (prologue kernel, main kernel, fix-up kernel) instead of the single fused kernel
+     * (with bits 0-1: the main kernel alone, reading the rotated q an earlier bit-2 call left in the workspace).
+     * 0 in production. */
     int debug_flags;
 
     void* stream;

@@ -35,6 +35,12 @@ B200_DEVICE void fence_proxy_async()
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// generic <-> async proxy ordering for GLOBAL memory touched by bulk copies on both sides of a generic-proxy handshake
+B200_DEVICE void fence_proxy_async_all()
+{
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
 B200_DEVICE void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -87,6 +93,18 @@ B200_DEVICE void bulk_g2s_hint(uint32_t dst_smem, const void* src, uint32_t byte
         "r"(bar),
         "l"(policy)
         : "memory");
+}
+
+// 1-D bulk async copy shared -> global (bulk-group completion): commit, then wait until the writes are performed
+B200_DEVICE void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+B200_DEVICE void bulk_commit_wait_all()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 B200_DEVICE uint64_t make_evict_first_policy()
@@ -166,6 +184,7 @@ struct TypeOps<half> {
     static B200_DEVICE half fma(half a, half b, half c) { return __hfma(a, b, c); }
     static B200_DEVICE half neg(half a) { return __hneg(a); }
     static B200_DEVICE half from_bits(uint16_t b) { return __ushort_as_half(b); }
+    static B200_DEVICE uint16_t to_bits(half x) { return __half_as_ushort(x); }
     static B200_DEVICE uint32_t fma2(uint32_t a, uint32_t b, uint32_t c)
     {
         uint32_t d;
@@ -232,6 +251,7 @@ struct TypeOps<nv_bfloat16> {
     static B200_DEVICE nv_bfloat16 fma(nv_bfloat16 a, nv_bfloat16 b, nv_bfloat16 c) { return __hfma(a, b, c); }
     static B200_DEVICE nv_bfloat16 neg(nv_bfloat16 a) { return __hneg(a); }
     static B200_DEVICE nv_bfloat16 from_bits(uint16_t b) { return __ushort_as_bfloat16(b); }
+    static B200_DEVICE uint16_t to_bits(nv_bfloat16 x) { return __bfloat16_as_ushort(x); }
     static B200_DEVICE uint32_t fma2(uint32_t a, uint32_t b, uint32_t c)
     {
         uint32_t d;

@@ -10,20 +10,6 @@
 namespace b200 {
 namespace attn {
 
-// ------------------------------------------------------------------------------------------------
-// RoPE constants: init_rope_kernel_param (src/turbomind/models/attention_weight.cc:37-93)
-// ------------------------------------------------------------------------------------------------
-struct RopeConst {
-    int   type;
-    int   dim;
-    float scale_factor;
-    float inv_factor;
-    float attention_scaling;
-    float llama3_alpha, llama3_beta;
-    float yarn_div2, yarn_mulmin;
-    int   exact;  // b200_rope_config::exact_math
-};
-
 static RopeConst make_rope_const(const b200_rope_config& r)
 {
     RopeConst c{};
@@ -55,85 +41,16 @@ static RopeConst make_rope_const(const b200_rope_config& r)
     return c;
 }
 
-__device__ __forceinline__ float mul_ftz(float a, float b)
-{
-    float c;
-    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(c) : "f"(a), "f"(b));
-    return c;
-}
-__device__ __forceinline__ float fma_ftz(float a, float b, float c)
-{
-    float d;
-    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
-
-// inv_freq of the pair starting at even dim `idx` (rotary_embedding.h:10-52).
-// Default: the instruction sequence of the reference's release build (--use_fast_math: ex2.approx.ftz, ftz
-// multiplies, mul+add contracted to fma) so results are bit-identical to TurboMind on the same GPU; `exact`:
-// correctly rounded exp2 and un-fused fp32 ops (what the CPU oracle computes).
-__device__ __forceinline__ float rope_inv_freq(const RopeConst& r, int idx)
-{
-    if (r.exact) {
-        const float e    = __fmul_rn((float)idx, r.scale_factor);
-        const float freq = (float)exp2((double)e);
-        if (r.type == 5) {
-            float sm = fmaf(r.llama3_alpha, freq, -r.llama3_beta);
-            sm       = fmaxf(0.f, fminf(1.f, sm));
-            const float a = __fmul_rn(__fsub_rn(1.f, sm), freq);
-            const float b = __fmul_rn(a, r.inv_factor);
-            const float c = __fmul_rn(sm, freq);
-            return __fadd_rn(b, c);
-        }
-        if (r.type == 4) {
-            float alpha = __fsub_rn(__fmul_rn((float)idx, r.yarn_div2), r.yarn_mulmin);
-            alpha       = fmaxf(0.f, fminf(1.f, alpha));
-            const float t = __fmul_rn(__fmul_rn(freq, alpha), __fsub_rn(1.f, r.inv_factor));
-            return __fsub_rn(freq, t);
-        }
-        return __fmul_rn(r.inv_factor, freq);
-    }
-    const float freq = exp2_approx(mul_ftz((float)idx, r.scale_factor));
-    if (r.type == 5) {
-        // (1 - smooth) * freq * inv_factor + smooth * freq
-        float sm = fma_ftz(r.llama3_alpha, freq, -r.llama3_beta);
-        sm       = fmaxf(0.f, fminf(1.f, sm));
-        const float a = mul_ftz(mul_ftz(1.f - sm, freq), r.inv_factor);
-        return fma_ftz(sm, freq, a);
-    }
-    if (r.type == 4) {
-        // freq - freq * alpha * (1 - inv_factor)
-        float alpha = fma_ftz((float)idx, r.yarn_div2, -r.yarn_mulmin);
-        alpha       = fmaxf(0.f, fminf(1.f, alpha));
-        const float t = mul_ftz(freq, alpha);
-        return fma_ftz(-t, 1.f - r.inv_factor, freq);
-    }
-    return mul_ftz(r.inv_factor, freq);
-}
-
-__device__ __forceinline__ float2 rope_cos_sin(const RopeConst& r, int idx, int pos)
-{
-    if (r.exact) {
-        const float ang = __fmul_rn((float)pos, rope_inv_freq(r, idx));
-        double      s, c;
-        sincos((double)ang, &s, &c);
-        return make_float2(__fmul_rn((float)c, r.attention_scaling), __fmul_rn((float)s, r.attention_scaling));
-    }
-    // sincosf under --use_fast_math = sin.approx.ftz / cos.approx.ftz of the ftz product (no range reduction)
-    const float ang = mul_ftz((float)pos, rope_inv_freq(r, idx));
-    float       s, c;
-    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
-    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
-    return make_float2(mul_ftz(c, r.attention_scaling), mul_ftz(s, r.attention_scaling));
-}
-
 // ------------------------------------------------------------------------------------------------
 // plan: tiles per sequence prefix + (optionally) cos/sin table of the decode positions
 // ------------------------------------------------------------------------------------------------
-__global__ void plan_kernel(int* plan, const int* cu_k_len, const uint8_t* finished, int batch)
+__global__ void plan_kernel(int* plan, const int* cu_k_len, const uint8_t* finished, int batch, int* zero, int nzero)
 {
     pdl_launch_dependents();
     pdl_wait();
+    for (int i = threadIdx.x; i < nzero; i += blockDim.x) {
+        zero[i] = 0;  // arrival counters of the in-kernel fix-up (a launch that was aborted may have left some armed)
+    }
     // one block; serial scan by chunks of blockDim
     __shared__ int s_scan[1024];
     __shared__ int s_base;
@@ -218,13 +135,6 @@ struct PrologueParams {
     RopeConst   rope;
     const float2* rope_table;  // [token][kHeadDim/2] (cos, sin) or null
 };
-
-template<class T>
-__device__ __forceinline__ void load4(const T* p, T (&x)[4])
-{
-    uint2 u                          = *reinterpret_cast<const uint2*>(p);
-    *reinterpret_cast<uint2*>(&x[0]) = u;
-}
 
 template<class T, int KVBITS>
 __global__ void __launch_bounds__(128) kv_prologue_kernel(const PrologueParams p)
@@ -432,6 +342,7 @@ struct Workspace {
     float* partial_O;
     float* partial_ML;
     int*   plan;
+    int*   seg_counters;
     size_t total;
 };
 
@@ -448,6 +359,9 @@ static Workspace carve(void* base, int token_num, int batch, int num_heads)
     w.partial_O  = (float*)take((size_t)2 * kMaxGridBound * kMaxGroup * kHeadDim * 4);
     w.partial_ML = (float*)take((size_t)2 * kMaxGridBound * kMaxGroup * 2 * 4);
     w.plan       = (int*)take((size_t)(batch + 1) * 4);
+    // arrival counters of the in-kernel fix-up, one per (sequence, kv-head): must be zero on first use (the kernel re-arms
+    // them; the op's own plan launch clears them as well); sized for the largest kv-head count per group size 1
+    w.seg_counters = (int*)take((size_t)batch * num_heads * 4);
     w.total      = off;
     return w;
 }
@@ -525,15 +439,23 @@ static int launch_decode(const b200_attention_params* a)
     if (!a->workspace || a->workspace_bytes < w.total) {
         return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_decode_attention_workspace_bytes)");
     }
+    // debug_flags bit 2: the round-1 three-kernel form (separate prologue kernel, main kernel, fix-up kernel) instead of the
+    // single fused kernel; B200_ATTN_UNFUSED=1 selects it process-wide (A/B measurements, fallback)
+    static const bool env_unfused = [] {
+        const char* e = getenv("B200_ATTN_UNFUSED");
+        return e && *e && *e != '0';
+    }();
+    const bool unfused = env_unfused || (a->debug_flags & 4);
     const int* plan = a->plan;
     if (!plan) {
-        launch_k(plan_kernel, dim3(1), dim3(256), 0, st, w.plan, a->cu_k_len, a->finished, a->batch_size);
+        launch_k(plan_kernel, dim3(1), dim3(256), 0, st, w.plan, a->cu_k_len, a->finished, a->batch_size, w.seg_counters,
+                 a->batch_size * a->num_kv_heads);
         if (int e = check_launch("plan_kernel")) {
             return e;
         }
         plan = w.plan;
     }
-    if (!(a->debug_flags & 1)) {
+    if (unfused && !(a->debug_flags & 1)) {
         if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st)) {
             return e;
         }
@@ -561,11 +483,23 @@ static int launch_decode(const b200_attention_params* a)
     p.num_kv_heads  = a->num_kv_heads;
     p.qk_scale      = a->inv_sqrt_dh;
     p.out_mt        = a->out_packed_mt;
+    p.grid_main     = grid;
+    if (!unfused) {
+        // debug_flags bit 0 / bit 1 keep their meaning (skip the prologue / the fix-up) for kernel-only timing
+        p.fused = ((a->debug_flags & 1) ? 0 : 1) | ((a->debug_flags & 2) ? 0 : 2);
+        p.q = a->q, p.k = a->k, p.v = a->v, p.stride = a->stride;
+        p.q_bias = a->q_bias, p.k_bias = a->k_bias, p.v_bias = a->v_bias;
+        p.cu_q_len           = a->cu_q_len;
+        p.readonly_block_num = a->readonly_block_num;
+        p.rope_table         = reinterpret_cast<const float2*>(a->rope_table);
+        p.rope               = make_rope_const(a->rope);
+        p.seg_counters       = w.seg_counters;
+    }
     launch_k(decode_attention_kernel<T, KVBITS, STAGES>, dim3(grid), dim3(kThreads), sizeof(SS), st, p);
     if (int e = check_launch("decode_attention_kernel")) {
         return e;
     }
-    if (a->debug_flags & 2) {
+    if ((a->debug_flags & 2) || !unfused) {
         return 0;
     }
     dim3 rgrid(a->num_kv_heads, a->batch_size);
@@ -658,7 +592,7 @@ extern "C" int b200_decode_attention_plan(int* plan, const int* cu_k_len, const 
     if (!plan || !cu_k_len || batch_size <= 0) {
         return fail(B200_ERR_INVALID_ARG, "bad plan arguments");
     }
-    launch_k(plan_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, plan, cu_k_len, finished, batch_size);
+    launch_k(plan_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, plan, cu_k_len, finished, batch_size, (int*)nullptr, 0);
     return check_launch("plan_kernel");
 }
 

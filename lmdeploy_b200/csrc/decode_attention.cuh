@@ -49,6 +49,189 @@ struct TileCfg {
     static constexpr int kOffVP = 2 * kTileBytes + kParamBytes;
 };
 
+// ------------------------------------------------------------------------------------------------
+// RoPE constants: init_rope_kernel_param (src/turbomind/models/attention_weight.cc:37-93)
+// ------------------------------------------------------------------------------------------------
+struct RopeConst {
+    int   type;
+    int   dim;
+    float scale_factor;
+    float inv_factor;
+    float attention_scaling;
+    float llama3_alpha, llama3_beta;
+    float yarn_div2, yarn_mulmin;
+    int   exact;  // b200_rope_config::exact_math
+};
+
+
+__device__ __forceinline__ float mul_ftz(float a, float b)
+{
+    float c;
+    asm("mul.ftz.f32 %0, %1, %2;" : "=f"(c) : "f"(a), "f"(b));
+    return c;
+}
+__device__ __forceinline__ float fma_ftz(float a, float b, float c)
+{
+    float d;
+    asm("fma.rn.ftz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// inv_freq of the pair starting at even dim `idx` (rotary_embedding.h:10-52).
+// Default: the instruction sequence of the reference's release build (--use_fast_math: ex2.approx.ftz, ftz
+// multiplies, mul+add contracted to fma) so results are bit-identical to TurboMind on the same GPU; `exact`:
+// correctly rounded exp2 and un-fused fp32 ops (what the CPU oracle computes).
+__device__ __forceinline__ float rope_inv_freq(const RopeConst& r, int idx)
+{
+    if (r.exact) {
+        const float e    = __fmul_rn((float)idx, r.scale_factor);
+        const float freq = (float)exp2((double)e);
+        if (r.type == 5) {
+            float sm = fmaf(r.llama3_alpha, freq, -r.llama3_beta);
+            sm       = fmaxf(0.f, fminf(1.f, sm));
+            const float a = __fmul_rn(__fsub_rn(1.f, sm), freq);
+            const float b = __fmul_rn(a, r.inv_factor);
+            const float c = __fmul_rn(sm, freq);
+            return __fadd_rn(b, c);
+        }
+        if (r.type == 4) {
+            float alpha = __fsub_rn(__fmul_rn((float)idx, r.yarn_div2), r.yarn_mulmin);
+            alpha       = fmaxf(0.f, fminf(1.f, alpha));
+            const float t = __fmul_rn(__fmul_rn(freq, alpha), __fsub_rn(1.f, r.inv_factor));
+            return __fsub_rn(freq, t);
+        }
+        return __fmul_rn(r.inv_factor, freq);
+    }
+    const float freq = exp2_approx(mul_ftz((float)idx, r.scale_factor));
+    if (r.type == 5) {
+        // (1 - smooth) * freq * inv_factor + smooth * freq
+        float sm = fma_ftz(r.llama3_alpha, freq, -r.llama3_beta);
+        sm       = fmaxf(0.f, fminf(1.f, sm));
+        const float a = mul_ftz(mul_ftz(1.f - sm, freq), r.inv_factor);
+        return fma_ftz(sm, freq, a);
+    }
+    if (r.type == 4) {
+        // freq - freq * alpha * (1 - inv_factor)
+        float alpha = fma_ftz((float)idx, r.yarn_div2, -r.yarn_mulmin);
+        alpha       = fmaxf(0.f, fminf(1.f, alpha));
+        const float t = mul_ftz(freq, alpha);
+        return fma_ftz(-t, 1.f - r.inv_factor, freq);
+    }
+    return mul_ftz(r.inv_factor, freq);
+}
+
+__device__ __forceinline__ float2 rope_cos_sin(const RopeConst& r, int idx, int pos)
+{
+    if (r.exact) {
+        const float ang = __fmul_rn((float)pos, rope_inv_freq(r, idx));
+        double      s, c;
+        sincos((double)ang, &s, &c);
+        return make_float2(__fmul_rn((float)c, r.attention_scaling), __fmul_rn((float)s, r.attention_scaling));
+    }
+    // sincosf under --use_fast_math = sin.approx.ftz / cos.approx.ftz of the ftz product (no range reduction)
+    const float ang = mul_ftz((float)pos, rope_inv_freq(r, idx));
+    float       s, c;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(ang));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(ang));
+    return make_float2(mul_ftz(c, r.attention_scaling), mul_ftz(s, r.attention_scaling));
+}
+
+
+// bias + RoPE of 4 consecutive dims [di, di + 4) of one head vector, T arithmetic exactly as the reference binary's
+// (rotary_embedding.h:168-181 compiled with --use_fast_math: `c*x0 - s*x1` contracted to HMUL2 + HFMA2)
+template<class T>
+__device__ __forceinline__ void rope_rotate4(T (&x)[4], const float2 (&cs)[2], const RopeConst& rope, int di)
+{
+    using Ops = TypeOps<T>;
+    if (rope.type == 0) {
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (di + 2 * i < rope.dim) {
+            const T c = Ops::from_f32(cs[i].x), s = Ops::from_f32(cs[i].y);
+            const T a = x[2 * i], bb = x[2 * i + 1];
+            x[2 * i]     = Ops::fma(c, a, Ops::neg(Ops::mul(s, bb)));
+            x[2 * i + 1] = Ops::fma(c, bb, Ops::mul(s, a));
+        }
+    }
+}
+
+// out of line: the exact-math variant drags double-precision sincos (and its stack frame) into whoever inlines it
+__device__ __noinline__ float2 rope_cos_sin_call(const RopeConst& r, int idx, int pos)
+{
+    return rope_cos_sin(r, idx, pos);
+}
+
+// (cos, sin) of the two pairs starting at even dim `di` for position `ti`: from the per-step table when there is one
+__device__ __forceinline__ void rope_cs2(float2 (&cs)[2], const RopeConst& rope, const float2* table, int tok, int di, int ti)
+{
+    if (table) {
+        const float4 v = *reinterpret_cast<const float4*>(table + (size_t)tok * (kHeadDim / 2) + (di >> 1));
+        cs[0]          = make_float2(v.x, v.y);
+        cs[1]          = make_float2(v.z, v.w);
+    }
+    else {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            cs[i] = (rope.type != 0 && di + 2 * i < rope.dim) ? rope_cos_sin_call(rope, di + 2 * i, ti) : make_float2(1.f, 0.f);
+        }
+    }
+}
+
+template<class T>
+__device__ __forceinline__ void load4(const T* p, T (&x)[4])
+{
+    uint2 u                          = *reinterpret_cast<const uint2*>(p);
+    *reinterpret_cast<uint2*>(&x[0]) = u;
+}
+
+// Quantise one K or V head vector spread over a warp (lane = 4 consecutive dims): warp_stats + ConvertKvCache
+// (quantization.h:341-366, 427-490).  Returns this lane's packed bytes in `bytes` (int8: 4 bytes; int4: the even lane of a pair
+// holds 4 bytes covering 8 dims, valid = false on odd lanes) and the (scale, zero) pair as two T in one u32.
+template<class T, int KVBITS>
+__device__ __forceinline__ void quantize_head(const T (&x)[4], int lane, uint32_t& bytes, bool& valid, uint32_t& param)
+{
+    using Ops = TypeOps<T>;
+    float mn = Ops::to_f32(x[0]), mx = mn;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) {
+        mn = fminf(mn, Ops::to_f32(x[i]));
+        mx = fmaxf(mx, Ops::to_f32(x[i]));
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, m));
+    }
+    constexpr float inv_q_max = 1.0f / (float)((1 << KVBITS) - 1);
+    const T         scale     = Ops::from_f32(__fmul_rn(__fsub_rn(mx, mn), inv_q_max));
+    const T         zero      = Ops::from_f32(mn);
+    const T         inv_scale = Ops::from_f32(__fdiv_rn(1.f, Ops::to_f32(scale)));
+    uint32_t        q[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        q[i] = Ops::round_u8(Ops::mul(Ops::sub(x[i], zero), inv_scale));
+        if (KVBITS == 4) {
+            q[i] = min(q[i], 15u);
+        }
+    }
+    if constexpr (KVBITS == 8) {
+        bytes = q[0] | (q[1] << 8) | (q[2] << 16) | (q[3] << 24);
+        valid = true;
+    }
+    else {
+        // nibble j of each u32 holds element [0,2,4,6,1,3,5,7][j]  (ConvertKvCache<T,uint4_t>::pack)
+        const uint32_t mine = (lane & 1) ? ((q[0] << 8) | (q[2] << 12) | (q[1] << 24) | (q[3] << 28)) :
+                                           ((q[0]) | (q[2] << 4) | (q[1] << 16) | (q[3] << 20));
+        const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        bytes = mine | other;
+        valid = (lane & 1) == 0;
+    }
+    T pr[2] = {scale, zero};
+    param   = *reinterpret_cast<uint32_t*>(&pr[0]);
+}
+
 struct KernelParams {
     const void* q_rot;  // [token][Hq][D]  (bias + RoPE applied)
     void*       out;    // [token][Hq*D], row stride out_stride elements
@@ -66,6 +249,24 @@ struct KernelParams {
     int         num_kv_heads;
     float       qk_scale;  // log2(e)/sqrt(D)  (AttentionParams::inv_sqrt_dh)
     int         out_mt;    // > 0: write `out` in the UMMA K-major tile layout [Hq*D/8][out_mt][8]
+    // ---- in-kernel prologue (fused & 1): bias + RoPE of q at segment start, and the warp that owns the new token's slot
+    // quantises K/V, stores them into the page and patches its shared-memory tile (attention_universal.h:168-348 does the
+    // same inside the reference kernel); q_rot is then unused
+    int            fused;  // bit 0: in-kernel prologue, bit 1: in-kernel fix-up (the CTA that completes a straddling
+                           // (sequence, kv-head) last merges its partials; no reduce kernel)
+    const void*    q;
+    const void*    k;
+    const void*    v;
+    int64_t        stride;
+    const void*    q_bias;
+    const void*    k_bias;
+    const void*    v_bias;
+    const int*     cu_q_len;
+    const int*     readonly_block_num;
+    const float2*  rope_table;
+    RopeConst      rope;
+    int*           seg_counters;  // [batch * Hkv] arrivals per straddling segment; zero on entry, left zero
+    int            grid_main;
 };
 
 // slot (0..15 inside a warp's 16-key MMA) -> token index inside the 64-token tile
@@ -158,6 +359,7 @@ struct SharedStorage {
     float    merge_L[kConsumerWarps][kMaxGroup];
     float    final_M[kMaxGroup];
     float    final_L[kMaxGroup];
+    int      fix[4];  // in-kernel fix-up: first / last CTA of the segment, partial slot of the first, "this CTA merges"
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
 };
@@ -399,6 +601,145 @@ B200_DEVICE void process_tile(const ConsumerCtx<T, KVBITS>& cx, uint32_t st, boo
 
 }
 
+B200_DEVICE void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+B200_DEVICE void sts64(uint32_t addr, uint2 v)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// In-kernel prologue for the new token of (sequence b, kv-head h) at cache position ti (= tile slot `pos`): one warp,
+// lane = 4 consecutive dims (the mapping of kv_prologue_kernel, whose arithmetic this repeats instruction for instruction).
+template<class T, int KVBITS>
+__device__ __noinline__ void new_token_kv(const KernelParams& p, int b, int h, int ti, int pos, int lane, uint32_t st)
+{
+    using Ops = TypeOps<T>;
+    using Cfg = TileCfg<KVBITS>;
+    const int ro_len = p.readonly_block_num ? p.readonly_block_num[b] * p.block_len : 0;
+    if (ti < ro_len) {
+        return;  // inside a shared read-only prefix block: the page already holds this position
+    }
+    const int tok = p.cu_q_len ? p.cu_q_len[b] : b;
+    const int di  = lane * 4;
+    T         xk[4], xv[4];
+    load4(reinterpret_cast<const T*>(p.k) + (size_t)tok * p.stride + (size_t)h * kHeadDim + di, xk);
+    load4(reinterpret_cast<const T*>(p.v) + (size_t)tok * p.stride + (size_t)h * kHeadDim + di, xv);
+    if (p.k_bias) {
+        T bk[4], bv[4];
+        load4(reinterpret_cast<const T*>(p.k_bias) + (size_t)h * kHeadDim + di, bk);
+        load4(reinterpret_cast<const T*>(p.v_bias) + (size_t)h * kHeadDim + di, bv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xk[i] = Ops::add(xk[i], bk[i]);
+            xv[i] = Ops::add(xv[i], bv[i]);
+        }
+    }
+    float2 cs[2];
+    rope_cs2(cs, p.rope, p.rope_table, tok, di, ti);
+    rope_rotate4<T>(xk, cs, p.rope, di);
+
+    constexpr int kRow          = Cfg::kRowBytes;
+    const int     head_data_sz  = p.block_len * kRow;
+    const int     head_param_sz = p.block_len * 4;
+    char*         blk = p.block_ptrs[p.cu_block_nums[b] + ti / p.block_len] + p.layer_offset;
+    const int     bt  = ti % p.block_len;
+    char*         kd  = blk + (size_t)(h * 2) * head_data_sz + (size_t)bt * kRow;
+    char*         vd  = kd + head_data_sz;
+    const uint32_t srow = token_smem_offset<KVBITS>(pos);
+    if constexpr (KVBITS == 16) {
+        const uint2 uk = *reinterpret_cast<uint2*>(&xk[0]), uv = *reinterpret_cast<uint2*>(&xv[0]);
+        *reinterpret_cast<uint2*>(kd + 8 * lane) = uk;
+        *reinterpret_cast<uint2*>(vd + 8 * lane) = uv;
+        sts64(st + Cfg::kOffK + srow + 8 * lane, uk);
+        sts64(st + Cfg::kOffV + srow + 8 * lane, uv);
+    }
+    else {
+        char* kp = blk + (size_t)p.num_kv_heads * 2 * head_data_sz + (size_t)(h * 2) * head_param_sz + (size_t)bt * 4;
+        char* vp = kp + head_param_sz;
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+            uint32_t bytes, param;
+            bool     valid;
+            quantize_head<T, KVBITS>(kv ? xv : xk, lane, bytes, valid, param);
+            char*          dd   = kv ? vd : kd;
+            const uint32_t sdat = st + (kv ? Cfg::kOffV : Cfg::kOffK) + srow;
+            if constexpr (KVBITS == 8) {
+                *reinterpret_cast<uint32_t*>(dd + 4 * lane) = bytes;
+                sts32(sdat + 4 * lane, bytes);
+            }
+            else if (valid) {
+                *reinterpret_cast<uint32_t*>(dd + 4 * (lane >> 1)) = bytes;
+                sts32(sdat + 4 * (lane >> 1), bytes);
+            }
+            if (lane == 0) {
+                *reinterpret_cast<uint32_t*>(kv ? vp : kp) = param;
+                sts32(st + (kv ? Cfg::kOffVP : Cfg::kOffKP) + pos * 4, param);
+            }
+        }
+    }
+}
+
+// Merge of the partials of one (sequence b, kv-head h) segment that straddled main-kernel CTAs cf..cl.
+// Same math as attention::reduce (reduce.cu:90-153): O = sum_k w_k O_k / sum_k w_k L_k, w_k = exp2((M_k - M) * c),
+// partials visited in ascending CTA order whoever runs the merge (deterministic).  Loads bypass L1 (ld.global.cg): the
+// partials may have been written by other SMs during this very kernel.
+template<class T>
+__device__ __noinline__ void merge_segment(const KernelParams& p, int b, int h, int cf, int cl, int first_slot, int tid, int nthreads)
+{
+    using Ops     = TypeOps<T>;
+    const int   G = p.num_heads / p.num_kv_heads;
+    const float c = p.qk_scale;
+    // thread -> 4 consecutive dims of one head (float4 partial loads)
+    for (int i4 = tid; i4 < G * kHeadDim / 4; i4 += nthreads) {
+        const int i  = i4 * 4;
+        const int hd = i / kHeadDim;
+        float     m  = -INFINITY;
+        for (int cta = cf; cta <= cl; ++cta) {
+            const int slot = 2 * cta + (cta == cf ? first_slot : 0);
+            m              = fmaxf(m, __ldcg(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]));
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float  l   = 0.f;
+        for (int cta = cf; cta <= cl; ++cta) {
+            const int    slot = 2 * cta + (cta == cf ? first_slot : 0);
+            const float2 ml   = __ldcg(reinterpret_cast<const float2*>(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]));
+            const float  w    = (ml.x == -INFINITY) ? 0.f : exp2_approx((ml.x - m) * c);
+            const float4 o    = __ldcg(reinterpret_cast<const float4*>(&p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i]));
+            l += w * ml.y;
+            acc.x += w * o.x, acc.y += w * o.y, acc.z += w * o.z, acc.w += w * o.w;
+        }
+        const int col = h * G * kHeadDim + i;
+        T*        dst = reinterpret_cast<T*>(p.out)
+                 + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + b) * 8 + (col & 7) : (size_t)b * p.out_stride + col);
+        uint2 v;
+        v.x = Ops::pack2(acc.x / l, acc.y / l);
+        v.y = Ops::pack2(acc.z / l, acc.w / l);
+        *reinterpret_cast<uint2*>(dst) = v;
+    }
+}
+
+// segment (b, h) -> main-kernel CTA range [cf, cl] and the partial slot CTA cf used for it (64-bit divisions: one thread)
+B200_DEVICE void segment_ctas(const KernelParams& p, int b, int h, int grid_main, int& cf, int& cl, int& first_slot)
+{
+    const int       Hkv   = p.num_kv_heads;
+    const int       tiles = p.tile_prefix[b + 1] - p.tile_prefix[b];
+    const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
+    const long long s0    = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
+    const long long s1    = s0 + tiles;
+    cf                    = (int)(((s0 + 1) * grid_main - 1) / total);
+    cl                    = (int)((s1 * grid_main - 1) / total);
+    first_slot            = (total * cf / grid_main != s0) ? 1 : 0;
+}
+
+B200_DEVICE int atom_add_acq_rel_gpu(int* p, int v)
+{
+    int old;
+    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
 struct TileDesc {
     const char* blk;  // block base + layer offset
     int         h;
@@ -406,8 +747,17 @@ struct TileDesc {
     int         rows;  // valid tokens in the tile
 };
 
+// Resident CTAs per SM the register budget must allow (the shared-memory ring is sized for the same numbers): the tile
+// loop keeps ~125 registers live; the rare paths (new token's K/V, segment merge) are out-of-line calls so they cannot
+// inflate it.  __grid_constant__: those calls take the parameter block by reference without a local copy.
+template<int KVBITS>
+constexpr int min_ctas_per_sm()
+{
+    return KVBITS == 16 ? 2 : 3;
+}
+
 template<class T, int KVBITS, int STAGES>
-__global__ void __launch_bounds__(kThreads) decode_attention_kernel(const KernelParams p)
+__global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_attention_kernel(const __grid_constant__ KernelParams p)
 {
     using Ops = TypeOps<T>;
     using Cfg = TileCfg<KVBITS>;
@@ -550,15 +900,43 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
         const int ntile      = (int)min((long long)(it.tiles - it.tile), hi - idx);
         const int k_len      = p.cu_k_len[it.b + 1] - p.cu_k_len[it.b];
         {
-            const T* qb = reinterpret_cast<const T*>(p.q_rot) + ((size_t)it.b * p.num_heads + (size_t)it.h * G) * kHeadDim;
+            if (p.fused & 1) {
+                // RoPE applied in registers: every lane rotates the 4-dim chunks of its own B fragments
+                const int tokq = p.cu_q_len ? p.cu_q_len[it.b] : it.b;
+                const T*  qb   = reinterpret_cast<const T*>(p.q) + (size_t)tokq * p.stride + (size_t)it.h * G * kHeadDim;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                uint2 v = make_uint2(0u, 0u);
-                if (g < G) {
-                    v = *reinterpret_cast<const uint2*>(qb + (size_t)g * kHeadDim + qk_dim0<KVBITS>(t, j));
+                for (int j = 0; j < 8; ++j) {
+                    uint2 v = make_uint2(0u, 0u);
+                    if (g < G) {
+                        const int di = qk_dim0<KVBITS>(t, j);
+                        T         x[4];
+                        load4(qb + (size_t)g * kHeadDim + di, x);
+                        if (p.q_bias) {
+                            T bq[4];
+                            load4(reinterpret_cast<const T*>(p.q_bias) + (size_t)(it.h * G + g) * kHeadDim + di, bq);
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) x[i] = Ops::add(x[i], bq[i]);
+                        }
+                        float2 cs[2];
+                        rope_cs2(cs, p.rope, p.rope_table, tokq, di, k_len - 1);
+                        rope_rotate4<T>(x, cs, p.rope, di);
+                        v = *reinterpret_cast<uint2*>(&x[0]);
+                    }
+                    qf[j][0] = v.x;
+                    qf[j][1] = v.y;
                 }
-                qf[j][0] = v.x;
-                qf[j][1] = v.y;
+            }
+            else {
+                const T* qb = reinterpret_cast<const T*>(p.q_rot) + ((size_t)it.b * p.num_heads + (size_t)it.h * G) * kHeadDim;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint2 v = make_uint2(0u, 0u);
+                    if (g < G) {
+                        v = *reinterpret_cast<const uint2*>(qb + (size_t)g * kHeadDim + qk_dim0<KVBITS>(t, j));
+                    }
+                    qf[j][0] = v.x;
+                    qf[j][1] = v.y;
+                }
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -567,11 +945,36 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
             M[0] = M[1] = -INFINITY;
             L[0] = L[1] = 0.f;
         }
-        for (int tt = 0; tt < ntile; ++tt) {
+        // The tile that holds the new token (position k_len - 1, always the sequence's last tile) is peeled out of the loop:
+        // the out-of-line prologue call must not sit inside the loop (the ABI would pin the loop state in local memory).
+        const bool peel  = (p.fused & 1) && first_tile + ntile == it.tiles;
+        const int  nloop = ntile - (peel ? 1 : 0);
+        for (int tt = 0; tt < nloop; ++tt) {
             const int  t0      = (first_tile + tt) * kTile;
             const bool residue = t0 + kTile > k_len;
             mbar_wait(full0 + 8 * s, ph);
             process_tile<T, KVBITS>(cx, stage0 + s * (uint32_t)Cfg::kStageBytes, residue, k_len, t0, c, qf, O, M, L);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(empty0 + 8 * s);
+            }
+            if (++s == STAGES) {
+                s = 0;
+                ph ^= 1;
+            }
+        }
+        if (peel) {
+            const int t0 = (it.tiles - 1) * kTile;
+            mbar_wait(full0 + 8 * s, ph);
+            // The new token's slot belongs to exactly one consumer warp (slot_token: token & 15 = 4 * warp + i): that warp runs
+            // the prologue for this (sequence, kv-head) -- bias, RoPE(k), quantise, store into the page for later steps -- and
+            // overwrites the row the bulk copy brought in (stale bytes) in ITS OWN view of the tile; no other warp reads it.
+            const int pos = k_len - 1 - t0;
+            if (((pos >> 2) & 3) == warp) {
+                new_token_kv<T, KVBITS>(p, it.b, it.h, k_len - 1, pos, lane, stage0 + s * (uint32_t)Cfg::kStageBytes);
+                __syncwarp();
+            }
+            process_tile<T, KVBITS>(cx, stage0 + s * (uint32_t)Cfg::kStageBytes, true, k_len, t0, c, qf, O, M, L);
             __syncwarp();
             if (lane == 0) {
                 mbar_arrive(empty0 + 8 * s);
@@ -669,6 +1072,26 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
                 p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2]     = ss.final_M[ctid];
                 p.partial_ML[((size_t)slot * kMaxGroup + ctid) * 2 + 1] = ss.final_L[ctid];
             }
+            if (p.fused & 2) {
+                // In-kernel fix-up: arrive on the segment's counter (the CTA barrier orders every thread's partial stores
+                // before thread 0's gpu-scope acq_rel atomic); the CTA that arrives LAST merges all partials of the segment
+                // in CTA order -- the same sum whoever merges -- and re-arms the counter.
+                named_bar_sync(1, kConsumerWarps * 32);
+                if (ctid == 0) {
+                    int cf, cl, fs;
+                    segment_ctas(p, it.b, it.h, p.grid_main, cf, cl, fs);
+                    int*      ctr = p.seg_counters + it.b * Hkv + it.h;
+                    const int old = atom_add_acq_rel_gpu(ctr, 1);
+                    ss.fix[0] = cf, ss.fix[1] = cl, ss.fix[2] = fs, ss.fix[3] = (old == cl - cf);
+                    if (old == cl - cf) {
+                        *ctr = 0;  // every CTA of the segment has arrived: nobody touches the counter again in this launch
+                    }
+                }
+                named_bar_sync(1, kConsumerWarps * 32);
+                if (ss.fix[3]) {
+                    merge_segment<T>(p, it.b, it.h, ss.fix[0], ss.fix[1], ss.fix[2], ctid, kConsumerWarps * 32);
+                }
+            }
         }
         named_bar_sync(1, kConsumerWarps * 32);
 
@@ -679,67 +1102,29 @@ __global__ void __launch_bounds__(kThreads) decode_attention_kernel(const Kernel
     }
 }
 
-// Fix-up reduction over the partials of one (sequence, kv-head) segment that straddled CTAs.
-// Same math as attention::reduce (reduce.cu:90-153): O = sum_k w_k O_k / sum_k w_k L_k,
-// w_k = exp2((M_k - M) * c), partials visited in ascending CTA order.
+// Fix-up reduction as a separate kernel (used when the in-kernel fix-up is off).
 template<class T>
 __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
 {
     pdl_launch_dependents();
     pdl_wait();
-    using Ops          = TypeOps<T>;
-    const int       b   = blockIdx.y;
-    const int       h   = blockIdx.x;
-    const int       Hkv = p.num_kv_heads;
-    const int       G   = p.num_heads / Hkv;
-    const int       tiles = p.tile_prefix[b + 1] - p.tile_prefix[b];
+    const int b     = blockIdx.y;
+    const int h     = blockIdx.x;
+    const int tiles = p.tile_prefix[b + 1] - p.tile_prefix[b];
     if (tiles == 0) {
         return;
     }
-    // segment -> CTA range of the main kernel (64-bit divisions: once per block, by one thread)
     __shared__ int s_cf, s_cl, s_first_slot;
     if (threadIdx.x == 0) {
-        const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
-        const long long s0    = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
-        const long long s1    = s0 + tiles;
-        const int       cf    = (int)(((s0 + 1) * grid_main - 1) / total);
-        s_cf                  = cf;
-        s_cl                  = (int)((s1 * grid_main - 1) / total);
-        s_first_slot          = (total * cf / grid_main != s0) ? 1 : 0;
+        int cf, cl, fs;
+        segment_ctas(p, b, h, grid_main, cf, cl, fs);
+        s_cf = cf, s_cl = cl, s_first_slot = fs;
     }
     __syncthreads();
-    const int cf = s_cf, cl = s_cl;
-    if (cf == cl) {
+    if (s_cf == s_cl) {
         return;  // written directly by the main kernel
     }
-    const float c = p.qk_scale;
-    // thread -> 4 consecutive dims of one head (float4 partial loads)
-    for (int i4 = threadIdx.x; i4 < G * kHeadDim / 4; i4 += blockDim.x) {
-        const int i  = i4 * 4;
-        const int hd = i / kHeadDim;
-        float     m  = -INFINITY;
-        for (int cta = cf; cta <= cl; ++cta) {
-            const int slot = 2 * cta + (cta == cf ? s_first_slot : 0);
-            m              = fmaxf(m, p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]);
-        }
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        float  l   = 0.f;
-        for (int cta = cf; cta <= cl; ++cta) {
-            const int    slot = 2 * cta + (cta == cf ? s_first_slot : 0);
-            const float2 ml   = *reinterpret_cast<const float2*>(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]);
-            const float  w    = (ml.x == -INFINITY) ? 0.f : exp2_approx((ml.x - m) * c);
-            const float4 o    = *reinterpret_cast<const float4*>(&p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i]);
-            l += w * ml.y;
-            acc.x += w * o.x, acc.y += w * o.y, acc.z += w * o.z, acc.w += w * o.w;
-        }
-        const int col = h * G * kHeadDim + i;
-        T*        dst = reinterpret_cast<T*>(p.out)
-                 + (p.out_mt > 0 ? ((size_t)(col >> 3) * p.out_mt + b) * 8 + (col & 7) : (size_t)b * p.out_stride + col);
-        uint2 v;
-        v.x = Ops::pack2(acc.x / l, acc.y / l);
-        v.y = Ops::pack2(acc.z / l, acc.w / l);
-        *reinterpret_cast<uint2*>(dst) = v;
-    }
+    merge_segment<T>(p, b, h, s_cf, s_cl, s_first_slot, threadIdx.x, blockDim.x);
 }
 
 }  // namespace attn

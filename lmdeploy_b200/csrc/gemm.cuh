@@ -231,6 +231,14 @@ B200_DEVICE void finalize_pair(const Params& p, int tok, int n_g, float a0, floa
     }
 }
 
+B200_DEVICE void red_release_gpu_add(int* p, int v)
+{
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+B200_DEVICE void sts32(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 B200_DEVICE int ld_acquire_gpu(const int* p)
 {
     int v;
@@ -250,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     __shared__ uint64_t bar_xfull[kMaxX], bar_xempty[kMaxX];
     __shared__ uint64_t bar_aready[kASlots], bar_aempty[kASlots];
     __shared__ uint64_t bar_dready;
+    __shared__ uint64_t bar_xchg;  // split-K exchange: the bulk loads of the other splits' partial slices
     __shared__ uint32_t s_tmem;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
@@ -277,21 +286,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     const int      d_stride = p.MT <= 64 ? 64 : 128;
 
     if (threadIdx.x == 64) GEMM_TRACE(7, 4);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxW; ++s) {
-            mbar_init(smem_u32(&bar_wfull[s]), 1);
-            mbar_init(smem_u32(&bar_wempty[s]), kDequant ? kDqWarps * 32 : 1);
+    // one barrier per thread (a single thread initialising all 37 costs ~800 cycles before the first weight copy can be issued)
+    {
+        const int t = threadIdx.x;
+        if (t < kMaxW) {
+            mbar_init(smem_u32(&bar_wfull[t]), 1);
         }
-        for (int s = 0; s < kMaxX; ++s) {
-            mbar_init(smem_u32(&bar_xfull[s]), 1);
-            mbar_init(smem_u32(&bar_xempty[s]), kMmaWarps);
+        else if (t < 2 * kMaxW) {
+            mbar_init(smem_u32(&bar_wempty[t - kMaxW]), kDequant ? kDqWarps * 32 : 1);
         }
-        for (int s = 0; s < kASlots; ++s) {
-            mbar_init(smem_u32(&bar_aready[s]), kDqWarps * 32 / TILES);
-            mbar_init(smem_u32(&bar_aempty[s]), 1);
+        else if (t < 2 * kMaxW + kMaxX) {
+            mbar_init(smem_u32(&bar_xfull[t - 2 * kMaxW]), 1);
         }
-        mbar_init(smem_u32(&bar_dready), kMmaWarps);
-        fence_mbar_init();
+        else if (t < 2 * kMaxW + 2 * kMaxX) {
+            mbar_init(smem_u32(&bar_xempty[t - 2 * kMaxW - kMaxX]), kMmaWarps);
+        }
+        else if (t < 2 * kMaxW + 2 * kMaxX + kASlots) {
+            mbar_init(smem_u32(&bar_aready[t - 2 * kMaxW - 2 * kMaxX]), kDqWarps * 32 / TILES);
+        }
+        else if (t < 2 * kMaxW + 2 * kMaxX + 2 * kASlots) {
+            mbar_init(smem_u32(&bar_aempty[t - 2 * kMaxW - 2 * kMaxX - kASlots]), 1);
+        }
+        else if (t == 2 * kMaxW + 2 * kMaxX + 2 * kASlots) {
+            mbar_init(smem_u32(&bar_dready), kMmaWarps);
+        }
+        else if (t == 2 * kMaxW + 2 * kMaxX + 2 * kASlots + 1) {
+            mbar_init(smem_u32(&bar_xchg), 1);
+        }
+        if (t <= 2 * kMaxW + 2 * kMaxX + 2 * kASlots + 1) {
+            fence_mbar_init();
+        }
     }
     __syncthreads();
 
@@ -634,31 +658,83 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             const int half = TILES == 4 ? p.MT : p.MT >> 1;  // TILES == 4: one warp per (tile, lane quarter) takes every token
             const int tb = epi_half * half, te = tb + half;
             const uint32_t drow = trow + epi_tile * d_stride;
-            if (p.splits == 1) {
-                if (epi_active) {
-                    const int n_g = (nt0 + epi_tile) * kBN + n_local;
-                    for (int t0 = tb; t0 < te; t0 += 8) {
-                        uint32_t v[8];
-                        umma::ld_32x32b_x8(drow + t0, v);
-                        umma::wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) finalize<T>(p, t0 + i, n_g, __uint_as_float(v[i]));
+            // Accumulators -> fp32 staging tile [token][row] in the (now idle) operand rings: thread = row, so a warp's 32
+            // stores of one token are consecutive words (conflict-free).  Everything downstream -- the direct epilogue and
+            // the split-K exchange -- works in the token-major orientation, with wide accesses.  Row pitch: ROWS words, + 4
+            // when the direct epilogue reads it token-fastest (quarter-warp 128-bit loads then hit distinct bank groups).
+            if (epi_active) {
+                constexpr int  ROWS  = kBN * TILES;
+                const int      pitch = ROWS + (p.splits == 1 ? 4 : 0);
+                const uint32_t dst   = w_ring + (uint32_t)(epi_tile * kBN + n_local) * 4;
+                for (int t0 = tb; t0 < te; t0 += 32) {
+                    uint32_t v[2][16];
+                    umma::ld_32x32b_x16(drow + t0, v[0]);
+                    if (t0 + 16 < te) {
+                        umma::ld_32x32b_x16(drow + t0 + 16, v[1]);
                     }
-                }
-            }
-            else if (epi_active) {
-                // fp32 partial tile -> global exchange buffer [group][split][tok][row] (stays in L2)
-                constexpr int ROWS = kBN * TILES;
-                float* part = p.partials + ((size_t)blockIdx.x * p.splits + sp) * p.MT * ROWS + epi_tile * kBN + n_local;
-                for (int t0 = tb; t0 < te; t0 += 8) {
-                    uint32_t v[8];
-                    umma::ld_32x32b_x8(drow + t0, v);
                     umma::wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) __stcg(part + (size_t)(t0 + i) * ROWS, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) {
+                        if (t0 + i < te) {
+                            sts32(dst + (uint32_t)((t0 + i) * pitch) * 4, v[i >> 4][i & 15]);
+                        }
+                    }
+                }
+                if (p.splits > 1) {
+                    fence_proxy_async();  // the tile leaves through the async proxy (bulk store)
                 }
             }
             if (threadIdx.x == 64) GEMM_TRACE(4, 3);
+        }
+    }
+    if (p.splits == 1 && warp >= 2 && warp < kXWarp) {
+        // ============================== epilogue, part 2 (no split): staging tile -> bias / gated SiLU -> global ==============================
+        // unit = 8 output columns of one token: 128-bit reads of the staging tile, one 16-byte store
+        named_bar_sync(2, kDqWarps * 32);
+        constexpr int ROWS  = kBN * TILES;
+        const int     pitch = ROWS + 4;
+        const bool    gated = p.epilogue == 1;
+        const int     OC    = gated ? ROWS / 2 : ROWS;                    // output columns of this CTA
+        const int     c0    = gated ? nt0 * (kBN / 2) : nt0 * kBN;        // its first output column
+        const int     tid   = threadIdx.x - 64;
+        const int     UC    = OC / 8;                                     // units per token
+        T*            y     = reinterpret_cast<T*>(p.y);
+        const T*      bias  = reinterpret_cast<const T*>(p.bias);
+        for (int u = tid; u < UC * p.M; u += kDqWarps * 32) {
+            // packed output: tokens fastest (a warp writes 512 contiguous bytes); row-major: columns fastest
+            const int c   = p.out_mode == 1 ? u / p.M : u % UC;
+            const int tok = p.out_mode == 1 ? u - c * p.M : u / UC;
+            float     o[8];
+            if (gated) {
+                const uint32_t src = w_ring + (uint32_t)(tok * pitch + c * 16) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 v = lds128(src + q * 16);
+                    float       g0 = __uint_as_float(v.x), u0 = __uint_as_float(v.y);
+                    float       g1 = __uint_as_float(v.z), u1 = __uint_as_float(v.w);
+                    if (bias) {
+                        const int n = nt0 * kBN + c * 16 + q * 4;
+                        g0 += Ops::to_f32(bias[n]), u0 += Ops::to_f32(bias[n + 1]);
+                        g1 += Ops::to_f32(bias[n + 2]), u1 += Ops::to_f32(bias[n + 3]);
+                    }
+                    o[2 * q]     = __fdividef(g0, 1.f + __expf(-g0)) * u0;
+                    o[2 * q + 1] = __fdividef(g1, 1.f + __expf(-g1)) * u1;
+                }
+            }
+            else {
+                const uint32_t src = w_ring + (uint32_t)(tok * pitch + c * 8) * 4;
+                const uint4    a = lds128(src), b2 = lds128(src + 16);
+                o[0] = __uint_as_float(a.x), o[1] = __uint_as_float(a.y), o[2] = __uint_as_float(a.z), o[3] = __uint_as_float(a.w);
+                o[4] = __uint_as_float(b2.x), o[5] = __uint_as_float(b2.y), o[6] = __uint_as_float(b2.z), o[7] = __uint_as_float(b2.w);
+                if (bias) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o[q] += Ops::to_f32(bias[nt0 * kBN + c * 8 + q]);
+                }
+            }
+            uint4 pk;
+            pk.x = Ops::pack2(o[0], o[1]), pk.y = Ops::pack2(o[2], o[3]), pk.z = Ops::pack2(o[4], o[5]), pk.w = Ops::pack2(o[6], o[7]);
+            T* d = p.out_mode == 1 ? y + ((size_t)(c0 / 8 + c) * p.out_mt + tok) * 8 : y + (size_t)tok * p.ldy + c0 + c * 8;
+            *reinterpret_cast<uint4*>(d) = pk;
         }
     }
     if (p.splits > 1 && warp >= 2 && warp < kXWarp) {
@@ -667,29 +743,54 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         // then sums ITS token slice over all partials in rank order (deterministic) and writes the output.
         constexpr int ROWS = kBN * TILES;
         int*          ctr  = p.counters + 2 * blockIdx.x;
-        __threadfence();
+        // Publish: the partial stores of all 512 threads are ordered before thread 64's gpu-scope RELEASE by the CTA barrier
+        // (cumulativity), so no per-thread __threadfence (= fence.sc.gpu: measured ~0.9 us here) is needed; the readers
+        // are ordered behind thread 64's ACQUIRE spin by the second barrier.
         named_bar_sync(2, kDqWarps * 32);
+        const int t_lo = p.MT * sp / p.splits, t_hi = p.MT * (sp + 1) / p.splits;
+        const int slice_cap = (p.MT + p.splits - 1) / p.splits * ROWS * 4;  // bytes reserved per split in the receive area
         if (threadIdx.x == 64) {
+            // my partial tile leaves as ONE bulk store (the staging tile has the exchange buffer's layout)
+            float* mine = p.partials + ((size_t)blockIdx.x * p.splits + sp) * p.MT * ROWS;
+            bulk_s2g(mine, w_ring, (uint32_t)(p.MT * ROWS * 4));
+            bulk_commit_wait_all();  // writes performed (and the staging tile free again)
+            fence_proxy_async_all();  // async-proxy writes before the generic-proxy release ...
             GEMM_TRACE(7, 0);
-            atomicAdd(ctr, 1);
+            red_release_gpu_add(ctr, 1);
             while (ld_acquire_gpu(ctr) < p.splits) {
             }
+            fence_proxy_async_all();  // ... and the async-proxy reads below after the generic-proxy acquire
             GEMM_TRACE(7, 1);
+            if (p.epilogue != 2) {
+                // my token slice of every split's partial comes back with bulk loads, all in flight at once
+                const uint32_t bar   = smem_u32(&bar_xchg);
+                const uint32_t bytes = (uint32_t)((t_hi - t_lo) * ROWS * 4);
+                if (bytes) {
+                    mbar_expect_tx(bar, bytes * p.splits);
+                    const float* src = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
+                    for (int r = 0; r < p.splits; ++r) {
+                        bulk_g2s(w_ring + (uint32_t)(r * slice_cap), src + (size_t)r * p.MT * ROWS, bytes, bar);
+                    }
+                }
+                else {
+                    mbar_arrive(bar);
+                }
+            }
         }
         named_bar_sync(2, kDqWarps * 32);
         // token ownership: split r sums tokens [MT * r / splits, MT * (r + 1) / splits)  (any split count works)
-        const int    t_lo = p.MT * sp / p.splits, t_hi = p.MT * (sp + 1) / p.splits;
         const int    tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
         const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
         if (p.epilogue != 2) {
+            mbar_wait(smem_u32(&bar_xchg), 0);
             for (int idx = tid; idx < (t_hi - t_lo) * (ROWS / 2); idx += kDqWarps * 32) {
-                const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
-                float2    acc = make_float2(0.f, 0.f);
+                const int      tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+                const uint32_t src = w_ring + (uint32_t)(tl * ROWS + 2 * np) * 4;
+                float2         acc = make_float2(0.f, 0.f);
                 for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
-                    const float2 v =
-                        __ldcg(reinterpret_cast<const float2*>(base + (size_t)r * p.MT * ROWS + tl * ROWS) + np);
-                    acc.x += v.x;
-                    acc.y += v.y;
+                    const uint2 v = lds64(src + (uint32_t)(r * slice_cap));
+                    acc.x += __uint_as_float(v.x);
+                    acc.y += __uint_as_float(v.y);
                 }
                 finalize_pair<T>(p, t_lo + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
             }

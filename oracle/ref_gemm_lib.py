@@ -11,8 +11,11 @@ import os
 ROOT = os.path.dirname(os.path.abspath(__file__))
 # B200_REF_GEMM_LIB=ptx: the build whose kernel TUs hold compute_80 PTX only (JIT-compiled by the driver at load time, the way
 # the reference's wheels reach Blackwell); default: the ahead-of-time sm_100 SASS build of the same sources
-LIB_PATH = os.path.join(ROOT, "_ref", "libtm_ref_gemm_ptx.so" if os.environ.get("B200_REF_GEMM_LIB") == "ptx"
-                        else "libtm_ref_gemm.so")
+# default ("dd"): the reference's kernel templates registered with the evict-first L2 hint off (oracle/ref_build/
+# ref_gemm_kernels_dd.cu) -- the reference's own registration raises "illegal instruction" on a B200 with this toolchain;
+# "sass" = its own registration compiled ahead of time, "ptx" = the same through the driver JIT (both kept for the record)
+LIB_PATH = os.path.join(ROOT, "_ref", {"ptx": "libtm_ref_gemm_ptx.so", "sass": "libtm_ref_gemm.so"}.get(
+    os.environ.get("B200_REF_GEMM_LIB", "dd"), "libtm_ref_gemm_dd.so"))
 DISPATCH_DEFAULT, DISPATCH_MEASURE, DISPATCH_REUSE = 0, 1, 2
 
 _lib = None

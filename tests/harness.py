@@ -146,12 +146,13 @@ class PagedCase:
         p.stream = torch.cuda.current_stream().cuda_stream
         return p
 
-    def run_device(self, finished=None):
+    def run_device(self, finished=None, debug_flags=0):
         from lmdeploy_b200 import _lib as L
         torch = torch_mod()
         lib = L.load()
         self.upload()
         p = self.params(lib, finished)
+        p.debug_flags = debug_flags
         L.check(lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")
         torch.cuda.synchronize()
         return from_dev_T(self.d_out, self.dtype), self.d_pool.cpu().numpy()

@@ -171,3 +171,34 @@ def test_full_size_sampled():
     K, V = cache.read_tokens(tables[5], layer, 2, ctx + 1)
     o = out_h[5, 2 * G:(2 + 1) * G]
     assert (o <= V.max(0) + 2e-3).all() and (o >= V.min(0) - 2e-3).all()
+
+
+@pytest.mark.parametrize("kv_bits", [8, 4, 16])
+@pytest.mark.parametrize("dtype", [F16, BF16])
+def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype):
+    """The single fused kernel (in-register RoPE of q, the owning warp quantises + stores the new token's K/V and patches
+    its tile, the last-arriving CTA merges straddling segments) against the round-1 form (prologue kernel, main kernel,
+    fix-up kernel; debug_flags bit 2): KV pages and outputs BIT-IDENTICAL -- same arithmetic, same merge order.  Histories
+    cover an empty cache, block / tile boundaries and a sequence long enough to straddle CTAs; bias + llama3 rope on."""
+    rope = OA.RopeParam(type=OA.ROPE_LLAMA3, dim=128, base=5e5, factor=8.0, llama3_low_freq_factor=1.0,
+                        llama3_high_freq_factor=4.0, llama3_original_max_position_embeddings=8192)
+    hist = [0, 1, 63, 64, 65, 127, 128, 700, 2047, 4100]
+    # exact_math=False: the reference release build's transcendentals, the arithmetic the engine runs with
+    a = PagedCase(batch_hist=hist, num_heads=8, num_kv_heads=2, kv_bits=kv_bits, dtype=dtype, seed=5, bias=True, rope=rope,
+                  exact_math=False)
+    b = PagedCase(batch_hist=hist, num_heads=8, num_kv_heads=2, kv_bits=kv_bits, dtype=dtype, seed=5, bias=True, rope=rope,
+                  exact_math=False)
+    out_f, pool_f = a.run_device()
+    out_u, pool_u = b.run_device(debug_flags=4)
+    assert (pool_f == pool_u).all(), "KV pages differ between the fused and the three-kernel form"
+    assert (out_f.view(np.uint16) == out_u.view(np.uint16)).all(), "outputs differ between the fused and the three-kernel form"
+    # and the workspace's arrival counters are back at zero: a second call on the same workspace gives the same result
+    from lmdeploy_b200 import _lib as L
+    import ctypes as C
+    import torch
+    lib = L.load()
+    p = a.params(lib, workspace=a.d_ws)
+    L.check(lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")
+    torch.cuda.synchronize()
+    from harness import from_dev_T
+    assert (from_dev_T(a.d_out, dtype).view(np.uint16) == out_f.view(np.uint16)).all()

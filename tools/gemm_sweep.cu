@@ -176,9 +176,9 @@ int main(int argc, char** argv)
                 continue;
             }
             const int nts = s.N / (128 * tiles);
-            for (int splits : {1, 2, 3, 4, 6, 8, 12, 16}) {
-                if (nts * splits > 148 || kgs / splits < 2 || kgs % splits) {
-                    continue;  // cooperative launch needs one wave; K-groups divide evenly
+            for (int splits : {1, 2, 3, 4, 5, 6, 7, 8, 9, 12, 16}) {
+                if (nts * splits > 148 || kgs / splits < 2) {
+                    continue;  // cooperative launch needs one wave (uneven K ranges are fine: kg0 = kgs * sp / splits)
                 }
                 for (int depth = 0; depth < 3; ++depth) {
                     g_plan_override = {tiles, splits, 0, 0, 0};
