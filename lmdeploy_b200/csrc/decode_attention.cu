@@ -439,13 +439,21 @@ static int launch_decode(const b200_attention_params* a)
     if (!a->workspace || a->workspace_bytes < w.total) {
         return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_decode_attention_workspace_bytes)");
     }
-    // debug_flags bit 2: the round-1 three-kernel form (separate prologue kernel, main kernel, fix-up kernel) instead of the
-    // single fused kernel; B200_ATTN_UNFUSED=1 selects it process-wide (A/B measurements, fallback)
-    static const bool env_unfused = [] {
-        const char* e = getenv("B200_ATTN_UNFUSED");
-        return e && *e && *e != '0';
+    // Which parts run inside the main kernel.  B200_ATTN_FUSED = 1 (default): the prologue (RoPE of q in registers, the warp
+    // that owns the new token's slot quantises + stores K/V); the fix-up stays a separate PDL-overlapped kernel -- measured at
+    // C2, merging inside the main kernel (= 3) serialises an atomic round trip and the merge's two dependent L2 passes into
+    // every CTA's critical path (+14 us stand-alone, +2 us per layer in the step) where the separate kernel spreads them
+    // over 512 small CTAs.  0 = the round-1 three-kernel form; debug_flags bit 2 selects that form per call.
+    static const int env_fused = [] {
+        const char* e = getenv("B200_ATTN_FUSED");
+        const char* u = getenv("B200_ATTN_UNFUSED");
+        if (u && *u && *u != '0') {
+            return 0;
+        }
+        return e && *e ? atoi(e) & 3 : 1;
     }();
-    const bool unfused = env_unfused || (a->debug_flags & 4);
+    const int  want    = (a->debug_flags & 4) ? 0 : ((a->debug_flags & 8) ? 3 : env_fused);  // bit 3: everything in one kernel
+    const bool unfused = want == 0;
     const int* plan = a->plan;
     if (!plan) {
         launch_k(plan_kernel, dim3(1), dim3(256), 0, st, w.plan, a->cu_k_len, a->finished, a->batch_size, w.seg_counters,
@@ -455,7 +463,7 @@ static int launch_decode(const b200_attention_params* a)
         }
         plan = w.plan;
     }
-    if (unfused && !(a->debug_flags & 1)) {
+    if (!(want & 1) && !(a->debug_flags & 1)) {
         if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st)) {
             return e;
         }
@@ -486,7 +494,7 @@ static int launch_decode(const b200_attention_params* a)
     p.grid_main     = grid;
     if (!unfused) {
         // debug_flags bit 0 / bit 1 keep their meaning (skip the prologue / the fix-up) for kernel-only timing
-        p.fused = ((a->debug_flags & 1) ? 0 : 1) | ((a->debug_flags & 2) ? 0 : 2);
+        p.fused = ((a->debug_flags & 1) ? 0 : (want & 1)) | ((a->debug_flags & 2) ? 0 : (want & 2));
         p.q = a->q, p.k = a->k, p.v = a->v, p.stride = a->stride;
         p.q_bias = a->q_bias, p.k_bias = a->k_bias, p.v_bias = a->v_bias;
         p.cu_q_len           = a->cu_q_len;
@@ -499,7 +507,7 @@ static int launch_decode(const b200_attention_params* a)
     if (int e = check_launch("decode_attention_kernel")) {
         return e;
     }
-    if ((a->debug_flags & 2) || !unfused) {
+    if ((a->debug_flags & 2) || (want & 2)) {
         return 0;
     }
     dim3 rgrid(a->num_kv_heads, a->batch_size);

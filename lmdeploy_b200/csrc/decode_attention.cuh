@@ -350,6 +350,17 @@ struct WorkIter {
     }
 };
 
+// The main-kernel CTAs that hold a piece of segment (sequence b, kv-head h).  CTA c owns units [total * c / grid,
+// total * (c + 1) / grid).  With total >= grid every CTA is non-empty and the pieces sit in CTAs cf..cl; with total < grid a
+// CTA holds at most ONE unit (= one tile), empty CTAs lie in between, and the pieces are the segment's `tiles` units, unit
+// u living in CTA ((u + 1) * grid - 1) / total.  (Round 1 walked cf..cl in both cases and read the never-written -- or,
+// worse, stale -- partial slots of the empty CTAs in between.)
+struct SegCtas {
+    int       cf, cl, first_slot, n;  // n = number of pieces
+    int       sparse;
+    long long s0, total;
+};
+
 template<class T, int KVBITS, int STAGES>
 struct SharedStorage {
     using Cfg = TileCfg<KVBITS>;
@@ -359,7 +370,8 @@ struct SharedStorage {
     float    merge_L[kConsumerWarps][kMaxGroup];
     float    final_M[kMaxGroup];
     float    final_L[kMaxGroup];
-    int      fix[4];  // in-kernel fix-up: first / last CTA of the segment, partial slot of the first, "this CTA merges"
+    SegCtas  seg;       // in-kernel fix-up: where the pieces of the segment being closed live
+    int      fix_last;  // ... and whether this CTA arrived last (it merges)
     uint64_t full[STAGES];
     uint64_t empty[STAGES];
 };
@@ -681,29 +693,51 @@ __device__ __noinline__ void new_token_kv(const KernelParams& p, int b, int h, i
     }
 }
 
-// Merge of the partials of one (sequence b, kv-head h) segment that straddled main-kernel CTAs cf..cl.
-// Same math as attention::reduce (reduce.cu:90-153): O = sum_k w_k O_k / sum_k w_k L_k, w_k = exp2((M_k - M) * c),
-// partials visited in ascending CTA order whoever runs the merge (deterministic).  Loads bypass L1 (ld.global.cg): the
-// partials may have been written by other SMs during this very kernel.
+B200_DEVICE SegCtas segment_ctas(const KernelParams& p, int b, int h, int grid_main)
+{
+    SegCtas         s;
+    const int       Hkv   = p.num_kv_heads;
+    const int       tiles = p.tile_prefix[b + 1] - p.tile_prefix[b];
+    s.total               = (long long)p.tile_prefix[p.batch] * Hkv;
+    s.s0                  = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
+    const long long s1    = s.s0 + tiles;
+    s.cf                  = (int)(((s.s0 + 1) * grid_main - 1) / s.total);
+    s.cl                  = (int)((s1 * grid_main - 1) / s.total);
+    s.first_slot          = (s.total * s.cf / grid_main != s.s0) ? 1 : 0;
+    s.sparse              = s.total < grid_main;
+    s.n                   = s.sparse ? tiles : s.cl - s.cf + 1;
+    return s;
+}
+
+// Merge of the partials of one segment.  Same math as attention::reduce (reduce.cu:90-153): O = sum_k w_k O_k / sum_k w_k L_k,
+// w_k = exp2((M_k - M) * c), pieces visited in ascending CTA order whoever runs the merge (deterministic).  Loads bypass L1
+// (ld.global.cg): the partials may have been written by other SMs during this very kernel.
 template<class T>
-__device__ __noinline__ void merge_segment(const KernelParams& p, int b, int h, int cf, int cl, int first_slot, int tid, int nthreads)
+__device__ __noinline__ void merge_segment(const KernelParams& p, int b, int h, const SegCtas& sg, int grid_main, int tid,
+                                           int nthreads)
 {
     using Ops     = TypeOps<T>;
     const int   G = p.num_heads / p.num_kv_heads;
     const float c = p.qk_scale;
+    auto slot_of  = [&](int k) {
+        if (sg.sparse) {
+            return 2 * (int)(((sg.s0 + k + 1) * grid_main - 1) / sg.total);  // one unit per CTA: always its first slot
+        }
+        const int cta = sg.cf + k;
+        return 2 * cta + (k == 0 ? sg.first_slot : 0);
+    };
     // thread -> 4 consecutive dims of one head (float4 partial loads)
     for (int i4 = tid; i4 < G * kHeadDim / 4; i4 += nthreads) {
         const int i  = i4 * 4;
         const int hd = i / kHeadDim;
         float     m  = -INFINITY;
-        for (int cta = cf; cta <= cl; ++cta) {
-            const int slot = 2 * cta + (cta == cf ? first_slot : 0);
-            m              = fmaxf(m, __ldcg(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]));
+        for (int k = 0; k < sg.n; ++k) {
+            m = fmaxf(m, __ldcg(&p.partial_ML[((size_t)slot_of(k) * kMaxGroup + hd) * 2]));
         }
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float  l   = 0.f;
-        for (int cta = cf; cta <= cl; ++cta) {
-            const int    slot = 2 * cta + (cta == cf ? first_slot : 0);
+        for (int k = 0; k < sg.n; ++k) {
+            const int    slot = slot_of(k);
             const float2 ml   = __ldcg(reinterpret_cast<const float2*>(&p.partial_ML[((size_t)slot * kMaxGroup + hd) * 2]));
             const float  w    = (ml.x == -INFINITY) ? 0.f : exp2_approx((ml.x - m) * c);
             const float4 o    = __ldcg(reinterpret_cast<const float4*>(&p.partial_O[(size_t)slot * kMaxGroup * kHeadDim + i]));
@@ -718,19 +752,6 @@ __device__ __noinline__ void merge_segment(const KernelParams& p, int b, int h, 
         v.y = Ops::pack2(acc.z / l, acc.w / l);
         *reinterpret_cast<uint2*>(dst) = v;
     }
-}
-
-// segment (b, h) -> main-kernel CTA range [cf, cl] and the partial slot CTA cf used for it (64-bit divisions: one thread)
-B200_DEVICE void segment_ctas(const KernelParams& p, int b, int h, int grid_main, int& cf, int& cl, int& first_slot)
-{
-    const int       Hkv   = p.num_kv_heads;
-    const int       tiles = p.tile_prefix[b + 1] - p.tile_prefix[b];
-    const long long total = (long long)p.tile_prefix[p.batch] * Hkv;
-    const long long s0    = (long long)Hkv * p.tile_prefix[b] + (long long)h * tiles;
-    const long long s1    = s0 + tiles;
-    cf                    = (int)(((s0 + 1) * grid_main - 1) / total);
-    cl                    = (int)((s1 * grid_main - 1) / total);
-    first_slot            = (total * cf / grid_main != s0) ? 1 : 0;
 }
 
 B200_DEVICE int atom_add_acq_rel_gpu(int* p, int v)
@@ -1078,18 +1099,17 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
                 // in CTA order -- the same sum whoever merges -- and re-arms the counter.
                 named_bar_sync(1, kConsumerWarps * 32);
                 if (ctid == 0) {
-                    int cf, cl, fs;
-                    segment_ctas(p, it.b, it.h, p.grid_main, cf, cl, fs);
+                    ss.seg        = segment_ctas(p, it.b, it.h, p.grid_main);
                     int*      ctr = p.seg_counters + it.b * Hkv + it.h;
                     const int old = atom_add_acq_rel_gpu(ctr, 1);
-                    ss.fix[0] = cf, ss.fix[1] = cl, ss.fix[2] = fs, ss.fix[3] = (old == cl - cf);
-                    if (old == cl - cf) {
-                        *ctr = 0;  // every CTA of the segment has arrived: nobody touches the counter again in this launch
+                    ss.fix_last   = (old == ss.seg.n - 1);
+                    if (old == ss.seg.n - 1) {
+                        *ctr = 0;  // every piece of the segment has arrived: nobody touches the counter again in this launch
                     }
                 }
                 named_bar_sync(1, kConsumerWarps * 32);
-                if (ss.fix[3]) {
-                    merge_segment<T>(p, it.b, it.h, ss.fix[0], ss.fix[1], ss.fix[2], ctid, kConsumerWarps * 32);
+                if (ss.fix_last) {
+                    merge_segment<T>(p, it.b, it.h, ss.seg, p.grid_main, ctid, kConsumerWarps * 32);
                 }
             }
         }
@@ -1114,17 +1134,15 @@ __global__ void decode_reduce_kernel(const KernelParams p, int grid_main)
     if (tiles == 0) {
         return;
     }
-    __shared__ int s_cf, s_cl, s_first_slot;
+    __shared__ SegCtas s_seg;
     if (threadIdx.x == 0) {
-        int cf, cl, fs;
-        segment_ctas(p, b, h, grid_main, cf, cl, fs);
-        s_cf = cf, s_cl = cl, s_first_slot = fs;
+        s_seg = segment_ctas(p, b, h, grid_main);
     }
     __syncthreads();
-    if (s_cf == s_cl) {
+    if (s_seg.n <= 1) {
         return;  // written directly by the main kernel
     }
-    merge_segment<T>(p, b, h, s_cf, s_cl, s_first_slot, threadIdx.x, blockDim.x);
+    merge_segment<T>(p, b, h, s_seg, grid_main, threadIdx.x, blockDim.x);
 }
 
 }  // namespace attn

@@ -258,7 +258,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
     __shared__ uint64_t bar_xfull[kMaxX], bar_xempty[kMaxX];
     __shared__ uint64_t bar_aready[kASlots], bar_aempty[kASlots];
     __shared__ uint64_t bar_dready;
-    __shared__ uint64_t bar_xchg;  // split-K exchange: the bulk loads of the other splits' partial slices
     __shared__ uint32_t s_tmem;
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // warp-uniform
@@ -310,10 +309,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         else if (t == 2 * kMaxW + 2 * kMaxX + 2 * kASlots) {
             mbar_init(smem_u32(&bar_dready), kMmaWarps);
         }
-        else if (t == 2 * kMaxW + 2 * kMaxX + 2 * kASlots + 1) {
-            mbar_init(smem_u32(&bar_xchg), 1);
-        }
-        if (t <= 2 * kMaxW + 2 * kMaxX + 2 * kASlots + 1) {
+        if (t <= 2 * kMaxW + 2 * kMaxX + 2 * kASlots) {
             fence_mbar_init();
         }
     }
@@ -658,14 +654,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
             const int half = TILES == 4 ? p.MT : p.MT >> 1;  // TILES == 4: one warp per (tile, lane quarter) takes every token
             const int tb = epi_half * half, te = tb + half;
             const uint32_t drow = trow + epi_tile * d_stride;
-            // Accumulators -> fp32 staging tile [token][row] in the (now idle) operand rings: thread = row, so a warp's 32
-            // stores of one token are consecutive words (conflict-free).  Everything downstream -- the direct epilogue and
-            // the split-K exchange -- works in the token-major orientation, with wide accesses.  Row pitch: ROWS words, + 4
-            // when the direct epilogue reads it token-fastest (quarter-warp 128-bit loads then hit distinct bank groups).
-            if (epi_active) {
-                constexpr int  ROWS  = kBN * TILES;
-                const int      pitch = ROWS + (p.splits == 1 ? 4 : 0);
-                const uint32_t dst   = w_ring + (uint32_t)(epi_tile * kBN + n_local) * 4;
+            if (p.splits == 1) {
+                // Accumulators -> fp32 staging tile [token][row] in the (now idle) operand rings: thread = row, so a warp's 32
+                // stores of one token are consecutive words (conflict-free); the direct epilogue below then works token-major
+                // with 128-bit accesses (measured on w1w3: 3.6 us -> 0.5 us for this phase).  Row pitch ROWS + 4 words: the
+                // token-fastest 128-bit reads of a quarter-warp hit distinct bank groups.
+                if (epi_active) {
+                    constexpr int  ROWS  = kBN * TILES;
+                    const int      pitch = ROWS + 4;
+                    const uint32_t dst   = w_ring + (uint32_t)(epi_tile * kBN + n_local) * 4;
+                    for (int t0 = tb; t0 < te; t0 += 32) {
+                        uint32_t v[2][16];
+                        umma::ld_32x32b_x16(drow + t0, v[0]);
+                        if (t0 + 16 < te) {
+                            umma::ld_32x32b_x16(drow + t0 + 16, v[1]);
+                        }
+                        umma::wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            if (t0 + i < te) {
+                                sts32(dst + (uint32_t)((t0 + i) * pitch) * 4, v[i >> 4][i & 15]);
+                            }
+                        }
+                    }
+                }
+            }
+            else if (epi_active) {
+                // fp32 partial tile -> global exchange buffer [group][split][tok][row] (stays in L2), 128-byte rows per warp
+                // store.  (Staging the tile in shared memory and moving it with ONE bulk store / bulk loads was measured:
+                // 3.7k cycles for the 64 KB store alone against 2.2k for these direct stores -- the TMA engine moves a single
+                // large copy at ~17 B/clk.)
+                constexpr int ROWS = kBN * TILES;
+                float* part = p.partials + ((size_t)blockIdx.x * p.splits + sp) * p.MT * ROWS + epi_tile * kBN + n_local;
                 for (int t0 = tb; t0 < te; t0 += 32) {
                     uint32_t v[2][16];
                     umma::ld_32x32b_x16(drow + t0, v[0]);
@@ -676,12 +696,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (t0 + i < te) {
-                            sts32(dst + (uint32_t)((t0 + i) * pitch) * 4, v[i >> 4][i & 15]);
+                            __stcg(part + (size_t)(t0 + i) * ROWS, __uint_as_float(v[i >> 4][i & 15]));
                         }
                     }
-                }
-                if (p.splits > 1) {
-                    fence_proxy_async();  // the tile leaves through the async proxy (bulk store)
                 }
             }
             if (threadIdx.x == 64) GEMM_TRACE(4, 3);
@@ -748,49 +765,38 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
         // are ordered behind thread 64's ACQUIRE spin by the second barrier.
         named_bar_sync(2, kDqWarps * 32);
         const int t_lo = p.MT * sp / p.splits, t_hi = p.MT * (sp + 1) / p.splits;
-        const int slice_cap = (p.MT + p.splits - 1) / p.splits * ROWS * 4;  // bytes reserved per split in the receive area
         if (threadIdx.x == 64) {
-            // my partial tile leaves as ONE bulk store (the staging tile has the exchange buffer's layout)
-            float* mine = p.partials + ((size_t)blockIdx.x * p.splits + sp) * p.MT * ROWS;
-            bulk_s2g(mine, w_ring, (uint32_t)(p.MT * ROWS * 4));
-            bulk_commit_wait_all();  // writes performed (and the staging tile free again)
-            fence_proxy_async_all();  // async-proxy writes before the generic-proxy release ...
             GEMM_TRACE(7, 0);
             red_release_gpu_add(ctr, 1);
             while (ld_acquire_gpu(ctr) < p.splits) {
             }
-            fence_proxy_async_all();  // ... and the async-proxy reads below after the generic-proxy acquire
             GEMM_TRACE(7, 1);
-            if (p.epilogue != 2) {
-                // my token slice of every split's partial comes back with bulk loads, all in flight at once
-                const uint32_t bar   = smem_u32(&bar_xchg);
-                const uint32_t bytes = (uint32_t)((t_hi - t_lo) * ROWS * 4);
-                if (bytes) {
-                    mbar_expect_tx(bar, bytes * p.splits);
-                    const float* src = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
-                    for (int r = 0; r < p.splits; ++r) {
-                        bulk_g2s(w_ring + (uint32_t)(r * slice_cap), src + (size_t)r * p.MT * ROWS, bytes, bar);
-                    }
-                }
-                else {
-                    mbar_arrive(bar);
-                }
-            }
         }
         named_bar_sync(2, kDqWarps * 32);
         // token ownership: split r sums tokens [MT * r / splits, MT * (r + 1) / splits)  (any split count works)
         const int    tid  = threadIdx.x - 64;  // 0 .. 32 * kDqWarps - 1
         const float* base = p.partials + (size_t)blockIdx.x * p.splits * p.MT * ROWS + (size_t)t_lo * ROWS;
         if (p.epilogue != 2) {
-            mbar_wait(smem_u32(&bar_xchg), 0);
             for (int idx = tid; idx < (t_hi - t_lo) * (ROWS / 2); idx += kDqWarps * 32) {
-                const int      tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
-                const uint32_t src = w_ring + (uint32_t)(tl * ROWS + 2 * np) * 4;
-                float2         acc = make_float2(0.f, 0.f);
-                for (int r = 0; r < p.splits; ++r) {  // fixed order: deterministic
-                    const uint2 v = lds64(src + (uint32_t)(r * slice_cap));
-                    acc.x += __uint_as_float(v.x);
-                    acc.y += __uint_as_float(v.y);
+                const int tl = idx / (ROWS / 2), np = idx - tl * (ROWS / 2);
+                float2    acc = make_float2(0.f, 0.f);
+                const float2* src = reinterpret_cast<const float2*>(base + tl * ROWS) + np;
+                // eight partials in flight per batch; summed in split order: deterministic
+                for (int r0 = 0; r0 < p.splits; r0 += 8) {
+                    float2 v[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (r0 + r < p.splits) {
+                            v[r] = __ldcg(src + (size_t)(r0 + r) * (p.MT * ROWS / 2));
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (r0 + r < p.splits) {
+                            acc.x += v[r].x;
+                            acc.y += v[r].y;
+                        }
+                    }
                 }
                 finalize_pair<T>(p, t_lo + tl, nt0 * kBN + 2 * np, acc.x, acc.y);
             }

@@ -175,11 +175,14 @@ def test_full_size_sampled():
 
 @pytest.mark.parametrize("kv_bits", [8, 4, 16])
 @pytest.mark.parametrize("dtype", [F16, BF16])
-def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype):
-    """The single fused kernel (in-register RoPE of q, the owning warp quantises + stores the new token's K/V and patches
-    its tile, the last-arriving CTA merges straddling segments) against the round-1 form (prologue kernel, main kernel,
-    fix-up kernel; debug_flags bit 2): KV pages and outputs BIT-IDENTICAL -- same arithmetic, same merge order.  Histories
-    cover an empty cache, block / tile boundaries and a sequence long enough to straddle CTAs; bias + llama3 rope on."""
+@pytest.mark.parametrize("flags", [0, 8])
+def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype, flags):
+    """The production form (flags 0: in-register RoPE of q, the owning warp quantises + stores the new token's K/V and patches
+    its tile; fix-up in a second kernel) and the single-launch form (flags 8: the last-arriving CTA also merges straddling
+    segments) against the round-1 form (prologue kernel, main kernel, fix-up kernel; debug_flags bit 2): KV pages and outputs
+    BIT-IDENTICAL -- same arithmetic, same merge order.  Histories cover an empty cache, block / tile boundaries and
+    sequences long enough to straddle CTAs (the grid has more CTAs than there are tiles here: every multi-tile sequence is
+    spread over CTAs with empty ones in between); bias + llama3 rope on."""
     rope = OA.RopeParam(type=OA.ROPE_LLAMA3, dim=128, base=5e5, factor=8.0, llama3_low_freq_factor=1.0,
                         llama3_high_freq_factor=4.0, llama3_original_max_position_embeddings=8192)
     hist = [0, 1, 63, 64, 65, 127, 128, 700, 2047, 4100]
@@ -188,7 +191,7 @@ def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype):
                   exact_math=False)
     b = PagedCase(batch_hist=hist, num_heads=8, num_kv_heads=2, kv_bits=kv_bits, dtype=dtype, seed=5, bias=True, rope=rope,
                   exact_math=False)
-    out_f, pool_f = a.run_device()
+    out_f, pool_f = a.run_device(debug_flags=flags)
     out_u, pool_u = b.run_device(debug_flags=4)
     assert (pool_f == pool_u).all(), "KV pages differ between the fused and the three-kernel form"
     assert (out_f.view(np.uint16) == out_u.view(np.uint16)).all(), "outputs differ between the fused and the three-kernel form"
@@ -198,7 +201,36 @@ def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype):
     import torch
     lib = L.load()
     p = a.params(lib, workspace=a.d_ws)
+    p.debug_flags = flags
     L.check(lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")
     torch.cuda.synchronize()
     from harness import from_dev_T
     assert (from_dev_T(a.d_out, dtype).view(np.uint16) == out_f.view(np.uint16)).all()
+
+
+@pytest.mark.parametrize("flags", [0, 4, 8])
+def test_partials_of_an_earlier_call_do_not_leak_into_a_sparse_one(flags):
+    """A workspace that served a big call (every CTA of the grid left fp32 partials) then serves a small one whose tiles are
+    fewer than the grid's CTAs: the pieces of a multi-tile sequence then sit in CTAs with EMPTY CTAs in between, whose
+    partial slots still hold the big call's values.  The merge must visit the pieces only (round 1 walked the whole CTA
+    range and was right only on a zeroed workspace)."""
+    import ctypes as C
+    import torch
+    from lmdeploy_b200 import _lib as L
+    from harness import from_dev_T
+    lib = L.load()
+    big = PagedCase(batch_hist=[3000] * 24, num_heads=8, num_kv_heads=2, kv_bits=8, seed=21)
+    big.upload()
+    pb = big.params(lib)
+    pb.debug_flags = flags
+    L.check(lib.b200_decode_attention(C.byref(pb)), "b200_decode_attention")
+    torch.cuda.synchronize()
+    small = PagedCase(batch_hist=[130, 517, 70, 200], num_heads=8, num_kv_heads=2, kv_bits=8, seed=22)
+    small.upload()
+    ps = small.params(lib, workspace=big.d_ws)             # the used workspace, not a zeroed one
+    ps.debug_flags = flags
+    L.check(lib.b200_decode_attention(C.byref(ps)), "b200_decode_attention")
+    torch.cuda.synchronize()
+    out = from_dev_T(small.d_out, F16)
+    ref = small.run_oracle()
+    assert np.isfinite(out).all() and np.abs(out - ref).max() <= 2e-3, float(np.abs(out - ref).max())
