@@ -142,7 +142,8 @@ typedef struct {
     /* profiling aid: bit 0 = skip the prologue (bias, RoPE, KV quantise + page store), bit 1 = skip the fix-up merge,
      * bit 2 = run the three-kernel form (prologue kernel, main kernel, fix-up kernel; with bits 0-1: the main kernel alone,
      * reading the rotated q an earlier bit-2 call left in the workspace), bit 3 = the fix-up inside the main kernel as well
-     * (one launch).  0 in production: the prologue runs inside the main kernel, the fix-up is a second kernel. */
+     * (one launch; bit 3 alone also moves the prologue inside).  0 in production: three PDL-chained kernels (the fastest
+     * form on B200, see decode_attention.cu). */
     int debug_flags;
 
     void* stream;

@@ -439,18 +439,21 @@ static int launch_decode(const b200_attention_params* a)
     if (!a->workspace || a->workspace_bytes < w.total) {
         return fail(B200_ERR_WORKSPACE, "workspace too small (see b200_decode_attention_workspace_bytes)");
     }
-    // Which parts run inside the main kernel.  B200_ATTN_FUSED = 1 (default): the prologue (RoPE of q in registers, the warp
-    // that owns the new token's slot quantises + stores K/V); the fix-up stays a separate PDL-overlapped kernel -- measured at
-    // C2, merging inside the main kernel (= 3) serialises an atomic round trip and the merge's two dependent L2 passes into
-    // every CTA's critical path (+14 us stand-alone, +2 us per layer in the step) where the separate kernel spreads them
-    // over 512 small CTAs.  0 = the round-1 three-kernel form; debug_flags bit 2 selects that form per call.
+    // Which parts run inside the main kernel (B200_ATTN_FUSED; debug_flags bits 2 / 3 select per call).  Default 0: the
+    // three-kernel form -- prologue kernel, main kernel, fix-up kernel chained by programmatic dependent launch.  Measured
+    // at C2 (profiles/r02_attention_variants.md, ncu per-kernel + CUDA events): the prologue inside the main kernel (bit 0:
+    // RoPE of q in registers, the warp that owns the new token's slot quantises + stores K/V) costs the main kernel +7.2 us
+    // (dependent global loads at every segment start / last tile sit on each CTA's critical path) against a 5.9 us kernel
+    // that PDL overlaps; the fix-up inside (bit 1) costs +6.2 us (an acq_rel atomic round trip + two dependent L2 passes per
+    // straddling segment) against an 8.5 us kernel spread over 512 CTAs.  All forms are bit-identical
+    // (tests/test_decode_attention_gpu.py::test_fused_kernel_equals_the_three_kernel_form).
     static const int env_fused = [] {
         const char* e = getenv("B200_ATTN_FUSED");
         const char* u = getenv("B200_ATTN_UNFUSED");
         if (u && *u && *u != '0') {
             return 0;
         }
-        return e && *e ? atoi(e) & 3 : 1;
+        return e && *e ? atoi(e) & 3 : 0;
     }();
     const int  want    = (a->debug_flags & 4) ? 0 : ((a->debug_flags & 8) ? 3 : env_fused);  // bit 3: everything in one kernel
     const bool unfused = want == 0;

@@ -175,11 +175,11 @@ def test_full_size_sampled():
 
 @pytest.mark.parametrize("kv_bits", [8, 4, 16])
 @pytest.mark.parametrize("dtype", [F16, BF16])
-@pytest.mark.parametrize("flags", [0, 8])
+@pytest.mark.parametrize("flags", [8])
 def test_fused_kernel_equals_the_three_kernel_form(kv_bits, dtype, flags):
-    """The production form (flags 0: in-register RoPE of q, the owning warp quantises + stores the new token's K/V and patches
-    its tile; fix-up in a second kernel) and the single-launch form (flags 8: the last-arriving CTA also merges straddling
-    segments) against the round-1 form (prologue kernel, main kernel, fix-up kernel; debug_flags bit 2): KV pages and outputs
+    """The single-launch form (flags 8: in-register RoPE of q, the owning warp quantises + stores the new token's K/V and
+    patches its tile, the last-arriving CTA merges straddling segments) against the production form (prologue kernel, main
+    kernel, fix-up kernel; debug_flags bit 2): KV pages and outputs
     BIT-IDENTICAL -- same arithmetic, same merge order.  Histories cover an empty cache, block / tile boundaries and
     sequences long enough to straddle CTAs (the grid has more CTAs than there are tiles here: every multi-tile sequence is
     spread over CTAs with empty ones in between); bias + llama3 rope on."""

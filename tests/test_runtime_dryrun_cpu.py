@@ -129,7 +129,8 @@ def test_engine_device_step_marshals_what_the_scheduler_formed(dry, monkeypatch)
     assert m.active_seqs == 0 and m.free_blocks == 32
 
 
-def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys):
+@pytest.mark.parametrize("ingest_limit", [150000, 0])
+def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys, ingest_limit):
     """bench.run_b200 end to end on a tiny geometry with the recording library: every key the driver reads is on the one
     JSON line, with the right types -- the script itself is what the round-end run executes."""
     import json
@@ -162,7 +163,7 @@ def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys):
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
         monkeypatch.delenv(k, raising=False)
     args = types.SimpleNamespace(gpus=1, steps=4, warmup=3, impl="b200", config="c2", no_graph=False, no_cpu_baseline=False,
-                                 attn_iters=2)
+                                 attn_iters=2, engine_ingest_limit=ingest_limit)
     bench.run_b200(args)
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
@@ -177,6 +178,7 @@ def test_bench_main_arm_prints_the_contract_line(dry, monkeypatch, capsys):
     assert d["roofline"]["frac"] == pytest.approx(d["roofline"]["achieved"] / d["roofline"]["peak"])
     assert set(d["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and d["e2e"]["h2d_bytes_per_step"] >= (4 * 4 + 3) * 4     # the packed control buffer, + the block table when it changes
     assert "TurboMind.step" in d["e2e"]["path"] and d["e2e"]["prompt_ingest"]["tokens"] == 4 * 100
+    assert d["e2e"]["prompt_ingest"]["how"].startswith("engine" if ingest_limit else "synthetic")
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
     assert d["gpu_launches"] == (4 + 9 * 2 + 4) * 4 and "workload" in d["config"] and "model" not in d["config"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}

@@ -307,7 +307,7 @@ def _bench_worker(rank, world, port, q):
         TM.SPECS["tiny"] = ModelSpec("tiny", "llama", 512, 2, 4, 2, 1024, 1000, 1e4, weight_format="awq")
         bench.CONFIGS["c2"] = ("tiny", 4, 100, 8)
         args = types.SimpleNamespace(gpus=world, steps=4, warmup=3, impl="b200", config="c2", no_graph=False,
-                                     no_cpu_baseline=False, attn_iters=2)
+                                     no_cpu_baseline=False, attn_iters=2, engine_ingest_limit=150000)
         buf = io.StringIO()
         with contextlib.redirect_stdout(buf):
             bench.run_b200(args)

