@@ -266,6 +266,49 @@ B200_API int b200_qk_rmsnorm(void* qkv, int64_t stride, const void* q_weight, co
 B200_API int b200_argmax(int* out, const void* logits, int rows, int vocab, int64_t ld, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Sampling beyond greedy (do_sample requests).  Replaces LogitsProcessor::Forward (generation/logits_processor.cc:66-125:
+ * repetition penalty, temperature) + Sampling::Forward (generation/sampling.cc:92-183: top-k sort filter, softmax, top-p /
+ * min-p filter, invokeSampling with a per-sequence curandState_t) with ONE kernel, one CTA per sampled row.
+ *   logits      [*, ld] T (the step's logits buffer); item i reads row rows[i] (rows NULL: i) and entries [0, vocab)
+ *   temperature / top_k / top_p / min_p   per item (NULL: 1 / 0 = no top-k filter / 1 / 0); top_k is capped at 1024
+ *   repetition_penalty (optional) with history[i] = device pointer to the history_len[i] token ids seen so far
+ *   rng_states  b200_sampling_rng_state_bytes() bytes per sequence slot (curandState_t, XORWOW), seeded by
+ *               b200_sampling_init_rng = curand_init(seed, 0, 0) as InitializeRandomStates; item i uses slot rng_index[i]
+ *   out_uniform / out_kept (optional): the uniform number drawn and the size of the filtered candidate set (tests)
+ *   workspace   b200_sampling_workspace_bytes(count, vocab) bytes
+ * Candidate set and probabilities follow the reference's arithmetic; with top_k > 0 the draw walks the candidates in
+ * descending-probability order like the reference, with top_k = 0 in vocabulary order (same distribution, no 92k-entry sort).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void*       logits;
+    int64_t           ld;
+    int               dtype;
+    int               count;
+    int               vocab;
+    const int*        rows;
+    const float*      temperature;
+    const int*        top_k;
+    const float*      top_p;
+    const float*      min_p;
+    const float*      repetition_penalty;
+    const int* const* history;
+    const int*        history_len;
+    void*             rng_states;
+    const int*        rng_index;
+    int*              out_ids;
+    float*            out_uniform;
+    int*              out_kept;
+    void*             workspace;
+    size_t            workspace_bytes;
+    void*             stream;
+} b200_sampling_params;
+
+B200_API size_t b200_sampling_rng_state_bytes(void);
+B200_API size_t b200_sampling_workspace_bytes(int count, int vocab);
+B200_API int    b200_sampling_init_rng(void* states, const unsigned long long* seeds, const uint8_t* mask, int n, void* stream);
+B200_API int    b200_sample(const b200_sampling_params* params);
+
+/* ------------------------------------------------------------------------------------------------
  * Tensor-parallel device communicator over NVLink peer memory (one process per GPU; peers' buffers are
  * mapped with CUDA IPC by the host side and handed over as raw pointers).  Replaces
  *   DeviceCommImpl::AllreduceResidualBiasRMSnorm / AllReduceSum / AllGather

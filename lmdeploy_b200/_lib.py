@@ -60,6 +60,17 @@ class ModelConfig(C.Structure):
     ]
 
 
+class SamplingParams(C.Structure):
+    """b200_sampling_params (include/b200_turbomind.h)."""
+    _fields_ = [
+        ("logits", C.c_void_p), ("ld", C.c_int64), ("dtype", C.c_int), ("count", C.c_int), ("vocab", C.c_int),
+        ("rows", C.c_void_p), ("temperature", C.c_void_p), ("top_k", C.c_void_p), ("top_p", C.c_void_p), ("min_p", C.c_void_p),
+        ("repetition_penalty", C.c_void_p), ("history", C.c_void_p), ("history_len", C.c_void_p),
+        ("rng_states", C.c_void_p), ("rng_index", C.c_void_p), ("out_ids", C.c_void_p), ("out_uniform", C.c_void_p),
+        ("out_kept", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("stream", C.c_void_p),
+    ]
+
+
 class StepInputs(C.Structure):
     _fields_ = [
         ("batch_size", C.c_int), ("token_ids", C.c_void_p), ("cu_q_len", C.c_void_p), ("cu_k_len", C.c_void_p),
@@ -128,6 +139,12 @@ def load():
     lib.b200_embedding_lookup.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_void_p]
     lib.b200_argmax.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p]
+    lib.b200_sampling_rng_state_bytes.restype = C.c_size_t
+    lib.b200_sampling_rng_state_bytes.argtypes = []
+    lib.b200_sampling_workspace_bytes.restype = C.c_size_t
+    lib.b200_sampling_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    lib.b200_sampling_init_rng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200_sample.argtypes = [C.POINTER(SamplingParams)]
     lib.b200_comm_buffer_bytes.restype = C.c_size_t
     lib.b200_comm_buffer_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
     lib.b200_comm_flags_bytes.restype = C.c_size_t
