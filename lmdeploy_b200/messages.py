@@ -135,12 +135,12 @@ class GenerationConfig:
             self.repetition_ngram_size = self.repetition_ngram_threshold = 0
         if self.max_new_tokens is not None and self.max_new_tokens < 0:
             raise ConfigError("max_new_tokens must be >= 0")
-        # The decode hot path samples greedily (top_k == 1, generation/sampling.cc:113-126).  With do_sample=False -- the
-        # default -- the reference decodes greedily WHATEVER top_k / top_p / temperature / repetition_penalty say
-        # (async_engine.py `_determine_gen_config` resets them), so those are accepted; asking for real sampling is refused.
-        if self.do_sample and (self.top_k != 1 or self.repetition_penalty != 1.0):
-            raise NotImplementedError("lmdeploy_b200 implements the greedy decode path: do_sample=True needs top_k=1 and "
-                                      "repetition_penalty=1.0")
+        # With do_sample=False -- the default -- the reference decodes greedily WHATEVER top_k / top_p / temperature /
+        # repetition_penalty say (async_engine.py `_determine_gen_config` resets them).  do_sample=True runs the sampling
+        # stage on the device (csrc/sampling.cu: repetition penalty, temperature, top-k <= 1024, top-p, min-p, per-request
+        # random_seed); under tensor parallelism the logits are vocabulary-sharded and the engine refuses it at submission.
+        if self.do_sample and self.top_k > 1024:
+            raise ConfigError("top_k must be <= 1024 (the reference's top-k kernel limit, sampling_topk_kernels.cu:262-264)")
         # extra outputs read from the step's logits buffer (one GPU): the sampled row's logits / its top log-probabilities
         if self.output_logits not in (None, "generation"):
             raise NotImplementedError("output_logits='all' needs the logits of every prompt position; 'generation' is supported")

@@ -157,10 +157,78 @@ class TurboMind:
         out = self._execute(st)
         cu_q = st["cu_q_len"]
         rows = [cu_q[i + 1] - 1 for i in range(len(batch))]                              # sample = last row of each sequence
-        events = sched.update(batch, [out[r] for r in rows])
+        sampled = [out[r] for r in rows]
+        if any(s.sampling is not None for s in batch):
+            self._sample(batch, rows, sampled)
+        events = sched.update(batch, sampled)
         if any(s.want_logits or s.want_logprobs for s in batch):
             self._collect_extras(batch, rows, events, st["token_num"])
         return events
+
+    def _sample(self, batch, rows, sampled):
+        """do_sample sequences that produce a token in this step: the device sampling stage (b200_sample: repetition penalty,
+        temperature, top-k, top-p, min-p, one XORWOW state per request seeded by GenerationConfig.random_seed -- what
+        LogitsProcessor + Sampling do in the reference, generation/logits_processor.cc:66-125, generation/sampling.cc:92-183)
+        replaces the step's arg-max for their rows, reading the same logits buffer."""
+        import ctypes as C
+        import numpy as np
+        from .. import _lib as L
+        lib, dev = self.model.lib, self.model.device
+        items = [(i, s) for i, s in enumerate(batch) if s.sampling is not None and s.cached + s.step_tokens >= s.context_len]
+        if not items:
+            return
+        if not hasattr(self, "_rng_states"):
+            self._rng_bytes = lib.b200_sampling_rng_state_bytes()
+            self._rng_states = torch.zeros(self.max_batch * self._rng_bytes, dtype=torch.uint8, device=dev)
+            self._rng_free = list(range(self.max_batch - 1, -1, -1))
+            self._samp_ws = torch.zeros(lib.b200_sampling_workspace_bytes(self.max_batch, self.spec.vocab), dtype=torch.uint8,
+                                        device=dev)
+            self._rng_owner = {}
+        stream = torch.cuda.current_stream().cuda_stream
+        # slots of finished requests return to the free list; new requests get a slot and their seed
+        for slot, owner in list(self._rng_owner.items()):
+            if owner.finished:
+                del self._rng_owner[slot]
+                self._rng_free.append(slot)
+        fresh = [s for _, s in items if s.rng_slot < 0]
+        if fresh:
+            seeds = np.zeros(self.max_batch, np.uint64)
+            mask = np.zeros(self.max_batch, np.uint8)
+            for s in fresh:
+                s.rng_slot = self._rng_free.pop()
+                self._rng_owner[s.rng_slot] = s
+                seeds[s.rng_slot], mask[s.rng_slot] = s.sampling["seed"] & 0xFFFFFFFFFFFFFFFF, 1
+            d_seeds = torch.from_numpy(seeds.view(np.int64)).to(dev)
+            d_mask = torch.from_numpy(mask).to(dev)
+            L.check(lib.b200_sampling_init_rng(self._rng_states.data_ptr(), d_seeds.data_ptr(), d_mask.data_ptr(), self.max_batch,
+                                               stream), "b200_sampling_init_rng")
+        n = len(items)
+        f32 = lambda key: torch.tensor([s.sampling[key] for _, s in items], dtype=torch.float32, device=dev)
+        d_rows = torch.tensor([rows[i] for i, _ in items], dtype=torch.int32, device=dev)
+        d_t, d_p, d_m, d_pen = f32("temperature"), f32("top_p"), f32("min_p"), f32("repetition_penalty")
+        d_k = torch.tensor([s.sampling["top_k"] for _, s in items], dtype=torch.int32, device=dev)
+        d_slot = torch.tensor([s.rng_slot for _, s in items], dtype=torch.int32, device=dev)
+        d_out = torch.zeros(n, dtype=torch.int32, device=dev)
+        p = L.SamplingParams()
+        p.logits, p.ld = lib.b200_model_buffer(self.model.handle, 0), self.model.vocab_local
+        p.dtype, p.count, p.vocab = self.model.cfg.dtype, n, self.spec.vocab
+        p.rows, p.temperature, p.top_k, p.top_p, p.min_p = (d_rows.data_ptr(), d_t.data_ptr(), d_k.data_ptr(), d_p.data_ptr(),
+                                                            d_m.data_ptr())
+        hist = None
+        if any(s.sampling["repetition_penalty"] != 1.0 for _, s in items):
+            # the ids seen so far (prompt + generated), uploaded for the requests that ask for the penalty
+            hist = [torch.tensor((s.prompt + s.generated) if s.sampling["repetition_penalty"] != 1.0 else [0], dtype=torch.int32,
+                                 device=dev) for _, s in items]
+            d_hp = torch.tensor([h.data_ptr() for h in hist], dtype=torch.int64, device=dev)
+            d_hl = torch.tensor([h.numel() if s.sampling["repetition_penalty"] != 1.0 else 0 for h, (_, s) in zip(hist, items)],
+                                dtype=torch.int32, device=dev)
+            p.repetition_penalty, p.history, p.history_len = d_pen.data_ptr(), d_hp.data_ptr(), d_hl.data_ptr()
+        p.rng_states, p.rng_index, p.out_ids = self._rng_states.data_ptr(), d_slot.data_ptr(), d_out.data_ptr()
+        p.workspace, p.workspace_bytes, p.stream = self._samp_ws.data_ptr(), self._samp_ws.numel(), stream
+        L.check(lib.b200_sample(C.byref(p)), "b200_sample")
+        ids = d_out.cpu().tolist()
+        for (i, _), t in zip(items, ids):
+            sampled[i] = int(t)
 
     def _collect_extras(self, batch, rows, events, token_num):
         """output_logits='generation' / logprobs=k: for every token accepted in this step, the fp32 logits of the row it was
@@ -280,6 +348,12 @@ class TurboMindInstance:
         seq = Sequence(session_id=session_id, prompt=list(map(int, input_ids)), max_new_tokens=budget,
                        stop_token_ids=list(g.stop_token_ids or []), ignore_eos=g.ignore_eos, eos_id=self.engine.eos_id)
         seq.want_logits, seq.want_logprobs = g.output_logits == "generation", int(g.logprobs or 0)
+        if g.do_sample and not (g.top_k == 1 and g.repetition_penalty == 1.0):     # top_k == 1 without a penalty IS greedy
+            if getattr(self.engine, "channel", None) is not None or self.engine.model.tp_size != 1:
+                raise NotImplementedError("do_sample under tensor parallelism (the logits are vocabulary-sharded)")
+            seed = g.random_seed if g.random_seed is not None else int.from_bytes(os.urandom(8), "little")
+            seq.sampling = dict(temperature=float(g.temperature), top_k=int(g.top_k), top_p=float(g.top_p),
+                                min_p=float(g.min_p), repetition_penalty=float(g.repetition_penalty), seed=int(seed))
         if (seq.want_logits or seq.want_logprobs) and getattr(self.engine, "channel", None) is not None:
             raise NotImplementedError("logits / logprobs outputs under tensor parallelism (the logits are vocabulary-sharded)")
         self.engine.scheduler.add(seq)

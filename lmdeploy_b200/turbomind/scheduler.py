@@ -52,6 +52,8 @@ class Sequence:
     logits: List = field(default_factory=list)
     logprobs: List = field(default_factory=list)
     chain: List[int] = field(default_factory=list)      # prefix-cache identity of each full block so far
+    sampling: Optional[dict] = None   # do_sample requests: temperature / top_k / top_p / min_p / repetition_penalty / seed
+    rng_slot: int = -1                # ... and the device RNG state slot the engine gave it
 
     def token_at(self, pos):
         return self.prompt[pos] if pos < len(self.prompt) else self.generated[pos - len(self.prompt)]

@@ -11,7 +11,8 @@ sys.path.insert(0, ROOT)
 from lmdeploy_b200 import _lib as L  # noqa: E402
 
 PAIRS = [("b200_rope_config", L.RopeConfig), ("b200_attention_params", L.AttentionParams),
-         ("b200_linear_desc", L.LinearDesc), ("b200_model_config", L.ModelConfig), ("b200_step_inputs", L.StepInputs)]
+         ("b200_linear_desc", L.LinearDesc), ("b200_model_config", L.ModelConfig), ("b200_step_inputs", L.StepInputs),
+         ("b200_sampling_params", L.SamplingParams)]
 ENUMS = [("B200_T_EMBEDDING", L.T_EMBEDDING), ("B200_T_FINAL_NORM", L.T_FINAL_NORM), ("B200_T_ATTN_NORM", L.T_ATTN_NORM),
          ("B200_T_FFN_NORM", L.T_FFN_NORM), ("B200_T_QKV_BIAS", L.T_QKV_BIAS), ("B200_ERR_INVALID_ARG", L.ERR_INVALID_ARG),
          ("B200_ERR_UNSUPPORTED", L.ERR_UNSUPPORTED), ("B200_ERR_WORKSPACE", L.ERR_WORKSPACE), ("B200_ERR_STATE", L.ERR_STATE)]

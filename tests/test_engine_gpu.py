@@ -69,3 +69,24 @@ def test_engine_chunked_prefill_matches_token_by_token(monkeypatch):
     assert eng.scheduler.tick < 70 + 12                      # the 70-token prompt no longer costs 70 steps
     for x, y in zip(base, got):
         assert x[:4] == y[:4]
+
+
+def test_engine_sampling_is_a_function_of_the_seed(monkeypatch):
+    """do_sample requests through the engine: the same random_seed reproduces the same tokens (whatever the batch
+    composition -- every request owns its RNG state), different seeds differ, top_k = 1 is the greedy stream, and greedy
+    requests sharing the batch are untouched."""
+    from lmdeploy_b200.messages import GenerationConfig
+    from lmdeploy_b200.turbomind.engine import batched_generate
+    greedy = GenerationConfig(max_new_tokens=16, ignore_eos=True)
+    def samp(seed, **kw):
+        return GenerationConfig(max_new_tokens=16, ignore_eos=True, do_sample=True, top_k=kw.pop("top_k", 40), top_p=0.95,
+                                temperature=1.0, random_seed=seed, **kw)
+    prompts = [_PROMPTS[0], _PROMPTS[0], _PROMPTS[0], _PROMPTS[1]]
+    run = lambda cfgs: [list(s.generated) for s in batched_generate(_tiny_engine(monkeypatch), prompts, cfgs)]
+    a = run([samp(1), samp(2), greedy, samp(1, top_k=1)])
+    b = run([samp(2), samp(1), samp(1, repetition_penalty=1.3), greedy])
+    base = run([greedy] * 4)
+    assert a[0] == b[1] and a[1] == b[0]                       # seed decides, not the slot or the neighbours
+    assert a[0] != a[1] and a[0] != base[0]                    # 16 tokens of a random-weight model: collisions are ~impossible
+    assert a[2] == base[2] and b[3] == base[3] and a[3] == base[3]      # greedy rows, and top_k = 1, give the greedy stream
+    assert all(0 <= t < 1024 for row in a + b for t in row)

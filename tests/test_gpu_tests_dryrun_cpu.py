@@ -85,7 +85,7 @@ def cpu_as_cuda(monkeypatch, lib):
 
 GPU_MODULES = ("test_zz_pending_gpu", "test_decode_attention_gpu", "test_linear_gpu", "test_norm_gpu", "test_ref_attention_gpu",
                "test_decode_step_gpu", "test_linear_fp8_gpu", "test_decode_step_variants_gpu", "test_prefill_attention_gpu",
-               "test_engine_gpu")          # test_tp_gpu spawns NCCL ranks: its host side is tests/test_tp_gloo.py
+               "test_engine_gpu", "test_sampling_gpu")          # test_tp_gpu spawns NCCL ranks: its host side is tests/test_tp_gloo.py
 
 
 def _gpu_tests():

@@ -346,3 +346,30 @@ def test_logits_and_logprobs_outputs(dry, monkeypatch):
     eng.channel = object()
     with pytest.raises(NotImplementedError):
         TurboMindInstance(eng)._submit(78, [1, 2], cfg)
+
+
+def test_do_sample_requests_go_through_the_device_sampling_stage(dry, monkeypatch):
+    """A do_sample request: the engine seeds one RNG slot for it, calls b200_sample for its row with its parameters every step it
+    produces a token (the recording library "samples" id 0), greedy requests of the same batch keep the arg-max; the slot
+    returns to the pool when the request ends."""
+    import ctypes as C
+    from lmdeploy_b200.messages import GenerationConfig, TurbomindEngineConfig
+    from lmdeploy_b200.turbomind.engine import TurboMind, TurboMindInstance
+    from lmdeploy_b200.turbomind.runtime import DecodeModel
+    monkeypatch.setenv("B200_CHUNKED_PREFILL", "1")
+    model = DecodeModel(tiny("awq"), quant_policy=8, max_batch=8, device="cpu")
+    model.load_synthetic(seed=0)
+    eng = TurboMind(tiny("awq"), TurbomindEngineConfig(max_batch_size=8, session_len=64, cache_max_entry_count=16, quant_policy=8),
+                    model=model)
+    inst = TurboMindInstance(eng)
+    a = inst._submit(1, [5, 6], GenerationConfig(max_new_tokens=3, ignore_eos=True, do_sample=True, top_k=40, top_p=0.9,
+                                                 temperature=0.7, random_seed=123, repetition_penalty=1.2))
+    b = inst._submit(2, [7], GenerationConfig(max_new_tokens=3, ignore_eos=True))
+    assert a.sampling == dict(temperature=0.7, top_k=40, top_p=0.9, min_p=0.0, repetition_penalty=1.2, seed=123) and b.sampling is None
+    while eng.scheduler.has_work:
+        eng.step()
+    names = dry.names()
+    assert names.count("b200_sampling_init_rng") == 1 and names.count("b200_sample") == 3      # one per generated token of `a`
+    p = [args for n, args in dry.calls if n == "b200_sample"][0][0]._obj
+    assert p.count == 1 and p.vocab == 1000 and p.ld == model.vocab_local and p.repetition_penalty and p.history
+    assert a.rng_slot >= 0 and len(a.generated) == 3 and len(b.generated) == 3

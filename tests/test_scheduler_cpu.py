@@ -111,8 +111,9 @@ def test_engine_config_validation_matches_reference_rules():
         TurbomindEngineConfig(cache_max_entry_count=0)
     with pytest.raises(ValueError):
         TurbomindEngineConfig(dtype="float32")
-    with pytest.raises(NotImplementedError):
-        GenerationConfig(do_sample=True, top_k=40)
+    GenerationConfig(do_sample=True, top_k=40)                 # device sampling stage (csrc/sampling.cu)
+    with pytest.raises(ValueError):
+        GenerationConfig(do_sample=True, top_k=2000)           # the top-k kernel's limit, as in the reference
     GenerationConfig(max_new_tokens=8, top_k=1, ignore_eos=True)
 
 
@@ -658,7 +659,8 @@ def test_options_that_would_change_greedy_tokens_are_refused():
     GenerationConfig(temperature=0.3, top_p=0.8, top_k=40, min_p=0.1)          # sampling knobs are inert without do_sample
     GenerationConfig(do_sample=True, top_k=1)                                   # top_k = 1 is greedy
     GenerationConfig(repetition_penalty=1.1)        # reset to 1.0 for greedy requests by the reference (_determine_gen_config)
-    for kw in (dict(do_sample=True, top_k=1, repetition_penalty=1.1), dict(min_new_tokens=4), dict(do_sample=True, top_k=40)):
+    GenerationConfig(do_sample=True, top_k=40, repetition_penalty=1.1)         # sampled on the device
+    for kw in (dict(min_new_tokens=4),):
         with pytest.raises(NotImplementedError):
             GenerationConfig(**kw)
 
