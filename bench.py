@@ -442,12 +442,13 @@ def run_b200(args):
     torch.cuda.empty_cache()
     e2e = run_engine_e2e(args, torch, dist, model, spec, batch, ctx, qp, world, barrier)
 
+    kv_label = f"KV-int{qp}" if qp else "KV-fp16"
     line = {
         "metric": "decode tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": spec.dtype, "data": "synthetic",
-        "config": {"workload": {"awq": f"{name} W4A16(AWQ u4 g128)+KV-int{qp} greedy decode, bs={batch}, ctx={ctx}",
-                                "fp8": f"{name} FP8(e4m3 weights, bf16 activations)+KV-int{qp} greedy decode, bs={batch}, "
+        "config": {"workload": {"awq": f"{name} W4A16(AWQ u4 g128)+{kv_label} greedy decode, bs={batch}, ctx={ctx}",
+                                "fp8": f"{name} FP8(e4m3 weights, bf16 activations)+{kv_label} greedy decode, bs={batch}, "
                                        f"ctx={ctx}"}.get(spec.weight_format,
                                                          f"{name} fp16 + KV quant {qp} decode bs={batch} ctx={ctx}"),
                    "parallelism": f"tp{world}", "cuda_graph": use_graph,

@@ -329,6 +329,11 @@ B200_API void b200_comm_destroy(b200_comm* comm);
  * b200_comm_set_geometry fixes where the second half starts */
 B200_API int b200_comm_set_geometry(b200_comm* comm, int max_tokens, int hidden);
 B200_API void* b200_comm_local_buffer(b200_comm* comm, int half);
+/* NVLS: `mc_data` = the multicast address that maps every rank's exchange buffer (same offsets on every rank, e.g. from
+ * torch.distributed._symmetric_memory: rendezvous(...).multicast_ptr).  The fused all-reduce then takes the rank sum with
+ * ONE multimem.ld_reduce per 16 bytes (reduced inside the NVSwitch) instead of `world` peer loads -- what the reference's
+ * NVLS path does (comm/cuda_ipc/fused_allreduce.cu:169-274, multimem.cuh:14-45).  NULL = peer loads. */
+B200_API int b200_comm_set_multicast(b200_comm* comm, void* mc_data);
 /* hidden_partial: this rank's [tokens, dim] partial sums (T).  On return (stream order):
  *   residual += sum_ranks(hidden_partial) (+ bias);  out = RMSNorm(residual) * weight  (packed if out_packed_mt > 0) */
 B200_API int b200_comm_allreduce_residual_rmsnorm(b200_comm* comm, void* out, int out_packed_mt, void* residual,

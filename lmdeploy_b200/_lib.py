@@ -153,6 +153,7 @@ def load():
     lib.b200_comm_destroy.argtypes = [C.c_void_p]
     lib.b200_comm_local_buffer.restype = C.c_void_p
     lib.b200_comm_local_buffer.argtypes = [C.c_void_p, C.c_int]
+    lib.b200_comm_set_multicast.argtypes = [C.c_void_p, C.c_void_p]
     lib.b200_comm_set_geometry.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.b200_comm_set_geometry.restype = C.c_int
     lib.b200_comm_allreduce_residual_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,

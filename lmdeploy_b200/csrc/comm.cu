@@ -31,6 +31,7 @@ struct Peers {
     void* data[kMaxRanks];
     int*  flags[kMaxRanks];
     int*  slot_epoch;  // [kFlagSlots] this rank's per-CTA-slot epoch counters (device memory)
+    void* mc_data;     // NVLS: multicast address of the (symmetric) exchange buffers, or null
 };
 
 // epoch of this launch for this CTA slot (read by thread 0, broadcast through shared memory)
@@ -83,6 +84,27 @@ __device__ __forceinline__ uint4 ld_peer_v4(const void* p)
     return v;
 }
 
+// NVLS: one load returns the sum over every rank's copy of the address, reduced inside the NVSwitch
+// (multimem.ld_reduce, the instruction the reference's NVLS path uses: comm/cuda_ipc/multimem.cuh:14-45).
+template<class T>
+__device__ __forceinline__ uint4 multimem_ld_reduce_v4(const void* mc_ptr)
+{
+    uint4 v;
+    if constexpr (std::is_same<T, half>::value) {
+        asm volatile("multimem.ld_reduce.weak.global.add.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(mc_ptr)
+                     : "memory");
+    }
+    else {
+        asm volatile("multimem.ld_reduce.weak.global.add.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                     : "l"(mc_ptr)
+                     : "memory");
+    }
+    return v;
+}
+
 // Epochs grow by one per launch for the life of the communicator (2 L + 1 launches per step): compare them modulo
 // 2^32 so the waits stay correct when the counter wraps (a plain `flag < epoch` falls through at INT_MIN).
 __device__ __forceinline__ bool epoch_before(int flag, int epoch)
@@ -132,7 +154,9 @@ constexpr int kArMaxPass = 2;  // dim <= 512 * 8 * 2 = 8192
 // One CTA per token (grid-strided).  All peer loads of a token (world x passes 16-byte loads per thread) are issued
 // before the first add, so the exchange costs ONE NVLink round trip; the sum runs in rank order in T (bit-identical
 // on every rank), then residual add, sum of squares, normalisation -- the row never leaves registers.
-template<class T>
+// MC = true: the rank sum comes from ONE multimem.ld_reduce per 16 bytes (in-switch reduction, NVLS) instead of `world` peer
+// loads: a rank then moves tokens * dim * 2 bytes over its links instead of world times that.
+template<class T, bool MC>
 __global__ void __launch_bounds__(kArBlock) allreduce_residual_rmsnorm_kernel(
     Peers peers, int rank, int world, T* out, int out_mt, T* residual, const T* weight, const T* bias,
     int tokens, int dim, float eps, size_t data_offset)
@@ -153,11 +177,19 @@ __global__ void __launch_bounds__(kArBlock) allreduce_residual_rmsnorm_kernel(
 #pragma unroll
         for (int ps = 0; ps < kArMaxPass; ++ps) {
             const int i = (ps * kArBlock + threadIdx.x) * 8;
+            if constexpr (MC) {
+                if (ps < npass && i < dim) {
+                    v[ps][0] = multimem_ld_reduce_v4<T>(reinterpret_cast<const T*>((const char*)peers.mc_data + data_offset)
+                                                        + (size_t)tok * dim + i);
+                }
+            }
+            else {
 #pragma unroll
-            for (int q = 0; q < kMaxRanks; ++q) {
-                if (ps < npass && q < world && i < dim) {
-                    v[ps][q] = ld_peer_v4(reinterpret_cast<const T*>((const char*)peers.data[q] + data_offset)
-                                          + (size_t)tok * dim + i);
+                for (int q = 0; q < kMaxRanks; ++q) {
+                    if (ps < npass && q < world && i < dim) {
+                        v[ps][q] = ld_peer_v4(reinterpret_cast<const T*>((const char*)peers.data[q] + data_offset)
+                                              + (size_t)tok * dim + i);
+                    }
                 }
             }
         }
@@ -171,7 +203,7 @@ __global__ void __launch_bounds__(kArBlock) allreduce_residual_rmsnorm_kernel(
                 *reinterpret_cast<uint4*>(&sum[0]) = v[ps][0];
 #pragma unroll
                 for (int q = 1; q < kMaxRanks; ++q) {
-                    if (q < world) {
+                    if (!MC && q < world) {
                         T pv[8];
                         *reinterpret_cast<uint4*>(&pv[0]) = v[ps][q];
 #pragma unroll
@@ -381,6 +413,15 @@ extern "C" int b200_comm_create(b200_comm** out, int rank, int world, void* cons
     return 0;
 }
 
+extern "C" int b200_comm_set_multicast(b200_comm* c, void* mc_data)
+{
+    if (!c) {
+        return fail(B200_ERR_INVALID_ARG, "comm_set_multicast: comm is NULL");
+    }
+    c->peers.mc_data = mc_data;  // null switches back to the peer-load kernel
+    return 0;
+}
+
 extern "C" void* b200_comm_local_buffer(b200_comm* c, int half)
 {
     return c ? (char*)c->peers.data[c->rank] + (half ? c->half_bytes : 0) : nullptr;
@@ -411,16 +452,16 @@ extern "C" int b200_comm_allreduce_residual_rmsnorm(b200_comm* c, void* out, int
     const size_t off = (const char*)hidden_partial - base;
     cudaStream_t st  = (cudaStream_t)stream;
     const int    grid = comm_grid(tokens);
+    const bool mc = c->peers.mc_data != nullptr;
     if (dtype == B200_DTYPE_F16) {
-        launch_k(allreduce_residual_rmsnorm_kernel<half>, dim3(grid), dim3(kArBlock), 0, st, c->peers, c->rank, c->world, (half*)out,
-                                                                         out_packed_mt, (half*)residual,
-                                                                         (const half*)weight, (const half*)bias, tokens,
-                                                                         dim, eps, off);
+        auto kern = mc ? allreduce_residual_rmsnorm_kernel<half, true> : allreduce_residual_rmsnorm_kernel<half, false>;
+        launch_k(kern, dim3(grid), dim3(kArBlock), 0, st, c->peers, c->rank, c->world, (half*)out, out_packed_mt, (half*)residual,
+                 (const half*)weight, (const half*)bias, tokens, dim, eps, off);
     }
     else {
-        launch_k(allreduce_residual_rmsnorm_kernel<nv_bfloat16>, dim3(grid), dim3(kArBlock), 0, st, 
-            c->peers, c->rank, c->world, (nv_bfloat16*)out, out_packed_mt, (nv_bfloat16*)residual,
-            (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, tokens, dim, eps, off);
+        auto kern = mc ? allreduce_residual_rmsnorm_kernel<nv_bfloat16, true> : allreduce_residual_rmsnorm_kernel<nv_bfloat16, false>;
+        launch_k(kern, dim3(grid), dim3(kArBlock), 0, st, c->peers, c->rank, c->world, (nv_bfloat16*)out, out_packed_mt,
+                 (nv_bfloat16*)residual, (const nv_bfloat16*)weight, (const nv_bfloat16*)bias, tokens, dim, eps, off);
     }
     return check_launch("allreduce_residual_rmsnorm_kernel");
 }

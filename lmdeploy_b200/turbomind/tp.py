@@ -4,6 +4,7 @@ native NVLink communicator (b200_comm).  One process per GPU; torch.distributed 
 Stands where DeviceCommImpl allocation/registration stands in the reference
 (src/turbomind/comm/cuda_ipc/cuda_ipc_comm.cu:165-291)."""
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -18,7 +19,21 @@ class TpGroup:
         spec = model.spec
         nbytes = self.lib.b200_comm_buffer_bytes(model.max_batch, spec.hidden, model.vocab_local)
         fbytes = self.lib.b200_comm_flags_bytes()
-        self.local = []
+        self.local, self.opened, self.symm = [], [], None
+        self.nvls = False
+        # NVLS (B200_TP_NVLS=1, or =auto: used when the fabric offers it): the exchange buffers come from torch's symmetric
+        # memory, whose rendezvous also yields a MULTICAST address; the fused all-reduce then reduces inside the NVSwitch.
+        want = os.environ.get("B200_TP_NVLS", "0")
+        if want not in ("", "0") and world > 1:
+            try:
+                self._init_symmetric(model, rank, world, nbytes, fbytes, group)
+                return
+            except Exception as e:  # noqa: BLE001 -- any failure of the optional path falls back to CUDA IPC peer loads
+                if want != "auto":
+                    raise
+                self.symm = None
+                import warnings
+                warnings.warn(f"NVLS exchange unavailable ({e}); using CUDA-IPC peer loads")
         handles = []
         for size in (nbytes, fbytes):
             ptr = C.c_void_p()
@@ -28,7 +43,6 @@ class TpGroup:
             handles.append(bytes(h.raw))
         gathered = [None] * world
         dist.all_gather_object(gathered, handles, group=group)
-        self.opened = []
         data = (C.c_void_p * world)()
         flags = (C.c_void_p * world)()
         for r in range(world):
@@ -44,6 +58,28 @@ class TpGroup:
             data[r], flags[r] = ptrs
         self.handle = C.c_void_p()
         L.check(self.lib.b200_comm_create(C.byref(self.handle), rank, world, data, flags), "b200_comm_create")
+        model.set_comm(self.handle)
+        dist.barrier(group=group)
+
+    def _init_symmetric(self, model, rank, world, nbytes, fbytes, group):
+        import torch.distributed._symmetric_memory as symm
+        dev = model.device
+        total = (nbytes + 4095) // 4096 * 4096 + fbytes
+        gname = (group or dist.group.WORLD).group_name
+        buf = symm.empty(total, dtype=torch.uint8, device=dev)
+        buf.zero_()
+        torch.cuda.synchronize()
+        h = symm.rendezvous(buf, gname)
+        mc = int(getattr(h, "multicast_ptr", 0) or 0)
+        if not mc:
+            raise RuntimeError("symmetric memory rendezvous returned no multicast address")
+        foff = (nbytes + 4095) // 4096 * 4096
+        data = (C.c_void_p * world)(*[int(p) for p in h.buffer_ptrs])
+        flags = (C.c_void_p * world)(*[int(p) + foff for p in h.buffer_ptrs])
+        self.handle = C.c_void_p()
+        L.check(self.lib.b200_comm_create(C.byref(self.handle), rank, world, data, flags), "b200_comm_create")
+        L.check(self.lib.b200_comm_set_multicast(self.handle, C.c_void_p(mc)), "b200_comm_set_multicast")
+        self.symm, self.nvls = (buf, h), True
         model.set_comm(self.handle)
         dist.barrier(group=group)
 
