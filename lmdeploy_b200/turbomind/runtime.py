@@ -81,7 +81,15 @@ class DecodeModel:
         """rope_exact_math: correctly rounded RoPE transcendentals (comparable with the CPU oracle) instead of the
         reference release build's hardware approximations (the default; bit-identical K pages to TurboMind)."""
         self.lib = L.load()
-        plans = os.environ.get("B200_GEMM_PLANS")     # tuned GEMM launch plans (tools/gemm_sweep.cu writes the lines)
+        # tuned GEMM launch plans (tools/gemm_sweep.cu writes the lines): B200_GEMM_PLANS=<file>, else the table measured on a
+        # B200 that ships with the package (lmdeploy_b200/gemm_plans.txt; B200_GEMM_PLANS=none = heuristic only) -- the
+        # counterpart of the reference's GEMM dispatch cache (kernels/gemm/dispatch_cache.cu)
+        plans = os.environ.get("B200_GEMM_PLANS")
+        if plans is None:
+            default = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gemm_plans.txt")
+            plans = default if os.path.exists(default) else None
+        elif plans in ("", "none", "0"):
+            plans = None
         if plans:
             n = self.lib.b200_linear_load_plans(plans.encode())
             if n < 0:
