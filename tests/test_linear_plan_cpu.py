@@ -124,3 +124,24 @@ def _check_budgets_only(p, K, N, fmt, m):
     d_cols = (64 if mt <= 64 else 128) * p["tiles"]
     assert p["a_col"] >= d_cols and p["a_col"] + 64 * p["na"] <= p["tmem_cols"] <= TMEM_COLS
     assert p["na"] % p["tiles"] == 0 and p["na"] // p["tiles"] >= 1
+
+
+def test_the_shipped_plan_table_loads_and_every_entry_is_a_plan_the_kernel_accepts(lib):
+    """lmdeploy_b200/gemm_plans.txt (measured on a B200 by tools/gemm_sweep.cu) is what DecodeModel loads by default: it must
+    parse, pass the loader's budget checks, and change the plan of the shapes it names."""
+    import ctypes as C
+    import os
+    from lmdeploy_b200 import _lib as L
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lmdeploy_b200", "gemm_plans.txt")
+    entries = [ln.split()[1:9] for ln in open(path) if ln.startswith("PLAN")]
+    assert len(entries) >= 10
+    try:
+        assert lib.b200_linear_load_plans(path.encode()) == len({tuple(e[:4]) for e in entries}), lib.b200_last_error()
+        for fmt, mt, N, K, tiles, splits, nw, nx in (map(int, e) for e in entries):
+            d = L.LinearDesc(K, N, fmt, 0 if fmt != 3 else 1, 128, None, None)
+            out = (C.c_int * 8)()
+            assert lib.b200_linear_plan(C.byref(d), mt, out) == 0
+            assert (out[0], out[1], out[2], out[3]) == (tiles, splits, nw, nx), (N, K, list(out))
+            assert out[7] <= 225 * 1024
+    finally:
+        lib.b200_linear_load_plans(None)
