@@ -226,6 +226,13 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     while (pl.splits < 8 && nts * (pl.splits * 2) <= slots && kgs / (pl.splits * 2) >= 4) {
         pl.splits *= 2;
     }
+    // Short K (<= 16 groups: the row-split wo / w2 of a tensor-parallel shard): one tile per CTA and NO split beats any
+    // split plan -- the 4.3 us exchange costs more than the K-groups it saves (measured on the per-rank shapes of
+    // InternLM2-7B / 20B and Llama-3-70B at TP 2-8, profiles/r02_raw/gemm_sweep_*: e.g. K 1024, N 4096: 11.8 -> 5.3 us).
+    if (fmt != kDense && ov.tiles == 0 && ov.splits == 0 && kgs <= 16 && N / kBN <= slots) {
+        pl.tiles  = 1;
+        pl.splits = 1;
+    }
     if (ov.splits > 0) {
         pl.splits = ov.splits;
     }
