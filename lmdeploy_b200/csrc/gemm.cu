@@ -200,7 +200,7 @@ static bool lookup_plan(int fmt, int MT, int N, int K, PlanOverride* out)
     return true;
 }
 
-static Plan make_plan(int fmt, int MT, int N, int K)
+static Plan make_plan(int fmt, int MT, int N, int K, bool need_split = false)
 {
     const int WB     = block_bytes_of(fmt);
     const int WB_pad = (WB + 1023) & ~1023;
@@ -229,7 +229,8 @@ static Plan make_plan(int fmt, int MT, int N, int K)
     // Short K (<= 16 groups: the row-split wo / w2 of a tensor-parallel shard): one tile per CTA and NO split beats any
     // split plan -- the 4.3 us exchange costs more than the K-groups it saves (measured on the per-rank shapes of
     // InternLM2-7B / 20B and Llama-3-70B at TP 2-8, profiles/r02_raw/gemm_sweep_*: e.g. K 1024, N 4096: 11.8 -> 5.3 us).
-    if (fmt != kDense && ov.tiles == 0 && ov.splits == 0 && kgs <= 16 && N / kBN <= slots) {
+    // (need_split: the fused residual + RMSNorm epilogue lives in the split-K exchange and keeps the split plan.)
+    if (!need_split && fmt != kDense && ov.tiles == 0 && ov.splits == 0 && kgs <= 16 && N / kBN <= slots) {
         pl.tiles  = 1;
         pl.splits = 1;
     }
@@ -492,7 +493,7 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     p.K        = d->input_dim;
     p.MT       = mt;
     p.M        = m;
-    const Plan rg = make_plan(d->weight_format, mt, p.N, p.K);
+    const Plan rg = make_plan(d->weight_format, mt, p.N, p.K, epilogue == 2);
     p.splits = rg.splits, p.nw = rg.nw, p.nx = rg.nx, p.na = rg.na;
 #ifdef B200_GEMM_TOOL
     p.variant = g_plan_override.variant;

@@ -36,7 +36,7 @@ constexpr int kKG        = 128;  // K per pipeline stage (= quant group size)
 constexpr int kNormMaxItems = 4;  // fused residual+RMSNorm epilogue: (token, column-pair) items per thread
 constexpr int kMaxW     = 8;    // W ring slots (barrier arrays)
 constexpr int kMaxX     = 6;    // X ring slots
-constexpr int kASlots   = 6;    // max TMEM A-operand ring slots (64 columns each); Params::na in use
+constexpr int kASlots   = 4;    // max TMEM A-operand ring slots (64 columns each); Params::na in use
 constexpr int kDqWarps  = 16;   // dequant warps: 4 per TMEM lane quarter, one 32-wide k-chunk each
 constexpr int kXWarp    = 2 + kDqWarps;
 constexpr int kMmaWarp2 = kXWarp + 1;  // second MMA issuer (tile 1 of a two-tile CTA)
@@ -586,56 +586,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                 if (nk > 0) {
                     fetch(0, 0, 0);
                 }
-                // One 32-wide k-chunk of this thread's row: packed weights -> 16 registers of T pairs
-                auto convert = [&](int q, uint32_t s2, uint32_t t2, uint32_t (&r)[16]) {
-                    if constexpr (FMT == kU4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            uint32_t h[4];
-                            Ops::cvt_u4x8((&v[q][0].x)[u], h);
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
-                        }
-                    }
-                    else {
-                        // w = T(e4m3) *_T T(block scale): both factors are exact in fp32, so one fp32 multiply
-                        // rounded once to T is the T multiply of the reference (transform.h:92-97)
-                        const float sc = Ops::to_f32(Ops::from_bits((uint16_t)(st2 & 0xffffu)));
-#pragma unroll
-                        for (int u = 0; u < UNITS; ++u) {
-#pragma unroll
-                            for (int x = 0; x < 4; ++x) {
-                                const uint32_t w4 = (&v[q][u].x)[x];
-                                const float2   lo = cvt_e4m3x2_f32(w4 & 0xffffu);
-                                const float2   hi = cvt_e4m3x2_f32(w4 >> 16);
-                                r[u * 8 + x * 2]     = Ops::pack2(lo.x * sc, lo.y * sc);
-                                r[u * 8 + x * 2 + 1] = Ops::pack2(hi.x * sc, hi.y * sc);
-                            }
-                        }
-                    }
-                };
-                // The loop is rotated: the first chunk of group i is converted BEFORE waiting for group i - 1's tcgen05.st to
-                // retire (all warps of a tile used to stall on that wait together, right after issuing the stores: ~45 % of
-                // the loop's cycles were not issuing); group i - 1 is handed to the MMA warp half a conversion later, which
-                // the third A-operand slot per tile absorbs.
-                int prev_slot = -1;
                 for (int i = 0; i < nk; ++i) {
                     const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
-                    uint32_t       r[16];
-                    convert(0, s2, t2, r);
-                    if (prev_slot >= 0) {
-                        umma::wait_st();
-                        umma::fence_before_sync();
-                        mbar_arrive(smem_u32(&bar_aready[prev_slot]));
-                        if (warp == 2 && lane == 0) GEMM_TRACE(2, i - 1);
-                    }
                     // the TMEM slot must have been drained by the MMAs that used it last
                     GEMM_WAIT(smem_u32(&bar_aempty[a0 + sa]), pha ^ 1, 8, i);
                     umma::fence_after_sync();
-                    umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + kc0 * 16, r);
 #pragma unroll
-                    for (int q = 1; q < NKC; ++q) {
-                        convert(q, s2, t2, r);
+                    for (int q = 0; q < NKC; ++q) {
+                        uint32_t r[16];
+                        if constexpr (FMT == kU4) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                uint32_t h[4];
+                                Ops::cvt_u4x8((&v[q][0].x)[u], h);
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                            }
+                        }
+                        else {
+                            // w = T(e4m3) *_T T(block scale): both factors are exact in fp32, so one fp32 multiply
+                            // rounded once to T is the T multiply of the reference (transform.h:92-97)
+                            const float sc = Ops::to_f32(Ops::from_bits((uint16_t)(st2 & 0xffffu)));
+#pragma unroll
+                            for (int u = 0; u < UNITS; ++u) {
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) {
+                                    const uint32_t w4 = (&v[q][u].x)[x];
+                                    const float2   lo = cvt_e4m3x2_f32(w4 & 0xffffu);
+                                    const float2   hi = cvt_e4m3x2_f32(w4 >> 16);
+                                    r[u * 8 + x * 2]     = Ops::pack2(lo.x * sc, lo.y * sc);
+                                    r[u * 8 + x * 2 + 1] = Ops::pack2(hi.x * sc, hi.y * sc);
+                                }
+                            }
+                        }
                         umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + (kc0 + q) * 16, r);
                     }
                     // the W slot is free once its bytes are in registers (the arrive releases the reads)
@@ -647,17 +630,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                     if (i + 1 < nk) {
                         fetch(i + 1, sw, phw);
                     }
-                    prev_slot = a0 + sa;
+                    umma::wait_st();
+                    umma::fence_before_sync();
+                    mbar_arrive(smem_u32(&bar_aready[a0 + sa]));
+                    if (warp == 2 && lane == 0) GEMM_TRACE(2, i);
                     if (++sa == NAt) {
                         sa = 0;
                         pha ^= 1;
                     }
-                }
-                if (prev_slot >= 0) {
-                    umma::wait_st();
-                    umma::fence_before_sync();
-                    mbar_arrive(smem_u32(&bar_aready[prev_slot]));
-                    if (warp == 2 && lane == 0) GEMM_TRACE(2, nk - 1);
                 }
             }
             // epilogue role: (tile, token half) of the accumulator rows in this warp's lane quarter
