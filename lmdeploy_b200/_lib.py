@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200tm.so")
+# B200_LIB_PATH: another build of the same library (A/B measurements of a kernel variant); still no fallback
+LIB_PATH = os.environ.get("B200_LIB_PATH") or os.path.join(_HERE, "lib", "libb200tm.so")
 
 
 class B200LibraryError(RuntimeError):

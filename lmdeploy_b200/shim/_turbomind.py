@@ -170,9 +170,13 @@ class LinearWeight:
     def output_dtype(self):
         return self.data_type
 
-    def prepare(self):
-        """LinearWeight::prepare (models/linear_weight.cc:101-324): loader-visible layout -> kernel layout."""
+    def prepare(self, gated=False):
+        """LinearWeight::prepare (models/linear_weight.cc:101-324): loader-visible layout -> kernel layout.
+        gated: the harness sets Epilogue.kGatedSilu AFTER prepare() on a weight whose columns are packed
+        [gate block | up block] in 64-wide blocks (the sm90 layout); this library's gated epilogue pairs element-interleaved
+        (gate, up) columns, so forward_dense re-runs prepare with the columns permuted (dense weights only)."""
         lib = L.load()
+        self._gated = gated
         wt = self.weight_format.dtype
         dt = 0 if self.data_type == DataType.TYPE_FP16 else 1
         K, N = self.input_dim, self.output_dim
@@ -195,10 +199,16 @@ class LinearWeight:
         elif wt == self.data_type:
             fmt = L.FMT_DENSE
             wd = w.contiguous()
+            if gated:
+                blk = 64
+                wd = wd.view(K, N // (2 * blk), 2, blk).transpose(2, 3).reshape(K, N).contiguous()
             args = (wd.data_ptr(), None, None)
             keep = (wd,)
         else:
             raise NotImplementedError(f"weight type {wt}")
+        if gated and fmt != L.FMT_DENSE:
+            raise NotImplementedError("block-packed fused SiLU exists for dense weights only here (the quantised form is the "
+                                      "reference's sm90 path: per-block scales cannot follow an element-interleaved pairing)")
         self._desc = L.LinearDesc(K, N, fmt, dt, 128, None, None)
         nbytes = lib.b200_linear_prepared_bytes(C.byref(self._desc))
         if nbytes == 0:
@@ -226,6 +236,8 @@ class LlamaLinear:
             x = x.contiguous()
         m, K = x.shape
         gated = weight.epilogue == Epilogue.kGatedSilu
+        if gated and not getattr(weight, "_gated", False):
+            weight.prepare(gated=True)
         nout = weight.output_dim // 2 if gated else weight.output_dim
         y = output._t if output else torch.empty(m, nout, dtype=x.dtype, device=x.device)
         st = torch.cuda.current_stream().cuda_stream
@@ -307,7 +319,7 @@ def QuantizeGroupwise(quant=None, scales=None, zeros=None, dequant=None, src=Non
     dequant._t.copy_(dq.to(dequant._t.dtype))
     qi = q.reshape(N, K).to(torch.uint8).t().contiguous()                 # [K, N]
     packed = (qi[:, 0::2] | (qi[:, 1::2] << 4)).contiguous()              # two columns per byte, low nibble first
-    quant._t.t().copy_(packed) if quant._t.shape != packed.shape else quant._t.copy_(packed)
+    quant._t.t().copy_(packed)                                             # quant is the .t() view of the [K, N / 2] bytes
 
 
 def MakeStridedPtrs(ptrs, dtype):

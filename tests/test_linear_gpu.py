@@ -77,7 +77,7 @@ def _assert_close(got, ref, atol=2e-4, rtol=2e-3):
     assert not bad.any(), f"{bad.sum()} / {bad.size} out of tolerance; max err {err.max()} at {np.unravel_index(err.argmax(), err.shape)} ref {ref.flat[err.argmax()]} got {got.flat[err.argmax()]}"
 
 
-@pytest.mark.parametrize("shape", [(256, 128), (1024, 256), (4096, 6144), (4096, 4096), (14336, 4096)])
+@pytest.mark.parametrize("shape", [(256, 128), (1024, 256), (4096, 6144), (4096, 4096), (14336, 4096), (2048, 4096), (3072, 6144)])
 @pytest.mark.parametrize("m", [1, 16, 64])
 def test_w4a16_f16(lib, shape, m):
     K, N = shape

@@ -33,3 +33,61 @@ def test_reference_smoke_linear_suite_passes_against_the_shim():
     print(r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+
+
+# The harness's `custom` suite (cases.py: expand_suite) widened to the formats of the hot path -- the W4A16 (f16 x u4 g128)
+# GEMM first -- on decode batch sizes, TP 1 and 2.  The module below is the only file added next to the harness; it repeats
+# the body of the harness's own smoke test over another case list.
+_CUSTOM_MODULE = """
+import pytest
+from . import linear as linear_mod
+from .cases import expand_suite
+from .fixture import LinearFixture
+
+RUNS = [r for r in expand_suite('custom',
+                                type_names=('f16_u4k128_f16', 'f16_f16_f16', 'bf16_bf16_bf16', 'bf16_e4m3b128_bf16'),
+                                shape_names=('llama3_8b_qkv', 'llama3_8b_o', 'llama3_8b_gate_up', 'llama3_8b_down',
+                                             'internlm2_20b_o'),
+                                batches=(1, 3, 16, 17, 64, 128), tps=(1, 2))
+        if r.case.fuse_silu == FUSE and not (FUSE and r.case.weight_type != r.case.data_type)]
+
+
+@pytest.mark.parametrize('run', RUNS, ids=lambda r: f'{r.case.name}_tp{r.case.tp}_m{r.batch_size}')
+def test_custom_linear_correctness(run):
+    fx = LinearFixture(run.case)
+    try:
+        fx.prepare_batch(run.batch_size)
+        fx.run_reference()
+        fx.run_linear()
+        fx.check_tolerances(fx.compare())
+    finally:
+        fx.close()
+"""
+
+
+def _run_custom(fuse):
+    d = _harness_dir()
+    if d is None or not os.access(d, os.W_OK):
+        pytest.skip("needs a writable copy of the reference's tests/turbomind/linear directory (B200_REF_LINEAR_TESTS)")
+    name = f"test_b200_custom_{'silu' if fuse else 'plain'}.py"
+    with open(os.path.join(d, name), "w") as f:
+        f.write(_CUSTOM_MODULE.replace("FUSE", "True" if fuse else "False"))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "lmdeploy_b200", "shim"), ROOT, env.get("PYTHONPATH", "")])
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(d, name), "-q", "-p", "no:cacheprovider", "-rfE",
+                        "--tb=line"], env=env, capture_output=True, text=True, timeout=1800)
+    print(r.stdout[-6000:])
+    print(r.stderr[-2000:])
+    return r
+
+
+def test_reference_harness_custom_suite_w4a16_dense_fp8():
+    r = _run_custom(False)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
+
+
+def test_reference_harness_custom_suite_block_packed_fused_silu_dense():
+    r = _run_custom(True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "skipped" not in r.stdout.splitlines()[-1], r.stdout[-500:]
