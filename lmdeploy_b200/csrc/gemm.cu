@@ -64,6 +64,51 @@ __global__ void prepare_u4_kernel(uint8_t* dst, const uint32_t* qweight, const T
     }
 }
 
+// u4 x f16 "subnormal" layout (gemm.cuh: kU4FastShift).  Pass 1: is every scale * 2^17 finite in f16?  Pass 2 (device-side
+// decision, no host round trip): rotate the packed words left by 3, store the scales times 2^17, raise the flag.
+__global__ void u4_fast_check_kernel(const uint8_t* blocks_, size_t nblocks, int* trailer)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        trailer[0] = 0;
+    }
+    int bad = 0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nblocks * kBN; idx += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t pr = reinterpret_cast<const uint32_t*>(blocks_ + (idx / kBN) * kU4BlockBytes + 8192)[idx % kBN];
+        const float    sc = __half2float(__ushort_as_half((unsigned short)(pr & 0xffffu)));
+        bad |= !(fabsf(sc) * (float)(1 << kU4FastShift) <= 65504.f);  // also catches NaN / inf
+    }
+    if (bad) {
+        atomicOr(trailer + 1, 1);
+    }
+}
+
+__global__ void u4_fast_apply_kernel(uint8_t* blocks_, size_t nblocks, int* trailer)
+{
+    if (*(volatile int*)(trailer + 1) != 0) {
+        return;  // some scale is out of range: the stream keeps the plain layout, flag stays 0
+    }
+    const size_t nw = nblocks * (kU4BlockBytes / 4);
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < nw; idx += (size_t)gridDim.x * blockDim.x) {
+        const int within = (int)(idx % (kU4BlockBytes / 4));
+        uint32_t* w      = reinterpret_cast<uint32_t*>(blocks_) + idx;
+        uint32_t  x      = *w;
+        if (within < 2048) {
+            x = __funnelshift_l(x, x, 3);
+        }
+        else {
+            const float sc = __half2float(__ushort_as_half((unsigned short)(x & 0xffffu))) * (float)(1 << kU4FastShift);
+            x              = (x & 0xffff0000u) | __half_as_ushort(__float2half_rn(sc));  // exact: a power-of-two multiple
+        }
+        *w = x;
+    }
+}
+
+__global__ void u4_fast_flag_kernel(int* trailer)
+{
+    trailer[0] = trailer[1] == 0 ? 1 : 0;
+    trailer[1] = 0;
+}
+
 // fp8 (e4m3 + 128x128 block scales, SURVEY 8a11 / linear_weight.cc:138-150): W u8 [K, N] (trans == 0) or [N, K]
 // (trans == 1), scale_inv f32 [K/128, N/128]  ->  per (nt, kg): data [k16:8][n:128][16 B], then the block scale cast to T
 template<class T>
@@ -246,6 +291,16 @@ static Plan make_plan(int fmt, int MT, int N, int K, bool need_split = false)
         pl.nw = 3;
         pl.nx = std::max(2, std::min(kMaxX, (budget - pl.nw * wslot) / XB));
     }
+    // u4: a W ring of exactly 8 slots selects the de-quantisation loop that is unrolled over one lap of the ring (all ring
+    // positions compile-time constants, 126 instead of 162 instructions per k-group); trade X slots for it while >= 3 remain
+    if (fmt == kU4 && pl.nw < 8) {
+        for (int nx = pl.nx - 1; nx >= 3; --nx) {
+            if ((budget - nx * XB) / wslot >= 8) {
+                pl.nx = nx, pl.nw = 8;
+                break;
+            }
+        }
+    }
     if (ov.nw > 0 && ov.nx > 0) {
         pl.nw = std::min(kMaxW, ov.nw), pl.nx = std::min(kMaxX, ov.nx);
     }
@@ -382,7 +437,12 @@ extern "C" size_t b200_linear_prepared_bytes(const b200_linear_desc* d)
         return 0;
     }
     const size_t blocks = (size_t)(d->output_dim / kBN) * (d->input_dim / kKG);
-    return blocks * block_bytes_of(d->weight_format);
+    return blocks * block_bytes_of(d->weight_format) + (d->weight_format == kU4 ? kU4TrailerBytes : 0);
+}
+
+static size_t u4_trailer_offset(const b200_linear_desc* d)
+{
+    return (size_t)(d->output_dim / kBN) * (d->input_dim / kKG) * kU4BlockBytes;
 }
 
 extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight, const void* scales, const void* zeros,
@@ -400,9 +460,21 @@ extern "C" int b200_linear_prepare(const b200_linear_desc* d, const void* weight
         if (!scales) {
             return fail(B200_ERR_INVALID_ARG, "u4 weights need scales");
         }
+        int* trailer = reinterpret_cast<int*>((uint8_t*)prepared + u4_trailer_offset(d));
+        cudaMemsetAsync(trailer, 0, kU4TrailerBytes, st);
         if (d->dtype == B200_DTYPE_F16) {
             prepare_u4_kernel<half><<<1024, 256, 0, st>>>((uint8_t*)prepared, (const uint32_t*)weight,
                                                           (const half*)scales, (const half*)zeros, K, N);
+            static const bool plain = [] {
+                const char* e = getenv("B200_U4_PLAIN");  // keep the plain layout (A/B measurements, tests of the fallback)
+                return e && *e && *e != '0';
+            }();
+            if (!plain) {
+                const size_t nblocks = (size_t)(N / kBN) * (K / kKG);
+                u4_fast_check_kernel<<<512, 256, 0, st>>>((const uint8_t*)prepared, nblocks, trailer);
+                u4_fast_apply_kernel<<<1024, 256, 0, st>>>((uint8_t*)prepared, nblocks, trailer);
+                u4_fast_flag_kernel<<<1, 1, 0, st>>>(trailer);
+            }
         }
         else {
             prepare_u4_kernel<nv_bfloat16><<<1024, 256, 0, st>>>((uint8_t*)prepared, (const uint32_t*)weight,
@@ -484,6 +556,7 @@ static int forward_packed(const b200_linear_desc* d, const void* xp, int mt, int
     }
     Params p{};
     p.w        = (const uint8_t*)d->prepared;
+    p.u4_fast  = d->weight_format == kU4 ? reinterpret_cast<const int*>((const uint8_t*)d->prepared + u4_trailer_offset(d)) : nullptr;
     p.xp       = xp;
     p.y        = y;
     p.bias     = d->bias;

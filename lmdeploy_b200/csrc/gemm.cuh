@@ -28,6 +28,8 @@
 
 #include "umma.cuh"
 
+#include <type_traits>
+
 namespace b200 {
 namespace gemm {
 
@@ -56,6 +58,15 @@ enum WeightFormat : int
 };
 
 constexpr int kU4BlockBytes    = 8192 + 512;           // one (n-tile, k-group): data + fused params
+// u4 x f16 "subnormal" layout (chosen by b200_linear_prepare when every |scale| * 2^17 is finite in f16, i.e. always for real
+// checkpoints): a nibble q sitting at bits 7..10 of an f16 lane IS the number q * 2^-17 (the f16 encoding is linear across the
+// subnormals and the first binade), so  fma(q * 2^-17, s * 2^17, t)  ==  fma(q, s, t)  bit for bit -- the same single rounding
+// of the same real number -- without the magic-number subtraction: 11 instead of 13 instructions per 8 weights, and 4 instead of
+// 8 of them on the fma pipe.  The packed words are stored rotated left by 3 so that the nibble fields sit at bits 3, 7, .. 31
+// (the last one wraps) and three shifts / one rotate bring every pair to bits 7..10 / 23..26; scales are stored times 2^17.
+constexpr int      kU4FastShift  = 17;
+constexpr uint32_t kU4FastMask   = 0x07800780u;
+constexpr int      kU4TrailerBytes = 256;  // after the last block: word 0 = layout flag, word 1 = scratch of the range check
 constexpr int kDenseBlockBytes = kBN * kKG * 2;        // 32 KB
 constexpr int kFp8BlockBytes   = kBN * kKG + 16;       // e4m3 data [k16:8][n:128][16 B] + block scale (T, padded to 16 B)
 constexpr int kFp8ColBlockBytes = kBN * kKG + kBN * 4; // same data + one scale per row (T in the low half of 4 B)
@@ -149,6 +160,7 @@ struct Params {
     int            out_mode;  // 0 row-major [M][ldy]; 1 packed [Nout/8][out_mt][8]
     int            ldy;
     int            out_mt;
+    const int*     u4_fast;    // u4 + f16 only: trailer word of the prepared stream, 1 = "subnormal" layout (see kU4FastShift)
     int            tmem_cols;  // 256 or 512 (power of two)
     int            a_col;      // first TMEM column of the A-operand ring
 #ifdef B200_GEMM_TRACE
@@ -583,60 +595,138 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_kernel(const Params p)
                         }
                     }
                 };
+                // One 32-wide k-chunk of this thread's row: packed weights -> 16 registers of T pairs
+                auto convert = [&](auto DN, int q, uint32_t s2, uint32_t t2, uint32_t (&r)[16]) {
+                    if constexpr (FMT == kU4) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            uint32_t h[4];
+                            if constexpr (decltype(DN)::value) {
+                                const uint32_t x = (&v[q][0].x)[u];
+                                h[0] = (x << 4) & kU4FastMask;
+                                h[1] = x & kU4FastMask;
+                                h[2] = (x >> 4) & kU4FastMask;
+                                h[3] = __funnelshift_r(x, x, 8) & kU4FastMask;
+                            }
+                            else {
+                                Ops::cvt_u4x8((&v[q][0].x)[u], h);
+                            }
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
+                        }
+                    }
+                    else {
+                        // w = T(e4m3) *_T T(block scale): both factors are exact in fp32, so one fp32 multiply
+                        // rounded once to T is the T multiply of the reference (transform.h:92-97)
+                        const float sc = Ops::to_f32(Ops::from_bits((uint16_t)(st2 & 0xffffu)));
+#pragma unroll
+                        for (int u = 0; u < UNITS; ++u) {
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                const uint32_t w4 = (&v[q][u].x)[x];
+                                const float2   lo = cvt_e4m3x2_f32(w4 & 0xffffu);
+                                const float2   hi = cvt_e4m3x2_f32(w4 >> 16);
+                                r[u * 8 + x * 2]     = Ops::pack2(lo.x * sc, lo.y * sc);
+                                r[u * 8 + x * 2 + 1] = Ops::pack2(hi.x * sc, hi.y * sc);
+                            }
+                        }
+                    }
+                };
+                // layout flag of the prepared stream (a constant of the weight: read before griddepcontrol.wait matters not)
+                bool dn = false;
+                if constexpr (FMT == kU4 && std::is_same<T, half>::value) {
+                    dn = p.u4_fast != nullptr && __ldg(p.u4_fast) != 0;
+                }
                 if (nk > 0) {
                     fetch(0, 0, 0);
                 }
-                for (int i = 0; i < nk; ++i) {
-                    const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
-                    // the TMEM slot must have been drained by the MMAs that used it last
-                    GEMM_WAIT(smem_u32(&bar_aempty[a0 + sa]), pha ^ 1, 8, i);
-                    umma::fence_after_sync();
+                // Fast path (u4, W ring of exactly kFastW slots, kASlots A slots): the loop is unrolled over one lap of the W
+                // ring, so every ring position -- barrier addresses, shared-memory and TMEM offsets, the A ring's phase --
+                // is a compile-time constant.  ncu (r02_gemm.ncu-rep, w1w3): the schedulers of an active SM issue 96 % of
+                // the cycles and 55 of the 162 instructions a de-quantisation warp spends per k-group were ring
+                // bookkeeping (uniform-datapath address arithmetic, wrap / phase selects) re-derived every group.
+                constexpr int kFastW = 8;
+                constexpr int NAT_C  = kASlots / TILES;
+                if (FMT == kU4 && TILES <= 2 && p.nw == kFastW && NAt == NAT_C) {
+                    const uint32_t aempty0 = smem_u32(&bar_aempty[0]) + a0 * 8, aready0 = smem_u32(&bar_aready[0]) + a0 * 8;
+                    const uint32_t wempty0 = smem_u32(&bar_wempty[0]);
+                    const uint32_t tm_a    = trow + p.a_col + a0 * 64 + kc0 * 16;
+                    auto           lap_loop = [&](auto DN) {
+                        uint32_t lap = 0;  // parity of the W ring's lap = (i / kFastW) & 1
+                        for (int i0 = 0; i0 < nk; i0 += kFastW) {
 #pragma unroll
-                    for (int q = 0; q < NKC; ++q) {
-                        uint32_t r[16];
-                        if constexpr (FMT == kU4) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                uint32_t h[4];
-                                Ops::cvt_u4x8((&v[q][0].x)[u], h);
-#pragma unroll
-                                for (int x = 0; x < 4; ++x) r[u * 4 + x] = Ops::fma2(h[x], s2, t2);
-                            }
-                        }
-                        else {
-                            // w = T(e4m3) *_T T(block scale): both factors are exact in fp32, so one fp32 multiply
-                            // rounded once to T is the T multiply of the reference (transform.h:92-97)
-                            const float sc = Ops::to_f32(Ops::from_bits((uint16_t)(st2 & 0xffffu)));
-#pragma unroll
-                            for (int u = 0; u < UNITS; ++u) {
-#pragma unroll
-                                for (int x = 0; x < 4; ++x) {
-                                    const uint32_t w4 = (&v[q][u].x)[x];
-                                    const float2   lo = cvt_e4m3x2_f32(w4 & 0xffffu);
-                                    const float2   hi = cvt_e4m3x2_f32(w4 >> 16);
-                                    r[u * 8 + x * 2]     = Ops::pack2(lo.x * sc, lo.y * sc);
-                                    r[u * 8 + x * 2 + 1] = Ops::pack2(hi.x * sc, hi.y * sc);
+                            for (int U = 0; U < kFastW; ++U) {
+                                const int i = i0 + U;
+                                if (i >= nk) {
+                                    break;
                                 }
+                                const int      SA = U % NAT_C;               // compile-time after unrolling
+                                const uint32_t pa = ((U / NAT_C) & 1) ^ 1u;  // kFastW / NAT_C is even: the A phase restarts every lap
+                                const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
+                                GEMM_WAIT(aempty0 + SA * 8, pa, 8, i);
+                                umma::fence_after_sync();
+#pragma unroll
+                                for (int q = 0; q < NKC; ++q) {
+                                    uint32_t r[16];
+                                    convert(DN, q, s2, t2, r);
+                                    umma::st_32x32b_x16(tm_a + SA * 64 + q * 16, r);
+                                }
+                                mbar_arrive(wempty0 + U * 8);
+                                if (i + 1 < nk) {
+                                    fetch(i + 1, (U + 1) % kFastW, U + 1 == kFastW ? lap ^ 1u : lap);
+                                }
+                                umma::wait_st();
+                                umma::fence_before_sync();
+                                mbar_arrive(aready0 + SA * 8);
+                                if (warp == 2 && lane == 0) GEMM_TRACE(2, i);
+                            }
+                            lap ^= 1u;
+                        }
+                    };
+                    if (dn) {
+                        lap_loop(std::true_type{});
+                    }
+                    else {
+                        lap_loop(std::false_type{});
+                    }
+                }
+                else {
+                    auto ring_loop = [&](auto DN) {
+                        for (int i = 0; i < nk; ++i) {
+                            const uint32_t s2 = __byte_perm(st2, st2, 0x1010), t2 = __byte_perm(st2, st2, 0x3232);
+                            // the TMEM slot must have been drained by the MMAs that used it last
+                            GEMM_WAIT(smem_u32(&bar_aempty[a0 + sa]), pha ^ 1, 8, i);
+                            umma::fence_after_sync();
+#pragma unroll
+                            for (int q = 0; q < NKC; ++q) {
+                                uint32_t r[16];
+                                convert(DN, q, s2, t2, r);
+                                umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + (kc0 + q) * 16, r);
+                            }
+                            // the W slot is free once its bytes are in registers (the arrive releases the reads)
+                            mbar_arrive(smem_u32(&bar_wempty[sw]));
+                            if (++sw == p.nw) {
+                                sw = 0;
+                                phw ^= 1;
+                            }
+                            if (i + 1 < nk) {
+                                fetch(i + 1, sw, phw);
+                            }
+                            umma::wait_st();
+                            umma::fence_before_sync();
+                            mbar_arrive(smem_u32(&bar_aready[a0 + sa]));
+                            if (warp == 2 && lane == 0) GEMM_TRACE(2, i);
+                            if (++sa == NAt) {
+                                sa = 0;
+                                pha ^= 1;
                             }
                         }
-                        umma::st_32x32b_x16(trow + p.a_col + (a0 + sa) * 64 + (kc0 + q) * 16, r);
+                    };
+                    if (dn) {
+                        ring_loop(std::true_type{});
                     }
-                    // the W slot is free once its bytes are in registers (the arrive releases the reads)
-                    mbar_arrive(smem_u32(&bar_wempty[sw]));
-                    if (++sw == p.nw) {
-                        sw = 0;
-                        phw ^= 1;
-                    }
-                    if (i + 1 < nk) {
-                        fetch(i + 1, sw, phw);
-                    }
-                    umma::wait_st();
-                    umma::fence_before_sync();
-                    mbar_arrive(smem_u32(&bar_aready[a0 + sa]));
-                    if (warp == 2 && lane == 0) GEMM_TRACE(2, i);
-                    if (++sa == NAt) {
-                        sa = 0;
-                        pha ^= 1;
+                    else {
+                        ring_loop(std::false_type{});
                     }
                 }
             }

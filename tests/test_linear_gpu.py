@@ -90,6 +90,34 @@ def test_w4a16_f16(lib, shape, m):
     _assert_close(got, ref)
 
 
+def _layout_flag(lin):
+    """trailer word 0 of a prepared u4 stream: 1 = the f16 "subnormal" layout (gemm.cuh: kU4FastShift), 0 = plain"""
+    import torch
+    return int(lin.prepared[-256:-252].view(torch.int32).item())
+
+
+def test_w4a16_layout_flag_and_out_of_range_scales(lib):
+    """f16 streams whose scales all fit use the subnormal layout (nibble at bits 7..10 of an f16 lane = q * 2^-17, scales stored
+    times 2^17: the same fma, bit for bit); one scale >= 0.5 keeps the whole tensor in the plain layout; bf16 is always plain.
+    Both layouts must give the oracle's numbers."""
+    K, N = 1024, 256
+    rng = np.random.default_rng(77)
+    w = (rng.standard_normal((K, N)) * 0.1 / np.sqrt(K)).astype(np.float32)
+    x = rn(rng.standard_normal((17, K)).astype(np.float32), F16)
+    q, s, z = OL.quantize_groupwise_u4(w, 128)
+    lin = DevLinear(lib, K, N, 1, F16, q, s, z)
+    assert _layout_flag(lin) == 1
+    _assert_close(lin.forward(x), OL.linear(x, OL.dequant_u4(q, s, z, F16), F16))
+    assert _layout_flag(DevLinear(lib, K, N, 1, BF16, q, s, z)) == 0
+    w2 = w.copy()
+    w2[:128, :64] *= 3000.0                       # one 128 x 64 patch with a range of ~60: scales ~4
+    q2, s2, z2 = OL.quantize_groupwise_u4(w2, 128)
+    assert float(np.abs(s2).max()) > 0.5
+    lin2 = DevLinear(lib, K, N, 1, F16, q2, s2, z2)
+    assert _layout_flag(lin2) == 0
+    _assert_close(lin2.forward(x), OL.linear(x, OL.dequant_u4(q2, s2, z2, F16), F16), atol=2e-3, rtol=2e-3)
+
+
 @pytest.mark.parametrize("m", [3, 33, 128])
 def test_w4a16_ragged_m_and_bias(lib, m):
     K, N = 512, 384
