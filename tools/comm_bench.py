@@ -22,7 +22,8 @@ class RawBuf:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
-for tokens, hidden in ((64, 4096), (64, 6144), (32, 8192), (8, 4096)):
+SHAPES = ((64, 4096), (32, 8192)) if "--short" in sys.argv else ((64, 4096), (64, 6144), (32, 8192), (8, 4096))
+for tokens, hidden in SHAPES:
     model = types.SimpleNamespace(spec=types.SimpleNamespace(hidden=hidden), max_batch=64, vocab_local=92544 // world,
                                   device=torch.device("cuda", torch.cuda.current_device()), set_comm=lambda h: None)
     tp = TpGroup(model, rank, world)
