@@ -143,6 +143,11 @@ B200_DEVICE void named_bar_sync(int id, int threads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
+// non-blocking arrival on a named barrier other warps bar.sync on (`threads` = arrivals + waiters)
+B200_DEVICE void named_bar_arrive(int id, int threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------
 // shared loads

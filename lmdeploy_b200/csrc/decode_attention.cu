@@ -134,13 +134,20 @@ struct PrologueParams {
     int         num_kv_heads;
     RopeConst   rope;
     const float2* rope_table;  // [token][kHeadDim/2] (cos, sin) or null
+    int           wait_first;  // trigger the dependent grid only after griddepcontrol.wait (KernelParams::early)
 };
 
 template<class T, int KVBITS>
 __global__ void __launch_bounds__(128) kv_prologue_kernel(const PrologueParams p)
 {
-    pdl_launch_dependents();
-    pdl_wait();
+    if (p.wait_first) {
+        pdl_wait();
+        pdl_launch_dependents();
+    }
+    else {
+        pdl_launch_dependents();
+        pdl_wait();
+    }
     using Ops      = TypeOps<T>;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -405,9 +412,10 @@ static int validate(const b200_attention_params* a, bool decode)
 }
 
 template<class T, int KVBITS>
-static int launch_prologue(const b200_attention_params* a, void* q_rot, cudaStream_t st)
+static int launch_prologue(const b200_attention_params* a, void* q_rot, cudaStream_t st, int wait_first = 0)
 {
     PrologueParams p{};
+    p.wait_first         = wait_first;
     p.q = a->q, p.k = a->k, p.v = a->v, p.stride = a->stride;
     p.q_bias = a->q_bias, p.k_bias = a->k_bias, p.v_bias = a->v_bias;
     p.q_rot              = q_rot;
@@ -466,8 +474,16 @@ static int launch_decode(const b200_attention_params* a)
         }
         plan = w.plan;
     }
-    if (!(want & 1) && !(a->debug_flags & 1)) {
-        if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st)) {
+    // Early KV streaming (KernelParams::early): needs a plan computed well before this call (the caller's), the separate
+    // prologue kernel, and is pointless without it.  B200_ATTN_EARLY=0 turns it off (A/B measurements).
+    static const bool env_early = [] {
+        const char* e = getenv("B200_ATTN_EARLY");
+        return !(e && *e == '0');  // measured: 4.148 -> 4.101 ms per C2 step (profiles/r02_attention_variants.md)
+    }();
+    const bool run_prologue = !(want & 1) && !(a->debug_flags & 1);
+    const int  early        = env_early && a->plan != nullptr && run_prologue ? 1 : 0;
+    if (run_prologue) {
+        if (int e = launch_prologue<T, KVBITS>(a, w.q_rot, st, early)) {
             return e;
         }
     }
@@ -495,6 +511,7 @@ static int launch_decode(const b200_attention_params* a)
     p.qk_scale      = a->inv_sqrt_dh;
     p.out_mt        = a->out_packed_mt;
     p.grid_main     = grid;
+    p.early         = early;
     if (!unfused) {
         // debug_flags bit 0 / bit 1 keep their meaning (skip the prologue / the fix-up) for kernel-only timing
         p.fused = ((a->debug_flags & 1) ? 0 : (want & 1)) | ((a->debug_flags & 2) ? 0 : (want & 2));

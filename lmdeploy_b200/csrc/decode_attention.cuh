@@ -267,6 +267,7 @@ struct KernelParams {
     RopeConst      rope;
     int*           seg_counters;  // [batch * Hkv] arrivals per straddling segment; zero on entry, left zero
     int            grid_main;
+    int            early;  // the producer warp streams KV tiles before griddepcontrol.wait (see the kernel's head)
 };
 
 // slot (0..15 inside a warp's 16-key MMA) -> token index inside the 64-token tile
@@ -789,9 +790,16 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    // the tile plan, q and the page of the new token all come from kernels earlier in the step
+    // q and the page of the new token come from the prologue kernel right before this one; the tile plan, the block table and
+    // the lengths from kernels (or copies) several launches back.  p.early (the caller supplied the plan and the prologue kernel
+    // triggers its dependents only AFTER its own griddepcontrol.wait, so everything older than the prologue is complete when
+    // this grid starts): the producer warp does not wait here -- it fills the ring with tiles the prologue does not touch
+    // (every tile but the last of a sequence) while the prologue runs, and waits before the first tile that holds a new token.
     pdl_launch_dependents();
-    pdl_wait();
+    const bool early = p.early != 0 && warp == kConsumerWarps;
+    if (!early) {
+        pdl_wait();
+    }
 
     const int       Hkv   = p.num_kv_heads;
     const int       G     = p.num_heads / Hkv;
@@ -799,14 +807,21 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
     const long long lo    = total * blockIdx.x / gridDim.x;
     const long long hi    = total * (blockIdx.x + 1) / gridDim.x;
 
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&ss.full[s]), 1);
-            mbar_init(smem_u32(&ss.empty[s]), kConsumerWarps);
+    // the producer warp owns the ring's barriers: it initialises them and ARRIVES on named barrier 3; the consumers sync on it
+    if (warp == kConsumerWarps) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(smem_u32(&ss.full[s]), 1);
+                mbar_init(smem_u32(&ss.empty[s]), kConsumerWarps);
+            }
+            fence_mbar_init();
         }
-        fence_mbar_init();
+        __syncwarp();
+        named_bar_arrive(3, kThreads);
     }
-    __syncthreads();
+    else {
+        named_bar_sync(3, kThreads);
+    }
 
     if (lo >= hi) {
         return;
@@ -832,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
                 it.seek(idx);
                 const int k_len = p.cu_k_len[it.b + 1] - p.cu_k_len[it.b];
                 const int t0    = it.tile * kTile;
-                d.rows          = min(kTile, k_len - t0);
+                d.rows          = min(kTile, k_len - t0) | (t0 + kTile >= k_len ? 128 : 0);  // bit 7: holds the new token
                 d.h             = it.h;
                 d.bt            = t0 % p.block_len;
                 d.blk           = p.block_ptrs[p.cu_block_nums[it.b] + t0 / p.block_len] + p.layer_offset;
@@ -841,6 +856,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
         };
         int      s  = 0;
         uint32_t ph = 0;
+        bool     pending = early;  // griddepcontrol.wait still to come
+        int      issued  = 0;
         TileDesc cur = fetch(lo);
         // Copy roles: lanes 0-7 move the four 16-row groups of K (even) and V (odd), lanes 8/9 the K/V quant params.
         // The ten copies of one tile are issued by ten lanes in ONE pass (a single lane issuing them serially costs
@@ -855,7 +872,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas_per_sm<KVBITS>()) decode_at
             for (int l = 0; l < cnt; ++l) {
                 const unsigned long long blk = __shfl_sync(0xffffffffu, (unsigned long long)cur.blk, l);
                 const int packed = __shfl_sync(0xffffffffu, cur.h | (cur.bt << 8) | (cur.rows << 24), l);
-                const int h = packed & 0xff, bt = (packed >> 8) & 0xffff, rows = packed >> 24;
+                const int h = packed & 0xff, bt = (packed >> 8) & 0xffff, rows = (packed >> 24) & 127;
+                if (pending && (((packed >> 31) & 1) || issued == STAGES)) {
+                    pdl_wait();  // warp-uniform: the prologue's stores (new token's K / V, their params) are visible from here
+                    pending = false;
+                }
+                ++issued;
                 const uint32_t bar = full0 + 8 * s;
                 if (lane == 0) {
                     mbar_wait(empty0 + 8 * s, ph ^ 1);

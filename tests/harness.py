@@ -146,13 +146,19 @@ class PagedCase:
         p.stream = torch.cuda.current_stream().cuda_stream
         return p
 
-    def run_device(self, finished=None, debug_flags=0):
+    def run_device(self, finished=None, debug_flags=0, external_plan=False):
         from lmdeploy_b200 import _lib as L
         torch = torch_mod()
         lib = L.load()
         self.upload()
         p = self.params(lib, finished)
         p.debug_flags = debug_flags
+        if external_plan:
+            # the caller's plan (as b200_model_decode_step passes one per step): lets the main kernel's producer warp stream
+            # KV tiles before griddepcontrol.wait (KernelParams::early)
+            self.d_plan = torch.zeros(self.B + 1, dtype=torch.int32, device="cuda")
+            L.check(lib.b200_decode_attention_plan(self.d_plan.data_ptr(), p.cu_k_len, p.finished, self.B, p.stream), "plan")
+            p.plan = self.d_plan.data_ptr()
         L.check(lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")
         torch.cuda.synchronize()
         return from_dev_T(self.d_out, self.dtype), self.d_pool.cpu().numpy()

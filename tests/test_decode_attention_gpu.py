@@ -234,3 +234,18 @@ def test_partials_of_an_earlier_call_do_not_leak_into_a_sparse_one(flags):
     out = from_dev_T(small.d_out, F16)
     ref = small.run_oracle()
     assert np.isfinite(out).all() and np.abs(out - ref).max() <= 2e-3, float(np.abs(out - ref).max())
+
+
+@pytest.mark.parametrize("kv_bits", [8, 4, 16])
+def test_early_kv_streaming_with_a_caller_plan_is_bit_identical(kv_bits):
+    """With the caller's plan the producer warp starts copying KV tiles before griddepcontrol.wait and waits only before the
+    first tile that holds a new token (written by the prologue kernel); outputs and pages must equal the plain call's bit for
+    bit -- histories chosen so that CTAs start on first, middle and last tiles, and on sequences of one tile."""
+    hist = [0, 1, 63, 64, 65, 127, 128, 700, 2047, 2048, 3000, 5]
+    a = PagedCase(batch_hist=hist, num_heads=8, num_kv_heads=2, kv_bits=kv_bits, seed=21)
+    out_a, pool_a = a.run_device()
+    b = PagedCase(batch_hist=hist, num_heads=8, num_kv_heads=2, kv_bits=kv_bits, seed=21)
+    for _ in range(3):                       # repeated: a race with the prologue would not show every time
+        out_b, pool_b = b.run_device(external_plan=True)
+        assert (pool_a == pool_b).all()
+        assert (out_a == out_b).all()
