@@ -23,7 +23,9 @@ class TpGroup:
         self.nvls = False
         # NVLS (B200_TP_NVLS=1, or =auto: used when the fabric offers it): the exchange buffers come from torch's symmetric
         # memory, whose rendezvous also yields a MULTICAST address; the fused all-reduce then reduces inside the NVSwitch.
-        want = os.environ.get("B200_TP_NVLS", "0")
+        # Default: "auto" from 4 ranks up (measured on B200s, profiles/r02_scale.md: C2 at TP 4 2.70 ms with NVLS vs 2.75 ms with
+        # peer loads, the fused exchange alone 8.0 vs 8.5 us; at TP 2 peer loads win, 6.9 vs 7.6 us).
+        want = os.environ.get("B200_TP_NVLS", "auto" if world >= 4 else "0")
         if want not in ("", "0") and world > 1:
             try:
                 self._init_symmetric(model, rank, world, nbytes, fbytes, group)
