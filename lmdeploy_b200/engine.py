@@ -127,6 +127,12 @@ class StaticBatchRunner:
         # main-kernel-only timing uses the round-1 three-kernel form (debug bit 2) with prologue and fix-up skipped (bits 0, 1):
         # one unfused full call first leaves the rotated q it reads; full=True times the op as callers get it (one fused kernel)
         p.debug_flags = 0 if full else 4
+        if full:
+            # as a decode step calls the operator: with the step's tile plan computed once up front (b200_model_decode_step),
+            # which also lets the main kernel's producer warp stream KV tiles while the prologue kernel runs
+            plan = torch.zeros(self.batch + 1, dtype=torch.int32, device=dev)
+            L.check(m.lib.b200_decode_attention_plan(plan.data_ptr(), cu_k.data_ptr(), None, self.batch, p.stream), "plan")
+            p.plan = plan.data_ptr()
         L.check(m.lib.b200_decode_attention(C.byref(p)), "b200_decode_attention")     # full call once
         p.debug_flags = 0 if full else 7
         # rotate over layers so successive launches never hit L2-resident pages (each layer is >> L2 anyway)
@@ -145,5 +151,5 @@ class StaticBatchRunner:
         us = e0.elapsed_time(e1) * 1e3 / iters
         q_bits = 16 if m.quant_policy == 0 else m.quant_policy
         nbytes = self.batch * k_len * 2 * m.kv_heads * (D * q_bits // 8 + (4 if m.quant_policy else 0))
-        self._attn_params = (p, qkv, out, ws, cu_k)   # kept alive: bench.py times the reference kernel on the same buffers
+        self._attn_params = (p, qkv, out, ws, cu_k, plan if full else None)   # kept alive: bench.py times the reference kernel on the same buffers
         return dict(us=us, bytes=nbytes, gbs=nbytes / (us * 1e-6) / 1e9)

@@ -86,8 +86,35 @@ def test_static_batch_runner_bench_loop(dry):
     assert r.cur_len == 101 + 1 + 3
     out = r.step_host(np.array([1, 2, 3, 4], np.int32))
     assert out.shape == (4,) and dry.names()[-1] == "graph.replay"
-    t = r.time_attention_kernel(150, iters=2) if hasattr(torch.cuda, "Event") and False else None
-    assert t is None
+    # bench.py's roofline block: the main kernel alone, then the whole operator WITH the step's plan (as a decode step calls it)
+    class FakeEvent:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+    import pytest
+    mp = pytest.MonkeyPatch()
+    mp.setattr(torch.cuda, "Event", FakeEvent)
+    try:
+        n1 = len(dry.calls)
+        t = r.time_attention_kernel(150, iters=2)
+        assert t["bytes"] > 0 and "b200_decode_attention_plan" not in dry.names()[n1:]
+        calls = [c for c in dry.calls[n1:] if c[0] == "b200_decode_attention"]      # the recorded struct is the live one
+        assert len(calls) == 1 + 3 + 2 and calls[-1][1][0]._obj.debug_flags == 7 and not calls[-1][1][0]._obj.plan
+        n2 = len(dry.calls)
+        t = r.time_attention_kernel(150, iters=2, full=True)
+        names = dry.names()[n2:]
+        assert names.count("b200_decode_attention_plan") == 1 and names.count("b200_decode_attention") == 1 + 3 + 2
+        assert names.index("b200_decode_attention_plan") < names.index("b200_decode_attention")
+        calls = [c for c in dry.calls[n2:] if c[0] == "b200_decode_attention"]
+        assert calls[-1][1][0]._obj.debug_flags == 0 and calls[-1][1][0]._obj.plan
+        assert r._attn_params[5] is not None
+    finally:
+        mp.undo()
     sb = m.step_bytes(4, 150)
     assert sb["total"] == sum(v for k, v in sb.items() if k != "total") and sb["kv_read"] > 0
     assert r.launches_per_step == 4 + 9 * 2 + 4
