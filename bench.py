@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
 # capture (profiles/): filled per config once measured
-TRAFFIC_NCU = {"c2": 282659584}   # profiles/r01b_attention_ncu.md
+TRAFFIC_NCU = {"c2": 278094848 + 5309696}   # profiles/r02_attention_ncu.md (r02_attn.ncu-rep): dram read + write per launch
 
 CONFIGS = {
     # name: (spec, batch, ctx, kv quant policy)
@@ -222,7 +222,11 @@ def run_reference(args):
     r = cpu_baseline.time_decode(spec, batch, ctx, layers_sample=1, reps=reps, threads=cores)
     line = {
         "impl": "reference", "metric": "decode tokens/sec", "value": r["tokens_per_s"], "unit": "tokens/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["t_step"] * 1e3,
+        # `steps` / `warmup` / `ms_per_step` = what actually ran: each "step" of this arm is the bounded sample named in
+        # cpu_baseline.sample (one decoder layer + lm_head); `value` extrapolates it to the whole model
+        "n_gpus": args.gpus, "steps": reps, "warmup": max(0, min(args.warmup, 1)), "steps_requested": args.steps,
+        "warmup_requested": args.warmup, "ms_per_step": (r["t_layer"] + r["t_head"]) * 1e3,
+        "ms_per_full_step_extrapolated": r["t_step"] * 1e3,   # what `value` is computed from: layers x t_layer + t_head
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{name} {WEIGHT_LABEL.get(spec.weight_format, spec.weight_format)}+"
                                f"{'KV-int%d' % qp if qp else 'KV-fp16'} decode bs={batch} ctx={ctx} (CPU port of the path)"},
@@ -397,7 +401,7 @@ def run_b200(args):
     step_gbs = sb["total"] / (ms_per_step * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "decode_attention_kernel", "achieved": attn["gbs"], "peak": peak, "unit": "GB/s",
-        "frac": attn["gbs"] / peak, "traffic": TRAFFIC_NCU.get(args.config), "peak_source": peak_src,
+        "frac": attn["gbs"] / peak, "traffic": TRAFFIC_NCU.get(args.config), "traffic_source": "ncu --set full capture of this kernel, profiles/r02_attention_ncu.md (not re-measured in this run)", "peak_source": peak_src,
         "bytes_per_launch": attn["bytes"], "us_per_launch": attn["us"],
         # the whole operator (prologue + main kernel + fix-up), what a caller of b200_decode_attention pays
         "full_op": {"us_per_call": attn_full["us"], "achieved": attn_full["gbs"], "frac": attn_full["gbs"] / peak},

@@ -19,6 +19,9 @@ def test_reference_arm_prints_the_contract_line():
     assert d["impl"] == "reference" and d["metric"] == "decode tokens/sec" and d["unit"] == "tokens/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    # steps / ms_per_step describe what ran (one sampled layer + head per step); value comes from the extrapolated whole step
+    assert d["steps_requested"] == 1 and d["ms_per_full_step_extrapolated"] >= d["ms_per_step"]
+    assert abs(d["value"] - 1 / (d["ms_per_full_step_extrapolated"] * 1e-3)) < 1e-6 * d["value"]        # c1-tiny: bs = 1
     assert d["config"]["workload"].startswith("internlm2-1.8b fp16")
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
