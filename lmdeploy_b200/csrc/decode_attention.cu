@@ -322,18 +322,18 @@ static int main_grid()
     constexpr int STAGES = stages_for<KVBITS>();
     using SS             = SharedStorage<T, KVBITS, STAGES>;
     auto       kern      = decode_attention_kernel<T, KVBITS, STAGES>;
-    static int grid      = 0;
-    static std::once_flag once;
-    // NOTE: per (T, KVBITS) instantiation; single-device-type process assumed (all GPUs identical)
-    std::call_once(once, [&] {
+    static PerDevice grids{};  // per (T, KVBITS) instantiation and per device
+    const int        dev = current_device();
+    int              grid = grids.value[dev].load(std::memory_order_acquire);
+    if (grid == 0) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SS));
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, sizeof(SS));
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
+        int sms = 0;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        grid = std::max(1, occ) * sms;
-    });
+        grid = std::max(1, occ) * std::max(1, sms);
+        grids.value[dev].store(grid, std::memory_order_release);
+    }
     return grid;
 }
 

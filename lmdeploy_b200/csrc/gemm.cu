@@ -361,13 +361,14 @@ template<class T, int FMT, int TILES>
 static int launch(const Params& p, int smem, cudaStream_t st)
 {
     auto        kern       = gemm_kernel<T, FMT, TILES>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice configured{};  // per instantiation and per device
+    const int        dev = current_device();
+    if (configured.value[dev].load(std::memory_order_acquire) == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
         if (e != cudaSuccess) {
             return fail_cuda(e, "cudaFuncSetAttribute(gemm_kernel)");
         }
-        configured = true;
+        configured.value[dev].store(1, std::memory_order_release);
     }
     if (smem > 227 * 1024 - 2048) {
         return fail(B200_ERR_UNSUPPORTED, "gemm: shared memory budget exceeded");

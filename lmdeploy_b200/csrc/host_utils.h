@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <utility>
 #include <string>
 
@@ -55,6 +56,21 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     cfg.attrs                                          = attr;
     cfg.numAttrs                                       = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+// One-time, PER-DEVICE set-up at a call site (kernel attributes such as the dynamic shared-memory limit belong to the device's
+// context: a process that drives several GPUs from several threads -- the reference's engine -- must repeat them on each).
+// `slot` is a static of the call site; returns the current device, and true in *first for the first caller on that device
+// (a concurrent second caller may also see true: the set-up calls are idempotent).
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    std::atomic<int> value[kMaxDevices];   // 0 = not configured yet on that device
+};
+inline int current_device()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < kMaxDevices ? dev : 0;
 }
 
 #define B200_CUDA_TRY(expr)                                                                                            \
