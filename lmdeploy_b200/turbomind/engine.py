@@ -26,22 +26,26 @@ def marshal_step(batch, block_ptr=None):
     q = k = max_k = 0
     for s in batch:
         n = s.step_tokens
-        if n == 1 and s.cached < s.context_len:      # steady decode: one row, the token at position `cached`
-            tokens.append(int(s.token_at(s.cached)))
+        cached = s.cached
+        prompt = s.prompt
+        if n == 1 and cached < len(prompt) + len(s.generated):      # steady decode: one row, the token at position `cached`
+            tokens.append(int(prompt[cached] if cached < len(prompt) else s.generated[cached - len(prompt)]))
         else:
             toks = s.next_inputs()
             if len(toks) != n:
                 raise RuntimeError(f"session {s.session_id}: scheduled {n} tokens but {len(toks)} are available")
             tokens += [int(t) for t in toks]
-        if not s.blocks:
+        blocks = s.blocks
+        if not blocks:
             raise RuntimeError(f"session {s.session_id} runs without KV blocks")
         q += n
-        k += s.cached + n
-        if s.cached + n > max_k:
-            max_k = s.cached + n
+        end = cached + n
+        k += end
+        if end > max_k:
+            max_k = end
         cu_q.append(q)
         cu_k.append(k)
-        ids += s.blocks
+        ids += blocks
         cu_blocks.append(len(ids))
     st = dict(batch_size=len(batch), token_ids=tokens, token_num=len(tokens), cu_q_len=cu_q, cu_k_len=cu_k, block_ids=ids,
               cu_block_nums=cu_blocks, max_k_len=max_k)

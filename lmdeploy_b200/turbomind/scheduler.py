@@ -222,6 +222,8 @@ class Scheduler:
 
     def _retire(self):
         """Give back the blocks and the session slot of every finished active sequence."""
+        if not any(s.finished for s in self.active):       # the common tick: nothing to give back
+            return
         still = []
         for s in self.active:
             if s.finished:
@@ -254,10 +256,15 @@ class Scheduler:
         # src/turbomind/models/llama/SequenceManager.cc; there is no host swap on this path).  Published prefix blocks
         # stay in the cache index, so with prefix caching a resumed sequence usually finds most of itself again.
         preempted = False
+        bl = self.block_len
         for s in list(self.active):
-            if s not in self.active or s.finished:
+            if s.finished:
                 continue
-            need = self._blocks_needed(s, s.cached + 1)
+            need = (s.cached + bl) // bl - len(s.blocks)          # == _blocks_needed(s, s.cached + 1)
+            if need <= 0:
+                continue                   # the common case, decided without the O(n) membership test below
+            if s not in self.active:       # preempted earlier in this loop (its blocks are gone, so need > 0 brought us here)
+                continue
             while need > 0:
                 got = self.alloc.allocate(need)
                 if got is not None:
@@ -307,10 +314,13 @@ class Scheduler:
             self.active.append(s)
         batch = [s for s in self.active if not s.finished]
         budget = self.token_budget - len(batch)
+        chunked = self.prefill_chunk > 1
         for s in batch:
             s.step_tokens = 1
-            rem = s.context_len - s.cached         # tokens still to feed, the one that produces the next logits included
-            if self.prefill_chunk > 1 and rem > 1 and budget > 0:
+            if not chunked:
+                continue
+            rem = len(s.prompt) + len(s.generated) - s.cached   # tokens still to feed, the one that produces the next logits included
+            if rem > 1 and budget > 0:
                 extra = min(self.prefill_chunk - 1, rem - 1, budget)
                 need = self._blocks_needed(s, s.cached + 1 + extra)
                 got = self.alloc.allocate(need) if need > 0 else []
@@ -325,33 +335,36 @@ class Scheduler:
         """Account for one executed step: every sequence cached its `step_tokens` tokens; `sampled[i]` is the token
         sampled from the LAST row of sequence i, emitted once the sequence is past its prompt."""
         events = []
+        prefix, bl, session_len = self.prefix, self.block_len, self.session_len
         for s, tok in zip(batch, sampled):
             n = s.step_tokens
             before = s.cached
-            s.cached += n
-            s.fed = min(len(s.prompt), s.fed + n)
+            cached = s.cached = before + n
+            plen = len(s.prompt)
+            s.fed = min(plen, s.fed + n)
             s.step_tokens = 1
-            if self.prefix is not None:
-                for j in range(before // self.block_len, s.cached // self.block_len):       # blocks that just filled
+            if prefix is not None:
+                for j in range(before // bl, cached // bl):       # blocks that just filled
                     if len(s.chain) == j:
-                        toks = [s.token_at(p) for p in range(j * self.block_len, (j + 1) * self.block_len)]
-                        s.chain.append(self.prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
-            if s.cached < s.context_len:
+                        toks = [s.token_at(p) for p in range(j * bl, (j + 1) * bl)]
+                        s.chain.append(prefix.publish(s.chain[-1] if s.chain else PrefixCache.ROOT, toks, s.blocks[j]))
+            gen = s.generated
+            if cached < plen + len(gen):
                 continue                   # still filling the cache (prompt, or refill after a preemption): sample discarded
             if s.max_new_tokens == 0:
                 s.finished, s.finish_reason = True, "length"
                 events.append((s, None))
                 continue
-            s.generated.append(int(tok))
+            tok = int(tok)
+            gen.append(tok)
             # ignore_eos switches off EVERY stop id, user stop words included: the reference only hands stop_ids to its
             # engine when ignore_eos is off (lmdeploy/turbomind/turbomind.py `_get_generation_config`); the stop token
             # itself is appended to the sequence, the pipeline layer hides it from the response
-            stop = not s.ignore_eos and ((s.eos_id is not None and tok == s.eos_id) or tok in s.stop_token_ids)
-            if stop:
+            if not s.ignore_eos and ((s.eos_id is not None and tok == s.eos_id) or tok in s.stop_token_ids):
                 s.finished, s.finish_reason = True, "stop"
-            elif len(s.generated) >= s.max_new_tokens or s.cached + 1 > self.session_len:
+            elif len(gen) >= s.max_new_tokens or cached + 1 > session_len:
                 s.finished, s.finish_reason = True, "length"
-            events.append((s, int(tok)))
+            events.append((s, tok))
         self._retire()                     # an idle engine holds no blocks of finished requests
         return events
 
