@@ -400,3 +400,36 @@ def test_do_sample_requests_go_through_the_device_sampling_stage(dry, monkeypatc
     p = [args for n, args in dry.calls if n == "b200_sample"][0][0]._obj
     assert p.count == 1 and p.vocab == 1000 and p.ld == model.vocab_local and p.repetition_penalty and p.history
     assert a.rng_slot >= 0 and len(a.generated) == 3 and len(b.generated) == 3
+
+
+def test_tp_group_picks_the_exchange_by_world_size(dry, monkeypatch):
+    """TpGroup: CUDA-IPC peer loads below 4 ranks, NVLS (torch symmetric memory + multicast) from 4 ranks up with a silent
+    fall-back to peer loads when the fabric offers none, B200_TP_NVLS=1 insists, =0 forbids (measured: profiles/r02_scale.md)."""
+    import types
+    import warnings
+    import torch.distributed as dist
+    from lmdeploy_b200.turbomind import tp as TP
+    monkeypatch.setattr(dist, "all_gather_object", lambda out, obj, group=None: out.__setitem__(slice(None), [obj] * len(out)))
+    monkeypatch.setattr(dist, "barrier", lambda group=None: None)
+    tried = []
+
+    def no_multicast(self, model, rank, world, nbytes, fbytes, group):
+        tried.append(world)
+        raise RuntimeError("no multicast on this fabric")
+    monkeypatch.setattr(TP.TpGroup, "_init_symmetric", no_multicast)
+    model = types.SimpleNamespace(spec=types.SimpleNamespace(hidden=256), max_batch=8, vocab_local=128,
+                                  device=torch.device("cpu"), set_comm=lambda h: None)
+    monkeypatch.delenv("B200_TP_NVLS", raising=False)
+    g = TP.TpGroup(model, 0, 2)
+    assert tried == [] and not g.nvls and "b200_comm_create" in dry.names()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        g = TP.TpGroup(model, 1, 4)
+    assert tried == [4] and not g.nvls and any("NVLS exchange unavailable" in str(x.message) for x in w)
+    monkeypatch.setenv("B200_TP_NVLS", "0")
+    TP.TpGroup(model, 0, 8)
+    assert tried == [4]
+    monkeypatch.setenv("B200_TP_NVLS", "1")
+    import pytest
+    with pytest.raises(RuntimeError, match="no multicast"):
+        TP.TpGroup(model, 0, 2)
