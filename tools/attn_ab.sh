@@ -1,6 +1,8 @@
 #!/bin/bash
 # A/B of decode attention variants (1 GPU): HEAD build, post-scaling with exact-int operands, post-scaling with fp16-subnormal
-# operands, each with L2 prefetch off / 3 / 6.
+# operands, each with L2 prefetch off / 3 / 6.  The variant libraries (libb200tm_head.so, libb200tm_exactint.so) were one-off builds
+# of decode_attention.cu linked against the other objects (nvcc ... -DB200_RAW_DENORMAL=0), loaded through B200_LIB_PATH; the
+# experiment's outcome is in profiles/r02_attention_variants.md and the variants are not kept in the tree.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
